@@ -1,0 +1,223 @@
+/* tpp_b200.h — C-ABI of the B200-native PPO rollout-and-update hot path.
+ *
+ * One shared library (train-procgen-pytorch_b200/csrc/libtpp_b200.so, built by nvcc for sm_100a only).
+ * Every entry point takes plain device pointers + sizes + a cudaStream_t passed as void*, launches
+ * asynchronously on that stream, never allocates or frees, keeps no hidden global state, and returns 0 or a
+ * cudaError_t / TPP_E* code (never throws).  The caller (PyTorch on the Python side, ctypes binding in
+ * train-procgen-pytorch_b200/_lib.py) owns every buffer.
+ *
+ * The reference (tbuckworth/train-procgen-pytorch) is pure Python; it has no FFI.  Each entry point therefore
+ * cites the reference *function* it replaces (path:line under the reference root).
+ *
+ * Layouts:
+ *   vector observations  : feature-major ("SoA") float32  obs[T+1][n_obs][ld]   (ld >= N envs, ld % 4 == 0)
+ *   image observations   : uint8 NHWC                     frame[T+1][N][H][W][3]
+ *   per-step scalars     : [T][N] row-major (act int32, logp/rew/value/adv/ret float32, done uint8)
+ */
+#ifndef TPP_B200_H
+#define TPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPP_OK 0
+#define TPP_EINVAL 10001   /* bad argument (null pointer, size, alignment)            */
+#define TPP_ENOTSUP 10002  /* shape/config outside what the kernel was built for      */
+
+/* ---- library / device -------------------------------------------------------------------------------- */
+int tpp_version(void);                       /* ABI version, bumped on any signature change             */
+int tpp_device_sm_count(int* out_sm_count);  /* multiProcessorCount of the current device               */
+const char* tpp_error_string(int code);
+
+/* ---- pre-vectorised env families --------------------------------------------------------------------- */
+enum { TPP_CARTPOLE = 0, TPP_CARTPOLE_SWING = 1, TPP_MOUNTAIN_CAR = 2, TPP_ACROBOT = 3, TPP_LUNAR_LANDER = 4 };
+
+/* Static description of one env family instance (replaces the ctor kwargs of the reference classes:
+ * discrete_env/cartpole_pre_vec.py:92-109, cartpole_swing_pre_vec.py:91-106, mountain_car_pre_vec.py:107-126,
+ * acrobot_pre_vec.py:164-180).  `p[]` meaning per family:
+ *   cartpole        p0 x_threshold, p1 theta_threshold_radians, p2 tau
+ *   cartpole_swing  p0 x_threshold, p2 tau
+ *   mountain_car    p0 force, p1 max_speed, p2 left_boundary, p3 goal_velocity, p4 sparse_rewards(0/1)
+ *   acrobot         p0 max_vel_1, p1 max_vel_2, p2 dt
+ *   lunar_lander    see DESIGN.md (own semantics; the reference has no implementation)                  */
+typedef struct {
+  int32_t family;
+  int32_t n_envs;          /* N                                                                        */
+  int32_t max_steps;       /* truncation horizon (pre_vec_env.py:84-86)                                */
+  int32_t n_state;         /* columns of the start space: 9 / 9 / 5 / 12 / 8                           */
+  uint64_t seed;           /* Philox4x32-10 key                                                        */
+  float start_low[16];     /* StartSpace low/high per state column (helper_pre_vec.py:4-12)            */
+  float start_high[16];
+  float p[8];
+} tpp_env_cfg;
+
+/* Fused transition + step counter + truncation + auto-reset + obs/reward/done emit for one step of N envs.
+ * Replaces PreVecEnv.step + set (discrete_env/pre_vec_env.py:78-93,108-119) and the family's
+ * transition_model.  obs_in / obs_out are rollout slots t and t+1 (feature-major, column stride ld).
+ * For families whose observation IS the state (cartpole, swing, mountain car) the state lives only in the
+ * slots; acrobot additionally updates dyn_state[4][ld] (theta1, theta2, dtheta1, dtheta2) in place.
+ * done_out holds the PRE-reset flag, obs_out the POST-reset observation (reference semantics).
+ * reset_rows: NULL -> start states drawn in-kernel from Philox(seed, env, tick); otherwise feature-major
+ * [n_state][ld] rows used for the finished envs (teacher forcing for parity tests).
+ * tick: device counter mixed into the Philox counter (may be NULL -> 0); t_offset is added to it.
+ * ep_ret/ep_len (nullable): device-side episode accounting (running return / length per env);
+ * fin_ret/fin_len (nullable, [N]): return/length of the episode that finished at this step, else NaN/-1.  */
+int tpp_env_step(const tpp_env_cfg* cfg, const float* obs_in, float* obs_out, float* dyn_state,
+                 const int32_t* action, int32_t* step_ctr, float* rew_out, uint8_t* done_out,
+                 const float* reset_rows, const uint64_t* tick, uint64_t t_offset, int64_t ld, void* stream);
+
+/* Full reset of all N envs into obs_out (+ dyn_state) and step_ctr = 0.
+ * Replaces PreVecEnv.reset (discrete_env/pre_vec_env.py:98-106).                                         */
+int tpp_env_reset(const tpp_env_cfg* cfg, float* obs_out, float* dyn_state, int32_t* step_ctr,
+                  const float* reset_rows, const uint64_t* tick, uint64_t t_offset, int64_t ld, void* stream);
+
+/* tick[0] += delta (one thread).  Lets a captured CUDA graph advance the RNG stream between replays.     */
+int tpp_tick_advance(uint64_t* tick, uint64_t delta, void* stream);
+
+/* ---- Box-World ----------------------------------------------------------------------------------------- */
+/* Device-resident state of N Box-World envs (replaces the numpy members of BoxWorldVec,
+ * boxworld/box_world_env_vec.py:24-60).  cells = (n+2)*(n+2).                                            */
+typedef struct {
+  int32_t n_envs, n;             /* grid side n (frames are (n+2) x (n+2) x 3)                            */
+  int32_t max_steps;
+  int32_t n_levels;              /* >0: levels cycle through a bank of n_levels; 0: unbounded (streamed)  */
+  int64_t start_seed;
+  int32_t goal_length, num_distractor, distractor_length, _pad;
+  uint8_t* world;                /* [N][n+2][n+2][3]                                                      */
+  int8_t* world_dic;             /* [N][n+2][n+2]  -1 / 0 / 1   (lock status)                            */
+  int32_t* player_pos;           /* [N][2]                                                                */
+  uint8_t* owned_key;            /* [N][4]  (rgb + pad)                                                   */
+  int32_t* num_env_steps;        /* [N]                                                                   */
+  int32_t* episode_reward;       /* [N]                                                                   */
+  int64_t* seed_counter;         /* [1] next level seed (box_world_env_vec.py:294-297)                    */
+  const uint8_t* bank_world;     /* [n_levels][cells][3]   (NULL when n_levels == 0)                      */
+  const int8_t* bank_dic;        /* [n_levels][cells]                                                     */
+  const int32_t* bank_pos;       /* [n_levels][2]                                                         */
+  int32_t* scratch;              /* [N + 1024] per-CTA done counts + scan workspace                       */
+} tpp_boxworld_state;
+
+/* One step of all envs: grid transition, rewards, done, level replacement in env-index order with the
+ * sequential seed counter, and emit of the post-reset frame into frame_out (rollout slot t+1, uint8 NHWC).
+ * Replaces BoxWorldVec.step (boxworld/box_world_env_vec.py:70-209).
+ * reward_out int32 [N] (raw env reward), done_out uint8 [N]; fin_ret/fin_len/fin_solved nullable [N].     */
+int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* action, int32_t* reward_out,
+                      uint8_t* done_out, uint8_t* frame_out, int32_t* fin_ret, int32_t* fin_len,
+                      uint8_t* fin_solved, void* stream);
+
+/* Host-side level generator (MT19937 + CPython random.sample/choices semantics), `count` consecutive seeds
+ * starting at seed0.  Replaces world_gen / sampling_pairs (boxworld/boxworld_gen_vec.py:4-97).
+ * Outputs are HOST buffers: world [count][cells][3], dic [count][cells], pos [count][2].                  */
+int tpp_boxworld_gen_levels_host(int32_t n, int32_t goal_length, int32_t num_distractor,
+                                 int32_t distractor_length, int64_t seed0, int32_t count, uint8_t* world,
+                                 int8_t* dic, int32_t* pos);
+
+/* Same generator on the device, one level per thread, writing straight into env slots `env_ids[i]`
+ * (or slots 0..count-1 when env_ids is NULL) of a tpp_boxworld_state; seeds[i] per level.                */
+int tpp_boxworld_gen_levels_device(const tpp_boxworld_state* st, const int32_t* env_ids, const int64_t* seeds,
+                                   int32_t count, void* stream);
+
+/* Copy frames of all envs into a rollout slot (used after reset()).                                      */
+int tpp_boxworld_emit_frames(const tpp_boxworld_state* st, uint8_t* frame_out, void* stream);
+
+/* Return-based reward normalisation for N envs, one step.  Replaces VecNormalize.step_wait +
+ * RunningMeanStd.update (common/env/procgen_wrappers.py:282-342, ob=False).
+ * ret [N] f64 running discounted return; rms [3] f64 = (mean, var, count); raw_rew int32 or float32
+ * (raw_is_int); out_rew f32 [N] normalised+clipped; done u8 [N].  n_envs <= 65536 (single CTA pass).      */
+int tpp_vecnormalize_step(double* ret, double* rms, const void* raw_rew, int raw_is_int, const uint8_t* done,
+                          float* out_rew, int32_t n_envs, double gamma, double cliprew, double epsilon,
+                          void* stream);
+
+/* ---- rollout storage ----------------------------------------------------------------------------------- */
+/* GAE(gamma, lambda) reverse scan with done-masking + returns + global first/second moments.
+ * Replaces the loop of Storage.compute_estimates (common/storage.py:56-77).
+ * rew,done: [T][ld]; value: [T+1][ld]; adv,ret: [T][ld]; moments: double[3] = (sum, sum of squares, count),
+ * ACCUMULATED into (caller zeroes).  Arithmetic order equals the reference's fp32 ops (bit-exact raw adv). */
+int tpp_gae(const float* rew, const uint8_t* done, const float* value, float* adv, float* ret,
+            double* moments, int32_t T, int32_t N, int64_t ld, float gamma, float lambda, void* stream);
+
+/* adv <- (adv - mean) / (std_unbiased + 1e-8) with the moments from tpp_gae (after an optional cross-rank
+ * all-reduce of the three doubles).  Replaces common/storage.py:78-79.                                   */
+int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream);
+
+/* Minibatch gather from the resident rollout by flat sample index k = t*N + e (common/storage.py:112-128).
+ * Vector observations: obs feature-major [T+1][n_obs][ld] -> out_obs row-major [mb][ld_out] (cols >= n_obs
+ * zero-filled).  out_* arrays are [mb].  idx: int64 [mb] (from torch.randperm on the host: bit-exact).    */
+int tpp_gather_vec(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t n_obs, const float* obs,
+                   const int32_t* act, const float* logp, const float* value, const float* ret,
+                   const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out, int32_t* out_act,
+                   float* out_logp, float* out_value, float* out_ret, float* out_adv, float* out_done,
+                   void* stream);
+
+/* Image observations: frames uint8 NHWC [T+1][N][H][W][C] -> out_obs float32 NCHW [mb][C][H][W] / 255
+ * (TransposeFrame + ScaledFloatFrame, common/env/procgen_wrappers.py:391-419, applied at gather time).    */
+int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int32_t H, int32_t W, int32_t C,
+                   const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
+                   const float* ret, const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out,
+                   int32_t* out_act, float* out_logp, float* out_value, float* out_ret, float* out_adv,
+                   float* out_done, void* stream);
+
+/* uint8 NHWC frames of one rollout slot -> float32 NCHW/255 rows [N][ld_out] (policy input at rollout).   */
+int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
+                      int32_t ld_out, void* stream);
+
+/* ---- policy: dense layers ------------------------------------------------------------------------------ */
+/* C[m][n] (+)= epilogue( sum_k A(m,k) * B(n,k) ), fp32 in / fp32 accumulate, generic strides:
+ *   A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk],  C(m,n) = C[m*ldc + n].
+ * flags: TPP_EPI_BIAS (add bias[n]), TPP_EPI_RELU, TPP_EPI_MASK (multiply by mask(m,n) > 0, mask ld = ldc),
+ *        TPP_EPI_ACCUM (C += result; with split_k > 1 partial sums are combined with atomics).
+ * This one entry serves nn.Linear forward (common/model.py:962-967), its data gradient and its weight
+ * gradient (autograd of agents/ppo.py:170).  CUDA-core exact-fp32 path; the tensor-core path is below.    */
+enum { TPP_EPI_BIAS = 1, TPP_EPI_RELU = 2, TPP_EPI_MASK = 4, TPP_EPI_ACCUM = 8 };
+int tpp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
+                 int64_t ldc, const float* bias, const float* mask, int32_t M, int32_t N, int32_t K,
+                 int32_t flags, int32_t split_k, void* stream);
+
+/* out[n] += sum_m dZ[m*ld + n]   (bias gradient).                                                        */
+int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t N, float* out, void* stream);
+
+/* ---- policy: action sampling at rollout --------------------------------------------------------------- */
+/* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.
+ * Replaces dist.sample()/log_prob in PPO.predict (agents/ppo.py:72-81, common/policy.py:74-87).
+ * Philox(seed, env, tick + t_offset); greedy != 0 -> argmax.                                             */
+int tpp_sample_actions(const float* head, int32_t ld_head, int32_t n_envs, int32_t n_actions, int32_t* act,
+                       float* logp, float* value, uint64_t seed, const uint64_t* tick, uint64_t t_offset,
+                       int32_t greedy, void* stream);
+
+/* ---- PPO loss, fused forward + backward ---------------------------------------------------------------- */
+typedef struct {
+  float eps_clip, value_coef, entropy_coef, entropy_multiplier, x_entropy_coef;
+  int32_t n_actions, mb;
+} tpp_loss_cfg;
+
+/* head [mb][ld_head] = (A logits, value) -> dhead [mb][ld_head] = dLoss/d(logits, value) and raw sums
+ * stats[0..3+A] (double, ACCUMULATED): [0] sum min(s1,s2), [1] sum max(v1,v2), [2] sum entropy_b,
+ * [3] sample count, [4..4+A) sum_b p_b.  pbar (nullable float[A]): batch-mean probabilities, required when
+ * x_entropy_coef != 0 (compute with tpp_ppo_pbar first).
+ * Replaces agents/ppo.py:131-170 + common/misc_util.py:32-51 and their autograd.       */
+int tpp_ppo_loss_fwd_bwd(const tpp_loss_cfg* cfg, const float* head, int32_t ld_head, const int32_t* act,
+                         const float* old_logp, const float* old_value, const float* ret, const float* adv,
+                         const float* pbar, float* dhead, double* stats, void* stream);
+int tpp_ppo_pbar(const float* head, int32_t ld_head, int32_t mb, int32_t n_actions, float* pbar_sum,
+                 void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float lr, beta1, beta2, eps, max_grad_norm, grad_scale; /* grad_scale: 1/world_size after all-reduce    */
+  int32_t step;       /* number of optimizer steps taken so far (device-resident copy is authoritative)   */
+  int32_t _pad;
+  double sqnorm[2];   /* ping-pong accumulators of sum g^2                                                */
+} tpp_adam_state;     /* lives in DEVICE memory; host updates lr with a small memcpy                      */
+
+/* sqnorm[(step)&1] += sum (grad_scale*g)^2 ; thread 0 also bumps state->step.                            */
+int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n, void* stream);
+/* clip_grad_norm_(max_grad_norm) + Adam(lr, betas, eps) + zero grad over flat buffers, one pass.
+ * Replaces agents/ppo.py:173-176 (torch.nn.utils.clip_grad_norm_, optim.Adam(eps=1e-5)).                 */
+int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPP_B200_H */

@@ -1,0 +1,73 @@
+"""CPU: the C-ABI library loads, exports every symbol include/tpp_b200.h declares, validates arguments without
+touching a GPU, and its host-side level generator equals the oracle (no device compute here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle.boxworld import world_gen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tpp_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    header = open(os.path.join(ROOT, "include", "tpp_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(tpp_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 20
+    cdll = lib.load()
+    for name in declared:
+        assert hasattr(cdll, name), f"{name} declared in the header but not exported"
+    assert declared - {"tpp_error_string"} == set(lib.SIGNATURES), "ctypes binding out of sync with the header"
+    assert cdll.tpp_version() == lib.ABI_VERSION
+
+
+def test_struct_sizes_match_the_header(lib):
+    assert ctypes.sizeof(lib.EnvCfg) == 4 * 4 + 8 + 16 * 4 * 2 + 8 * 4
+    assert ctypes.sizeof(lib.BoxWorldState) == 4 * 4 + 8 + 4 * 4 + 11 * 8
+    assert ctypes.sizeof(lib.LossCfg) == 7 * 4
+    assert ctypes.sizeof(lib.AdamState) == 6 * 4 + 2 * 4 + 2 * 8
+
+
+def test_null_and_bad_arguments_are_rejected_without_a_gpu(lib):
+    cdll = lib.load()
+    assert cdll.tpp_gae(None, None, None, None, None, None, 4, 4, 4, 0.99, 0.95, None) == 10001
+    assert cdll.tpp_env_step(None, None, None, None, None, None, None, None, None, None, 0, 0, None) == 10001
+    assert cdll.tpp_gemm_f32(None, 1, 1, None, 1, 1, None, 1, None, None, 1, 1, 1, 0, 1, None) == 10001
+    with pytest.raises(lib.TppError):
+        lib.call("tpp_adam_clip_step", None, None, None, None, None, 0, None)
+    assert b"TPP_EINVAL" in cdll.tpp_error_string(10001)
+
+
+@pytest.mark.parametrize("spec", [(6, 2, 1, 1), (12, 5, 3, 3), (12, 4, 2, 2), (9, 3, 2, 2), (12, 5, 0, 0)])
+def test_host_level_generator_equals_oracle(lib, spec):
+    from tpp_b200.boxworld.box_world_env_vec import generate_levels_host
+    for seed0 in (0, 6033, 2 ** 32 - 3, 2 ** 40 + 1):
+        w, d, p = generate_levels_host(*spec, seed0, 24)
+        for i in range(24):
+            ow, op, od = world_gen(*spec, seed0 + i)
+            assert np.array_equal(w[i], ow) and np.array_equal(p[i], op) and np.array_equal(d[i], od.astype(np.int8))
+
+
+def test_generator_rejects_unsupported_specs(lib):
+    with pytest.raises(lib.TppError):
+        lib.call("tpp_boxworld_gen_levels_host", 40, 2, 1, 1, 0, 1, 1, 1, 1)
+
+
+def test_product_fails_loudly_without_cuda(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from tpp_b200.common.storage import Storage
+    with pytest.raises(lib.TppError):
+        Storage((9,), 4, 8, 8, "cpu")

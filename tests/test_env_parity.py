@@ -1,0 +1,186 @@
+"""GPU: fused env-step kernels (csrc/env_prevec.cu) against the float64 oracle, teacher-forced one step at a time
+(SURVEY 8c protocol): the oracle's pre-step state (rounded to fp32) and the reference's reset rows are injected,
+then post-step state / obs / reward / done are compared.
+
+Tolerance (stated, fp32 vs float64): |a - b| <= ATOL + 1e-5 * |b| with ATOL = 2e-6; done flags must be equal
+unless a threshold quantity lies within 1e-5 of its threshold."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.prevec import OraclePreVec
+
+pytestmark = pytest.mark.gpu
+ATOL, RTOL = 2e-6, 1e-5
+FAMILIES = ["cartpole", "cartpole_swing", "mountain_car", "acrobot"]
+
+
+def _make(family, n, **kw):
+    from tpp_b200.discrete_env.acrobot_pre_vec import AcrobotVecEnv
+    from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    from tpp_b200.discrete_env.cartpole_swing_pre_vec import CartPoleSwingVecEnv
+    from tpp_b200.discrete_env.mountain_car_pre_vec import MountainCarVecEnv
+    cls = {"cartpole": CartPoleVecEnv, "cartpole_swing": CartPoleSwingVecEnv, "mountain_car": MountainCarVecEnv,
+           "acrobot": AcrobotVecEnv}[family]
+    return cls(n_envs=n, **kw)
+
+
+def _kwargs(g):
+    kw = {k: float(v) for k, v in zip(g["kwargs_keys"], g["kwargs_vals"])}
+    kw["max_steps"] = int(kw["max_steps"])
+    return kw
+
+
+def _close(a, b, what):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    bad = np.abs(a - b) > ATOL + RTOL * np.abs(b)
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} outside tolerance, max abs err {np.abs(a - b).max():.3e}"
+
+
+def _near_threshold(family, pre, kw):
+    """Envs whose termination test is within 1e-5 of its threshold (done may legitimately differ in fp32)."""
+    if family == "cartpole":
+        th = 12 * 2 * np.pi / 360
+        return (np.abs(np.abs(pre[:, 0]) - 2.4) < 1e-5) | (np.abs(np.abs(pre[:, 2]) - th) < 1e-5)
+    if family == "cartpole_swing":
+        return np.abs(np.abs(pre[:, 0]) - 2.4) < 1e-5
+    if family == "mountain_car":
+        return (np.abs(pre[:, 0] - pre[:, 4]) < 1e-5) | (np.abs(pre[:, 1]) < 1e-7)
+    return np.abs(-np.cos(pre[:, 0]) - np.cos(pre[:, 1] + pre[:, 0]) - 1.0) < 1e-5
+
+
+def _force_state(env, state64, n_steps):
+    """Upload an oracle state (fp32-rounded) as the env's current slot."""
+    st = torch.from_numpy(state64.astype(np.float32)).cuda()
+    N = env.n_envs
+    if env.family == "acrobot":
+        env._dyn[:, :N] = st[:, :4].t()
+        ob = torch.cat((torch.cos(st[:, 0:1]), torch.sin(st[:, 0:1]), torch.cos(st[:, 1:2]), torch.sin(st[:, 1:2]),
+                        st[:, 2:]), 1)
+        env._slots[env._cur][:, :N] = ob.t()
+    else:
+        env._slots[env._cur][:, :N] = st.t()
+    env._step_ctr[:N] = torch.from_numpy(n_steps.astype(np.int32)).cuda()
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_teacher_forced_against_golden(golden_dir, family):
+    """Same inputs as the reference saw (fixtures minted from it), one step at a time."""
+    g = np.load(os.path.join(golden_dir, f"prevec_{family}.npz"))
+    S, N = g["action"].shape
+    kw = _kwargs(g)
+    env = _make(family, N, seed=0, **kw)
+    orc = OraclePreVec(family, N, seed=0, **kw)
+    mismatched_done = 0
+    for t in range(S):
+        s32 = g["state_before"][t].astype(np.float32).astype(np.float64)
+        _force_state(env, s32, g["n_steps_before"][t])
+        orc.state, orc.n_steps = s32.copy(), g["n_steps_before"][t].copy()
+        obs, rew, done, _ = env.step(g["action"][t], reset_rows=g["reset_rows"][t])
+        o_obs, o_rew, o_done = orc.step(g["action"][t], reset_rows=g["reset_rows"][t])
+        done = done.cpu().numpy()
+        near = _near_threshold(family, orc.pre_reset_state, kw)
+        ok = (done == o_done) | near
+        assert ok.all(), f"step {t}: done mismatch away from thresholds"
+        same = done == o_done
+        mismatched_done += int((~same).sum())
+        _close(obs.cpu().numpy()[same], o_obs[same], f"{family} obs step {t}")
+        _close(rew.cpu().numpy()[same], o_rew[same], f"{family} reward step {t}")
+        st = env.state.cpu().numpy()
+        if family == "acrobot":
+            d = (st[same, :2] - orc.state[same, :2]) / (2 * np.pi)
+            assert np.abs(d - np.round(d)).max() < 1e-6
+            _close(st[same, 2:], orc.state[same, 2:], "acrobot state")
+        else:
+            _close(st[same], orc.state[same], f"{family} state step {t}")
+        assert np.array_equal(env.n_steps.cpu().numpy()[same], orc.n_steps[same].astype(np.int32))
+    assert mismatched_done <= 2
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("n_envs", [2, 37, 4096])
+def test_teacher_forced_random_states(family, n_envs):
+    """Ragged (N % 4 != 0 -> scalar kernel) and large N (vectorised kernel) against the oracle."""
+    kw = dict(max_steps=5)
+    env = _make(family, n_envs, seed=3, **kw)
+    orc = OraclePreVec(family, n_envs, seed=3, **kw)
+    rng = np.random.default_rng(n_envs)
+    n_act = env.n_actions
+    for t in range(12):
+        # widen the start block so that terminations (not only truncations) occur
+        lo, hi = orc.low.copy(), orc.high.copy()
+        if family in ("cartpole", "cartpole_swing"):
+            lo[:4], hi[:4] = [-2.6, -2, lo[2] - 0.25, -2], [2.6, 2, hi[2] + 0.25, 2]
+        elif family == "mountain_car":
+            lo[:2], hi[:2] = [-1.2, -0.07], [0.6, 0.07]
+        else:
+            lo[:4], hi[:4] = [-3.1, -3.1, -12, -28], [3.1, 3.1, 12, 28]
+        s64 = rng.uniform(lo, hi, size=(n_envs, len(lo))).astype(np.float32).astype(np.float64)
+        steps = rng.integers(0, 5, n_envs).astype(np.float64)
+        rows = orc.sample_block()
+        a = rng.integers(0, n_act, n_envs)
+        _force_state(env, s64, steps)
+        orc.state, orc.n_steps = s64.copy(), steps.copy()
+        obs, rew, done, _ = env.step(a, reset_rows=rows)
+        o_obs, o_rew, o_done = orc.step(a, reset_rows=rows)
+        done = done.cpu().numpy()
+        near = _near_threshold(family, orc.pre_reset_state, kw)
+        assert ((done == o_done) | near).all()
+        same = done == o_done
+        _close(obs.cpu().numpy()[same], o_obs[same], f"{family} obs")
+        _close(rew.cpu().numpy()[same], o_rew[same], f"{family} reward")
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_philox_resets_inside_start_space(family):
+    """Without injected rows, finished envs restart inside the family's start space (and mountain car's
+    rejection rule goal <= right boundary holds); step counters return to zero."""
+    env = _make(family, 4096, seed=5, max_steps=3)
+    orc = OraclePreVec(family, 4, seed=0)
+    lo, hi = orc.low.astype(np.float32), orc.high.astype(np.float32)
+    first = env.state.cpu().numpy()
+    assert (first >= lo - 1e-6).all() and (first <= hi + 1e-6).all()
+    acts = torch.zeros(4096, dtype=torch.int32, device="cuda")
+    for t in range(3):
+        obs, rew, done, _ = env.step(acts)
+    assert bool(done.all())                       # truncation at max_steps=3
+    st = env.state.cpu().numpy()
+    assert (st >= lo - 1e-6).all() and (st <= hi + 1e-6).all()
+    assert (env.n_steps == 0).all()
+    if family == "mountain_car":
+        assert (st[:, 4] <= st[:, 3]).all()
+    assert not np.array_equal(st, first)           # a fresh draw, not a replay of the first block
+    assert len(np.unique(st[:, 0])) > 3000         # per-env independent streams
+
+
+def test_contract_errors():
+    from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    with pytest.raises(Exception):
+        CartPoleVecEnv(n_envs=1)
+    env = CartPoleVecEnv(n_envs=8)
+    with pytest.raises(AssertionError):
+        env.step(np.zeros(7, dtype=np.int64))
+    with pytest.raises(AssertionError):
+        env.step(np.full(8, 2))
+    assert env.observation_space.shape == (9,) and env.action_space.n == 2
+    assert set(env.get_params()) == set(env.customizable_params)
+
+
+def test_numpy_compat_matches_reference_types():
+    from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    env = CartPoleVecEnv(n_envs=16, numpy_compat=True)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.dtype == np.float64 and obs.shape == (16, 9)
+    obs, rew, done, info = env.step(np.ones(16, dtype=np.int64))
+    assert rew.dtype == np.float64 and done.dtype == np.bool_ and info[0]["env_reward"] == 1.0
+
+
+def test_create_from_yaml_set():
+    from tpp_b200.discrete_env.cartpole_pre_vec import create_cartpole
+    hp = dict(n_envs=32, degrees_v=9, h_range_v=1.8, n_steps=256, gamma=0.99)
+    env = create_cartpole(None, hp)
+    env_v = create_cartpole(None, hp, is_valid=True)
+    assert env.degrees == 12 and env_v.degrees == 9 and env_v.h_range == 1.8
+    assert env_v.min_gravity == 10.4 and env.min_gravity == 9.8

@@ -1,0 +1,124 @@
+"""ctypes binding of the C-ABI in include/tpp_b200.h.
+
+The product path has NO fallback: if ``csrc/libtpp_b200.so`` is missing or a call returns a non-zero status,
+a ``TppError`` is raised.  (Build with ``python -c "import __graft_entry__ as g; g.build()"``.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtpp_b200.so")
+ABI_VERSION = 1
+
+
+class TppError(RuntimeError):
+    pass
+
+
+class EnvCfg(C.Structure):
+    _fields_ = [("family", C.c_int32), ("n_envs", C.c_int32), ("max_steps", C.c_int32), ("n_state", C.c_int32),
+                ("seed", C.c_uint64), ("start_low", C.c_float * 16), ("start_high", C.c_float * 16),
+                ("p", C.c_float * 8)]
+
+
+class BoxWorldState(C.Structure):
+    _fields_ = [("n_envs", C.c_int32), ("n", C.c_int32), ("max_steps", C.c_int32), ("n_levels", C.c_int32),
+                ("start_seed", C.c_int64), ("goal_length", C.c_int32), ("num_distractor", C.c_int32),
+                ("distractor_length", C.c_int32), ("_pad", C.c_int32),
+                ("world", C.c_void_p), ("world_dic", C.c_void_p), ("player_pos", C.c_void_p),
+                ("owned_key", C.c_void_p), ("num_env_steps", C.c_void_p), ("episode_reward", C.c_void_p),
+                ("seed_counter", C.c_void_p), ("bank_world", C.c_void_p), ("bank_dic", C.c_void_p),
+                ("bank_pos", C.c_void_p), ("scratch", C.c_void_p)]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [("eps_clip", C.c_float), ("value_coef", C.c_float), ("entropy_coef", C.c_float),
+                ("entropy_multiplier", C.c_float), ("x_entropy_coef", C.c_float), ("n_actions", C.c_int32),
+                ("mb", C.c_int32)]
+
+
+class AdamState(C.Structure):   # mirrors tpp_adam_state (lives in device memory; this is the host image)
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("_pad", C.c_int32),
+                ("sqnorm", C.c_double * 2)]
+
+
+FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}
+EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM = 1, 2, 4, 8
+
+_vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
+
+# name -> argtypes (every function returns int status unless listed in _SPECIAL)
+SIGNATURES = {
+    "tpp_version": [],
+    "tpp_device_sm_count": [C.POINTER(C.c_int)],
+    "tpp_env_step": [C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _vp],
+    "tpp_env_reset": [C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp, _u64, _i64, _vp],
+    "tpp_tick_advance": [_vp, _u64, _vp],
+    "tpp_boxworld_step": [C.POINTER(BoxWorldState), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tpp_boxworld_gen_levels_host": [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp],
+    "tpp_boxworld_gen_levels_device": [C.POINTER(BoxWorldState), _vp, _vp, _i32, _vp],
+    "tpp_boxworld_emit_frames": [C.POINTER(BoxWorldState), _vp, _vp],
+    "tpp_vecnormalize_step": [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _f64, _f64, _f64, _vp],
+    "tpp_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp],
+    "tpp_adv_normalize": [_vp, _vp, _i32, _i32, _i64, _vp],
+    "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                       _vp, _vp, _vp, _vp],
+    "tpp_gather_img": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
+                       _vp, _vp, _vp, _vp, _vp],
+    "tpp_frames_to_obs": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "tpp_gemm_f32": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "tpp_colsum_accum": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],
+    "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],
+    "tpp_grad_sqnorm": [_vp, _vp, _i64, _vp],
+    "tpp_adam_clip_step": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+}
+_NO_STATUS = {"tpp_version"}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly when it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TppError(f"{LIB_PATH} not found: the CUDA extension is not built. "
+                       "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                       "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.tpp_error_string.argtypes = [C.c_int]
+    lib.tpp_error_string.restype = C.c_char_p
+    if lib.tpp_version() != ABI_VERSION:
+        raise TppError(f"ABI mismatch: library {lib.tpp_version()} vs binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an entry point and raise TppError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0 and name not in _NO_STATUS:
+        msg = lib.tpp_error_string(rc)
+        raise TppError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")
+    return rc
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

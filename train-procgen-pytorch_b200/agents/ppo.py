@@ -1,0 +1,403 @@
+"""PPO agent with the reference's interface (agents/ppo.py:9-279) on B200-native kernels.
+
+``optimize()`` = epochs x minibatches of: device gather -> policy forward -> fused loss fwd+bwd -> policy
+backward into the flat gradient buffer -> (one NCCL all-reduce when sharded) -> fused clip+Adam.  No autograd,
+no host synchronisation inside the loop: per-minibatch loss statistics are accumulated on the device and read
+back once per call.  ``train()`` runs the rollout on the device (policy forward -> Philox action sampling ->
+fused env step writing into the rollout slots), optionally replayed from a CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..common.engine import MLPEngine, TorchModuleEngine
+from ..common.model import MLPModel
+from .base_agent import BaseAgent
+
+
+def adjust_lr(optimizer, init_lr, timesteps, max_timesteps):
+    """common/misc_util.py:92-96."""
+    lr = init_lr * (1 - (timesteps / max_timesteps))
+    for g in optimizer.param_groups:
+        g["lr"] = lr
+    return optimizer, lr
+
+
+def adjust_lr_grok(optimizer, init_lr, timesteps, max_timesteps):
+    """common/misc_util.py:98-102."""
+    lr = init_lr * (1.1 ** (timesteps / 1e6))
+    for g in optimizer.param_groups:
+        g["lr"] = lr
+    return optimizer, lr
+
+
+class FlatAdam:
+    """Adam(lr, betas=(0.9, 0.999), eps) + clip_grad_norm_ over the policy's flat buffer; state lives on the
+    device (``tpp_adam_state``).  ``state_dict()`` has torch.optim.Adam's layout so reference tooling can load it."""
+
+    def __init__(self, policy, lr, eps=1e-5, betas=(0.9, 0.999), max_grad_norm=0.5):
+        self.policy = policy
+        self.flat, self.gflat = policy.flat, policy.flat_grad
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.param_groups = [dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)]
+        host = _lib.AdamState(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, max_grad_norm=max_grad_norm,
+                              grad_scale=1.0, step=0)
+        raw = bytes(host)
+        self.state = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.flat.device)
+        self._f32 = self.state.view(torch.float32)
+        self._i32 = self.state.view(torch.int32)
+        self._lr_on_device = lr
+        self.n_launches = 0
+
+    def set_grad_scale(self, s):
+        self._f32[5:6].copy_(torch.tensor([s], dtype=torch.float32))
+
+    def _sync_lr(self):
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_device:
+            self._f32[0:1].copy_(torch.tensor([lr], dtype=torch.float32), non_blocking=True)
+            self._lr_on_device = lr
+
+    def step(self):
+        self._sync_lr()
+        n, s = self.flat.numel(), _lib.stream_ptr()
+        _lib.call("tpp_grad_sqnorm", _lib.ptr(self.state), _lib.ptr(self.gflat), n, s)
+        _lib.call("tpp_adam_clip_step", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(self.gflat),
+                  _lib.ptr(self.m), _lib.ptr(self.v), n, s)
+        self.n_launches += 2
+
+    @property
+    def step_count(self):
+        return int(self._i32[6].item())
+
+    def state_dict(self):
+        state, names = {}, [n for n, _ in self.policy.named_parameters()]
+        step = torch.tensor(float(self.step_count))
+        for i, n in enumerate(names):
+            off, shape = self.policy.layout[n]
+            k = int(np.prod(shape))
+            state[i] = {"step": step.clone(), "exp_avg": self.m[off:off + k].view(shape).clone(),
+                        "exp_avg_sq": self.v[off:off + k].view(shape).clone()}
+        group = dict(self.param_groups[0], params=list(range(len(names))))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        names = [n for n, _ in self.policy.named_parameters()]
+        step = 0
+        for i, n in enumerate(names):
+            if i in sd["state"]:
+                off, shape = self.policy.layout[n]
+                k = int(np.prod(shape))
+                self.m[off:off + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
+                self.v[off:off + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
+                step = int(sd["state"][i]["step"])
+        self._i32[6:7].copy_(torch.tensor([step], dtype=torch.int32))
+        self.param_groups[0]["lr"] = sd["param_groups"][0]["lr"]
+
+
+class PPO(BaseAgent):
+    def __init__(self, env, policy, logger, storage, device, n_checkpoints, env_valid=None, storage_valid=None,
+                 n_steps=128, n_envs=8, epoch=3, n_minibatch=8, mini_batch_size=32 * 8, gamma=0.99, lmbda=0.95,
+                 learning_rate=2.5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.01,
+                 x_entropy_coef=0., normalize_adv=True, normalize_rew=True, use_gae=True, entropy_scaling=None,
+                 increasing_lr=False, sparsity_coef=0., fs_coef=0., **kwargs):
+        super().__init__(env, policy, logger, storage, device, n_checkpoints, env_valid, storage_valid)
+        self.fs_coef = fs_coef
+        self.total_timesteps = 0
+        self.entropy_scaling = entropy_scaling
+        self.entropy_multiplier = 1.
+        self.s_loss_coef = sparsity_coef
+        self.min_rew, self.max_rew = -1., 11.
+        self.n_steps, self.n_envs = n_steps, n_envs
+        self.epoch, self.n_minibatch, self.mini_batch_size = epoch, n_minibatch, mini_batch_size
+        self.gamma, self.lmbda = gamma, lmbda
+        self.learning_rate = learning_rate
+        self.grad_clip_norm, self.eps_clip = grad_clip_norm, eps_clip
+        self.value_coef, self.entropy_coef, self.x_entropy_coef = value_coef, entropy_coef, x_entropy_coef
+        self.normalize_adv, self.normalize_rew, self.use_gae = normalize_adv, normalize_rew, use_gae
+        self.adjust_lr = adjust_lr_grok if increasing_lr else adjust_lr
+        self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", True))
+        self.sample_seed = int(kwargs.get("sample_seed", 0))
+
+        if policy.flat is None:
+            policy.flatten_(device)
+        self.n_actions = policy.action_size
+        if isinstance(policy.embedder, MLPModel):
+            self.engine = MLPEngine(policy, self.n_actions)
+        else:
+            self.engine = TorchModuleEngine(policy, self.n_actions, storage.obs_shape)
+        self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
+        self.world_size = 1
+        self.process_group = None
+        self._tick = torch.zeros(1, dtype=torch.int64, device=policy.flat.device)
+        self._rollout_graph = None
+        self._stats = None
+        self._pbar = None
+        self.last_stats = None
+        self.n_launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def shard(self, world_size, process_group=None):
+        """Env-sharded data parallel: gradients are summed with ONE all-reduce per optimizer step and scaled by
+        1/world inside the clip+Adam kernel; advantage moments are all-reduced once per rollout."""
+        self.world_size, self.process_group = world_size, process_group
+        self.optimizer.set_grad_scale(1.0 / world_size)
+        self.storage.world_size, self.storage.process_group = world_size, process_group
+
+    # ------------------------------------------------------------------------------------------
+    def _policy_head(self, obs_slot, storage):
+        """Policy forward on a rollout slot -> head buffer [N, ld_head]."""
+        N = storage.num_envs
+        if storage.is_image:
+            c, h, w = storage.obs_shape
+            mb = storage.minibatch_buffers(N)
+            _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot), N, h, w, c, _lib.ptr(mb.obs), mb.ld_obs,
+                      _lib.stream_ptr())
+            self.n_launches += 1
+            return self.engine.forward(mb.obs, N)
+        return self.engine.forward(obs_slot, N, feature_major_ld=storage.ld)
+
+    def _sample(self, head, N, act, logp, value, t_offset, greedy=False):
+        _lib.call("tpp_sample_actions", _lib.ptr(head), self.engine.ld_head, N, self.n_actions, _lib.ptr(act),
+                  _lib.ptr(logp), _lib.ptr(value), self.sample_seed, _lib.ptr(self._tick), int(t_offset),
+                  1 if greedy else 0, _lib.stream_ptr())
+        self.n_launches += 1
+
+    def predict(self, obs, hidden_state, done):
+        """Reference signature (agents/ppo.py:72-81): obs [N, *obs_shape] numpy or tensor ->
+        (act, log_prob_act, value, hidden_state); numpy in, numpy out."""
+        was_numpy = not torch.is_tensor(obs)
+        dev = self.policy.flat.device
+        x = torch.as_tensor(np.asarray(obs) if was_numpy else obs).to(dev, torch.float32)
+        N = x.shape[0]
+        x = x.reshape(N, -1).contiguous()
+        head = self.engine.forward(x, N)
+        act = torch.empty(N, dtype=torch.int32, device=dev)
+        logp = torch.empty(N, dtype=torch.float32, device=dev)
+        value = torch.empty(N, dtype=torch.float32, device=dev)
+        self._sample(head, N, act, logp, value, 0)
+        _lib.call("tpp_tick_advance", _lib.ptr(self._tick), 1, _lib.stream_ptr())
+        if was_numpy:
+            return act.cpu().numpy().astype(np.int64), logp.cpu().numpy(), value.cpu().numpy(), hidden_state
+        return act, logp, value, hidden_state
+
+    # ------------------------------------------------------------------------------------------
+    def optimize(self):
+        if self.entropy_scaling == "reward_based":
+            mean_rew = np.mean(self.logger.episode_reward_buffer)
+            self.entropy_multiplier = 1 - ((mean_rew - self.min_rew) / (self.max_rew - self.min_rew))
+        elif self.entropy_scaling == "time_based":
+            self.entropy_multiplier = 1 - (self.t / self.total_timesteps)
+
+        st = self.storage
+        batch_size = self.n_steps * self.n_envs // self.n_minibatch
+        if batch_size < self.mini_batch_size:
+            self.mini_batch_size = batch_size
+        accum = batch_size / self.mini_batch_size
+        cnt = 1
+        mb = self.mini_batch_size
+        n_mb = (st.num_steps * st.num_envs) // mb
+        total = n_mb * self.epoch
+        dev, A = self.policy.flat.device, self.n_actions
+        if self._stats is None or self._stats.shape[0] != total:
+            self._stats = torch.zeros(total, 4 + 16, dtype=torch.float64, device=dev)
+            self._pbar = torch.zeros(total, 16, dtype=torch.float32, device=dev)
+        self._stats.zero_()
+        cfg = _lib.LossCfg(self.eps_clip, self.value_coef, self.entropy_coef, float(self.entropy_multiplier),
+                           self.x_entropy_coef, A, mb)
+        ld_obs = st.obs_width if st.is_image else None
+        buf = st.minibatch_buffers(mb, _round4(ld_obs) if ld_obs else None)
+        engine, s = self.engine, _lib.stream_ptr()
+        fs_vals = []
+        is_torch_engine = isinstance(engine, TorchModuleEngine)
+        self.policy.train()
+        k = 0
+        for _ in range(self.epoch):
+            idx = st.epoch_indices(mb)
+            for i in range(n_mb):
+                st.gather(idx[i], buf)
+                head = engine.forward(buf.obs, mb, train=True) if is_torch_engine else engine.forward(buf.obs, mb)
+                ws_dhead = engine._workspace(mb).dhead if not is_torch_engine else self._dhead(mb)
+                pbar = None
+                if self.x_entropy_coef != 0.0:
+                    self._pbar[k].zero_()
+                    _lib.call("tpp_ppo_pbar", _lib.ptr(head), engine.ld_head, mb, A, _lib.ptr(self._pbar[k]), s)
+                    pbar = self._pbar[k]
+                    self.n_launches += 1
+                _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
+                          _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
+                          _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(self._stats[k]), s)
+                self.n_launches += 1
+                if is_torch_engine:
+                    engine.backward(ws_dhead, mb, self.fs_coef)
+                    if engine.last_fs is not None:
+                        fs_vals.append(engine.last_fs.detach())
+                else:
+                    engine.backward(ws_dhead, mb)
+                if cnt % accum == 0:
+                    if self.world_size > 1:
+                        torch.distributed.all_reduce(self.policy.flat_grad, group=self.process_group)
+                    self.optimizer.step()
+                cnt += 1
+                k += 1
+        return self._summary(fs_vals)
+
+    def _dhead(self, mb):
+        if getattr(self, "_dhead_buf", None) is None or self._dhead_buf.shape[0] != mb:
+            self._dhead_buf = torch.zeros(mb, self.engine.ld_head, dtype=torch.float32, device=self.policy.flat.device)
+        return self._dhead_buf
+
+    def _summary(self, fs_vals):
+        """One device->host read of the accumulated sums, then the reference's nine summary keys in order
+        (agents/ppo.py:199-207).  Loss/pi and Loss/v keep the reference's sign quirk (negated)."""
+        S = self._stats.cpu().numpy()
+        A = self.n_actions
+        B = S[:, 3]
+        pi_loss = -S[:, 0] / B
+        v_loss = 0.5 * S[:, 1] / B
+        ent = S[:, 2] / B
+        pbar = S[:, 4:4 + A] / B[:, None]
+        marg = -(pbar * np.log(pbar)).sum(1)
+        x_ent = marg - ent
+        fs = np.array([float(v) for v in fs_vals]) if fs_vals else None
+        total = (pi_loss + self.value_coef * v_loss - self.entropy_coef * ent * self.entropy_multiplier
+                 - self.x_entropy_coef * x_ent)
+        if fs is not None:
+            total = total + self.fs_coef * fs
+        self.last_stats = dict(pi_loss=pi_loss, value_loss=v_loss, entropy=ent, x_entropy=x_ent, total=total)
+        nan = float("nan")
+        return {"Loss/pi": float(np.mean(-pi_loss)), "Loss/v": float(np.mean(-v_loss)),
+                "Loss/entropy": float(np.mean(ent)), "Loss/x_entropy": float(np.mean(x_ent)),
+                "Loss/atn_entropy": nan, "Loss/atn_entropy2": nan, "Loss/sparsity": nan,
+                "Loss/feature_sparsity": float(np.mean(fs)) if fs is not None else nan,
+                "Loss/total": float(np.mean(total))}
+
+    # ------------------------------------------------------------------------------------------
+    # Rollout
+    # ------------------------------------------------------------------------------------------
+    def _device_env(self, env):
+        return hasattr(env, "rollout_step")
+
+    def _rollout_steps(self, env, storage):
+        T, N = storage.num_steps, storage.num_envs
+        for t in range(T):
+            head = self._policy_head(storage.obs_slot(t), storage)
+            self._sample(head, N, storage.act_i32[t], storage.logp[t], storage.value[t], t)
+            env.rollout_step(storage, t)
+        head = self._policy_head(storage.obs_slot(T), storage)
+        storage.value[T, :N] = head[:N, self.n_actions]
+        _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
+        env.advance_tick(T)
+        self.n_launches += 2
+
+    def collect_rollout(self, env=None, storage=None):
+        """T fused steps on the device (policy -> sample -> env) followed by the bootstrap value."""
+        env, storage = env or self.env, storage or self.storage
+        key = (id(env), id(storage))
+        if not self.use_cuda_graph:
+            return self._rollout_steps(env, storage)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        if key not in graphs:
+            self._rollout_steps(env, storage)            # eager warm-up (allocates workspaces, loads modules)
+            graphs[key] = None
+            return
+        if graphs[key] is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            launches = (self.n_launches, self.engine.n_launches)
+            with torch.cuda.graph(g):
+                self._rollout_steps(env, storage)
+            graphs[key] = (g, self.n_launches - launches[0], self.engine.n_launches - launches[1])
+        g, d_self, d_eng = graphs[key]
+        g.replay()
+        self.n_launches += d_self
+        self.engine.n_launches += d_eng
+
+    def _carry_over(self, storage):
+        """Slot T of the finished rollout is slot 0 of the next one."""
+        T = storage.num_steps
+        storage.obs_slot(0).copy_(storage.obs_slot(T))
+
+    def train(self, num_timesteps):
+        self.total_timesteps = num_timesteps
+        save_every = num_timesteps // self.num_checkpoints if self.num_checkpoints else num_timesteps + 1
+        checkpoints = sorted((i + 1) * save_every for i in range(max(self.num_checkpoints, 1)))
+        checkpoint_cnt = 0
+        if not self._device_env(self.env):
+            return self._train_host_env(num_timesteps, checkpoints)
+        self.env.reset_rollout(self.storage)
+        if self.env_valid is not None:
+            self.env_valid.reset_rollout(self.storage_valid)
+        while self.t < num_timesteps:
+            self.policy.eval()
+            self.collect_rollout(self.env, self.storage)
+            self.storage.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
+            if self.env_valid is not None:
+                self.collect_rollout(self.env_valid, self.storage_valid)
+                self.storage_valid.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
+            summary = self.optimize()
+            self.t += self.n_steps * self.n_envs
+            self._log(summary, num_timesteps)
+            self._carry_over(self.storage)
+            if self.env_valid is not None:
+                self._carry_over(self.storage_valid)
+            if self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]:
+                self.save_checkpoint()
+                checkpoint_cnt += 1
+        self.env.close()
+        if self.env_valid is not None:
+            self.env_valid.close()
+
+    def _log(self, summary, num_timesteps):
+        if self.logger is not None:
+            rew_batch, done_batch, tar = self.storage.fetch_log_data()
+            if self.storage_valid is not None:
+                rew_v, done_v, tar_v = self.storage_valid.fetch_log_data()
+            else:
+                rew_v = done_v = tar_v = None
+            self.logger.feed(rew_batch, done_batch, tar, rew_v, done_v, tar_v)
+        self.optimizer, lr = self.adjust_lr(self.optimizer, self.learning_rate, self.t, num_timesteps)
+        if self.logger is not None:
+            self.logger.dump(summary, lr)
+
+    def save_checkpoint(self):
+        """Same file name and keys as the reference (agents/ppo.py:271-276)."""
+        if self.logger is None or getattr(self.logger, "logdir", None) is None:
+            return
+        torch.save({"model_state_dict": self.policy.state_dict(), "optimizer_state_dict": self.optimizer.state_dict()},
+                   self.logger.logdir + "/model_" + str(self.t) + ".pth")
+
+    def _train_host_env(self, num_timesteps, checkpoints):
+        """Host-stepped envs (Procgen or any numpy VecEnv): the reference loop (agents/ppo.py:216-236) with the
+        observations staged into the GPU rollout by Storage.store; GAE and the update stay on the device."""
+        checkpoint_cnt = 0
+        obs = self.env.reset()
+        hidden_state = np.zeros((self.n_envs, self.storage.hidden_state_size))
+        done = np.zeros(self.n_envs)
+        while self.t < num_timesteps:
+            self.policy.eval()
+            for _ in range(self.n_steps):
+                act, log_prob_act, value, next_hidden_state = self.predict(obs, hidden_state, done)
+                next_obs, rew, done, info = self.env.step(act)
+                self.storage.store(obs, hidden_state, act, rew, done, info, log_prob_act, value)
+                obs, hidden_state = next_obs, next_hidden_state
+            _, _, last_val, hidden_state = self.predict(obs, hidden_state, done)
+            self.storage.store_last(obs, hidden_state, last_val)
+            self.storage.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
+            summary = self.optimize()
+            self.t += self.n_steps * self.n_envs
+            self._log(summary, num_timesteps)
+            if self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]:
+                self.save_checkpoint()
+                checkpoint_cnt += 1
+        self.env.close()
+
+
+def _round4(x):
+    return (x + 3) // 4 * 4

@@ -1,0 +1,237 @@
+"""GPU-resident rollout storage with the reference's ``Storage`` interface (common/storage.py:7-162).
+
+Layout in HBM: per-step scalars are ``[T(+1), ld]`` rows (ld = N rounded up to 4);
+vector observations are feature-major ``[T+1, n_obs, ld]`` so that the env kernels and the policy read/write
+coalesced columns; image observations are uint8 NHWC ``[T+1, N, H, W, C]`` and become float NCHW/255 only when
+a minibatch is gathered.  The reference-shaped public tensors (``obs_batch``, ``act_batch`` ...) are exposed as
+views / on-demand conversions of these buffers.
+
+GAE, advantage normalisation and the minibatch gather are CUDA kernels (csrc/storage.cu); minibatch indices come
+from ``torch.randperm`` on the default CPU generator exactly like the reference's ``SubsetRandomSampler`` /
+``BatchSampler(drop_last=True)`` pair, so minibatch composition is bit-identical under the same torch seed.
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class MiniBatch:
+    """Device buffers of one gathered minibatch (reused between minibatches: no allocation in the loop)."""
+
+    def __init__(self, mb, obs_width, ld_obs, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.mb, self.obs_width, self.ld_obs = mb, obs_width, ld_obs
+        self.obs = torch.zeros(mb, ld_obs, **f)
+        self.act = torch.zeros(mb, dtype=torch.int32, device=device)
+        self.logp, self.value, self.ret, self.adv, self.done = (torch.zeros(mb, **f) for _ in range(5))
+
+
+class Storage:
+    def __init__(self, obs_shape, hidden_state_size, num_steps, num_envs, device, continuous_actions=False,
+                 act_shape=None):
+        if continuous_actions:
+            raise NotImplementedError("continuous actions are outside the north-star hot path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.TppError("Storage is GPU-resident: device must be a CUDA device (there is no CPU fallback)")
+        _lib.load()
+        self.continuous_actions = False
+        self.performance_track = {}
+        self.obs_shape = tuple(obs_shape)
+        self.act_shape = act_shape
+        self.hidden_state_size = hidden_state_size
+        self.num_steps, self.num_envs = int(num_steps), int(num_envs)
+        self.ld = _round_up(self.num_envs, 4)
+        self.is_image = len(self.obs_shape) == 3
+        self.obs_width = int(np.prod(self.obs_shape))
+        self.world_size, self.process_group = 1, None
+        self._mb = {}
+        self.n_launches = 0
+        self.reset()
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self):
+        T, N, ld, dev = self.num_steps, self.num_envs, self.ld, self.device
+        f = dict(dtype=torch.float32, device=dev)
+        if self.is_image:
+            c, h, w = self.obs_shape
+            self.frames = torch.zeros(T + 1, N, h, w, c, dtype=torch.uint8, device=dev)
+            self.obs_fm = None
+        else:
+            self.obs_fm = torch.zeros(T + 1, self.obs_width, ld, **f)
+            self.frames = None
+        self.act_i32 = torch.zeros(T, ld, dtype=torch.int32, device=dev)
+        self.logp = torch.zeros(T, ld, **f)
+        self.rew = torch.zeros(T, ld, **f)
+        self.env_rew = None            # raw rewards when the env normalises them (Box-World / Procgen)
+        self.done_u8 = torch.zeros(T, ld, dtype=torch.uint8, device=dev)
+        self.value = torch.zeros(T + 1, ld, **f)
+        self.ret = torch.zeros(T, ld, **f)
+        self.adv = torch.zeros(T, ld, **f)
+        self.moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.info_batch = deque(maxlen=T)
+        self._hidden = None
+        self.step = 0
+
+    # ---- reference-shaped public tensors -------------------------------------------------------------
+    @property
+    def obs_batch(self):
+        if self.is_image:
+            return self.frames.permute(0, 1, 4, 2, 3).float() / 255.0
+        return self.obs_fm.permute(0, 2, 1)[:, :self.num_envs]
+
+    @property
+    def hidden_states_batch(self):
+        if self._hidden is None:
+            self._hidden = torch.zeros(self.num_steps + 1, self.num_envs, self.hidden_state_size, device=self.device)
+        return self._hidden
+
+    @property
+    def act_batch(self):
+        return self.act_i32[:, :self.num_envs].float()
+
+    @property
+    def log_prob_act_batch(self):
+        return self.logp[:, :self.num_envs]
+
+    @property
+    def rew_batch(self):
+        return self.rew[:, :self.num_envs]
+
+    @property
+    def done_batch(self):
+        return self.done_u8[:, :self.num_envs].float()
+
+    @property
+    def value_batch(self):
+        return self.value[:, :self.num_envs]
+
+    @property
+    def return_batch(self):
+        return self.ret[:, :self.num_envs]
+
+    @property
+    def adv_batch(self):
+        return self.adv[:, :self.num_envs]
+
+    # ---- rollout slots for the fused kernels -----------------------------------------------------------
+    def obs_slot(self, t):
+        return self.frames[t] if self.is_image else self.obs_fm[t]
+
+    def enable_raw_rewards(self):
+        if self.env_rew is None:
+            self.env_rew = torch.zeros(self.num_steps, self.ld, dtype=torch.float32, device=self.device)
+
+    # ---- reference API: host-driven stores (compat path) -------------------------------------------------
+    def _t(self, x, dtype):
+        if torch.is_tensor(x):
+            return x.to(self.device, dtype)
+        return torch.from_numpy(np.ascontiguousarray(x)).to(self.device, dtype)
+
+    def _store_obs(self, slot, obs):
+        o = self._t(obs, torch.float32)
+        if self.is_image:
+            self.frames[slot] = (o * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+        else:
+            self.obs_fm[slot, :, :self.num_envs] = o.reshape(self.num_envs, -1).t()
+
+    def store(self, obs, hidden_state, act, rew, done, info, log_prob_act, value):
+        s, N = self.step, self.num_envs
+        self._store_obs(s, obs)
+        self.act_i32[s, :N] = self._t(act, torch.int32).reshape(-1)
+        self.rew[s, :N] = self._t(rew, torch.float32).reshape(-1)
+        self.done_u8[s, :N] = self._t(done, torch.uint8).reshape(-1)
+        self.logp[s, :N] = self._t(log_prob_act, torch.float32).reshape(-1)
+        self.value[s, :N] = self._t(value, torch.float32).reshape(-1)
+        self.info_batch.append(info)
+        self.step = (self.step + 1) % self.num_steps
+
+    def store_last(self, last_obs, last_hidden_state, last_value):
+        self._store_obs(self.num_steps, last_obs)
+        self.value[self.num_steps, :self.num_envs] = self._t(last_value, torch.float32).reshape(-1)
+
+    # ---- GAE -----------------------------------------------------------------------------------------------
+    def compute_estimates(self, gamma=0.99, lmbda=0.95, use_gae=True, normalize_adv=True):
+        if not use_gae:
+            # common/storage.py:69-77: the reference overwrites the Monte-Carlo returns with adv(=0)+V, i.e. the
+            # use_gae=False branch is broken upstream; refuse rather than silently reproduce or "fix" it.
+            raise NotImplementedError("use_gae=False is broken in the reference (storage.py:69-77); unsupported")
+        T, N, s = self.num_steps, self.num_envs, _lib.stream_ptr()
+        self.moments.zero_()
+        _lib.call("tpp_gae", _lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value), _lib.ptr(self.adv),
+                  _lib.ptr(self.ret), _lib.ptr(self.moments), T, N, self.ld, float(gamma), float(lmbda), s)
+        self.n_launches += 1
+        if normalize_adv:
+            if self.world_size > 1:   # exact global moments under env sharding: 3 doubles, once per rollout
+                torch.distributed.all_reduce(self.moments, group=self.process_group)
+            _lib.call("tpp_adv_normalize", _lib.ptr(self.adv), _lib.ptr(self.moments), T, N, self.ld, s)
+            self.n_launches += 1
+
+    # ---- minibatches -----------------------------------------------------------------------------------------
+    def minibatch_buffers(self, mb, ld_obs=None):
+        ld_obs = ld_obs or _round_up(self.obs_width, 4)
+        key = (mb, ld_obs)
+        if key not in self._mb:
+            self._mb[key] = MiniBatch(mb, self.obs_width, ld_obs, self.device)
+        return self._mb[key]
+
+    def epoch_indices(self, mini_batch_size):
+        """One ``torch.randperm(T*N)`` on the default CPU generator, cut into consecutive minibatches
+        (drop_last) — common/storage.py:87-91.  Returns a device int64 tensor [n_mb, mb]."""
+        batch = self.num_steps * self.num_envs
+        n_mb = batch // mini_batch_size
+        perm = torch.randperm(batch)
+        self.last_perm = perm
+        idx = perm[:n_mb * mini_batch_size].view(n_mb, mini_batch_size)
+        return idx.pin_memory().to(self.device, non_blocking=True)
+
+    def gather(self, idx_row, out):
+        """Gather one minibatch (device int64 indices [mb]) into ``out`` (a MiniBatch)."""
+        s, N = _lib.stream_ptr(), self.num_envs
+        scal = (_lib.ptr(self.act_i32), _lib.ptr(self.logp), _lib.ptr(self.value), _lib.ptr(self.ret),
+                _lib.ptr(self.adv), _lib.ptr(self.done_u8))
+        outs = (_lib.ptr(out.act), _lib.ptr(out.logp), _lib.ptr(out.value), _lib.ptr(out.ret), _lib.ptr(out.adv),
+                _lib.ptr(out.done))
+        if self.ld != N and not self.is_image:
+            pass   # flat index k = t*N + e is decoded in-kernel, rows are ld apart
+        if self.is_image:
+            c, h, w = self.obs_shape
+            if self.ld != N:
+                raise _lib.TppError("image rollouts need n_envs % 4 == 0")
+            _lib.call("tpp_gather_img", _lib.ptr(idx_row), out.mb, N, h, w, c, _lib.ptr(self.frames), *scal,
+                      _lib.ptr(out.obs), out.ld_obs, *outs, s)
+        else:
+            _lib.call("tpp_gather_vec", _lib.ptr(idx_row), out.mb, N, self.ld, self.obs_width, _lib.ptr(self.obs_fm),
+                      *scal, _lib.ptr(out.obs), out.ld_obs, *outs, s)
+        self.n_launches += 1
+        return out
+
+    def fetch_train_generator(self, mini_batch_size=None, recurrent=False):
+        if recurrent:
+            raise NotImplementedError("recurrent minibatching is a 'next' row (SURVEY 8f N4)")
+        batch = self.num_steps * self.num_envs
+        mini_batch_size = mini_batch_size or batch
+        idx = self.epoch_indices(mini_batch_size)
+        hidden = torch.zeros(1, self.hidden_state_size, device=self.device).expand(batch, self.hidden_state_size)
+        for i in range(idx.shape[0]):
+            out = self.gather(idx[i], MiniBatch(mini_batch_size, self.obs_width, _round_up(self.obs_width, 4),
+                                                self.device))
+            obs = out.obs[:, :self.obs_width].reshape(mini_batch_size, *self.obs_shape)
+            yield obs, hidden, out.act.float(), out.done, out.logp, out.value, out.ret, out.adv
+
+    # ---- logging ---------------------------------------------------------------------------------------------
+    def fetch_log_data(self):
+        """(rew_batch [T,N], done_batch [T,N], true_average_reward) as numpy, raw env rewards when available
+        (common/storage.py:130-162; per-level tracking needs Procgen's prev_level_seed and stays NaN here)."""
+        rew = self.env_rew if self.env_rew is not None else self.rew
+        return (rew[:, :self.num_envs].cpu().numpy(), self.done_u8[:, :self.num_envs].float().cpu().numpy(),
+                float("nan"))

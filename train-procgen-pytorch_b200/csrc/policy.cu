@@ -1,0 +1,417 @@
+// Policy-side kernels: exact-fp32 CUDA-core GEMM (generic strides), bias gradient, action sampling,
+// the fused PPO loss forward+backward, gradient-norm reduction and clipped Adam.
+//
+// Replaces (reference, eager PyTorch): nn.Linear forward/backward of MLPModel (common/model.py:954-980) and the
+// policy heads (common/policy.py:74-87); dist.sample()/log_prob in PPO.predict (agents/ppo.py:72-81); the loss
+// chain agents/ppo.py:131-170 with cross_batch_entropy (common/misc_util.py:32-51) and its autograd;
+// clip_grad_norm_ + optim.Adam(eps=1e-5) + zero_grad (agents/ppo.py:173-176).
+#include <math_constants.h>
+
+#include "tpp_common.cuh"
+
+namespace tpp {
+
+// ================================================================================================
+// Exact fp32 GEMM on CUDA cores:  C(m,n) (+)= epi( sum_k A(m,k) B(n,k) )
+// 64x64x16 tiles, 256 threads, 4x4 register tile per thread.  The tile loaders pick the thread->element
+// map whose fastest index follows the operand's contiguous dimension, so forward (K-contiguous),
+// data-gradient and weight-gradient (M-contiguous) calls are all coalesced.  This is the parity /
+// small-shape path; the large policy GEMMs go through the tcgen05 kernel (gemm_tc.cu).
+// ================================================================================================
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool ROW_FAST>   // ROW_FAST: consecutive threads walk the row (m or n) index; else the k index
+__device__ __forceinline__ void load_tile(const float* __restrict__ P, int64_t s_row, int64_t s_k, int row0, int k0,
+                                          int rows, int kend, float (*sm)[BM + 4]) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < (BM * BK) / 256; ++i) {
+    const int lin = tid + i * 256;
+    int r, k;
+    if (ROW_FAST) { r = lin % BM; k = lin / BM; } else { k = lin % BK; r = lin / BK; }
+    const int gr = row0 + r, gk = k0 + k;
+    float v = 0.0f;
+    if (gr < rows && gk < kend) v = P[(int64_t)gr * s_row + (int64_t)gk * s_k];
+    sm[k][r] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
+                                                       const float* __restrict__ B, int64_t sbn, int64_t sbk,
+                                                       float* __restrict__ C, int64_t ldc,
+                                                       const float* __restrict__ bias, const float* __restrict__ mask,
+                                                       int M, int N, int K, int flags, int k_chunk) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_chunk;
+  const int kend = min(K, kbeg + k_chunk);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // 16 x 16 threads, 4x4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  const bool a_row_fast = (sam == 1), b_row_fast = (sbn == 1);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    if (a_row_fast) load_tile<true>(A, sam, sak, m0, k0, M, kend, As); else load_tile<false>(A, sam, sak, m0, k0, M, kend, As);
+    if (b_row_fast) load_tile<true>(B, sbn, sbk, n0, k0, N, kend, Bs); else load_tile<false>(B, sbn, sbk, n0, k0, N, kend, Bs);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if ((flags & TPP_EPI_BIAS) && blockIdx.z == 0) v += bias[n];
+      if (flags & TPP_EPI_RELU) v = fmaxf(v, 0.0f);
+      if (flags & TPP_EPI_MASK) v = mask[(int64_t)m * ldc + n] > 0.0f ? v : 0.0f;
+      float* c = C + (int64_t)m * ldc + n;
+      if (split) atomicAdd(c, v);
+      else if (flags & TPP_EPI_ACCUM) *c += v;
+      else *c = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dZ, int64_t ld, int M, int N,
+                                                     float* __restrict__ out) {
+  // block = 32 columns x 8 row-lanes; rows strided by 8*gridDim.y
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  float s = 0.0f;
+  if (c < N)
+    for (int m = blockIdx.y * 8 + rl; m < M; m += 8 * gridDim.y) s += dZ[(int64_t)m * ld + c];
+  part[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && c < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += part[r][threadIdx.x & 31];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ================================================================================================
+// Action sampling (rollout): log-softmax, inverse-CDF draw from Philox, log-prob, value passthrough
+// ================================================================================================
+constexpr int MAX_A = 16;
+
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ head, int ld_head, int n_envs, int A,
+                                                     int32_t* __restrict__ act, float* __restrict__ logp,
+                                                     float* __restrict__ value, uint64_t seed, const uint64_t* tick,
+                                                     uint64_t t_offset, int greedy) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  const float* h = head + (int64_t)e * ld_head;
+  float z[MAX_A];
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < MAX_A; ++j)
+    if (j < A) { z[j] = h[j]; mx = fmaxf(mx, z[j]); }
+  float se = 0.0f;
+#pragma unroll
+  for (int j = 0; j < MAX_A; ++j)
+    if (j < A) se += expf(z[j] - mx);
+  const float lse = mx + logf(se);
+  int a = A - 1;
+  if (greedy) {
+    float best = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A && z[j] > best) { best = z[j]; a = j; }
+  } else {
+    const uint64_t tk = (tick ? *tick : 0ull) + t_offset;
+    const uint4 r = Philox(seed)((uint32_t)e, (uint32_t)tk, (uint32_t)(tk >> 32), 0x5A17u);
+    const float u = u01(r.x);
+    float cdf = 0.0f;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A && !found) {
+        cdf += expf(z[j] - lse);
+        if (u < cdf) { a = j; found = true; }
+      }
+  }
+  float la = 0.0f;
+#pragma unroll
+  for (int j = 0; j < MAX_A; ++j)
+    if (j == a) la = z[j] - lse;
+  act[e] = a;
+  logp[e] = la;
+  value[e] = h[A];
+}
+
+// ================================================================================================
+// Fused PPO loss forward + backward.  One thread per sample; raw sums reduced per CTA
+// and accumulated in double.  The min/max/clamp sub-gradients follow torch autograd exactly (ties split
+// 1/2-1/2, clamp passes the gradient on the closed interval), and the clipped-value arithmetic is done
+// with non-fused fp32 ops in the reference's order so that tie cases fall the same way.
+// ================================================================================================
+__global__ void __launch_bounds__(256) ppo_pbar_kernel(const float* __restrict__ head, int ld_head, int mb, int A,
+                                                       float* pbar_sum) {
+  __shared__ float red[32];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float p[MAX_A];
+#pragma unroll
+  for (int j = 0; j < MAX_A; ++j) p[j] = 0.0f;
+  if (b < mb) {
+    const float* h = head + (int64_t)b * ld_head;
+    float mx = -CUDART_INF_F, se = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) { p[j] = h[j]; mx = fmaxf(mx, p[j]); }
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) { p[j] = expf(p[j] - mx); se += p[j]; }
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j) p[j] = j < A ? p[j] / se : 0.0f;
+  }
+  for (int j = 0; j < A; ++j) {
+    const float s = block_sum(p[j], red);
+    if (threadIdx.x == 0) atomicAdd(pbar_sum + j, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) ppo_loss_kernel(tpp_loss_cfg c, const float* __restrict__ head, int ld_head,
+                                                       const int32_t* __restrict__ act,
+                                                       const float* __restrict__ old_logp,
+                                                       const float* __restrict__ old_value,
+                                                       const float* __restrict__ ret, const float* __restrict__ adv,
+                                                       const float* __restrict__ pbar_sum, float* __restrict__ dhead,
+                                                       double* stats) {
+  __shared__ double red[32];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int A = c.n_actions;
+  const float invB = 1.0f / (float)c.mb;
+  double s_pi = 0.0, s_v = 0.0, s_ent = 0.0;
+  float p[MAX_A];
+#pragma unroll
+  for (int j = 0; j < MAX_A; ++j) p[j] = 0.0f;
+  if (b < c.mb) {
+    const float* h = head + (int64_t)b * ld_head;
+    float l[MAX_A];
+    float mx = -CUDART_INF_F, se = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) { l[j] = h[j]; mx = fmaxf(mx, l[j]); }
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) se += expf(l[j] - mx);
+    const float lse = mx + logf(se);
+    float H = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) { l[j] -= lse; p[j] = expf(l[j]); H -= p[j] * l[j]; }
+    const int a = act[b];
+    float la = 0.0f;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j == a) la = l[j];
+
+    // ---- clipped surrogate (agents/ppo.py:131-135) ----
+    const float Ah = adv[b];
+    const float r = expf(la - old_logp[b]);
+    const float lo = 1.0f - c.eps_clip, hi = 1.0f + c.eps_clip;
+    const float s1 = r * Ah, s2 = fminf(fmaxf(r, lo), hi) * Ah;
+    s_pi = (double)fminf(s1, s2);
+    const float u1 = s1 < s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);
+    const float pass_r = (r >= lo && r <= hi) ? 1.0f : 0.0f;
+    const float dla = -invB * Ah * r * (u1 + (1.0f - u1) * pass_r);   // d pi_loss / d logp_a
+
+    // ---- clipped value error (agents/ppo.py:138-142) ----
+    const float v = h[A], v0 = old_value[b], R = ret[b];
+    const float dvv = __fsub_rn(v, v0);
+    const float vc = __fadd_rn(v0, fminf(fmaxf(dvv, -c.eps_clip), c.eps_clip));
+    const float e1 = __fsub_rn(v, R), e2 = __fsub_rn(vc, R);
+    const float q1 = __fmul_rn(e1, e1), q2 = __fmul_rn(e2, e2);
+    s_v = (double)fmaxf(q1, q2);
+    const float w1 = q1 > q2 ? 1.0f : (q1 == q2 ? 0.5f : 0.0f);
+    const float pass_v = (dvv >= -c.eps_clip && dvv <= c.eps_clip) ? 1.0f : 0.0f;
+    const float dv = c.value_coef * invB * (w1 * e1 + (1.0f - w1) * e2 * pass_v);
+    s_ent = (double)H;
+
+    // ---- logits gradient ----
+    const float ce = c.entropy_coef * c.entropy_multiplier;
+    float xq[MAX_A];
+    float xdot = 0.0f;
+    const bool use_x = (c.x_entropy_coef != 0.0f) && pbar_sum;
+    if (use_x) {
+#pragma unroll
+      for (int j = 0; j < MAX_A; ++j)
+        if (j < A) { xq[j] = logf(pbar_sum[j] * invB) + 1.0f; xdot += p[j] * xq[j]; }
+    }
+    float* dh = dhead + (int64_t)b * ld_head;
+#pragma unroll
+    for (int j = 0; j < MAX_A; ++j)
+      if (j < A) {
+        const float dent = -p[j] * (l[j] + H) * invB;                 // d entropy_mean / d z_j
+        float g = dla * ((j == a ? 1.0f : 0.0f) - p[j]) - ce * dent;
+        if (use_x) {
+          const float dM = -invB * p[j] * (xq[j] - xdot);             // d marg_entropy / d z_j
+          g -= c.x_entropy_coef * (dM - dent);
+        }
+        dh[j] = g;
+      }
+    dh[A] = dv;
+    for (int j = A + 1; j < ld_head; ++j) dh[j] = 0.0f;
+  }
+  s_pi = block_sum(s_pi, red);
+  s_v = block_sum(s_v, red);
+  s_ent = block_sum(s_ent, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 0, s_pi);
+    atomicAdd(stats + 1, s_v);
+    atomicAdd(stats + 2, s_ent);
+    if (blockIdx.x == 0) atomicAdd(stats + 3, (double)c.mb);
+  }
+  for (int j = 0; j < A; ++j) {
+    const double s = block_sum((double)p[j], red);
+    if (threadIdx.x == 0) atomicAdd(stats + 4 + j, s);
+  }
+}
+
+// ================================================================================================
+// Global-norm clip + Adam over one flat fp32 buffer
+// ================================================================================================
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(tpp_adam_state* st, const float* __restrict__ g, int64_t n) {
+  __shared__ double red[32];
+  const float gs = st->grad_scale;
+  const int slot = st->step & 1;   // step is bumped by the Adam kernel, after every CTA here has retired
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = g[i] * gs;
+    s += (double)x * (double)x;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(&st->sqnorm[slot], s);
+}
+
+__global__ void __launch_bounds__(256) adam_clip_kernel(tpp_adam_state* st, float* __restrict__ p,
+                                                        float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, unsigned int* ticket) {
+  const int step0 = st->step;
+  const int slot = step0 & 1;
+  const int t = step0 + 1;
+  const float lr = st->lr, b1 = st->beta1, b2 = st->beta2, eps = st->eps, gs = st->grad_scale;
+  const float total_norm = (float)sqrt(st->sqnorm[slot]);
+  const float coef = fminf(st->max_grad_norm / (total_norm + 1e-6f), 1.0f) * gs;   // clip_grad_norm_ semantics
+  const float bc1 = 1.0f - powf(b1, (float)t);
+  const float bc2_sqrt = sqrtf(1.0f - powf(b2, (float)t));
+  const float step_size = lr / bc1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);               // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;              // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = 0.0f;
+  }
+  // the last CTA to finish publishes step+1 and clears the OTHER accumulator for the next reduction
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    st->sqnorm[slot] = 0.0;
+    st->step = t;
+    *ticket = 0u;
+    __threadfence();
+  }
+}
+
+}  // namespace tpp
+
+extern "C" int tpp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+                            float* C, int64_t ldc, const float* bias, const float* mask, int32_t M, int32_t N,
+                            int32_t K, int32_t flags, int32_t split_k, void* stream) {
+  TPP_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N);
+  TPP_CHECK_ARG(!(flags & TPP_EPI_BIAS) || bias);
+  TPP_CHECK_ARG(!(flags & TPP_EPI_MASK) || mask);
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1 && (!(flags & TPP_EPI_ACCUM) || (flags & (TPP_EPI_RELU | TPP_EPI_MASK)))) return TPP_ENOTSUP;
+  int k_chunk = tpp_ceil_div(tpp_ceil_div(K, split_k), tpp::BK) * tpp::BK;
+  split_k = tpp_ceil_div(K, k_chunk);
+  dim3 grid(tpp_ceil_div(N, tpp::BN), tpp_ceil_div(M, tpp::BM), split_k);
+  tpp::gemm_f32_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(A, sam, sak, B, sbn, sbk, C, ldc, bias, mask, M, N, K,
+                                                            flags, k_chunk);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t N, float* out, void* stream) {
+  TPP_CHECK_ARG(dZ && out && M > 0 && N > 0 && ld >= N);
+  int gy = tpp_ceil_div(M, 8 * 16);
+  if (gy > 64) gy = 64;
+  dim3 grid(tpp_ceil_div(N, 32), gy);
+  tpp::colsum_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(dZ, ld, M, N, out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_sample_actions(const float* head, int32_t ld_head, int32_t n_envs, int32_t n_actions, int32_t* act,
+                                  float* logp, float* value, uint64_t seed, const uint64_t* tick, uint64_t t_offset,
+                                  int32_t greedy, void* stream) {
+  TPP_CHECK_ARG(head && act && logp && value && n_envs > 0 && n_actions > 0 && n_actions <= tpp::MAX_A);
+  TPP_CHECK_ARG(ld_head > n_actions);
+  tpp::sample_kernel<<<tpp_ceil_div(n_envs, 256), 256, 0, tpp_stream(stream)>>>(head, ld_head, n_envs, n_actions, act,
+                                                                                logp, value, seed, tick, t_offset,
+                                                                                greedy);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_ppo_pbar(const float* head, int32_t ld_head, int32_t mb, int32_t n_actions, float* pbar_sum,
+                            void* stream) {
+  TPP_CHECK_ARG(head && pbar_sum && mb > 0 && n_actions > 0 && n_actions <= tpp::MAX_A && ld_head > n_actions);
+  tpp::ppo_pbar_kernel<<<tpp_ceil_div(mb, 256), 256, 0, tpp_stream(stream)>>>(head, ld_head, mb, n_actions, pbar_sum);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_ppo_loss_fwd_bwd(const tpp_loss_cfg* cfg, const float* head, int32_t ld_head, const int32_t* act,
+                                    const float* old_logp, const float* old_value, const float* ret, const float* adv,
+                                    const float* pbar, float* dhead, double* stats, void* stream) {
+  TPP_CHECK_ARG(cfg && head && act && old_logp && old_value && ret && adv && dhead && stats);
+  TPP_CHECK_ARG(cfg->mb > 0 && cfg->n_actions > 0 && cfg->n_actions <= tpp::MAX_A && ld_head > cfg->n_actions);
+  TPP_CHECK_ARG(cfg->x_entropy_coef == 0.0f || pbar);
+  tpp::ppo_loss_kernel<<<tpp_ceil_div(cfg->mb, 256), 256, 0, tpp_stream(stream)>>>(
+      *cfg, head, ld_head, act, old_logp, old_value, ret, adv, pbar, dhead, stats);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n, void* stream) {
+  TPP_CHECK_ARG(state && g && n > 0);
+  int grid = tpp_ceil_div(n, 256 * 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  tpp::grad_sqnorm_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(state, g, n);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n,
+                                  void* stream) {
+  TPP_CHECK_ARG(state && p && g && m && v && n > 0);
+  int grid = tpp_ceil_div(n, 256 * 4);
+  if (grid > 148 * 4) grid = 148 * 4;
+  // the completion ticket lives in the padding word of the device-resident state
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(&state->_pad);
+  tpp::adam_clip_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(state, p, g, m, v, n, ticket);
+  TPP_LAUNCH_STATUS();
+}

@@ -1,0 +1,207 @@
+// Rollout-storage kernels: GAE reverse scan (+ moments), advantage normalisation, minibatch gathers.
+//
+// Replaces (reference, torch CPU): Storage.compute_estimates (common/storage.py:56-79) and
+// Storage.collate_data (common/storage.py:112-128), plus TransposeFrame/ScaledFloatFrame
+// (common/env/procgen_wrappers.py:391-419) folded into the image gather.
+#include "tpp_common.cuh"
+
+namespace tpp {
+
+// ------------------------------------------------------------------------------------------------
+// GAE: one thread per env walks t = T-1 .. 0 (coalesced across the warp: consecutive envs are
+// contiguous in [T][ld]).  The recurrence is two dependent fp32 ops per step; the loads do not depend on
+// it and are issued U steps ahead.  Arithmetic uses explicit non-fused fp32 mul/add/sub in the
+// reference's evaluation order, so the raw advantages and returns are bit-identical to torch CPU:
+//   delta = (rew + (gamma * V[t+1]) * (1 - done)) - V[t]
+//   A     = ((gamma*lambda) * A) * (1 - done) + delta
+// ------------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                  const float* __restrict__ value, float* __restrict__ adv,
+                                                  float* __restrict__ ret, double* moments, int T, int N, int64_t ld,
+                                                  float gamma, float gl) {
+  __shared__ double red[32];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (e < N) {
+    float A = 0.0f;
+    float v_next = value[(int64_t)T * ld + e];
+    int t = T - 1;
+    for (; t >= U - 1; t -= U) {
+      float r[U], v[U];
+      uint8_t d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t o = (int64_t)(t - u) * ld + e;
+        r[u] = __ldcs(rew + o);
+        d[u] = __ldcs(done + o);
+        v[u] = __ldcs(value + o);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float nd = 1.0f - (float)d[u];
+        const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(gamma, v_next), nd)), v[u]);
+        A = __fadd_rn(__fmul_rn(__fmul_rn(gl, A), nd), delta);
+        const int64_t o = (int64_t)(t - u) * ld + e;
+        __stcs(adv + o, A);
+        __stcs(ret + o, __fadd_rn(A, v[u]));
+        s1 += (double)A;
+        s2 += (double)A * (double)A;
+        v_next = v[u];
+      }
+    }
+    for (; t >= 0; --t) {
+      const int64_t o = (int64_t)t * ld + e;
+      const float r = rew[o], v = value[o];
+      const float nd = 1.0f - (float)done[o];
+      const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), nd)), v);
+      A = __fadd_rn(__fmul_rn(__fmul_rn(gl, A), nd), delta);
+      adv[o] = A;
+      ret[o] = __fadd_rn(A, v);
+      s1 += (double)A;
+      s2 += (double)A * (double)A;
+      v_next = v;
+    }
+  }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(moments + 0, s1);
+    atomicAdd(moments + 1, s2);
+    if (blockIdx.x == 0) atomicAdd(moments + 2, (double)T * (double)N);
+  }
+}
+
+__global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const double* moments, int T, int N,
+                                                            int64_t ld) {
+  const double n = moments[2];
+  const double mean_d = moments[0] / n;
+  double var = (moments[1] - moments[0] * mean_d) / (n - 1.0);   // unbiased (torch.std default)
+  var = var > 0.0 ? var : 0.0;
+  const float mean = (float)mean_d;
+  const float denom = (float)sqrt(var) + 1e-8f;
+  const int64_t total = (int64_t)T * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = (i / N) * ld + (i % N);
+    adv[o] = (adv[o] - mean) / denom;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Minibatch gathers.  One thread per (sample, feature) with the feature index fastest, so the row-major
+// output [mb][ld_out] is written fully coalesced; the 4-byte reads from the feature-major rollout are
+// scattered by construction (random sample indices).  Thread (k, 0) also moves the per-sample scalars.
+// ------------------------------------------------------------------------------------------------
+struct GatherScalars {
+  const int32_t* act; const float* logp; const float* value; const float* ret; const float* adv; const uint8_t* done;
+  int32_t* o_act; float* o_logp; float* o_value; float* o_ret; float* o_adv; float* o_done;
+};
+
+__device__ __forceinline__ void gather_scalars(const GatherScalars& g, int64_t src, int k) {
+  if (g.o_act) g.o_act[k] = g.act[src];
+  if (g.o_logp) g.o_logp[k] = g.logp[src];
+  if (g.o_value) g.o_value[k] = g.value[src];
+  if (g.o_ret) g.o_ret[k] = g.ret[src];
+  if (g.o_adv) g.o_adv[k] = g.adv[src];
+  if (g.o_done) g.o_done[k] = (float)g.done[src];
+}
+
+__global__ void __launch_bounds__(256) gather_vec_kernel(const int64_t* __restrict__ idx, int mb, int N, int64_t ld,
+                                                         int n_obs, const float* __restrict__ obs, GatherScalars g,
+                                                         float* __restrict__ out_obs, int ld_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)mb * ld_out) return;
+  const int k = (int)(i / ld_out), j = (int)(i % ld_out);
+  const int64_t flat = idx[k];
+  const int64_t t = flat / N, e = flat % N;
+  out_obs[i] = j < n_obs ? obs[(t * n_obs + j) * ld + e] : 0.0f;
+  if (j == 0) gather_scalars(g, t * ld + e, k);
+}
+
+// frames uint8 NHWC -> float NCHW / 255.  One CTA (128 threads) per sample: the H*W*C contiguous bytes of
+// the frame are staged through shared memory with 4-byte loads, then written channel-major.
+__global__ void __launch_bounds__(128) gather_img_kernel(const int64_t* __restrict__ idx, int mb, int N, int HW, int C,
+                                                         const uint8_t* __restrict__ frames, GatherScalars g,
+                                                         float* __restrict__ out_obs, int ld_out) {
+  extern __shared__ uint8_t px[];
+  const int k = blockIdx.x;
+  const int64_t flat = idx ? idx[k] : k;
+  const int bytes = HW * C;
+  const uint8_t* src = frames + flat * bytes;      // flat = t*N + e indexes [T+1][N] frames directly
+  if ((bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+    for (int w = threadIdx.x; w < bytes / 4; w += blockDim.x)
+      reinterpret_cast<uint32_t*>(px)[w] = reinterpret_cast<const uint32_t*>(src)[w];
+  } else {
+    for (int b = threadIdx.x; b < bytes; b += blockDim.x) px[b] = src[b];
+  }
+  __syncthreads();
+  float* dst = out_obs + (int64_t)k * ld_out;
+  for (int o = threadIdx.x; o < ld_out; o += blockDim.x) {
+    float v = 0.0f;
+    if (o < bytes) {
+      const int c = o / HW, p = o % HW;
+      v = (float)px[p * C + c] / 255.0f;
+    }
+    dst[o] = v;
+  }
+  if (threadIdx.x == 0 && idx) gather_scalars(g, flat, k);
+}
+
+}  // namespace tpp
+
+extern "C" int tpp_gae(const float* rew, const uint8_t* done, const float* value, float* adv, float* ret,
+                       double* moments, int32_t T, int32_t N, int64_t ld, float gamma, float lambda, void* stream) {
+  TPP_CHECK_ARG(rew && done && value && adv && ret && moments && T > 0 && N > 0 && ld >= N);
+  // (gamma*lambda) is formed in double and rounded once, as python does before it meets the fp32 tensor
+  const float gl = (float)((double)gamma * (double)lambda);
+  const int grid = tpp_ceil_div(N, 128);
+  tpp::gae_kernel<8><<<grid, 128, 0, tpp_stream(stream)>>>(rew, done, value, adv, ret, moments, T, N, ld, gamma, gl);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream) {
+  TPP_CHECK_ARG(adv && moments && T > 0 && N > 0 && ld >= N);
+  const int64_t total = (int64_t)T * N;
+  int grid = tpp_ceil_div(total, 256 * 4);
+  if (grid > 148 * 16) grid = 148 * 16;
+  tpp::adv_normalize_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(adv, moments, T, N, ld);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_gather_vec(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t n_obs, const float* obs,
+                              const int32_t* act, const float* logp, const float* value, const float* ret,
+                              const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out,
+                              int32_t* out_act, float* out_logp, float* out_value, float* out_ret, float* out_adv,
+                              float* out_done, void* stream) {
+  TPP_CHECK_ARG(idx && obs && out_obs && mb > 0 && N > 0 && ld >= N && n_obs > 0 && ld_out >= n_obs);
+  tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
+  const int64_t total = (int64_t)mb * ld_out;
+  tpp::gather_vec_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(idx, mb, N, ld, n_obs, obs, g,
+                                                                                   out_obs, ld_out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int32_t H, int32_t W, int32_t C,
+                              const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
+                              const float* ret, const float* adv, const uint8_t* done, float* out_obs,
+                              int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value, float* out_ret,
+                              float* out_adv, float* out_done, void* stream) {
+  TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && H > 0 && W > 0 && C > 0 && ld_out >= H * W * C);
+  const int bytes = H * W * C;
+  TPP_CHECK_ARG(bytes <= 48 * 1024);
+  tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
+  tpp::gather_img_kernel<<<mb, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(idx, mb, N, H * W, C, frames, g, out_obs,
+                                                                            ld_out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
+                                 int32_t ld_out, void* stream) {
+  TPP_CHECK_ARG(frames && out_obs && N > 0 && ld_out >= H * W * C);
+  const int bytes = H * W * C;
+  TPP_CHECK_ARG(bytes <= 48 * 1024);
+  tpp::GatherScalars g{};
+  tpp::gather_img_kernel<<<N, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(nullptr, N, N, H * W, C, frames, g, out_obs,
+                                                                           ld_out);
+  TPP_LAUNCH_STATUS();
+}
