@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the PPO rollout-and-update hot path (BASELINE.json metric: PPO env-steps/sec, rollout+GAE+update).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload boxworld|cartpole]
+
+One "step" = one full PPO iteration: T fused rollout steps over the rank's envs (policy forward -> Philox action
+sampling -> env step kernel writing into the rollout), bootstrap value, GAE + advantage normalisation, and
+`epoch` x minibatch updates (device gather -> policy fwd -> fused loss fwd+bwd -> policy bwd -> clip+Adam).
+
+Default workload = BASELINE.json configs[1]: boxworld_env_vec PPO, n_envs=4096 per GPU (weak scaling), grid 12,
+goal 5, 3x3 distractors, 500-level bank, T=256, 3 epochs, n_minibatch 8, mini_batch_size 8192 (the reference's
+`boxworld-impala` YAML set, hyperparams/procgen/config.yml:575-601), with an MLP policy on the flattened
+3x14x14 frame (the reference has no working Box-World policy; choice documented in DESIGN.md).
+
+Prints ONE JSON line (rank 0).  `value` = device-timed iterations with inputs resident (minibatch permutations
+pre-uploaded); `e2e` = the same iterations through the public API `PPO.train()` with per-epoch index upload from
+pinned host memory and device->host reads of the loss summary and the logger's reward/done batches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # reference YAML set `boxworld-impala` (config.yml:575-601) at BASELINE configs[1]'s n_envs
+    "boxworld": dict(n_envs=4096, n_steps=256, epoch=3, n_minibatch=8, mini_batch_size=8192, gamma=0.999, lmbda=0.95,
+                     learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.01,
+                     grid_size=12, goal_length=5, num_distractor=3, distractor_length=3, max_steps=1000,
+                     normalize_rew=True, depth=4, mid_weight=256, latent_size=64),
+    # reference YAML set `cartpole` (config.yml:972-995): BASELINE configs[0], the reference's CPU-runnable case
+    "cartpole": dict(n_envs=256, n_steps=256, epoch=3, n_minibatch=16, mini_batch_size=8192, gamma=0.99, lmbda=0.95,
+                     learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.02,
+                     depth=4, mid_weight=256, latent_size=64),
+}
+PPO_KEYS = ("n_steps", "n_envs", "epoch", "n_minibatch", "mini_batch_size", "gamma", "lmbda", "learning_rate",
+            "grad_clip_norm", "eps_clip", "value_coef", "entropy_coef")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# Our arm
+# --------------------------------------------------------------------------------------------------
+
+def build_agent(name, hp, rank, device):
+    from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    from tpp_b200.common.storage import Storage
+    N, T = hp["n_envs"], hp["n_steps"]
+    if name == "boxworld":
+        from tpp_b200.boxworld.box_world_env_vec import create_bw_env
+
+        class A:
+            seed, num_levels = 6033 + 1000 * rank, 500
+        env = create_bw_env(A, dict(hp, device=device))
+        obs_shape = env.observation_space.shape
+    else:
+        from tpp_b200.discrete_env.cartpole_pre_vec import create_cartpole
+
+        class A:
+            seed = 6033 + rank
+        env = create_cartpole(A, dict(hp, device=device))
+        obs_shape = env.observation_space.shape
+    in_dim = int(np.prod(obs_shape))
+    torch.manual_seed(6033)                      # identical initial weights on every rank
+    pol = CategoricalPolicy(MLPModel(in_dim, hp["depth"], hp["mid_weight"], hp["latent_size"]), False,
+                            env.action_space.n).to(device).flatten_()
+    st = Storage(obs_shape, hp["latent_size"], T, N, device)
+    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank)
+    return agent, in_dim
+
+
+def time_kernel(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3     # seconds per launch
+
+
+def kernel_rooflines(pk, device):
+    """Live CUDA-event timings of the HBM-bound kernels on inputs larger than L2 (126 MB), achieved = algorithmic
+    bytes (SURVEY 8d per-unit figures) / time."""
+    from tpp_b200 import _lib
+    from tpp_b200.common.storage import Storage
+    from tpp_b200.discrete_env.acrobot_pre_vec import AcrobotVecEnv
+    from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    from tpp_b200.discrete_env.mountain_car_pre_vec import MountainCarVecEnv
+    out = []
+    N = 1 << 22
+    for cls, bytes_per_step in ((CartPoleVecEnv, 89), (MountainCarVecEnv, 57), (AcrobotVecEnv, 137)):
+        env = cls(n_envs=N, seed=1, device=device)
+        act = torch.randint(0, env.n_actions, (N,), device=device, dtype=torch.int32)
+        state = {"cur": 0}
+
+        def step():
+            c = state["cur"]
+            env.step_into(env._slots[c], env._slots[c ^ 1], act, env._rew, env._done)
+            state["cur"] = c ^ 1
+        dt = time_kernel(step, iters=30)
+        gbs = bytes_per_step * N / dt / 1e9
+        out.append(dict(kernel=f"env_step_{env.family}", n_envs=N, bytes_per_unit=bytes_per_step, bound="hbm",
+                        achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                        env_steps_per_s=round(N / dt, 1)))
+        del env
+    T, Ng = 256, 1 << 16
+    st = Storage((1,), 1, T, Ng, device)
+    st.rew.normal_(); st.value.normal_()
+    st.done_u8.copy_((torch.rand(T, Ng, device=device) < 0.02).to(torch.uint8))
+    dt = time_kernel(lambda: st.compute_estimates(0.99, 0.95, True, True), iters=10)
+    gbs = 25 * T * Ng / dt / 1e9
+    out.append(dict(kernel="gae_scan+adv_normalize", T=T, n_envs=Ng, bytes_per_unit=25, bound="hbm",
+                    achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4)))
+    torch.cuda.empty_cache()
+    return out
+
+
+def gemm_roofline(agent, in_dim, hp, pk):
+    """The dominant kernel of the PPO iteration: the policy's dense layers.  Timed live: forward+backward of the
+    policy on one minibatch (the kernels the update loop launches), FLOPs = 6 * MACs * mb (fwd + dgrad + wgrad)."""
+    mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
+    eng = agent.engine
+    x = torch.randn(mb, in_dim, device=agent.policy.flat.device)
+    dhead = torch.randn(mb, eng.ld_head, device=x.device) / mb
+
+    def fb():
+        eng.forward(x, mb)
+        eng.backward(dhead, mb)
+    dt = time_kernel(fb, iters=10)
+    agent.policy.flat_grad.zero_()
+    macs = sum(l[2] * l[3] for l in eng.layers) + eng.latent * (eng.A + 1)
+    flops = 6.0 * macs * mb - 2.0 * eng.layers[0][2] * eng.layers[0][3] * mb    # no dgrad for the first layer
+    tf = flops / dt / 1e12
+    return dict(kernel="policy_mlp_fwd_bwd", bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
+                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=None, minibatch=mb,
+                note="exact-fp32 path; peak = measured dense bf16 cuBLAS (" + pk["source"] + ")")
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    hp = dict(WORKLOADS[args.workload])
+    agent, in_dim = build_agent(args.workload, hp, rank, device)
+    if world > 1:
+        agent.shard(world)
+    N, T = hp["n_envs"], hp["n_steps"]
+    st, env = agent.storage, agent.env
+
+    def counters():
+        return agent.n_launches + agent.engine.n_launches + st.n_launches + agent.optimizer.n_launches
+
+    def iteration():
+        agent.collect_rollout(env, st)
+        st.compute_estimates(agent.gamma, agent.lmbda, True, True)
+        agent.optimize()
+        agent._carry_over(st)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: minibatch permutations pre-generated and pre-uploaded -------------------
+    env.reset_rollout(st)
+    mb = min(hp["mini_batch_size"], T * N // hp["n_minibatch"])
+    n_perm = hp["epoch"] * (args.warmup + args.steps + 2)
+    pre = [torch.randperm(T * N)[:(T * N) // mb * mb].view(-1, mb).to(device) for _ in range(hp["epoch"])]
+    real_epoch_indices = st.epoch_indices
+    cyc = {"i": 0}
+
+    def resident_indices(_mb):
+        cyc["i"] += 1
+        return pre[cyc["i"] % len(pre)]
+    st.epoch_indices = resident_indices
+    for _ in range(max(args.warmup, 3)):
+        iteration()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        iteration()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = counters() - l0
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end to end through the public API: PPO.train() with host-side index generation + upload + readbacks -
+    st.epoch_indices = real_epoch_indices
+
+    class NullLogger:      # the reference's Logger consumes (rew_batch, done_batch) on the host every iteration
+        logdir = None
+        episode_reward_buffer = [0.0]
+
+        def feed(self, *a):
+            self.n = sum(x.size for x in a[:2])
+
+        def dump(self, *a):
+            pass
+    agent.logger = NullLogger()
+    agent.t = 0
+    agent.train(T * N * 2)                              # warm the API path (graph already captured)
+    barrier()
+    agent.t = 0
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    agent.train(T * N * args.steps)
+    t1.record()
+    barrier()
+    wall = time.perf_counter() - w0
+    ms_e2e = max(t0.elapsed_time(t1), wall * 1e3)
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = times.tolist()
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    pk = peaks()
+    total_steps = N * T * args.steps * world
+    value = total_steps / (ms * 1e-3)
+    e2e_value = total_steps / (ms_e2e * 1e-3)
+    n_mb = (T * N) // mb
+    h2d = hp["epoch"] * n_mb * mb * 8 + 8
+    d2h = hp["epoch"] * n_mb * 20 * 8 + 2 * T * N * 4
+    roof = gemm_roofline(agent, in_dim, hp, pk)
+    extra = kernel_rooflines(pk, device) if not args.no_kernel_rooflines else []
+    cpu = cpu_baseline(args.workload, budget_s=20.0) if not args.no_cpu_baseline else None
+    line = {
+        "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(value, 1), "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}_env_vec PPO: n_envs={N}/GPU, n_steps={T}, "
+                               f"epoch={hp['epoch']}, minibatch={mb}, MLP policy {in_dim}-256-256-256-64 (fp32)",
+                   "parallelism": f"env-sharded dp{world}", "l2": "rollout + minibatch working set > L2 (inputs "
+                   "larger than 126 MB)" if args.workload == "boxworld" else "small working set (latency-bound)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
+                "api": "PPO.train(): host randperm -> pinned H2D per epoch; D2H loss summary + logger batches"},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernel_rooflines": extra,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's numpy/torch path (the reference itself is Python and cannot
+# travel to the GPU box; oracle/* restates it and is pinned against it bit-for-bit, see tests/)
+# --------------------------------------------------------------------------------------------------
+
+def _cpu_setup(name, n_envs, n_steps):
+    from oracle import boxworld as obw
+    from oracle import ppo as oppo
+    from oracle.prevec import OraclePreVec
+    hp = dict(WORKLOADS[name], n_envs=n_envs, n_steps=n_steps)
+    torch.manual_seed(6033)
+    if name == "boxworld":
+        env = obw.BoxWorldOracle(n_envs, hp["grid_size"], hp["goal_length"], hp["num_distractor"],
+                                 hp["distractor_length"], max_steps=hp["max_steps"], start_seed=6033, n_levels=500)
+        vn = obw.VecNormalizeOracle(n_envs)
+
+        def env_step(a):
+            w, r, d = env.step(a)
+            return w, vn.step(r.astype(np.float64), d), d
+        tf = lambda w: obw.frame_to_obs(w).reshape(n_envs, -1)
+        obs0, in_dim, A = env.world, 3 * (hp["grid_size"] + 2) ** 2, 4
+    else:
+        env = OraclePreVec("cartpole", n_envs, seed=6033)
+        env.reset()
+
+        def env_step(a):
+            return env.step(a)
+        tf, obs0, in_dim, A = None, env.obs(), 9, 2
+    pol = oppo.OraclePolicy(oppo.OracleMLP(in_dim, hp["depth"], hp["mid_weight"], hp["latent_size"]), A)
+    opt = oppo.make_adam(pol, hp["learning_rate"])
+    kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
+              grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
+              entropy_coef=hp["entropy_coef"])
+
+    def iteration(obs):
+        obs, _ = oppo.ppo_iteration(env_step, obs, pol, opt, n_steps, n_envs, hp["gamma"], hp["lmbda"],
+                                    obs_transform=tf, **kw)
+        return obs
+    return iteration, obs0
+
+
+def cpu_baseline(name, budget_s=20.0, steps=None):
+    """Time the oracle port on the host cores on a bounded sample of the same workload."""
+    n_envs, n_steps = (256, 64) if name == "boxworld" else (256, 256)
+    iteration, obs = _cpu_setup(name, n_envs, n_steps)
+    obs = iteration(obs)                     # warm-up
+    t0, k = time.perf_counter(), 0
+    while True:
+        obs = iteration(obs)
+        k += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and k >= steps) or (steps is None and (el > budget_s or k >= 50)):
+            break
+    return {"value": round(n_envs * n_steps * k / el, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(),
+            "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{k} PPO iterations of the oracle port at n_envs={n_envs}, n_steps={n_steps} "
+                      f"(same hyperparameters, minibatch clamped); numpy env step is single-threaded, torch uses "
+                      f"{torch.get_num_threads()} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    hp = WORKLOADS[args.workload]
+    n_envs, n_steps = (256, 64) if args.workload == "boxworld" else (256, 256)
+    iteration, obs = _cpu_setup(args.workload, n_envs, n_steps)
+    for _ in range(max(1, min(args.warmup, 2))):
+        obs = iteration(obs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        obs = iteration(obs)
+    el = time.perf_counter() - t0
+    value = n_envs * n_steps * args.steps / el
+    cpu = {"value": round(value, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"{args.steps} PPO iterations at n_envs={n_envs}, n_steps={n_steps} on the host CPU"}
+    print(json.dumps({
+        "impl": "reference", "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(value, 1),
+        "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}_env_vec PPO (CPU port of the reference path, bounded sample "
+                               f"n_envs={n_envs}, n_steps={n_steps}; hyperparameters of the GPU arm)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="boxworld", choices=list(WORKLOADS))
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs only)")
+    ap.add_argument("--only-kernel-rooflines", action="store_true", help="time just the HBM-bound kernels")
+    args = ap.parse_args()
+    if args.only_kernel_rooflines:
+        print(json.dumps(kernel_rooflines(peaks(), "cuda:0")))
+    elif args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

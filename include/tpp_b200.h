@@ -62,9 +62,7 @@ typedef struct {
  * done_out holds the PRE-reset flag, obs_out the POST-reset observation (reference semantics).
  * reset_rows: NULL -> start states drawn in-kernel from Philox(seed, env, tick); otherwise feature-major
  * [n_state][ld] rows used for the finished envs (teacher forcing for parity tests).
- * tick: device counter mixed into the Philox counter (may be NULL -> 0); t_offset is added to it.
- * ep_ret/ep_len (nullable): device-side episode accounting (running return / length per env);
- * fin_ret/fin_len (nullable, [N]): return/length of the episode that finished at this step, else NaN/-1.  */
+ * tick: device counter mixed into the Philox counter (may be NULL -> 0); t_offset is added to it.            */
 int tpp_env_step(const tpp_env_cfg* cfg, const float* obs_in, float* obs_out, float* dyn_state,
                  const int32_t* action, int32_t* step_ctr, float* rew_out, uint8_t* done_out,
                  const float* reset_rows, const uint64_t* tick, uint64_t t_offset, int64_t ld, void* stream);
@@ -205,13 +203,15 @@ int tpp_ppo_pbar(const float* head, int32_t ld_head, int32_t mb, int32_t n_actio
 
 /* ---- optimizer ------------------------------------------------------------------------------------------ */
 typedef struct {
-  float lr, beta1, beta2, eps, max_grad_norm, grad_scale; /* grad_scale: 1/world_size after all-reduce    */
-  int32_t step;       /* number of optimizer steps taken so far (device-resident copy is authoritative)   */
-  int32_t _pad;
-  double sqnorm[2];   /* ping-pong accumulators of sum g^2                                                */
+  double lr, beta1, beta2, eps;      /* python floats of torch.optim.Adam (kept in double: torch forms 1-beta and
+                                        the bias corrections in double before they meet the fp32 tensors)       */
+  float max_grad_norm, grad_scale;   /* grad_scale: 1/world_size after the gradient all-reduce                   */
+  int32_t step;       /* optimizer steps taken so far; bumped by tpp_adam_clip_step                               */
+  int32_t ticket;     /* completion counter of the Adam kernel (must start at 0)                                   */
+  double sqnorm[2];   /* ping-pong accumulators of sum (grad_scale*g)^2                                            */
 } tpp_adam_state;     /* lives in DEVICE memory; host updates lr with a small memcpy                      */
 
-/* sqnorm[(step)&1] += sum (grad_scale*g)^2 ; thread 0 also bumps state->step.                            */
+/* sqnorm[step & 1] += sum (grad_scale*g)^2.                                                               */
 int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n, void* stream);
 /* clip_grad_norm_(max_grad_norm) + Adam(lr, betas, eps) + zero grad over flat buffers, one pass.
  * Replaces agents/ppo.py:173-176 (torch.nn.utils.clip_grad_norm_, optim.Adam(eps=1e-5)).                 */

@@ -175,7 +175,7 @@ def optimize(policy, optimizer, data, n_steps, n_envs, epoch=3, n_minibatch=8, m
                 optimizer.step()
                 optimizer.zero_grad()
             cnt += 1
-            logs.append({k: float(v) for k, v in terms.items()})
+            logs.append({k: float(v.detach()) for k, v in terms.items()})
     return logs
 
 

@@ -40,8 +40,8 @@ class LossCfg(C.Structure):
 
 
 class AdamState(C.Structure):   # mirrors tpp_adam_state (lives in device memory; this is the host image)
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("ticket", C.c_int32),
                 ("sqnorm", C.c_double * 2)]
 
 

@@ -50,18 +50,19 @@ class FlatAdam:
                               grad_scale=1.0, step=0)
         raw = bytes(host)
         self.state = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.flat.device)
-        self._f32 = self.state.view(torch.float32)
-        self._i32 = self.state.view(torch.int32)
+        self._f64 = self.state.view(torch.float64)    # [lr, beta1, beta2, eps, (f32 pair), (i32 pair), sqnorm x2]
+        self._f32 = self.state.view(torch.float32)    # max_grad_norm @8, grad_scale @9
+        self._i32 = self.state.view(torch.int32)      # step @10, ticket @11
         self._lr_on_device = lr
         self.n_launches = 0
 
     def set_grad_scale(self, s):
-        self._f32[5:6].copy_(torch.tensor([s], dtype=torch.float32))
+        self._f32[9:10].copy_(torch.tensor([s], dtype=torch.float32))
 
     def _sync_lr(self):
         lr = float(self.param_groups[0]["lr"])
         if lr != self._lr_on_device:
-            self._f32[0:1].copy_(torch.tensor([lr], dtype=torch.float32), non_blocking=True)
+            self._f64[0:1].copy_(torch.tensor([lr], dtype=torch.float64), non_blocking=True)
             self._lr_on_device = lr
 
     def step(self):
@@ -74,7 +75,7 @@ class FlatAdam:
 
     @property
     def step_count(self):
-        return int(self._i32[6].item())
+        return int(self._i32[10].item())
 
     def state_dict(self):
         state, names = {}, [n for n, _ in self.policy.named_parameters()]
@@ -97,7 +98,7 @@ class FlatAdam:
                 self.m[off:off + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
                 self.v[off:off + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
                 step = int(sd["state"][i]["step"])
-        self._i32[6:7].copy_(torch.tensor([step], dtype=torch.int32))
+        self._i32[10:11].copy_(torch.tensor([step], dtype=torch.int32))
         self.param_groups[0]["lr"] = sd["param_groups"][0]["lr"]
 
 

@@ -308,19 +308,29 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(tpp_adam_state* st, co
 __global__ void __launch_bounds__(256) adam_clip_kernel(tpp_adam_state* st, float* __restrict__ p,
                                                         float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n, unsigned int* ticket) {
+  __shared__ float sc[6];
   const int step0 = st->step;
   const int slot = step0 & 1;
   const int t = step0 + 1;
-  const float lr = st->lr, b1 = st->beta1, b2 = st->beta2, eps = st->eps, gs = st->grad_scale;
-  const float total_norm = (float)sqrt(st->sqnorm[slot]);
-  const float coef = fminf(st->max_grad_norm / (total_norm + 1e-6f), 1.0f) * gs;   // clip_grad_norm_ semantics
-  const float bc1 = 1.0f - powf(b1, (float)t);
-  const float bc2_sqrt = sqrtf(1.0f - powf(b2, (float)t));
-  const float step_size = lr / bc1;
+  if (threadIdx.x == 0) {
+    // scalars are formed in double exactly as torch's python code does, then rounded once to fp32
+    const double b1 = st->beta1, b2 = st->beta2;
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    const float total_norm = (float)sqrt(st->sqnorm[slot]);
+    sc[0] = fminf(st->max_grad_norm / (total_norm + 1e-6f), 1.0f) * st->grad_scale;   // clip_grad_norm_ semantics
+    sc[1] = (float)(1.0 - b1);
+    sc[2] = (float)b2;
+    sc[3] = (float)(1.0 - b2);
+    sc[4] = (float)(st->lr / bc1);          // step_size
+    sc[5] = (float)sqrt(bc2);               // bias_correction2_sqrt
+  }
+  __syncthreads();
+  const float coef = sc[0], omb1 = sc[1], b2 = sc[2], omb2 = sc[3], step_size = sc[4], bc2_sqrt = sc[5];
+  const float eps = (float)st->eps;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * coef;
-    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);               // exp_avg.lerp_(grad, 1-beta1)
-    const float vi = v[i] * b2 + (1.0f - b2) * gi * gi;              // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float mi = m[i] + (gi - m[i]) * omb1;                     // exp_avg.lerp_(grad, 1-beta1)
+    const float vi = v[i] * b2 + omb2 * gi * gi;                     // mul_(beta2).addcmul_(g, g, 1-beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = p[i] - step_size * (mi / denom);
     m[i] = mi;
@@ -410,8 +420,7 @@ extern "C" int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, flo
   TPP_CHECK_ARG(state && p && g && m && v && n > 0);
   int grid = tpp_ceil_div(n, 256 * 4);
   if (grid > 148 * 4) grid = 148 * 4;
-  // the completion ticket lives in the padding word of the device-resident state
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(&state->_pad);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(&state->ticket);
   tpp::adam_clip_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(state, p, g, m, v, n, ticket);
   TPP_LAUNCH_STATUS();
 }
