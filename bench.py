@@ -118,7 +118,8 @@ def build_agent(name, hp, rank, device):
     pol = CategoricalPolicy(MLPModel(in_dim, hp["depth"], hp["mid_weight"], hp["latent_size"]), False,
                             env.action_space.n).to(device).flatten_()
     st = Storage(obs_shape, hp["latent_size"], T, N, device)
-    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank)
+    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank,
+                matmul=hp.get("matmul", "tf32x3"))
     return agent, in_dim
 
 
@@ -173,24 +174,45 @@ def kernel_rooflines(pk, device):
 
 
 def gemm_roofline(agent, in_dim, hp, pk):
-    """The dominant kernel of the PPO iteration: the policy's dense layers.  Timed live: forward+backward of the
-    policy on one minibatch (the kernels the update loop launches), FLOPs = 6 * MACs * mb (fwd + dgrad + wgrad)."""
+    """Roofline of the dominant kernel of the PPO iteration: the policy's dense-layer GEMM.  Timed live with CUDA
+    events on the launching stream: the largest layer of the update (layer 1 forward, M = minibatch, N = 256,
+    K = in_dim) launched alone, algorithmic FLOPs = 2*M*N*K per launch (the 3xTF32 split passes are overhead, not
+    algorithmic work), against the measured dense bf16 tensor peak.  Also reports the whole policy forward+backward
+    (all its launches) in TFLOP/s."""
+    from tpp_b200.common.engine import MLPEngineTC
+    from tpp_b200._lib import EPI_BIAS, EPI_RELU, ptr
     mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
     eng = agent.engine
-    x = torch.randn(mb, in_dim, device=agent.policy.flat.device)
+    ld = (in_dim + 3) // 4 * 4
+    x = torch.randn(mb, ld, device=agent.policy.flat.device)[:, :in_dim]
     dhead = torch.randn(mb, eng.ld_head, device=x.device) / mb
 
     def fb():
         eng.forward(x, mb)
         eng.backward(dhead, mb)
-    dt = time_kernel(fb, iters=10)
+    dt_all = time_kernel(fb, iters=10)
     agent.policy.flat_grad.zero_()
     macs = sum(l[2] * l[3] for l in eng.layers) + eng.latent * (eng.A + 1)
-    flops = 6.0 * macs * mb - 2.0 * eng.layers[0][2] * eng.layers[0][3] * mb    # no dgrad for the first layer
-    tf = flops / dt / 1e12
-    return dict(kernel="policy_mlp_fwd_bwd", bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
-                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=None, minibatch=mb,
-                note="exact-fp32 path; peak = measured dense bf16 cuBLAS (" + pk["source"] + ")")
+    flops_all = 6.0 * macs * mb - 2.0 * eng.layers[0][2] * eng.layers[0][3] * mb    # no dgrad for the first layer
+    w_off, b_off, fin, fout, relu = eng.layers[0]
+    ws = eng._workspace(mb)
+    if isinstance(eng, MLPEngineTC):
+        w, h = eng.w[0], ws.h[0]
+        one = lambda: eng._tc((ws.x["hi"], ws.x["lo"]), eng.ld_in, (w["hi"], w["lo"]), w["ldk"], mb, fout, fin,
+                              flags=EPI_BIAS | EPI_RELU, bias=eng._p(b_off), out_pair=(h["hi"], h["lo"]), ldc=h["ld"])
+        name = "gemm_tc_kernel<128> (tcgen05 kind::tf32, %s)" % ("3xTF32" if eng.precision == 3 else "1xTF32")
+    else:
+        one = lambda: eng._gemm(ptr(x), x.stride(0), 1, eng._p(w_off), fin, 1, ptr(ws.acts[0]), fout, eng._p(b_off),
+                                None, mb, fout, fin, EPI_BIAS | EPI_RELU)
+        name = "gemm_f32_kernel (CUDA cores, exact fp32)"
+    dt = time_kernel(one, iters=50)
+    tf = 2.0 * mb * fout * fin / dt / 1e12
+    return dict(kernel=name, shape=[mb, fout, fin], bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
+                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=None, us_per_launch=round(dt * 1e6, 2),
+                policy_fwd_bwd_tflops=round(flops_all / dt_all / 1e12, 2),
+                policy_fwd_bwd_us=round(dt_all * 1e6, 1),
+                note="peak = dense bf16 cuBLAS (" + pk["source"] + "); a TF32 kernel tops out at 1/2 of it, the "
+                     "fp32-parity 3xTF32 mode at 1/6")
 
 
 def run_ours(args):
@@ -203,7 +225,7 @@ def run_ours(args):
     device = f"cuda:{local}"
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    hp = dict(WORKLOADS[args.workload])
+    hp = dict(WORKLOADS[args.workload], matmul=args.matmul)
     agent, in_dim = build_agent(args.workload, hp, rank, device)
     if world > 1:
         agent.shard(world)
@@ -244,15 +266,21 @@ def run_ours(args):
         clocks.start()
     l0 = counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the timed region
     e0.record()
     for _ in range(args.steps):
         iteration()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = counters() - l0
     clk = clocks.stop() if rank == 0 else None
 
+    if args.timed_region_only:
+        if rank == 0:
+            print(json.dumps({"ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
+        return
     # ---- end to end through the public API: PPO.train() with host-side index generation + upload + readbacks -
     st.epoch_indices = real_epoch_indices
 
@@ -410,8 +438,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="boxworld", choices=list(WORKLOADS))
+    ap.add_argument("--matmul", default="tf32x3", choices=["tf32x3", "tf32", "fp32"],
+                    help="dense-layer arithmetic: tcgen05 3xTF32 (fp32-parity, default), tcgen05 single TF32, CUDA-core fp32")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs only)")
+    ap.add_argument("--timed-region-only", action="store_true", help="stop after the device-timed loop (ncu runs)")
     ap.add_argument("--only-kernel-rooflines", action="store_true", help="time just the HBM-bound kernels")
     args = ap.parse_args()
     if args.only_kernel_rooflines:

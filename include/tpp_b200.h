@@ -145,21 +145,23 @@ int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, i
  * zero-filled).  out_* arrays are [mb].  idx: int64 [mb] (from torch.randperm on the host: bit-exact).    */
 int tpp_gather_vec(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t n_obs, const float* obs,
                    const int32_t* act, const float* logp, const float* value, const float* ret,
-                   const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out, int32_t* out_act,
-                   float* out_logp, float* out_value, float* out_ret, float* out_adv, float* out_done,
-                   void* stream);
+                   const float* adv, const uint8_t* done, float* out_obs, float* out_obs_lo, int32_t ld_out,
+                   int32_t* out_act, float* out_logp, float* out_value, float* out_ret, float* out_adv,
+                   float* out_done, void* stream);
+/* out_obs_lo (both gathers, nullable): when given, out_obs receives tf32_round(x) and out_obs_lo the residual, i.e.
+ * the (hi, lo) operand pair of tpp_gemm_tc is produced by the gather itself.                                  */
 
 /* Image observations: frames uint8 NHWC [T+1][N][H][W][C] -> out_obs float32 NCHW [mb][C][H][W] / 255
  * (TransposeFrame + ScaledFloatFrame, common/env/procgen_wrappers.py:391-419, applied at gather time).    */
-int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int32_t H, int32_t W, int32_t C,
+int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t H, int32_t W, int32_t C,
                    const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
-                   const float* ret, const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out,
-                   int32_t* out_act, float* out_logp, float* out_value, float* out_ret, float* out_adv,
-                   float* out_done, void* stream);
+                   const float* ret, const float* adv, const uint8_t* done, float* out_obs, float* out_obs_lo,
+                   int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value, float* out_ret,
+                   float* out_adv, float* out_done, void* stream);
 
 /* uint8 NHWC frames of one rollout slot -> float32 NCHW/255 rows [N][ld_out] (policy input at rollout).   */
 int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
-                      int32_t ld_out, void* stream);
+                      float* out_obs_lo, int32_t ld_out, void* stream);
 
 /* ---- policy: dense layers ------------------------------------------------------------------------------ */
 /* C[m][n] (+)= epilogue( sum_k A(m,k) * B(n,k) ), fp32 in / fp32 accumulate, generic strides:
@@ -175,6 +177,39 @@ int tpp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64
 
 /* out[n] += sum_m dZ[m*ld + n]   (bias gradient).                                                        */
 int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t N, float* out, void* stream);
+
+/* Tensor-core dense layer (tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed, csrc/gemm_tc.cu):
+ *   C[m][n] = epilogue( sum_k A(m,k) * B(n,k) ).
+ * Operand layouts: K-major (a_mn/b_mn = 0): matrix [M or N rows][ld], contraction index contiguous;
+ *                  MN-major (= 1): matrix [K rows][ld], m / n index contiguous, ld >= ceil32(M or N).
+ * So forward (X[mb][in], W[out][in]: K,K), data gradient (dZ[mb][out] K-major, W[out][in] MN-major) and weight
+ * gradient (dZ[mb][out], X[mb][in]: MN,MN, contraction over mb) all read the SAME row-major arrays.
+ * Every operand is a (hi, lo) pair of fp32 arrays, hi = tf32_round(x), lo = x - hi; precision 3 accumulates
+ * hi*hi + hi*lo + lo*hi (3xTF32, fp32-grade: the parity path), precision 1 only hi*hi (fast mode; *_lo unused).
+ * Addresses must be 16-byte aligned and lda/ldb multiples of 4 (TMA); out-of-range k is zero-filled by TMA.
+ * flags: TPP_EPI_BIAS, TPP_EPI_RELU, TPP_EPI_MASK (zero where mask[m*ld_mask+n] <= 0), TPP_EPI_ACCUM (fp32 atomic
+ *        accumulation of the raw product into `out`; the only mode that allows split_k > 1: weight gradients).
+ * Outputs (each nullable): out (plain fp32 [M][ldc]), out_hi/out_lo (TF32 pair, [M][ldc]), colsum ([N], += column
+ * sums of the result: the bias gradient of the layer below).  block_n: 0 = auto, or 16/64/128/256.
+ * Replaces nn.Linear forward / backward (common/model.py:954-980, common/policy.py:74-87).                  */
+typedef struct {
+  const float* a_hi; const float* a_lo; int64_t lda;
+  const float* b_hi; const float* b_lo; int64_t ldb;
+  int32_t M, N, K;
+  int32_t precision, split_k, flags, block_n;
+  int32_t a_mn, b_mn, _pad;
+  const float* bias;
+  const float* mask; int64_t ld_mask;
+  float* out; float* out_hi; float* out_lo; int64_t ldc;
+  float* colsum;
+} tpp_tc_gemm;
+int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
+
+/* x [rows][ld_in] -> (hi, lo) [rows][ld_out] (columns >= cols zero-filled) and/or transposed (t_hi, t_lo)
+ * [cols][ld_t] (columns >= rows zero-filled): makes a foreign fp32 tensor (gathered observations, weights after an
+ * optimizer step, loss gradients) an operand of tpp_gemm_tc.                                                */
+int tpp_split_tf32(const float* x, int64_t ld_in, int32_t rows, int32_t cols, float* hi, float* lo, int64_t ld_out,
+                   float* t_hi, float* t_lo, int64_t ld_t, void* stream);
 
 /* ---- policy: action sampling at rollout --------------------------------------------------------------- */
 /* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.

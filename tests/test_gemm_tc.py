@@ -1,0 +1,163 @@
+"""GPU: the tcgen05 tensor-core GEMM (csrc/gemm_tc.cu) against float64 matmul.
+
+Stated tolerances: precision 3 (3xTF32, the parity path): max |err| <= 2e-6 * sum_k |a||b| (fp32-grade);
+precision 1 (single TF32 product, fast mode): <= 2e-3 * sum_k |a||b|."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _split(x, ld_out=None, transposed_ld=None):
+    from tpp_b200 import _lib
+    rows, cols = x.shape
+    ld_out = ld_out or (cols + 3) // 4 * 4
+    hi = torch.full((rows, ld_out), 7.0, device="cuda")
+    lo = torch.full((rows, ld_out), 7.0, device="cuda")
+    th = tl = None
+    if transposed_ld:
+        th = torch.full((cols, transposed_ld), 7.0, device="cuda")
+        tl = torch.full((cols, transposed_ld), 7.0, device="cuda")
+    _lib.call("tpp_split_tf32", _lib.ptr(x), x.stride(0), rows, cols, _lib.ptr(hi), _lib.ptr(lo), ld_out,
+              _lib.ptr(th), _lib.ptr(tl), transposed_ld or 0, _lib.stream_ptr())
+    return hi, lo, th, tl
+
+
+def _operand(x, mn_major):
+    """x: logical [rows(M or N), K].  K-major: stored as is (ld = ceil4(K)); MN-major: stored transposed
+    [K, ceil32(rows)] via the split kernel's transposed output."""
+    rows, K = x.shape
+    if not mn_major:
+        ld = (K + 3) // 4 * 4
+        hi, lo, _, _ = _split(x, ld)
+        return hi, lo, ld
+    ld = (rows + 31) // 32 * 32
+    _, _, th, tl = _split(x, None, ld)
+    return th, tl, ld
+
+
+def _gemm(a, b, precision, flags=0, bias=None, mask=None, split_k=1, block_n=0, want_colsum=False, out=None,
+          a_mn=False, b_mn=False):
+    from tpp_b200 import _lib
+    M, K = a.shape
+    N = b.shape[0]
+    a_hi, a_lo, lda = _operand(a, a_mn)
+    b_hi, b_lo, ldb = _operand(b, b_mn)
+    ldc = (N + 3) // 4 * 4
+    g = _lib.TcGemm()
+    g.a_hi, g.a_lo, g.lda = a_hi.data_ptr(), a_lo.data_ptr(), lda
+    g.b_hi, g.b_lo, g.ldb = b_hi.data_ptr(), b_lo.data_ptr(), ldb
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.M, g.N, g.K, g.precision, g.split_k, g.flags, g.block_n = M, N, K, precision, split_k, flags, block_n
+    res = {}
+    if out is None:
+        res["out"] = torch.full((M, ldc), 5.0, device="cuda")
+        res["hi"] = torch.full((M, ldc), 5.0, device="cuda")
+        res["lo"] = torch.full((M, ldc), 5.0, device="cuda")
+        g.out, g.out_hi, g.out_lo = res["out"].data_ptr(), res["hi"].data_ptr(), res["lo"].data_ptr()
+    else:
+        res["out"] = out
+        g.out = out.data_ptr()
+        ldc = out.stride(0)
+    g.ldc = ldc
+    if want_colsum:
+        res["colsum"] = torch.ones(N, device="cuda")
+        g.colsum = res["colsum"].data_ptr()
+    if bias is not None:
+        g.bias = bias.data_ptr()
+    if mask is not None:
+        g.mask, g.ld_mask = mask.data_ptr(), mask.stride(0)
+    _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return res
+
+
+def _ref(a, b):
+    a64, b64 = a.double().cpu(), b.double().cpu()
+    return a64 @ b64.t(), a64.abs() @ b64.abs().t()
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 32), (100, 9), (5, 588), (256, 256)])
+def test_split_pairs_are_exact(rows, cols):
+    x = torch.randn(rows, cols, device="cuda") * 3
+    ld, ldt = (cols + 3) // 4 * 4 + 4, (rows + 3) // 4 * 4
+    hi, lo, th, tl = _split(x, ld, ldt)
+    assert torch.equal(hi[:, :cols] + lo[:, :cols], x)                 # exact decomposition
+    assert (hi[:, cols:] == 0).all() and (lo[:, cols:] == 0).all()      # padding is zero
+    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))   # tf32-representable
+    assert (lo.abs() <= hi.abs() * 2.0 ** -11 + 1e-38).all()
+    assert torch.equal(th[:, :rows], hi[:, :cols].t()) and torch.equal(tl[:, :rows], lo[:, :cols].t())
+    assert (th[:, rows:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 256), (256, 256, 256), (8192, 256, 588), (4096, 64, 256),
+                                   (128, 5, 64), (384, 256, 12), (130, 70, 100), (128, 256, 8192)])
+@pytest.mark.parametrize("precision", [3, 1])
+def test_plain_product(M, N, K, precision):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    res = _gemm(a, b, precision)
+    want, scale = _ref(a, b)
+    err = (res["out"][:, :N].double().cpu() - want).abs() / scale
+    # fp32 accumulation in TMEM over K terms: the bound grows with K (an unsplit K=8192 contraction measures 5e-6);
+    # the engine splits long contractions (weight gradients) across CTAs, which also shortens each accumulation.
+    tol = (2e-6 if precision == 3 else 2e-3) * max(1.0, K / 2048)
+    assert err.max() < tol, f"max scaled err {err.max():.3e}"
+    assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])
+
+
+@pytest.mark.parametrize("block_n", [16, 64, 128, 256])
+def test_block_n_variants(block_n):
+    a = torch.randn(256, 96, device="cuda")
+    b = torch.randn(block_n * 2 - 8, 96, device="cuda")
+    res = _gemm(a, b, 3, block_n=block_n)
+    want, scale = _ref(a, b)
+    assert ((res["out"][:, :b.shape[0]].double().cpu() - want).abs() / scale).max() < 2e-6
+
+
+def test_epilogue_bias_relu_mask_and_transposed_outputs():
+    M, N, K = 384, 256, 200
+    a, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    mask = torch.randn(M, N, device="cuda")
+    want, scale = _ref(a, b)
+    res = _gemm(a, b, 3, flags=1 | 2, bias=bias)                        # bias + relu (forward layer)
+    w = torch.relu(want + bias.double().cpu())
+    assert ((res["out"].double().cpu() - w).abs() / (scale + 1)).max() < 2e-6
+    res = _gemm(a, b, 3, flags=4, mask=mask, want_colsum=True)            # relu-mask + column sums (data gradient)
+    w = want * (mask.cpu() > 0)
+    assert ((res["out"].double().cpu() - w).abs() / scale).max() < 2e-6
+    cs = res["colsum"].double().cpu() - 1.0                               # accumulated on top of the initial ones
+    np.testing.assert_allclose(cs.numpy(), w.sum(0).numpy(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 256, 100), (4096, 256, 9), (8192, 588, 256), (256, 608, 1000),
+                                   (130, 70, 50)])
+def test_mn_major_operands(a_mn, b_mn, M, N, K):
+    """Rollout layer 1 (feature-major obs: A MN-major), data gradient (W as MN-major B), weight gradient (both)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    res = _gemm(a, b, 3, a_mn=a_mn, b_mn=b_mn)
+    want, scale = _ref(a, b)
+    err = (res["out"][:, :N].double().cpu() - want).abs() / scale
+    assert err.max() < 2e-6, f"max scaled err {err.max():.3e}"
+
+
+@pytest.mark.parametrize("split_k", [1, 7, 64])
+@pytest.mark.parametrize("mn", [False, True])
+def test_split_k_atomic_accumulation(split_k, mn):
+    """Weight-gradient shape: small output, long contraction over the minibatch, accumulated on top of `out`
+    (mn=True: both operands MN-major, i.e. read straight from the row-major dZ [mb][out] and X [mb][in])."""
+    a, b = torch.randn(256, 8192, device="cuda"), torch.randn(588, 8192, device="cuda")
+    base = torch.randn(256, 588, device="cuda")
+    out = base.clone()
+    _gemm(a, b, 3, flags=8, split_k=split_k, out=out, a_mn=mn, b_mn=mn)
+    want, scale = _ref(a, b)
+    err = (out.double().cpu() - (base.double().cpu() + want)).abs() / scale
+    assert err.max() < (2e-6 if split_k > 1 else 8e-6)       # unsplit: 8192-term fp32 accumulation

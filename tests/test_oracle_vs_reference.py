@@ -1,0 +1,108 @@
+"""CPU, container only: the oracle against the LIVE, unmodified reference imported from /root/reference through
+oracle/ref_shim.py.  Skipped where the reference tree is absent (the GPU box): there the committed fixtures
+(tests/golden, minted from this same reference) carry the pin."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference tree not present")
+
+MODS = {"cartpole": ("discrete_env.cartpole_pre_vec", "CartPoleVecEnv", 2),
+        "cartpole_swing": ("discrete_env.cartpole_swing_pre_vec", "CartPoleSwingVecEnv", 2),
+        "mountain_car": ("discrete_env.mountain_car_pre_vec", "MountainCarVecEnv", 3),
+        "acrobot": ("discrete_env.acrobot_pre_vec", "AcrobotVecEnv", 3)}
+
+
+@pytest.mark.parametrize("family", list(MODS))
+def test_prevec_free_running_bit_equal(family):
+    from oracle.prevec import OraclePreVec
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod, cls, n_act = MODS[family]
+        ref = getattr(ref_shim.load(mod), cls)(n_envs=96, seed=5, max_steps=40)
+    orc = OraclePreVec(family, 96, seed=5, max_steps=40)
+    assert np.array_equal(ref.reset(), orc.reset())
+    rng = np.random.default_rng(2)
+    for t in range(250):
+        a = rng.integers(0, n_act, 96)
+        o_r, r_r, d_r, _ = ref.step(a)
+        o_o, r_o, d_o = orc.step(a)
+        assert np.array_equal(o_r, o_o) and np.array_equal(d_r, d_o), (family, t)
+        assert np.array_equal(np.asarray(r_r, dtype=np.float64), r_o)
+
+
+@pytest.mark.parametrize("spec,n_levels", [((6, 2, 1, 1), 0), ((12, 5, 3, 3), 0), ((12, 4, 2, 2), 500), ((6, 2, 1, 1), 5)])
+def test_boxworld_bit_equal(spec, n_levels):
+    from oracle.boxworld import BoxWorldOracle
+    bw = ref_shim.load("boxworld.box_world_env_vec")
+    ref = bw.BoxWorldVec(64, *spec, max_steps=30, start_seed=3, n_levels=n_levels)
+    orc = BoxWorldOracle(64, *spec, max_steps=30, start_seed=3, n_levels=n_levels)
+    rng = np.random.default_rng(0)
+    for t in range(150):
+        a = rng.integers(0, 4, 64)
+        w, r, d, info = ref.step(a)
+        ow, orr, od = orc.step(a)
+        assert np.array_equal(w, ow) and np.array_equal(r, orr) and np.array_equal(d, od), t
+        assert ref.np_random_seed == orc.seed_counter
+        assert [i["action.moved_player"] for i in info] == list(orc.moved_player)
+
+
+def test_vecnormalize_and_frame_wrappers():
+    from oracle.boxworld import VecNormalizeOracle
+    pw = ref_shim.load("common.env.procgen_wrappers")
+    rms, mine = pw.RunningMeanStd(shape=()), VecNormalizeOracle(32)
+    ret = np.zeros(32)
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        rews = rng.integers(-1, 12, 32).astype(np.float64)
+        news = rng.random(32) < 0.1
+        ret = ret * 0.99 + rews                                   # procgen_wrappers.py:335-341
+        rms.update(ret)
+        want = np.clip(rews / np.sqrt(rms.var + 1e-8), -10.0, 10.0)
+        ret[news] = 0.0
+        assert np.array_equal(mine.step(rews, news), want)
+
+
+def test_policy_architectures_match_reference_state_dicts():
+    from oracle import ppo as oppo
+    model, policy = ref_shim.load("common.model"), ref_shim.load("common.policy")
+    torch.manual_seed(0)
+    ref = policy.CategoricalPolicy(model.MLPModel(9, 4, 256, 64), False, 2)
+    torch.manual_seed(0)
+    mine = oppo.OraclePolicy(oppo.OracleMLP(9, 4, 256, 64), 2)
+    assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == \
+           [(k, tuple(v.shape)) for k, v in mine.state_dict().items()]
+    for (k, a), (_, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert torch.equal(a, b), k                                # same init stream => same weights
+    torch.manual_seed(1)
+    ref = policy.CategoricalPolicy(model.ImpalaModel(3), False, 15)
+    torch.manual_seed(1)
+    mine = oppo.OraclePolicy(oppo.OracleImpala(3), 15)
+    x = torch.rand(4, 3, 64, 64)
+    for (k, a), (_, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
+        assert torch.equal(a, b), k
+    feat, _, fs, _ = ref.embedder.forward_with_attn_indices(x)
+    d_ref, v_ref = ref.hidden_to_output(feat)
+    d, v, fs2 = mine(x)
+    assert torch.equal(d_ref.logits, d.logits) and torch.equal(v_ref, v) and torch.equal(fs, fs2)
+
+
+def test_product_policy_state_dict_keys_match_reference():
+    """Checkpoint compatibility: the product's policy modules expose the reference's state_dict layout."""
+    from tpp_b200.common.model import ImpalaModel, MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    model, policy = ref_shim.load("common.model"), ref_shim.load("common.policy")
+    for mk_ref, mk_mine, A in ((lambda: model.MLPModel(9, 4, 256, 64), lambda: MLPModel(9, 4, 256, 64), 2),
+                               (lambda: model.ImpalaModel(3), lambda: ImpalaModel(3), 15)):
+        torch.manual_seed(3)
+        ref = policy.CategoricalPolicy(mk_ref(), False, A)
+        torch.manual_seed(3)
+        mine = CategoricalPolicy(mk_mine(), False, A)
+        assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+        for (k, a), (_, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
+            assert torch.equal(a, b), k
+        mine.load_state_dict(ref.state_dict())

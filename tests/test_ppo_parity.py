@@ -28,17 +28,22 @@ def _close(a, b, rtol=1e-5, atol=1e-6, what=""):
 
 @pytest.mark.parametrize("M,in_dim,A,mid,latent", [(64, 9, 2, 32, 16), (4096, 9, 2, 256, 64), (1000, 588, 4, 256, 64),
                                                    (130, 5, 3, 48, 24), (256, 14, 15, 256, 64)])
-def test_engine_forward_backward_vs_torch(M, in_dim, A, mid, latent):
-    """Hand-written forward/backward on the flat buffer == torch autograd on the same (aliased) parameters."""
-    from tpp_b200.common.engine import MLPEngine
+@pytest.mark.parametrize("kind", ["fp32", "tf32x3"])
+def test_engine_forward_backward_vs_torch(M, in_dim, A, mid, latent, kind):
+    """Hand-written forward/backward on the flat buffer == torch autograd on the same (aliased) parameters, for
+    the CUDA-core fp32 engine and the tcgen05 3xTF32 engine (both must hold the fp32 tolerance)."""
+    from tpp_b200.common.engine import MLPEngine, MLPEngineTC
+    torch.backends.cuda.matmul.allow_tf32 = False
     pol = _policy(in_dim, A, mid=mid, latent=latent, seed=M)
-    eng = MLPEngine(pol, A)
-    x = torch.randn(M, in_dim, device="cuda")
+    eng = MLPEngine(pol, A) if kind == "fp32" else MLPEngineTC(pol, A, precision=3)
+    x = torch.randn(M, (in_dim + 3) // 4 * 4, device="cuda")[:, :in_dim]
     head = eng.forward(x, M)
     dist, v, _ = pol(x, None, None)
     logits = pol.fc_policy(pol.embedder(x))
-    _close(head[:, :A].cpu(), logits.detach().cpu(), what="logits")
-    _close(head[:, A].cpu(), v.detach().cpu(), what="value")
+    # two independent fp32-grade evaluations of a 5-layer network (cuBLAS fp32 vs ours): rounding of the K<=588
+    # contractions compounds to ~1e-5 absolute on O(1) outputs -> stated atol 2e-5 (+ 1e-5 relative)
+    _close(head[:, :A].cpu(), logits.detach().cpu(), atol=2e-5, what="logits")
+    _close(head[:, A].cpu(), v.detach().cpu(), atol=2e-5, what="value")
     dhead = torch.zeros_like(head)
     dhead[:, :A + 1] = torch.randn(M, A + 1, device="cuda") / M
     pol.flat_grad.zero_()
@@ -52,17 +57,23 @@ def test_engine_forward_backward_vs_torch(M, in_dim, A, mid, latent):
     _close(mine.cpu(), ref.cpu(), rtol=1e-4, atol=2e-6 * max(scale, 1.0), what="flat gradient")
 
 
-def test_engine_feature_major_input_equals_row_major():
-    from tpp_b200.common.engine import MLPEngine
+@pytest.mark.parametrize("kind", ["fp32", "tf32x3"])
+def test_engine_feature_major_input_equals_row_major(kind):
+    from tpp_b200.common.engine import MLPEngine, MLPEngineTC
     pol = _policy(9, 2, mid=64, latent=32)
-    eng = MLPEngine(pol, 2)
-    N, ld = 300, 304
+    eng = MLPEngine(pol, 2) if kind == "fp32" else MLPEngineTC(pol, 2)
+    N, ld = 300, 320
     x = torch.randn(N, 9, device="cuda")
     fm = torch.zeros(9, ld, device="cuda")
     fm[:, :N] = x.t()
-    a = eng.forward(x, N).clone()
+    xp = torch.zeros(N, 12, device="cuda")
+    xp[:, :9] = x
+    a = eng.forward(xp[:, :9], N).clone()
     b = eng.forward(fm, N, feature_major_ld=ld).clone()
-    assert torch.equal(a, b)
+    if kind == "fp32":
+        assert torch.equal(a, b)
+    else:   # first layer runs on CUDA cores for feature-major input and on tensor cores for row-major input
+        _close(a.cpu(), b.cpu(), rtol=1e-5, atol=1e-6)
 
 
 @pytest.mark.parametrize("A,x_coef", [(2, 0.0), (3, 0.05), (15, 0.0), (4, 0.3)])
@@ -139,8 +150,9 @@ def test_adam_clip_vs_torch():
     _close(sd["state"][0]["exp_avg_sq"].cpu(), sd_ref["state"][0]["exp_avg_sq"], rtol=1e-5, atol=1e-12)
 
 
+@pytest.mark.parametrize("matmul", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("tag,x_coef", [("plain", 0.0), ("xent", 0.05)])
-def test_optimize_against_reference_fixture(golden_dir, tag, x_coef):
+def test_optimize_against_reference_fixture(golden_dir, tag, x_coef, matmul):
     """PPO.optimize on the reference's recorded rollout + initial weights + torch seed: same minibatches, and
     final parameters / logged summary within fp32 tolerance of what the reference produced."""
     from tpp_b200.agents.ppo import PPO
@@ -164,7 +176,7 @@ def test_optimize_against_reference_fixture(golden_dir, tag, x_coef):
     _close(st.adv_batch.cpu(), g[f"opt_{tag}_adv_batch"], atol=2e-6, what="normalised advantages")
     agent = PPO(None, pol, None, st, "cuda", 1, n_steps=T, n_envs=N, epoch=2, n_minibatch=4, mini_batch_size=64,
                 gamma=0.99, lmbda=0.95, learning_rate=5e-3, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5,
-                entropy_coef=0.02, x_entropy_coef=x_coef)
+                entropy_coef=0.02, x_entropy_coef=x_coef, matmul=matmul)
     torch.manual_seed(4321)
     summary = agent.optimize()
     assert list(summary.keys()) == [str(k) for k in g[f"opt_{tag}_summary_keys"]]

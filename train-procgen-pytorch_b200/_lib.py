@@ -45,6 +45,17 @@ class AdamState(C.Structure):   # mirrors tpp_adam_state (lives in device memory
                 ("sqnorm", C.c_double * 2)]
 
 
+class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64),
+                ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("precision", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32), ("block_n", C.c_int32),
+                ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("_pad", C.c_int32),
+                ("bias", C.c_void_p), ("mask", C.c_void_p), ("ld_mask", C.c_int64),
+                ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
+                ("colsum", C.c_void_p)]
+
+
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}
 EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM = 1, 2, 4, 8
 
@@ -64,13 +75,15 @@ SIGNATURES = {
     "tpp_vecnormalize_step": [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _f64, _f64, _f64, _vp],
     "tpp_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp],
     "tpp_adv_normalize": [_vp, _vp, _i32, _i32, _i64, _vp],
-    "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+    "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],
-    "tpp_gather_img": [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
-                       _vp, _vp, _vp, _vp, _vp],
-    "tpp_frames_to_obs": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp],
+    "tpp_gather_img": [_vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                       _vp, _vp, _vp, _vp, _vp, _vp],
+    "tpp_frames_to_obs": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
     "tpp_gemm_f32": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "tpp_colsum_accum": [_vp, _i64, _i32, _i32, _vp, _vp],
+    "tpp_gemm_tc": [C.POINTER(TcGemm), _vp],
+    "tpp_split_tf32": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],

@@ -14,8 +14,8 @@ import math
 import numpy as np
 import torch
 
-from .. import _lib
-from ..common.engine import MLPEngine, TorchModuleEngine
+from .. import _lib, parallel
+from ..common.engine import MLPEngine, MLPEngineTC, TorchModuleEngine
 from ..common.model import MLPModel
 from .base_agent import BaseAgent
 
@@ -129,8 +129,14 @@ class PPO(BaseAgent):
         if policy.flat is None:
             policy.flatten_(device)
         self.n_actions = policy.action_size
+        # dense-layer arithmetic: "tf32x3" (default) = tcgen05 tensor cores with the error-compensated 3xTF32 split
+        # (fp32-grade, the parity path), "tf32" = single-pass tensor-core fast mode (~1e-3), "fp32" = CUDA cores.
+        self.matmul = kwargs.get("matmul", "tf32x3")
         if isinstance(policy.embedder, MLPModel):
-            self.engine = MLPEngine(policy, self.n_actions)
+            if self.matmul == "fp32":
+                self.engine = MLPEngine(policy, self.n_actions)
+            else:
+                self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1)
         else:
             self.engine = TorchModuleEngine(policy, self.n_actions, storage.obs_shape)
         self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
@@ -157,12 +163,23 @@ class PPO(BaseAgent):
         N = storage.num_envs
         if storage.is_image:
             c, h, w = storage.obs_shape
-            mb = storage.minibatch_buffers(N)
-            _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot), N, h, w, c, _lib.ptr(mb.obs), mb.ld_obs,
-                      _lib.stream_ptr())
+            mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
+            _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot), N, h, w, c, _lib.ptr(mb.obs), _lib.ptr(mb.obs_lo),
+                      mb.ld_obs, _lib.stream_ptr())
             self.n_launches += 1
-            return self.engine.forward(mb.obs, N)
-        return self.engine.forward(obs_slot, N, feature_major_ld=storage.ld)
+            return self._fwd(mb.obs, N, x_lo=mb.obs_lo)
+        return self._fwd(obs_slot, N, feature_major_ld=storage.ld)
+
+    def _obs_buf_args(self, storage):
+        """(row stride, split) of gathered-observation buffers: the TC engine wants TF32 pairs with ld = ceil32(in)."""
+        if isinstance(self.engine, MLPEngineTC):
+            return self.engine.ld_in, True
+        return _round4(storage.obs_width), False
+
+    def _fwd(self, x, M, feature_major_ld=None, x_lo=None):
+        if isinstance(self.engine, MLPEngineTC):
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False)
+        return self.engine.forward(x, M, feature_major_ld=feature_major_ld)
 
     def _sample(self, head, N, act, logp, value, t_offset, greedy=False):
         _lib.call("tpp_sample_actions", _lib.ptr(head), self.engine.ld_head, N, self.n_actions, _lib.ptr(act),
@@ -178,7 +195,7 @@ class PPO(BaseAgent):
         x = torch.as_tensor(np.asarray(obs) if was_numpy else obs).to(dev, torch.float32)
         N = x.shape[0]
         x = x.reshape(N, -1).contiguous()
-        head = self.engine.forward(x, N)
+        head = self._fwd(x, N)
         act = torch.empty(N, dtype=torch.int32, device=dev)
         logp = torch.empty(N, dtype=torch.float32, device=dev)
         value = torch.empty(N, dtype=torch.float32, device=dev)
@@ -212,42 +229,87 @@ class PPO(BaseAgent):
         self._stats.zero_()
         cfg = _lib.LossCfg(self.eps_clip, self.value_coef, self.entropy_coef, float(self.entropy_multiplier),
                            self.x_entropy_coef, A, mb)
-        ld_obs = st.obs_width if st.is_image else None
-        buf = st.minibatch_buffers(mb, _round4(ld_obs) if ld_obs else None)
-        engine, s = self.engine, _lib.stream_ptr()
+        buf = st.minibatch_buffers(mb, *self._obs_buf_args(st))
+        engine = self.engine
         fs_vals = []
         is_torch_engine = isinstance(engine, TorchModuleEngine)
         self.policy.train()
+        # fixed staging buffers so that one minibatch (gather -> forward -> loss -> backward) is a replayable graph
+        if getattr(self, "_idx_cur", None) is None or self._idx_cur.numel() != mb:
+            self._idx_cur = torch.zeros(mb, dtype=torch.int64, device=dev)
+            self._stats_cur = torch.zeros(4 + 16, dtype=torch.float64, device=dev)
+            self._pbar_cur = torch.zeros(16, dtype=torch.float32, device=dev)
+        if hasattr(engine, "refresh_weights"):
+            engine.refresh_weights()
+
+        def minibatch_body():
+            s = _lib.stream_ptr()          # evaluated here: under graph capture the current stream is the capture stream
+            self._stats_cur.zero_()
+            st.gather(self._idx_cur, buf)
+            if is_torch_engine:
+                head = engine.forward(buf.obs, mb, train=True)
+            elif buf.obs_lo is not None:
+                head = engine.forward(buf.obs, mb, x_lo=buf.obs_lo)
+            else:
+                head = engine.forward(buf.obs, mb)
+            ws_dhead = engine._workspace(mb).dhead if not is_torch_engine else self._dhead(mb)
+            pbar = None
+            if self.x_entropy_coef != 0.0:
+                self._pbar_cur.zero_()
+                _lib.call("tpp_ppo_pbar", _lib.ptr(head), engine.ld_head, mb, A, _lib.ptr(self._pbar_cur), s)
+                pbar = self._pbar_cur
+                self.n_launches += 1
+            _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
+                      _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
+                      _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(self._stats_cur), s)
+            self.n_launches += 1
+            if is_torch_engine:
+                engine.backward(ws_dhead, mb, self.fs_coef)
+            else:
+                engine.backward(ws_dhead, mb)
+
+        graph_key = (mb, float(self.entropy_multiplier), id(st))
+        use_graph = self.use_cuda_graph and not is_torch_engine
+        graphs = self.__dict__.setdefault("_mb_graphs", {})
         k = 0
         for _ in range(self.epoch):
             idx = st.epoch_indices(mb)
             for i in range(n_mb):
-                st.gather(idx[i], buf)
-                head = engine.forward(buf.obs, mb, train=True) if is_torch_engine else engine.forward(buf.obs, mb)
-                ws_dhead = engine._workspace(mb).dhead if not is_torch_engine else self._dhead(mb)
-                pbar = None
-                if self.x_entropy_coef != 0.0:
-                    self._pbar[k].zero_()
-                    _lib.call("tpp_ppo_pbar", _lib.ptr(head), engine.ld_head, mb, A, _lib.ptr(self._pbar[k]), s)
-                    pbar = self._pbar[k]
-                    self.n_launches += 1
-                _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
-                          _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
-                          _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(self._stats[k]), s)
-                self.n_launches += 1
-                if is_torch_engine:
-                    engine.backward(ws_dhead, mb, self.fs_coef)
-                    if engine.last_fs is not None:
-                        fs_vals.append(engine.last_fs.detach())
-                else:
-                    engine.backward(ws_dhead, mb)
+                self._idx_cur.copy_(idx[i])
+                entry = graphs.get(graph_key) if use_graph else None
+                if entry is None or entry == "warm":
+                    if use_graph and entry == "warm":                  # second minibatch: capture, then replay
+                        g = torch.cuda.CUDAGraph()
+                        torch.cuda.synchronize()
+                        c0 = self._launch_count()
+                        with torch.cuda.graph(g):
+                            minibatch_body()
+                        n_captured = sum(self._launch_count()) - sum(c0)
+                        # kernels recorded during capture did not execute: count them per replay instead
+                        self.n_launches, self.engine.n_launches, self.storage.n_launches = c0
+                        entry = graphs[graph_key] = (g, n_captured)
+                    else:                                              # first minibatch (or graphs off): eager
+                        minibatch_body()
+                        if use_graph:
+                            graphs[graph_key] = "warm"
+                if isinstance(entry, tuple):
+                    entry[0].replay()
+                    self.n_launches += entry[1]
+                if is_torch_engine and engine.last_fs is not None:
+                    fs_vals.append(engine.last_fs.detach())
+                self._stats[k].copy_(self._stats_cur)
                 if cnt % accum == 0:
                     if self.world_size > 1:
-                        torch.distributed.all_reduce(self.policy.flat_grad, group=self.process_group)
+                        parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
                     self.optimizer.step()
+                    if hasattr(engine, "refresh_weights"):
+                        engine.refresh_weights()
                 cnt += 1
                 k += 1
         return self._summary(fs_vals)
+
+    def _launch_count(self):
+        return (self.n_launches, self.engine.n_launches, self.storage.n_launches)
 
     def _dhead(self, mb):
         if getattr(self, "_dhead_buf", None) is None or self._dhead_buf.shape[0] != mb:
@@ -287,6 +349,8 @@ class PPO(BaseAgent):
 
     def _rollout_steps(self, env, storage):
         T, N = storage.num_steps, storage.num_envs
+        if hasattr(self.engine, "refresh_weights"):
+            self.engine.refresh_weights()     # always part of the (captured) rollout: weights changed since last time
         for t in range(T):
             head = self._policy_head(storage.obs_slot(t), storage)
             self._sample(head, N, storage.act_i32[t], storage.logp[t], storage.value[t], t)

@@ -174,3 +174,153 @@ class TorchModuleEngine:
             torch.autograd.backward([self._head, extra], [dhead, torch.ones_like(extra)])
         else:
             self._head.backward(dhead)
+
+
+class MLPEngineTC(MLPEngine):
+    """MLPModel + heads on the tcgen05 tensor-core GEMM (csrc/gemm_tc.cu).
+
+    Every GEMM operand is a (hi, lo) TF32 pair in its natural row-major layout; forward, data-gradient and
+    weight-gradient GEMMs read the same arrays as K-major or MN-major operands, so nothing is transposed.  Pairs are
+    written by the producer (GEMM epilogue, minibatch gather, frames_to_obs) or by ``tpp_split_tf32`` (weights after
+    an optimizer step, the head's data gradient).  Bias gradients are column sums fused into the epilogue of the
+    GEMM that produces the corresponding dZ.  ``precision=3`` (default) is the fp32-parity 3xTF32 mode,
+    ``precision=1`` the single-pass fast mode.  The two head GEMMs of the backward pass (A+1 <= 16 columns) stay on
+    the CUDA-core kernel: they are < 1 % of the FLOPs.
+    """
+
+    def __init__(self, policy, n_actions, precision=3):
+        super().__init__(policy, n_actions)
+        assert precision in (1, 3)
+        self.precision = precision
+        f = dict(dtype=torch.float32, device=self.device)
+        self.w = []   # per layer: hi, lo [out, ceil32(in)]
+        for (w_off, b_off, fin, fout, relu) in self.layers:
+            ldk = _ceil(fin, 32) * 32
+            self.w.append(dict(hi=torch.zeros(fout, ldk, **f), lo=torch.zeros(fout, ldk, **f), ldk=ldk))
+        nh = n_actions + 1
+        self.wh = dict(hi=torch.zeros(nh, self.latent, **f), lo=torch.zeros(nh, self.latent, **f))
+        self.ld_in = self.w[0]["ldk"]          # row stride the gathered observations must have
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------------------------------
+    def refresh_weights(self):
+        """Re-split the (changed) fp32 weights into TF32 pairs."""
+        s = _lib.stream_ptr()
+        for (w_off, b_off, fin, fout, relu), w in zip(self.layers, self.w):
+            _lib.call("tpp_split_tf32", self._p(w_off), fin, fout, fin, _lib.ptr(w["hi"]), _lib.ptr(w["lo"]), w["ldk"],
+                      None, None, 0, s)
+        _lib.call("tpp_split_tf32", self._p(self.head_w_off), self.latent, self.A + 1, self.latent,
+                  _lib.ptr(self.wh["hi"]), _lib.ptr(self.wh["lo"]), self.latent, None, None, 0, s)
+        self.n_launches += len(self.layers) + 1
+
+    def _workspace(self, M):
+        ws = self._ws.get(M)
+        if ws is None:
+            ws = _Workspace()
+            f = dict(dtype=torch.float32, device=self.device)
+            ws.x = dict(hi=torch.zeros(M, self.ld_in, **f), lo=torch.zeros(M, self.ld_in, **f))
+            ws.h = [dict(hi=torch.zeros(M, _ceil(l[3], 32) * 32, **f), lo=torch.zeros(M, _ceil(l[3], 32) * 32, **f),
+                         ld=_ceil(l[3], 32) * 32) for l in self.layers]
+            ws.last_plain = torch.zeros(M, _ceil(self.latent, 32) * 32, **f)   # same row stride as its TF32 pair
+            ws.head = torch.zeros(M, self.ld_head, **f)
+            ws.dhead = torch.zeros(M, self.ld_head, **f)
+            mw = _ceil(self.max_width, 32) * 32
+            ws.dz = [dict(plain=torch.zeros(M, mw, **f), hi=torch.zeros(M, mw, **f), lo=torch.zeros(M, mw, **f))
+                     for _ in range(2)]
+            ws.fm = None       # TF32 pair of a feature-major rollout slot, allocated on first use
+            self._ws[M] = ws
+        return ws
+
+    def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
+            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0):
+        g = _lib.TcGemm()
+        g.a_hi, g.a_lo, g.lda = a[0].data_ptr(), a[1].data_ptr(), lda
+        g.b_hi, g.b_lo, g.ldb = b[0].data_ptr(), b[1].data_ptr(), ldb
+        g.M, g.N, g.K, g.a_mn, g.b_mn = M, N, K, a_mn, b_mn
+        g.precision, g.split_k, g.flags, g.block_n = self.precision, split_k, flags, block_n
+        if bias is not None:
+            g.bias = bias.value
+        if mask is not None:
+            g.mask, g.ld_mask = mask.data_ptr(), ld_mask
+        if out is not None:
+            g.out = out.value if hasattr(out, "value") else out.data_ptr()
+        if out_pair is not None:
+            g.out_hi, g.out_lo = out_pair[0].data_ptr(), out_pair[1].data_ptr()
+        if colsum is not None:
+            g.colsum = colsum.value
+        g.ldc = ldc
+        _lib.call("tpp_gemm_tc", _lib.C.byref(g), _lib.stream_ptr())
+        self.n_launches += 1
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True):
+        """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given), or with
+        ``feature_major_ld`` a feature-major [in_dim, ld] rollout slot."""
+        ws, s = self._workspace(M), _lib.stream_ptr()
+        L = len(self.layers)
+        if feature_major_ld:
+            ld = feature_major_ld
+            if ws.fm is None or ws.fm[0].shape[1] != ld:
+                ws.fm = (torch.zeros(self.in_dim, ld, dtype=torch.float32, device=self.device),
+                         torch.zeros(self.in_dim, ld, dtype=torch.float32, device=self.device))
+            _lib.call("tpp_split_tf32", _lib.ptr(x), ld, self.in_dim, M, _lib.ptr(ws.fm[0]), _lib.ptr(ws.fm[1]), ld,
+                      None, None, 0, s)
+            self.n_launches += 1
+            cur, ld_cur, a_mn = ws.fm, ld, 1
+        elif x_lo is not None:
+            cur, ld_cur, a_mn = (x, x_lo), x.stride(0), 0
+        else:
+            _lib.call("tpp_split_tf32", _lib.ptr(x), x.stride(0), M, self.in_dim, _lib.ptr(ws.x["hi"]),
+                      _lib.ptr(ws.x["lo"]), self.ld_in, None, None, 0, s)
+            self.n_launches += 1
+            cur, ld_cur, a_mn = (ws.x["hi"], ws.x["lo"]), self.ld_in, 0
+        self._x_pair, self._x_ld = (cur, ld_cur), None
+        for i in range(L):
+            w_off, b_off, fin, fout, relu = self.layers[i]
+            h, w = ws.h[i], self.w[i]
+            self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
+                     flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
+                     out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"])
+            cur, ld_cur, a_mn = (h["hi"], h["lo"]), h["ld"], 0
+        self._tc(cur, ld_cur, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
+                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
+        self._x = (x, feature_major_ld)
+        return ws.head
+
+    def backward(self, dhead, M):
+        ws, s = self._workspace(M), _lib.stream_ptr()
+        x, fm_ld = self._x
+        assert not fm_ld, "backward needs the row-major (minibatch) forward"
+        (x_pair, x_ld) = self._x_pair
+        H, nh, L = self.latent, self.A + 1, len(self.layers)
+        ldl = ws.h[-1]["ld"]
+        # heads on CUDA cores (tiny): gWh += dhead^T latent ; gbh += colsum ; dlatent = dhead Wh
+        self._gemm(_lib.ptr(dhead), 1, self.ld_head, _lib.ptr(ws.last_plain), 1, ldl, self._g(self.head_w_off), H, None,
+                   None, nh, H, M, EPI_ACCUM, self._split_k(M, nh, H))
+        _lib.call("tpp_colsum_accum", _lib.ptr(dhead), self.ld_head, M, nh, self._g(self.head_b_off), s)
+        dz = ws.dz[0]
+        last_relu = self.layers[-1][4]
+        self._gemm(_lib.ptr(dhead), self.ld_head, 1, self._p(self.head_w_off), 1, H, _lib.ptr(dz["plain"]), ldl, None,
+                   _lib.ptr(ws.h[-1]["hi"]) if last_relu else None, M, H, nh, EPI_MASK if last_relu else 0)
+        _lib.call("tpp_split_tf32", _lib.ptr(dz["plain"]), ldl, M, H, _lib.ptr(dz["hi"]), _lib.ptr(dz["lo"]), ldl,
+                  None, None, 0, s)
+        _lib.call("tpp_colsum_accum", _lib.ptr(dz["plain"]), ldl, M, H, self._g(self.layers[-1][1]), s)
+        self.n_launches += 3
+        cur, ld_dz = 0, ldl
+        for i in range(L - 1, -1, -1):
+            w_off, b_off, fin, fout, relu = self.layers[i]
+            dz = ws.dz[cur]
+            inp, ld_inp = ((ws.h[i - 1]["hi"], ws.h[i - 1]["lo"]), ws.h[i - 1]["ld"]) if i > 0 else (x_pair, x_ld)
+            # gW[fout, fin] += dZ^T X : both operands MN-major, contraction over the M samples split across CTAs
+            tiles = _ceil(fout, 128) * _ceil(fin, 128)
+            self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
+                     out=self._g(w_off), ldc=fin, split_k=max(1, min(_ceil(M, 32), _ceil(148, tiles))), block_n=128)
+            if i > 0:
+                # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
+                nxt, w, prev = ws.dz[cur ^ 1], self.w[i], ws.h[i - 1]
+                prev_relu = self.layers[i - 1][4]
+                self._tc((dz["hi"], dz["lo"]), ld_dz, (w["hi"], w["lo"]), w["ldk"], M, fin, fout, b_mn=1,
+                         flags=EPI_MASK if prev_relu else 0, mask=prev["hi"] if prev_relu else None,
+                         ld_mask=prev["ld"], out_pair=(nxt["hi"], nxt["lo"]), ldc=prev["ld"],
+                         colsum=self._g(self.layers[i - 1][1]))
+                cur, ld_dz = cur ^ 1, prev["ld"]

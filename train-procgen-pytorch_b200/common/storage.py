@@ -17,7 +17,7 @@ from collections import deque
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, parallel
 
 
 def _round_up(x, m):
@@ -27,10 +27,11 @@ def _round_up(x, m):
 class MiniBatch:
     """Device buffers of one gathered minibatch (reused between minibatches: no allocation in the loop)."""
 
-    def __init__(self, mb, obs_width, ld_obs, device):
+    def __init__(self, mb, obs_width, ld_obs, device, split=False):
         f = dict(dtype=torch.float32, device=device)
         self.mb, self.obs_width, self.ld_obs = mb, obs_width, ld_obs
         self.obs = torch.zeros(mb, ld_obs, **f)
+        self.obs_lo = torch.zeros(mb, ld_obs, **f) if split else None   # TF32 pair (obs = hi) for the TC policy
         self.act = torch.zeros(mb, dtype=torch.int32, device=device)
         self.logp, self.value, self.ret, self.adv, self.done = (torch.zeros(mb, **f) for _ in range(5))
 
@@ -50,7 +51,7 @@ class Storage:
         self.act_shape = act_shape
         self.hidden_state_size = hidden_state_size
         self.num_steps, self.num_envs = int(num_steps), int(num_envs)
-        self.ld = _round_up(self.num_envs, 4)
+        self.ld = _round_up(self.num_envs, 32)   # row stride of every [T][ld] buffer (TMA / MN-major operand friendly)
         self.is_image = len(self.obs_shape) == 3
         self.obs_width = int(np.prod(self.obs_shape))
         self.world_size, self.process_group = 1, None
@@ -172,16 +173,16 @@ class Storage:
         self.n_launches += 1
         if normalize_adv:
             if self.world_size > 1:   # exact global moments under env sharding: 3 doubles, once per rollout
-                torch.distributed.all_reduce(self.moments, group=self.process_group)
+                parallel.allreduce_moments_(self.moments, self.process_group)
             _lib.call("tpp_adv_normalize", _lib.ptr(self.adv), _lib.ptr(self.moments), T, N, self.ld, s)
             self.n_launches += 1
 
     # ---- minibatches -----------------------------------------------------------------------------------------
-    def minibatch_buffers(self, mb, ld_obs=None):
+    def minibatch_buffers(self, mb, ld_obs=None, split=False):
         ld_obs = ld_obs or _round_up(self.obs_width, 4)
-        key = (mb, ld_obs)
+        key = (mb, ld_obs, split)
         if key not in self._mb:
-            self._mb[key] = MiniBatch(mb, self.obs_width, ld_obs, self.device)
+            self._mb[key] = MiniBatch(mb, self.obs_width, ld_obs, self.device, split)
         return self._mb[key]
 
     def epoch_indices(self, mini_batch_size):
@@ -201,17 +202,14 @@ class Storage:
                 _lib.ptr(self.adv), _lib.ptr(self.done_u8))
         outs = (_lib.ptr(out.act), _lib.ptr(out.logp), _lib.ptr(out.value), _lib.ptr(out.ret), _lib.ptr(out.adv),
                 _lib.ptr(out.done))
-        if self.ld != N and not self.is_image:
-            pass   # flat index k = t*N + e is decoded in-kernel, rows are ld apart
+        # flat index k = t*N + e is decoded in-kernel; scalar rows are ld apart
         if self.is_image:
             c, h, w = self.obs_shape
-            if self.ld != N:
-                raise _lib.TppError("image rollouts need n_envs % 4 == 0")
-            _lib.call("tpp_gather_img", _lib.ptr(idx_row), out.mb, N, h, w, c, _lib.ptr(self.frames), *scal,
-                      _lib.ptr(out.obs), out.ld_obs, *outs, s)
+            _lib.call("tpp_gather_img", _lib.ptr(idx_row), out.mb, N, self.ld, h, w, c, _lib.ptr(self.frames), *scal,
+                      _lib.ptr(out.obs), _lib.ptr(out.obs_lo), out.ld_obs, *outs, s)
         else:
             _lib.call("tpp_gather_vec", _lib.ptr(idx_row), out.mb, N, self.ld, self.obs_width, _lib.ptr(self.obs_fm),
-                      *scal, _lib.ptr(out.obs), out.ld_obs, *outs, s)
+                      *scal, _lib.ptr(out.obs), _lib.ptr(out.obs_lo), out.ld_obs, *outs, s)
         self.n_launches += 1
         return out
 

@@ -1,0 +1,491 @@
+// Tensor-core path of the policy's dense layers: tcgen05.mma (kind::tf32) with TMEM accumulators, operands staged
+// by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier pipeline, warp-specialised
+// (1 TMA warp, 1 MMA warp, 4 epilogue warps).  sm_100a only.
+//
+// Precision.  The parity bar of this path is fp32 (<= 1e-5 relative against the reference's torch-fp32 result),
+// which a single TF32 product (10-bit mantissa) cannot meet.  Every operand therefore exists as a pair
+//   x = hi + lo,  hi = tf32_round(x),  lo = x - hi   (both stored as fp32 words),
+// and `precision == 3` accumulates  hi*hi + hi*lo + lo*hi  in the same fp32 TMEM accumulator ("3xTF32",
+// relative error ~2^-21).  `precision == 1` issues only hi*hi (fast mode, ~1e-3; documented tolerance).
+// The pairs are produced where the tensors are produced: by this kernel's own epilogue, by the minibatch gather,
+// and by tpp_split_tf32 for tensors that come from elsewhere (weights after an optimizer step, loss gradients).
+//
+// C[m][n] = sum_k A(m,k) * B(n,k).  Each operand is either K-major (rows of the matrix are m / n, the contraction
+// index is contiguous) or MN-major (rows are the contraction index, m / n is contiguous); tcgen05 reads both
+// straight from 128B-swizzled shared memory (instruction-descriptor a_major / b_major bits), so no tensor is ever
+// transposed in memory:
+//   forward        : A = activations [mb][in]   K-major,   B = W  [out][in]   K-major
+//   rollout, vector envs: A = feature-major obs slot [in][N]  MN-major
+//   data gradient  : A = dZ [mb][out]           K-major,   B = W  [out][in]   MN-major  (contraction over out)
+//   weight gradient: A = dZ [mb][out]           MN-major,  B = X  [mb][in]    MN-major  (contraction over mb),
+//                    split over the mb contraction across CTAs, fp32 atomics into the flat gradient.
+//
+// Replaces: nn.Linear forward/backward of MLPModel and the policy heads on cuBLAS (reference
+// common/model.py:954-980, common/policy.py:74-87, autograd of agents/ppo.py:170).
+#include <cuda.h>
+
+#include "tpp_common.cuh"
+
+namespace tpp {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;              // fp32 words per row of a stage = 128 bytes = one 128B-swizzle row
+constexpr int UMMA_K = 8;                // tf32: 32 bytes per MMA k-step
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+constexpr int NUM_THREADS = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+struct Params {
+  int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
+  int npass;                   // 1 (tf32) or 3 (3xTF32)
+  int stages;
+  int kb_per_split;            // k-blocks handled by one blockIdx.z
+  int flags;
+  const float* bias;
+  const float* mask; long long ld_mask;
+  float* out; long long ldc;   // plain fp32 (or atomic accumulation target)
+  float* out_hi; float* out_lo;
+  float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
+  int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
+};
+
+enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8 };
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {   // try_wait suspends the thread in hardware for a bounded time, so this is not a hot spin
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive fp32 columns of the accumulator -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version 1):
+// start address >> 4 | LBO(=1, ignored for swizzled K-major) << 16 | SBO(=1024 B between 8-row groups) << 32 |
+// version 1 << 46 | layout SWIZZLE_128B (2) << 61.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// MN-major 32-bit operands have exactly one legal shared-memory layout on sm_100: "128B swizzle with 32B atoms"
+// (cute::UMMA::Layout_MN_SW128_32B_Atom, LayoutType::SWIZZLE_128B_BASE32B = 1, TMA mode SWIZZLE_128B_ATOM_32B):
+// atoms of 4 k-rows x 128 bytes (32 fp32 along m/n), 32-byte chunks XOR-swizzled by (k-row mod 4).
+// LBO = distance between 32-wide m/n blocks (= BLOCK_K rows x 128 B, one TMA box column block),
+// SBO = distance between 4-row k groups (= 512 B, rows are contiguous).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  constexpr uint64_t LBO = (BLOCK_K * 128) >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (LBO << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The kernel: one 128 x BLOCK_N output tile (x one k-split) per CTA
+// ---------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), a_major bit 15,
+  // b_major bit 16 (1 = MN-major), N>>3 at bit 17, M>>4 at bit 24
+  const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                         ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                         ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nops = p.npass == 3 ? 2 : 1;
+  const int stage_bytes = (A_BYTES + B_BYTES) * nops;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, total_kb - kb0);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % p.stages;
+        const uint32_t ph = (kb / p.stages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, (uint32_t)stage_bytes);
+        uint8_t* st = smem + s * stage_bytes;
+        const int kc = (kb0 + kb) * BLOCK_K;
+        // K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n}
+        if (p.a_mn) tma_load_3d(&tmA_hi, full_bar + s, st, 0, kc, m0 >> 5); else tma_load_2d(&tmA_hi, full_bar + s, st, kc, m0);
+        if (p.b_mn) tma_load_3d(&tmB_hi, full_bar + s, st + A_BYTES * nops, 0, kc, n0 >> 5);
+        else tma_load_2d(&tmB_hi, full_bar + s, st + A_BYTES * nops, kc, n0);
+        if (nops == 2) {
+          if (p.a_mn) tma_load_3d(&tmA_lo, full_bar + s, st + A_BYTES, 0, kc, m0 >> 5);
+          else tma_load_2d(&tmA_lo, full_bar + s, st + A_BYTES, kc, m0);
+          if (p.b_mn) tma_load_3d(&tmB_lo, full_bar + s, st + A_BYTES * 2 + B_BYTES, 0, kc, n0 >> 5);
+          else tma_load_2d(&tmB_lo, full_bar + s, st + A_BYTES * 2 + B_BYTES, kc, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % p.stages;
+      const uint32_t ph = (kb / p.stages) & 1;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
+        const uint32_t a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + A_BYTES * nops;
+        const uint32_t b_lo = b_hi + B_BYTES;
+        // small terms first, then hi*hi
+        for (int pass = p.npass - 1; pass >= 0; --pass) {
+          const uint32_t a = (pass == 2) ? a_lo : a_hi;
+          const uint32_t b = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t acc = (kb > 0 || pass != p.npass - 1 || k > 0) ? 1u : 0u;
+            // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
+            const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4);
+            const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4);
+            umma_tf32(tmem_base, da, db, IDESC, acc);
+          }
+        }
+        umma_commit(empty_bar + s);                 // frees the smem stage when these MMAs retire
+        if (kb == nkb - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int m = m0 + quarter * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool row_ok = m < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+      float v[16];
+      tmem_ld16(t_row + (uint32_t)c, v);
+      const int n = n0 + c;
+      if (n >= p.N) break;
+      if (p.flags & F_ATOMIC) {
+        if (row_ok && nkb > 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.N) atomicAdd(p.out + (long long)m * p.ldc + n + j, v[j]);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = v[j];
+        if ((p.flags & F_BIAS) && n + j < p.N) x += __ldg(p.bias + n + j);
+        if (p.flags & F_RELU) x = fmaxf(x, 0.0f);
+        v[j] = x;
+      }
+      if ((p.flags & F_MASK) && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < p.N && !(p.mask[(long long)m * p.ld_mask + n + j] > 0.0f)) v[j] = 0.0f;
+      }
+      float hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        hi[j] = tf32_round(v[j]);
+        lo[j] = v[j] - hi[j];
+      }
+      const bool full16 = (n + 16 <= p.N) && ((p.ldc & 3) == 0);
+      if (row_ok) {
+        float* rows[3] = {p.out, p.out_hi, p.out_lo};
+        const float* src[3] = {v, hi, lo};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (!rows[a]) continue;
+          float* dst = rows[a] + (long long)m * p.ldc + n;
+          if (full16) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(src[a][j], src[a][j + 1], src[a][j + 2], src[a][j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.N) dst[j] = src[a][j];
+          }
+        }
+      }
+      if (p.colsum) {   // column sums of this warp's 32 rows (rows >= M contribute zero), one atomic per column
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float t = row_ok ? v[j] : 0.0f;
+          t = warp_sum(t);
+          if (lane == j && n + j < p.N) atomicAdd(p.colsum + n + j, t);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// x -> (hi, lo) [+ transposed (hi, lo)]; rows x cols, source row stride ld_in, destination row stride ld_out
+// (columns in [cols, ld_out) are zero-filled so that padded operands stay exact).
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, long long ld_in, int rows, int cols,
+                                                         float* __restrict__ hi, float* __restrict__ lo,
+                                                         long long ld_out, float* __restrict__ t_hi,
+                                                         float* __restrict__ t_lo, long long ld_t) {
+  __shared__ float th[32][33], tl[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + i * 8, c = c0 + tx;
+    float v = 0.0f;
+    if (r < rows && c < cols) v = x[(long long)r * ld_in + c];
+    const float h = tf32_round(v), l = v - h;
+    if (r < rows && c < ld_out) {
+      if (hi) hi[(long long)r * ld_out + c] = h;
+      if (lo) lo[(long long)r * ld_out + c] = l;
+    }
+    th[ty + i * 8][tx] = h;
+    tl[ty + i * 8][tx] = l;
+  }
+  if (!t_hi) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + i * 8, r = r0 + tx;       // transposed: row index of the output is the source column
+    if (c < cols && r < ld_t) {
+      const bool in = r < rows;
+      t_hi[(long long)c * ld_t + r] = in ? th[tx][ty + i * 8] : 0.0f;
+      t_lo[(long long)c * ld_t + r] = in ? tl[tx][ty + i * 8] : 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+// K-major operand: matrix [rows][ld] with the contraction index contiguous; box = {32 k, box_rows}.
+// MN-major operand: matrix [K rows][ld] with the m/n index contiguous; viewed as a 3-D tensor
+// (32 m/n, K rows, blocks of 32 m/n) so that one TMA box {32, 32 k-rows, box_rows/32} lands in shared memory as the
+// canonical MN-major SW128_32B layout (atoms 4 k-rows x 128 B; m/n blocks BLOCK_K*128 B apart).
+// cuTensorMapEncodeTiled is a driver-API symbol: resolve it through the runtime at first use so that the library has
+// no link-time dependency on libcuda.so (it must load, and export its symbols, on machines without a driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, int K, int box_rows, int mn_major) {
+  if (!base) return TPP_EINVAL;
+  EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled();
+  if (!cuTensorMapEncodeTiled) return TPP_ENOTSUP;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3)) return TPP_EINVAL;   // TMA: 16-byte address and stride
+  CUresult r;
+  cuuint32_t estr[3] = {1, 1, 1};
+  if (!mn_major) {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    if (box_rows < 32) return TPP_ENOTSUP;
+    const long long blocks = (rows + 31) / 32;
+    if (ld < blocks * 32) return TPP_EINVAL;         // the last 32-wide block must lie inside the (padded) row
+    cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)blocks};
+    cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, 128};
+    cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)(box_rows / 32)};
+    r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
+}
+
+template <int BLOCK_N>
+static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  const int npass = g->precision == 3 ? 3 : 1;
+  int rc;
+  if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn))) return rc;
+  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn))) return rc;
+  if (npass == 3) {
+    if ((rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn))) return rc;
+    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn))) return rc;
+  } else {
+    tmA_lo = tmA_hi;
+    tmB_lo = tmB_hi;
+  }
+  Params p;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.npass = npass; p.flags = g->flags;
+  p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
+  p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
+  p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
+  const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  p.kb_per_split = (total_kb + split_k - 1) / split_k;
+  split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  const int stage_bytes = (A_BYTES + BLOCK_N * BLOCK_K * 4) * (npass == 3 ? 2 : 1);
+  int stages = (220 * 1024 - 1024 - 256) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, split_k);
+  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  TPP_LAUNCH_STATUS();
+}
+
+}  // namespace tc
+}  // namespace tpp
+
+extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
+  TPP_CHECK_ARG(g && g->a_hi && g->b_hi && g->M > 0 && g->N > 0 && g->K > 0);
+  TPP_CHECK_ARG(g->precision == 1 || (g->precision == 3 && g->a_lo && g->b_lo));
+  const bool atomic = g->flags & tpp::tc::F_ATOMIC;
+  TPP_CHECK_ARG(!atomic || g->out);
+  TPP_CHECK_ARG(g->split_k <= 1 || atomic);
+  TPP_CHECK_ARG(!(g->flags & tpp::tc::F_BIAS) || g->bias);
+  TPP_CHECK_ARG(!(g->flags & tpp::tc::F_MASK) || g->mask);
+  TPP_CHECK_ARG((g->out_hi == nullptr) == (g->out_lo == nullptr));
+  cudaStream_t s = tpp_stream(stream);
+  int bn = g->block_n;
+  if (bn == 0) bn = g->N <= 16 ? 16 : (g->N <= 64 ? 64 : 128);
+  switch (bn) {
+    case 16: return tpp::tc::launch<16>(g, g->split_k, s);
+    case 64: return tpp::tc::launch<64>(g, g->split_k, s);
+    case 128: return tpp::tc::launch<128>(g, g->split_k, s);
+    case 256: return tpp::tc::launch<256>(g, g->split_k, s);
+    default: return TPP_ENOTSUP;
+  }
+}
+
+extern "C" int tpp_split_tf32(const float* x, int64_t ld_in, int32_t rows, int32_t cols, float* hi, float* lo,
+                              int64_t ld_out, float* t_hi, float* t_lo, int64_t ld_t, void* stream) {
+  TPP_CHECK_ARG(x && rows > 0 && cols > 0 && ld_in >= cols);
+  TPP_CHECK_ARG((hi == nullptr) == (lo == nullptr) && (t_hi == nullptr) == (t_lo == nullptr) && (hi || t_hi));
+  TPP_CHECK_ARG(!hi || ld_out >= cols);
+  TPP_CHECK_ARG(!t_hi || ld_t >= rows);
+  const int64_t ext_c = hi && ld_out > cols ? ld_out : cols, ext_r = t_hi && ld_t > rows ? ld_t : rows;
+  dim3 grid(tpp_ceil_div(ext_c, 32), tpp_ceil_div(ext_r, 32));
+  tpp::tc::split_tf32_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(x, ld_in, rows, cols, hi, lo, ld_out, t_hi, t_lo,
+                                                                   ld_t);
+  TPP_LAUNCH_STATUS();
+}

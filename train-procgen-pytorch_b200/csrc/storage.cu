@@ -92,6 +92,12 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const do
 // output [mb][ld_out] is written fully coalesced; the 4-byte reads from the feature-major rollout are
 // scattered by construction (random sample indices).  Thread (k, 0) also moves the per-sample scalars.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 struct GatherScalars {
   const int32_t* act; const float* logp; const float* value; const float* ret; const float* adv; const uint8_t* done;
   int32_t* o_act; float* o_logp; float* o_value; float* o_ret; float* o_adv; float* o_done;
@@ -108,21 +114,30 @@ __device__ __forceinline__ void gather_scalars(const GatherScalars& g, int64_t s
 
 __global__ void __launch_bounds__(256) gather_vec_kernel(const int64_t* __restrict__ idx, int mb, int N, int64_t ld,
                                                          int n_obs, const float* __restrict__ obs, GatherScalars g,
-                                                         float* __restrict__ out_obs, int ld_out) {
+                                                         float* __restrict__ out_obs, float* __restrict__ out_lo,
+                                                         int ld_out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)mb * ld_out) return;
   const int k = (int)(i / ld_out), j = (int)(i % ld_out);
   const int64_t flat = idx[k];
   const int64_t t = flat / N, e = flat % N;
-  out_obs[i] = j < n_obs ? obs[(t * n_obs + j) * ld + e] : 0.0f;
+  const float v = j < n_obs ? obs[(t * n_obs + j) * ld + e] : 0.0f;
+  if (out_lo) {             // TF32 pair for the tensor-core policy (hi in out_obs, residual in out_lo)
+    const float h = tf32_hi(v);
+    out_obs[i] = h;
+    out_lo[i] = v - h;
+  } else {
+    out_obs[i] = v;
+  }
   if (j == 0) gather_scalars(g, t * ld + e, k);
 }
 
 // frames uint8 NHWC -> float NCHW / 255.  One CTA (128 threads) per sample: the H*W*C contiguous bytes of
 // the frame are staged through shared memory with 4-byte loads, then written channel-major.
-__global__ void __launch_bounds__(128) gather_img_kernel(const int64_t* __restrict__ idx, int mb, int N, int HW, int C,
-                                                         const uint8_t* __restrict__ frames, GatherScalars g,
-                                                         float* __restrict__ out_obs, int ld_out) {
+__global__ void __launch_bounds__(128) gather_img_kernel(const int64_t* __restrict__ idx, int mb, int N, int64_t ld,
+                                                         int HW, int C, const uint8_t* __restrict__ frames,
+                                                         GatherScalars g, float* __restrict__ out_obs,
+                                                         float* __restrict__ out_lo, int ld_out) {
   extern __shared__ uint8_t px[];
   const int k = blockIdx.x;
   const int64_t flat = idx ? idx[k] : k;
@@ -142,9 +157,15 @@ __global__ void __launch_bounds__(128) gather_img_kernel(const int64_t* __restri
       const int c = o / HW, p = o % HW;
       v = (float)px[p * C + c] / 255.0f;
     }
-    dst[o] = v;
+    if (out_lo) {
+      const float h = tf32_hi(v);
+      dst[o] = h;
+      out_lo[(int64_t)k * ld_out + o] = v - h;
+    } else {
+      dst[o] = v;
+    }
   }
-  if (threadIdx.x == 0 && idx) gather_scalars(g, flat, k);
+  if (threadIdx.x == 0 && idx) gather_scalars(g, (flat / N) * ld + (flat % N), k);
 }
 
 }  // namespace tpp
@@ -170,38 +191,39 @@ extern "C" int tpp_adv_normalize(float* adv, const double* moments, int32_t T, i
 
 extern "C" int tpp_gather_vec(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t n_obs, const float* obs,
                               const int32_t* act, const float* logp, const float* value, const float* ret,
-                              const float* adv, const uint8_t* done, float* out_obs, int32_t ld_out,
-                              int32_t* out_act, float* out_logp, float* out_value, float* out_ret, float* out_adv,
-                              float* out_done, void* stream) {
+                              const float* adv, const uint8_t* done, float* out_obs, float* out_obs_lo,
+                              int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value, float* out_ret,
+                              float* out_adv, float* out_done, void* stream) {
   TPP_CHECK_ARG(idx && obs && out_obs && mb > 0 && N > 0 && ld >= N && n_obs > 0 && ld_out >= n_obs);
   tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
   const int64_t total = (int64_t)mb * ld_out;
   tpp::gather_vec_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(idx, mb, N, ld, n_obs, obs, g,
-                                                                                   out_obs, ld_out);
+                                                                                   out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }
 
-extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int32_t H, int32_t W, int32_t C,
+extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_t H, int32_t W, int32_t C,
                               const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
                               const float* ret, const float* adv, const uint8_t* done, float* out_obs,
-                              int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value, float* out_ret,
-                              float* out_adv, float* out_done, void* stream) {
-  TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && H > 0 && W > 0 && C > 0 && ld_out >= H * W * C);
+                              float* out_obs_lo, int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value,
+                              float* out_ret, float* out_adv, float* out_done, void* stream) {
+  TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && ld >= N && H > 0 && W > 0 && C > 0 &&
+                ld_out >= H * W * C);
   const int bytes = H * W * C;
   TPP_CHECK_ARG(bytes <= 48 * 1024);
   tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
-  tpp::gather_img_kernel<<<mb, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(idx, mb, N, H * W, C, frames, g, out_obs,
-                                                                            ld_out);
+  tpp::gather_img_kernel<<<mb, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(idx, mb, N, ld, H * W, C, frames, g,
+                                                                            out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }
 
 extern "C" int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
-                                 int32_t ld_out, void* stream) {
+                                 float* out_obs_lo, int32_t ld_out, void* stream) {
   TPP_CHECK_ARG(frames && out_obs && N > 0 && ld_out >= H * W * C);
   const int bytes = H * W * C;
   TPP_CHECK_ARG(bytes <= 48 * 1024);
   tpp::GatherScalars g{};
-  tpp::gather_img_kernel<<<N, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(nullptr, N, N, H * W, C, frames, g, out_obs,
-                                                                           ld_out);
+  tpp::gather_img_kernel<<<N, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(nullptr, N, N, N, H * W, C, frames, g,
+                                                                           out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }

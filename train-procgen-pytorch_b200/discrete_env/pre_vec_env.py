@@ -75,7 +75,7 @@ class PreVecEnv:
         self.observation_space = Box(self.low[self.non_drop_index], self.high[self.non_drop_index])
         self.n_inputs = self.n_state
 
-        self.ld = _round_up(self.n_envs, 4)
+        self.ld = _round_up(self.n_envs, 32)
         dev = self.device
         # two private rollout slots (ping-pong) used when the env is stepped stand-alone; inside PPO.train the
         # kernel writes straight into the Storage slots instead (step_into).
