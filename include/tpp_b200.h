@@ -202,6 +202,7 @@ typedef struct {
   const float* mask; int64_t ld_mask;
   float* out; float* out_hi; float* out_lo; int64_t ldc;
   float* colsum;
+  void* dbg;          /* optional int64[8]: clock64 timeline of CTA (0,0,0) — profiling aid, normally NULL */
 } tpp_tc_gemm;
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 

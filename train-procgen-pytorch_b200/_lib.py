@@ -53,7 +53,7 @@ class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
                 ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("_pad", C.c_int32),
                 ("bias", C.c_void_p), ("mask", C.c_void_p), ("ld_mask", C.c_int64),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
-                ("colsum", C.c_void_p)]
+                ("colsum", C.c_void_p), ("dbg", C.c_void_p)]
 
 
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}

@@ -26,6 +26,7 @@ template <> struct Fam<TPP_CARTPOLE>       { static constexpr int NS = 9,  NO = 
 template <> struct Fam<TPP_CARTPOLE_SWING> { static constexpr int NS = 9,  NO = 9,  DYN = 0; };
 template <> struct Fam<TPP_MOUNTAIN_CAR>   { static constexpr int NS = 5,  NO = 5,  DYN = 0; };
 template <> struct Fam<TPP_ACROBOT>        { static constexpr int NS = 12, NO = 14, DYN = 4; };
+template <> struct Fam<TPP_LUNAR_LANDER>   { static constexpr int NS = 8,  NO = 8,  DYN = 0; };
 
 // ------------------------------------------------------------------------------------------------
 // Dynamics (one env, registers only).  fp32 with IEEE division and accurate sin/cos: the one-step
@@ -137,6 +138,90 @@ __device__ __forceinline__ void transition<TPP_ACROBOT>(float* s, int a, const E
   s[3] = fminf(fmaxf(y[3], -c.p[1]), c.p[1]);
   term = (-cosf(s[0]) - cosf(s[1] + s[0])) > 1.0f;
   rew = term ? 0.0f : -1.0f;
+}
+
+// lunar_lander_pre_vec: the reference has no implementation (discrete_env/lunar_lander_pre_vec.py:16 raises; the
+// rest of that file is Gymnasium's scalar Box2D lander).  Own vectorised semantics, restated in oracle/lunar.py
+// ("parity unpinned"): one rigid hull, two massless legs as spring-damper foot contacts on flat ground at the
+// helipad height, no engine dispersion, dt = 1/50.  Taken from the reference file: observation layout and
+// normalisation (:606-615), engine impulse geometry (:520-601), reward shaping (:617-633), terminal rewards.
+// State == the 8-wide normalised observation [x, y, vx, vy, angle, 20*omega/FPS, leg1, leg2].
+__device__ __forceinline__ float lander_shaping(const float* s) {
+  return -100.0f * sqrtf(s[0] * s[0] + s[1] * s[1]) - 100.0f * sqrtf(s[2] * s[2] + s[3] * s[3]) -
+         100.0f * fabsf(s[4]) + 10.0f * s[6] + 10.0f * s[7];
+}
+
+template <>
+__device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, const EnvParams& c, float& rew,
+                                                              bool& term) {
+  constexpr float FPS = 50.0f, SC = 30.0f, W2 = 10.0f, H2 = 400.0f / 30.0f / 2.0f;
+  constexpr float PAD = (400.0f / 30.0f) / 4.0f, LEG_DOWN = 18.0f / SC, DT = 1.0f / FPS;
+  constexpr float MASS = 4.82f, INERTIA = 0.84f;
+  constexpr float K_N = 1500.0f, C_N = 60.0f, C_T = 30.0f, MU = 1.0f;
+  const float gravity = c.p[0], main_power = c.p[1], side_power = c.p[2];
+  const float prev = lander_shaping(s);
+  float x = s[0] * W2 + W2, y = s[1] * H2 + (PAD + LEG_DOWN);
+  float vx = s[2] * FPS / W2, vy = s[3] * FPS / H2, ang = s[4], om = s[5] * FPS / 20.0f;
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  const float tipx = sn, tipy = cs, sidex = -cs, sidey = sn;
+  const float mainf = (a == 2) ? 1.0f : 0.0f;
+  {
+    const float ox = tipx * (4.0f / SC), oy = -tipy * (4.0f / SC);
+    const float jx = -ox * main_power * mainf, jy = -oy * main_power * mainf;
+    vx += jx / MASS;
+    vy += jy / MASS;
+    om += (ox * jy - oy * jx) / INERTIA;
+  }
+  const float sidef = (a == 1 || a == 3) ? 1.0f : 0.0f;
+  {
+    const float d = (float)(a - 2) * sidef;
+    const float ox = sidex * (d * 12.0f / SC), oy = -sidey * (d * 12.0f / SC);
+    const float jx = -ox * side_power, jy = -oy * side_power;
+    const float rx = ox - tipx * 17.0f / SC, ry = oy + tipy * 14.0f / SC;
+    vx += jx / MASS;
+    vy += jy / MASS;
+    om += (rx * jy - ry * jx) / INERTIA * sidef;
+  }
+  const float footx[2] = {-20.0f / SC, 20.0f / SC}, footy = -26.0f / SC;
+  float fx = 0.0f, fy = 0.0f, tq = 0.0f;
+#pragma unroll
+  for (int f = 0; f < 2; ++f) {
+    const float rx = cs * footx[f] - sn * footy, ry = sn * footx[f] + cs * footy;
+    const float pen = PAD - (y + ry);
+    if (pen > 0.0f) {
+      const float vfx = vx - om * ry, vfy = vy + om * rx;
+      const float fn = fmaxf(K_N * pen - C_N * vfy, 0.0f);
+      const float ft = fminf(fmaxf(-C_T * vfx, -MU * fn), MU * fn);
+      fx += ft;
+      fy += fn;
+      tq += rx * fn - ry * ft;
+    }
+  }
+  vx += fx * DT / MASS;
+  vy += (fy / MASS - gravity) * DT;
+  om += tq * DT / INERTIA;
+  x += vx * DT;
+  y += vy * DT;
+  ang += om * DT;
+  sincosf(ang, &sn, &cs);
+  const float c0 = (y + sn * footx[0] + cs * footy <= PAD) ? 1.0f : 0.0f;
+  const float c1 = (y + sn * footx[1] + cs * footy <= PAD) ? 1.0f : 0.0f;
+  const float hull = fminf(y + sn * (-17.0f / SC) + cs * (-10.0f / SC), y + sn * (17.0f / SC) + cs * (-10.0f / SC));
+  s[0] = (x - W2) / W2;
+  s[1] = (y - (PAD + LEG_DOWN)) / H2;
+  s[2] = vx * W2 / FPS;
+  s[3] = vy * H2 / FPS;
+  s[4] = ang;
+  s[5] = 20.0f * om / FPS;
+  s[6] = c0;
+  s[7] = c1;
+  rew = lander_shaping(s) - prev - 0.30f * mainf - 0.03f * sidef;
+  const bool crashed = (hull <= PAD) | (fabsf(s[0]) >= 1.0f);
+  const bool landed = (c0 > 0.0f) & (c1 > 0.0f) & (fabsf(vx) < 0.05f) & (fabsf(vy) < 0.05f) & (fabsf(om) < 0.05f) & !crashed;
+  if (crashed) rew = -100.0f;
+  if (landed) rew = 100.0f;
+  term = crashed | landed;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -362,6 +447,9 @@ extern "C" int tpp_env_step(const tpp_env_cfg* cfg, const float* obs_in, float* 
       TPP_CHECK_ARG(dyn_state);
       return tpp::launch_step<TPP_ACROBOT>(cfg, obs_in, obs_out, dyn_state, action, step_ctr, rew_out, done_out,
                                            reset_rows, tick, t_offset, ld, s);
+    case TPP_LUNAR_LANDER:
+      return tpp::launch_step<TPP_LUNAR_LANDER>(cfg, obs_in, obs_out, nullptr, action, step_ctr, rew_out, done_out,
+                                                reset_rows, tick, t_offset, ld, s);
     default:
       return TPP_ENOTSUP;
   }
@@ -388,6 +476,9 @@ extern "C" int tpp_env_reset(const tpp_env_cfg* cfg, float* obs_out, float* dyn_
     case TPP_ACROBOT:
       TPP_CHECK_ARG(dyn_state);
       tpp::env_reset_kernel<TPP_ACROBOT><<<grid, 256, 0, s>>>(p, obs_out, dyn_state, step_ctr, reset_rows, tick, t_offset, ld);
+      break;
+    case TPP_LUNAR_LANDER:
+      tpp::env_reset_kernel<TPP_LUNAR_LANDER><<<grid, 256, 0, s>>>(p, obs_out, nullptr, step_ctr, reset_rows, tick, t_offset, ld);
       break;
     default:
       return TPP_ENOTSUP;

@@ -33,13 +33,17 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;              // fp32 words per row of a stage = 128 bytes = one 128B-swizzle row
 constexpr int UMMA_K = 8;                // tf32: 32 bytes per MMA k-step
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
-constexpr int NUM_THREADS = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int EPI_WARPS = 16;            // 4 per TMEM lane quarter: the epilogue is instruction-latency bound, not bandwidth bound
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
+constexpr int STG_PITCH = 36;            // floats per staged row (16-byte aligned, conflict-free 128-bit LDS/STS)
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;   // one 32x32 patch per epilogue warp
 
 struct Params {
   int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
   int npass;                   // 1 (tf32) or 3 (3xTF32)
   int stages;
   int kb_per_split;            // k-blocks handled by one blockIdx.z
+  int bar_offset;              // byte offset of the mbarriers behind the stage / staging region
   int flags;
   const float* bias;
   const float* mask; long long ld_mask;
@@ -47,6 +51,7 @@ struct Params {
   float* out_hi; float* out_lo;
   float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
   int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
+  long long* dbg;              // optional timeline probe (block 0 only): clock64 at 8 milestones
 };
 
 enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8 };
@@ -129,6 +134,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version 1):
 // start address >> 4 | LBO(=1, ignored for swizzled K-major) << 16 | SBO(=1024 B between 8-row groups) << 32 |
 // version 1 << 46 | layout SWIZZLE_128B (2) << 61.
@@ -146,10 +167,12 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (LBO << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 
+// Round to TF32 (10-bit mantissa), nearest with ties away from zero — the same result as `cvt.rna.tf32.f32`, but
+// as two full-rate integer ops: measured on B200 the cvt form issues at ~1 warp instruction per 32-64 cycles and
+// made the epilogue 10x slower (profiles/README.md).  Adding half an ulp to the magnitude bits and truncating is
+// exact for all finite values (a carry into the exponent is the correct rounding).
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -167,17 +190,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                          ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                          ((uint32_t)(BLOCK_M >> 4) << 24);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 128B-swizzled tiles need 1024-byte alignment.  The alignment is requested on the declaration (and checked) instead
+  // of rounding the address through an integer: that cast loses the shared address space and turns every staging
+  // access into a generic LD/ST (measured: ~430 cycles per dependent access instead of ~30).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int nops = p.npass == 3 ? 2 : 1;
   const int stage_bytes = (A_BYTES + B_BYTES) * nops;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
+  if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, total_kb - kb0);
@@ -198,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) TPP_PROBE(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -206,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int s = kb % p.stages;
         const uint32_t ph = (kb / p.stages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
+        if (kb == 0) TPP_PROBE(2);
         mbar_expect_tx(full_bar + s, (uint32_t)stage_bytes);
         uint8_t* st = smem + s * stage_bytes;
         const int kc = (kb0 + kb) * BLOCK_K;
@@ -228,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t ph = (kb / p.stages) & 1;
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
+      if (kb == 0) TPP_PROBE(3);
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
         const uint32_t a_lo = a_hi + A_BYTES;
@@ -247,82 +280,183 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         umma_commit(empty_bar + s);                 // frees the smem stage when these MMAs retire
-        if (kb == nkb - 1) umma_commit(tmem_full);  // accumulator complete
+        if (kb == nkb - 1) { umma_commit(tmem_full); TPP_PROBE(4); }  // accumulator complete
       }
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> (bias / relu / mask / tf32 split) -> coalesced global ====
+    // A thread owns one accumulator ROW (TMEM lane).  Writing rows directly would touch 32 different 128-byte lines
+    // per store instruction, so each warp first transposes 32x32 blocks through a private shared-memory patch; after
+    // that a lane owns 4 fixed COLUMNS of 8 rows: bias is 4 registers, mask / output accesses are full 128-byte
+    // lines (8 lanes per row, 4 rows per instruction), column sums are register accumulations.  EPI_WARPS/4 warps serve each
+    // TMEM lane quarter (column groups round-robin).  The pipeline stages are free by now (tmem_full => all MMAs
+    // retired), the patches alias them.
+    const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
+    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
+    const int mrow0 = m0 + quarter * 32;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* stg = reinterpret_cast<float*>(smem) + ew * (32 * STG_PITCH);
+    constexpr int GW = BLOCK_N < 32 ? BLOCK_N : 32;     // columns per staged group
+    const int rr = lane >> 3, cc = (lane & 7) * 4;      // post-transpose mapping: 4 rows x (8 lanes x 4 columns)
+    const bool atomic = p.flags & F_ATOMIC;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int m = m0 + quarter * 32 + lane;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const bool row_ok = m < p.M;
+    if (warp == 2) TPP_PROBE(5);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-      float v[16];
-      tmem_ld16(t_row + (uint32_t)c, v);
+    for (int c = half * GW; c < BLOCK_N; c += (EPI_WARPS / 4) * GW) {
       const int n = n0 + c;
       if (n >= p.N) break;
-      if (p.flags & F_ATOMIC) {
-        if (row_ok && nkb > 0) {
+      float v[GW];
+      if (GW == 32) tmem_ld32(t_row + (uint32_t)c, v); else tmem_ld16(t_row + (uint32_t)c, v);
+      if (warp == 2 && c == 0) TPP_PROBE(8);
+      __syncwarp();                                     // previous group's readers are done with the patch
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < p.N) atomicAdd(p.out + (long long)m * p.ldc + n + j, v[j]);
+      for (int j = 0; j < GW; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      if (warp == 2 && c == 0) TPP_PROBE(9);
+      const bool lane_on = cc < GW;                     // (BLOCK_N == 16: lanes owning columns >= 16 idle)
+      const int nc = n + cc;                            // first of this lane's 4 columns
+      const bool cols4 = lane_on && nc + 4 <= p.N;
+      float b4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.flags & F_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (lane_on && nc + j < p.N) b4[j] = __ldg(p.bias + nc + j);
+      }
+      float cs4[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool vec = cols4 && ((p.ldc & 3) == 0);
+      // Fast path: interior 32x32 block, everything 16-byte aligned -> branch-free body with running pointers.
+      const bool interior = lane_on && (mrow0 + 32 <= p.M) && (n + GW <= p.N) && ((p.ldc & 3) == 0) &&
+                            (((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out_hi) |
+                               reinterpret_cast<uintptr_t>(p.out_lo)) & 15) == 0) &&
+                            (!(p.flags & F_MASK) || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+      if (__all_sync(0xffffffffu, interior || !lane_on) && !atomic) {
+        if (lane_on) {
+          const long long o0 = (long long)(mrow0 + rr) * p.ldc + nc, ostep = 4 * p.ldc;
+          float* po = p.out ? p.out + o0 : nullptr;
+          float* ph = p.out_hi ? p.out_hi + o0 : nullptr;
+          float* pl = p.out_lo ? p.out_lo + o0 : nullptr;
+          const float* pm = (p.flags & F_MASK) ? p.mask + (long long)(mrow0 + rr) * p.ld_mask + nc : nullptr;
+          const long long mstep = 4 * p.ld_mask;
+          const float floor_v = (p.flags & F_RELU) ? 0.0f : -3.402823466e38f;
+          const float* sp = stg + rr * STG_PITCH + cc;
+#pragma unroll 2
+          for (int it = 0; it < 8; ++it) {
+            const float4 q = *reinterpret_cast<const float4*>(sp + it * 4 * STG_PITCH);
+            float x[4] = {fmaxf(q.x + b4[0], floor_v), fmaxf(q.y + b4[1], floor_v), fmaxf(q.z + b4[2], floor_v),
+                          fmaxf(q.w + b4[3], floor_v)};
+            if (pm) {
+              const float4 mq = *reinterpret_cast<const float4*>(pm);
+              pm += mstep;
+              x[0] = mq.x > 0.0f ? x[0] : 0.0f;
+              x[1] = mq.y > 0.0f ? x[1] : 0.0f;
+              x[2] = mq.z > 0.0f ? x[2] : 0.0f;
+              x[3] = mq.w > 0.0f ? x[3] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cs4[j] += x[j];
+            if (po) { *reinterpret_cast<float4*>(po) = make_float4(x[0], x[1], x[2], x[3]); po += ostep; }
+            if (ph) {
+              const float h0 = tf32_round(x[0]), h1 = tf32_round(x[1]), h2 = tf32_round(x[2]), h3 = tf32_round(x[3]);
+              *reinterpret_cast<float4*>(ph) = make_float4(h0, h1, h2, h3);
+              *reinterpret_cast<float4*>(pl) = make_float4(x[0] - h0, x[1] - h1, x[2] - h2, x[3] - h3);
+              ph += ostep;
+              pl += ostep;
+            }
+          }
         }
-        continue;
-      }
+      } else
+      // Generic path (edges, unaligned, atomic accumulation).
+      // NOT unrolled: the body is ~200 instructions; eight unrolled copies (x2 groups, x4 template instances) do not
+      // fit the instruction caches and every iteration then stalls ~400 cycles on instruction fetch (measured).
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rr, gm = mrow0 + r;
+        const float4 q = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cc);
+        float x[4] = {q.x, q.y, q.z, q.w};
+        if (gm >= p.M || !lane_on) continue;
+        const long long off = (long long)gm * p.ldc + nc;
+        if (atomic) {
+          if (nkb > 0) {
+            float* dst = p.out + off;
+            if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]),
+                           "f"(x[3])
+                           : "memory");
+            } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = v[j];
-        if ((p.flags & F_BIAS) && n + j < p.N) x += __ldg(p.bias + n + j);
-        if (p.flags & F_RELU) x = fmaxf(x, 0.0f);
-        v[j] = x;
-      }
-      if ((p.flags & F_MASK) && row_ok) {
+              for (int j = 0; j < 4; ++j)
+                if (nc + j < p.N) atomicAdd(dst + j, x[j]);
+            }
+          }
+          continue;
+        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n + j < p.N && !(p.mask[(long long)m * p.ld_mask + n + j] > 0.0f)) v[j] = 0.0f;
-      }
-      float hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        hi[j] = tf32_round(v[j]);
-        lo[j] = v[j] - hi[j];
-      }
-      const bool full16 = (n + 16 <= p.N) && ((p.ldc & 3) == 0);
-      if (row_ok) {
-        float* rows[3] = {p.out, p.out_hi, p.out_lo};
-        const float* src[3] = {v, hi, lo};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          if (!rows[a]) continue;
-          float* dst = rows[a] + (long long)m * p.ldc + n;
-          if (full16) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(src[a][j], src[a][j + 1], src[a][j + 2], src[a][j + 3]);
+        for (int j = 0; j < 4; ++j) {
+          x[j] += b4[j];
+          if (p.flags & F_RELU) x[j] = fmaxf(x[j], 0.0f);
+        }
+        if (p.flags & F_MASK) {
+          const float* mk = p.mask + (long long)gm * p.ld_mask + nc;
+          if (cols4 && ((p.ld_mask & 3) == 0) && (reinterpret_cast<uintptr_t>(mk) & 15) == 0) {
+            const float4 mq = *reinterpret_cast<const float4*>(mk);
+            if (!(mq.x > 0.0f)) x[0] = 0.0f;
+            if (!(mq.y > 0.0f)) x[1] = 0.0f;
+            if (!(mq.z > 0.0f)) x[2] = 0.0f;
+            if (!(mq.w > 0.0f)) x[3] = 0.0f;
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n + j < p.N) dst[j] = src[a][j];
+            for (int j = 0; j < 4; ++j)
+              if (nc + j < p.N && !(mk[j] > 0.0f)) x[j] = 0.0f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cs4[j] += x[j];
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = tf32_round(x[j]);
+          l[j] = x[j] - h[j];
+        }
+        float* outs[3] = {p.out, p.out_hi, p.out_lo};
+        const float* src[3] = {x, h, l};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          if (!outs[a]) continue;
+          float* dst = outs[a] + off;
+          if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(src[a][0], src[a][1], src[a][2], src[a][3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (nc + j < p.N) dst[j] = src[a][j];
           }
         }
       }
-      if (p.colsum) {   // column sums of this warp's 32 rows (rows >= M contribute zero), one atomic per column
+      if (warp == 2 && c == 0) TPP_PROBE(10);
+      if (p.colsum && !atomic) {   // bias gradient: this warp's 32 rows of columns nc..nc+3 (lanes l, l+8, l+16, l+24)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = row_ok ? v[j] : 0.0f;
-          t = warp_sum(t);
-          if (lane == j && n + j < p.N) atomicAdd(p.colsum + n + j, t);
+        for (int j = 0; j < 4; ++j) {
+          cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 8);
+          cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 16);
+        }
+        if (rr == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (lane_on && nc + j < p.N) atomicAdd(p.colsum + nc + j, cs4[j]);
         }
       }
     }
   }
+  if (warp == 2) TPP_PROBE(6);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 1) TPP_PROBE(7);
+#undef TPP_PROBE
 }
 
 // x -> (hi, lo) [+ transposed (hi, lo)]; rows x cols, source row stride ld_in, destination row stride ld_out
@@ -431,17 +565,22 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
   p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
+  p.dbg = reinterpret_cast<long long*>(g->dbg);
   const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
   split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   const int stage_bytes = (A_BYTES + BLOCK_N * BLOCK_K * 4) * (npass == 3 ? 2 : 1);
-  int stages = (220 * 1024 - 1024 - 256) / stage_bytes;
+  int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
   if (stages > 4) stages = 4;
   if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  // the epilogue's transpose patches alias the pipeline stages: the region must hold at least STG_BYTES
+  size_t region = (size_t)stages * stage_bytes;
+  if (region < (size_t)STG_BYTES) region = STG_BYTES;
+  p.bar_offset = (int)region;
+  const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

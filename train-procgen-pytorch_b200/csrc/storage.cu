@@ -92,10 +92,8 @@ __global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const do
 // output [mb][ld_out] is written fully coalesced; the 4-byte reads from the feature-major rollout are
 // scattered by construction (random sample indices).  Thread (k, 0) also moves the per-sample scalars.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+__device__ __forceinline__ float tf32_hi(float x) {   // == cvt.rna.tf32.f32 (see csrc/gemm_tc.cu), full-rate form
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 struct GatherScalars {
