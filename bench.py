@@ -330,7 +330,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}_env_vec PPO: n_envs={N}/GPU, n_steps={T}, "
-                               f"epoch={hp['epoch']}, minibatch={mb}, MLP policy {in_dim}-256-256-256-64 (fp32)",
+                               f"epoch={hp['epoch']}, minibatch={mb}, MLP policy {in_dim}-256-256-256-64 ({args.matmul})",
                    "parallelism": f"env-sharded dp{world}", "l2": "rollout + minibatch working set > L2 (inputs "
                    "larger than 126 MB)" if args.workload == "boxworld" else "small working set (latency-bound)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,

@@ -206,6 +206,16 @@ typedef struct {
 } tpp_tc_gemm;
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
+/* Backward of the policy/value heads ([nh = A+1 <= 16][H] weights) in one kernel: from dhead [mb][ld_head]
+ * (tpp_ppo_loss_fwd_bwd) and the latent activations [mb][ldl] it produces dlatent = dhead @ Wh as a TF32 (hi, lo)
+ * pair [mb][ld_dz] (optionally masked by relu_mask > 0 and/or also as plain fp32), and accumulates
+ * gWh += dhead^T latent, gbh += colsum(dhead), gb_last += colsum(dlatent) (bias gradient of the last embedder layer).
+ * H in {16, 32, 64, 128, 256}.  Replaces autograd through CategoricalPolicy.hidden_to_output
+ * (common/policy.py:74-87).                                                                                  */
+int tpp_head_backward(const float* dhead, int32_t ld_head, const float* latent, const float* relu_mask, int64_t ldl,
+                      const float* Wh, int32_t nh, int32_t H, float* dz_hi, float* dz_lo, float* dz_plain,
+                      int64_t ld_dz, float* gWh, float* gbh, float* gb_last, int32_t mb, void* stream);
+
 /* x [rows][ld_in] -> (hi, lo) [rows][ld_out] (columns >= cols zero-filled) and/or transposed (t_hi, t_lo)
  * [cols][ld_t] (columns >= rows zero-filled): makes a foreign fp32 tensor (gathered observations, weights after an
  * optimizer step, loss gradients) an operand of tpp_gemm_tc.                                                */

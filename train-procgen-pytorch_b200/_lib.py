@@ -84,6 +84,7 @@ SIGNATURES = {
     "tpp_colsum_accum": [_vp, _i64, _i32, _i32, _vp, _vp],
     "tpp_gemm_tc": [C.POINTER(TcGemm), _vp],
     "tpp_split_tf32": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
+    "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
     "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],

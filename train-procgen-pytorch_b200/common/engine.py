@@ -294,18 +294,26 @@ class MLPEngineTC(MLPEngine):
         (x_pair, x_ld) = self._x_pair
         H, nh, L = self.latent, self.A + 1, len(self.layers)
         ldl = ws.h[-1]["ld"]
-        # heads on CUDA cores (tiny): gWh += dhead^T latent ; gbh += colsum ; dlatent = dhead Wh
-        self._gemm(_lib.ptr(dhead), 1, self.ld_head, _lib.ptr(ws.last_plain), 1, ldl, self._g(self.head_w_off), H, None,
-                   None, nh, H, M, EPI_ACCUM, self._split_k(M, nh, H))
-        _lib.call("tpp_colsum_accum", _lib.ptr(dhead), self.ld_head, M, nh, self._g(self.head_b_off), s)
         dz = ws.dz[0]
         last_relu = self.layers[-1][4]
-        self._gemm(_lib.ptr(dhead), self.ld_head, 1, self._p(self.head_w_off), 1, H, _lib.ptr(dz["plain"]), ldl, None,
-                   _lib.ptr(ws.h[-1]["hi"]) if last_relu else None, M, H, nh, EPI_MASK if last_relu else 0)
-        _lib.call("tpp_split_tf32", _lib.ptr(dz["plain"]), ldl, M, H, _lib.ptr(dz["hi"]), _lib.ptr(dz["lo"]), ldl,
-                  None, None, 0, s)
-        _lib.call("tpp_colsum_accum", _lib.ptr(dz["plain"]), ldl, M, H, self._g(self.layers[-1][1]), s)
-        self.n_launches += 3
+        if H in (16, 32, 64, 128, 256) and nh <= 16:
+            # one fused kernel: dlatent (TF32 pair), gWh, gbh and the last embedder layer's bias gradient
+            _lib.call("tpp_head_backward", _lib.ptr(dhead), self.ld_head, _lib.ptr(ws.last_plain),
+                      _lib.ptr(ws.h[-1]["hi"]) if last_relu else None, ldl, self._p(self.head_w_off), nh, H,
+                      _lib.ptr(dz["hi"]), _lib.ptr(dz["lo"]), None, ldl, self._g(self.head_w_off),
+                      self._g(self.head_b_off), self._g(self.layers[-1][1]), M, s)
+            self.n_launches += 1
+        else:
+            # generic shapes: heads on the CUDA-core GEMM: gWh += dhead^T latent ; gbh += colsum ; dlatent = dhead Wh
+            self._gemm(_lib.ptr(dhead), 1, self.ld_head, _lib.ptr(ws.last_plain), 1, ldl, self._g(self.head_w_off), H,
+                       None, None, nh, H, M, EPI_ACCUM, self._split_k(M, nh, H))
+            _lib.call("tpp_colsum_accum", _lib.ptr(dhead), self.ld_head, M, nh, self._g(self.head_b_off), s)
+            self._gemm(_lib.ptr(dhead), self.ld_head, 1, self._p(self.head_w_off), 1, H, _lib.ptr(dz["plain"]), ldl,
+                       None, _lib.ptr(ws.h[-1]["hi"]) if last_relu else None, M, H, nh, EPI_MASK if last_relu else 0)
+            _lib.call("tpp_split_tf32", _lib.ptr(dz["plain"]), ldl, M, H, _lib.ptr(dz["hi"]), _lib.ptr(dz["lo"]), ldl,
+                      None, None, 0, s)
+            _lib.call("tpp_colsum_accum", _lib.ptr(dz["plain"]), ldl, M, H, self._g(self.layers[-1][1]), s)
+            self.n_launches += 3
         cur, ld_dz = 0, ldl
         for i in range(L - 1, -1, -1):
             w_off, b_off, fin, fout, relu = self.layers[i]

@@ -85,17 +85,20 @@ __device__ __forceinline__ void transition<TPP_MOUNTAIN_CAR>(float* s, int a, co
 }
 
 // "book" equations, acrobot_pre_vec.py:359-394.  y = (th1, th2, dth1, dth2); pr = 8 physical parameters.
-__device__ __forceinline__ void acrobot_dsdt(const float* y, float torque, const float* pr, float* dy) {
+// tr = (cos th1, sin th1, cos th2, sin th2) of y: supplied by the caller (stage 1 reuses the previous observation,
+// whose first four columns are exactly these values) so that a stage costs two sincosf instead of sincosf + 2 sinf;
+// sin(th1 + th2) follows from the addition theorem.  The kernel is ALU-bound (ncu: 22 % DRAM), trig dominates.
+__device__ __forceinline__ void acrobot_dsdt(const float* y, const float* tr, float torque, const float* pr, float* dy) {
   const float g = pr[0], l1 = pr[1], m1 = pr[3], m2 = pr[4], lc1 = pr[5], lc2 = pr[6], moi = pr[7];
-  const float th1 = y[0], th2 = y[1], d1v = y[2], d2v = y[3];
-  float s2, c2;
-  sincosf(th2, &s2, &c2);
+  const float d1v = y[2], d2v = y[3];
+  const float c1 = tr[0], s1 = tr[1], c2 = tr[2], s2 = tr[3];
+  const float s12 = s1 * c2 + c1 * s2;
   const float dd1 = m1 * lc1 * lc1 + m2 * (l1 * l1 + lc2 * lc2 + 2.0f * l1 * lc2 * c2) + moi + moi;
   const float dd2 = m2 * (lc2 * lc2 + l1 * lc2 * c2) + moi;
   // cos(x - pi/2) == sin(x): evaluated as sin to avoid the fp32 rounding of the shifted argument
-  const float phi2 = m2 * lc2 * g * sinf(th1 + th2);
+  const float phi2 = m2 * lc2 * g * s12;
   const float phi1 = -m2 * l1 * lc2 * d2v * d2v * s2 - 2.0f * m2 * l1 * lc2 * d2v * d1v * s2 +
-                     (m1 * lc1 + m2 * l1) * g * sinf(th1) + phi2;
+                     (m1 * lc1 + m2 * l1) * g * s1 + phi2;
   const float ddth2 = (torque + dd2 / dd1 * phi1 - m2 * l1 * lc2 * d1v * d1v * s2 - phi2) /
                       (m2 * lc2 * lc2 + moi - dd2 * dd2 / dd1);
   const float ddth1 = -(dd2 * ddth2 + phi1) / dd1;
@@ -117,17 +120,23 @@ __device__ __forceinline__ void transition<TPP_ACROBOT>(float* s, int a, const E
   const float torque = (float)(a - 1);
   const float dt = c.p[2], dt2 = 0.5f * c.p[2];
   const float* pr = s + 4;
-  float k1[4], k2[4], k3[4], k4[4], y[4];
-  acrobot_dsdt(s, torque, pr, k1);
+  float k1[4], k2[4], k3[4], k4[4], y[4], tr[4];
+  acrobot_dsdt(s, s + 12, torque, pr, k1);               // s[12..15] = (cos, sin) of th1, th2 from the previous obs
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = s[i] + dt2 * k1[i];
-  acrobot_dsdt(y, torque, pr, k2);
+  sincosf(y[0], &tr[1], &tr[0]);
+  sincosf(y[1], &tr[3], &tr[2]);
+  acrobot_dsdt(y, tr, torque, pr, k2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = s[i] + dt2 * k2[i];
-  acrobot_dsdt(y, torque, pr, k3);
+  sincosf(y[0], &tr[1], &tr[0]);
+  sincosf(y[1], &tr[3], &tr[2]);
+  acrobot_dsdt(y, tr, torque, pr, k3);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = s[i] + dt * k3[i];
-  acrobot_dsdt(y, torque, pr, k4);
+  sincosf(y[0], &tr[1], &tr[0]);
+  sincosf(y[1], &tr[3], &tr[2]);
+  acrobot_dsdt(y, tr, torque, pr, k4);
 #pragma unroll
   for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / 6.0f * (k1[i] + 2.0f * k2[i] + 2.0f * k3[i] + k4[i]);
   if (fabsf(y[0]) > 3.1415925f) y[0] = wrap_pi(y[0]);   // cheap pre-filter just below pi; exact test in double
@@ -136,7 +145,9 @@ __device__ __forceinline__ void transition<TPP_ACROBOT>(float* s, int a, const E
   s[1] = y[1];
   s[2] = fminf(fmaxf(y[2], -c.p[0]), c.p[0]);
   s[3] = fminf(fmaxf(y[3], -c.p[1]), c.p[1]);
-  term = (-cosf(s[0]) - cosf(s[1] + s[0])) > 1.0f;
+  sincosf(s[0], &s[13], &s[12]);                          // reused by the terminal test and by the observation
+  sincosf(s[1], &s[15], &s[14]);
+  term = (-s[12] - (s[12] * s[14] - s[13] * s[15])) > 1.0f;   // -cos th1 - cos(th1 + th2)
   rew = term ? 0.0f : -1.0f;
 }
 
@@ -279,6 +290,23 @@ template <> struct Vec<4> {
     __stcs(reinterpret_cast<uchar4*>(p), make_uchar4(v[0], v[1], v[2], v[3]));
   }
 };
+template <> struct Vec<2> {
+  static __device__ __forceinline__ void ldf(const float* p, float* o) {
+    const float2 q = __ldcs(reinterpret_cast<const float2*>(p)); o[0] = q.x; o[1] = q.y;
+  }
+  static __device__ __forceinline__ void stf(float* p, const float* v) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  }
+  static __device__ __forceinline__ void ldi(const int32_t* p, int32_t* o) {
+    const int2 q = __ldcs(reinterpret_cast<const int2*>(p)); o[0] = q.x; o[1] = q.y;
+  }
+  static __device__ __forceinline__ void sti(int32_t* p, const int32_t* v) {
+    __stcs(reinterpret_cast<int2*>(p), make_int2(v[0], v[1]));
+  }
+  static __device__ __forceinline__ void stb(uint8_t* p, const uint8_t* v) {
+    *reinterpret_cast<uchar2*>(p) = make_uchar2(v[0], v[1]);
+  }
+};
 template <> struct Vec<1> {
   static __device__ __forceinline__ void ldf(const float* p, float* o) { o[0] = __ldcs(p); }
   static __device__ __forceinline__ void stf(float* p, const float* v) { __stcs(p, v[0]); }
@@ -290,8 +318,8 @@ template <> struct Vec<1> {
 template <int F>
 __device__ __forceinline__ void emit_obs(const float* s, float* o) {
   if (F == TPP_ACROBOT) {
-    sincosf(s[0], &o[1], &o[0]);
-    sincosf(s[1], &o[3], &o[2]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = s[12 + j];        // (cos, sin) pairs cached behind the state
 #pragma unroll
     for (int j = 2; j < 12; ++j) o[j + 2] = s[j];
   } else {
@@ -312,12 +340,14 @@ __global__ void __launch_bounds__(256) env_step_kernel(EnvParams c, const float*
   const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (e0 >= c.n_envs) return;
 
-  float s[NS][VEC];
+  float s[NS + 4][VEC];        // + 4: acrobot's cached (cos, sin) pairs; unused (and eliminated) elsewhere
   int32_t act[VEC], ctr[VEC];
   // ---- all loads first (independent 128-bit requests in flight) ----
   if (DYN) {
 #pragma unroll
     for (int j = 0; j < DYN; ++j) Vec<VEC>::ldf(dyn + j * ld + e0, s[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Vec<VEC>::ldf(obs_in + (int64_t)j * ld + e0, s[NS + j]);
 #pragma unroll
     for (int j = DYN; j < NS; ++j) Vec<VEC>::ldf(obs_in + (int64_t)(j + NO - NS) * ld + e0, s[j]);
   } else {
@@ -332,9 +362,9 @@ __global__ void __launch_bounds__(256) env_step_kernel(EnvParams c, const float*
   uint8_t dn[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    float st[NS], ob[NO];
+    float st[NS + 4], ob[NO];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) st[j] = s[j][i];
+    for (int j = 0; j < NS + (DYN ? 4 : 0); ++j) st[j] = s[j][i];
     bool term;
     transition<F>(st, act[i], c, rew[i], term);
     const int32_t n = ctr[i] + 1;
@@ -345,6 +375,10 @@ __global__ void __launch_bounds__(256) env_step_kernel(EnvParams c, const float*
         for (int j = 0; j < NS; ++j) st[j] = reset_rows[(int64_t)j * ld + e0 + i];
       } else {
         draw_start<F>(st, c, (uint32_t)(e0 + i), tk);
+      }
+      if (F == TPP_ACROBOT) {
+        sincosf(st[0], &st[13], &st[12]);
+        sincosf(st[1], &st[15], &st[14]);
       }
     }
     ctr[i] = done ? 0 : n;
@@ -376,12 +410,16 @@ __global__ void __launch_bounds__(256) env_reset_kernel(EnvParams c, float* obs_
   constexpr int NS = Fam<F>::NS, NO = Fam<F>::NO, DYN = Fam<F>::DYN;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= c.n_envs) return;
-  float st[NS], ob[NO];
+  float st[NS + 4], ob[NO];
   if (reset_rows) {
 #pragma unroll
     for (int j = 0; j < NS; ++j) st[j] = reset_rows[(int64_t)j * ld + e];
   } else {
     draw_start<F>(st, c, (uint32_t)e, (tick ? *tick : 0ull) + t_offset);
+  }
+  if (F == TPP_ACROBOT) {
+    sincosf(st[0], &st[13], &st[12]);
+    sincosf(st[1], &st[15], &st[14]);
   }
   emit_obs<F>(st, ob);
 #pragma unroll
@@ -412,7 +450,13 @@ static int launch_step(const tpp_env_cfg* cfg, const float* obs_in, float* obs_o
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool vec4 = (N % 4 == 0) && (ld % 4 == 0) && al16(obs_in) && al16(obs_out) && al16(action) && al16(step_ctr) &&
                     al16(rew_out) && ((reinterpret_cast<uintptr_t>(done_out) & 3) == 0) && (!dyn || al16(dyn));
-  if (vec4) {
+  // cfg->p[7] = envs per thread hint (0 = default 4): the ALU-bound families trade vector width for occupancy
+  const int hint = (int)cfg->p[7];
+  if (vec4 && hint == 2) {
+    const int grid = tpp_ceil_div(N / 2, 256);
+    env_step_kernel<F, 2><<<grid, 256, 0, s>>>(p, obs_in, obs_out, dyn, action, step_ctr, rew_out, done_out,
+                                               reset_rows, tick, t_offset, ld);
+  } else if (vec4 && hint != 1) {
     const int grid = tpp_ceil_div(N / 4, 256);
     env_step_kernel<F, 4><<<grid, 256, 0, s>>>(p, obs_in, obs_out, dyn, action, step_ctr, rew_out, done_out,
                                                reset_rows, tick, t_offset, ld);

@@ -1,0 +1,104 @@
+// Backward pass of the policy/value heads in ONE kernel (the heads are [A+1 <= 16, H] — far too small for a GEMM
+// launch each): given dLoss/d(logits, value) from the fused loss kernel it produces
+//   dlatent = dhead @ Wh            (as a TF32 (hi, lo) pair: the A operand of the next tensor-core GEMMs)
+//   gWh    += dhead^T @ latent       gbh += colsum(dhead)        gb_last += colsum(dlatent)
+// Replaces four launches (two CUDA-core GEMMs, two column sums) plus a split kernel per minibatch.
+// Reference: autograd through CategoricalPolicy.hidden_to_output (common/policy.py:74-87) in agents/ppo.py:170.
+#include "tpp_common.cuh"
+
+namespace tpp {
+
+constexpr int HB_THREADS = 256;
+constexpr int HB_ROWS = 64;       // samples per CTA: the latent tile [64][H] is staged in shared memory
+constexpr int HB_MAX_NH = 16;
+
+__device__ __forceinline__ float hb_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+__global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
+    const float* __restrict__ dhead, int ld_head, const float* __restrict__ latent, const float* __restrict__ mask,
+    int64_t ldl, const float* __restrict__ Wh, int nh, int H, float* __restrict__ dz_hi, float* __restrict__ dz_lo,
+    float* __restrict__ dz_plain, int64_t ld_dz, float* __restrict__ gWh, float* __restrict__ gbh,
+    float* __restrict__ gb_last, int mb) {
+  extern __shared__ float sm[];
+  float* sdh = sm;                                  // [HB_ROWS][HB_MAX_NH + 1]
+  float* sW = sdh + HB_ROWS * (HB_MAX_NH + 1);      // [nh][H]
+  float* slat = sW + HB_MAX_NH * 256;               // [HB_ROWS][H + 1]
+  float* sred = slat + HB_ROWS * 257;               // [HB_THREADS]
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * HB_ROWS;
+  const int nb = min(HB_ROWS, mb - b0);
+  for (int i = tid; i < nh * H; i += HB_THREADS) sW[i] = Wh[i];
+  for (int i = tid; i < HB_ROWS * nh; i += HB_THREADS) {
+    const int b = i / nh, a = i % nh;
+    sdh[b * (HB_MAX_NH + 1) + a] = b < nb ? dhead[(int64_t)(b0 + b) * ld_head + a] : 0.0f;
+  }
+  for (int i = tid; i < HB_ROWS * H; i += HB_THREADS) {       // coalesced: consecutive threads walk a row
+    const int b = i / H, k = i % H;
+    slat[b * (H + 1) + k] = b < nb ? latent[(int64_t)(b0 + b) * ldl + k] : 0.0f;
+  }
+  __syncthreads();
+
+  // ---- gbh[a] += sum_b dhead[b][a] ----
+  if (tid < nh) {
+    float s = 0.0f;
+    for (int b = 0; b < nb; ++b) s += sdh[b * (HB_MAX_NH + 1) + tid];
+    atomicAdd(gbh + tid, s);
+  }
+
+  // ---- dlatent[b][k] = sum_a dhead[b][a] Wh[a][k]; thread -> (row lane r, column k), coalesced row writes ----
+  const int rows_per_pass = HB_THREADS / H;          // H in {16..256} -> 16..1 samples per pass
+  const int k = tid % H, r = tid / H;
+  float colsum = 0.0f;
+  for (int b = r; b < nb; b += rows_per_pass) {
+    float acc = 0.0f;
+    for (int a = 0; a < nh; ++a) acc += sdh[b * (HB_MAX_NH + 1) + a] * sW[a * H + k];
+    const int64_t row = b0 + b;
+    if (mask && !(mask[row * ldl + k] > 0.0f)) acc = 0.0f;
+    colsum += acc;
+    const float hi = hb_tf32(acc);
+    dz_hi[row * ld_dz + k] = hi;
+    dz_lo[row * ld_dz + k] = acc - hi;
+    if (dz_plain) dz_plain[row * ld_dz + k] = acc;
+  }
+  sred[tid] = colsum;
+  __syncthreads();
+  if (tid < H) {
+    float s = 0.0f;
+    for (int q = 0; q < rows_per_pass; ++q) s += sred[q * H + tid];
+    atomicAdd(gb_last + tid, s);
+  }
+
+  // ---- gWh[a][k] += sum_b dhead[b][a] latent[b][k] from the staged tile ----
+  for (int o = tid; o < nh * H; o += HB_THREADS) {
+    const int a = o / H, kk = o % H;
+    float s = 0.0f;
+#pragma unroll 8
+    for (int b = 0; b < HB_ROWS; ++b) s += sdh[b * (HB_MAX_NH + 1) + a] * slat[b * (H + 1) + kk];
+    atomicAdd(gWh + o, s);
+  }
+}
+
+}  // namespace tpp
+
+extern "C" int tpp_head_backward(const float* dhead, int32_t ld_head, const float* latent, const float* relu_mask,
+                                 int64_t ldl, const float* Wh, int32_t nh, int32_t H, float* dz_hi, float* dz_lo,
+                                 float* dz_plain, int64_t ld_dz, float* gWh, float* gbh, float* gb_last, int32_t mb,
+                                 void* stream) {
+  TPP_CHECK_ARG(dhead && latent && Wh && dz_hi && dz_lo && gWh && gbh && gb_last && mb > 0);
+  TPP_CHECK_ARG(nh > 0 && nh <= tpp::HB_MAX_NH && ld_head >= nh && ldl >= H && ld_dz >= H);
+  if (!(H == 64 || H == 128 || H == 256 || H == 32 || H == 16)) return TPP_ENOTSUP;
+  const size_t smem = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * 256 + tpp::HB_ROWS * 257 + tpp::HB_THREADS) *
+                      sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tpp::head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = tpp_ceil_div(mb, tpp::HB_ROWS);
+  tpp::head_backward_kernel<<<grid, tpp::HB_THREADS, smem, tpp_stream(stream)>>>(
+      dhead, ld_head, latent, relu_mask, ldl, Wh, nh, H, dz_hi, dz_lo, dz_plain, ld_dz, gWh, gbh, gb_last, mb);
+  TPP_LAUNCH_STATUS();
+}

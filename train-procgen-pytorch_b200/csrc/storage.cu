@@ -27,15 +27,25 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
     float A = 0.0f;
     float v_next = value[(int64_t)T * ld + e];
     int t = T - 1;
-    for (; t >= U - 1; t -= U) {
-      float r[U], v[U];
-      uint8_t d[U];
+    // software pipeline: the loads of batch i+1 are issued before the (serial) recurrence of batch i is evaluated
+    float r[U], v[U], rn[U], vn[U];
+    uint8_t d[U], dn[U];
+    const bool have = t >= U - 1;
+    if (have) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t o = (int64_t)(t - u) * ld + e;
-        r[u] = __ldcs(rew + o);
-        d[u] = __ldcs(done + o);
-        v[u] = __ldcs(value + o);
+        r[u] = __ldcs(rew + o); d[u] = __ldcs(done + o); v[u] = __ldcs(value + o);
+      }
+    }
+    for (; t >= U - 1; t -= U) {
+      const bool more = (t - U) >= U - 1;
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t o = (int64_t)(t - U - u) * ld + e;
+          rn[u] = __ldcs(rew + o); dn[u] = __ldcs(done + o); vn[u] = __ldcs(value + o);
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -49,18 +59,22 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
         s2 += (double)A * (double)A;
         v_next = v[u];
       }
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u] = rn[u]; d[u] = dn[u]; v[u] = vn[u]; }
+      }
     }
     for (; t >= 0; --t) {
       const int64_t o = (int64_t)t * ld + e;
-      const float r = rew[o], v = value[o];
+      const float rr = rew[o], vv = value[o];
       const float nd = 1.0f - (float)done[o];
-      const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), nd)), v);
+      const float delta = __fsub_rn(__fadd_rn(rr, __fmul_rn(__fmul_rn(gamma, v_next), nd)), vv);
       A = __fadd_rn(__fmul_rn(__fmul_rn(gl, A), nd), delta);
       adv[o] = A;
-      ret[o] = __fadd_rn(A, v);
+      ret[o] = __fadd_rn(A, vv);
       s1 += (double)A;
       s2 += (double)A * (double)A;
-      v_next = v;
+      v_next = vv;
     }
   }
   s1 = block_sum(s1, red);
@@ -74,16 +88,22 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
 
 __global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const double* moments, int T, int N,
                                                             int64_t ld) {
+  // grid = (column chunks, T): no per-element div/mod; 128-bit accesses when the row allows it
   const double n = moments[2];
   const double mean_d = moments[0] / n;
   double var = (moments[1] - moments[0] * mean_d) / (n - 1.0);   // unbiased (torch.std default)
   var = var > 0.0 ? var : 0.0;
   const float mean = (float)mean_d;
   const float denom = (float)sqrt(var) + 1e-8f;
-  const int64_t total = (int64_t)T * N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t o = (i / N) * ld + (i % N);
-    adv[o] = (adv[o] - mean) / denom;
+  float* row = adv + (int64_t)blockIdx.y * ld;
+  const int c4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= N) return;
+  if (c4 + 4 <= N && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(adv) & 15) == 0) {
+    float4 q = __ldcs(reinterpret_cast<const float4*>(row + c4));
+    q.x = (q.x - mean) / denom; q.y = (q.y - mean) / denom; q.z = (q.z - mean) / denom; q.w = (q.w - mean) / denom;
+    __stcs(reinterpret_cast<float4*>(row + c4), q);
+  } else {
+    for (int c = c4; c < N && c < c4 + 4; ++c) row[c] = (row[c] - mean) / denom;
   }
 }
 
@@ -130,40 +150,50 @@ __global__ void __launch_bounds__(256) gather_vec_kernel(const int64_t* __restri
   if (j == 0) gather_scalars(g, t * ld + e, k);
 }
 
-// frames uint8 NHWC -> float NCHW / 255.  One CTA (128 threads) per sample: the H*W*C contiguous bytes of
-// the frame are staged through shared memory with 4-byte loads, then written channel-major.
-__global__ void __launch_bounds__(128) gather_img_kernel(const int64_t* __restrict__ idx, int mb, int N, int64_t ld,
-                                                         int HW, int C, const uint8_t* __restrict__ frames,
-                                                         GatherScalars g, float* __restrict__ out_obs,
-                                                         float* __restrict__ out_lo, int ld_out) {
-  extern __shared__ uint8_t px[];
-  const int k = blockIdx.x;
-  const int64_t flat = idx ? idx[k] : k;
+// frames uint8 NHWC -> float NCHW / 255.  One WARP per sample (8 samples per CTA): the H*W*C contiguous bytes of the
+// frame are staged in the warp's shared-memory patch with 4-byte loads, then written channel-major with full
+// 128-byte lines.  Warps never synchronise with each other, so 64 samples are in flight per SM.
+constexpr int GI_WARPS = 8;
+__global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t* __restrict__ idx, int mb, int N,
+                                                                   int64_t ld, int HW, int C,
+                                                                   const uint8_t* __restrict__ frames, GatherScalars g,
+                                                                   float* __restrict__ out_obs,
+                                                                   float* __restrict__ out_lo, int ld_out) {
+  extern __shared__ uint8_t px_all[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int k = blockIdx.x * GI_WARPS + w;
+  if (k >= mb) return;
   const int bytes = HW * C;
+  const int patch = (bytes + 15) & ~15;
+  uint8_t* px = px_all + w * patch;
+  const int64_t flat = idx ? idx[k] : k;
   const uint8_t* src = frames + flat * bytes;      // flat = t*N + e indexes [T+1][N] frames directly
   if ((bytes & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
-    for (int w = threadIdx.x; w < bytes / 4; w += blockDim.x)
-      reinterpret_cast<uint32_t*>(px)[w] = reinterpret_cast<const uint32_t*>(src)[w];
+    for (int i = lane; i < bytes / 4; i += 32)
+      reinterpret_cast<uint32_t*>(px)[i] = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
   } else {
-    for (int b = threadIdx.x; b < bytes; b += blockDim.x) px[b] = src[b];
+    for (int b = lane; b < bytes; b += 32) px[b] = src[b];
   }
-  __syncthreads();
+  __syncwarp();
   float* dst = out_obs + (int64_t)k * ld_out;
-  for (int o = threadIdx.x; o < ld_out; o += blockDim.x) {
+  float* dlo = out_lo ? out_lo + (int64_t)k * ld_out : nullptr;
+  int c = 0, p = lane;                              // o = c*HW + p, advanced without div/mod
+  for (int o = lane; o < ld_out; o += 32) {
     float v = 0.0f;
     if (o < bytes) {
-      const int c = o / HW, p = o % HW;
+      while (p >= HW) { p -= HW; ++c; }
       v = (float)px[p * C + c] / 255.0f;
     }
-    if (out_lo) {
+    p += 32;
+    if (dlo) {
       const float h = tf32_hi(v);
       dst[o] = h;
-      out_lo[(int64_t)k * ld_out + o] = v - h;
+      dlo[o] = v - h;
     } else {
       dst[o] = v;
     }
   }
-  if (threadIdx.x == 0 && idx) gather_scalars(g, (flat / N) * ld + (flat % N), k);
+  if (lane == 0 && idx) gather_scalars(g, (flat / N) * ld + (flat % N), k);
 }
 
 }  // namespace tpp
@@ -180,9 +210,7 @@ extern "C" int tpp_gae(const float* rew, const uint8_t* done, const float* value
 
 extern "C" int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream) {
   TPP_CHECK_ARG(adv && moments && T > 0 && N > 0 && ld >= N);
-  const int64_t total = (int64_t)T * N;
-  int grid = tpp_ceil_div(total, 256 * 4);
-  if (grid > 148 * 16) grid = 148 * 16;
+  dim3 grid(tpp_ceil_div(N, 256 * 4), T);
   tpp::adv_normalize_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(adv, moments, T, N, ld);
   TPP_LAUNCH_STATUS();
 }
@@ -208,10 +236,10 @@ extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t
   TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && ld >= N && H > 0 && W > 0 && C > 0 &&
                 ld_out >= H * W * C);
   const int bytes = H * W * C;
-  TPP_CHECK_ARG(bytes <= 48 * 1024);
+  TPP_CHECK_ARG(bytes <= 5 * 1024);   // 8 warps x one frame each in 48 KB of shared memory (Box-World frames: 588 B)
   tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
-  tpp::gather_img_kernel<<<mb, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(idx, mb, N, ld, H * W, C, frames, g,
-                                                                            out_obs, out_obs_lo, ld_out);
+  tpp::gather_img_kernel<<<tpp_ceil_div(mb, tpp::GI_WARPS), tpp::GI_WARPS * 32, tpp::GI_WARPS * ((bytes + 15) & ~15),
+                           tpp_stream(stream)>>>(idx, mb, N, ld, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }
 
@@ -219,9 +247,9 @@ extern "C" int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, in
                                  float* out_obs_lo, int32_t ld_out, void* stream) {
   TPP_CHECK_ARG(frames && out_obs && N > 0 && ld_out >= H * W * C);
   const int bytes = H * W * C;
-  TPP_CHECK_ARG(bytes <= 48 * 1024);
+  TPP_CHECK_ARG(bytes <= 5 * 1024);
   tpp::GatherScalars g{};
-  tpp::gather_img_kernel<<<N, 128, (bytes + 3) & ~3, tpp_stream(stream)>>>(nullptr, N, N, N, H * W, C, frames, g,
-                                                                           out_obs, out_obs_lo, ld_out);
+  tpp::gather_img_kernel<<<tpp_ceil_div(N, tpp::GI_WARPS), tpp::GI_WARPS * 32, tpp::GI_WARPS * ((bytes + 15) & ~15),
+                           tpp_stream(stream)>>>(nullptr, N, N, N, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }

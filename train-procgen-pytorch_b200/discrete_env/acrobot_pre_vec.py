@@ -15,6 +15,7 @@ class AcrobotVecEnv(PreVecEnv):
     family = "acrobot"
     n_state = 12
     n_obs = 14
+    envs_per_thread = 1     # ALU-bound (RK4 / contact model): occupancy beats vector width (profiles/README.md)
     dt = 0.2
     AVAIL_TORQUE = np.array([-1.0, 0.0, +1])
     book_or_nips = "book"

@@ -22,6 +22,7 @@ class LunarLanderVecEnv(PreVecEnv):
     family = "lunar_lander"
     n_state = 8
     n_obs = 8
+    envs_per_thread = 1     # ALU-bound (RK4 / contact model): occupancy beats vector width (profiles/README.md)
 
     def __init__(self, n_envs, gravity=10.0, main_engine_power=13.0, side_engine_power=0.6, initial_random=1000.0,
                  max_steps=1000, seed=0, drop_same=False, render_mode=None, device="cuda", numpy_compat=False):

@@ -53,6 +53,7 @@ class PreVecEnv:
     n_state = 0
     n_obs = 0
     drop_same = False
+    envs_per_thread = 0     # kernel hint (tpp_env_cfg.p[7]): 0 = default (4, 128-bit accesses); ALU-bound families use 1
 
     def __init__(self, n_envs, n_actions, env_name, max_steps=500, seed=0, render_mode=None, device="cuda",
                  numpy_compat=False):
@@ -104,6 +105,7 @@ class PreVecEnv:
             cfg.start_high[i] = float(hi)
         for i, v in enumerate(self.kernel_params):
             cfg.p[i] = float(v)
+        cfg.p[7] = float(self.envs_per_thread)
         return cfg
 
     def _rows_to_device(self, rows):
