@@ -124,51 +124,90 @@ def build_agent(name, hp, rank, device):
 
 
 def time_kernel(fn, iters=20, warm=3):
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        fn()
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters * 1e-3     # seconds per launch
+    """Average device time of one `fn()` (one or more launches on the current stream): `iters` calls are captured in
+    a CUDA graph and the replay is bracketed by CUDA events, so the number contains no Python / ctypes launch cost
+    (which is ~10 us per call and would otherwise bound every kernel shorter than that)."""
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+    return a.elapsed_time(b) / (2 * iters) * 1e-3     # seconds per call
 
 
-def kernel_rooflines(pk, device):
-    """Live CUDA-event timings of the HBM-bound kernels on inputs larger than L2 (126 MB), achieved = algorithmic
-    bytes (SURVEY 8d per-unit figures) / time."""
-    from tpp_b200 import _lib
+def kernel_rooflines(pk, device, sweep=True):
+    """Live CUDA-event timings of the HBM-bound kernels, achieved = algorithmic bytes (SURVEY 8d per-unit figures,
+    DESIGN.md section 4) / time.  Env steps ping-pong between two rollout slots; at N = 2^22 one slot is 75-235 MB,
+    i.e. the working set exceeds the 126 MB L2 (smaller N of the C3 sweep are L2-resident and say so)."""
+    from tpp_b200.boxworld.box_world_env_vec import BoxWorldVec
     from tpp_b200.common.storage import Storage
     from tpp_b200.discrete_env.acrobot_pre_vec import AcrobotVecEnv
     from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    from tpp_b200.discrete_env.cartpole_swing_pre_vec import CartPoleSwingVecEnv
+    from tpp_b200.discrete_env.lunar_lander_pre_vec import LunarLanderVecEnv
     from tpp_b200.discrete_env.mountain_car_pre_vec import MountainCarVecEnv
     out = []
-    N = 1 << 22
-    for cls, bytes_per_step in ((CartPoleVecEnv, 89), (MountainCarVecEnv, 57), (AcrobotVecEnv, 137)):
-        env = cls(n_envs=N, seed=1, device=device)
-        act = torch.randint(0, env.n_actions, (N,), device=device, dtype=torch.int32)
-        state = {"cur": 0}
+    fams = ((CartPoleVecEnv, 89), (CartPoleSwingVecEnv, 89), (MountainCarVecEnv, 57), (AcrobotVecEnv, 137),
+            (LunarLanderVecEnv, 81))
+    for cls, bytes_per_step in fams:
+        sizes = [1 << 22]
+        if sweep and cls in (AcrobotVecEnv, MountainCarVecEnv, LunarLanderVecEnv):     # BASELINE configs[2] (C3)
+            sizes = [1 << 16, 1 << 18, 1 << 20, 1 << 22]
+        for N in sizes:
+            env = cls(n_envs=N, seed=1, device=device)
+            act = torch.randint(0, env.n_actions, (N,), device=device, dtype=torch.int32)
+            state = {"cur": 0}
 
-        def step():
-            c = state["cur"]
-            env.step_into(env._slots[c], env._slots[c ^ 1], act, env._rew, env._done)
-            state["cur"] = c ^ 1
-        dt = time_kernel(step, iters=30)
-        gbs = bytes_per_step * N / dt / 1e9
-        out.append(dict(kernel=f"env_step_{env.family}", n_envs=N, bytes_per_unit=bytes_per_step, bound="hbm",
+            def step():
+                c = state["cur"]
+                env.step_into(env._slots[c], env._slots[c ^ 1], act, env._rew, env._done)
+                state["cur"] = c ^ 1
+            dt = time_kernel(step, iters=50)
+            gbs = bytes_per_step * N / dt / 1e9
+            out.append(dict(kernel=f"env_step_{env.family}", n_envs=N, bytes_per_unit=bytes_per_step, bound="hbm",
+                            achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                            env_steps_per_s=round(N / dt, 1), us=round(dt * 1e6, 2),
+                            working_set_mb=round(2 * env.n_obs * 4 * N / 1e6, 1)))
+            del env
+    # Box-World step (+ in-order level replacement + frame emit into the rollout slot), uint8 rollout contract:
+    # read frame 588 + write frame 588 + ~57 B of cells / meta / reward / done per env-step (SURVEY 8d)
+    for N in (4096, 1 << 18):
+        bw = BoxWorldVec(N, 12, 5, 3, 3, max_steps=1000, start_seed=6033, n_levels=500, device=device)
+        frames = torch.zeros(2, N, 14, 14, 3, dtype=torch.uint8, device=device)
+        act = torch.randint(0, 4, (N,), device=device, dtype=torch.int32)
+        k = {"i": 0}
+
+        def bstep():
+            k["i"] ^= 1
+            bw.step_device(act, frame_out=frames[k["i"]])
+        dt = time_kernel(bstep, iters=50)
+        gbs = 1233 * N / dt / 1e9
+        out.append(dict(kernel="boxworld_step+reset (n=12)", n_envs=N, bytes_per_unit=1233, bound="hbm",
                         achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                        env_steps_per_s=round(N / dt, 1)))
-        del env
-    T, Ng = 256, 1 << 16
-    st = Storage((1,), 1, T, Ng, device)
-    st.rew.normal_(); st.value.normal_()
-    st.done_u8.copy_((torch.rand(T, Ng, device=device) < 0.02).to(torch.uint8))
-    dt = time_kernel(lambda: st.compute_estimates(0.99, 0.95, True, True), iters=10)
-    gbs = 25 * T * Ng / dt / 1e9
-    out.append(dict(kernel="gae_scan+adv_normalize", T=T, n_envs=Ng, bytes_per_unit=25, bound="hbm",
-                    achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4)))
+                        env_steps_per_s=round(N / dt, 1), us=round(dt * 1e6, 2)))
+        del bw, frames
+    for T, Ng in ((256, 4096), (256, 1 << 16), (64, 1 << 20)):
+        st = Storage((1,), 1, T, Ng, device)
+        st.rew.normal_(); st.value.normal_()
+        st.done_u8.copy_((torch.rand(T, st.ld, device=device) < 0.02).to(torch.uint8))
+        dt = time_kernel(lambda: st.compute_estimates(0.99, 0.95, True, True), iters=10)
+        gbs = 25 * T * Ng / dt / 1e9
+        out.append(dict(kernel="gae_scan+adv_normalize", T=T, n_envs=Ng, bytes_per_unit=25, bound="hbm",
+                        achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
+                        us=round(dt * 1e6, 2)))
+        del st
     torch.cuda.empty_cache()
     return out
 
@@ -207,8 +246,12 @@ def gemm_roofline(agent, in_dim, hp, pk):
         name = "gemm_f32_kernel (CUDA cores, exact fp32)"
     dt = time_kernel(one, iters=50)
     tf = 2.0 * mb * fout * fin / dt / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic = json.load(open(tpath)).get(f"gemm_tc_kernel<128>[{mb},{fout},{fin}]")
     return dict(kernel=name, shape=[mb, fout, fin], bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
-                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=None, us_per_launch=round(dt * 1e6, 2),
+                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=traffic, us_per_launch=round(dt * 1e6, 2),
                 policy_fwd_bwd_tflops=round(flops_all / dt_all / 1e12, 2),
                 policy_fwd_bwd_us=round(dt_all * 1e6, 1),
                 note="peak = dense bf16 cuBLAS (" + pk["source"] + "); a TF32 kernel tops out at 1/2 of it, the "
@@ -307,8 +350,15 @@ def run_ours(args):
     wall = time.perf_counter() - w0
     ms_e2e = max(t0.elapsed_time(t1), wall * 1e3)
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    in_sync = None
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+        # every rank applied the same averaged gradient: the parameter vectors must be bit-identical
+        chk = agent.policy.flat.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+        in_sync = bool((lo == hi).item())
     ms, ms_e2e = times.tolist()
 
     if rank != 0:
@@ -336,7 +386,8 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
                 "api": "PPO.train(): host randperm -> pinned H2D per epoch; D2H loss summary + logger batches"},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernel_rooflines": extra,
+        "gpu_launches": int(launches), "clocks": clk, "replicas_in_sync": in_sync, "roofline": roof,
+        "kernel_rooflines": extra,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

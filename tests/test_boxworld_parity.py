@@ -73,14 +73,16 @@ def test_reference_scenarios(golden_dir, name):
         assert int(r[0]) == 11 and bool(d[0]) and info[0]["episode"]["solved"]
 
 
-@pytest.mark.parametrize("N,spec,n_levels", [(4096, (12, 5, 3, 3), 500), (1000, (6, 2, 1, 1), 0), (3, (7, 3, 1, 2), 0)])
+@pytest.mark.parametrize("N,spec,n_levels", [(4096, (12, 5, 3, 3), 500), (1000, (6, 2, 1, 1), 0), (3, (7, 3, 1, 2), 0),
+                                             (16384, (6, 2, 1, 1), 50)])   # > 1024 CTAs: prefix-scan reset path
 def test_long_trajectory_against_oracle(N, spec, n_levels):
     """Full-size config (N=4096, n=12, 500-level bank), odd grid (byte-copy path) and ragged N, with a policy
     that walks towards keys often enough to open locks; every array compared for equality at every step."""
-    env = _env(N, spec, max_steps=30, start_seed=7, n_levels=n_levels)
-    orc = obw.BoxWorldOracle(N, *spec, max_steps=30, start_seed=7, n_levels=n_levels)
+    ms = 5 if N > 8192 else 30
+    env = _env(N, spec, max_steps=ms, start_seed=7, n_levels=n_levels)
+    orc = obw.BoxWorldOracle(N, *spec, max_steps=ms, start_seed=7, n_levels=n_levels)
     rng = np.random.default_rng(1)
-    steps = 40 if N > 2000 else 120
+    steps = (12 if N > 8192 else 40) if N > 2000 else 120
     for t in range(steps):
         a = rng.integers(0, 4, N)
         w, r, d, _ = env.step(a)

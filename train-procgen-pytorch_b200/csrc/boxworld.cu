@@ -305,18 +305,59 @@ __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_step_kernel(tpp_boxwor
 
 // Reset kernel: same grid.  rank of a finished env = (# finished envs in lower CTAs) + (# finished in lower
 // warps of this CTA); its level seed follows the reference's sequential counter.
+// Exclusive prefix sum of the per-CTA finished-env counts (single CTA; only launched when there are many CTAs, where
+// letting every reset CTA re-sum its predecessors would be quadratic).  scratch: [0, n) counts, [n] ticket,
+// [n+1, 2n+1) prefix.
+__global__ void __launch_bounds__(1024) boxworld_scan_kernel(int32_t* scratch, int n) {
+  __shared__ int warp_off[32];
+  __shared__ int chunk_total;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? scratch[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_off[w] = incl;                 // warp totals
+    __syncthreads();
+    if (w == 0) {
+      const int t = warp_off[lane];
+      int inc2 = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += u;
+      }
+      warp_off[lane] = inc2 - t;                        // exclusive offset of each warp inside the chunk
+      if (lane == 31) chunk_total = inc2;
+    }
+    __syncthreads();
+    if (i < n) scratch[n + 1 + i] = carry + warp_off[w] + incl - v;
+    carry += chunk_total;
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxworld_state st,
                                                                       const uint8_t* __restrict__ done_in,
-                                                                      uint8_t* __restrict__ frame_out) {
+                                                                      uint8_t* __restrict__ frame_out, int use_prefix) {
   __shared__ int red[32];
   __shared__ int base_s;
   __shared__ uint32_t mtbuf[BW_WARPS][624];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ncta = gridDim.x;
-  int part = 0;
-  for (int c = threadIdx.x; c < (int)blockIdx.x; c += blockDim.x) part += st.scratch[c];
-  part = block_sum(part, red);
-  if (threadIdx.x == 0) base_s = part;
+  if (use_prefix) {          // exclusive prefix of the per-CTA counts was produced by boxworld_scan_kernel
+    if (threadIdx.x == 0) base_s = st.scratch[ncta + 1 + blockIdx.x];
+  } else {                   // few CTAs: sum the counts of the lower CTAs directly
+    int part = 0;
+    for (int c = threadIdx.x; c < (int)blockIdx.x; c += blockDim.x) part += st.scratch[c];
+    part = block_sum(part, red);
+    if (threadIdx.x == 0) base_s = part;
+  }
   __syncthreads();
   const int64_t sc = *st.seed_counter;
   const int e = blockIdx.x * BW_WARPS + wid;
@@ -471,7 +512,9 @@ extern "C" int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* ac
   cudaStream_t s = tpp_stream(stream);
   tpp::boxworld_step_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, action, reward_out, done_out, frame_out, fin_ret,
                                                                fin_len, fin_solved);
-  tpp::boxworld_reset_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, done_out, frame_out);
+  const int use_prefix = grid > 1024;
+  if (use_prefix) tpp::boxworld_scan_kernel<<<1, 1024, 0, s>>>(st->scratch, grid);
+  tpp::boxworld_reset_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, done_out, frame_out, use_prefix);
   TPP_LAUNCH_STATUS();
 }
 
