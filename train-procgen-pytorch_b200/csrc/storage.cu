@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t
                                                                    float* __restrict__ out_lo, int ld_out) {
   extern __shared__ uint8_t px_all[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int k = blockIdx.x * GI_WARPS + w;
+  const int k = blockIdx.x * (blockDim.x >> 5) + w;
   if (k >= mb) return;
   const int bytes = HW * C;
   const int patch = (bytes + 15) & ~15;
@@ -194,6 +194,13 @@ __global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t
     }
   }
   if (lane == 0 && idx) gather_scalars(g, (flat / N) * ld + (flat % N), k);
+}
+
+// warps (= samples) per CTA such that the per-warp frame patches fit the default 48 KB of shared memory
+static int gi_warps(int bytes) {
+  const int patch = (bytes + 15) & ~15;
+  int w = (48 * 1024) / patch;
+  return w > GI_WARPS ? GI_WARPS : (w < 1 ? 1 : w);
 }
 
 }  // namespace tpp
@@ -236,10 +243,11 @@ extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t
   TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && ld >= N && H > 0 && W > 0 && C > 0 &&
                 ld_out >= H * W * C);
   const int bytes = H * W * C;
-  TPP_CHECK_ARG(bytes <= 5 * 1024);   // 8 warps x one frame each in 48 KB of shared memory (Box-World frames: 588 B)
+  TPP_CHECK_ARG(bytes <= 24 * 1024);  // one frame per warp in <= 48 KB of shared memory (588 B Box-World, 12 KB Procgen)
   tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
-  tpp::gather_img_kernel<<<tpp_ceil_div(mb, tpp::GI_WARPS), tpp::GI_WARPS * 32, tpp::GI_WARPS * ((bytes + 15) & ~15),
-                           tpp_stream(stream)>>>(idx, mb, N, ld, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
+  const int warps = tpp::gi_warps(bytes);
+  tpp::gather_img_kernel<<<tpp_ceil_div(mb, warps), warps * 32, warps * ((bytes + 15) & ~15), tpp_stream(stream)>>>(
+      idx, mb, N, ld, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }
 
@@ -247,9 +255,10 @@ extern "C" int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, in
                                  float* out_obs_lo, int32_t ld_out, void* stream) {
   TPP_CHECK_ARG(frames && out_obs && N > 0 && ld_out >= H * W * C);
   const int bytes = H * W * C;
-  TPP_CHECK_ARG(bytes <= 5 * 1024);
+  TPP_CHECK_ARG(bytes <= 24 * 1024);
   tpp::GatherScalars g{};
-  tpp::gather_img_kernel<<<tpp_ceil_div(N, tpp::GI_WARPS), tpp::GI_WARPS * 32, tpp::GI_WARPS * ((bytes + 15) & ~15),
-                           tpp_stream(stream)>>>(nullptr, N, N, N, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
+  const int warps = tpp::gi_warps(bytes);
+  tpp::gather_img_kernel<<<tpp_ceil_div(N, warps), warps * 32, warps * ((bytes + 15) & ~15), tpp_stream(stream)>>>(
+      nullptr, N, N, N, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
   TPP_LAUNCH_STATUS();
 }
