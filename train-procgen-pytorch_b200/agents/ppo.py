@@ -439,24 +439,31 @@ class PPO(BaseAgent):
                    self.logger.logdir + "/model_" + str(self.t) + ".pth")
 
     def _train_host_env(self, num_timesteps, checkpoints):
-        """Host-stepped envs (Procgen or any numpy VecEnv): the reference loop (agents/ppo.py:216-236) with the
-        observations staged into the GPU rollout by Storage.store; GAE and the update stay on the device."""
+        """Host-stepped envs (Procgen or any numpy VecEnv; reference loop agents/ppo.py:216-236).  Per step: the
+        observation is staged once into rollout slot t (pinned H2D; uint8 frames stay uint8), the policy forward and
+        the action sampling run on the device on that slot, only the N actions come back to the host for
+        ``env.step``, and reward / done go up.  GAE and the update never leave the device."""
         checkpoint_cnt = 0
+        st, N, T = self.storage, self.n_envs, self.n_steps
         obs = self.env.reset()
-        hidden_state = np.zeros((self.n_envs, self.storage.hidden_state_size))
-        done = np.zeros(self.n_envs)
         while self.t < num_timesteps:
             self.policy.eval()
-            for _ in range(self.n_steps):
-                act, log_prob_act, value, next_hidden_state = self.predict(obs, hidden_state, done)
-                next_obs, rew, done, info = self.env.step(act)
-                self.storage.store(obs, hidden_state, act, rew, done, info, log_prob_act, value)
-                obs, hidden_state = next_obs, next_hidden_state
-            _, _, last_val, hidden_state = self.predict(obs, hidden_state, done)
-            self.storage.store_last(obs, hidden_state, last_val)
-            self.storage.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
+            if hasattr(self.engine, "refresh_weights"):
+                self.engine.refresh_weights()
+            for t in range(T):
+                st.stage_obs(t, obs)
+                head = self._policy_head(st.obs_slot(t), st)
+                self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t)
+                act = st.act_i32[t, :N].cpu().numpy().astype(np.int64)      # the step's only device->host read
+                obs, rew, done, info = self.env.step(act)
+                st.stage_step(t, rew, done)
+            st.stage_obs(T, obs)
+            head = self._policy_head(st.obs_slot(T), st)
+            st.value[T, :N] = head[:N, self.n_actions]
+            _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
+            st.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
             summary = self.optimize()
-            self.t += self.n_steps * self.n_envs
+            self.t += T * N
             self._log(summary, num_timesteps)
             if self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]:
                 self.save_checkpoint()
