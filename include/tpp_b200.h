@@ -170,7 +170,9 @@ int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, in
  *        TPP_EPI_ACCUM (C += result; with split_k > 1 partial sums are combined with atomics).
  * This one entry serves nn.Linear forward (common/model.py:962-967), its data gradient and its weight
  * gradient (autograd of agents/ppo.py:170).  CUDA-core exact-fp32 path; the tensor-core path is below.    */
-enum { TPP_EPI_BIAS = 1, TPP_EPI_RELU = 2, TPP_EPI_MASK = 4, TPP_EPI_ACCUM = 8 };
+enum { TPP_EPI_BIAS = 1, TPP_EPI_RELU = 2, TPP_EPI_MASK = 4, TPP_EPI_ACCUM = 8, TPP_EPI_ADD = 16,
+       TPP_EPI_RELU_OUT = 32 /* tpp_gemm_tc only: max(.,0) once more AFTER the addend (the ReLU behind the last
+                                residual block, common/model.py:182) */ };
 int tpp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
                  int64_t ldc, const float* bias, const float* mask, int32_t M, int32_t N, int32_t K,
                  int32_t flags, int32_t split_k, void* stream);
@@ -190,7 +192,7 @@ int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t N, float* o
  * flags: TPP_EPI_BIAS, TPP_EPI_RELU, TPP_EPI_MASK (zero where mask[m*ld_mask+n] <= 0), TPP_EPI_ACCUM (fp32 atomic
  *        accumulation of the raw product into `out`; the only mode that allows split_k > 1: weight gradients).
  * Outputs (each nullable): out (plain fp32 [M][ldc]), out_hi/out_lo (TF32 pair, [M][ldc]), colsum ([N], += column
- * sums of the result: the bias gradient of the layer below).  block_n: 0 = auto, or 16/64/128/256.
+ * sums of the result: the bias gradient of the layer below).  block_n: 0 = auto, or 16/32/64/128/256.
  * Replaces nn.Linear forward / backward (common/model.py:954-980, common/policy.py:74-87).                  */
 typedef struct {
   const float* a_hi; const float* a_lo; int64_t lda;
@@ -203,6 +205,9 @@ typedef struct {
   float* out; float* out_hi; float* out_lo; int64_t ldc;
   float* colsum;
   void* dbg;          /* optional int64[8]: clock64 timeline of CTA (0,0,0) — profiling aid, normally NULL */
+  const float* addend; int64_t ld_add;   /* TPP_EPI_ADD (tpp_gemm_tc only): result += addend[m*ld_add + n], applied
+                                            after bias / relu / mask: the residual connection (forward) and the
+                                            skip-path gradient (backward) of ResidualBlock, common/model.py:134-153 */
 } tpp_tc_gemm;
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
@@ -221,6 +226,44 @@ int tpp_head_backward(const float* dhead, int32_t ld_head, const float* latent, 
  * optimizer step, loss gradients) an operand of tpp_gemm_tc.                                                */
 int tpp_split_tf32(const float* x, int64_t ld_in, int32_t rows, int32_t cols, float* hi, float* lo, int64_t ld_out,
                    float* t_hi, float* t_lo, int64_t ld_t, void* stream);
+
+/* ---- policy: IMPALA-CNN pieces (NHWC activations; common/model.py:134-208) ------------------------------ */
+/* 3x3 / pad-1 window gather: col[p][tap*C + c] = act(scale * x[b, y+ky-1, x+kx-1, c]) for p = (b*H + y)*W + x,
+ * tap = ky*3 + kx (zero outside the image; columns [9C, Kp) zero), written as the TF32 (hi, lo) operand pair
+ * [B*H*W][Kp] of tpp_gemm_tc.  x is float32 NHWC, or uint8 NHWC frames when x_is_u8 (scale = 1/255 then fuses
+ * ScaledFloatFrame, common/env/procgen_wrappers.py:407-419); relu != 0 applies max(.,0) on load (the nn.ReLU in
+ * front of the residual convolutions, common/model.py:146-150).  nn.Conv2d(k=3, pad=1) forward is then
+ * Y[p][co] = col . Wf[co] with Wf[co][tap*Cin + ci] = W[co][ci][ky][kx]; the data gradient is the same operation on
+ * dY with Wd[ci][tap*Cout + co] = W[co][ci][2-ky][2-kx]; the weight gradient is dY^T col (both MN-major).
+ * col_lo may be NULL (single-pass TF32 mode needs only the hi half).                                           */
+int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t H, int32_t W, int32_t C, int64_t sb, int64_t sy,
+                  int64_t sx, int64_t sc, int32_t relu, float scale, float* col_hi, float* col_lo, int32_t Kp,
+                  void* stream);
+/* (sb, sy, sx, sc): element strides of x over (sample, row, column, channel): NHWC = (HWC, WC, C, 1); the gathered
+ * NCHW observation rows of tpp_gather_img = (ld_out, W, 1, HW).                                                 */
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (common/model.py:163,171): y [B][(H+1)/2][(W+1)/2][C],
+ * arg = winning tap (first maximum); backward routes dy to the winning input pixel (gather form, no atomics).   */
+int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,
+                         void* stream);
+int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t B, int32_t H, int32_t W, int32_t C, float* dx,
+                         float* dx_hi, float* dx_lo, void* stream);   /* dx_hi/dx_lo (nullable): TF32 pair of dx */
+/* out[c] += sum_m x[m*C + c] for a narrow row-major [M][C] matrix (C in 4/8/16/32/64): a convolution's bias gradient
+ * from its NHWC output gradient (autograd of nn.Conv2d bias, common/model.py:137-138,158).                     */
+int tpp_colsum_narrow(const float* x, int64_t M, int32_t C, float* out, void* stream);
+/* y = act(x + bias) -> plain fp32 (out) and/or TF32 pair (out_hi, out_lo), rows [M][ld]: finishes a dense layer whose
+ * contraction was split across CTAs (TPP_EPI_ACCUM) -- the tensor core adds into its fp32 accumulator with
+ * truncation, so contractions longer than ~512 terms are chunked and the chunks summed with IEEE adds to stay
+ * fp32-grade (IMPALA's 2048-wide fc layer, common/model.py:175).                                               */
+int tpp_bias_act_split(const float* x, int64_t ld_in, int32_t M, int32_t N, const float* bias, int32_t relu, float* out,
+                       float* out_hi, float* out_lo, int64_t ld_out, void* stream);
+
+/* Diagnostic (tests only): one TMA im2col box of an NHWC fp32 tensor (3x3 / pad-1 bounding box) copied out of shared
+ * memory: out[pixels][channels_per_pixel].  (w, h, n) = base pixel in bounding-box coordinates (output pixel - 1),
+ * (off_w, off_h) = filter tap; swizzle: 0 none, 128 = SWIZZLE_128B, 1 = SWIZZLE_128B_ATOM_32B.                 */
+int tpp_debug_tma_im2col(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t channels_per_pixel,
+                         int32_t pixels, int32_t w, int32_t h, int32_t n, int32_t off_w, int32_t off_h,
+                         int32_t swizzle, float* out, void* stream);
 
 /* ---- policy: action sampling at rollout --------------------------------------------------------------- */
 /* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.

@@ -3,10 +3,11 @@
 The Procgen engine is a closed C++ library that is not in this image, so the host side is a stand-in
 that hands out pre-generated uint8 64x64x3 frames, Bernoulli(0.01)*10 rewards and Bernoulli(1/200) dones
 at no CPU cost: what is measured is this repo's staging + GPU pipeline — pinned H2D of the frames into the uint8
-rollout, policy forward + Philox sampling on the device, GAE, gather, fused loss, clip+Adam.  The IMPALA convolutions
-themselves run through torch/cuDNN this round (library path, common/engine.py::TorchModuleEngine).
+rollout, policy forward + Philox sampling on the device, GAE, gather, fused loss, clip+Adam.  --matmul tf32x3 / tf32
+runs the IMPALA convolutions on this repo's im2col + tcgen05 GEMM path (common/engine.py::ImpalaEngineTC), --matmul
+library on torch/cuDNN fp32 (TorchModuleEngine) for comparison.
 
-    python profiles/bench_procgen_synth.py [--n-envs 64] [--iters 3]
+    python profiles/bench_procgen_synth.py [--n-envs 64] [--iters 3] [--matmul tf32x3|tf32|library]
 """
 import argparse
 import json
@@ -48,6 +49,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-envs", type=int, default=64)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--matmul", default="tf32x3", choices=["tf32x3", "tf32", "library"])
+    ap.add_argument("--phase-times", action="store_true", help="also time rollout and update separately")
     args = ap.parse_args()
     from tpp_b200.agents.ppo import PPO
     from tpp_b200.common.model import ImpalaModel
@@ -60,7 +63,7 @@ def main():
     st = Storage((3, 64, 64), 256, T, N, "cuda")
     # hard-500 set (hyperparams/procgen/config.yml:81-99): 3 epochs, n_minibatch 8 (default), mini_batch_size 8192
     agent = PPO(env, pol, None, st, "cuda", 0, n_steps=T, n_envs=N, epoch=3, n_minibatch=8, mini_batch_size=8192,
-                gamma=0.999, lmbda=0.95, learning_rate=5e-4, entropy_coef=0.01)
+                gamma=0.999, lmbda=0.95, learning_rate=5e-4, entropy_coef=0.01, matmul=args.matmul)
     agent.train(T * N)                       # warm-up iteration
     torch.cuda.synchronize()
     st.h2d_bytes = 0
@@ -69,10 +72,18 @@ def main():
     agent.train(T * N * args.iters)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print(json.dumps({"workload": f"procgen-shaped PPO, IMPALA-CNN (library convs), n_envs={N}, n_steps={T}, "
-                                  f"minibatch={agent.mini_batch_size}, synthetic host frames",
-                      "env_steps_per_s": round(T * N * args.iters / dt, 1), "s_per_iteration": round(dt / args.iters, 4),
-                      "h2d_bytes_per_iteration": st.h2d_bytes // args.iters}))
+    out = {"workload": f"procgen-shaped PPO, IMPALA-CNN ({type(agent.engine).__name__}, matmul={args.matmul}), "
+                       f"n_envs={N}, n_steps={T}, minibatch={agent.mini_batch_size}, synthetic host frames",
+           "env_steps_per_s": round(T * N * args.iters / dt, 1), "s_per_iteration": round(dt / args.iters, 4),
+           "h2d_bytes_per_iteration": st.h2d_bytes // args.iters}
+    if args.phase_times:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            agent.optimize()
+        torch.cuda.synchronize()
+        out["s_per_update_phase"] = round((time.perf_counter() - t0) / 3, 4)
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,250 @@
+"""GPU: the IMPALA-CNN building blocks (csrc/conv.cu + tpp_gemm_tc) against torch fp32 / fp64 references of the same
+ops (reference common/model.py:134-208): 3x3 convolution forward, data gradient and weight gradient as im2col +
+tensor-core GEMM, max-pool 3x3/2 forward and backward, narrow column sums, and the whole ImpalaEngineTC forward /
+backward against torch autograd on the same flat parameters.  Tolerances: 3xTF32 is fp32-grade -> 2e-5 relative to
+the output scale for single layers, 1e-4 for gradients that contract over B*H*W >= 10^4 terms."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from tpp_b200 import _lib
+    return _lib
+
+
+def _pair(x):
+    hi = ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, x - hi
+
+
+def _close(a, b, tol):
+    a, b = a.double().cpu(), b.double().cpu()
+    scale = b.abs().max().item() + 1e-30
+    err = (a - b).abs().max().item()
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e} (tol {tol})"
+
+
+@pytest.mark.parametrize("B,H,W,C,relu,u8", [(2, 8, 8, 16, 0, 0), (3, 7, 5, 32, 1, 0), (2, 14, 14, 3, 0, 0),
+                                             (2, 9, 6, 3, 0, 1)])
+def test_im2col_matches_unfold(B, H, W, C, relu, u8):
+    L = _lib()
+    torch.manual_seed(0)
+    if u8:
+        x = torch.randint(0, 256, (B, H, W, C), dtype=torch.uint8, device="cuda")
+        xf, scale = x.float() / 255.0, 1.0 / 255.0
+    else:
+        x = torch.randn(B, H, W, C, device="cuda")
+        xf, scale = x, 1.0
+    Kp = (9 * C + 31) // 32 * 32
+    hi = torch.full((B * H * W, Kp), 7.0, device="cuda")
+    lo = torch.full((B * H * W, Kp), 7.0, device="cuda")
+    L.call("tpp_im2col3x3", L.ptr(x), u8, B, H, W, C, H * W * C, W * C, C, 1, relu, scale, L.ptr(hi), L.ptr(lo), Kp,
+           L.stream_ptr())
+    ref_in = (F.relu(xf) if relu else xf).permute(0, 3, 1, 2)
+    # unfold: [B, C*9, HW] with index c*9 + tap -> reorder to tap*C + c
+    ref = F.unfold(ref_in, 3, padding=1).view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)
+    got = hi + lo
+    if u8:
+        torch.testing.assert_close(got[:, :9 * C], ref, rtol=1e-6, atol=1e-7)   # x*(1/255) vs x/255
+    else:
+        assert torch.equal(got[:, :9 * C], ref)
+    assert torch.equal(hi[:, :9 * C], _pair(got[:, :9 * C].contiguous())[0])
+    assert (hi[:, 9 * C:] == 0).all() and (lo[:, 9 * C:] == 0).all()
+
+
+def test_im2col_reads_nchw_rows_through_strides():
+    L = _lib()
+    B, C, H, W = 3, 3, 10, 12
+    ld = C * H * W + 8
+    x = torch.randn(B, ld, device="cuda")
+    Kp = 32
+    hi = torch.zeros(B * H * W, Kp, device="cuda")
+    lo = torch.zeros_like(hi)
+    L.call("tpp_im2col3x3", L.ptr(x), 0, B, H, W, C, ld, W, 1, H * W, 0, 1.0, L.ptr(hi), L.ptr(lo), Kp, L.stream_ptr())
+    img = x[:, :C * H * W].reshape(B, C, H, W)
+    ref = F.unfold(img, 3, padding=1).view(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)
+    assert torch.equal((hi + lo)[:, :27], ref)
+
+
+def _conv_gemm(L, col, w_pair, rows, cout, Kp, **kw):
+    g = L.TcGemm()
+    g.a_hi, g.a_lo, g.lda = col[0].data_ptr(), col[1].data_ptr(), Kp
+    g.b_hi, g.b_lo, g.ldb = w_pair[0].data_ptr(), w_pair[1].data_ptr(), Kp
+    g.M, g.N, g.K, g.precision, g.split_k = rows, cout, Kp, 3, 1
+    for k, v in kw.items():
+        setattr(g, k, v)
+    L.call("tpp_gemm_tc", L.C.byref(g), L.stream_ptr())
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32),
+                                            (2, 64, 64, 3, 16), (5, 7, 7, 32, 32)])
+def test_conv3x3_forward_residual_relu(B, H, W, cin, cout):
+    L = _lib()
+    torch.manual_seed(1)
+    x = torch.randn(B, H, W, cin, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+    bias = torch.randn(cout, device="cuda")
+    skip = torch.randn(B * H * W, cout, device="cuda")
+    Kp = (9 * cin + 31) // 32 * 32
+    rows = B * H * W
+    col = (torch.zeros(rows, Kp, device="cuda"), torch.zeros(rows, Kp, device="cuda"))
+    L.call("tpp_im2col3x3", L.ptr(x), 0, B, H, W, cin, H * W * cin, W * cin, cin, 1, 1, 1.0, L.ptr(col[0]),
+           L.ptr(col[1]), Kp, L.stream_ptr())
+    wf = torch.zeros(cout, Kp, device="cuda")
+    wf[:, :9 * cin] = w.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    out = torch.zeros(rows, cout, device="cuda")
+    oh, ol = torch.zeros_like(out), torch.zeros_like(out)
+    _conv_gemm(L, col, _pair(wf), rows, cout, Kp, flags=L.EPI_BIAS | L.EPI_ADD | L.EPI_RELU_OUT,
+               bias=bias.data_ptr(), addend=skip.data_ptr(), ld_add=cout, out=out.data_ptr(), out_hi=oh.data_ptr(),
+               out_lo=ol.data_ptr(), ldc=cout)
+    ref = F.conv2d(F.relu(x.double()).permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)
+    ref = F.relu(ref.permute(0, 2, 3, 1).reshape(rows, cout) + skip.double())
+    _close(out, ref, 2e-5)
+    assert torch.equal(oh + ol, out)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32),
+                                            (2, 14, 14, 3, 16)])
+def test_conv3x3_weight_gradient(B, H, W, cin, cout):
+    """dWf = dY^T col(X): both operands MN-major, 16-wide dY exercises the narrow (ld < 32) tensor map."""
+    L = _lib()
+    torch.manual_seed(2)
+    x = torch.randn(B, H, W, cin, device="cuda")
+    dy = torch.randn(B * H * W, cout, device="cuda")
+    Kp = (9 * cin + 31) // 32 * 32
+    rows = B * H * W
+    col = (torch.zeros(rows, Kp, device="cuda"), torch.zeros(rows, Kp, device="cuda"))
+    L.call("tpp_im2col3x3", L.ptr(x), 0, B, H, W, cin, H * W * cin, W * cin, cin, 1, 0, 1.0, L.ptr(col[0]),
+           L.ptr(col[1]), Kp, L.stream_ptr())
+    dyp = _pair(dy)
+    for bn, split in ((128, 1), (256, 7), (128, 64)):
+        gw = torch.zeros(cout, Kp, device="cuda")
+        g = L.TcGemm()
+        g.a_hi, g.a_lo, g.lda = dyp[0].data_ptr(), dyp[1].data_ptr(), cout
+        g.b_hi, g.b_lo, g.ldb = col[0].data_ptr(), col[1].data_ptr(), Kp
+        g.M, g.N, g.K, g.precision, g.split_k, g.a_mn, g.b_mn = cout, 9 * cin, rows, 3, split, 1, 1
+        g.flags, g.out, g.ldc, g.block_n = L.EPI_ACCUM, gw.data_ptr(), Kp, bn
+        L.call("tpp_gemm_tc", L.C.byref(g), L.stream_ptr())
+        xd = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+        wd = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+        y = F.conv2d(xd, wd, padding=1)
+        y.backward(dy.double().view(B, H, W, cout).permute(0, 3, 1, 2))
+        ref = wd.grad.permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+        _close(gw[:, :9 * cin], ref, 1e-4)
+        assert (gw[:, 9 * cin:] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 9, 9, 32, 32)])
+def test_conv3x3_data_gradient_mask_skip_colsum(B, H, W, cin, cout):
+    L = _lib()
+    torch.manual_seed(3)
+    xpre = torch.randn(B * H * W, cin, device="cuda")          # pre-ReLU input of the conv (mask)
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+    dy = torch.randn(B, H, W, cout, device="cuda")
+    skip = torch.randn(B * H * W, cin, device="cuda")
+    Kd = (9 * cout + 31) // 32 * 32
+    rows = B * H * W
+    col = (torch.zeros(rows, Kd, device="cuda"), torch.zeros(rows, Kd, device="cuda"))
+    L.call("tpp_im2col3x3", L.ptr(dy), 0, B, H, W, cout, H * W * cout, W * cout, cout, 1, 0, 1.0, L.ptr(col[0]),
+           L.ptr(col[1]), Kd, L.stream_ptr())
+    wdm = torch.zeros(cin, Kd, device="cuda")
+    wdm[:, :9 * cout] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, 9 * cout)
+    dx = torch.zeros(rows, cin, device="cuda")
+    dh, dl = torch.zeros_like(dx), torch.zeros_like(dx)
+    cs = torch.zeros(cin, device="cuda")
+    _conv_gemm(L, col, _pair(wdm), rows, cin, Kd, flags=L.EPI_MASK | L.EPI_ADD, mask=xpre.data_ptr(), ld_mask=cin,
+               addend=skip.data_ptr(), ld_add=cin, out=dx.data_ptr(), out_hi=dh.data_ptr(), out_lo=dl.data_ptr(),
+               ldc=cin, colsum=cs.data_ptr())
+    xd = xpre.double().view(B, H, W, cin).permute(0, 3, 1, 2).requires_grad_(True)
+    y = F.conv2d(F.relu(xd), w.double(), padding=1)
+    y.backward(dy.double().permute(0, 3, 1, 2))
+    ref = xd.grad.permute(0, 2, 3, 1).reshape(rows, cin) + skip.double()
+    _close(dx, ref, 2e-5)
+    _close(cs, ref.sum(0), 1e-4)
+    assert torch.equal(dh + dl, dx)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 64, 64, 16), (2, 14, 14, 16), (2, 7, 7, 32), (4, 5, 9, 32), (1, 2, 2, 16)])
+def test_maxpool_forward_backward(B, H, W, C):
+    L = _lib()
+    torch.manual_seed(4)
+    x = torch.randn(B, H, W, C, device="cuda")
+    x[0, :, :, 0] = 0.5                                           # ties: first maximum wins, like torch
+    Ho, Wo = (H + 1) // 2, (W + 1) // 2
+    y = torch.zeros(B, Ho, Wo, C, device="cuda")
+    arg = torch.zeros(B, Ho, Wo, C, dtype=torch.uint8, device="cuda")
+    L.call("tpp_maxpool3x3s2_fwd", L.ptr(x), B, H, W, C, L.ptr(y), L.ptr(arg), L.stream_ptr())
+    xt = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = F.max_pool2d(xt, 3, 2, 1)
+    assert torch.equal(y.permute(0, 3, 1, 2), ref)
+    dy = torch.randn(B, Ho, Wo, C, device="cuda")
+    ref.backward(dy.permute(0, 3, 1, 2))
+    dx = torch.zeros_like(x)
+    dh, dl = torch.zeros_like(x), torch.zeros_like(x)
+    L.call("tpp_maxpool3x3s2_bwd", L.ptr(dy), L.ptr(arg), B, H, W, C, L.ptr(dx), L.ptr(dh), L.ptr(dl), L.stream_ptr())
+    torch.testing.assert_close(dx.permute(0, 3, 1, 2), xt.grad, rtol=1e-6, atol=1e-6)
+    assert torch.equal(dh + dl, dx)
+
+
+@pytest.mark.parametrize("M,C", [(1000, 16), (4097, 32), (64 * 64 * 8, 16), (3, 64)])
+def test_colsum_narrow(M, C):
+    L = _lib()
+    x = torch.randn(M, C, device="cuda")
+    out = torch.ones(C, device="cuda")
+    L.call("tpp_colsum_narrow", L.ptr(x), M, C, L.ptr(out), L.stream_ptr())
+    _close(out, 1.0 + x.double().sum(0), 1e-5)
+
+
+@pytest.mark.parametrize("hw,B,A", [((64, 64), 6, 15), ((14, 14), 9, 4)])
+def test_impala_engine_forward_backward_vs_autograd(hw, B, A):
+    """Whole embedder + heads: head outputs and every parameter gradient against torch autograd of a float64 copy of
+    the same parameters (the fp32 cuDNN path's own error against float64 is printed for scale: the hand-written
+    path must be at least as close)."""
+    import copy
+    from tpp_b200.common.engine import ImpalaEngineTC
+    from tpp_b200.common.model import ImpalaModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(5)
+    pol = CategoricalPolicy(ImpalaModel(3, input_hw=hw), False, A).to("cuda")
+    pol64 = copy.deepcopy(pol).double()
+    pol.flatten_()
+    eng = ImpalaEngineTC(pol, A, (3, *hw))
+    ld = 3 * hw[0] * hw[1]
+    x = torch.rand(B, ld, device="cuda")
+    head = eng.forward(x, B, train=True)
+    feat64, _, fs64, _ = pol64.embedder.forward_with_attn_indices(x.double().view(B, 3, *hw))
+    ref_head = torch.cat((pol64.fc_policy(feat64), pol64.fc_value(feat64)), 1)
+    feat32, _, _, _ = pol.embedder.forward_with_attn_indices(x.view(B, 3, *hw))
+    lib_head = torch.cat((pol.fc_policy(feat32), pol.fc_value(feat32)), 1)
+    scale = ref_head.abs().max().item()
+    err_tc = (head[:, :A + 1].double() - ref_head).abs().max().item() / scale
+    err_lib = (lib_head.double() - ref_head).abs().max().item() / scale
+    print(f"head rel err vs float64: hand-written {err_tc:.2e}, cuDNN fp32 {err_lib:.2e}")
+    # 17 layers deep; the tensor core adds into its fp32 accumulator with truncation, which costs ~1e-5 over cuDNN
+    assert err_tc <= max(5e-5, 2.0 * err_lib)
+    np.testing.assert_allclose(eng.last_fs.item(), fs64.item(), rtol=1e-5)
+    dhead = torch.zeros(B, eng.ld_head, device="cuda")
+    dhead[:, :A + 1] = torch.randn(B, A + 1, device="cuda")
+    ref_head.backward(dhead[:, :A + 1].double())
+    ref = {n: p.grad for n, p in pol64.named_parameters()}
+    pol.flat_grad.zero_()
+    lib_head.backward(dhead[:, :A + 1])
+    lib_grad = pol.flat_grad.clone()
+    pol.flat_grad.zero_()
+    eng.backward(dhead, B)
+    worst_tc = worst_lib = 0.0
+    for name, (off, shape) in pol.layout.items():
+        n = int(np.prod(shape))
+        b = ref[name].reshape(-1)
+        scale = b.abs().max().item() + 1e-12
+        e_tc = (pol.flat_grad[off:off + n].double() - b).abs().max().item() / scale
+        e_lib = (lib_grad[off:off + n].double() - b).abs().max().item() / scale
+        worst_tc, worst_lib = max(worst_tc, e_tc), max(worst_lib, e_lib)
+        assert e_tc <= max(1e-4, 3.0 * e_lib), f"{name}: rel err {e_tc:.3e} (cuDNN fp32: {e_lib:.3e})"
+    print(f"gradient rel err vs float64: hand-written {worst_tc:.2e}, cuDNN fp32 {worst_lib:.2e}")

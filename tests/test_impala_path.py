@@ -1,5 +1,6 @@
-"""GPU: IMPALA-CNN policy (reference common/model.py:134-208) through the engine's library path (cuDNN via torch for
-the convolutions this round) with this repo's gather / fused loss / clip+Adam kernels, and the host-stepped env path
+"""GPU: IMPALA-CNN policy (reference common/model.py:134-208) through the hand-written engine (im2col + tcgen05 GEMM,
+matmul="tf32x3") and through the library cross-check path (cuDNN via torch, matmul="library"), both with this
+repo's gather / fused loss / clip+Adam kernels, and the host-stepped env path
 (Procgen-style numpy VecEnv staged through Storage.store).  Parity: one optimize() against the torch-CPU oracle."""
 import numpy as np
 import pytest
@@ -23,11 +24,14 @@ def _impala_agent(T, N, A, hw=(64, 64), **kw):
     return agent, pol, st
 
 
-def test_impala_optimize_matches_oracle():
+@pytest.mark.parametrize("matmul", ["tf32x3", "library"])
+def test_impala_optimize_matches_oracle(matmul):
+    from tpp_b200.common.engine import ImpalaEngineTC, TorchModuleEngine
     T, N, A = 8, 16, 15
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    agent, pol, st = _impala_agent(T, N, A)
+    agent, pol, st = _impala_agent(T, N, A, matmul=matmul)
+    assert isinstance(agent.engine, ImpalaEngineTC if matmul == "tf32x3" else TorchModuleEngine)
     g = torch.Generator().manual_seed(0)
     frames = torch.randint(0, 256, (T + 1, N, 64, 64, 3), generator=g, dtype=torch.uint8)
     st.frames.copy_(frames.cuda())

@@ -15,8 +15,8 @@ import numpy as np
 import torch
 
 from .. import _lib, parallel
-from ..common.engine import MLPEngine, MLPEngineTC, TorchModuleEngine
-from ..common.model import MLPModel
+from ..common.engine import ImpalaEngineTC, MLPEngine, MLPEngineTC, TorchModuleEngine
+from ..common.model import ImpalaModel, MLPModel
 from .base_agent import BaseAgent
 
 
@@ -137,7 +137,13 @@ class PPO(BaseAgent):
                 self.engine = MLPEngine(policy, self.n_actions)
             else:
                 self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1)
+        elif isinstance(policy.embedder, ImpalaModel) and self.matmul in ("tf32x3", "tf32") \
+                and not fs_coef:
+            # IMPALA convolutions as im2col + tcgen05 GEMM (hand-written path)
+            self.engine = ImpalaEngineTC(policy, self.n_actions, storage.obs_shape,
+                                         precision=3 if self.matmul == "tf32x3" else 1)
         else:
+            # matmul="library": cuDNN/cuBLAS through torch autograd (cross-check path, other embedders)
             self.engine = TorchModuleEngine(policy, self.n_actions, storage.obs_shape)
         self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
         self.world_size = 1
@@ -246,7 +252,7 @@ class PPO(BaseAgent):
             s = _lib.stream_ptr()          # evaluated here: under graph capture the current stream is the capture stream
             self._stats_cur.zero_()
             st.gather(self._idx_cur, buf)
-            if is_torch_engine:
+            if is_torch_engine or isinstance(engine, ImpalaEngineTC):
                 head = engine.forward(buf.obs, mb, train=True)
             elif buf.obs_lo is not None:
                 head = engine.forward(buf.obs, mb, x_lo=buf.obs_lo)
@@ -295,8 +301,8 @@ class PPO(BaseAgent):
                 if isinstance(entry, tuple):
                     entry[0].replay()
                     self.n_launches += entry[1]
-                if is_torch_engine and engine.last_fs is not None:
-                    fs_vals.append(engine.last_fs.detach())
+                if getattr(engine, "last_fs", None) is not None:
+                    fs_vals.append(engine.last_fs.detach().clone())
                 self._stats[k].copy_(self._stats_cur)
                 if cnt % accum == 0:
                     if self.world_size > 1:

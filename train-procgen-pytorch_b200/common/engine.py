@@ -3,9 +3,12 @@ kernels (no autograd on the hot path).
 
 * ``MLPEngine``   — MLPModel + heads: every layer is one C-ABI GEMM call with fused bias/ReLU(-mask) epilogue;
                     backward accumulates straight into the flat gradient buffer.
-* ``TorchModuleEngine`` — library path (cuDNN/cuBLAS through torch autograd) for embedders that do not yet have
-                    hand-written kernels (IMPALA convolutions this round).  The heads' output still feeds the
-                    fused loss kernel and the flat-buffer Adam; only the embedder's contraction is library code.
+* ``MLPEngineTC`` — the same on the tcgen05 tensor-core GEMM (3xTF32 parity mode or single-pass TF32).
+* ``ImpalaEngineTC`` — ImpalaModel + heads: NHWC activations, 3x3 convolutions as im2col + tcgen05 GEMM with the
+                    residual adds / ReLU masks / bias gradients fused into the GEMM epilogues, max-pool kernels.
+* ``TorchModuleEngine`` — library path (cuDNN/cuBLAS through torch autograd) kept as the cross-check for
+                    ``ImpalaEngineTC`` and for embedders without hand-written kernels.  The heads' output still
+                    feeds the fused loss kernel and the flat-buffer Adam.
 
 Replaces: ``policy.embedder.forward_with_attn_indices`` + ``policy.hidden_to_output`` + ``loss.backward()``
 (agents/ppo.py:125-128,170) and ``policy(obs, hx, mask)`` in ``PPO.predict`` (agents/ppo.py:76).
@@ -15,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import EPI_ACCUM, EPI_BIAS, EPI_MASK, EPI_RELU
+from .._lib import EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -232,7 +235,7 @@ class MLPEngineTC(MLPEngine):
         return ws
 
     def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
-            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0):
+            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0):
         g = _lib.TcGemm()
         g.a_hi, g.a_lo, g.lda = a[0].data_ptr(), a[1].data_ptr(), lda
         g.b_hi, g.b_lo, g.ldb = b[0].data_ptr(), b[1].data_ptr(), ldb
@@ -248,6 +251,8 @@ class MLPEngineTC(MLPEngine):
             g.out_hi, g.out_lo = out_pair[0].data_ptr(), out_pair[1].data_ptr()
         if colsum is not None:
             g.colsum = colsum.value
+        if addend is not None:
+            g.addend, g.ld_add = addend.data_ptr(), ld_add
         g.ldc = ldc
         _lib.call("tpp_gemm_tc", _lib.C.byref(g), _lib.stream_ptr())
         self.n_launches += 1
@@ -332,3 +337,303 @@ class MLPEngineTC(MLPEngine):
                          ld_mask=prev["ld"], out_pair=(nxt["hi"], nxt["lo"]), ldc=prev["ld"],
                          colsum=self._g(self.layers[i - 1][1]))
                 cur, ld_dz = cur ^ 1, prev["ld"]
+
+
+class ImpalaEngineTC:
+    """ImpalaModel (common/model.py:81-114; reference common/model.py:134-208) + heads on this repo's kernels.
+
+    Activations are NHWC fp32 ``[B*H*W, C]`` matrices.  A 3x3 / pad-1 convolution is ``tpp_im2col3x3`` (window
+    gather that also applies the ReLU in front of residual convolutions and writes the TF32 operand pair) followed by
+    one ``tpp_gemm_tc`` with the bias, the residual add (``TPP_EPI_ADD``) and -- behind the last block -- the trailing
+    ReLU fused into the epilogue.  Backward mirrors it: the data gradient is the same two kernels applied to dY with
+    tap-flipped weights, with the ReLU mask of the convolution's input, the skip-path gradient and the bias gradient
+    of the layer below (column sums) fused into the epilogue; the weight gradient is ``dY^T col(X)`` with both
+    operands MN-major and the contraction over B*H*W split across CTAs.  Weight copies in GEMM layout
+    (``Wf[co][tap*Cin+ci]``, ``Wd[ci][tap*Cout+co]``, the fc weight with NHWC column order) are rebuilt from the flat
+    fp32 parameters by ``refresh_weights`` after every optimizer step; their gradients are accumulated in GEMM layout
+    and folded back into the flat gradient buffer at the end of ``backward``.
+
+    ``x`` for ``forward`` is what ``tpp_gather_img`` / ``tpp_frames_to_obs`` produce: fp32 rows ``[M][ld]`` holding
+    the frame as NCHW / 255 (the first im2col reads it through strides, nothing is transposed).
+    The feature-sparsity term of ``forward_with_attn_indices`` (common/model.py:203-208) has coefficient 0 in every
+    shipped config: its VALUE is reported (three small torch reductions over the flattened features, logging only),
+    its gradient is not implemented here (``fs_coef != 0`` selects ``TorchModuleEngine``).
+    """
+
+    _tc = MLPEngineTC._tc
+    WGRAD_CHUNK = 1024   # rows contracted per CTA before the partial sums meet in IEEE fp32 atomics
+
+    def __init__(self, policy, n_actions, obs_shape, precision=3):
+        assert policy.flat is not None, "call policy.flatten_() first"
+        assert precision in (1, 3)
+        self.policy, self.A, self.precision = policy, n_actions, precision
+        self.flat, self.gflat = policy.flat, policy.flat_grad
+        self.device = self.flat.device
+        self.ld_head = _ceil(n_actions + 1, 4) * 4
+        self.obs_shape = tuple(obs_shape)
+        self.n_launches = 0
+        self.last_fs = None
+        self._ws = {}
+        emb = policy.embedder
+        self._names = {id(p): n for n, p in policy.named_parameters()}
+        C, H, W = self.obs_shape
+        self.convs, self.blocks = [], []
+        h, w, cin = H, W, C
+        for blk in (emb.block1, emb.block2, emb.block3):
+            cout = blk.conv.out_channels
+            assert cout % 16 == 0 and cout <= 64, "conv widths must be 16/32/48/64 (GEMM N tile, narrow column sums)"
+            ci = self._add_conv(blk.conv, cin, cout, need_dgrad=len(self.convs) > 0)
+            ho, wo = (h + 1) // 2, (w + 1) // 2
+            res = [(self._add_conv(rb.conv1, cout, cout), self._add_conv(rb.conv2, cout, cout))
+                   for rb in (blk.res1, blk.res2)]
+            self.blocks.append(dict(conv=ci, res=res, H=h, W=w, Ho=ho, Wo=wo, cin=cin, cout=cout))
+            h, w, cin = ho, wo, cout
+        self.enc_hw, self.enc_c, self.enc = h * w, cin, h * w * cin
+        assert emb.fc.in_features == self.enc and self.enc % 32 == 0
+        self.latent = emb.fc.out_features
+        self.fc_w_off, self.fc_b_off = self._off(emb.fc.weight), self._off(emb.fc.bias)
+        self.head_w_off = policy.layout["fc_policy.weight"][0]
+        self.head_b_off = policy.layout["fc_policy.bias"][0]
+        assert policy.layout["fc_value.weight"][0] == self.head_w_off + n_actions * self.latent
+        assert policy.layout["fc_value.bias"][0] == self.head_b_off + n_actions
+        f = dict(dtype=torch.float32, device=self.device)
+        # weight-gradient accumulators in GEMM layout: one zeroable buffer, one view per layer
+        sizes = [c["cout"] * c["Kf"] for c in self.convs] + [self.latent * self.enc]
+        self.gtmp = torch.zeros(sum(sizes), **f)
+        o = 0
+        for c, n in zip(self.convs, sizes[:-1]):
+            c["gw"] = self.gtmp[o:o + n].view(c["cout"], c["Kf"])
+            o += n
+        self.gfc = self.gtmp[o:o + sizes[-1]].view(self.latent, self.enc)
+        self.wfc_plain = torch.zeros(self.latent, self.enc, **f)
+        self.wfc = (torch.zeros(self.latent, self.enc, **f), torch.zeros(self.latent, self.enc, **f))
+        nh = n_actions + 1
+        self.wh = (torch.zeros(nh, self.latent, **f), torch.zeros(nh, self.latent, **f))
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------------------------------
+    def _off(self, param):
+        return self.policy.layout[self._names[id(param)]][0]
+
+    def _p(self, off):
+        return _lib.C.c_void_p(self.flat.data_ptr() + 4 * off)
+
+    def _g(self, off):
+        return _lib.C.c_void_p(self.gflat.data_ptr() + 4 * off)
+
+    def _add_conv(self, conv, cin, cout, need_dgrad=True):
+        f = dict(dtype=torch.float32, device=self.device)
+        Kf, Kd = _ceil(9 * cin, 32) * 32, _ceil(9 * cout, 32) * 32
+        c = dict(w_off=self._off(conv.weight), b_off=self._off(conv.bias), cin=cin, cout=cout, Kf=Kf, Kd=Kd,
+                 wf_plain=torch.zeros(cout, Kf, **f), wf=(torch.zeros(cout, Kf, **f), torch.zeros(cout, Kf, **f)))
+        if need_dgrad:
+            c["wd_plain"] = torch.zeros(cin, Kd, **f)
+            c["wd"] = (torch.zeros(cin, Kd, **f), torch.zeros(cin, Kd, **f))
+        self.convs.append(c)
+        return len(self.convs) - 1
+
+    def _split(self, plain, pair):
+        rows, cols = plain.shape
+        _lib.call("tpp_split_tf32", _lib.ptr(plain), cols, rows, cols, _lib.ptr(pair[0]), _lib.ptr(pair[1]), cols,
+                  None, None, 0, _lib.stream_ptr())
+        self.n_launches += 1
+
+    def refresh_weights(self):
+        """Rebuild the GEMM-layout TF32 weight copies from the flat fp32 parameters (after an optimizer step)."""
+        for c in self.convs:
+            cin, cout = c["cin"], c["cout"]
+            w = self.flat[c["w_off"]:c["w_off"] + cout * cin * 9].view(cout, cin, 3, 3)
+            c["wf_plain"][:, :9 * cin].view(cout, 3, 3, cin).copy_(w.permute(0, 2, 3, 1))
+            self._split(c["wf_plain"], c["wf"])
+            if "wd" in c:
+                c["wd_plain"][:, :9 * cout].view(cin, 3, 3, cout).copy_(w.flip(2, 3).permute(1, 2, 3, 0))
+                self._split(c["wd_plain"], c["wd"])
+        wfc = self.flat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
+        self.wfc_plain.view(self.latent, self.enc_hw, self.enc_c).copy_(wfc.permute(0, 2, 1))
+        self._split(self.wfc_plain, self.wfc)
+        wh = self.flat[self.head_w_off:self.head_w_off + (self.A + 1) * self.latent].view(self.A + 1, self.latent)
+        self._split(wh, self.wh)
+
+    # ------------------------------------------------------------------------------------------
+    def _workspace(self, M):
+        ws = self._ws.get(M)
+        if ws is not None:
+            return ws
+        ws = _Workspace()
+        f = dict(dtype=torch.float32, device=self.device)
+
+        def trio(n):
+            return dict(plain=torch.zeros(n, **f), hi=torch.zeros(n, **f), lo=torch.zeros(n, **f))
+
+        col_a = col_b = 0
+        ws.blk = []
+        for b in self.blocks:
+            rows_in, rows = M * b["H"] * b["W"], M * b["Ho"] * b["Wo"]
+            cout = b["cout"]
+            col_a = max(col_a, rows_in * self.convs[b["conv"]]["Kf"], rows * self.convs[b["res"][0][0]]["Kf"])
+            col_b = max(col_b, rows * self.convs[b["res"][0][0]]["Kd"],
+                        rows_in * self.convs[b["conv"]]["Kd"] if "wd" in self.convs[b["conv"]] else 0)
+            ws.blk.append(dict(a=torch.zeros(rows_in * cout, **f),
+                               arg=torch.zeros(rows * cout, dtype=torch.uint8, device=self.device),
+                               p=torch.zeros(rows * cout, **f), c1=torch.zeros(rows * cout, **f),
+                               r1=torch.zeros(rows * cout, **f), c2=torch.zeros(rows * cout, **f),
+                               r2=torch.zeros(rows * cout, **f),
+                               gX=trio(rows * cout), gY=trio(rows * cout), gZ=trio(rows * cout),
+                               ga=trio(rows_in * cout)))
+        ws.colA = (torch.zeros(col_a, **f), torch.zeros(col_a, **f))
+        ws.colB = (torch.zeros(col_b, **f), torch.zeros(col_b, **f))
+        ws.h = (torch.zeros(M, self.enc, **f), torch.zeros(M, self.enc, **f))        # relu(block3), NHWC-flattened
+        ws.f = (torch.zeros(M, self.latent, **f), torch.zeros(M, self.latent, **f))  # relu(fc)
+        ws.last_plain = torch.zeros(M, self.latent, **f)
+        ws.fc_acc = torch.zeros(M, self.latent, **f)
+        ws.dz = (torch.zeros(M, self.latent, **f), torch.zeros(M, self.latent, **f))
+        ws.head = torch.zeros(M, self.ld_head, **f)
+        ws.dhead = torch.zeros(M, self.ld_head, **f)
+        self._ws[M] = ws
+        return ws
+
+    def _im2col(self, src, B, H, W, C, strides, relu, col, Kp):
+        _lib.call("tpp_im2col3x3", _lib.ptr(src), 0, B, H, W, C, strides[0], strides[1], strides[2], strides[3],
+                  1 if relu else 0, 1.0, _lib.ptr(col[0]), _lib.ptr(col[1]) if self.precision == 3 else None, Kp,
+                  _lib.stream_ptr())
+        self.n_launches += 1
+
+    @staticmethod
+    def _nhwc(H, W, C):
+        return (H * W * C, W * C, C, 1)
+
+    def _conv_fwd(self, ws, ci, src, B, H, W, strides, relu, out=None, out_pair=None, addend=None, relu_out=False):
+        c = self.convs[ci]
+        rows = B * H * W
+        self._im2col(src, B, H, W, c["cin"], strides, relu, ws.colA, c["Kf"])
+        flags = EPI_BIAS | (EPI_ADD if addend is not None else 0) | (EPI_RELU_OUT if relu_out else 0)
+        self._tc(ws.colA, c["Kf"], c["wf"], c["Kf"], rows, c["cout"], c["Kf"], flags=flags, bias=self._p(c["b_off"]),
+                 out=out, out_pair=out_pair, ldc=c["cout"], addend=addend, ld_add=c["cout"])
+
+    def forward(self, x, M, feature_major_ld=None, need_backward=True, train=False):
+        assert feature_major_ld is None
+        ws = self._workspace(M)
+        C0, H0, W0 = self.obs_shape
+        src, strides = x, (x.stride(0), W0, 1, H0 * W0)
+        nb = len(self.blocks)
+        for k, (b, wb) in enumerate(zip(self.blocks, ws.blk)):
+            H, W, Ho, Wo, cout = b["H"], b["W"], b["Ho"], b["Wo"], b["cout"]
+            self._conv_fwd(ws, b["conv"], src, M, H, W, strides, relu=False, out=wb["a"])
+            _lib.call("tpp_maxpool3x3s2_fwd", _lib.ptr(wb["a"]), M, H, W, cout, _lib.ptr(wb["p"]), _lib.ptr(wb["arg"]),
+                      _lib.stream_ptr())
+            self.n_launches += 1
+            st = self._nhwc(Ho, Wo, cout)
+            (a1, b1), (a2, b2) = b["res"]
+            self._conv_fwd(ws, a1, wb["p"], M, Ho, Wo, st, relu=True, out=wb["c1"])
+            self._conv_fwd(ws, b1, wb["c1"], M, Ho, Wo, st, relu=True, out=wb["r1"], addend=wb["p"])
+            self._conv_fwd(ws, a2, wb["r1"], M, Ho, Wo, st, relu=True, out=wb["c2"])
+            if k == nb - 1:   # trailing ReLU + flatten: written directly as the fc layer's TF32 operand
+                self._conv_fwd(ws, b2, wb["c2"], M, Ho, Wo, st, relu=True, out_pair=ws.h, addend=wb["r1"], relu_out=True)
+            else:
+                self._conv_fwd(ws, b2, wb["c2"], M, Ho, Wo, st, relu=True, out=wb["r2"], addend=wb["r1"])
+            src, strides = wb["r2"], st
+        if self.enc > 512 and self.precision == 3:
+            # long contraction: chunks of 256 accumulated with IEEE adds (the tensor core truncates when it adds into
+            # its fp32 accumulator), then bias + ReLU + TF32 split
+            ws.fc_acc.zero_()
+            self._tc(ws.h, self.enc, self.wfc, self.enc, M, self.latent, self.enc, flags=EPI_ACCUM, out=ws.fc_acc,
+                     ldc=self.latent, split_k=_ceil(self.enc, 256))
+            _lib.call("tpp_bias_act_split", _lib.ptr(ws.fc_acc), self.latent, M, self.latent, self._p(self.fc_b_off), 1,
+                      _lib.ptr(ws.last_plain), _lib.ptr(ws.f[0]), _lib.ptr(ws.f[1]), self.latent, _lib.stream_ptr())
+            self.n_launches += 1
+        else:
+            self._tc(ws.h, self.enc, self.wfc, self.enc, M, self.latent, self.enc, flags=EPI_BIAS | EPI_RELU,
+                     bias=self._p(self.fc_b_off), out=ws.last_plain, out_pair=ws.f, ldc=self.latent)
+        self._tc(ws.f, self.latent, self.wh, self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
+                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
+        self._x = x
+        if train:   # logged value only: mean_j max_b tanh(|100 h_bj|), h >= 0 so the max commutes with tanh
+            self.last_fs = torch.tanh(100.0 * (ws.h[0] + ws.h[1]).amax(0)).mean()
+        return ws.head
+
+    # ------------------------------------------------------------------------------------------
+    def _wgrad(self, ws, ci, dy, src, B, H, W, strides, relu):
+        """gw[cout][tap*cin+ci] += dY^T col(X): dY pair [rows][cout] and col [rows][Kf] both MN-major."""
+        c = self.convs[ci]
+        rows = B * H * W
+        self._im2col(src, B, H, W, c["cin"], strides, relu, ws.colA, c["Kf"])
+        n = 9 * c["cin"]
+        bn = 256 if n > 128 else 128
+        tiles = _ceil(n, bn)
+        self._tc((dy["hi"], dy["lo"]), c["cout"], ws.colA, c["Kf"], c["cout"], n, rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
+                 out=c["gw"], ldc=c["Kf"], block_n=bn,
+                 split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, tiles), _ceil(rows, self.WGRAD_CHUNK)))))
+
+    def _dgrad(self, ws, ci, dy, B, H, W, out, mask=None, addend=None, colsum_off=None):
+        """dX = col(dY) Wd^T (* relu mask of the conv input) (+ skip gradient); column sums -> bias grad below."""
+        c = self.convs[ci]
+        rows = B * H * W
+        self._im2col(dy["plain"], B, H, W, c["cout"], self._nhwc(H, W, c["cout"]), False, ws.colB, c["Kd"])
+        flags = (EPI_MASK if mask is not None else 0) | (EPI_ADD if addend is not None else 0)
+        self._tc(ws.colB, c["Kd"], c["wd"], c["Kd"], rows, c["cin"], c["Kd"], flags=flags, mask=mask, ld_mask=c["cin"],
+                 out=out["plain"], out_pair=(out["hi"], out["lo"]), ldc=c["cin"], addend=addend, ld_add=c["cin"],
+                 colsum=self._g(colsum_off) if colsum_off is not None else None)
+
+    def _colsum(self, x, rows, C, off):
+        _lib.call("tpp_colsum_narrow", _lib.ptr(x), rows, C, self._g(off), _lib.stream_ptr())
+        self.n_launches += 1
+
+    def backward(self, dhead, M, fs_coef=0.0):
+        if fs_coef:
+            raise NotImplementedError("feature-sparsity gradient: use the library engine (matmul='library')")
+        ws, s = self._workspace(M), _lib.stream_ptr()
+        H, nh = self.latent, self.A + 1
+        assert H in (16, 32, 64, 128, 256) and nh <= 16
+        self.gtmp.zero_()
+        _lib.call("tpp_head_backward", _lib.ptr(dhead), self.ld_head, _lib.ptr(ws.last_plain), _lib.ptr(ws.f[0]), H,
+                  self._p(self.head_w_off), nh, H, _lib.ptr(ws.dz[0]), _lib.ptr(ws.dz[1]), None, H,
+                  self._g(self.head_w_off), self._g(self.head_b_off), self._g(self.fc_b_off), M, s)
+        self.n_launches += 1
+        # fc: weight gradient in NHWC column order, data gradient masked by the trailing ReLU of block 3
+        tiles = _ceil(H, 128) * _ceil(self.enc, 128)
+        self._tc(ws.dz, H, ws.h, self.enc, H, self.enc, M, a_mn=1, b_mn=1, flags=EPI_ACCUM, out=self.gfc, ldc=self.enc,
+                 split_k=max(1, min(_ceil(M, 32), max(_ceil(148, tiles), _ceil(M, 512)))), block_n=128)
+        last = ws.blk[-1]
+        d = last["gX"]
+        self._tc(ws.dz, H, self.wfc, self.enc, M, self.enc, H, b_mn=1, flags=EPI_MASK, mask=ws.h[0], ld_mask=self.enc,
+                 out=d["plain"], out_pair=(d["hi"], d["lo"]), ldc=self.enc)
+        for k in range(len(self.blocks) - 1, -1, -1):
+            b, wb = self.blocks[k], ws.blk[k]
+            Hh, Ww, Ho, Wo, cout = b["H"], b["W"], b["Ho"], b["Wo"], b["cout"]
+            rows = M * Ho * Wo
+            st = self._nhwc(Ho, Wo, cout)
+            (a1, b1), (a2, b2) = b["res"]
+            X, Y, Z = wb["gX"], wb["gY"], wb["gZ"]
+            if k == len(self.blocks) - 1:
+                self._colsum(X["plain"], rows, cout, self.convs[b2]["b_off"])
+            # res2: r2 = conv_b2(relu(c2)) + r1 ; c2 = conv_a2(relu(r1))
+            self._wgrad(ws, b2, X, wb["c2"], M, Ho, Wo, st, True)
+            self._dgrad(ws, b2, X, M, Ho, Wo, Y, mask=wb["c2"], colsum_off=self.convs[a2]["b_off"])
+            self._wgrad(ws, a2, Y, wb["r1"], M, Ho, Wo, st, True)
+            self._dgrad(ws, a2, Y, M, Ho, Wo, Z, mask=wb["r1"], addend=X["plain"], colsum_off=self.convs[b1]["b_off"])
+            # res1: r1 = conv_b1(relu(c1)) + p ; c1 = conv_a1(relu(p))
+            self._wgrad(ws, b1, Z, wb["c1"], M, Ho, Wo, st, True)
+            self._dgrad(ws, b1, Z, M, Ho, Wo, Y, mask=wb["c1"], colsum_off=self.convs[a1]["b_off"])
+            self._wgrad(ws, a1, Y, wb["p"], M, Ho, Wo, st, True)
+            self._dgrad(ws, a1, Y, M, Ho, Wo, X, mask=wb["p"], addend=Z["plain"])
+            # max-pool, then the block's first convolution
+            ga = wb["ga"]
+            _lib.call("tpp_maxpool3x3s2_bwd", _lib.ptr(X["plain"]), _lib.ptr(wb["arg"]), M, Hh, Ww, cout,
+                      _lib.ptr(ga["plain"]), _lib.ptr(ga["hi"]), _lib.ptr(ga["lo"]), s)
+            self.n_launches += 1
+            self._colsum(ga["plain"], M * Hh * Ww, cout, self.convs[b["conv"]]["b_off"])
+            if k == 0:
+                C0, H0, W0 = self.obs_shape
+                self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, (self._x.stride(0), W0, 1, H0 * W0), False)
+            else:
+                prev = ws.blk[k - 1]
+                self._wgrad(ws, b["conv"], ga, prev["r2"], M, Hh, Ww, self._nhwc(Hh, Ww, b["cin"]), False)
+                self._dgrad(ws, b["conv"], ga, M, Hh, Ww, prev["gX"],
+                            colsum_off=self.convs[self.blocks[k - 1]["res"][1][1]]["b_off"])
+        # fold the GEMM-layout weight gradients back into the flat gradient buffer
+        for c in self.convs:
+            cin, cout = c["cin"], c["cout"]
+            g = self.gflat[c["w_off"]:c["w_off"] + cout * cin * 9].view(cout, cin, 3, 3)
+            g += c["gw"][:, :9 * cin].view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        g = self.gflat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
+        g += self.gfc.view(self.latent, self.enc_hw, self.enc_c).permute(0, 2, 1)

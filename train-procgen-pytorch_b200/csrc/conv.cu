@@ -1,0 +1,234 @@
+// IMPALA-CNN building blocks in NHWC (reference: common/model.py:134-208): the 3x3 / pad-1 convolutions are run as
+// GEMMs on the tcgen05 kernel (csrc/gemm_tc.cu) over an explicitly materialised im2col matrix,
+//     col[p][tap*C + c] = act(x[b, y + ky - 1, x + kx - 1, c]),   p = (b*H + y)*W + x,  tap = ky*3 + kx,
+// written directly as the TF32 (hi, lo) operand pair; ReLU-on-load and the uint8 -> [0,1] frame scaling are fused
+// into this gather.  forward: Y = col(X) Wf^T; data gradient: dX = col(dY) Wd^T with flipped taps; weight gradient:
+// dWf = dY^T col(X) (both operands MN-major).  Max-pooling 3x3 / stride 2 / pad 1 keeps the argmax tap for the
+// backward pass, which is written in gather form (no atomics, deterministic).
+// Round-1 note: materialising col costs 9x the activation bytes; the TMA-im2col (implicit GEMM) variant is next.
+#include "tpp_common.cuh"
+
+namespace tpp {
+
+__device__ __forceinline__ float cv_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
+// One thread per 16-byte chunk of a col row (4 consecutive k): a warp writes 512 contiguous bytes of hi and of lo.
+// C % 4 == 0 and unit channel stride: the 4 values are one float4 of the source pixel.
+__global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                            long long sb, long long sy_, long long sx_, int relu,
+                                                            float scale, float* __restrict__ hi,
+                                                            float* __restrict__ lo, int Kp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kq = Kp >> 2;
+  const long long M = (long long)B * H * W;
+  if (t >= M * kq) return;
+  const long long p = t / kq;
+  const int k = (int)(t - p * kq) * 4;
+  const int tap = k / C, c = k - tap * C;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tap < 9) {
+    const int xx = (int)(p % W), yy = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + b * sb + sy * sy_ + sx * sx_ + c));
+  }
+  float a[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  float h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (relu) a[j] = fmaxf(a[j], 0.0f);
+    h[j] = cv_tf32(a[j]);
+  }
+  *reinterpret_cast<float4*>(hi + p * Kp + k) = make_float4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<float4*>(lo + p * Kp + k) = make_float4(a[0] - h[0], a[1] - h[1], a[2] - h[2], a[3] - h[3]);
+}
+
+// Generic layout (uint8 frames, NCHW rows, C = 3): one thread per col element, k fastest -> coalesced stores.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const TIn* __restrict__ x, int B, int H, int W, int C,
+                                                        long long sb, long long sy_, long long sx_, long long sc,
+                                                        int relu, float scale, float* __restrict__ hi,
+                                                        float* __restrict__ lo, int Kp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long M = (long long)B * H * W;
+  if (t >= M * Kp) return;
+  const long long p = t / Kp;
+  const int k = (int)(t - p * Kp);
+  const int tap = k / C, c = k - tap * C;
+  float q = 0.0f;
+  if (tap < 9) {
+    const int xx = (int)(p % W), yy = (int)((p / W) % H);
+    const long long b = p / ((long long)W * H);
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) q = (float)x[b * sb + sy * sy_ + sx * sx_ + c * sc] * scale;
+  }
+  if (relu) q = fmaxf(q, 0.0f);
+  const float h = cv_tf32(q);
+  hi[t] = h;
+  if (lo) lo[t] = q - h;
+}
+
+// NHWC max-pool 3x3, stride 2, pad 1: y [B, Ho, Wo, C], arg = winning tap 0..8 (first maximum, like torch).
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                          float* __restrict__ y, uint8_t* __restrict__ arg, int Ho,
+                                                          int Wo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * Ho * Wo * C;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int ox = (int)((t / C) % Wo), oy = (int)((t / ((long long)C * Wo)) % Ho);
+  const long long b = t / ((long long)C * Wo * Ho);
+  float best = -3.402823466e38f;
+  int bi = 0;
+  bool any = false;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = oy * 2 + tap / 3 - 1, sx = ox * 2 + tap % 3 - 1;
+    if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
+    const float v = x[((b * H + sy) * W + sx) * C + c];
+    if (!any || v > best) { best = v; bi = tap; any = true; }
+  }
+  y[t] = best;
+  arg[t] = (uint8_t)bi;
+}
+
+// dx[b, y, x, c] = sum over the (<= 4) pooling windows that contain (y, x) and whose argmax is this pixel.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                          int B, int H, int W, int C, int Ho, int Wo,
+                                                          float* __restrict__ dx, float* __restrict__ dx_hi,
+                                                          float* __restrict__ dx_lo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * H * W * C;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int xx = (int)((t / C) % W), yy = (int)((t / ((long long)C * W)) % H);
+  const long long b = t / ((long long)C * W * H);
+  float s = 0.0f;
+  // windows (oy, ox) with oy*2 - 1 <= yy <= oy*2 + 1
+  for (int oy = (yy) / 2; oy <= (yy + 1) / 2; ++oy) {
+    if (oy < 0 || oy >= Ho) continue;
+    const int ky = yy - (oy * 2 - 1);
+    if (ky < 0 || ky > 2) continue;
+    for (int ox = (xx) / 2; ox <= (xx + 1) / 2; ++ox) {
+      if (ox < 0 || ox >= Wo) continue;
+      const int kx = xx - (ox * 2 - 1);
+      if (kx < 0 || kx > 2) continue;
+      const long long o = ((b * Ho + oy) * Wo + ox) * C + c;
+      if (arg[o] == ky * 3 + kx) s += dy[o];
+    }
+  }
+  dx[t] = s;
+  if (dx_hi) {
+    const float h = cv_tf32(s);
+    dx_hi[t] = h;
+    dx_lo[t] = s - h;
+  }
+}
+
+// Column sums of a narrow row-major matrix [M][C], C in {4, 8, 16, 32, 64} (bias gradient of a convolution from its
+// NHWC output gradient): the matrix is read as one flat float4 stream, a thread's 4 columns never change.
+__global__ void __launch_bounds__(256) colsum_narrow_kernel(const float* __restrict__ x, long long total4, int C,
+                                                            float* __restrict__ out) {
+  __shared__ float part[256][4];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) part[threadIdx.x][j] = a[j];
+  __syncthreads();
+  // threads t, t + C/4, t + 2C/4, ... own the same columns (stride and blockDim are multiples of C/4)
+  const int groups = C / 4;
+  if ((int)threadIdx.x < groups) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = threadIdx.x; t < 256; t += groups)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] += part[t][j];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(out + threadIdx.x * 4 + j, s[j]);
+  }
+}
+
+// y = act(x + bias) as plain fp32 and/or TF32 pair: finishes a split-K (atomically accumulated) dense layer.
+__global__ void __launch_bounds__(256) bias_act_split_kernel(const float* __restrict__ x, long long ld_in, int M, int N,
+                                                             const float* __restrict__ bias, int relu,
+                                                             float* __restrict__ out, float* __restrict__ hi,
+                                                             float* __restrict__ lo, long long ld_out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)M * N) return;
+  const int n = (int)(t % N);
+  const long long m = t / N;
+  float v = x[m * ld_in + n] + (bias ? bias[n] : 0.0f);
+  if (relu) v = fmaxf(v, 0.0f);
+  if (out) out[m * ld_out + n] = v;
+  if (hi) {
+    const float h = cv_tf32(v);
+    hi[m * ld_out + n] = h;
+    lo[m * ld_out + n] = v - h;
+  }
+}
+
+}  // namespace tpp
+
+extern "C" int tpp_bias_act_split(const float* x, int64_t ld_in, int32_t M, int32_t N, const float* bias, int32_t relu,
+                                  float* out, float* out_hi, float* out_lo, int64_t ld_out, void* stream) {
+  TPP_CHECK_ARG(x && M > 0 && N > 0 && ld_in >= N && ld_out >= N && (out || out_hi));
+  TPP_CHECK_ARG((out_hi == nullptr) == (out_lo == nullptr));
+  tpp::bias_act_split_kernel<<<tpp_ceil_div((long long)M * N, 256), 256, 0, tpp_stream(stream)>>>(
+      x, ld_in, M, N, bias, relu, out, out_hi, out_lo, ld_out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t H, int32_t W, int32_t C, int64_t sb,
+                             int64_t sy, int64_t sx, int64_t sc, int32_t relu, float scale, float* col_hi,
+                             float* col_lo, int32_t Kp, void* stream) {
+  TPP_CHECK_ARG(x && col_hi && B > 0 && H > 0 && W > 0 && C > 0 && Kp >= 9 * C && (Kp & 3) == 0);
+  TPP_CHECK_ARG((reinterpret_cast<uintptr_t>(col_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(col_lo) & 15) == 0);
+  const long long rows = (long long)B * H * W;
+  cudaStream_t s = tpp_stream(stream);
+  if (x_is_u8) {
+    tpp::im2col3x3_kernel<uint8_t><<<tpp_ceil_div(rows * Kp, 256), 256, 0, s>>>(
+        reinterpret_cast<const uint8_t*>(x), B, H, W, C, sb, sy, sx, sc, relu, scale, col_hi, col_lo, Kp);
+  } else if ((C & 3) == 0 && sc == 1 && ((sb | sy | sx) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    tpp::im2col3x3_vec_kernel<<<tpp_ceil_div(rows * (Kp / 4), 256), 256, 0, s>>>(
+        reinterpret_cast<const float*>(x), B, H, W, C, sb, sy, sx, relu, scale, col_hi, col_lo, Kp);
+  } else {
+    tpp::im2col3x3_kernel<float><<<tpp_ceil_div(rows * Kp, 256), 256, 0, s>>>(
+        reinterpret_cast<const float*>(x), B, H, W, C, sb, sy, sx, sc, relu, scale, col_hi, col_lo, Kp);
+  }
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,
+                                    void* stream) {
+  TPP_CHECK_ARG(x && y && arg && B > 0 && H > 0 && W > 0 && C > 0);
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * Ho * Wo * C;
+  tpp::maxpool_fwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(x, B, H, W, C, y, arg, Ho, Wo);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t B, int32_t H, int32_t W, int32_t C,
+                                    float* dx, float* dx_hi, float* dx_lo, void* stream) {
+  TPP_CHECK_ARG(dy && arg && dx && B > 0 && H > 0 && W > 0 && C > 0 && ((dx_hi == nullptr) == (dx_lo == nullptr)));
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)B * H * W * C;
+  tpp::maxpool_bwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(dy, arg, B, H, W, C, Ho, Wo, dx,
+                                                                                    dx_hi, dx_lo);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_colsum_narrow(const float* x, int64_t M, int32_t C, float* out, void* stream) {
+  TPP_CHECK_ARG(x && out && M > 0 && (C == 4 || C == 8 || C == 16 || C == 32 || C == 64));
+  TPP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const long long total4 = M * C / 4;
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tpp::colsum_narrow_kernel<<<(int)blocks, 256, 0, tpp_stream(stream)>>>(x, total4, C, out);
+  TPP_LAUNCH_STATUS();
+}

@@ -33,10 +33,13 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;              // fp32 words per row of a stage = 128 bytes = one 128B-swizzle row
 constexpr int UMMA_K = 8;                // tf32: 32 bytes per MMA k-step
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
-constexpr int EPI_WARPS = 16;            // 4 per TMEM lane quarter: the epilogue is instruction-latency bound, not bandwidth bound
-constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue
+// Epilogue warps: 4 per TMEM lane quarter for wide tiles (the epilogue is instruction-latency bound, not bandwidth
+// bound); narrow tiles (one 32-column group: convolution outputs) have work for 4 warps only, and the small CTA
+// (192 threads x 80 registers) lets 3-4 tiles share an SM so that prologue / epilogue overlap other tiles' loads.
+constexpr int epi_warps(int block_n) { return block_n <= 32 ? 4 : 16; }
+constexpr int num_threads(int block_n) { return 64 + epi_warps(block_n) * 32; }   // warp 0: TMA, warp 1: MMA + TMEM
 constexpr int STG_PITCH = 36;            // floats per staged row (16-byte aligned, conflict-free 128-bit LDS/STS)
-constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;   // one 32x32 patch per epilogue warp
+constexpr int stg_bytes(int block_n) { return epi_warps(block_n) * 32 * STG_PITCH * 4; }   // a 32x32 patch per warp
 
 struct Params {
   int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
@@ -52,9 +55,11 @@ struct Params {
   float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
   int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
   long long* dbg;              // optional timeline probe (block 0 only): clock64 at 8 milestones
+  int ntn;                     // number of N tiles (grid.x = ntn * number of M tiles)
+  const float* addend; long long ld_add;   // optional residual: result += addend[m][n] (after bias / relu / mask)
 };
 
-enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8 };
+enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT = 32 };
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -179,7 +184,7 @@ __device__ __forceinline__ float tf32_round(float x) {
 // The kernel: one 128 x BLOCK_N output tile (x one k-split) per CTA
 // ---------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
   constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
@@ -204,8 +209,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
-  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  // tiles are flattened on grid.x (n fastest) so that M is not limited by the 65535 bound of grid.y (conv rows)
+  const int m0 = (int)(blockIdx.x / p.ntn) * BLOCK_M, n0 = (int)(blockIdx.x % p.ntn) * BLOCK_N;
+  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -292,6 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // lines (8 lanes per row, 4 rows per instruction), column sums are register accumulations.  EPI_WARPS/4 warps serve each
     // TMEM lane quarter (column groups round-robin).  The pipeline stages are free by now (tmem_full => all MMAs
     // retired), the patches alias them.
+    constexpr int EPI_WARPS = epi_warps(BLOCK_N);
     const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
@@ -332,7 +339,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const bool interior = lane_on && (mrow0 + 32 <= p.M) && (n + GW <= p.N) && ((p.ldc & 3) == 0) &&
                             (((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.out_hi) |
                                reinterpret_cast<uintptr_t>(p.out_lo)) & 15) == 0) &&
-                            (!(p.flags & F_MASK) || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0)));
+                            (!(p.flags & F_MASK) || (((p.ld_mask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0))) &&
+                            (!(p.flags & F_ADD) || (((p.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.addend) & 15) == 0)));
       if (__all_sync(0xffffffffu, interior || !lane_on) && !atomic) {
         if (lane_on) {
           const long long o0 = (long long)(mrow0 + rr) * p.ldc + nc, ostep = 4 * p.ldc;
@@ -341,7 +349,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float* pl = p.out_lo ? p.out_lo + o0 : nullptr;
           const float* pm = (p.flags & F_MASK) ? p.mask + (long long)(mrow0 + rr) * p.ld_mask + nc : nullptr;
           const long long mstep = 4 * p.ld_mask;
+          const float* pa = (p.flags & F_ADD) ? p.addend + (long long)(mrow0 + rr) * p.ld_add + nc : nullptr;
+          const long long astep = 4 * p.ld_add;
           const float floor_v = (p.flags & F_RELU) ? 0.0f : -3.402823466e38f;
+          const float floor_out = (p.flags & F_RELU_OUT) ? 0.0f : -3.402823466e38f;
           const float* sp = stg + rr * STG_PITCH + cc;
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
@@ -356,6 +367,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               x[2] = mq.z > 0.0f ? x[2] : 0.0f;
               x[3] = mq.w > 0.0f ? x[3] : 0.0f;
             }
+            if (pa) {
+              const float4 aq = *reinterpret_cast<const float4*>(pa);
+              pa += astep;
+              x[0] += aq.x; x[1] += aq.y; x[2] += aq.z; x[3] += aq.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_out);
 #pragma unroll
             for (int j = 0; j < 4; ++j) cs4[j] += x[j];
             if (po) { *reinterpret_cast<float4*>(po) = make_float4(x[0], x[1], x[2], x[3]); po += ostep; }
@@ -412,6 +430,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 4; ++j)
               if (nc + j < p.N && !(mk[j] > 0.0f)) x[j] = 0.0f;
           }
+        }
+        if (p.flags & F_ADD) {
+          const float* ad = p.addend + (long long)gm * p.ld_add + nc;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (nc + j < p.N) x[j] += ad[j];
+        }
+        if (p.flags & F_RELU_OUT) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) cs4[j] += x[j];
@@ -535,8 +563,10 @@ static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, 
   } else {
     if (box_rows < 32) return TPP_ENOTSUP;
     const long long blocks = (rows + 31) / 32;
-    if (ld < blocks * 32) return TPP_EINVAL;         // the last 32-wide block must lie inside the (padded) row
-    cuuint64_t gdim[3] = {32, (cuuint64_t)K, (cuuint64_t)blocks};
+    // the last 32-wide block must lie inside the (padded) row; a single narrow block (ld < 32, e.g. 16 conv channels)
+    // is described with its true width and the rest of the box is zero-filled by TMA
+    if (ld < blocks * 32 && blocks != 1) return TPP_EINVAL;
+    cuuint64_t gdim[3] = {(cuuint64_t)(ld < 32 ? ld : 32), (cuuint64_t)K, (cuuint64_t)blocks};
     cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, 128};
     cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)(box_rows / 32)};
     r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
@@ -563,6 +593,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   Params p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.npass = npass; p.flags = g->flags;
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
+  p.addend = g->addend; p.ld_add = g->ld_add;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
   p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(g->dbg);
@@ -574,11 +605,15 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const int stage_bytes = (A_BYTES + BLOCK_N * BLOCK_K * 4) * (npass == 3 ? 2 : 1);
   int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
   if (stages > 4) stages = 4;
+  // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
+  // per SM so that one tile's epilogue / prologue overlaps another tile's loads
+  const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
+  if (n_tiles >= 4 * 148 && stages > 2 && p.kb_per_split <= 16) stages = 2;
   if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
   // the epilogue's transpose patches alias the pipeline stages: the region must hold at least STG_BYTES
   size_t region = (size_t)stages * stage_bytes;
-  if (region < (size_t)STG_BYTES) region = STG_BYTES;
+  if (region < (size_t)stg_bytes(BLOCK_N)) region = stg_bytes(BLOCK_N);
   p.bar_offset = (int)region;
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
@@ -587,8 +622,9 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((g->N + BLOCK_N - 1) / BLOCK_N, (g->M + BLOCK_M - 1) / BLOCK_M, split_k);
-  gemm_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  p.ntn = (g->N + BLOCK_N - 1) / BLOCK_N;
+  dim3 grid((unsigned)p.ntn * (unsigned)((g->M + BLOCK_M - 1) / BLOCK_M), 1, split_k);
+  gemm_tc_kernel<BLOCK_N><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
 
@@ -602,13 +638,15 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
   TPP_CHECK_ARG(!atomic || g->out);
   TPP_CHECK_ARG(g->split_k <= 1 || atomic);
   TPP_CHECK_ARG(!(g->flags & tpp::tc::F_BIAS) || g->bias);
+  TPP_CHECK_ARG(!(g->flags & tpp::tc::F_ADD) || (g->addend && !(g->flags & tpp::tc::F_ATOMIC)));
   TPP_CHECK_ARG(!(g->flags & tpp::tc::F_MASK) || g->mask);
   TPP_CHECK_ARG((g->out_hi == nullptr) == (g->out_lo == nullptr));
   cudaStream_t s = tpp_stream(stream);
   int bn = g->block_n;
-  if (bn == 0) bn = g->N <= 16 ? 16 : (g->N <= 64 ? 64 : 128);
+  if (bn == 0) bn = g->N <= 16 ? 16 : (g->N <= 32 ? 32 : (g->N <= 64 ? 64 : 128));
   switch (bn) {
     case 16: return tpp::tc::launch<16>(g, g->split_k, s);
+    case 32: return tpp::tc::launch<32>(g, g->split_k, s);
     case 64: return tpp::tc::launch<64>(g, g->split_k, s);
     case 128: return tpp::tc::launch<128>(g, g->split_k, s);
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
