@@ -171,8 +171,10 @@ int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, in
  * This one entry serves nn.Linear forward (common/model.py:962-967), its data gradient and its weight
  * gradient (autograd of agents/ppo.py:170).  CUDA-core exact-fp32 path; the tensor-core path is below.    */
 enum { TPP_EPI_BIAS = 1, TPP_EPI_RELU = 2, TPP_EPI_MASK = 4, TPP_EPI_ACCUM = 8, TPP_EPI_ADD = 16,
-       TPP_EPI_RELU_OUT = 32 /* tpp_gemm_tc only: max(.,0) once more AFTER the addend (the ReLU behind the last
-                                residual block, common/model.py:182) */ };
+       TPP_EPI_RELU_OUT = 32, /* tpp_gemm_tc only: max(.,0) once more AFTER the addend (the ReLU behind the last
+                                 residual block, common/model.py:182) */
+       TPP_EPI_PAIR_RELU = 64 /* tpp_gemm_tc only: out_hi/out_lo receive the TF32 pair of max(result, 0) while `out`
+                                 keeps the result itself: the next convolution's ReLU'd input, common/model.py:146-150 */ };
 int tpp_gemm_f32(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk, float* C,
                  int64_t ldc, const float* bias, const float* mask, int32_t M, int32_t N, int32_t K,
                  int32_t flags, int32_t split_k, void* stream);
@@ -199,7 +201,7 @@ typedef struct {
   const float* b_hi; const float* b_lo; int64_t ldb;
   int32_t M, N, K;
   int32_t precision, split_k, flags, block_n;
-  int32_t a_mn, b_mn, _pad;
+  int32_t a_mn, b_mn, conv_wgrad;   /* conv_wgrad: see conv_C */
   const float* bias;
   const float* mask; int64_t ld_mask;
   float* out; float* out_hi; float* out_lo; int64_t ldc;
@@ -208,6 +210,16 @@ typedef struct {
   const float* addend; int64_t ld_add;   /* TPP_EPI_ADD (tpp_gemm_tc only): result += addend[m*ld_add + n], applied
                                             after bias / relu / mask: the residual connection (forward) and the
                                             skip-path gradient (backward) of ResidualBlock, common/model.py:134-153 */
+  int32_t conv_B, conv_H, conv_W, conv_C;  /* conv_C > 0: implicit 3x3 / pad-1 convolution.  a_hi/a_lo are NHWC fp32
+                                            tensors [conv_B][conv_H][conv_W][conv_C] (conv_C in 4..32, multiple of 4);
+                                            the A tiles are gathered by TMA im2col loads (no col matrix): M must be
+                                            conv_B*conv_H*conv_W, K = 288 = 9 taps x 32 channel slots, and the K-major
+                                            B operand holds W[n][tap*32 + c] (zero for c >= conv_C).  lda / a_mn unused.
+                                            nn.Conv2d(k=3, pad=1) forward and data gradient, common/model.py:137-163.
+                                            With conv_wgrad = 1 the same tensor is the MN-major A operand of the
+                                            weight gradient: out[tap*32 + c][n] += sum_p X[p + tap][c] * dY[p][n] with
+                                            M = 288, K = conv_B*conv_H*conv_W pixels, B = dY [K][ldb] MN-major
+                                            (a_mn = b_mn = 1, TPP_EPI_ACCUM, any split_k).                          */
 } tpp_tc_gemm;
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
@@ -245,7 +257,7 @@ int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t H, int32_t 
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (common/model.py:163,171): y [B][(H+1)/2][(W+1)/2][C],
  * arg = winning tap (first maximum); backward routes dy to the winning input pixel (gather form, no atomics).   */
 int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,
-                         void* stream);
+                         float* relu_hi, float* relu_lo, void* stream);  /* relu_hi/lo (nullable): TF32 pair of relu(y) */
 int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t B, int32_t H, int32_t W, int32_t C, float* dx,
                          float* dx_hi, float* dx_lo, void* stream);   /* dx_hi/dx_lo (nullable): TF32 pair of dx */
 /* out[c] += sum_m x[m*C + c] for a narrow row-major [M][C] matrix (C in 4/8/16/32/64): a convolution's bias gradient

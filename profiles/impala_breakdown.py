@@ -39,7 +39,8 @@ def main():
     def logged(name, *a):
         if name == "tpp_gemm_tc":
             g = a[0]._obj
-            labels.append(f"gemm M={g.M} N={g.N} K={g.K} mn={g.a_mn}{g.b_mn} split={g.split_k} flags={g.flags}")
+            labels.append(f"gemm M={g.M} N={g.N} K={g.K} mn={g.a_mn}{g.b_mn} split={g.split_k} flags={g.flags}"
+                          + (f" conv C={g.conv_C}" if g.conv_C else ""))
         elif name == "tpp_im2col3x3":
             labels.append(f"im2col B={a[2]} {a[3]}x{a[4]}x{a[5]} Kp={a[14]}")
         else:

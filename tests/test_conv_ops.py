@@ -177,7 +177,9 @@ def test_maxpool_forward_backward(B, H, W, C):
     Ho, Wo = (H + 1) // 2, (W + 1) // 2
     y = torch.zeros(B, Ho, Wo, C, device="cuda")
     arg = torch.zeros(B, Ho, Wo, C, dtype=torch.uint8, device="cuda")
-    L.call("tpp_maxpool3x3s2_fwd", L.ptr(x), B, H, W, C, L.ptr(y), L.ptr(arg), L.stream_ptr())
+    rh, rl = torch.zeros_like(y), torch.zeros_like(y)
+    L.call("tpp_maxpool3x3s2_fwd", L.ptr(x), B, H, W, C, L.ptr(y), L.ptr(arg), L.ptr(rh), L.ptr(rl), L.stream_ptr())
+    assert torch.equal(rh + rl, y.clamp_min(0))
     xt = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
     ref = F.max_pool2d(xt, 3, 2, 1)
     assert torch.equal(y.permute(0, 3, 1, 2), ref)
@@ -248,3 +250,101 @@ def test_impala_engine_forward_backward_vs_autograd(hw, B, A):
         worst_tc, worst_lib = max(worst_tc, e_tc), max(worst_lib, e_lib)
         assert e_tc <= max(1e-4, 3.0 * e_lib), f"{name}: rel err {e_tc:.3e} (cuDNN fp32: {e_lib:.3e})"
     print(f"gradient rel err vs float64: hand-written {worst_tc:.2e}, cuDNN fp32 {worst_lib:.2e}")
+
+
+def _probe_expected(x, cpp, pixels, w, h, n, ow, oh):
+    B, H, W, C = x.shape
+    out = torch.zeros(pixels, cpp)
+    xc = x.cpu()
+    q, p, b = w + 1, h + 1, n
+    for i in range(pixels):
+        if b < B:
+            sy, sx = p - 1 + oh, q - 1 + ow
+            if 0 <= sy < H and 0 <= sx < W:
+                out[i, :min(C, cpp)] = xc[b, sy, sx, :min(C, cpp)]
+        q += 1
+        if q == W:
+            q, p = 0, p + 1
+            if p == H:
+                p, b = 0, b + 1
+    return out
+
+
+@pytest.mark.parametrize("B,H,W,C,cpp,base,tap", [
+    (3, 8, 8, 32, 32, (-1, -1, 0), (0, 0)), (3, 8, 8, 32, 32, (-1, -1, 0), (2, 2)), (3, 8, 8, 32, 32, (2, 4, 1), (1, 1)),
+    (3, 8, 8, 32, 32, (-1, 5, 2), (1, 1)), (3, 8, 8, 16, 32, (-1, -1, 0), (1, 1)), (3, 8, 8, 4, 32, (-1, -1, 0), (2, 0)),
+    (4, 7, 5, 16, 32, (1, 2, 0), (2, 1))])
+def test_tma_im2col_conventions(B, H, W, C, cpp, base, tap):
+    """Pins what the implicit-GEMM path assumes about TMA im2col loads: bounding box corners (-1, -1), base pixel =
+    output pixel - 1, tap offsets, W -> H -> N traversal across rows and images, zero fill of padding pixels, of channel
+    slots >= C and of pixels behind the last image."""
+    L = _lib()
+    b, h, w, c = torch.meshgrid(torch.arange(B), torch.arange(H), torch.arange(W), torch.arange(C), indexing="ij")
+    x = ((b + 1) * 1000000 + h * 10000 + w * 100 + c).float().cuda().contiguous()
+    out = torch.full((128, cpp), -1.0, device="cuda")
+    L.call("tpp_debug_tma_im2col", L.ptr(x), B, H, W, C, cpp, 128, base[0], base[1], base[2], tap[0], tap[1], 0,
+           L.ptr(out), L.stream_ptr())
+    assert torch.equal(out.cpu(), _probe_expected(x, cpp, 128, *base, *tap))
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32), (5, 7, 7, 32, 32),
+                                            (2, 14, 14, 4, 16), (1, 5, 3, 16, 16), (3, 64, 64, 4, 16)])
+@pytest.mark.parametrize("precision", [3, 1])
+def test_implicit_conv3x3_matches_conv2d(B, H, W, cin, cout, precision):
+    """tpp_gemm_tc in convolution mode (A tiles gathered by TMA im2col from the NHWC TF32 pair) against F.conv2d:
+    bias + residual add fused, plain output and ReLU'd TF32 pair output."""
+    L = _lib()
+    torch.manual_seed(7)
+    x = torch.randn(B, H, W, cin, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+    bias = torch.randn(cout, device="cuda")
+    rows = B * H * W
+    skip = torch.randn(rows, cout, device="cuda")
+    wf = torch.zeros(cout, 9, 32, device="cuda")
+    wf[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    wf = wf.view(cout, 288)
+    xp, wp = _pair(x), _pair(wf)
+    out = torch.zeros(rows, cout, device="cuda")
+    oh, ol = torch.zeros_like(out), torch.zeros_like(out)
+    g = L.TcGemm()
+    g.a_hi, g.a_lo = xp[0].data_ptr(), xp[1].data_ptr()
+    g.b_hi, g.b_lo, g.ldb = wp[0].data_ptr(), wp[1].data_ptr(), 288
+    g.M, g.N, g.K, g.precision, g.split_k = rows, cout, 288, precision, 1
+    g.conv_B, g.conv_H, g.conv_W, g.conv_C = B, H, W, cin
+    g.flags = L.EPI_BIAS | L.EPI_ADD | L.EPI_PAIR_RELU
+    g.bias, g.addend, g.ld_add = bias.data_ptr(), skip.data_ptr(), cout
+    g.out, g.out_hi, g.out_lo, g.ldc = out.data_ptr(), oh.data_ptr(), ol.data_ptr(), cout
+    L.call("tpp_gemm_tc", L.C.byref(g), L.stream_ptr())
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(rows, cout) + skip.double()
+    _close(out, ref, 2e-5 if precision == 3 else 3e-3)
+    assert torch.equal(oh + ol, out.clamp_min(0))
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32), (5, 7, 7, 32, 32),
+                                            (2, 14, 14, 4, 16), (1, 5, 3, 16, 16)])
+@pytest.mark.parametrize("split", [1, 5, 64])
+def test_implicit_conv3x3_weight_gradient(B, H, W, cin, cout, split):
+    """tpp_gemm_tc in conv_wgrad mode: gw[tap*32 + ci][co] = sum_p X[p + tap][ci] dY[p][co], A blocks gathered by TMA
+    im2col (MN-major, 32 pixels per k-block; the last k-block and the last tap tile are partial)."""
+    L = _lib()
+    torch.manual_seed(8)
+    x = torch.randn(B, H, W, cin, device="cuda")
+    rows = B * H * W
+    dy = torch.randn(rows, cout, device="cuda")
+    xp, dyp = _pair(x), _pair(dy)
+    gw = torch.zeros(288, cout, device="cuda")
+    g = L.TcGemm()
+    g.a_hi, g.a_lo = xp[0].data_ptr(), xp[1].data_ptr()
+    g.b_hi, g.b_lo, g.ldb = dyp[0].data_ptr(), dyp[1].data_ptr(), cout
+    g.M, g.N, g.K, g.precision, g.split_k, g.a_mn, g.b_mn = 288, cout, rows, 3, split, 1, 1
+    g.conv_B, g.conv_H, g.conv_W, g.conv_C, g.conv_wgrad = B, H, W, cin, 1
+    g.flags, g.out, g.ldc, g.block_n = L.EPI_ACCUM, gw.data_ptr(), cout, 32
+    L.call("tpp_gemm_tc", L.C.byref(g), L.stream_ptr())
+    xd = x.double().permute(0, 3, 1, 2)
+    wd = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(xd, wd, padding=1).backward(dy.double().view(B, H, W, cout).permute(0, 3, 1, 2))
+    ref = wd.grad.permute(2, 3, 1, 0)                       # [ky][kx][ci][co]
+    got = gw.view(3, 3, 32, cout)
+    _close(got[:, :, :cin, :], ref, 1e-4)
+    assert (got[:, :, cin:, :] == 0).all()

@@ -50,14 +50,15 @@ class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
                 ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", C.c_int64),
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("precision", C.c_int32), ("split_k", C.c_int32), ("flags", C.c_int32), ("block_n", C.c_int32),
-                ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("_pad", C.c_int32),
+                ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("conv_wgrad", C.c_int32),
                 ("bias", C.c_void_p), ("mask", C.c_void_p), ("ld_mask", C.c_int64),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
-                ("colsum", C.c_void_p), ("dbg", C.c_void_p), ("addend", C.c_void_p), ("ld_add", C.c_int64)]
+                ("colsum", C.c_void_p), ("dbg", C.c_void_p), ("addend", C.c_void_p), ("ld_add", C.c_int64),
+                ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32)]
 
 
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}
-EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM, EPI_ADD, EPI_RELU_OUT = 1, 2, 4, 8, 16, 32
+EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM, EPI_ADD, EPI_RELU_OUT, EPI_PAIR_RELU = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 
@@ -88,7 +89,7 @@ SIGNATURES = {
     "tpp_debug_tma_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "tpp_colsum_narrow": [_vp, _i64, _i32, _vp, _vp],
     "tpp_bias_act_split": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
-    "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
     "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_RELU, EPI_RELU_OUT
+from .._lib import EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -235,7 +235,7 @@ class MLPEngineTC(MLPEngine):
         return ws
 
     def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
-            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0):
+            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0, conv=None, conv_wgrad=0):
         g = _lib.TcGemm()
         g.a_hi, g.a_lo, g.lda = a[0].data_ptr(), a[1].data_ptr(), lda
         g.b_hi, g.b_lo, g.ldb = b[0].data_ptr(), b[1].data_ptr(), ldb
@@ -253,6 +253,9 @@ class MLPEngineTC(MLPEngine):
             g.colsum = colsum.value
         if addend is not None:
             g.addend, g.ld_add = addend.data_ptr(), ld_add
+        if conv is not None:
+            g.conv_B, g.conv_H, g.conv_W, g.conv_C = conv
+            g.conv_wgrad = conv_wgrad
         g.ldc = ldc
         _lib.call("tpp_gemm_tc", _lib.C.byref(g), _lib.stream_ptr())
         self.n_launches += 1
@@ -342,16 +345,18 @@ class MLPEngineTC(MLPEngine):
 class ImpalaEngineTC:
     """ImpalaModel (common/model.py:81-114; reference common/model.py:134-208) + heads on this repo's kernels.
 
-    Activations are NHWC fp32 ``[B*H*W, C]`` matrices.  A 3x3 / pad-1 convolution is ``tpp_im2col3x3`` (window
-    gather that also applies the ReLU in front of residual convolutions and writes the TF32 operand pair) followed by
-    one ``tpp_gemm_tc`` with the bias, the residual add (``TPP_EPI_ADD``) and -- behind the last block -- the trailing
-    ReLU fused into the epilogue.  Backward mirrors it: the data gradient is the same two kernels applied to dY with
-    tap-flipped weights, with the ReLU mask of the convolution's input, the skip-path gradient and the bias gradient
-    of the layer below (column sums) fused into the epilogue; the weight gradient is ``dY^T col(X)`` with both
-    operands MN-major and the contraction over B*H*W split across CTAs.  Weight copies in GEMM layout
-    (``Wf[co][tap*Cin+ci]``, ``Wd[ci][tap*Cout+co]``, the fc weight with NHWC column order) are rebuilt from the flat
-    fp32 parameters by ``refresh_weights`` after every optimizer step; their gradients are accumulated in GEMM layout
-    and folded back into the flat gradient buffer at the end of ``backward``.
+    Activations are NHWC fp32 ``[B*H*W, C]`` matrices, kept both plain (ReLU masks, skip connections) and as the TF32
+    (hi, lo) pair the tensor cores read.  A 3x3 / pad-1 convolution is ONE ``tpp_gemm_tc`` launch in convolution mode:
+    the A tiles are gathered from the NHWC pair by TMA im2col loads (implicit GEMM, no col matrix), the bias, the
+    residual add (``TPP_EPI_ADD``), the ReLU in front of the next convolution (``TPP_EPI_PAIR_RELU``: the pair output
+    is ReLU'd, the plain output is not) and -- behind the last block -- the trailing ReLU are fused into the epilogue.
+    The data gradient is the same launch on the dY pair with tap-flipped weights, with the ReLU mask of the
+    convolution's input, the skip-path gradient and the bias gradient of the layer below (column sums) fused into the
+    epilogue.  The weight gradient is ``dY^T col(X)`` with both operands MN-major and the contraction over B*H*W split
+    across CTAs; its col matrix is still materialised (``tpp_im2col3x3``), as is the first convolution's (3 input
+    channels).  Weight copies in GEMM layout are rebuilt from the flat fp32 parameters by ``refresh_weights`` after
+    every optimizer step; weight gradients are accumulated in GEMM layout and folded back into the flat gradient buffer
+    at the end of ``backward``.
 
     ``x`` for ``forward`` is what ``tpp_gather_img`` / ``tpp_frames_to_obs`` produce: fp32 rows ``[M][ld]`` holding
     the frame as NCHW / 255 (the first im2col reads it through strides, nothing is transposed).
@@ -362,6 +367,7 @@ class ImpalaEngineTC:
 
     _tc = MLPEngineTC._tc
     WGRAD_CHUNK = 1024   # rows contracted per CTA before the partial sums meet in IEEE fp32 atomics
+    KI = 288             # contraction length of an implicit convolution: 9 taps x 32 channel slots
 
     def __init__(self, policy, n_actions, obs_shape, precision=3):
         assert policy.flat is not None, "call policy.flatten_() first"
@@ -381,7 +387,7 @@ class ImpalaEngineTC:
         h, w, cin = H, W, C
         for blk in (emb.block1, emb.block2, emb.block3):
             cout = blk.conv.out_channels
-            assert cout % 16 == 0 and cout <= 64, "conv widths must be 16/32/48/64 (GEMM N tile, narrow column sums)"
+            assert cout in (16, 32), "conv widths must be 16 or 32 (GEMM N tile, 32 channel slots per tap)"
             ci = self._add_conv(blk.conv, cin, cout, need_dgrad=len(self.convs) > 0)
             ho, wo = (h + 1) // 2, (w + 1) // 2
             res = [(self._add_conv(rb.conv1, cout, cout), self._add_conv(rb.conv2, cout, cout))
@@ -398,11 +404,13 @@ class ImpalaEngineTC:
         assert policy.layout["fc_value.bias"][0] == self.head_b_off + n_actions
         f = dict(dtype=torch.float32, device=self.device)
         # weight-gradient accumulators in GEMM layout: one zeroable buffer, one view per layer
-        sizes = [c["cout"] * c["Kf"] for c in self.convs] + [self.latent * self.enc]
+        # (implicit convolutions: [tap*32 + channel slot][cout]; explicit first convolution: [cout][tap*cin + ci])
+        sizes = [c["cout"] * (self.KI if c["implicit"] else c["Kf"]) for c in self.convs] + [self.latent * self.enc]
         self.gtmp = torch.zeros(sum(sizes), **f)
         o = 0
         for c, n in zip(self.convs, sizes[:-1]):
-            c["gw"] = self.gtmp[o:o + n].view(c["cout"], c["Kf"])
+            c["gw"] = self.gtmp[o:o + n].view(self.KI, c["cout"]) if c["implicit"] else \
+                self.gtmp[o:o + n].view(c["cout"], c["Kf"])
             o += n
         self.gfc = self.gtmp[o:o + sizes[-1]].view(self.latent, self.enc)
         self.wfc_plain = torch.zeros(self.latent, self.enc, **f)
@@ -423,12 +431,14 @@ class ImpalaEngineTC:
 
     def _add_conv(self, conv, cin, cout, need_dgrad=True):
         f = dict(dtype=torch.float32, device=self.device)
-        Kf, Kd = _ceil(9 * cin, 32) * 32, _ceil(9 * cout, 32) * 32
-        c = dict(w_off=self._off(conv.weight), b_off=self._off(conv.bias), cin=cin, cout=cout, Kf=Kf, Kd=Kd,
-                 wf_plain=torch.zeros(cout, Kf, **f), wf=(torch.zeros(cout, Kf, **f), torch.zeros(cout, Kf, **f)))
+        Kf = _ceil(9 * cin, 32) * 32                     # explicit col width (weight gradient; forward of conv 1)
+        implicit = cin % 4 == 0 and cin <= 32            # forward through TMA im2col
+        kw = self.KI if implicit else Kf
+        c = dict(w_off=self._off(conv.weight), b_off=self._off(conv.bias), cin=cin, cout=cout, Kf=Kf, implicit=implicit,
+                 wf_plain=torch.zeros(cout, kw, **f), wf=(torch.zeros(cout, kw, **f), torch.zeros(cout, kw, **f)))
         if need_dgrad:
-            c["wd_plain"] = torch.zeros(cin, Kd, **f)
-            c["wd"] = (torch.zeros(cin, Kd, **f), torch.zeros(cin, Kd, **f))
+            c["wd_plain"] = torch.zeros(cin, self.KI, **f)
+            c["wd"] = (torch.zeros(cin, self.KI, **f), torch.zeros(cin, self.KI, **f))
         self.convs.append(c)
         return len(self.convs) - 1
 
@@ -443,10 +453,13 @@ class ImpalaEngineTC:
         for c in self.convs:
             cin, cout = c["cin"], c["cout"]
             w = self.flat[c["w_off"]:c["w_off"] + cout * cin * 9].view(cout, cin, 3, 3)
-            c["wf_plain"][:, :9 * cin].view(cout, 3, 3, cin).copy_(w.permute(0, 2, 3, 1))
+            if c["implicit"]:    # Wf[co][tap][32 slots]
+                c["wf_plain"].view(cout, 3, 3, 32)[..., :cin].copy_(w.permute(0, 2, 3, 1))
+            else:                # Wf[co][tap*cin + ci]
+                c["wf_plain"][:, :9 * cin].view(cout, 3, 3, cin).copy_(w.permute(0, 2, 3, 1))
             self._split(c["wf_plain"], c["wf"])
-            if "wd" in c:
-                c["wd_plain"][:, :9 * cout].view(cin, 3, 3, cout).copy_(w.flip(2, 3).permute(1, 2, 3, 0))
+            if "wd" in c:        # Wd[ci][tap][32 slots] = W[co][ci][2-ky][2-kx]
+                c["wd_plain"].view(cin, 3, 3, 32)[..., :cout].copy_(w.flip(2, 3).permute(1, 2, 3, 0))
                 self._split(c["wd_plain"], c["wd"])
         wfc = self.flat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
         self.wfc_plain.view(self.latent, self.enc_hw, self.enc_c).copy_(wfc.permute(0, 2, 1))
@@ -465,23 +478,20 @@ class ImpalaEngineTC:
         def trio(n):
             return dict(plain=torch.zeros(n, **f), hi=torch.zeros(n, **f), lo=torch.zeros(n, **f))
 
-        col_a = col_b = 0
+        col = 0
         ws.blk = []
         for b in self.blocks:
             rows_in, rows = M * b["H"] * b["W"], M * b["Ho"] * b["Wo"]
             cout = b["cout"]
-            col_a = max(col_a, rows_in * self.convs[b["conv"]]["Kf"], rows * self.convs[b["res"][0][0]]["Kf"])
-            col_b = max(col_b, rows * self.convs[b["res"][0][0]]["Kd"],
-                        rows_in * self.convs[b["conv"]]["Kd"] if "wd" in self.convs[b["conv"]] else 0)
+            if not self.convs[b["conv"]]["implicit"]:
+                col = max(col, rows_in * self.convs[b["conv"]]["Kf"])
             ws.blk.append(dict(a=torch.zeros(rows_in * cout, **f),
                                arg=torch.zeros(rows * cout, dtype=torch.uint8, device=self.device),
-                               p=torch.zeros(rows * cout, **f), c1=torch.zeros(rows * cout, **f),
-                               r1=torch.zeros(rows * cout, **f), c2=torch.zeros(rows * cout, **f),
-                               r2=torch.zeros(rows * cout, **f),
+                               p=trio(rows * cout), c1=trio(rows * cout), r1=trio(rows * cout), c2=trio(rows * cout),
+                               r2=trio(rows * cout),
                                gX=trio(rows * cout), gY=trio(rows * cout), gZ=trio(rows * cout),
                                ga=trio(rows_in * cout)))
-        ws.colA = (torch.zeros(col_a, **f), torch.zeros(col_a, **f))
-        ws.colB = (torch.zeros(col_b, **f), torch.zeros(col_b, **f))
+        ws.col = (torch.zeros(max(col, 4), **f), torch.zeros(max(col, 4), **f))   # col matrix of the first convolution
         ws.h = (torch.zeros(M, self.enc, **f), torch.zeros(M, self.enc, **f))        # relu(block3), NHWC-flattened
         ws.f = (torch.zeros(M, self.latent, **f), torch.zeros(M, self.latent, **f))  # relu(fc)
         ws.last_plain = torch.zeros(M, self.latent, **f)
@@ -502,36 +512,49 @@ class ImpalaEngineTC:
     def _nhwc(H, W, C):
         return (H * W * C, W * C, C, 1)
 
-    def _conv_fwd(self, ws, ci, src, B, H, W, strides, relu, out=None, out_pair=None, addend=None, relu_out=False):
+    def _conv_fwd(self, ws, ci, src, B, H, W, out=None, addend=None, relu_out=False, pair_relu=False, pair=None,
+                  strides=None):
+        """src: TF32 pair of the (already ReLU'd) NHWC input for an implicit convolution, or -- first convolution --
+        the plain source tensor with its element strides.  out: trio (plain + pair written) or plain tensor."""
         c = self.convs[ci]
         rows = B * H * W
-        self._im2col(src, B, H, W, c["cin"], strides, relu, ws.colA, c["Kf"])
-        flags = EPI_BIAS | (EPI_ADD if addend is not None else 0) | (EPI_RELU_OUT if relu_out else 0)
-        self._tc(ws.colA, c["Kf"], c["wf"], c["Kf"], rows, c["cout"], c["Kf"], flags=flags, bias=self._p(c["b_off"]),
-                 out=out, out_pair=out_pair, ldc=c["cout"], addend=addend, ld_add=c["cout"])
+        flags = EPI_BIAS | (EPI_ADD if addend is not None else 0) | (EPI_RELU_OUT if relu_out else 0) | \
+            (EPI_PAIR_RELU if pair_relu else 0)
+        plain = out["plain"] if isinstance(out, dict) else out
+        if pair is None and isinstance(out, dict):
+            pair = (out["hi"], out["lo"])
+        kw = dict(flags=flags, bias=self._p(c["b_off"]), out=plain, out_pair=pair, ldc=c["cout"], addend=addend,
+                  ld_add=c["cout"])
+        if c["implicit"]:
+            self._tc(src, 0, c["wf"], self.KI, rows, c["cout"], self.KI, conv=(B, H, W, c["cin"]), **kw)
+        else:
+            self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
+            self._tc(ws.col, c["Kf"], c["wf"], c["Kf"], rows, c["cout"], c["Kf"], **kw)
 
     def forward(self, x, M, feature_major_ld=None, need_backward=True, train=False):
         assert feature_major_ld is None
         ws = self._workspace(M)
         C0, H0, W0 = self.obs_shape
-        src, strides = x, (x.stride(0), W0, 1, H0 * W0)
         nb = len(self.blocks)
         for k, (b, wb) in enumerate(zip(self.blocks, ws.blk)):
             H, W, Ho, Wo, cout = b["H"], b["W"], b["Ho"], b["Wo"], b["cout"]
-            self._conv_fwd(ws, b["conv"], src, M, H, W, strides, relu=False, out=wb["a"])
-            _lib.call("tpp_maxpool3x3s2_fwd", _lib.ptr(wb["a"]), M, H, W, cout, _lib.ptr(wb["p"]), _lib.ptr(wb["arg"]),
-                      _lib.stream_ptr())
-            self.n_launches += 1
-            st = self._nhwc(Ho, Wo, cout)
-            (a1, b1), (a2, b2) = b["res"]
-            self._conv_fwd(ws, a1, wb["p"], M, Ho, Wo, st, relu=True, out=wb["c1"])
-            self._conv_fwd(ws, b1, wb["c1"], M, Ho, Wo, st, relu=True, out=wb["r1"], addend=wb["p"])
-            self._conv_fwd(ws, a2, wb["r1"], M, Ho, Wo, st, relu=True, out=wb["c2"])
-            if k == nb - 1:   # trailing ReLU + flatten: written directly as the fc layer's TF32 operand
-                self._conv_fwd(ws, b2, wb["c2"], M, Ho, Wo, st, relu=True, out_pair=ws.h, addend=wb["r1"], relu_out=True)
+            if k == 0:
+                self._conv_fwd(ws, b["conv"], x, M, H, W, out=wb["a"], strides=(x.stride(0), W0, 1, H0 * W0))
             else:
-                self._conv_fwd(ws, b2, wb["c2"], M, Ho, Wo, st, relu=True, out=wb["r2"], addend=wb["r1"])
-            src, strides = wb["r2"], st
+                prev = ws.blk[k - 1]["r2"]
+                self._conv_fwd(ws, b["conv"], (prev["hi"], prev["lo"]), M, H, W, out=wb["a"])
+            p, c1, r1, c2, r2 = wb["p"], wb["c1"], wb["r1"], wb["c2"], wb["r2"]
+            _lib.call("tpp_maxpool3x3s2_fwd", _lib.ptr(wb["a"]), M, H, W, cout, _lib.ptr(p["plain"]), _lib.ptr(wb["arg"]),
+                      _lib.ptr(p["hi"]), _lib.ptr(p["lo"]), _lib.stream_ptr())
+            self.n_launches += 1
+            (a1, b1), (a2, b2) = b["res"]
+            self._conv_fwd(ws, a1, (p["hi"], p["lo"]), M, Ho, Wo, out=c1, pair_relu=True)
+            self._conv_fwd(ws, b1, (c1["hi"], c1["lo"]), M, Ho, Wo, out=r1, addend=p["plain"], pair_relu=True)
+            self._conv_fwd(ws, a2, (r1["hi"], r1["lo"]), M, Ho, Wo, out=c2, pair_relu=True)
+            if k == nb - 1:   # trailing ReLU + flatten: written directly as the fc layer's TF32 operand
+                self._conv_fwd(ws, b2, (c2["hi"], c2["lo"]), M, Ho, Wo, pair=ws.h, addend=r1["plain"], relu_out=True)
+            else:             # the next block's convolution reads r2 without a ReLU
+                self._conv_fwd(ws, b2, (c2["hi"], c2["lo"]), M, Ho, Wo, out=r2, addend=r1["plain"])
         if self.enc > 512 and self.precision == 3:
             # long contraction: chunks of 256 accumulated with IEEE adds (the tensor core truncates when it adds into
             # its fp32 accumulator), then bias + ReLU + TF32 split
@@ -552,26 +575,34 @@ class ImpalaEngineTC:
         return ws.head
 
     # ------------------------------------------------------------------------------------------
-    def _wgrad(self, ws, ci, dy, src, B, H, W, strides, relu):
-        """gw[cout][tap*cin+ci] += dY^T col(X): dY pair [rows][cout] and col [rows][Kf] both MN-major."""
+    def _wgrad(self, ws, ci, dy, src, B, H, W, strides=None):
+        """Weight gradient from the dY pair and the convolution's input.  Implicit form (src = TF32 pair of the NHWC
+        input, already ReLU'd): gw[tap*32 + ci][co] += sum_p X[p + tap][ci] dY[p][co], the A tiles gathered by TMA im2col.
+        Explicit form (first convolution, src = plain tensor + strides): gw[co][tap*cin + ci] += dY^T col(X)."""
         c = self.convs[ci]
         rows = B * H * W
-        self._im2col(src, B, H, W, c["cin"], strides, relu, ws.colA, c["Kf"])
+        chunks = _ceil(rows, self.WGRAD_CHUNK)
+        if c["implicit"]:
+            self._tc(src, 0, (dy["hi"], dy["lo"]), c["cout"], self.KI, c["cout"], rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
+                     out=c["gw"], ldc=c["cout"], block_n=32, conv=(B, H, W, c["cin"]), conv_wgrad=1,
+                     split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, 3), chunks))))
+            return
+        self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
         n = 9 * c["cin"]
         bn = 256 if n > 128 else 128
         tiles = _ceil(n, bn)
-        self._tc((dy["hi"], dy["lo"]), c["cout"], ws.colA, c["Kf"], c["cout"], n, rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
+        self._tc((dy["hi"], dy["lo"]), c["cout"], ws.col, c["Kf"], c["cout"], n, rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
                  out=c["gw"], ldc=c["Kf"], block_n=bn,
-                 split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, tiles), _ceil(rows, self.WGRAD_CHUNK)))))
+                 split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, tiles), chunks))))
 
     def _dgrad(self, ws, ci, dy, B, H, W, out, mask=None, addend=None, colsum_off=None):
-        """dX = col(dY) Wd^T (* relu mask of the conv input) (+ skip gradient); column sums -> bias grad below."""
+        """dX = conv(dY, flipped W) (* relu mask of the conv input) (+ skip gradient); column sums -> bias grad below."""
         c = self.convs[ci]
         rows = B * H * W
-        self._im2col(dy["plain"], B, H, W, c["cout"], self._nhwc(H, W, c["cout"]), False, ws.colB, c["Kd"])
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ADD if addend is not None else 0)
-        self._tc(ws.colB, c["Kd"], c["wd"], c["Kd"], rows, c["cin"], c["Kd"], flags=flags, mask=mask, ld_mask=c["cin"],
-                 out=out["plain"], out_pair=(out["hi"], out["lo"]), ldc=c["cin"], addend=addend, ld_add=c["cin"],
+        self._tc((dy["hi"], dy["lo"]), 0, c["wd"], self.KI, rows, c["cin"], self.KI, conv=(B, H, W, c["cout"]),
+                 flags=flags, mask=mask, ld_mask=c["cin"], out=out["plain"], out_pair=(out["hi"], out["lo"]),
+                 ldc=c["cin"], addend=addend, ld_add=c["cin"],
                  colsum=self._g(colsum_off) if colsum_off is not None else None)
 
     def _colsum(self, x, rows, C, off):
@@ -585,6 +616,10 @@ class ImpalaEngineTC:
         H, nh = self.latent, self.A + 1
         assert H in (16, 32, 64, 128, 256) and nh <= 16
         self.gtmp.zero_()
+
+        def pair(t):
+            return (t["hi"], t["lo"])
+
         _lib.call("tpp_head_backward", _lib.ptr(dhead), self.ld_head, _lib.ptr(ws.last_plain), _lib.ptr(ws.f[0]), H,
                   self._p(self.head_w_off), nh, H, _lib.ptr(ws.dz[0]), _lib.ptr(ws.dz[1]), None, H,
                   self._g(self.head_w_off), self._g(self.head_b_off), self._g(self.fc_b_off), M, s)
@@ -593,8 +628,7 @@ class ImpalaEngineTC:
         tiles = _ceil(H, 128) * _ceil(self.enc, 128)
         self._tc(ws.dz, H, ws.h, self.enc, H, self.enc, M, a_mn=1, b_mn=1, flags=EPI_ACCUM, out=self.gfc, ldc=self.enc,
                  split_k=max(1, min(_ceil(M, 32), max(_ceil(148, tiles), _ceil(M, 512)))), block_n=128)
-        last = ws.blk[-1]
-        d = last["gX"]
+        d = ws.blk[-1]["gX"]
         self._tc(ws.dz, H, self.wfc, self.enc, M, self.enc, H, b_mn=1, flags=EPI_MASK, mask=ws.h[0], ld_mask=self.enc,
                  out=d["plain"], out_pair=(d["hi"], d["lo"]), ldc=self.enc)
         for k in range(len(self.blocks) - 1, -1, -1):
@@ -604,18 +638,19 @@ class ImpalaEngineTC:
             st = self._nhwc(Ho, Wo, cout)
             (a1, b1), (a2, b2) = b["res"]
             X, Y, Z = wb["gX"], wb["gY"], wb["gZ"]
+            p, c1, r1, c2 = wb["p"]["plain"], wb["c1"]["plain"], wb["r1"]["plain"], wb["c2"]["plain"]
             if k == len(self.blocks) - 1:
                 self._colsum(X["plain"], rows, cout, self.convs[b2]["b_off"])
             # res2: r2 = conv_b2(relu(c2)) + r1 ; c2 = conv_a2(relu(r1))
-            self._wgrad(ws, b2, X, wb["c2"], M, Ho, Wo, st, True)
-            self._dgrad(ws, b2, X, M, Ho, Wo, Y, mask=wb["c2"], colsum_off=self.convs[a2]["b_off"])
-            self._wgrad(ws, a2, Y, wb["r1"], M, Ho, Wo, st, True)
-            self._dgrad(ws, a2, Y, M, Ho, Wo, Z, mask=wb["r1"], addend=X["plain"], colsum_off=self.convs[b1]["b_off"])
+            self._wgrad(ws, b2, X, pair(wb["c2"]), M, Ho, Wo)
+            self._dgrad(ws, b2, X, M, Ho, Wo, Y, mask=c2, colsum_off=self.convs[a2]["b_off"])
+            self._wgrad(ws, a2, Y, pair(wb["r1"]), M, Ho, Wo)
+            self._dgrad(ws, a2, Y, M, Ho, Wo, Z, mask=r1, addend=X["plain"], colsum_off=self.convs[b1]["b_off"])
             # res1: r1 = conv_b1(relu(c1)) + p ; c1 = conv_a1(relu(p))
-            self._wgrad(ws, b1, Z, wb["c1"], M, Ho, Wo, st, True)
-            self._dgrad(ws, b1, Z, M, Ho, Wo, Y, mask=wb["c1"], colsum_off=self.convs[a1]["b_off"])
-            self._wgrad(ws, a1, Y, wb["p"], M, Ho, Wo, st, True)
-            self._dgrad(ws, a1, Y, M, Ho, Wo, X, mask=wb["p"], addend=Z["plain"])
+            self._wgrad(ws, b1, Z, pair(wb["c1"]), M, Ho, Wo)
+            self._dgrad(ws, b1, Z, M, Ho, Wo, Y, mask=c1, colsum_off=self.convs[a1]["b_off"])
+            self._wgrad(ws, a1, Y, pair(wb["p"]), M, Ho, Wo)
+            self._dgrad(ws, a1, Y, M, Ho, Wo, X, mask=p, addend=Z["plain"])
             # max-pool, then the block's first convolution
             ga = wb["ga"]
             _lib.call("tpp_maxpool3x3s2_bwd", _lib.ptr(X["plain"]), _lib.ptr(wb["arg"]), M, Hh, Ww, cout,
@@ -624,16 +659,19 @@ class ImpalaEngineTC:
             self._colsum(ga["plain"], M * Hh * Ww, cout, self.convs[b["conv"]]["b_off"])
             if k == 0:
                 C0, H0, W0 = self.obs_shape
-                self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, (self._x.stride(0), W0, 1, H0 * W0), False)
+                self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, strides=(self._x.stride(0), W0, 1, H0 * W0))
             else:
                 prev = ws.blk[k - 1]
-                self._wgrad(ws, b["conv"], ga, prev["r2"], M, Hh, Ww, self._nhwc(Hh, Ww, b["cin"]), False)
+                self._wgrad(ws, b["conv"], ga, pair(prev["r2"]), M, Hh, Ww)
                 self._dgrad(ws, b["conv"], ga, M, Hh, Ww, prev["gX"],
                             colsum_off=self.convs[self.blocks[k - 1]["res"][1][1]]["b_off"])
         # fold the GEMM-layout weight gradients back into the flat gradient buffer
         for c in self.convs:
             cin, cout = c["cin"], c["cout"]
             g = self.gflat[c["w_off"]:c["w_off"] + cout * cin * 9].view(cout, cin, 3, 3)
-            g += c["gw"][:, :9 * cin].view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+            if c["implicit"]:
+                g += c["gw"].view(3, 3, 32, cout)[:, :, :cin, :].permute(3, 2, 0, 1)
+            else:
+                g += c["gw"][:, :9 * cin].view(cout, 3, 3, cin).permute(0, 3, 1, 2)
         g = self.gflat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
         g += self.gfc.view(self.latent, self.enc_hw, self.enc_c).permute(0, 2, 1)

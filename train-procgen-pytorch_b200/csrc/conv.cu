@@ -46,7 +46,47 @@ __global__ void __launch_bounds__(256) im2col3x3_vec_kernel(const float* __restr
   if (lo) *reinterpret_cast<float4*>(lo + p * Kp + k) = make_float4(a[0] - h[0], a[1] - h[1], a[2] - h[2], a[3] - h[3]);
 }
 
-// Generic layout (uint8 frames, NCHW rows, C = 3): one thread per col element, k fastest -> coalesced stores.
+// Few input channels (9C <= 32 = Kp: the first convolution reading NCHW observation rows or uint8 frames): a warp
+// owns 32 consecutive pixels; lane = pixel while reading (consecutive x: coalesced for NCHW planes), lane = k while
+// writing (one 128-byte col row per instruction), transposed through a per-warp shared-memory tile.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col3x3_small_kernel(const TIn* __restrict__ x, int B, int H, int W, int C,
+                                                              long long sb, long long sy_, long long sx_, long long sc,
+                                                              int relu, float scale, float* __restrict__ hi,
+                                                              float* __restrict__ lo) {
+  __shared__ float tile[8][32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long M = (long long)B * H * W;
+  const long long p0 = ((long long)blockIdx.x * 8 + w) * 32;
+  if (p0 >= M) return;
+  const long long p = p0 + lane;
+  const bool live = p < M;
+  const int xx = (int)(p % W), yy = (int)((p / W) % H);
+  const long long b = p / ((long long)W * H);
+  const TIn* base = x + b * sb;
+  int k = 0;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    const bool inside = live && sy >= 0 && sy < H && sx >= 0 && sx < W;
+    const TIn* src = base + sy * sy_ + sx * sx_;
+    for (int c = 0; c < C; ++c, ++k) {
+      float q = inside ? (float)src[c * sc] * scale : 0.0f;
+      if (relu) q = fmaxf(q, 0.0f);
+      tile[w][lane][k] = q;
+    }
+  }
+  for (; k < 32; ++k) tile[w][lane][k] = 0.0f;
+  __syncwarp();
+  const int n = (int)(M - p0 < 32 ? M - p0 : 32);
+  for (int i = 0; i < n; ++i) {
+    const float q = tile[w][i][lane];
+    const float h = cv_tf32(q);
+    hi[(p0 + i) * 32 + lane] = h;
+    if (lo) lo[(p0 + i) * 32 + lane] = q - h;
+  }
+}
+
+// Generic layout: one thread per col element, k fastest -> coalesced stores.
 template <typename TIn>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const TIn* __restrict__ x, int B, int H, int W, int C,
                                                         long long sb, long long sy_, long long sx_, long long sc,
@@ -73,7 +113,8 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const TIn* __restrict__ 
 
 // NHWC max-pool 3x3, stride 2, pad 1: y [B, Ho, Wo, C], arg = winning tap 0..8 (first maximum, like torch).
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
-                                                          float* __restrict__ y, uint8_t* __restrict__ arg, int Ho,
+                                                          float* __restrict__ y, uint8_t* __restrict__ arg,
+                                                          float* __restrict__ r_hi, float* __restrict__ r_lo, int Ho,
                                                           int Wo) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * Ho * Wo * C;
@@ -93,38 +134,54 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
   }
   y[t] = best;
   arg[t] = (uint8_t)bi;
+  if (r_hi) {   // TF32 pair of relu(y): the operand of the residual block's first convolution
+    const float q = fmaxf(best, 0.0f), h = cv_tf32(q);
+    r_hi[t] = h;
+    r_lo[t] = q - h;
+  }
 }
 
 // dx[b, y, x, c] = sum over the (<= 4) pooling windows that contain (y, x) and whose argmax is this pixel.
+// One thread per pixel and 4 channels (C % 4 == 0): float4 / uchar4 accesses.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg,
                                                           int B, int H, int W, int C, int Ho, int Wo,
                                                           float* __restrict__ dx, float* __restrict__ dx_hi,
                                                           float* __restrict__ dx_lo) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * H * W * C;
+  const int cq = C >> 2;
+  const long long total = (long long)B * H * W * cq;
   if (t >= total) return;
-  const int c = (int)(t % C);
-  const int xx = (int)((t / C) % W), yy = (int)((t / ((long long)C * W)) % H);
-  const long long b = t / ((long long)C * W * H);
-  float s = 0.0f;
+  const int c = (int)(t % cq) * 4;
+  const int xx = (int)((t / cq) % W), yy = (int)((t / ((long long)cq * W)) % H);
+  const long long b = t / ((long long)cq * W * H);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   // windows (oy, ox) with oy*2 - 1 <= yy <= oy*2 + 1
-  for (int oy = (yy) / 2; oy <= (yy + 1) / 2; ++oy) {
-    if (oy < 0 || oy >= Ho) continue;
+  for (int oy = yy / 2; oy <= (yy + 1) / 2; ++oy) {
+    if (oy >= Ho) continue;
     const int ky = yy - (oy * 2 - 1);
-    if (ky < 0 || ky > 2) continue;
-    for (int ox = (xx) / 2; ox <= (xx + 1) / 2; ++ox) {
-      if (ox < 0 || ox >= Wo) continue;
+    for (int ox = xx / 2; ox <= (xx + 1) / 2; ++ox) {
+      if (ox >= Wo) continue;
       const int kx = xx - (ox * 2 - 1);
-      if (kx < 0 || kx > 2) continue;
       const long long o = ((b * Ho + oy) * Wo + ox) * C + c;
-      if (arg[o] == ky * 3 + kx) s += dy[o];
+      const uchar4 a = *reinterpret_cast<const uchar4*>(arg + o);
+      const int want = ky * 3 + kx;
+      if (a.x == want || a.y == want || a.z == want || a.w == want) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o));
+        if (a.x == want) s[0] += g.x;
+        if (a.y == want) s[1] += g.y;
+        if (a.z == want) s[2] += g.z;
+        if (a.w == want) s[3] += g.w;
+      }
     }
   }
-  dx[t] = s;
+  const long long o = t * 4;
+  *reinterpret_cast<float4*>(dx + o) = make_float4(s[0], s[1], s[2], s[3]);
   if (dx_hi) {
-    const float h = cv_tf32(s);
-    dx_hi[t] = h;
-    dx_lo[t] = s - h;
+    float h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = cv_tf32(s[j]);
+    *reinterpret_cast<float4*>(dx_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(dx_lo + o) = make_float4(s[0] - h[0], s[1] - h[1], s[2] - h[2], s[3] - h[3]);
   }
 }
 
@@ -191,7 +248,15 @@ extern "C" int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t 
   TPP_CHECK_ARG((reinterpret_cast<uintptr_t>(col_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(col_lo) & 15) == 0);
   const long long rows = (long long)B * H * W;
   cudaStream_t s = tpp_stream(stream);
-  if (x_is_u8) {
+  if (Kp == 32 && 9 * C <= 32) {
+    const int grid = tpp_ceil_div(rows, 256);
+    if (x_is_u8)
+      tpp::im2col3x3_small_kernel<uint8_t><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(x), B, H, W, C, sb, sy,
+                                                               sx, sc, relu, scale, col_hi, col_lo);
+    else
+      tpp::im2col3x3_small_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(x), B, H, W, C, sb, sy, sx,
+                                                             sc, relu, scale, col_hi, col_lo);
+  } else if (x_is_u8) {
     tpp::im2col3x3_kernel<uint8_t><<<tpp_ceil_div(rows * Kp, 256), 256, 0, s>>>(
         reinterpret_cast<const uint8_t*>(x), B, H, W, C, sb, sy, sx, sc, relu, scale, col_hi, col_lo, Kp);
   } else if ((C & 3) == 0 && sc == 1 && ((sb | sy | sx) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
@@ -205,19 +270,21 @@ extern "C" int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t 
 }
 
 extern "C" int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,
-                                    void* stream) {
-  TPP_CHECK_ARG(x && y && arg && B > 0 && H > 0 && W > 0 && C > 0);
+                                    float* relu_hi, float* relu_lo, void* stream) {
+  TPP_CHECK_ARG(x && y && arg && B > 0 && H > 0 && W > 0 && C > 0 && ((relu_hi == nullptr) == (relu_lo == nullptr)));
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)B * Ho * Wo * C;
-  tpp::maxpool_fwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(x, B, H, W, C, y, arg, Ho, Wo);
+  tpp::maxpool_fwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(x, B, H, W, C, y, arg, relu_hi,
+                                                                                    relu_lo, Ho, Wo);
   TPP_LAUNCH_STATUS();
 }
 
 extern "C" int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t B, int32_t H, int32_t W, int32_t C,
                                     float* dx, float* dx_hi, float* dx_lo, void* stream) {
-  TPP_CHECK_ARG(dy && arg && dx && B > 0 && H > 0 && W > 0 && C > 0 && ((dx_hi == nullptr) == (dx_lo == nullptr)));
+  TPP_CHECK_ARG(dy && arg && dx && B > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0);
+  TPP_CHECK_ARG((dx_hi == nullptr) == (dx_lo == nullptr));
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = (long long)B * H * W * C;
+  const long long total = (long long)B * H * W * (C / 4);
   tpp::maxpool_bwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(dy, arg, B, H, W, C, Ho, Wo, dx,
                                                                                     dx_hi, dx_lo);
   TPP_LAUNCH_STATUS();

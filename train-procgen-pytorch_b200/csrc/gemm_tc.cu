@@ -56,10 +56,15 @@ struct Params {
   int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
   long long* dbg;              // optional timeline probe (block 0 only): clock64 at 8 milestones
   int ntn;                     // number of N tiles (grid.x = ntn * number of M tiles)
+  int tx_bytes;                // bytes one stage receives (narrow MN-major operands use smaller TMA boxes)
+  int a_slot, b_slot;          // bytes of one A / B operand copy inside a stage
+  int b_tx;                    // bytes one B box delivers
+  int conv_W, conv_HW;         // implicit 3x3 convolution: A tiles come from TMA im2col loads of an NHWC tensor (0 = off)
+  int conv_wgrad;              // 1: weight-gradient form, A = im2col(X) MN-major (rows = (tap, channel slot), k = pixels)
   const float* addend; long long ld_add;   // optional residual: result += addend[m][n] (after bias / relu / mask)
 };
 
-enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT = 32 };
+enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT = 32, F_PAIR_RELU = 64 };
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -99,6 +104,17 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// im2col-mode TMA (NHWC tensor, 3x3 / pad-1 bounding box): BLOCK_M consecutive output pixels starting at base pixel
+// (w, h, n) [bounding-box coordinates = output pixel - 1], shifted by the filter tap (off_w, off_h); 32 channel slots
+// per pixel (channels beyond C, padding pixels and pixels behind the last image are zero-filled by the TMA unit).
+__device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, uint64_t* bar, void* dst, int w, int h, int n,
+                                                int off_w, int off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -187,7 +203,6 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), a_major bit 15,
   // b_major bit 16 (1 = MN-major), N>>3 at bit 17, M>>4 at bit 24
@@ -202,6 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int nops = p.npass == 3 ? 2 : 1;
+  const int A_BYTES = p.a_slot, B_BYTES = p.b_slot;
   const int stage_bytes = (A_BYTES + B_BYTES) * nops;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -239,23 +255,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      int cw = 0, ch = 0, cn = 0;
+      if (p.conv_W && !p.conv_wgrad) {   // base pixel of this tile in bounding-box coordinates
+        cn = m0 / p.conv_HW;
+        const int r = m0 - cn * p.conv_HW;
+        ch = r / p.conv_W - 1;
+        cw = r % p.conv_W - 1;
+      }
+      // weight-gradient form: this M tile covers filter taps tap0 .. tap0 + ntaps - 1 (32 channel slots each)
+      const int tap0 = (m0 / BLOCK_M) * (BLOCK_M / 32);
+      const int ntaps = min(BLOCK_M / 32, 9 - tap0);
+      const uint32_t tx = p.conv_wgrad ? (uint32_t)((ntaps * 4096 + p.b_tx) * nops) : (uint32_t)p.tx_bytes;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (kb / p.stages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         if (kb == 0) TPP_PROBE(2);
-        mbar_expect_tx(full_bar + s, (uint32_t)stage_bytes);
+        mbar_expect_tx(full_bar + s, tx);
         uint8_t* st = smem + s * stage_bytes;
         const int kc = (kb0 + kb) * BLOCK_K;
-        // K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n}
-        if (p.a_mn) tma_load_3d(&tmA_hi, full_bar + s, st, 0, kc, m0 >> 5); else tma_load_2d(&tmA_hi, full_bar + s, st, kc, m0);
-        if (p.b_mn) tma_load_3d(&tmB_hi, full_bar + s, st + A_BYTES * nops, 0, kc, n0 >> 5);
-        else tma_load_2d(&tmB_hi, full_bar + s, st + A_BYTES * nops, kc, n0);
-        if (nops == 2) {
-          if (p.a_mn) tma_load_3d(&tmA_lo, full_bar + s, st + A_BYTES, 0, kc, m0 >> 5);
-          else tma_load_2d(&tmA_lo, full_bar + s, st + A_BYTES, kc, m0);
-          if (p.b_mn) tma_load_3d(&tmB_lo, full_bar + s, st + A_BYTES * 2 + B_BYTES, 0, kc, n0 >> 5);
-          else tma_load_2d(&tmB_lo, full_bar + s, st + A_BYTES * 2 + B_BYTES, kc, n0);
+        // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
+        // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
+        // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
+        for (int o = 0; o < nops; ++o) {
+          const CUtensorMap* tmA = o ? &tmA_lo : &tmA_hi;
+          uint8_t* dst = st + o * A_BYTES;
+          if (p.conv_wgrad) {
+            const int n = kc / p.conv_HW, r = kc - n * p.conv_HW;
+            const int h = r / p.conv_W - 1, w = r % p.conv_W - 1;
+            for (int j = 0; j < ntaps; ++j)
+              tma_load_im2col(tmA, full_bar + s, dst + j * 4096, w, h, n, (tap0 + j) % 3, (tap0 + j) / 3);
+          } else if (p.conv_W) {
+            const int tap = kb0 + kb;
+            tma_load_im2col(tmA, full_bar + s, dst, cw, ch, cn, tap % 3, tap / 3);
+          } else if (p.a_mn) {
+            tma_load_3d(tmA, full_bar + s, dst, 0, kc, m0 >> 5);
+          } else {
+            tma_load_2d(tmA, full_bar + s, dst, kc, m0);
+          }
+          const CUtensorMap* tmB = o ? &tmB_lo : &tmB_hi;
+          uint8_t* dstb = st + A_BYTES * nops + o * B_BYTES;
+          if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
+          else tma_load_2d(tmB, full_bar + s, dstb, kc, n0);
         }
       }
     }
@@ -353,6 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const long long astep = 4 * p.ld_add;
           const float floor_v = (p.flags & F_RELU) ? 0.0f : -3.402823466e38f;
           const float floor_out = (p.flags & F_RELU_OUT) ? 0.0f : -3.402823466e38f;
+          const float floor_pair = (p.flags & F_PAIR_RELU) ? 0.0f : -3.402823466e38f;   // pair = relu(plain)
           const float* sp = stg + rr * STG_PITCH + cc;
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
@@ -378,6 +420,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 4; ++j) cs4[j] += x[j];
             if (po) { *reinterpret_cast<float4*>(po) = make_float4(x[0], x[1], x[2], x[3]); po += ostep; }
             if (ph) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_pair);
               const float h0 = tf32_round(x[0]), h1 = tf32_round(x[1]), h2 = tf32_round(x[2]), h3 = tf32_round(x[3]);
               *reinterpret_cast<float4*>(ph) = make_float4(h0, h1, h2, h3);
               *reinterpret_cast<float4*>(pl) = make_float4(x[0] - h0, x[1] - h1, x[2] - h2, x[3] - h3);
@@ -446,8 +490,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          h[j] = tf32_round(x[j]);
-          l[j] = x[j] - h[j];
+          const float y = (p.flags & F_PAIR_RELU) ? fmaxf(x[j], 0.0f) : x[j];
+          h[j] = tf32_round(y);
+          l[j] = y - h[j];
         }
         float* outs[3] = {p.out, p.out_hi, p.out_lo};
         const float* src[3] = {x, h, l};
@@ -546,7 +591,10 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, int K, int box_rows, int mn_major) {
+// *box_bytes: bytes one box delivers.  A narrow MN-major operand (fewer 32-wide blocks than the tile has) gets a
+// smaller box: the blocks it does not fill only feed accumulator rows / columns that are never stored.
+static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, int K, int box_rows, int mn_major,
+                    int* box_bytes) {
   if (!base) return TPP_EINVAL;
   EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled();
   if (!cuTensorMapEncodeTiled) return TPP_ENOTSUP;
@@ -557,6 +605,7 @@ static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, 
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    *box_bytes = BLOCK_K * box_rows * 4;
     r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -568,7 +617,9 @@ static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, 
     if (ld < blocks * 32 && blocks != 1) return TPP_EINVAL;
     cuuint64_t gdim[3] = {(cuuint64_t)(ld < 32 ? ld : 32), (cuuint64_t)K, (cuuint64_t)blocks};
     cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, 128};
-    cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)(box_rows / 32)};
+    const long long box_blocks = blocks < box_rows / 32 ? blocks : box_rows / 32;
+    cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)box_blocks};
+    *box_bytes = (int)(box_blocks * 32 * BLOCK_K * 4);
     r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -576,16 +627,64 @@ static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, 
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static EncodeIm2colFn encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  }
+  return fn;
+}
+
+// NHWC fp32 tensor [B][H][W][C] as the A operand of a 3x3 / pad-1 convolution: box = BLOCK_M pixels x 32 channel slots
+// (one 128-byte swizzled row per pixel, the same shared-memory tile as the K-major tiled map), conventions pinned by
+// tests/test_conv_ops.py::test_tma_im2col_conventions.
+static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int W, int C, int wgrad) {
+  if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || (C & 3) || C > 32) return TPP_EINVAL;
+  EncodeIm2colFn enc = encode_im2col();
+  if (!enc) return TPP_ENOTSUP;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  int lower[2] = {-1, -1}, upper[2] = {-1, -1};   // -pad ; pad - (3 - 1)
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // forward / data gradient: K-major A tile, 128 pixels x 128-byte rows; weight gradient: MN-major A blocks of
+  // 32 pixels (k rows) x 32 channel slots in the 32-byte-atom swizzle (the only legal MN-major fp32 layout)
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, lower, upper, 32,
+                   wgrad ? BLOCK_K : BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   wgrad ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
+}
+
 template <int BLOCK_N>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const int npass = g->precision == 3 ? 3 : 1;
-  int rc;
-  if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn))) return rc;
-  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn))) return rc;
+  int rc, a_bytes = A_BYTES, b_bytes = BLOCK_N * BLOCK_K * 4;
+  const bool conv = g->conv_C > 0;
+  const int wgrad = conv && g->conv_wgrad;
+  if (conv) {
+    const long long pixels = (long long)g->conv_B * g->conv_H * g->conv_W;
+    if (wgrad) {
+      if (!g->a_mn || !g->b_mn || g->M != 9 * 32 || pixels != g->K || !(g->flags & F_ATOMIC)) return TPP_EINVAL;
+    } else if (g->a_mn || g->K != 9 * BLOCK_K || pixels != g->M) {
+      return TPP_EINVAL;
+    }
+    if ((rc = make_map_im2col(&tmA_hi, g->a_hi, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad))) return rc;
+    if (npass == 3 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad)))
+      return rc;
+  } else if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
+  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes))) return rc;
   if (npass == 3) {
-    if ((rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn))) return rc;
-    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn))) return rc;
+    if (!conv && (rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
+    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes))) return rc;
   } else {
     tmA_lo = tmA_hi;
     tmB_lo = tmB_hi;
@@ -594,6 +693,9 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.M = g->M; p.N = g->N; p.K = g->K; p.npass = npass; p.flags = g->flags;
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
   p.addend = g->addend; p.ld_add = g->ld_add;
+  p.tx_bytes = (a_bytes + b_bytes) * (npass == 3 ? 2 : 1);
+  p.conv_W = conv ? g->conv_W : 0; p.conv_HW = conv ? g->conv_H * g->conv_W : 0;
+  p.conv_wgrad = wgrad; p.b_tx = b_bytes;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
   p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(g->dbg);
@@ -602,13 +704,17 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
   split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  const int stage_bytes = (A_BYTES + BLOCK_N * BLOCK_K * 4) * (npass == 3 ? 2 : 1);
+  // slots keep the full tile size: the MMA reads all BLOCK_M x BLOCK_N operand rows, also the ones a smaller TMA box
+  // left unfilled (their products land in accumulator rows / columns that are never stored)
+  p.a_slot = A_BYTES;
+  p.b_slot = BLOCK_N * BLOCK_K * 4;
+  const int stage_bytes = (p.a_slot + p.b_slot) * (npass == 3 ? 2 : 1);
   int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
-  if (stages > 4) stages = 4;
+  if (stages > 8) stages = 8;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
   // per SM so that one tile's epilogue / prologue overlaps another tile's loads
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
-  if (n_tiles >= 4 * 148 && stages > 2 && p.kb_per_split <= 16) stages = 2;
+  if (n_tiles >= 4 * 148 && stages > 2 && (p.kb_per_split <= 16 || BLOCK_N <= 32)) stages = 2;
   if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
   // the epilogue's transpose patches alias the pipeline stages: the region must hold at least STG_BYTES
