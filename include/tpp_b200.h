@@ -215,6 +215,8 @@ typedef struct {
                                             the A tiles are gathered by TMA im2col loads (no col matrix): M must be
                                             conv_B*conv_H*conv_W, K = 288 = 9 taps x 32 channel slots, and the K-major
                                             B operand holds W[n][tap*32 + c] (zero for c >= conv_C).  lda / a_mn unused.
+                                            conv_C <= 16 may instead pass K = 144 = 9 taps x 16 slots with
+                                            W[n][tap*16 + c]: 64-byte rows, half the shared-memory fill.
                                             nn.Conv2d(k=3, pad=1) forward and data gradient, common/model.py:137-163.
                                             With conv_wgrad = 1 the same tensor is the MN-major A operand of the
                                             weight gradient: out[tap*32 + c][n] += sum_p X[p + tap][c] * dY[p][n] with

@@ -289,8 +289,8 @@ def test_tma_im2col_conventions(B, H, W, C, cpp, base, tap):
 
 @pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32), (5, 7, 7, 32, 32),
                                             (2, 14, 14, 4, 16), (1, 5, 3, 16, 16), (3, 64, 64, 4, 16)])
-@pytest.mark.parametrize("precision", [3, 1])
-def test_implicit_conv3x3_matches_conv2d(B, H, W, cin, cout, precision):
+@pytest.mark.parametrize("precision,slots", [(3, 32), (1, 32), (3, 16)])
+def test_implicit_conv3x3_matches_conv2d(B, H, W, cin, cout, precision, slots):
     """tpp_gemm_tc in convolution mode (A tiles gathered by TMA im2col from the NHWC TF32 pair) against F.conv2d:
     bias + residual add fused, plain output and ReLU'd TF32 pair output."""
     L = _lib()
@@ -300,16 +300,19 @@ def test_implicit_conv3x3_matches_conv2d(B, H, W, cin, cout, precision):
     bias = torch.randn(cout, device="cuda")
     rows = B * H * W
     skip = torch.randn(rows, cout, device="cuda")
-    wf = torch.zeros(cout, 9, 32, device="cuda")
+    if slots < cin:
+        pytest.skip("16 channel slots per tap need cin <= 16")
+    K = 9 * slots
+    wf = torch.zeros(cout, 9, slots, device="cuda")
     wf[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, 9, cin)
-    wf = wf.view(cout, 288)
+    wf = wf.view(cout, K)
     xp, wp = _pair(x), _pair(wf)
     out = torch.zeros(rows, cout, device="cuda")
     oh, ol = torch.zeros_like(out), torch.zeros_like(out)
     g = L.TcGemm()
     g.a_hi, g.a_lo = xp[0].data_ptr(), xp[1].data_ptr()
-    g.b_hi, g.b_lo, g.ldb = wp[0].data_ptr(), wp[1].data_ptr(), 288
-    g.M, g.N, g.K, g.precision, g.split_k = rows, cout, 288, precision, 1
+    g.b_hi, g.b_lo, g.ldb = wp[0].data_ptr(), wp[1].data_ptr(), K
+    g.M, g.N, g.K, g.precision, g.split_k = rows, cout, K, precision, 1
     g.conv_B, g.conv_H, g.conv_W, g.conv_C = B, H, W, cin
     g.flags = L.EPI_BIAS | L.EPI_ADD | L.EPI_PAIR_RELU
     g.bias, g.addend, g.ld_add = bias.data_ptr(), skip.data_ptr(), cout

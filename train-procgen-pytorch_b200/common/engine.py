@@ -404,13 +404,12 @@ class ImpalaEngineTC:
         assert policy.layout["fc_value.bias"][0] == self.head_b_off + n_actions
         f = dict(dtype=torch.float32, device=self.device)
         # weight-gradient accumulators in GEMM layout: one zeroable buffer, one view per layer
-        # (implicit convolutions: [tap*32 + channel slot][cout]; explicit first convolution: [cout][tap*cin + ci])
+        # (implicit convolutions: [tap*32 + channel slot][cout]; explicit first convolution: [tap*cin + ci][cout])
         sizes = [c["cout"] * (self.KI if c["implicit"] else c["Kf"]) for c in self.convs] + [self.latent * self.enc]
         self.gtmp = torch.zeros(sum(sizes), **f)
         o = 0
         for c, n in zip(self.convs, sizes[:-1]):
-            c["gw"] = self.gtmp[o:o + n].view(self.KI, c["cout"]) if c["implicit"] else \
-                self.gtmp[o:o + n].view(c["cout"], c["Kf"])
+            c["gw"] = self.gtmp[o:o + n].view(self.KI if c["implicit"] else c["Kf"], c["cout"])
             o += n
         self.gfc = self.gtmp[o:o + sizes[-1]].view(self.latent, self.enc)
         self.wfc_plain = torch.zeros(self.latent, self.enc, **f)
@@ -433,12 +432,15 @@ class ImpalaEngineTC:
         f = dict(dtype=torch.float32, device=self.device)
         Kf = _ceil(9 * cin, 32) * 32                     # explicit col width (weight gradient; forward of conv 1)
         implicit = cin % 4 == 0 and cin <= 32            # forward through TMA im2col
-        kw = self.KI if implicit else Kf
+        # channel slots per tap of the implicit forms: 16 (64-byte rows) when the gathered tensor has <= 16 channels
+        sf, sd = (16 if cin <= 16 else 32), (16 if cout <= 16 else 32)
+        kw = 9 * sf if implicit else Kf
         c = dict(w_off=self._off(conv.weight), b_off=self._off(conv.bias), cin=cin, cout=cout, Kf=Kf, implicit=implicit,
+                 sf=sf, sd=sd,
                  wf_plain=torch.zeros(cout, kw, **f), wf=(torch.zeros(cout, kw, **f), torch.zeros(cout, kw, **f)))
         if need_dgrad:
-            c["wd_plain"] = torch.zeros(cin, self.KI, **f)
-            c["wd"] = (torch.zeros(cin, self.KI, **f), torch.zeros(cin, self.KI, **f))
+            c["wd_plain"] = torch.zeros(cin, 9 * sd, **f)
+            c["wd"] = (torch.zeros(cin, 9 * sd, **f), torch.zeros(cin, 9 * sd, **f))
         self.convs.append(c)
         return len(self.convs) - 1
 
@@ -454,12 +456,12 @@ class ImpalaEngineTC:
             cin, cout = c["cin"], c["cout"]
             w = self.flat[c["w_off"]:c["w_off"] + cout * cin * 9].view(cout, cin, 3, 3)
             if c["implicit"]:    # Wf[co][tap][32 slots]
-                c["wf_plain"].view(cout, 3, 3, 32)[..., :cin].copy_(w.permute(0, 2, 3, 1))
+                c["wf_plain"].view(cout, 3, 3, c["sf"])[..., :cin].copy_(w.permute(0, 2, 3, 1))
             else:                # Wf[co][tap*cin + ci]
                 c["wf_plain"][:, :9 * cin].view(cout, 3, 3, cin).copy_(w.permute(0, 2, 3, 1))
             self._split(c["wf_plain"], c["wf"])
             if "wd" in c:        # Wd[ci][tap][32 slots] = W[co][ci][2-ky][2-kx]
-                c["wd_plain"].view(cin, 3, 3, 32)[..., :cout].copy_(w.flip(2, 3).permute(1, 2, 3, 0))
+                c["wd_plain"].view(cin, 3, 3, c["sd"])[..., :cout].copy_(w.flip(2, 3).permute(1, 2, 3, 0))
                 self._split(c["wd_plain"], c["wd"])
         wfc = self.flat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
         self.wfc_plain.view(self.latent, self.enc_hw, self.enc_c).copy_(wfc.permute(0, 2, 1))
@@ -492,6 +494,7 @@ class ImpalaEngineTC:
                                gX=trio(rows * cout), gY=trio(rows * cout), gZ=trio(rows * cout),
                                ga=trio(rows_in * cout)))
         ws.col = (torch.zeros(max(col, 4), **f), torch.zeros(max(col, 4), **f))   # col matrix of the first convolution
+        ws.col_src = None
         ws.h = (torch.zeros(M, self.enc, **f), torch.zeros(M, self.enc, **f))        # relu(block3), NHWC-flattened
         ws.f = (torch.zeros(M, self.latent, **f), torch.zeros(M, self.latent, **f))  # relu(fc)
         ws.last_plain = torch.zeros(M, self.latent, **f)
@@ -526,9 +529,10 @@ class ImpalaEngineTC:
         kw = dict(flags=flags, bias=self._p(c["b_off"]), out=plain, out_pair=pair, ldc=c["cout"], addend=addend,
                   ld_add=c["cout"])
         if c["implicit"]:
-            self._tc(src, 0, c["wf"], self.KI, rows, c["cout"], self.KI, conv=(B, H, W, c["cin"]), **kw)
+            self._tc(src, 0, c["wf"], 9 * c["sf"], rows, c["cout"], 9 * c["sf"], conv=(B, H, W, c["cin"]), **kw)
         else:
             self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
+            ws.col_src = src
             self._tc(ws.col, c["Kf"], c["wf"], c["Kf"], rows, c["cout"], c["Kf"], **kw)
 
     def forward(self, x, M, feature_major_ld=None, need_backward=True, train=False):
@@ -587,20 +591,22 @@ class ImpalaEngineTC:
                      out=c["gw"], ldc=c["cout"], block_n=32, conv=(B, H, W, c["cin"]), conv_wgrad=1,
                      split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, 3), chunks))))
             return
-        self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
+        if ws.col_src is not src:        # the forward pass of this minibatch left col(X) in place
+            self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
+            ws.col_src = src
         n = 9 * c["cin"]
-        bn = 256 if n > 128 else 128
-        tiles = _ceil(n, bn)
-        self._tc((dy["hi"], dy["lo"]), c["cout"], ws.col, c["Kf"], c["cout"], n, rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                 out=c["gw"], ldc=c["Kf"], block_n=bn,
-                 split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, tiles), chunks))))
+        # transposed product gw[k][co] = col^T dY: the wide operand fills the 128-row M tile, N = cout stays narrow
+        # (small CTAs, several per SM)
+        self._tc(ws.col, c["Kf"], (dy["hi"], dy["lo"]), c["cout"], n, c["cout"], rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
+                 out=c["gw"], ldc=c["cout"], block_n=32,
+                 split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, _ceil(n, 128)), chunks))))
 
     def _dgrad(self, ws, ci, dy, B, H, W, out, mask=None, addend=None, colsum_off=None):
         """dX = conv(dY, flipped W) (* relu mask of the conv input) (+ skip gradient); column sums -> bias grad below."""
         c = self.convs[ci]
         rows = B * H * W
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ADD if addend is not None else 0)
-        self._tc((dy["hi"], dy["lo"]), 0, c["wd"], self.KI, rows, c["cin"], self.KI, conv=(B, H, W, c["cout"]),
+        self._tc((dy["hi"], dy["lo"]), 0, c["wd"], 9 * c["sd"], rows, c["cin"], 9 * c["sd"], conv=(B, H, W, c["cout"]),
                  flags=flags, mask=mask, ld_mask=c["cin"], out=out["plain"], out_pair=(out["hi"], out["lo"]),
                  ldc=c["cin"], addend=addend, ld_add=c["cin"],
                  colsum=self._g(colsum_off) if colsum_off is not None else None)
@@ -672,6 +678,6 @@ class ImpalaEngineTC:
             if c["implicit"]:
                 g += c["gw"].view(3, 3, 32, cout)[:, :, :cin, :].permute(3, 2, 0, 1)
             else:
-                g += c["gw"][:, :9 * cin].view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+                g += c["gw"][:9 * cin].view(3, 3, cin, cout).permute(3, 2, 0, 1)
         g = self.gflat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
         g += self.gfc.view(self.latent, self.enc_hw, self.enc_c).permute(0, 2, 1)

@@ -112,32 +112,44 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const TIn* __restrict__ 
 }
 
 // NHWC max-pool 3x3, stride 2, pad 1: y [B, Ho, Wo, C], arg = winning tap 0..8 (first maximum, like torch).
+// One thread per output pixel and 4 channels (C % 4 == 0): float4 loads, uchar4 / float4 stores.
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                                           float* __restrict__ y, uint8_t* __restrict__ arg,
                                                           float* __restrict__ r_hi, float* __restrict__ r_lo, int Ho,
                                                           int Wo) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)B * Ho * Wo * C;
+  const int cq = C >> 2;
+  const long long total = (long long)B * Ho * Wo * cq;
   if (t >= total) return;
-  const int c = (int)(t % C);
-  const int ox = (int)((t / C) % Wo), oy = (int)((t / ((long long)C * Wo)) % Ho);
-  const long long b = t / ((long long)C * Wo * Ho);
-  float best = -3.402823466e38f;
-  int bi = 0;
+  const int c = (int)(t % cq) * 4;
+  const int ox = (int)((t / cq) % Wo), oy = (int)((t / ((long long)cq * Wo)) % Ho);
+  const long long b = t / ((long long)cq * Wo * Ho);
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int bi[4] = {0, 0, 0, 0};
   bool any = false;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int sy = oy * 2 + tap / 3 - 1, sx = ox * 2 + tap % 3 - 1;
     if (sy < 0 || sy >= H || sx < 0 || sx >= W) continue;
-    const float v = x[((b * H + sy) * W + sx) * C + c];
-    if (!any || v > best) { best = v; bi = tap; any = true; }
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + ((b * H + sy) * W + sx) * C + c));
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (!any || v[j] > best[j]) { best[j] = v[j]; bi[j] = tap; }
+    any = true;
   }
-  y[t] = best;
-  arg[t] = (uint8_t)bi;
+  const long long o = t * 4;
+  *reinterpret_cast<float4*>(y + o) = make_float4(best[0], best[1], best[2], best[3]);
+  *reinterpret_cast<uchar4*>(arg + o) = make_uchar4((uint8_t)bi[0], (uint8_t)bi[1], (uint8_t)bi[2], (uint8_t)bi[3]);
   if (r_hi) {   // TF32 pair of relu(y): the operand of the residual block's first convolution
-    const float q = fmaxf(best, 0.0f), h = cv_tf32(q);
-    r_hi[t] = h;
-    r_lo[t] = q - h;
+    float q[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j] = fmaxf(best[j], 0.0f);
+      h[j] = cv_tf32(q[j]);
+    }
+    *reinterpret_cast<float4*>(r_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(r_lo + o) = make_float4(q[0] - h[0], q[1] - h[1], q[2] - h[2], q[3] - h[3]);
   }
 }
 
@@ -271,9 +283,10 @@ extern "C" int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t 
 
 extern "C" int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,
                                     float* relu_hi, float* relu_lo, void* stream) {
-  TPP_CHECK_ARG(x && y && arg && B > 0 && H > 0 && W > 0 && C > 0 && ((relu_hi == nullptr) == (relu_lo == nullptr)));
+  TPP_CHECK_ARG(x && y && arg && B > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0);
+  TPP_CHECK_ARG((relu_hi == nullptr) == (relu_lo == nullptr));
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-  const long long total = (long long)B * Ho * Wo * C;
+  const long long total = (long long)B * Ho * Wo * (C / 4);
   tpp::maxpool_fwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(x, B, H, W, C, y, arg, relu_hi,
                                                                                     relu_lo, Ho, Wo);
   TPP_LAUNCH_STATUS();

@@ -60,6 +60,8 @@ struct Params {
   int a_slot, b_slot;          // bytes of one A / B operand copy inside a stage
   int b_tx;                    // bytes one B box delivers
   int conv_W, conv_HW;         // implicit 3x3 convolution: A tiles come from TMA im2col loads of an NHWC tensor (0 = off)
+  int bk;                      // fp32 words per k-block row: 32 (128-byte swizzle) or 16 (64-byte swizzle: 16-channel
+                               // convolutions, whose taps would otherwise be half zero fill)
   int conv_wgrad;              // 1: weight-gradient form, A = im2col(X) MN-major (rows = (tap, channel slot), k = pixels)
   const float* addend; long long ld_add;   // optional residual: result += addend[m][n] (after bias / relu / mask)
 };
@@ -174,8 +176,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version 1):
 // start address >> 4 | LBO(=1, ignored for swizzled K-major) << 16 | SBO(=1024 B between 8-row groups) << 32 |
 // version 1 << 46 | layout SWIZZLE_128B (2) << 61.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// With 64-byte rows (bk = 16): SBO = 512 B, layout SWIZZLE_64B (4).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
+  const uint64_t sbo = bk == 32 ? 64ull : 32ull, layout = bk == 32 ? 2ull : 4ull;
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
 // MN-major 32-bit operands have exactly one legal shared-memory layout on sm_100: "128B swizzle with 32B atoms"
@@ -230,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int total_kb = (p.K + p.bk - 1) / p.bk;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, total_kb - kb0);
 
@@ -273,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (kb == 0) TPP_PROBE(2);
         mbar_expect_tx(full_bar + s, tx);
         uint8_t* st = smem + s * stage_bytes;
-        const int kc = (kb0 + kb) * BLOCK_K;
+        const int kc = (kb0 + kb) * p.bk;
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
         // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
         // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
@@ -317,12 +321,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int pass = p.npass - 1; pass >= 0; --pass) {
           const uint32_t a = (pass == 2) ? a_lo : a_hi;
           const uint32_t b = (pass == 1) ? b_lo : b_hi;
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const int ksteps = p.bk / UMMA_K;
+#pragma unroll 4
+          for (int k = 0; k < ksteps; ++k) {
             const uint32_t acc = (kb > 0 || pass != p.npass - 1 || k > 0) ? 1u : 0u;
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
-            const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4);
-            const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4);
+            const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, p.bk);
+            const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, p.bk);
             umma_tf32(tmem_base, da, db, IDESC, acc);
           }
         }
@@ -594,7 +599,7 @@ static EncodeTiledFn encode_tiled() {
 // *box_bytes: bytes one box delivers.  A narrow MN-major operand (fewer 32-wide blocks than the tile has) gets a
 // smaller box: the blocks it does not fill only feed accumulator rows / columns that are never stored.
 static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, int K, int box_rows, int mn_major,
-                    int* box_bytes) {
+                    int* box_bytes, int bk = BLOCK_K) {
   if (!base) return TPP_EINVAL;
   EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled();
   if (!cuTensorMapEncodeTiled) return TPP_ENOTSUP;
@@ -604,10 +609,11 @@ static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, 
   if (!mn_major) {
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-    *box_bytes = BLOCK_K * box_rows * 4;
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
+    *box_bytes = bk * box_rows * 4;
     r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     if (box_rows < 32) return TPP_ENOTSUP;
@@ -646,7 +652,7 @@ static EncodeIm2colFn encode_im2col() {
 // NHWC fp32 tensor [B][H][W][C] as the A operand of a 3x3 / pad-1 convolution: box = BLOCK_M pixels x 32 channel slots
 // (one 128-byte swizzled row per pixel, the same shared-memory tile as the K-major tiled map), conventions pinned by
 // tests/test_conv_ops.py::test_tma_im2col_conventions.
-static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int W, int C, int wgrad) {
+static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int W, int C, int wgrad, int bk) {
   if (!base || (reinterpret_cast<uintptr_t>(base) & 15) || (C & 3) || C > 32) return TPP_EINVAL;
   EncodeIm2colFn enc = encode_im2col();
   if (!enc) return TPP_ENOTSUP;
@@ -656,9 +662,11 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
   cuuint32_t estr[4] = {1, 1, 1, 1};
   // forward / data gradient: K-major A tile, 128 pixels x 128-byte rows; weight gradient: MN-major A blocks of
   // 32 pixels (k rows) x 32 channel slots in the 32-byte-atom swizzle (the only legal MN-major fp32 layout)
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, lower, upper, 32,
-                   wgrad ? BLOCK_K : BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   wgrad ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  // (bk = 16: 16 channel slots per pixel, 64-byte rows in the 64-byte swizzle)
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, lower, upper,
+                   (cuuint32_t)bk, wgrad ? BLOCK_K : BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   wgrad ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                         : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
@@ -670,21 +678,24 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   int rc, a_bytes = A_BYTES, b_bytes = BLOCK_N * BLOCK_K * 4;
   const bool conv = g->conv_C > 0;
   const int wgrad = conv && g->conv_wgrad;
+  int bk = BLOCK_K;
   if (conv) {
     const long long pixels = (long long)g->conv_B * g->conv_H * g->conv_W;
     if (wgrad) {
       if (!g->a_mn || !g->b_mn || g->M != 9 * 32 || pixels != g->K || !(g->flags & F_ATOMIC)) return TPP_EINVAL;
-    } else if (g->a_mn || g->K != 9 * BLOCK_K || pixels != g->M) {
-      return TPP_EINVAL;
+    } else {
+      if (g->K == 9 * 16 && g->conv_C <= 16 && !g->b_mn) bk = 16;    // 16 channel slots per tap
+      if (g->a_mn || g->K != 9 * bk || pixels != g->M) return TPP_EINVAL;
+      a_bytes = BLOCK_M * bk * 4;
     }
-    if ((rc = make_map_im2col(&tmA_hi, g->a_hi, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad))) return rc;
-    if (npass == 3 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad)))
+    if ((rc = make_map_im2col(&tmA_hi, g->a_hi, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk))) return rc;
+    if (npass == 3 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk)))
       return rc;
   } else if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
-  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes))) return rc;
+  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
   if (npass == 3) {
     if (!conv && (rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
-    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes))) return rc;
+    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
   } else {
     tmA_lo = tmA_hi;
     tmB_lo = tmB_hi;
@@ -699,22 +710,29 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
   p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(g->dbg);
-  const int total_kb = (g->K + BLOCK_K - 1) / BLOCK_K;
+  p.bk = bk;
+  const int total_kb = (g->K + bk - 1) / bk;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
   split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   // slots keep the full tile size: the MMA reads all BLOCK_M x BLOCK_N operand rows, also the ones a smaller TMA box
   // left unfilled (their products land in accumulator rows / columns that are never stored)
-  p.a_slot = A_BYTES;
-  p.b_slot = BLOCK_N * BLOCK_K * 4;
+  p.a_slot = BLOCK_M * bk * 4;
+  p.b_slot = BLOCK_N * bk * 4;
   const int stage_bytes = (p.a_slot + p.b_slot) * (npass == 3 ? 2 : 1);
   int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
   if (stages > 8) stages = 8;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
-  // per SM so that one tile's epilogue / prologue overlaps another tile's loads
+  // per SM so that one tile's epilogue / prologue overlaps another tile's loads (measured on the IMPALA shapes:
+  // throughput follows the number of resident CTAs, not the depth: 3 CTAs x 2 stages beat 1 CTA x 6 stages by 1.4-2x)
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
-  if (n_tiles >= 4 * 148 && stages > 2 && (p.kb_per_split <= 16 || BLOCK_N <= 32)) stages = 2;
+  if (n_tiles >= 4 * 148 && (p.kb_per_split <= 16 || BLOCK_N <= 32)) {
+    int few = (74 * 1024) / stage_bytes;   // as deep as three resident CTAs allow
+    if (few < 2) few = 2;
+    if (stages > few) stages = few;
+  }
+
   if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
   // the epilogue's transpose patches alias the pipeline stages: the region must hold at least STG_BYTES
