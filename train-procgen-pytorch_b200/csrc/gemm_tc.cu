@@ -221,7 +221,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int nops = p.npass == 3 ? 2 : 1;
-  const int A_BYTES = p.a_slot, B_BYTES = p.b_slot;
+  // Narrow tiles (BLOCK_N <= 32) are the convolution tiles: only they carry the residual / ReLU-pair epilogue extras,
+  // the 64-byte-row k-blocks and the im2col producer; wide tiles keep compile-time constants and the lean epilogue.
+  constexpr bool NARROW = BLOCK_N <= 32;
+  const int bk = NARROW ? p.bk : BLOCK_K;
+  const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : BLOCK_N * BLOCK_K * 4;
   const int stage_bytes = (A_BYTES + B_BYTES) * nops;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -234,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
-  const int total_kb = (p.K + p.bk - 1) / p.bk;
+  const int total_kb = (p.K + bk - 1) / bk;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, total_kb - kb0);
 
@@ -260,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
       int cw = 0, ch = 0, cn = 0;
-      if (p.conv_W && !p.conv_wgrad) {   // base pixel of this tile in bounding-box coordinates
+      if (NARROW && p.conv_W && !p.conv_wgrad) {   // base pixel of this tile in bounding-box coordinates
         cn = m0 / p.conv_HW;
         const int r = m0 - cn * p.conv_HW;
         ch = r / p.conv_W - 1;
@@ -269,7 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // weight-gradient form: this M tile covers filter taps tap0 .. tap0 + ntaps - 1 (32 channel slots each)
       const int tap0 = (m0 / BLOCK_M) * (BLOCK_M / 32);
       const int ntaps = min(BLOCK_M / 32, 9 - tap0);
-      const uint32_t tx = p.conv_wgrad ? (uint32_t)((ntaps * 4096 + p.b_tx) * nops) : (uint32_t)p.tx_bytes;
+      const uint32_t tx = (NARROW && p.conv_wgrad) ? (uint32_t)((ntaps * 4096 + p.b_tx) * nops) : (uint32_t)p.tx_bytes;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % p.stages;
         const uint32_t ph = (kb / p.stages) & 1;
@@ -277,19 +281,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (kb == 0) TPP_PROBE(2);
         mbar_expect_tx(full_bar + s, tx);
         uint8_t* st = smem + s * stage_bytes;
-        const int kc = (kb0 + kb) * p.bk;
+        const int kc = (kb0 + kb) * bk;
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
         // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
         // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
         for (int o = 0; o < nops; ++o) {
           const CUtensorMap* tmA = o ? &tmA_lo : &tmA_hi;
           uint8_t* dst = st + o * A_BYTES;
-          if (p.conv_wgrad) {
+          if (NARROW && p.conv_wgrad) {
             const int n = kc / p.conv_HW, r = kc - n * p.conv_HW;
             const int h = r / p.conv_W - 1, w = r % p.conv_W - 1;
             for (int j = 0; j < ntaps; ++j)
               tma_load_im2col(tmA, full_bar + s, dst + j * 4096, w, h, n, (tap0 + j) % 3, (tap0 + j) / 3);
-          } else if (p.conv_W) {
+          } else if (NARROW && p.conv_W) {
             const int tap = kb0 + kb;
             tma_load_im2col(tmA, full_bar + s, dst, cw, ch, cn, tap % 3, tap / 3);
           } else if (p.a_mn) {
@@ -321,13 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int pass = p.npass - 1; pass >= 0; --pass) {
           const uint32_t a = (pass == 2) ? a_lo : a_hi;
           const uint32_t b = (pass == 1) ? b_lo : b_hi;
-          const int ksteps = p.bk / UMMA_K;
-#pragma unroll 4
-          for (int k = 0; k < ksteps; ++k) {
+          const int ksteps = bk / UMMA_K;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            if (NARROW && k >= ksteps) break;
             const uint32_t acc = (kb > 0 || pass != p.npass - 1 || k > 0) ? 1u : 0u;
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
-            const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, p.bk);
-            const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, p.bk);
+            const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, bk);
+            const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, bk);
             umma_tf32(tmem_base, da, db, IDESC, acc);
           }
         }
@@ -395,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float* pl = p.out_lo ? p.out_lo + o0 : nullptr;
           const float* pm = (p.flags & F_MASK) ? p.mask + (long long)(mrow0 + rr) * p.ld_mask + nc : nullptr;
           const long long mstep = 4 * p.ld_mask;
-          const float* pa = (p.flags & F_ADD) ? p.addend + (long long)(mrow0 + rr) * p.ld_add + nc : nullptr;
+          const float* pa = (NARROW && (p.flags & F_ADD)) ? p.addend + (long long)(mrow0 + rr) * p.ld_add + nc : nullptr;
           const long long astep = 4 * p.ld_add;
           const float floor_v = (p.flags & F_RELU) ? 0.0f : -3.402823466e38f;
           const float floor_out = (p.flags & F_RELU_OUT) ? 0.0f : -3.402823466e38f;
@@ -414,19 +419,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               x[2] = mq.z > 0.0f ? x[2] : 0.0f;
               x[3] = mq.w > 0.0f ? x[3] : 0.0f;
             }
-            if (pa) {
-              const float4 aq = *reinterpret_cast<const float4*>(pa);
-              pa += astep;
-              x[0] += aq.x; x[1] += aq.y; x[2] += aq.z; x[3] += aq.w;
-            }
+            if (NARROW) {
+              if (pa) {
+                const float4 aq = *reinterpret_cast<const float4*>(pa);
+                pa += astep;
+                x[0] += aq.x; x[1] += aq.y; x[2] += aq.z; x[3] += aq.w;
+              }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_out);
+              for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_out);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) cs4[j] += x[j];
             if (po) { *reinterpret_cast<float4*>(po) = make_float4(x[0], x[1], x[2], x[3]); po += ostep; }
             if (ph) {
+              if (NARROW) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_pair);
+                for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], floor_pair);
+              }
               const float h0 = tf32_round(x[0]), h1 = tf32_round(x[1]), h2 = tf32_round(x[2]), h3 = tf32_round(x[3]);
               *reinterpret_cast<float4*>(ph) = make_float4(h0, h1, h2, h3);
               *reinterpret_cast<float4*>(pl) = make_float4(x[0] - h0, x[1] - h1, x[2] - h2, x[3] - h3);
@@ -480,13 +489,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (nc + j < p.N && !(mk[j] > 0.0f)) x[j] = 0.0f;
           }
         }
-        if (p.flags & F_ADD) {
+        if (NARROW && (p.flags & F_ADD)) {
           const float* ad = p.addend + (long long)gm * p.ld_add + nc;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (nc + j < p.N) x[j] += ad[j];
         }
-        if (p.flags & F_RELU_OUT) {
+        if (NARROW && (p.flags & F_RELU_OUT)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f);
         }
@@ -495,7 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float y = (p.flags & F_PAIR_RELU) ? fmaxf(x[j], 0.0f) : x[j];
+          const float y = (NARROW && (p.flags & F_PAIR_RELU)) ? fmaxf(x[j], 0.0f) : x[j];
           h[j] = tf32_round(y);
           l[j] = y - h[j];
         }
@@ -675,6 +684,8 @@ template <int BLOCK_N>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const int npass = g->precision == 3 ? 3 : 1;
+  if (BLOCK_N > 32 && ((g->flags & (F_ADD | F_RELU_OUT | F_PAIR_RELU)) || g->conv_C > 0))
+    return TPP_ENOTSUP;   // residual / ReLU-pair epilogues and convolution mode are compiled into the narrow tiles only
   int rc, a_bytes = A_BYTES, b_bytes = BLOCK_N * BLOCK_K * 4;
   const bool conv = g->conv_C > 0;
   const int wgrad = conv && g->conv_wgrad;
@@ -722,7 +733,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.b_slot = BLOCK_N * bk * 4;
   const int stage_bytes = (p.a_slot + p.b_slot) * (npass == 3 ? 2 : 1);
   int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
-  if (stages > 8) stages = 8;
+  if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
   // per SM so that one tile's epilogue / prologue overlaps another tile's loads (measured on the IMPALA shapes:
   // throughput follows the number of resident CTAs, not the depth: 3 CTAs x 2 stages beat 1 CTA x 6 stages by 1.4-2x)
