@@ -64,7 +64,7 @@ def main():
     # hard-500 set (hyperparams/procgen/config.yml:81-99): 3 epochs, n_minibatch 8 (default), mini_batch_size 8192
     agent = PPO(env, pol, None, st, "cuda", 0, n_steps=T, n_envs=N, epoch=3, n_minibatch=8, mini_batch_size=8192,
                 gamma=0.999, lmbda=0.95, learning_rate=5e-4, entropy_coef=0.01, matmul=args.matmul)
-    agent.train(T * N)                       # warm-up iteration
+    agent.train(T * N * 2)                   # warm-up: eager iteration, then the iteration that captures the graphs
     torch.cuda.synchronize()
     st.h2d_bytes = 0
     agent.t = 0

@@ -1,0 +1,81 @@
+"""Launch the three implicit-GEMM convolution forms at the IMPALA block-1 shape of the Procgen workload
+(2048 samples x 32x32 pixels, 16 -> 16 channels, 3xTF32), for `ncu --set full -k regex:gemm_tc_kernel`.
+
+    python profiles/run_conv_kernels.py          # plain run first (must exit 0), prints graph-timed durations
+"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tpp_b200 import _lib as L  # noqa: E402
+
+
+def pair(x):
+    hi = ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, x - hi
+
+
+def main():
+    B, H, W, Cc = 2048, 32, 32, 16
+    rows = B * H * W
+    torch.manual_seed(0)
+    x = pair(torch.randn(B, H, W, Cc, device="cuda").clamp_min(0))
+    dy = pair(torch.randn(rows, Cc, device="cuda"))
+    w16 = pair(torch.randn(Cc, 144, device="cuda") * 0.1)
+    bias = torch.zeros(Cc, device="cuda")
+    out = torch.zeros(rows, Cc, device="cuda")
+    oh, ol = torch.zeros_like(out), torch.zeros_like(out)
+    mask = torch.randn(rows, Cc, device="cuda")
+    gw = torch.zeros(288, Cc, device="cuda")
+    cs = torch.zeros(Cc, device="cuda")
+
+    fwd = L.TcGemm()
+    fwd.a_hi, fwd.a_lo, fwd.b_hi, fwd.b_lo, fwd.ldb = x[0].data_ptr(), x[1].data_ptr(), w16[0].data_ptr(), w16[1].data_ptr(), 144
+    fwd.M, fwd.N, fwd.K, fwd.precision, fwd.split_k = rows, Cc, 144, 3, 1
+    fwd.conv_B, fwd.conv_H, fwd.conv_W, fwd.conv_C = B, H, W, Cc
+    fwd.flags, fwd.bias = L.EPI_BIAS | L.EPI_PAIR_RELU, bias.data_ptr()
+    fwd.out, fwd.out_hi, fwd.out_lo, fwd.ldc = out.data_ptr(), oh.data_ptr(), ol.data_ptr(), Cc
+
+    dg = L.TcGemm()
+    dg.a_hi, dg.a_lo, dg.b_hi, dg.b_lo, dg.ldb = dy[0].data_ptr(), dy[1].data_ptr(), w16[0].data_ptr(), w16[1].data_ptr(), 144
+    dg.M, dg.N, dg.K, dg.precision, dg.split_k = rows, Cc, 144, 3, 1
+    dg.conv_B, dg.conv_H, dg.conv_W, dg.conv_C = B, H, W, Cc
+    dg.flags, dg.mask, dg.ld_mask, dg.addend, dg.ld_add = L.EPI_MASK | L.EPI_ADD, mask.data_ptr(), Cc, mask.data_ptr(), Cc
+    dg.out, dg.out_hi, dg.out_lo, dg.ldc, dg.colsum = out.data_ptr(), oh.data_ptr(), ol.data_ptr(), Cc, cs.data_ptr()
+
+    wg = L.TcGemm()
+    wg.a_hi, wg.a_lo, wg.b_hi, wg.b_lo, wg.ldb = x[0].data_ptr(), x[1].data_ptr(), dy[0].data_ptr(), dy[1].data_ptr(), Cc
+    wg.M, wg.N, wg.K, wg.precision, wg.split_k, wg.a_mn, wg.b_mn = 288, Cc, rows, 3, rows // 1024, 1, 1
+    wg.conv_B, wg.conv_H, wg.conv_W, wg.conv_C, wg.conv_wgrad = B, H, W, Cc, 1
+    wg.flags, wg.out, wg.ldc, wg.block_n = L.EPI_ACCUM, gw.data_ptr(), Cc, 32
+
+    res = {}
+    for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg)):
+        for _ in range(2):
+            L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(10):
+                L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / 10 * 1e3
+    flops = 2.0 * rows * Cc * 9 * Cc
+    act_bytes = rows * Cc * 4
+    for name, us in res.items():
+        print(f"{name}: {us:.1f} us  = {flops / us / 1e6:.1f} TFLOP/s algorithmic (2*pixels*9*Cin*Cout), "
+              f"gathered operand bytes 9 taps x 2 (hi, lo) x {act_bytes / 1e6:.0f} MB = {18 * act_bytes / us / 1e3:.0f} GB/s")
+
+
+if __name__ == "__main__":
+    main()

@@ -444,6 +444,34 @@ class PPO(BaseAgent):
         torch.save({"model_state_dict": self.policy.state_dict(), "optimizer_state_dict": self.optimizer.state_dict()},
                    self.logger.logdir + "/model_" + str(self.t) + ".pth")
 
+    def _host_step_device(self, st, t, N):
+        """Device side of one host-env step (frames -> policy forward -> Philox sampling into slot t).  The ~40
+        launches are captured once per slot (second visit) and replayed afterwards: the step is launch-bound."""
+        def body():
+            head = self._policy_head(st.obs_slot(t), st)
+            self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t)
+
+        graphs = self.__dict__.setdefault("_host_graphs", {})
+        key = (id(st), t)
+        entry = graphs.get(key)
+        if not self.use_cuda_graph or isinstance(self.engine, TorchModuleEngine):
+            return body()
+        if entry is None:                      # first visit: eager (allocates the workspaces)
+            body()
+            graphs[key] = "warm"
+            return
+        if entry == "warm":
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            c0 = (self.n_launches, self.engine.n_launches)
+            with torch.cuda.graph(g):
+                body()
+            entry = graphs[key] = (g, self.n_launches - c0[0], self.engine.n_launches - c0[1])
+            self.n_launches, self.engine.n_launches = c0
+        entry[0].replay()
+        self.n_launches += entry[1]
+        self.engine.n_launches += entry[2]
+
     def _train_host_env(self, num_timesteps, checkpoints):
         """Host-stepped envs (Procgen or any numpy VecEnv; reference loop agents/ppo.py:216-236).  Per step: the
         observation is staged once into rollout slot t (pinned H2D; uint8 frames stay uint8), the policy forward and
@@ -458,8 +486,7 @@ class PPO(BaseAgent):
                 self.engine.refresh_weights()
             for t in range(T):
                 st.stage_obs(t, obs)
-                head = self._policy_head(st.obs_slot(t), st)
-                self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t)
+                self._host_step_device(st, t, N)
                 act = st.act_i32[t, :N].cpu().numpy().astype(np.int64)      # the step's only device->host read
                 obs, rew, done, info = self.env.step(act)
                 st.stage_step(t, rew, done)

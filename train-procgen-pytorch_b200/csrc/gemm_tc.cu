@@ -1,6 +1,18 @@
-// Tensor-core path of the policy's dense layers: tcgen05.mma (kind::tf32) with TMEM accumulators, operands staged
-// by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier pipeline, warp-specialised
-// (1 TMA warp, 1 MMA warp, 4 epilogue warps).  sm_100a only.
+// Tensor-core path of the policy's dense layers AND 3x3 convolutions: tcgen05.mma (kind::tf32) with TMEM
+// accumulators, operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier pipeline,
+// warp-specialised (1 TMA warp, 1 MMA warp, 4 or 16 epilogue warps).  sm_100a only.
+//
+// Convolutions (IMPALA-CNN, reference common/model.py:134-208) are implicit GEMMs on the narrow tile instances
+// (BLOCK_N = 16 / 32 = output channels): the A tiles are gathered straight from the NHWC activation pair by TMA
+// *im2col* loads (cp.async.bulk.tensor.4d...im2col: 128 consecutive output pixels x one filter tap per k-block, the
+// TMA unit zero-fills padding pixels, unused channel slots and the tail behind the last image), so no col matrix
+// exists.  Forward and data gradient are K-major (k-block = tap; 16-channel tensors use 64-byte rows / 64-byte
+// swizzle, 32-channel ones 128-byte rows); the weight gradient gathers the same tensor as an MN-major operand
+// (k-block = 32 pixels, one im2col box per tap).  The narrow instances are PERSISTENT (two TMEM accumulators,
+// producer / MMA warps run ahead into the next tile while the epilogue drains the previous one) and carry the
+// fused residual add, ReLU-pair output and running bias-gradient column sums.  Measured on B200 (block-1 shape,
+// 2.1 M pixels, 16 -> 16 channels, 3xTF32): forward 322 us, data gradient 338 us, weight gradient 820 us; the bound is
+// the L2 -> shared-memory gather of 9 taps x (hi, lo) (7.5 TB/s achieved), see profiles/README.md.
 //
 // Precision.  The parity bar of this path is fp32 (<= 1e-5 relative against the reference's torch-fp32 result),
 // which a single TF32 product (10-bit mantissa) cannot meet.  Every operand therefore exists as a pair
@@ -55,7 +67,10 @@ struct Params {
   float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
   int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
   long long* dbg;              // optional timeline probe (block 0 only): clock64 at 8 milestones
-  int ntn;                     // number of N tiles (grid.x = ntn * number of M tiles)
+  int ntn;                     // number of N tiles
+  int ntiles;                  // ntn * number of M tiles
+  int total_work;              // ntiles * number of k-splits: work items (tile, split), split-major
+  int stg_offset;              // byte offset of the epilogue's transpose patches (0: they alias the pipeline stages)
   int tx_bytes;                // bytes one stage receives (narrow MN-major operands use smaller TMA boxes)
   int a_slot, b_slot;          // bytes of one A / B operand copy inside a stage
   int b_tx;                    // bytes one B box delivers
@@ -75,6 +90,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -207,7 +228,14 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  // Narrow tiles (BLOCK_N <= 32) are the convolution tiles.  Only they carry the residual / ReLU-pair epilogue extras,
+  // the 64-byte-row k-blocks and the im2col producer, and they run PERSISTENT: a CTA loops over work items with two
+  // TMEM accumulators, so that the producer / MMA warps start the next tile while the epilogue warps drain the
+  // previous one (per-tile prologue, epilogue and CTA launch were ~2/3 of a 9-k-block tile's time).  Wide tiles keep
+  // compile-time constants, the lean epilogue and one work item per CTA.
+  constexpr bool NARROW = BLOCK_N <= 32;
+  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;          // TMEM columns of one accumulator
+  constexpr uint32_t TMEM_COLS = NARROW ? 2 * ACC_COLS : ACC_COLS;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), a_major bit 15,
   // b_major bit 16 (1 = MN-major), N>>3 at bit 17, M>>4 at bit 24
   const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
@@ -221,25 +249,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   const int nops = p.npass == 3 ? 2 : 1;
-  // Narrow tiles (BLOCK_N <= 32) are the convolution tiles: only they carry the residual / ReLU-pair epilogue extras,
-  // the 64-byte-row k-blocks and the im2col producer; wide tiles keep compile-time constants and the lean epilogue.
-  constexpr bool NARROW = BLOCK_N <= 32;
   const int bk = NARROW ? p.bk : BLOCK_K;
   const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : BLOCK_N * BLOCK_K * 4;
   const int stage_bytes = (A_BYTES + B_BYTES) * nops;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + p.stages;      // [2]: accumulator i complete (MMA -> epilogue)
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]: accumulator i drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tiles are flattened on grid.x (n fastest) so that M is not limited by the 65535 bound of grid.y (conv rows)
-  const int m0 = (int)(blockIdx.x / p.ntn) * BLOCK_M, n0 = (int)(blockIdx.x % p.ntn) * BLOCK_N;
-  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.z == 0 && lane == 0;
+  // Work items (tile, k-split) are flattened on grid.x (n tile fastest, then m tile, then split), so M is not limited
+  // by the 65535 bound of grid.y.  A persistent CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int wstride = NARROW ? (int)gridDim.x : p.total_work;
+  const bool probe = p.dbg && blockIdx.x == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + bk - 1) / bk;
-  const int kb0 = blockIdx.z * p.kb_per_split;
+#define TPP_DECODE_WORK(w)                                                           \
+  const int tile_ = (w) % p.ntiles, split_ = (w) / p.ntiles;                         \
+  const int m0 = (tile_ / p.ntn) * BLOCK_M, n0 = (tile_ % p.ntn) * BLOCK_N;          \
+  const int kb0 = split_ * p.kb_per_split;                                           \
   const int nkb = min(p.kb_per_split, total_kb - kb0);
 
   if (warp == 0 && lane == 0) {
@@ -249,7 +279,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, epi_warps(BLOCK_N));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -263,6 +296,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+     int it = 0;                                   // k-blocks issued so far (stage ring position across work items)
+     for (int w = blockIdx.x; w < p.total_work; w += wstride) {
+      TPP_DECODE_WORK(w)
       int cw = 0, ch = 0, cn = 0;
       if (NARROW && p.conv_W && !p.conv_wgrad) {   // base pixel of this tile in bounding-box coordinates
         cn = m0 / p.conv_HW;
@@ -274,11 +310,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int tap0 = (m0 / BLOCK_M) * (BLOCK_M / 32);
       const int ntaps = min(BLOCK_M / 32, 9 - tap0);
       const uint32_t tx = (NARROW && p.conv_wgrad) ? (uint32_t)((ntaps * 4096 + p.b_tx) * nops) : (uint32_t)p.tx_bytes;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % p.stages;
-        const uint32_t ph = (kb / p.stages) & 1;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
-        if (kb == 0) TPP_PROBE(2);
+        if (it == 0) TPP_PROBE(2);
         mbar_expect_tx(full_bar + s, tx);
         uint8_t* st = smem + s * stage_bytes;
         const int kc = (kb0 + kb) * bk;
@@ -307,15 +343,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           else tma_load_2d(tmB, full_bar + s, dstb, kc, n0);
         }
       }
+     }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % p.stages;
-      const uint32_t ph = (kb / p.stages) & 1;
+    int it = 0, acc_i = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += wstride, ++acc_i) {
+     TPP_DECODE_WORK(w)
+     (void)m0; (void)n0; (void)kb0;
+     const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_i & 1) * ACC_COLS;
+     if (NARROW) {                                   // wait until the epilogue has drained this accumulator
+       mbar_wait(tmem_empty + (acc_i & 1), ((acc_i >> 1) & 1) ^ 1);
+       tc_fence_after();
+     }
+     for (int kb = 0; kb < nkb; ++kb, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
-      if (kb == 0) TPP_PROBE(3);
+      if (it == 0) TPP_PROBE(3);
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
         const uint32_t a_lo = a_hi + A_BYTES;
@@ -333,13 +379,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
             const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, bk);
             const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, bk);
-            umma_tf32(tmem_base, da, db, IDESC, acc);
+            umma_tf32(tmem_acc, da, db, IDESC, acc);
           }
         }
         umma_commit(empty_bar + s);                 // frees the smem stage when these MMAs retire
-        if (kb == nkb - 1) { umma_commit(tmem_full); TPP_PROBE(4); }  // accumulator complete
+        if (kb == nkb - 1) { umma_commit(tmem_full + (acc_i & 1)); TPP_PROBE(4); }  // accumulator complete
       }
       __syncwarp();
+     }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> smem transpose -> (bias / relu / mask / tf32 split) -> coalesced global ====
@@ -353,13 +400,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
-    const int mrow0 = m0 + quarter * 32;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float* stg = reinterpret_cast<float*>(smem) + ew * (32 * STG_PITCH);
+    float* stg = reinterpret_cast<float*>(smem + (NARROW ? p.stg_offset : 0)) + ew * (32 * STG_PITCH);
     constexpr int GW = BLOCK_N < 32 ? BLOCK_N : 32;     // columns per staged group
     const int rr = lane >> 3, cc = (lane & 7) * 4;      // post-transpose mapping: 4 rows x (8 lanes x 4 columns)
     const bool atomic = p.flags & F_ATOMIC;
-    mbar_wait(tmem_full, 0);
+    int acc_i = 0;
+    // running column sums of a persistent CTA (see the colsum flush below): kept in the 4 spare floats of this lane's
+    // patch row (STG_PITCH = 36) rather than in registers -- at 192 threads the third resident CTA is lost above 96
+    float* cs_run = stg + lane * STG_PITCH + 32;
+    if (NARROW) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cs_run[j] = 0.0f;
+    }
+    int cs_n = -1;
+    for (int w = blockIdx.x; w < p.total_work; w += wstride, ++acc_i) {
+    TPP_DECODE_WORK(w)
+    (void)kb0;
+    const int mrow0 = m0 + quarter * 32;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc_i & 1) * ACC_COLS;
+    if (NARROW && (p.flags & (F_MASK | F_ADD)) && cc < GW) {
+      // the ReLU mask / residual rows of this tile are known before its accumulator is complete: pull them into L1
+      // now, the epilogue's dependent loads then hit (they were ~1/3 of the data-gradient tiles' time)
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long gm = mrow0 + it * 4 + rr;
+        if (gm < p.M) {
+          if (p.flags & F_MASK) prefetch_l1(p.mask + gm * p.ld_mask + n0 + cc);
+          if (p.flags & F_ADD) prefetch_l1(p.addend + gm * p.ld_add + n0 + cc);
+        }
+      }
+    }
+    mbar_wait(tmem_full + (acc_i & 1), (acc_i >> 1) & 1);
     tc_fence_after();
     if (warp == 2) TPP_PROBE(5);
 #pragma unroll 1
@@ -525,16 +596,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       if (warp == 2 && c == 0) TPP_PROBE(10);
       if (p.colsum && !atomic) {   // bias gradient: this warp's 32 rows of columns nc..nc+3 (lanes l, l+8, l+16, l+24)
+        if (NARROW) {
+          // persistent CTA, one column group per tile: keep the sums in registers across tiles and flush them when the
+          // column group changes / at the end (16 addresses would otherwise take ~130 000 same-address atomics each)
+          if (cs_n != n && cs_n >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 8);
-          cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 16);
-        }
-        if (rr == 0) {
+            for (int j = 0; j < 4; ++j) {
+              float v = cs_run[j];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (rr == 0 && cc < GW && cs_n + cc + j < p.N) atomicAdd(p.colsum + cs_n + cc + j, v);
+              cs_run[j] = 0.0f;
+            }
+          }
+          cs_n = n;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (lane_on && nc + j < p.N) atomicAdd(p.colsum + nc + j, cs4[j]);
+          for (int j = 0; j < 4; ++j) cs_run[j] += cs4[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 8);
+            cs4[j] += __shfl_xor_sync(0xffffffffu, cs4[j], 16);
+          }
+          if (rr == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (lane_on && nc + j < p.N) atomicAdd(p.colsum + nc + j, cs4[j]);
+          }
         }
+      }
+    }
+    if (NARROW) {                       // accumulator drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + (acc_i & 1));
+    }
+    }   // work items
+    if (NARROW && cs_n >= 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = cs_run[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (rr == 0 && cc < GW && cs_n + cc + j < p.N) atomicAdd(p.colsum + cs_n + cc + j, v);
       }
     }
   }
@@ -732,23 +836,31 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.a_slot = BLOCK_M * bk * 4;
   p.b_slot = BLOCK_N * bk * 4;
   const int stage_bytes = (p.a_slot + p.b_slot) * (npass == 3 ? 2 : 1);
-  int stages = (224 * 1024 - 1024 - 256) / stage_bytes;
+  int stages = (224 * 1024 - 1024 - 256 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
+  if (stages < 1) return TPP_ENOTSUP;
   if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
   // per SM so that one tile's epilogue / prologue overlaps another tile's loads (measured on the IMPALA shapes:
   // throughput follows the number of resident CTAs, not the depth: 3 CTAs x 2 stages beat 1 CTA x 6 stages by 1.4-2x)
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
   if (n_tiles >= 4 * 148 && (p.kb_per_split <= 16 || BLOCK_N <= 32)) {
-    int few = (74 * 1024) / stage_bytes;   // as deep as three resident CTAs allow
+    int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;   // three resident CTAs
     if (few < 2) few = 2;
     if (stages > few) stages = few;
   }
-
-  if (stages > p.kb_per_split) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
+  if (stages > p.kb_per_split && BLOCK_N > 32) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
-  // the epilogue's transpose patches alias the pipeline stages: the region must hold at least STG_BYTES
+  constexpr bool NARROW = BLOCK_N <= 32;
   size_t region = (size_t)stages * stage_bytes;
-  if (region < (size_t)stg_bytes(BLOCK_N)) region = stg_bytes(BLOCK_N);
+  if (NARROW) {
+    // persistent CTAs: the epilogue's transpose patches get their own region (the next tile's loads are in flight)
+    p.stg_offset = (int)region;
+    region += stg_bytes(BLOCK_N);
+  } else {
+    // the patches alias the pipeline stages (free once the accumulator is complete): the region must hold them
+    p.stg_offset = 0;
+    if (region < (size_t)stg_bytes(BLOCK_N)) region = stg_bytes(BLOCK_N);
+  }
   p.bar_offset = (int)region;
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
@@ -758,7 +870,34 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     attr_set = true;
   }
   p.ntn = (g->N + BLOCK_N - 1) / BLOCK_N;
-  dim3 grid((unsigned)p.ntn * (unsigned)((g->M + BLOCK_M - 1) / BLOCK_M), 1, split_k);
+  p.ntiles = p.ntn * ((g->M + BLOCK_M - 1) / BLOCK_M);
+  p.total_work = p.ntiles * split_k;
+  unsigned grid_x = (unsigned)p.total_work;
+  if (NARROW) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // resident CTAs per SM from the kernel's own resources (registers, shared memory, TMEM columns)
+    static int regs_per_cta = 0;
+    if (!regs_per_cta) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N>) != cudaSuccess) return TPP_ENOTSUP;
+      regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N);
+    }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    // registers are allocated per warp inside each of the 4 SM sub-partitions (16384 registers each)
+    const int regs_per_warp = regs_per_cta / (num_threads(BLOCK_N) / 32);
+    const int warps_per_sm = 4 * (16384 / regs_per_warp);
+    if (per_sm > warps_per_sm / (num_threads(BLOCK_N) / 32)) per_sm = warps_per_sm / (num_threads(BLOCK_N) / 32);
+    if (per_sm > 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N))) per_sm = 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned resident = (unsigned)(per_sm * sms);
+    if (grid_x > resident) grid_x = resident;
+  }
+  dim3 grid(grid_x, 1, 1);
   gemm_tc_kernel<BLOCK_N><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
