@@ -2,6 +2,7 @@
 (2048 samples x 32x32 pixels, 16 -> 16 channels, 3xTF32), for `ncu --set full -k regex:gemm_tc_kernel`.
 
     python profiles/run_conv_kernels.py          # plain run first (must exit 0), prints graph-timed durations
+    ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 2 -c 1 -o X python profiles/run_conv_kernels.py forward
 """
 import ctypes as C
 import os
@@ -20,6 +21,7 @@ def pair(x):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None      # forward | dgrad | wgrad: 3 plain launches (ncu: -s 2 -c 1)
     B, H, W, Cc = 2048, 32, 32, 16
     rows = B * H * W
     torch.manual_seed(0)
@@ -55,6 +57,12 @@ def main():
 
     res = {}
     for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg)):
+        if only:
+            if name == only:
+                for _ in range(3):
+                    L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+                torch.cuda.synchronize()
+            continue
         for _ in range(2):
             L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
         torch.cuda.synchronize()
