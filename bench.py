@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PPO rollout-and-update hot path (BASELINE.json metric: PPO env-steps/sec, rollout+GAE+update).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload boxworld|cartpole]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload boxworld|cartpole|procgen]
 
 One "step" = one full PPO iteration: T fused rollout steps over the rank's envs (policy forward -> Philox action
 sampling -> env step kernel writing into the rollout), bootstrap value, GAE + advantage normalisation, and
@@ -11,6 +11,11 @@ Default workload = BASELINE.json configs[1]: boxworld_env_vec PPO, n_envs=4096 p
 goal 5, 3x3 distractors, 500-level bank, T=256, 3 epochs, n_minibatch 8, mini_batch_size 8192 (the reference's
 `boxworld-impala` YAML set, hyperparams/procgen/config.yml:575-601), with an MLP policy on the flattened
 3x14x14 frame (the reference has no working Box-World policy; choice documented in DESIGN.md).
+
+`--workload procgen` = BASELINE configs[3] shape (coinrun hard-500: IMPALA-CNN, 64 envs per GPU, 64x64x3 uint8
+frames) with a synthetic host engine (the Procgen engine is not in this image): `value` = policy rollout on frames
+resident in HBM + GAE + update, `e2e` = `PPO.train()` with every step's frames staged from pinned host memory and the
+actions read back.
 
 Prints ONE JSON line (rank 0).  `value` = device-timed iterations with inputs resident (minibatch permutations
 pre-uploaded); `e2e` = the same iterations through the public API `PPO.train()` with per-epoch index upload from
@@ -42,6 +47,9 @@ WORKLOADS = {
     "cartpole": dict(n_envs=256, n_steps=256, epoch=3, n_minibatch=16, mini_batch_size=8192, gamma=0.99, lmbda=0.95,
                      learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.02,
                      depth=4, mid_weight=256, latent_size=64),
+    # reference YAML set `hard-500` (config.yml:81-99) as launched for coinrun / maze / heist: BASELINE configs[3]
+    "procgen": dict(n_envs=64, n_steps=256, epoch=3, n_minibatch=8, mini_batch_size=8192, gamma=0.999, lmbda=0.95,
+                    learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.01),
 }
 PPO_KEYS = ("n_steps", "n_envs", "epoch", "n_minibatch", "mini_batch_size", "gamma", "lmbda", "learning_rate",
             "grad_clip_norm", "eps_clip", "value_coef", "entropy_coef")
@@ -395,6 +403,147 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+class SyntheticProcgen:
+    """Host-stepped VecEnv with Procgen's contract (uint8 64x64x3 frames, 15 actions): cycles a pool of pre-generated
+    frames, Bernoulli(0.01)*10 rewards, Bernoulli(1/200) dones at no CPU cost."""
+
+    def __init__(self, n, pool=64, seed=0):
+        from tpp_b200.discrete_env.pre_vec_env import Box, Discrete
+        rng = np.random.default_rng(seed)
+        self.n = n
+        self.frames = rng.integers(0, 256, (pool, n, 64, 64, 3), dtype=np.uint8)
+        self.rew = ((rng.random((pool, n)) < 0.01) * 10.0).astype(np.float32)
+        self.done = rng.random((pool, n)) < (1 / 200)
+        self.i = 0
+        self.observation_space = Box(np.zeros((3, 64, 64)), np.ones((3, 64, 64)))
+        self.action_space = Discrete(15)
+
+    def reset(self):
+        return self.frames[0]
+
+    def step(self, act):
+        self.i = (self.i + 1) % len(self.frames)
+        return self.frames[self.i], self.rew[self.i], self.done[self.i], None
+
+    def close(self):
+        pass
+
+
+def run_procgen(args):
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    from tpp_b200 import _lib
+    from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.model import ImpalaModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    from tpp_b200.common.storage import Storage
+    hp = WORKLOADS["procgen"]
+    N, T = hp["n_envs"], hp["n_steps"]
+    matmul = args.matmul if args.matmul in ("tf32x3", "tf32") else "tf32x3"
+    env = SyntheticProcgen(N, seed=rank)
+    torch.manual_seed(6033)
+    pol = CategoricalPolicy(ImpalaModel(3), False, 15).to(device).flatten_()
+    st = Storage((3, 64, 64), 256, T, N, device)
+    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank, matmul=matmul)
+    if world > 1:
+        agent.shard(world)
+    A = agent.n_actions
+
+    def counters():
+        return agent.n_launches + agent.engine.n_launches + st.n_launches + agent.optimizer.n_launches
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def resident_iteration():          # frames of the last rollout are in st.frames: policy rollout + GAE + update
+        agent.engine.refresh_weights()
+        for t in range(T):
+            agent._host_step_device(st, t, N)
+        head = agent._policy_head(st.obs_slot(T), st)
+        st.value[T, :N] = head[:N, A]
+        _lib.call("tpp_tick_advance", _lib.ptr(agent._tick), T, _lib.stream_ptr())
+        st.compute_estimates(agent.gamma, agent.lmbda, True, True)
+        agent.optimize()
+
+    agent.train(T * N * 2)             # eager iteration, then the iteration that captures the graphs
+    for _ in range(max(args.warmup, 3)):
+        resident_iteration()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        resident_iteration()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = counters() - l0
+    clk = clocks.stop() if rank == 0 else None
+    st.h2d_bytes = 0
+    agent.t = 0
+    w0 = time.perf_counter()
+    agent.train(T * N * args.steps)
+    barrier()
+    ms_e2e = (time.perf_counter() - w0) * 1e3
+    h2d = st.h2d_bytes // args.steps
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = times.tolist()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    pk = peaks()
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import run_conv_kernels as rck
+    forms = rck.time_forms()
+    pixels = rck.SHAPE["B"] * rck.SHAPE["H"] * rck.SHAPE["W"]
+    flops = 2.0 * pixels * 9 * rck.SHAPE["C"] ** 2
+    tf = flops / forms["forward"] / 1e6
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tj):
+        traffic = json.load(open(tj)).get("gemm_tc_conv_forward")
+    roof = {"kernel": "gemm_tc_kernel<16>, implicit 3x3 convolution forward (TMA im2col, 3xTF32), IMPALA block 1: "
+                      "2048 x 32x32 pixels, 16 -> 16 channels", "bound": "tensor", "achieved": round(tf, 2),
+            "peak": pk["bf16"], "unit": "TFLOP/s", "frac": round(tf / pk["bf16"], 4), "traffic": traffic,
+            "us_per_launch": round(forms["forward"], 1), "dgrad_us": round(forms["dgrad"], 1),
+            "wgrad_us": round(forms["wgrad"], 1),
+            "gathered_operand_GBps": round(18 * pixels * rck.SHAPE["C"] * 4 / forms["forward"] / 1e3, 1),
+            "note": f"peak = dense bf16 ({pk['source']}); algorithmic FLOPs 2*pixels*9*Cin*Cout; the tile is bound by "
+                    "the L2->shared-memory gather of 9 taps x (hi, lo), see profiles/ncu_conv_r01.md"}
+    total = N * T * args.steps * world
+    mb = min(hp["mini_batch_size"], T * N // hp["n_minibatch"])
+    cpu = cpu_baseline("procgen", budget_s=20.0) if not args.no_cpu_baseline else None
+    print(json.dumps({
+        "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(total / (ms * 1e-3), 1),
+        "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"procgen-shaped PPO (coinrun hard-500): n_envs={N}/GPU, n_steps={T}, epoch=3, "
+                               f"minibatch={mb}, IMPALA-CNN policy ({matmul}), synthetic 64x64x3 uint8 frames",
+                   "parallelism": f"env-sharded dp{world}", "l2": "minibatch activations (GBs) >> L2"},
+        "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(T * N * 4 + 24 * 20 * 8), "ms_per_step": round(ms_e2e / args.steps, 3),
+                "api": "PPO.train() with a host-stepped env: per step pinned uint8 frames H2D, actions D2H"},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's numpy/torch path (the reference itself is Python and cannot
 # travel to the GPU box; oracle/* restates it and is pinned against it bit-for-bit, see tests/)
@@ -406,6 +555,26 @@ def _cpu_setup(name, n_envs, n_steps):
     from oracle.prevec import OraclePreVec
     hp = dict(WORKLOADS[name], n_envs=n_envs, n_steps=n_steps)
     torch.manual_seed(6033)
+    if name == "procgen":
+        rng = np.random.default_rng(0)
+        pool = rng.integers(0, 256, (8, n_envs, 64, 64, 3), dtype=np.uint8)
+        state = {"i": 0}
+
+        def env_step(a):
+            state["i"] = (state["i"] + 1) % len(pool)
+            return pool[state["i"]], (rng.random(n_envs) < 0.01) * 10.0, rng.random(n_envs) < (1 / 200)
+        tf = lambda f: np.ascontiguousarray(f.transpose(0, 3, 1, 2)).astype(np.float32) / 255.0
+        pol = oppo.OraclePolicy(oppo.OracleImpala(3), 15)
+        opt = oppo.make_adam(pol, hp["learning_rate"])
+        kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
+                  grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
+                  entropy_coef=hp["entropy_coef"])
+
+        def iteration(obs):
+            obs, _ = oppo.ppo_iteration(env_step, obs, pol, opt, n_steps, n_envs, hp["gamma"], hp["lmbda"],
+                                        obs_transform=tf, **kw)
+            return obs
+        return iteration, pool[0]
     if name == "boxworld":
         env = obw.BoxWorldOracle(n_envs, hp["grid_size"], hp["goal_length"], hp["num_distractor"],
                                  hp["distractor_length"], max_steps=hp["max_steps"], start_seed=6033, n_levels=500)
@@ -436,9 +605,12 @@ def _cpu_setup(name, n_envs, n_steps):
     return iteration, obs0
 
 
+CPU_SAMPLE = {"boxworld": (256, 64), "cartpole": (256, 256), "procgen": (16, 32)}   # bounded (n_envs, n_steps)
+
+
 def cpu_baseline(name, budget_s=20.0, steps=None):
     """Time the oracle port on the host cores on a bounded sample of the same workload."""
-    n_envs, n_steps = (256, 64) if name == "boxworld" else (256, 256)
+    n_envs, n_steps = CPU_SAMPLE[name]
     iteration, obs = _cpu_setup(name, n_envs, n_steps)
     obs = iteration(obs)                     # warm-up
     t0, k = time.perf_counter(), 0
@@ -459,8 +631,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    hp = WORKLOADS[args.workload]
-    n_envs, n_steps = (256, 64) if args.workload == "boxworld" else (256, 256)
+    n_envs, n_steps = CPU_SAMPLE[args.workload]
     iteration, obs = _cpu_setup(args.workload, n_envs, n_steps)
     for _ in range(max(1, min(args.warmup, 2))):
         obs = iteration(obs)
@@ -500,6 +671,8 @@ def main():
         print(json.dumps(kernel_rooflines(peaks(), "cuda:0")))
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "procgen":
+        run_procgen(args)
     else:
         run_ours(args)
 

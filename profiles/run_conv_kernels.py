@@ -20,9 +20,12 @@ def pair(x):
     return hi, x - hi
 
 
-def main():
-    only = sys.argv[1] if len(sys.argv) > 1 else None      # forward | dgrad | wgrad: 3 plain launches (ncu: -s 2 -c 1)
-    B, H, W, Cc = 2048, 32, 32, 16
+SHAPE = dict(B=2048, H=32, W=32, C=16)
+
+
+def time_forms(only=None):
+    """Graph-timed duration (us) of each convolution form; with `only`, three plain launches of that form (ncu)."""
+    B, H, W, Cc = SHAPE["B"], SHAPE["H"], SHAPE["W"], SHAPE["C"]
     rows = B * H * W
     torch.manual_seed(0)
     x = pair(torch.randn(B, H, W, Cc, device="cuda").clamp_min(0))
@@ -78,6 +81,14 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / 10 * 1e3
+    return res
+
+
+def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None      # forward | dgrad | wgrad: 3 plain launches (ncu: -s 2 -c 1)
+    res = time_forms(only)
+    B, H, W, Cc = SHAPE["B"], SHAPE["H"], SHAPE["W"], SHAPE["C"]
+    rows = B * H * W
     flops = 2.0 * rows * Cc * 9 * Cc
     act_bytes = rows * Cc * 4
     for name, us in res.items():
