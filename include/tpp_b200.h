@@ -10,7 +10,7 @@
  * cites the reference *function* it replaces (path:line under the reference root).
  *
  * Layouts:
- *   vector observations  : feature-major ("SoA") float32  obs[T+1][n_obs][ld]   (ld >= N envs, ld % 4 == 0)
+ *   vector observations  : feature-major ("SoA") float32  obs[T+1][n_obs][ld]   (ld >= N envs, ld % 32 == 0)
  *   image observations   : uint8 NHWC                     frame[T+1][N][H][W][3]
  *   per-step scalars     : [T][N] row-major (act int32, logp/rew/value/adv/ret float32, done uint8)
  */
