@@ -261,15 +261,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work items (tile, k-split) are flattened on grid.x (n tile fastest, then m tile, then split), so M is not limited
   // by the 65535 bound of grid.y.  A persistent CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...
-  const int wstride = NARROW ? (int)gridDim.x : p.total_work;
-  const bool probe = p.dbg && blockIdx.x == 0 && lane == 0;
+  // Wide tiles: one work item per CTA on a (n tile, m tile, split) grid -- no index arithmetic on the critical path.
+  const int wbegin = NARROW ? (int)blockIdx.x : 0, wend = NARROW ? p.total_work : 1;
+  const int wstride = NARROW ? (int)gridDim.x : 1;
+  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + bk - 1) / bk;
 #define TPP_DECODE_WORK(w)                                                           \
-  const int tile_ = (w) % p.ntiles, split_ = (w) / p.ntiles;                         \
-  const int m0 = (tile_ / p.ntn) * BLOCK_M, n0 = (tile_ % p.ntn) * BLOCK_N;          \
-  const int kb0 = split_ * p.kb_per_split;                                           \
+  int m0, n0, kb0;                                                                   \
+  if (NARROW) {                                                                      \
+    /* (divisions only when there is something to divide: the common conv / head case is ntn == 1, no split) */ \
+    const int split_ = p.total_work == p.ntiles ? 0 : (w) / p.ntiles;               \
+    const int tile_ = (w) - split_ * p.ntiles;                                       \
+    const int mt_ = p.ntn == 1 ? tile_ : tile_ / p.ntn;                              \
+    m0 = mt_ * BLOCK_M;                                                              \
+    n0 = (tile_ - mt_ * p.ntn) * BLOCK_N;                                            \
+    kb0 = split_ * p.kb_per_split;                                                   \
+  } else {                                                                           \
+    m0 = (int)blockIdx.y * BLOCK_M;                                                  \
+    n0 = (int)blockIdx.x * BLOCK_N;                                                  \
+    kb0 = (int)blockIdx.z * p.kb_per_split;                                          \
+  }                                                                                  \
   const int nkb = min(p.kb_per_split, total_kb - kb0);
 
   if (warp == 0 && lane == 0) {
@@ -297,7 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
      int it = 0;                                   // k-blocks issued so far (stage ring position across work items)
-     for (int w = blockIdx.x; w < p.total_work; w += wstride) {
+     for (int w = wbegin; w < wend; w += wstride) {
       TPP_DECODE_WORK(w)
       int cw = 0, ch = 0, cn = 0;
       if (NARROW && p.conv_W && !p.conv_wgrad) {   // base pixel of this tile in bounding-box coordinates
@@ -348,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     int it = 0, acc_i = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += wstride, ++acc_i) {
+    for (int w = wbegin; w < wend; w += wstride, ++acc_i) {
      TPP_DECODE_WORK(w)
      (void)m0; (void)n0; (void)kb0;
      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_i & 1) * ACC_COLS;
@@ -413,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int j = 0; j < 4; ++j) cs_run[j] = 0.0f;
     }
     int cs_n = -1;
-    for (int w = blockIdx.x; w < p.total_work; w += wstride, ++acc_i) {
+    for (int w = wbegin; w < wend; w += wstride, ++acc_i) {
     TPP_DECODE_WORK(w)
     (void)kb0;
     const int mrow0 = m0 + quarter * 32;
@@ -898,6 +911,11 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (grid_x > resident) grid_x = resident;
   }
   dim3 grid(grid_x, 1, 1);
+  if (!NARROW) {
+    const int ntm = (g->M + BLOCK_M - 1) / BLOCK_M;
+    if (ntm > 65535) return TPP_ENOTSUP;
+    grid = dim3((unsigned)p.ntn, (unsigned)ntm, (unsigned)split_k);
+  }
   gemm_tc_kernel<BLOCK_N><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
