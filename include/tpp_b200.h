@@ -157,11 +157,14 @@ int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t ld, int32_
                    const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
                    const float* ret, const float* adv, const uint8_t* done, float* out_obs, float* out_obs_lo,
                    int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value, float* out_ret,
-                   float* out_adv, float* out_done, void* stream);
+                   float* out_adv, float* out_done, int32_t raw, void* stream);
+/* raw != 0 (out_obs_lo must be NULL): out_obs receives the integer pixel values 0..255 as float32 (exact in TF32, so
+ * the tensor-core policy needs no lo half: TPP_TC_A_EXACT) and the consumer folds ScaledFloatFrame's 1/255 into its
+ * first layer's weights.                                                                                       */
 
 /* uint8 NHWC frames of one rollout slot -> float32 NCHW/255 rows [N][ld_out] (policy input at rollout).   */
 int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
-                      float* out_obs_lo, int32_t ld_out, void* stream);
+                      float* out_obs_lo, int32_t ld_out, int32_t raw, void* stream);
 
 /* ---- policy: dense layers ------------------------------------------------------------------------------ */
 /* C[m][n] (+)= epilogue( sum_k A(m,k) * B(n,k) ), fp32 in / fp32 accumulate, generic strides:
@@ -222,7 +225,12 @@ typedef struct {
                                             weight gradient: out[tap*32 + c][n] += sum_p X[p + tap][c] * dY[p][n] with
                                             M = 288, K = conv_B*conv_H*conv_W pixels, B = dY [K][ldb] MN-major
                                             (a_mn = b_mn = 1, TPP_EPI_ACCUM, any split_k).                          */
+  float alpha; int32_t _reserved;          /* TPP_EPI_ACCUM: out += alpha * product (0 means 1)                      */
 } tpp_tc_gemm;
+/* precision: 1 = single-pass TF32, 3 = 3xTF32; with 3, | TPP_TC_A_EXACT / TPP_TC_B_EXACT declares that operand exactly
+ * representable in TF32 (e.g. integer pixel values 0..255): it has no lo half (a_lo / b_lo unused, not loaded) and the
+ * pass that would multiply it is skipped -- two passes, 3/4 of the operand traffic.                                */
+enum { TPP_TC_A_EXACT = 16, TPP_TC_B_EXACT = 32 };
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
 /* Backward of the policy/value heads ([nh = A+1 <= 16][H] weights) in one kernel: from dhead [mb][ld_head]

@@ -161,3 +161,43 @@ def test_split_k_atomic_accumulation(split_k, mn):
     want, scale = _ref(a, b)
     err = (out.double().cpu() - (base.double().cpu() + want)).abs() / scale
     assert err.max() < (2e-6 if split_k > 1 else 8e-6)       # unsplit: 8192-term fp32 accumulation
+
+
+@pytest.mark.parametrize("which", ["a", "b"])
+@pytest.mark.parametrize("M,N,K,mn", [(256, 128, 588, False), (130, 70, 100, False), (64, 588, 512, True)])
+def test_exact_operand_two_pass_mode(which, M, N, K, mn):
+    """TPP_TC_A_EXACT / TPP_TC_B_EXACT: the operand holds integer pixel values 0..255 (exact in TF32); its lo half is
+    neither passed nor loaded and the result still matches float64 to fp32 grade.  MN-major case = the first layer's
+    weight gradient (contraction over samples, alpha = 1/255 folded into the atomic accumulation)."""
+    from tpp_b200 import _lib
+    g0 = torch.Generator(device="cuda").manual_seed(M * 3 + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g0)
+    b = torch.randn(N, K, device="cuda", generator=g0)
+    pix = lambda t: torch.randint(0, 256, t.shape, device="cuda", generator=g0).float()
+    if which == "a":
+        a = pix(a)
+    else:
+        b = pix(b)
+    a_hi, a_lo, lda = _operand(a, mn)
+    b_hi, b_lo, ldb = _operand(b, mn)
+    assert (a_lo if which == "a" else b_lo).abs().max() == 0          # really exact
+    ldc = (N + 3) // 4 * 4
+    out = torch.zeros(M, ldc, device="cuda")
+    g = _lib.TcGemm()
+    g.a_hi, g.lda, g.b_hi, g.ldb = a_hi.data_ptr(), lda, b_hi.data_ptr(), ldb
+    if which == "a":
+        g.b_lo = b_lo.data_ptr()
+    else:
+        g.a_lo = a_lo.data_ptr()
+    g.a_mn = g.b_mn = int(mn)
+    g.M, g.N, g.K = M, N, K
+    g.precision = 3 | (_lib.TC_A_EXACT if which == "a" else _lib.TC_B_EXACT)
+    g.split_k, g.flags, g.out, g.ldc = (4 if mn else 1), (_lib.EPI_ACCUM if mn else 0), out.data_ptr(), ldc
+    g.alpha = 1.0 / 255.0 if mn else 0.0
+    _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want, scale = _ref(a, b)
+    if mn:
+        want, scale = want / 255.0, scale / 255.0
+    err = (out[:, :N].double().cpu() - want).abs() / scale
+    assert err.max() < 2e-6, f"max scaled err {err.max():.3e}"

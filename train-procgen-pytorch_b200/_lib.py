@@ -54,10 +54,12 @@ class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
                 ("bias", C.c_void_p), ("mask", C.c_void_p), ("ld_mask", C.c_int64),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
                 ("colsum", C.c_void_p), ("dbg", C.c_void_p), ("addend", C.c_void_p), ("ld_add", C.c_int64),
-                ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32)]
+                ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32),
+                ("alpha", C.c_float), ("_reserved", C.c_int32)]
 
 
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}
+TC_A_EXACT, TC_B_EXACT = 16, 32
 EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM, EPI_ADD, EPI_RELU_OUT, EPI_PAIR_RELU = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
@@ -79,8 +81,8 @@ SIGNATURES = {
     "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],
     "tpp_gather_img": [_vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
-                       _vp, _vp, _vp, _vp, _vp, _vp],
-    "tpp_frames_to_obs": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp],
+                       _vp, _vp, _vp, _vp, _vp, _i32, _vp],
+    "tpp_frames_to_obs": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp],
     "tpp_gemm_f32": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "tpp_colsum_accum": [_vp, _i64, _i32, _i32, _vp, _vp],
     "tpp_gemm_tc": [C.POINTER(TcGemm), _vp],

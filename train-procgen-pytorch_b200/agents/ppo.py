@@ -136,7 +136,10 @@ class PPO(BaseAgent):
             if self.matmul == "fp32":
                 self.engine = MLPEngine(policy, self.n_actions)
             else:
-                self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1)
+                # image observations reach the first layer as integer pixel values (exact in TF32: no lo half, two
+                # MMA passes) with ScaledFloatFrame's 1/255 folded into the layer's weight copy
+                self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1,
+                                          raw_pixels=bool(getattr(storage, "is_image", False)))
         elif isinstance(policy.embedder, ImpalaModel) and self.matmul in ("tf32x3", "tf32") \
                 and not fs_coef:
             # IMPALA convolutions as im2col + tcgen05 GEMM (hand-written path)
@@ -171,20 +174,20 @@ class PPO(BaseAgent):
             c, h, w = storage.obs_shape
             mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
             _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot), N, h, w, c, _lib.ptr(mb.obs), _lib.ptr(mb.obs_lo),
-                      mb.ld_obs, _lib.stream_ptr())
+                      mb.ld_obs, 1 if mb.raw else 0, _lib.stream_ptr())
             self.n_launches += 1
-            return self._fwd(mb.obs, N, x_lo=mb.obs_lo)
+            return self._fwd(mb.obs, N, x_lo=mb.obs_lo, raw=mb.raw)
         return self._fwd(obs_slot, N, feature_major_ld=storage.ld)
 
     def _obs_buf_args(self, storage):
         """(row stride, split) of gathered-observation buffers: the TC engine wants TF32 pairs with ld = ceil32(in)."""
         if isinstance(self.engine, MLPEngineTC):
-            return self.engine.ld_in, True
+            return self.engine.ld_in, ("raw" if self.engine.raw_pixels and storage.is_image else True)
         return _round4(storage.obs_width), False
 
-    def _fwd(self, x, M, feature_major_ld=None, x_lo=None):
+    def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False):
         if isinstance(self.engine, MLPEngineTC):
-            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False)
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False, raw=raw)
         return self.engine.forward(x, M, feature_major_ld=feature_major_ld)
 
     def _sample(self, head, N, act, logp, value, t_offset, greedy=False):
@@ -254,8 +257,8 @@ class PPO(BaseAgent):
             st.gather(self._idx_cur, buf)
             if is_torch_engine or isinstance(engine, ImpalaEngineTC):
                 head = engine.forward(buf.obs, mb, train=True)
-            elif buf.obs_lo is not None:
-                head = engine.forward(buf.obs, mb, x_lo=buf.obs_lo)
+            elif buf.obs_lo is not None or buf.raw:
+                head = engine.forward(buf.obs, mb, x_lo=buf.obs_lo, raw=buf.raw)
             else:
                 head = engine.forward(buf.obs, mb)
             ws_dhead = engine._workspace(mb).dhead if not is_torch_engine else self._dhead(mb)

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
+from .._lib import TC_A_EXACT, TC_B_EXACT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -191,10 +191,15 @@ class MLPEngineTC(MLPEngine):
     the CUDA-core kernel: they are < 1 % of the FLOPs.
     """
 
-    def __init__(self, policy, n_actions, precision=3):
+    def __init__(self, policy, n_actions, precision=3, raw_pixels=False):
         super().__init__(policy, n_actions)
         assert precision in (1, 3)
         self.precision = precision
+        # raw_pixels: image observations may arrive as integer pixel values 0..255 (``forward(..., raw=True)``).  They are
+        # exact in TF32, so the first layer needs no lo half of X (two MMA passes, 3/4 of the operand traffic, half the
+        # gather's writes); ScaledFloatFrame's 1/255 (common/env/procgen_wrappers.py:407-419) lives in a second copy of
+        # the first layer's weights and in the ``alpha`` of its weight-gradient GEMM.
+        self.raw_pixels = raw_pixels
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
         for (w_off, b_off, fin, fout, relu) in self.layers:
@@ -203,6 +208,10 @@ class MLPEngineTC(MLPEngine):
         nh = n_actions + 1
         self.wh = dict(hi=torch.zeros(nh, self.latent, **f), lo=torch.zeros(nh, self.latent, **f))
         self.ld_in = self.w[0]["ldk"]          # row stride the gathered observations must have
+        if raw_pixels:
+            fin, fout, ldk = self.layers[0][2], self.layers[0][3], self.w[0]["ldk"]
+            self.w0_scaled = torch.zeros(fout, fin, **f)
+            self.w0_raw = dict(hi=torch.zeros(fout, ldk, **f), lo=torch.zeros(fout, ldk, **f), ldk=ldk)
         self.refresh_weights()
 
     # ------------------------------------------------------------------------------------------
@@ -215,6 +224,12 @@ class MLPEngineTC(MLPEngine):
         _lib.call("tpp_split_tf32", self._p(self.head_w_off), self.latent, self.A + 1, self.latent,
                   _lib.ptr(self.wh["hi"]), _lib.ptr(self.wh["lo"]), self.latent, None, None, 0, s)
         self.n_launches += len(self.layers) + 1
+        if self.raw_pixels:
+            w_off, _, fin, fout, _ = self.layers[0]
+            torch.mul(self.flat[w_off:w_off + fout * fin].view(fout, fin), 1.0 / 255.0, out=self.w0_scaled)
+            _lib.call("tpp_split_tf32", _lib.ptr(self.w0_scaled), fin, fout, fin, _lib.ptr(self.w0_raw["hi"]),
+                      _lib.ptr(self.w0_raw["lo"]), self.w0_raw["ldk"], None, None, 0, s)
+            self.n_launches += 1
 
     def _workspace(self, M):
         ws = self._ws.get(M)
@@ -235,12 +250,15 @@ class MLPEngineTC(MLPEngine):
         return ws
 
     def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
-            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0, conv=None, conv_wgrad=0):
+            out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0, conv=None, conv_wgrad=0,
+            exact=0, alpha=0.0):
         g = _lib.TcGemm()
         g.a_hi, g.a_lo, g.lda = a[0].data_ptr(), a[1].data_ptr(), lda
         g.b_hi, g.b_lo, g.ldb = b[0].data_ptr(), b[1].data_ptr(), ldb
         g.M, g.N, g.K, g.a_mn, g.b_mn = M, N, K, a_mn, b_mn
-        g.precision, g.split_k, g.flags, g.block_n = self.precision, split_k, flags, block_n
+        g.precision, g.split_k, g.flags, g.block_n = self.precision | (exact if self.precision == 3 else 0), split_k, \
+            flags, block_n
+        g.alpha = alpha
         if bias is not None:
             g.bias = bias.value
         if mask is not None:
@@ -261,9 +279,10 @@ class MLPEngineTC(MLPEngine):
         self.n_launches += 1
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True):
-        """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given), or with
-        ``feature_major_ld`` a feature-major [in_dim, ld] rollout slot."""
+    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False):
+        """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given, or -- ``raw`` --
+        integer pixel values 0..255 with row stride ``ld_in``), or with ``feature_major_ld`` a feature-major
+        [in_dim, ld] rollout slot."""
         ws, s = self._workspace(M), _lib.stream_ptr()
         L = len(self.layers)
         if feature_major_ld:
@@ -275,6 +294,9 @@ class MLPEngineTC(MLPEngine):
                       None, None, 0, s)
             self.n_launches += 1
             cur, ld_cur, a_mn = ws.fm, ld, 1
+        elif raw:
+            assert self.raw_pixels
+            cur, ld_cur, a_mn = (x, x), x.stride(0), 0      # exact operand: the lo half is never loaded
         elif x_lo is not None:
             cur, ld_cur, a_mn = (x, x_lo), x.stride(0), 0
         else:
@@ -282,13 +304,14 @@ class MLPEngineTC(MLPEngine):
                       _lib.ptr(ws.x["lo"]), self.ld_in, None, None, 0, s)
             self.n_launches += 1
             cur, ld_cur, a_mn = (ws.x["hi"], ws.x["lo"]), self.ld_in, 0
-        self._x_pair, self._x_ld = (cur, ld_cur), None
+        self._x_pair, self._x_ld, self._x_raw = (cur, ld_cur), None, raw
         for i in range(L):
             w_off, b_off, fin, fout, relu = self.layers[i]
-            h, w = ws.h[i], self.w[i]
+            h, w = ws.h[i], (self.w0_raw if raw and i == 0 else self.w[i])
             self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
                      flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
-                     out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"])
+                     out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
+                     exact=TC_A_EXACT if raw and i == 0 else 0)
             cur, ld_cur, a_mn = (h["hi"], h["lo"]), h["ld"], 0
         self._tc(cur, ld_cur, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
                  bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
@@ -329,8 +352,10 @@ class MLPEngineTC(MLPEngine):
             inp, ld_inp = ((ws.h[i - 1]["hi"], ws.h[i - 1]["lo"]), ws.h[i - 1]["ld"]) if i > 0 else (x_pair, x_ld)
             # gW[fout, fin] += dZ^T X : both operands MN-major, contraction over the M samples split across CTAs
             tiles = _ceil(fout, 128) * _ceil(fin, 128)
+            raw0 = i == 0 and self._x_raw         # gW1 = (1/255) dZ^T X_pixels, X exact: no lo half, two passes
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                     out=self._g(w_off), ldc=fin, split_k=max(1, min(_ceil(M, 32), _ceil(148, tiles))), block_n=128)
+                     out=self._g(w_off), ldc=fin, split_k=max(1, min(_ceil(M, 32), _ceil(148, tiles))), block_n=128,
+                     exact=TC_B_EXACT if raw0 else 0, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
                 nxt, w, prev = ws.dz[cur ^ 1], self.w[i], ws.h[i - 1]

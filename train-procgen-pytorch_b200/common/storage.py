@@ -28,10 +28,13 @@ class MiniBatch:
     """Device buffers of one gathered minibatch (reused between minibatches: no allocation in the loop)."""
 
     def __init__(self, mb, obs_width, ld_obs, device, split=False):
+        """split: False = plain fp32 observations; True = TF32 pair (obs = hi, obs_lo = lo) for the tensor-core policy;
+        "raw" (image observations only) = the integer pixel values 0..255 as fp32, exact in TF32, no lo half."""
         f = dict(dtype=torch.float32, device=device)
         self.mb, self.obs_width, self.ld_obs = mb, obs_width, ld_obs
+        self.raw = split == "raw"
         self.obs = torch.zeros(mb, ld_obs, **f)
-        self.obs_lo = torch.zeros(mb, ld_obs, **f) if split else None   # TF32 pair (obs = hi) for the TC policy
+        self.obs_lo = torch.zeros(mb, ld_obs, **f) if split is True else None
         self.act = torch.zeros(mb, dtype=torch.int32, device=device)
         self.logp, self.value, self.ret, self.adv, self.done = (torch.zeros(mb, **f) for _ in range(5))
 
@@ -234,8 +237,9 @@ class Storage:
         if self.is_image:
             c, h, w = self.obs_shape
             _lib.call("tpp_gather_img", _lib.ptr(idx_row), out.mb, N, self.ld, h, w, c, _lib.ptr(self.frames), *scal,
-                      _lib.ptr(out.obs), _lib.ptr(out.obs_lo), out.ld_obs, *outs, s)
+                      _lib.ptr(out.obs), _lib.ptr(out.obs_lo), out.ld_obs, *outs, 1 if out.raw else 0, s)
         else:
+            assert not out.raw, "raw pixel mode is for image observations"
             _lib.call("tpp_gather_vec", _lib.ptr(idx_row), out.mb, N, self.ld, self.obs_width, _lib.ptr(self.obs_fm),
                       *scal, _lib.ptr(out.obs), _lib.ptr(out.obs_lo), out.ld_obs, *outs, s)
         self.n_launches += 1

@@ -56,6 +56,10 @@ constexpr int stg_bytes(int block_n) { return epi_warps(block_n) * 32 * STG_PITC
 struct Params {
   int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
   int npass;                   // 1 (tf32) or 3 (3xTF32)
+  int nops_a, nops_b;          // operand copies staged per k-block: 2 = (hi, lo), 1 = hi only (single pass, or the
+                               // operand is exact in TF32 -- e.g. integer pixel values -- and has no lo half)
+  int skip;                    // bit `pass` set: that pass is not issued (2: a_lo*b_hi, 1: a_hi*b_lo)
+  float alpha;                 // scale of the atomically accumulated product (TPP_EPI_ACCUM)
   int stages;
   int kb_per_split;            // k-blocks handled by one blockIdx.z
   int bar_offset;              // byte offset of the mbarriers behind the stage / staging region
@@ -248,10 +252,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int nops = p.npass == 3 ? 2 : 1;
+  const int nops_a = p.nops_a, nops_b = p.nops_b;
   const int bk = NARROW ? p.bk : BLOCK_K;
   const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : BLOCK_N * BLOCK_K * 4;
-  const int stage_bytes = (A_BYTES + B_BYTES) * nops;
+  const int stage_bytes = A_BYTES * nops_a + B_BYTES * nops_b;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;      // [2]: accumulator i complete (MMA -> epilogue)
@@ -322,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // weight-gradient form: this M tile covers filter taps tap0 .. tap0 + ntaps - 1 (32 channel slots each)
       const int tap0 = (m0 / BLOCK_M) * (BLOCK_M / 32);
       const int ntaps = min(BLOCK_M / 32, 9 - tap0);
-      const uint32_t tx = (NARROW && p.conv_wgrad) ? (uint32_t)((ntaps * 4096 + p.b_tx) * nops) : (uint32_t)p.tx_bytes;
+      const uint32_t tx = (NARROW && p.conv_wgrad) ? (uint32_t)(ntaps * 4096 * nops_a + p.b_tx * nops_b) : (uint32_t)p.tx_bytes;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
@@ -334,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
         // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
         // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
-        for (int o = 0; o < nops; ++o) {
+        for (int o = 0; o < nops_a; ++o) {
           const CUtensorMap* tmA = o ? &tmA_lo : &tmA_hi;
           uint8_t* dst = st + o * A_BYTES;
           if (NARROW && p.conv_wgrad) {
@@ -350,8 +354,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else {
             tma_load_2d(tmA, full_bar + s, dst, kc, m0);
           }
+        }
+        for (int o = 0; o < nops_b; ++o) {
           const CUtensorMap* tmB = o ? &tmB_lo : &tmB_hi;
-          uint8_t* dstb = st + A_BYTES * nops + o * B_BYTES;
+          uint8_t* dstb = st + A_BYTES * nops_a + o * B_BYTES;
           if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
           else tma_load_2d(tmB, full_bar + s, dstb, kc, n0);
         }
@@ -378,17 +384,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
         const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + A_BYTES * nops;
+        const uint32_t b_hi = a_hi + A_BYTES * nops_a;
         const uint32_t b_lo = b_hi + B_BYTES;
         // small terms first, then hi*hi
+        bool first = kb == 0;                       // the first MMA of a work item overwrites the accumulator
         for (int pass = p.npass - 1; pass >= 0; --pass) {
+          if ((p.skip >> pass) & 1) continue;
           const uint32_t a = (pass == 2) ? a_lo : a_hi;
           const uint32_t b = (pass == 1) ? b_lo : b_hi;
           const int ksteps = bk / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             if (NARROW && k >= ksteps) break;
-            const uint32_t acc = (kb > 0 || pass != p.npass - 1 || k > 0) ? 1u : 0u;
+            const uint32_t acc = first ? 0u : 1u;
+            first = false;
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
             const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, bk);
             const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, bk);
@@ -542,6 +551,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (atomic) {
           if (nkb > 0) {
             float* dst = p.out + off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] *= p.alpha;
             if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]),
                            "f"(x[3])
@@ -800,7 +811,9 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
 template <int BLOCK_N>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-  const int npass = g->precision == 3 ? 3 : 1;
+  const int npass = (g->precision & 15) == 3 ? 3 : 1;
+  const bool a_exact = npass == 3 && (g->precision & 16), b_exact = npass == 3 && (g->precision & 32);
+  const int nops_a = (npass == 3 && !a_exact) ? 2 : 1, nops_b = (npass == 3 && !b_exact) ? 2 : 1;
   if (BLOCK_N > 32 && ((g->flags & (F_ADD | F_RELU_OUT | F_PAIR_RELU)) || g->conv_C > 0))
     return TPP_ENOTSUP;   // residual / ReLU-pair epilogues and convolution mode are compiled into the narrow tiles only
   int rc, a_bytes = A_BYTES, b_bytes = BLOCK_N * BLOCK_K * 4;
@@ -817,22 +830,28 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
       a_bytes = BLOCK_M * bk * 4;
     }
     if ((rc = make_map_im2col(&tmA_hi, g->a_hi, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk))) return rc;
-    if (npass == 3 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk)))
+    if (nops_a == 2 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk)))
       return rc;
   } else if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
   if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
-  if (npass == 3) {
+  if (nops_a == 2) {
     if (!conv && (rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
-    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
   } else {
     tmA_lo = tmA_hi;
+  }
+  if (nops_b == 2) {
+    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
+  } else {
     tmB_lo = tmB_hi;
   }
   Params p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.npass = npass; p.flags = g->flags;
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
   p.addend = g->addend; p.ld_add = g->ld_add;
-  p.tx_bytes = (a_bytes + b_bytes) * (npass == 3 ? 2 : 1);
+  p.nops_a = nops_a; p.nops_b = nops_b;
+  p.skip = (a_exact ? 4 : 0) | (b_exact ? 2 : 0);
+  p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
+  p.tx_bytes = a_bytes * nops_a + b_bytes * nops_b;
   p.conv_W = conv ? g->conv_W : 0; p.conv_HW = conv ? g->conv_H * g->conv_W : 0;
   p.conv_wgrad = wgrad; p.b_tx = b_bytes;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
@@ -848,7 +867,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   // left unfilled (their products land in accumulator rows / columns that are never stored)
   p.a_slot = BLOCK_M * bk * 4;
   p.b_slot = BLOCK_N * bk * 4;
-  const int stage_bytes = (p.a_slot + p.b_slot) * (npass == 3 ? 2 : 1);
+  const int stage_bytes = p.a_slot * nops_a + p.b_slot * nops_b;
   int stages = (224 * 1024 - 1024 - 256 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
   if (stages < 1) return TPP_ENOTSUP;
   if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
@@ -925,7 +944,8 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
 
 extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
   TPP_CHECK_ARG(g && g->a_hi && g->b_hi && g->M > 0 && g->N > 0 && g->K > 0);
-  TPP_CHECK_ARG(g->precision == 1 || (g->precision == 3 && g->a_lo && g->b_lo));
+  TPP_CHECK_ARG((g->precision & ~48) == 1 || (g->precision & ~48) == 3);
+  TPP_CHECK_ARG((g->precision & 15) == 1 || ((g->a_lo || (g->precision & 16)) && (g->b_lo || (g->precision & 32))));
   const bool atomic = g->flags & tpp::tc::F_ATOMIC;
   TPP_CHECK_ARG(!atomic || g->out);
   TPP_CHECK_ARG(g->split_k <= 1 || atomic);

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t
                                                                    int64_t ld, int HW, int C,
                                                                    const uint8_t* __restrict__ frames, GatherScalars g,
                                                                    float* __restrict__ out_obs,
-                                                                   float* __restrict__ out_lo, int ld_out) {
+                                                                   float* __restrict__ out_lo, int ld_out, int raw) {
   extern __shared__ uint8_t px_all[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int k = blockIdx.x * (blockDim.x >> 5) + w;
@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t
     float v = 0.0f;
     if (o < bytes) {
       while (p >= HW) { p -= HW; ++c; }
-      v = (float)px[p * C + c] / 255.0f;
+      // raw: the integer pixel value itself (exact in TF32: no lo half; the policy folds 1/255 into its first layer)
+      v = raw ? (float)px[p * C + c] : (float)px[p * C + c] / 255.0f;
     }
     p += 32;
     if (dlo) {
@@ -239,7 +240,8 @@ extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t
                               const uint8_t* frames, const int32_t* act, const float* logp, const float* value,
                               const float* ret, const float* adv, const uint8_t* done, float* out_obs,
                               float* out_obs_lo, int32_t ld_out, int32_t* out_act, float* out_logp, float* out_value,
-                              float* out_ret, float* out_adv, float* out_done, void* stream) {
+                              float* out_ret, float* out_adv, float* out_done, int32_t raw, void* stream) {
+  TPP_CHECK_ARG(!(raw && out_obs_lo));
   TPP_CHECK_ARG(idx && frames && out_obs && mb > 0 && N > 0 && ld >= N && H > 0 && W > 0 && C > 0 &&
                 ld_out >= H * W * C);
   const int bytes = H * W * C;
@@ -247,18 +249,19 @@ extern "C" int tpp_gather_img(const int64_t* idx, int32_t mb, int32_t N, int64_t
   tpp::GatherScalars g{act, logp, value, ret, adv, done, out_act, out_logp, out_value, out_ret, out_adv, out_done};
   const int warps = tpp::gi_warps(bytes);
   tpp::gather_img_kernel<<<tpp_ceil_div(mb, warps), warps * 32, warps * ((bytes + 15) & ~15), tpp_stream(stream)>>>(
-      idx, mb, N, ld, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
+      idx, mb, N, ld, H * W, C, frames, g, out_obs, out_obs_lo, ld_out, raw);
   TPP_LAUNCH_STATUS();
 }
 
 extern "C" int tpp_frames_to_obs(const uint8_t* frames, int32_t N, int32_t H, int32_t W, int32_t C, float* out_obs,
-                                 float* out_obs_lo, int32_t ld_out, void* stream) {
+                                 float* out_obs_lo, int32_t ld_out, int32_t raw, void* stream) {
+  TPP_CHECK_ARG(!(raw && out_obs_lo));
   TPP_CHECK_ARG(frames && out_obs && N > 0 && ld_out >= H * W * C);
   const int bytes = H * W * C;
   TPP_CHECK_ARG(bytes <= 24 * 1024);
   tpp::GatherScalars g{};
   const int warps = tpp::gi_warps(bytes);
   tpp::gather_img_kernel<<<tpp_ceil_div(N, warps), warps * 32, warps * ((bytes + 15) & ~15), tpp_stream(stream)>>>(
-      nullptr, N, N, N, H * W, C, frames, g, out_obs, out_obs_lo, ld_out);
+      nullptr, N, N, N, H * W, C, frames, g, out_obs, out_obs_lo, ld_out, raw);
   TPP_LAUNCH_STATUS();
 }
