@@ -62,6 +62,10 @@ CASES = [
     ("head 8192x16x64", dict(M=8192, N=16, K=64, flags=1, pair=False, plain=True, block_n=16)),
     ("dgrad L4 8192x256x64", dict(M=8192, N=256, K=64, b_mn=1, flags=0, mask=True, colsum=True)),
     ("dgrad L3 8192x256x256", dict(M=8192, N=256, K=256, b_mn=1, flags=0, mask=True, colsum=True)),
+    ("dgrad L3, no colsum", dict(M=8192, N=256, K=256, b_mn=1, flags=0, mask=True, colsum=False)),
+    ("dgrad L3, no mask", dict(M=8192, N=256, K=256, b_mn=1, flags=0, mask=False, colsum=True)),
+    ("dgrad L3, neither", dict(M=8192, N=256, K=256, b_mn=1, flags=0)),
+    ("dgrad L3, neither, K-major B", dict(M=8192, N=256, K=256, b_mn=0, flags=0)),
     ("wgrad L1 256x588x8192", dict(M=256, N=588, K=8192, a_mn=1, b_mn=1, flags=8, split_k=15, block_n=128)),
     ("wgrad L2 256x256x8192", dict(M=256, N=256, K=8192, a_mn=1, b_mn=1, flags=8, split_k=37, block_n=128)),
     ("wgrad L4 64x256x8192", dict(M=64, N=256, K=8192, a_mn=1, b_mn=1, flags=8, split_k=74, block_n=128)),

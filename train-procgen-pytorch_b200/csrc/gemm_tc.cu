@@ -303,6 +303,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // wide tiles: per-CTA column sums are first combined in shared memory (behind the barriers), then flushed with one
+  // global atomic per column -- the 4 quarter-warps of 64 M tiles hitting the same 8 cache lines directly cost ~8 us
+  float* cs_sh = reinterpret_cast<float*>(smem + p.bar_offset + 256);
+  if (!NARROW && p.colsum)
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) cs_sh[i] = 0.0f;
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -645,10 +650,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (rr == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (lane_on && nc + j < p.N) atomicAdd(p.colsum + nc + j, cs4[j]);
+              if (lane_on && nc + j < p.N) atomicAdd(cs_sh + c + cc + j, cs4[j]);
           }
         }
       }
+    }
+    if (!NARROW && p.colsum && !atomic) {      // all epilogue warps of the CTA: combine, then one atomic per column
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");
+      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N) * 32)
+        if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, cs_sh[i]);
     }
     if (NARROW) {                       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
