@@ -252,7 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
-  const int nops_a = p.nops_a, nops_b = p.nops_b;
+  // (exact-operand modes exist on the wide tiles only: the narrow persistent kernels are sensitive to every extra
+  // instruction of their single-thread producer / MMA roles -- measured +9 % on the convolution tiles)
+  const int nops_a = NARROW ? (p.npass == 3 ? 2 : 1) : p.nops_a, nops_b = NARROW ? nops_a : p.nops_b;
   const int bk = NARROW ? p.bk : BLOCK_K;
   const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : BLOCK_N * BLOCK_K * 4;
   const int stage_bytes = A_BYTES * nops_a + B_BYTES * nops_b;
@@ -275,12 +277,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #define TPP_DECODE_WORK(w)                                                           \
   int m0, n0, kb0;                                                                   \
   if (NARROW) {                                                                      \
-    /* (divisions only when there is something to divide: the common conv / head case is ntn == 1, no split) */ \
-    const int split_ = p.total_work == p.ntiles ? 0 : (w) / p.ntiles;               \
-    const int tile_ = (w) - split_ * p.ntiles;                                       \
-    const int mt_ = p.ntn == 1 ? tile_ : tile_ / p.ntn;                              \
-    m0 = mt_ * BLOCK_M;                                                              \
-    n0 = (tile_ - mt_ * p.ntn) * BLOCK_N;                                            \
+    const int tile_ = (w) % p.ntiles, split_ = (w) / p.ntiles;                       \
+    m0 = (tile_ / p.ntn) * BLOCK_M;                                                  \
+    n0 = (tile_ % p.ntn) * BLOCK_N;                                                  \
     kb0 = split_ * p.kb_per_split;                                                   \
   } else {                                                                           \
     m0 = (int)blockIdx.y * BLOCK_M;                                                  \
@@ -306,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // wide tiles: per-CTA column sums are first combined in shared memory (behind the barriers), then flushed with one
   // global atomic per column -- the 4 quarter-warps of 64 M tiles hitting the same 8 cache lines directly cost ~8 us
   float* cs_sh = reinterpret_cast<float*>(smem + p.bar_offset + 256);
-  if (!NARROW && p.colsum)
+  if (p.colsum)
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) cs_sh[i] = 0.0f;
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -343,7 +342,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
         // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
         // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
-        for (int o = 0; o < nops_a; ++o) {
+        for (int o = 0; o < 2; ++o) {
+          if (o >= nops_a && o >= nops_b) break;
+          if (NARROW || o < nops_a) {
           const CUtensorMap* tmA = o ? &tmA_lo : &tmA_hi;
           uint8_t* dst = st + o * A_BYTES;
           if (NARROW && p.conv_wgrad) {
@@ -359,8 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else {
             tma_load_2d(tmA, full_bar + s, dst, kc, m0);
           }
-        }
-        for (int o = 0; o < nops_b; ++o) {
+          }
+          if (!NARROW && o >= nops_b) continue;
           const CUtensorMap* tmB = o ? &tmB_lo : &tmB_hi;
           uint8_t* dstb = st + A_BYTES * nops_a + o * B_BYTES;
           if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
@@ -394,14 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // small terms first, then hi*hi
         bool first = kb == 0;                       // the first MMA of a work item overwrites the accumulator
         for (int pass = p.npass - 1; pass >= 0; --pass) {
-          if ((p.skip >> pass) & 1) continue;
+          if (!NARROW && ((p.skip >> pass) & 1)) continue;
           const uint32_t a = (pass == 2) ? a_lo : a_hi;
           const uint32_t b = (pass == 1) ? b_lo : b_hi;
           const int ksteps = bk / UMMA_K;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             if (NARROW && k >= ksteps) break;
-            const uint32_t acc = first ? 0u : 1u;
+            const uint32_t acc = NARROW ? ((kb > 0 || pass != p.npass - 1 || k > 0) ? 1u : 0u) : (first ? 0u : 1u);
             first = false;
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
             const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, bk);
@@ -556,8 +557,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (atomic) {
           if (nkb > 0) {
             float* dst = p.out + off;
+            if (!NARROW) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] *= p.alpha;
+              for (int j = 0; j < 4; ++j) x[j] *= p.alpha;
+            }
             if (vec && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x[0]), "f"(x[1]), "f"(x[2]),
                            "f"(x[3])
@@ -666,14 +669,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (lane == 0) mbar_arrive(tmem_empty + (acc_i & 1));
     }
     }   // work items
-    if (NARROW && cs_n >= 0) {
+    if (NARROW && p.colsum && !atomic) {
+      // final flush of the running sums: the CTA's 4 epilogue warps combine in shared memory, one warp adds to global
+      if (cs_n >= 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = cs_run[j];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (rr == 0 && cc < GW && cs_n + cc + j < p.N) atomicAdd(p.colsum + cs_n + cc + j, v);
+        for (int j = 0; j < 4; ++j) {
+          float v = cs_run[j];
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (rr == 0 && cc < GW) atomicAdd(cs_sh + cc + j, v);
+        }
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");
+      if (ew == 0 && cs_n >= 0 && lane < GW && cs_n + lane < p.N) atomicAdd(p.colsum + cs_n + lane, cs_sh[lane]);
     }
   }
   if (warp == 2) TPP_PROBE(6);
@@ -822,6 +830,7 @@ template <int BLOCK_N>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const int npass = (g->precision & 15) == 3 ? 3 : 1;
+  if (BLOCK_N <= 32 && ((g->precision & 48) || (g->alpha != 0.0f && g->alpha != 1.0f))) return TPP_ENOTSUP;
   const bool a_exact = npass == 3 && (g->precision & 16), b_exact = npass == 3 && (g->precision & 32);
   const int nops_a = (npass == 3 && !a_exact) ? 2 : 1, nops_b = (npass == 3 && !b_exact) ? 2 : 1;
   if (BLOCK_N > 32 && ((g->flags & (F_ADD | F_RELU_OUT | F_PAIR_RELU)) || g->conv_C > 0))
