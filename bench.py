@@ -227,15 +227,22 @@ def gemm_roofline(agent, in_dim, hp, pk):
     algorithmic work), against the measured dense bf16 tensor peak.  Also reports the whole policy forward+backward
     (all its launches) in TFLOP/s."""
     from tpp_b200.common.engine import MLPEngineTC
-    from tpp_b200._lib import EPI_BIAS, EPI_RELU, ptr
+    from tpp_b200._lib import EPI_BIAS, EPI_RELU, TC_A_EXACT, ptr
     mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
     eng = agent.engine
     ld = (in_dim + 3) // 4 * 4
-    x = torch.randn(mb, ld, device=agent.policy.flat.device)[:, :in_dim]
+    raw = bool(getattr(eng, "raw_pixels", False))     # image observations reach layer 1 as integer pixel values
+    if raw:
+        x = torch.randint(0, 256, (mb, eng.ld_in), device=agent.policy.flat.device).float()
+    else:
+        x = torch.randn(mb, ld, device=agent.policy.flat.device)[:, :in_dim]
     dhead = torch.randn(mb, eng.ld_head, device=x.device) / mb
 
     def fb():
-        eng.forward(x, mb)
+        if raw:
+            eng.forward(x, mb, raw=True)
+        else:
+            eng.forward(x, mb)
         eng.backward(dhead, mb)
     dt_all = time_kernel(fb, iters=10)
     agent.policy.flat_grad.zero_()
@@ -244,10 +251,14 @@ def gemm_roofline(agent, in_dim, hp, pk):
     w_off, b_off, fin, fout, relu = eng.layers[0]
     ws = eng._workspace(mb)
     if isinstance(eng, MLPEngineTC):
-        w, h = eng.w[0], ws.h[0]
-        one = lambda: eng._tc((ws.x["hi"], ws.x["lo"]), eng.ld_in, (w["hi"], w["lo"]), w["ldk"], mb, fout, fin,
-                              flags=EPI_BIAS | EPI_RELU, bias=eng._p(b_off), out_pair=(h["hi"], h["lo"]), ldc=h["ld"])
-        name = "gemm_tc_kernel<128> (tcgen05 kind::tf32, %s)" % ("3xTF32" if eng.precision == 3 else "1xTF32")
+        w, h = (eng.w0_raw if raw else eng.w[0]), ws.h[0]
+        a = (x, x) if raw else (ws.x["hi"], ws.x["lo"])
+        one = lambda: eng._tc(a, eng.ld_in, (w["hi"], w["lo"]), w["ldk"], mb, fout, fin,
+                              flags=EPI_BIAS | EPI_RELU, bias=eng._p(b_off), out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
+                              exact=TC_A_EXACT if raw else 0)
+        name = "gemm_tc_kernel<128> (tcgen05 kind::tf32, %s%s)" % (
+            "3xTF32" if eng.precision == 3 else "1xTF32",
+            ", pixel operand exact in TF32: 2 of the 3 passes" if raw and eng.precision == 3 else "")
     else:
         one = lambda: eng._gemm(ptr(x), x.stride(0), 1, eng._p(w_off), fin, 1, ptr(ws.acts[0]), fout, eng._p(b_off),
                                 None, mb, fout, fin, EPI_BIAS | EPI_RELU)
