@@ -67,6 +67,10 @@ class FlatAdam:
 
     def step(self):
         self._sync_lr()
+        self.launch()
+
+    def launch(self):
+        """The two kernels of a step (capturable in a CUDA graph; ``_sync_lr`` must have run outside the capture)."""
         n, s = self.flat.numel(), _lib.stream_ptr()
         _lib.call("tpp_grad_sqnorm", _lib.ptr(self.state), _lib.ptr(self.gflat), n, s)
         _lib.call("tpp_adam_clip_step", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(self.gflat),
@@ -251,10 +255,12 @@ class PPO(BaseAgent):
         if hasattr(engine, "refresh_weights"):
             engine.refresh_weights()
 
-        def minibatch_body():
+        def minibatch_body(idx_row=None, stats_row=None):
             s = _lib.stream_ptr()          # evaluated here: under graph capture the current stream is the capture stream
-            self._stats_cur.zero_()
-            st.gather(self._idx_cur, buf)
+            idx_row = self._idx_cur if idx_row is None else idx_row
+            stats_row = self._stats_cur if stats_row is None else stats_row
+            stats_row.zero_()
+            st.gather(idx_row, buf)
             if is_torch_engine or isinstance(engine, ImpalaEngineTC):
                 head = engine.forward(buf.obs, mb, train=True)
             elif buf.obs_lo is not None or buf.raw:
@@ -270,7 +276,7 @@ class PPO(BaseAgent):
                 self.n_launches += 1
             _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
                       _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
-                      _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(self._stats_cur), s)
+                      _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(stats_row), s)
             self.n_launches += 1
             if is_torch_engine:
                 engine.backward(ws_dhead, mb, self.fs_coef)
@@ -281,6 +287,58 @@ class PPO(BaseAgent):
         use_graph = self.use_cuda_graph and not is_torch_engine
         graphs = self.__dict__.setdefault("_mb_graphs", {})
         k = 0
+        # Whole-epoch graph (single GPU, MLP engines): every minibatch of an epoch -- gather, forward, loss, backward --
+        # and the optimizer steps + weight re-splits at their fixed positions are ONE graph replay per epoch; the
+        # epoch's permutation is uploaded into a static index buffer first.  Removes ~400 graph launches, index copies
+        # and stats copies per iteration from the host's critical path.
+        step_every = int(accum) if float(accum).is_integer() else 0
+        epoch_graph = (use_graph and self.world_size == 1 and step_every > 0 and n_mb % step_every == 0
+                       and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0
+                       and self.entropy_scaling is None)
+        if epoch_graph:
+            if getattr(self, "_epoch_idx", None) is None or self._epoch_idx.shape != (n_mb, mb):
+                self._epoch_idx = torch.zeros(n_mb, mb, dtype=torch.int64, device=dev)
+                self._epoch_stats = torch.zeros(n_mb, 4 + 16, dtype=torch.float64, device=dev)
+            egraphs = self.__dict__.setdefault("_epoch_graphs", {})
+            ekey = (mb, n_mb, step_every, float(self.entropy_multiplier), id(st))
+
+            def epoch_body():
+                for i in range(n_mb):
+                    minibatch_body(self._epoch_idx[i], self._epoch_stats[i])
+                    if (i + 1) % step_every == 0:
+                        self.optimizer.launch()
+                        if hasattr(engine, "refresh_weights"):
+                            engine.refresh_weights()
+
+            def counts():
+                return (self.n_launches, self.engine.n_launches, self.storage.n_launches, self.optimizer.n_launches)
+
+            for _ in range(self.epoch):
+                self._epoch_idx.copy_(st.epoch_indices(mb))
+                self.optimizer._sync_lr()
+                entry = egraphs.get(ekey)
+                if entry is None:                      # first epoch ever: eager (allocates workspaces)
+                    epoch_body()
+                    egraphs[ekey] = "warm"
+                else:
+                    if entry == "warm":
+                        g = torch.cuda.CUDAGraph()
+                        torch.cuda.synchronize()
+                        c0 = counts()
+                        with torch.cuda.graph(g):
+                            epoch_body()
+                        delta = tuple(b - a for a, b in zip(c0, counts()))
+                        self.n_launches, self.engine.n_launches, self.storage.n_launches, \
+                            self.optimizer.n_launches = c0
+                        entry = egraphs[ekey] = (g, delta)
+                    entry[0].replay()
+                    self.n_launches += entry[1][0]
+                    self.engine.n_launches += entry[1][1]
+                    self.storage.n_launches += entry[1][2]
+                    self.optimizer.n_launches += entry[1][3]
+                self._stats[k:k + n_mb].copy_(self._epoch_stats)
+                k += n_mb
+            return self._summary(fs_vals)
         for _ in range(self.epoch):
             idx = st.epoch_indices(mb)
             for i in range(n_mb):
