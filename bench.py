@@ -127,7 +127,7 @@ def build_agent(name, hp, rank, device):
                             env.action_space.n).to(device).flatten_()
     st = Storage(obs_shape, hp["latent_size"], T, N, device)
     agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank,
-                matmul=hp.get("matmul", "tf32x3"))
+                matmul=hp.get("matmul", "tf32x3"), fuse_accum=hp.get("fuse_accum", "auto"))
     return agent, in_dim
 
 
@@ -229,6 +229,7 @@ def gemm_roofline(agent, in_dim, hp, pk):
     from tpp_b200.common.engine import MLPEngineTC
     from tpp_b200._lib import EPI_BIAS, EPI_RELU, TC_A_EXACT, ptr
     mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
+    mb *= getattr(agent, "group_size", 1)     # rows of one launch: the minibatches of an accumulation window share a pass
     eng = agent.engine
     ld = (in_dim + 3) // 4 * 4
     raw = bool(getattr(eng, "raw_pixels", False))     # image observations reach layer 1 as integer pixel values
@@ -287,7 +288,8 @@ def run_ours(args):
     device = f"cuda:{local}"
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    hp = dict(WORKLOADS[args.workload], matmul=args.matmul)
+    hp = dict(WORKLOADS[args.workload], matmul=args.matmul,
+              fuse_accum=args.fuse_accum if args.fuse_accum == "auto" else int(args.fuse_accum))
     agent, in_dim = build_agent(args.workload, hp, rank, device)
     if world > 1:
         agent.shard(world)
@@ -399,7 +401,8 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}_env_vec PPO: n_envs={N}/GPU, n_steps={T}, "
-                               f"epoch={hp['epoch']}, minibatch={mb}, MLP policy {in_dim}-256-256-256-64 ({args.matmul})",
+                               f"epoch={hp['epoch']}, minibatch={mb} (x{getattr(agent, 'group_size', 1)} per pass: "
+                               f"gradient-accumulation window), MLP policy {in_dim}-256-256-256-64 ({args.matmul})",
                    "parallelism": f"env-sharded dp{world}", "l2": "rollout + minibatch working set > L2 (inputs "
                    "larger than 126 MB)" if args.workload == "boxworld" else "small working set (latency-bound)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
@@ -673,6 +676,8 @@ def main():
     ap.add_argument("--workload", default="boxworld", choices=list(WORKLOADS))
     ap.add_argument("--matmul", default="tf32x3", choices=["tf32x3", "tf32", "fp32"],
                     help="dense-layer arithmetic: tcgen05 3xTF32 (fp32-parity, default), tcgen05 single TF32, CUDA-core fp32")
+    ap.add_argument("--fuse-accum", default="auto",
+                    help="minibatches of one gradient-accumulation window sharing a forward/backward pass (auto = all)")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs only)")
     ap.add_argument("--timed-region-only", action="store_true", help="stop after the device-timed loop (ncu runs)")

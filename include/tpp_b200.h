@@ -311,6 +311,14 @@ int tpp_ppo_loss_fwd_bwd(const tpp_loss_cfg* cfg, const float* head, int32_t ld_
                          const float* pbar, float* dhead, double* stats, void* stream);
 int tpp_ppo_pbar(const float* head, int32_t ld_head, int32_t mb, int32_t n_actions, float* pbar_sum,
                  void* stream);
+/* The same over `groups` consecutive minibatches of cfg->mb samples in one launch (head / per-sample arrays hold
+ * groups*mb rows): group g's loss terms are means over ITS mb samples and its sums go to stats + g*stats_stride.
+ * Used when the reference accumulates gradients over several minibatches before one optimizer step
+ * (agents/ppo.py:111,173-177: the weights do not change in between, so the minibatches can share one forward /
+ * backward pass).  groups > 1 needs mb % 256 == 0; x_entropy_coef must be 0.                                   */
+int tpp_ppo_loss_fwd_bwd_grouped(const tpp_loss_cfg* cfg, int32_t groups, const float* head, int32_t ld_head,
+                                 const int32_t* act, const float* old_logp, const float* old_value, const float* ret,
+                                 const float* adv, float* dhead, double* stats, int32_t stats_stride, void* stream);
 
 /* ---- optimizer ------------------------------------------------------------------------------------------ */
 typedef struct {

@@ -209,3 +209,68 @@ def test_predict_and_sampling_distribution():
     _close(value, np.full(50000, v.item()), rtol=1e-5, atol=1e-6)
     act2, *_ = agent.predict(obs, None, np.zeros(50000))
     assert (act2 != act).any()                                # the tick advances the stream between calls
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("matmul", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("image", [False, True])
+def test_accumulation_groups_match_oracle_and_unfused(matmul, image):
+    """Gradient accumulation (agents/ppo.py:111,173-177): the minibatches between two optimizer steps share one
+    gather / forward / loss / backward pass (``fuse_accum``).  Per-minibatch loss terms and the final parameters
+    must match the torch-CPU oracle, which runs them one by one, and the unfused engine path."""
+    from oracle import ppo as oppo
+    from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    from tpp_b200.common.storage import Storage
+    T, N, A = 16, 128, 4
+    obs_shape = (3, 6, 6) if image else (9,)
+    in_dim = int(np.prod(obs_shape))
+    kw = dict(n_steps=T, n_envs=N, epoch=2, n_minibatch=2, mini_batch_size=256, learning_rate=5e-4, entropy_coef=0.01,
+              gamma=0.99, lmbda=0.95, matmul=matmul)   # batch_size 1024 -> 4 minibatches accumulate per step
+    g = torch.Generator().manual_seed(7)
+    frames = torch.randint(0, 256, (T + 1, N, *obs_shape[1:], 3), generator=g, dtype=torch.uint8) if image else None
+    vec = torch.randn(T + 1, N, 9, generator=g)
+    rec = dict(act=torch.randint(0, A, (T, N), generator=g).int(), logp=-torch.rand(T, N, generator=g) * 2 - 0.5,
+               value=torch.randn(T + 1, N, generator=g) * 0.3, rew=torch.randn(T, N, generator=g),
+               done=(torch.rand(T, N, generator=g) < 0.1).to(torch.uint8))
+    results = {}
+    for fuse in ("auto", 2, 1):
+        torch.manual_seed(4)
+        pol = CategoricalPolicy(MLPModel(in_dim, 4, 64, 32), False, A).to("cuda").flatten_()
+        init = {k: v.detach().cpu().clone() for k, v in pol.state_dict().items()}
+        st = Storage(obs_shape, 32, T, N, "cuda")
+        agent = PPO(None, pol, None, st, "cuda", 0, fuse_accum=fuse, **kw)
+        if image:
+            st.frames.copy_(frames.cuda())
+        else:
+            st.obs_batch[:] = vec.cuda()
+        st.act_i32[:, :N], st.logp[:, :N], st.value[:, :N] = rec["act"].cuda(), rec["logp"].cuda(), rec["value"].cuda()
+        st.rew[:, :N], st.done_u8[:, :N] = rec["rew"].cuda(), rec["done"].cuda()
+        st.compute_estimates(0.99, 0.95, True, True)
+        torch.manual_seed(99)
+        summary = agent.optimize()
+        assert agent._group_size(4, 8, 256, agent.engine) == {"auto": 4, 2: 2, 1: 1}[fuse]
+        assert agent.optimizer.step_count == 2 * 2
+        results[fuse] = (summary, {k: v.detach().cpu() for k, v in pol.state_dict().items()},
+                         {k: np.array(v) for k, v in agent.last_stats.items()})
+    ref = oppo.OraclePolicy(oppo.OracleMLP(in_dim, 4, 64, 32), A)
+    ref.load_state_dict(init)
+    obs = (frames[:-1].permute(0, 1, 4, 2, 3).float() / 255.0) if image else vec[:-1]
+    data = dict(obs=obs.reshape(T * N, -1), act=st.act_batch.cpu().reshape(-1),
+                old_logp=st.log_prob_act_batch.cpu().reshape(-1), old_value=st.value_batch[:-1].cpu().reshape(-1),
+                ret=st.return_batch.cpu().reshape(-1), adv=st.adv_batch.cpu().reshape(-1))
+    opt = oppo.make_adam(ref, 5e-4)
+    torch.manual_seed(99)
+    logs = oppo.optimize(ref, opt, data, T, N, epoch=2, n_minibatch=2, mini_batch_size=256, grad_clip_norm=0.5,
+                         eps_clip=0.2, value_coef=0.5, entropy_coef=0.01)
+    assert len(logs) == 16                 # 8 minibatches per epoch, 4 per optimizer step
+    for fuse, (summary, params, stats) in results.items():
+        for key in ("pi_loss", "value_loss", "entropy", "total"):      # one entry per minibatch, in order
+            np.testing.assert_allclose(stats[key], [l[key] for l in logs], rtol=2e-4, atol=2e-5,
+                                       err_msg=f"fuse={fuse} {key}")
+        for (k, p), (_, q) in zip(params.items(), ref.state_dict().items()):
+            np.testing.assert_allclose(p.numpy(), q.numpy(), rtol=5e-3, atol=2e-5, err_msg=f"fuse={fuse} {k}")
+    for k in results[1][1]:                                            # fused vs unfused: only summation order differs
+        np.testing.assert_allclose(results["auto"][1][k].numpy(), results[1][1][k].numpy(), rtol=1e-4, atol=2e-6,
+                                   err_msg=k)

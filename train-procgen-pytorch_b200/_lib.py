@@ -97,6 +97,7 @@ SIGNATURES = {
     "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],
+    "tpp_ppo_loss_fwd_bwd_grouped": [C.POINTER(LossCfg), _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_grad_sqnorm": [_vp, _vp, _i64, _vp],
     "tpp_adam_clip_step": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
 }

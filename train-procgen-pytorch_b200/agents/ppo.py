@@ -129,6 +129,9 @@ class PPO(BaseAgent):
         self.adjust_lr = adjust_lr_grok if increasing_lr else adjust_lr
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", True))
         self.sample_seed = int(kwargs.get("sample_seed", 0))
+        # minibatches of one gradient-accumulation window processed as one pass ("auto" = all, int = cap, 1 = off)
+        self.fuse_accum = kwargs.get("fuse_accum", "auto")
+        self.max_group_rows = int(kwargs.get("max_group_rows", 1 << 18))
 
         if policy.flat is None:
             policy.flatten_(device)
@@ -231,81 +234,93 @@ class PPO(BaseAgent):
         if batch_size < self.mini_batch_size:
             self.mini_batch_size = batch_size
         accum = batch_size / self.mini_batch_size
-        cnt = 1
         mb = self.mini_batch_size
         n_mb = (st.num_steps * st.num_envs) // mb
         total = n_mb * self.epoch
         dev, A = self.policy.flat.device, self.n_actions
+        NS = 4 + 16                                    # doubles per minibatch row of the statistics
         if self._stats is None or self._stats.shape[0] != total:
-            self._stats = torch.zeros(total, 4 + 16, dtype=torch.float64, device=dev)
-            self._pbar = torch.zeros(total, 16, dtype=torch.float32, device=dev)
+            self._stats = torch.zeros(total, NS, dtype=torch.float64, device=dev)
         self._stats.zero_()
         cfg = _lib.LossCfg(self.eps_clip, self.value_coef, self.entropy_coef, float(self.entropy_multiplier),
                            self.x_entropy_coef, A, mb)
-        buf = st.minibatch_buffers(mb, *self._obs_buf_args(st))
         engine = self.engine
         fs_vals = []
         is_torch_engine = isinstance(engine, TorchModuleEngine)
+        step_every = int(accum) if float(accum).is_integer() else 0
+        # Gradient-accumulation groups.  The reference runs `accum` minibatches between two optimizer steps
+        # (agents/ppo.py:111,173-177) and the weights do not change in between, so G of them (G | accum) share ONE
+        # gather / forward / loss / backward pass over G*mb rows: the same sum of per-minibatch mean gradients, with
+        # per-minibatch statistics kept (tpp_ppo_loss_fwd_bwd_grouped).  Kernels of 8192-row minibatches are
+        # launch- and prologue-bound on 148 SMs; G*mb rows fill the machine (profiles/README.md).
+        G = self.group_size = self._group_size(step_every, n_mb, mb, engine)
+        rows, n_grp = G * mb, n_mb // G
+        buf = st.minibatch_buffers(rows, *self._obs_buf_args(st))
         self.policy.train()
-        # fixed staging buffers so that one minibatch (gather -> forward -> loss -> backward) is a replayable graph
-        if getattr(self, "_idx_cur", None) is None or self._idx_cur.numel() != mb:
-            self._idx_cur = torch.zeros(mb, dtype=torch.int64, device=dev)
-            self._stats_cur = torch.zeros(4 + 16, dtype=torch.float64, device=dev)
+        # fixed staging buffers so that one group (gather -> forward -> loss -> backward) is a replayable graph
+        if getattr(self, "_idx_cur", None) is None or self._idx_cur.numel() != rows:
+            self._idx_cur = torch.zeros(rows, dtype=torch.int64, device=dev)
+            self._stats_cur = torch.zeros(G, NS, dtype=torch.float64, device=dev)
             self._pbar_cur = torch.zeros(16, dtype=torch.float32, device=dev)
         if hasattr(engine, "refresh_weights"):
             engine.refresh_weights()
 
-        def minibatch_body(idx_row=None, stats_row=None):
+        def group_body(idx_rows=None, stats_rows=None):
             s = _lib.stream_ptr()          # evaluated here: under graph capture the current stream is the capture stream
-            idx_row = self._idx_cur if idx_row is None else idx_row
-            stats_row = self._stats_cur if stats_row is None else stats_row
-            stats_row.zero_()
-            st.gather(idx_row, buf)
+            idx_rows = self._idx_cur if idx_rows is None else idx_rows
+            stats_rows = self._stats_cur if stats_rows is None else stats_rows
+            stats_rows.zero_()
+            st.gather(idx_rows, buf)
             if is_torch_engine or isinstance(engine, ImpalaEngineTC):
-                head = engine.forward(buf.obs, mb, train=True)
+                head = engine.forward(buf.obs, rows, train=True)
             elif buf.obs_lo is not None or buf.raw:
-                head = engine.forward(buf.obs, mb, x_lo=buf.obs_lo, raw=buf.raw)
+                head = engine.forward(buf.obs, rows, x_lo=buf.obs_lo, raw=buf.raw)
             else:
-                head = engine.forward(buf.obs, mb)
-            ws_dhead = engine._workspace(mb).dhead if not is_torch_engine else self._dhead(mb)
-            pbar = None
-            if self.x_entropy_coef != 0.0:
-                self._pbar_cur.zero_()
-                _lib.call("tpp_ppo_pbar", _lib.ptr(head), engine.ld_head, mb, A, _lib.ptr(self._pbar_cur), s)
-                pbar = self._pbar_cur
-                self.n_launches += 1
-            _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
-                      _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
-                      _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(stats_row), s)
+                head = engine.forward(buf.obs, rows)
+            ws_dhead = engine._workspace(rows).dhead if not is_torch_engine else self._dhead(rows)
+            if G > 1:
+                _lib.call("tpp_ppo_loss_fwd_bwd_grouped", C.byref(cfg), G, _lib.ptr(head), engine.ld_head,
+                          _lib.ptr(buf.act), _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret),
+                          _lib.ptr(buf.adv), _lib.ptr(ws_dhead), _lib.ptr(stats_rows), NS, s)
+            else:
+                pbar = None
+                if self.x_entropy_coef != 0.0:
+                    self._pbar_cur.zero_()
+                    _lib.call("tpp_ppo_pbar", _lib.ptr(head), engine.ld_head, mb, A, _lib.ptr(self._pbar_cur), s)
+                    pbar = self._pbar_cur
+                    self.n_launches += 1
+                _lib.call("tpp_ppo_loss_fwd_bwd", C.byref(cfg), _lib.ptr(head), engine.ld_head, _lib.ptr(buf.act),
+                          _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
+                          _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(stats_rows), s)
             self.n_launches += 1
             if is_torch_engine:
-                engine.backward(ws_dhead, mb, self.fs_coef)
+                engine.backward(ws_dhead, rows, self.fs_coef)
             else:
-                engine.backward(ws_dhead, mb)
+                engine.backward(ws_dhead, rows)
 
-        graph_key = (mb, float(self.entropy_multiplier), id(st))
+        graph_key = (mb, G, float(self.entropy_multiplier), id(st))
         use_graph = self.use_cuda_graph and not is_torch_engine
         graphs = self.__dict__.setdefault("_mb_graphs", {})
         k = 0
-        # Whole-epoch graph (single GPU, MLP engines): every minibatch of an epoch -- gather, forward, loss, backward --
+        # Whole-epoch graph (single GPU, MLP engines): every group of an epoch -- gather, forward, loss, backward --
         # and the optimizer steps + weight re-splits at their fixed positions are ONE graph replay per epoch; the
-        # epoch's permutation is uploaded into a static index buffer first.  Removes ~400 graph launches, index copies
-        # and stats copies per iteration from the host's critical path.
-        step_every = int(accum) if float(accum).is_integer() else 0
+        # epoch's permutation is uploaded into a static index buffer first.  Removes the per-group graph launches, index
+        # copies and stats copies of an iteration from the host's critical path.
         epoch_graph = (use_graph and self.world_size == 1 and step_every > 0 and n_mb % step_every == 0
                        and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0
                        and self.entropy_scaling is None)
         if epoch_graph:
             if getattr(self, "_epoch_idx", None) is None or self._epoch_idx.shape != (n_mb, mb):
                 self._epoch_idx = torch.zeros(n_mb, mb, dtype=torch.int64, device=dev)
-                self._epoch_stats = torch.zeros(n_mb, 4 + 16, dtype=torch.float64, device=dev)
+                self._epoch_stats = torch.zeros(n_mb, NS, dtype=torch.float64, device=dev)
             egraphs = self.__dict__.setdefault("_epoch_graphs", {})
-            ekey = (mb, n_mb, step_every, float(self.entropy_multiplier), id(st))
+            ekey = (mb, n_mb, G, step_every, float(self.entropy_multiplier), id(st))
+            idx_g, stats_g = self._epoch_idx.view(n_grp, rows), self._epoch_stats.view(n_grp, G, NS)
 
             def epoch_body():
-                for i in range(n_mb):
-                    minibatch_body(self._epoch_idx[i], self._epoch_stats[i])
-                    if (i + 1) % step_every == 0:
+                for i in range(n_grp):
+                    group_body(idx_g[i], stats_g[i])
+                    if ((i + 1) * G) % step_every == 0:
                         self.optimizer.launch()
                         if hasattr(engine, "refresh_weights"):
                             engine.refresh_weights()
@@ -340,23 +355,23 @@ class PPO(BaseAgent):
                 k += n_mb
             return self._summary(fs_vals)
         for _ in range(self.epoch):
-            idx = st.epoch_indices(mb)
-            for i in range(n_mb):
+            idx = st.epoch_indices(mb).view(n_grp, rows)
+            for i in range(n_grp):
                 self._idx_cur.copy_(idx[i])
                 entry = graphs.get(graph_key) if use_graph else None
                 if entry is None or entry == "warm":
-                    if use_graph and entry == "warm":                  # second minibatch: capture, then replay
+                    if use_graph and entry == "warm":                  # second group: capture, then replay
                         g = torch.cuda.CUDAGraph()
                         torch.cuda.synchronize()
                         c0 = self._launch_count()
                         with torch.cuda.graph(g):
-                            minibatch_body()
+                            group_body()
                         n_captured = sum(self._launch_count()) - sum(c0)
                         # kernels recorded during capture did not execute: count them per replay instead
                         self.n_launches, self.engine.n_launches, self.storage.n_launches = c0
                         entry = graphs[graph_key] = (g, n_captured)
-                    else:                                              # first minibatch (or graphs off): eager
-                        minibatch_body()
+                    else:                                              # first group (or graphs off): eager
+                        group_body()
                         if use_graph:
                             graphs[graph_key] = "warm"
                 if isinstance(entry, tuple):
@@ -364,16 +379,28 @@ class PPO(BaseAgent):
                     self.n_launches += entry[1]
                 if getattr(engine, "last_fs", None) is not None:
                     fs_vals.append(engine.last_fs.detach().clone())
-                self._stats[k].copy_(self._stats_cur)
-                if cnt % accum == 0:
+                self._stats[k:k + G].copy_(self._stats_cur)
+                k += G
+                if k % accum == 0:                 # k minibatches done this call (reference: cnt % accum, :173)
                     if self.world_size > 1:
                         parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
                     self.optimizer.step()
                     if hasattr(engine, "refresh_weights"):
                         engine.refresh_weights()
-                cnt += 1
-                k += 1
         return self._summary(fs_vals)
+
+    def _group_size(self, step_every, n_mb, mb, engine):
+        """Minibatches sharing one forward/backward pass (see optimize): the largest divisor of the accumulation
+        count that the ``fuse_accum`` setting ("auto" = all of them, or an int cap; 1 / False = off) and the row
+        budget allow."""
+        want = self.__dict__.get("fuse_accum", "auto")
+        if want in (False, None, 0, 1) or step_every <= 1 or n_mb % step_every != 0 or mb % 256 != 0:
+            return 1
+        if not isinstance(engine, (MLPEngine, MLPEngineTC)) or self.x_entropy_coef != 0.0:
+            return 1
+        cap = step_every if want in ("auto", True) else max(1, int(want))
+        cap = min(cap, max(1, self.max_group_rows // mb))
+        return max(g for g in range(1, step_every + 1) if step_every % g == 0 and g <= cap)
 
     def _launch_count(self):
         return (self.n_launches, self.engine.n_launches, self.storage.n_launches)

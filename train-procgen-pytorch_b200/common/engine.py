@@ -200,6 +200,10 @@ class MLPEngineTC(MLPEngine):
         # gather's writes); ScaledFloatFrame's 1/255 (common/env/procgen_wrappers.py:407-419) lives in a second copy of
         # the first layer's weights and in the ``alpha`` of its weight-gradient GEMM.
         self.raw_pixels = raw_pixels
+        # 128 x 256 output tiles for 256-wide layers once a pass has enough rows to fill the machine with them: the
+        # activation tile is then fetched once for all 256 output columns (3/4 of the L2 -> shared-memory bytes per
+        # FLOP of two 128 x 128 tiles, which is what bounds these kernels; profiles/README.md)
+        self.wide_tile_rows = 32768
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
         for (w_off, b_off, fin, fout, relu) in self.layers:
@@ -279,6 +283,9 @@ class MLPEngineTC(MLPEngine):
         self.n_launches += 1
 
     # ------------------------------------------------------------------------------------------
+    def _bn(self, M, N):
+        return 256 if (N % 256 == 0 and M >= self.wide_tile_rows) else 0
+
     def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False):
         """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given, or -- ``raw`` --
         integer pixel values 0..255 with row stride ``ld_in``), or with ``feature_major_ld`` a feature-major
@@ -311,12 +318,19 @@ class MLPEngineTC(MLPEngine):
             self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
                      flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
                      out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
-                     exact=TC_A_EXACT if raw and i == 0 else 0)
+                     exact=TC_A_EXACT if raw and i == 0 else 0, block_n=self._bn(M, fout))
             cur, ld_cur, a_mn = (h["hi"], h["lo"]), h["ld"], 0
         self._tc(cur, ld_cur, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
                  bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         self._x = (x, feature_major_ld)
         return ws.head
+
+    @staticmethod
+    def _wgrad_split(M, tiles):
+        """k-splits of a weight-gradient GEMM (contraction over the M samples): enough CTAs to fill the machine, and
+        at most ~1024 samples per TMEM accumulator (the tensor core adds into it with truncation; longer chains lose
+        ~1e-4, DESIGN.md 'Long contractions')."""
+        return max(1, min(_ceil(M, 32), max(_ceil(148, tiles), _ceil(M, 1024))))
 
     def backward(self, dhead, M):
         ws, s = self._workspace(M), _lib.stream_ptr()
@@ -354,7 +368,7 @@ class MLPEngineTC(MLPEngine):
             tiles = _ceil(fout, 128) * _ceil(fin, 128)
             raw0 = i == 0 and self._x_raw         # gW1 = (1/255) dZ^T X_pixels, X exact: no lo half, two passes
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                     out=self._g(w_off), ldc=fin, split_k=max(1, min(_ceil(M, 32), _ceil(148, tiles))), block_n=128,
+                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, tiles), block_n=128,
                      exact=TC_B_EXACT if raw0 else 0, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
@@ -363,7 +377,7 @@ class MLPEngineTC(MLPEngine):
                 self._tc((dz["hi"], dz["lo"]), ld_dz, (w["hi"], w["lo"]), w["ldk"], M, fin, fout, b_mn=1,
                          flags=EPI_MASK if prev_relu else 0, mask=prev["hi"] if prev_relu else None,
                          ld_mask=prev["ld"], out_pair=(nxt["hi"], nxt["lo"]), ldc=prev["ld"],
-                         colsum=self._g(self.layers[i - 1][1]))
+                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin))
                 cur, ld_dz = cur ^ 1, prev["ld"]
 
 

@@ -70,7 +70,8 @@ struct Params {
   float* out_hi; float* out_lo;
   float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
   int a_mn, b_mn;              // operand majors (0 = K-major, 1 = MN-major)
-  long long* dbg;              // optional timeline probe (block 0 only): clock64 at 8 milestones
+  long long* dbg;              // optional timeline probe (one CTA): clock64 at 8 milestones
+  int dbg_y;                   // blockIdx.y of the probed CTA (wide tiles)
   int ntn;                     // number of N tiles
   int ntiles;                  // ntn * number of M tiles
   int total_work;              // ntiles * number of k-splits: work items (tile, split), split-major
@@ -270,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // Wide tiles: one work item per CTA on a (n tile, m tile, split) grid -- no index arithmetic on the critical path.
   const int wbegin = NARROW ? (int)blockIdx.x : 0, wend = NARROW ? p.total_work : 1;
   const int wstride = NARROW ? (int)gridDim.x : 1;
-  const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+  const bool probe = p.dbg && blockIdx.x == 0 && (int)blockIdx.y == p.dbg_y && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + bk - 1) / bk;
@@ -876,6 +877,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
   p.colsum = g->colsum; p.a_mn = g->a_mn ? 1 : 0; p.b_mn = g->b_mn ? 1 : 0;
   p.dbg = reinterpret_cast<long long*>(g->dbg);
+  p.dbg_y = BLOCK_N <= 32 ? 0 : g->_reserved;
   p.bk = bk;
   const int total_kb = (g->K + bk - 1) / bk;
   if (split_k < 1) split_k = 1;
@@ -894,7 +896,8 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   // per SM so that one tile's epilogue / prologue overlaps another tile's loads (measured on the IMPALA shapes:
   // throughput follows the number of resident CTAs, not the depth: 3 CTAs x 2 stages beat 1 CTA x 6 stages by 1.4-2x)
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
-  if (n_tiles >= 4 * 148 && (p.kb_per_split <= 16 || BLOCK_N <= 32)) {
+  // (narrow tiles only: the wide CTAs -- 576 threads x 67 registers -- are alone on their SM whatever their stage count)
+  if (n_tiles >= 4 * 148 && BLOCK_N <= 32) {
     int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;   // three resident CTAs
     if (few < 2) few = 2;
     if (stages > few) stages = few;

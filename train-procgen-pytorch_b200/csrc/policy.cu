@@ -197,16 +197,21 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(tpp_loss_cfg c, const flo
                                                        const float* __restrict__ old_value,
                                                        const float* __restrict__ ret, const float* __restrict__ adv,
                                                        const float* __restrict__ pbar_sum, float* __restrict__ dhead,
-                                                       double* stats) {
+                                                       double* stats, int rows, int stats_stride) {
+  // rows = groups * c.mb samples: group g = rows [g*mb, (g+1)*mb) is one minibatch of the reference loop (its loss
+  // terms are means over mb samples, its sums go to stats + g*stats_stride).  With groups > 1, mb % 256 == 0, so a
+  // block never straddles two groups.
   __shared__ double red[32];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int A = c.n_actions;
   const float invB = 1.0f / (float)c.mb;
+  const int block_row0 = blockIdx.x * blockDim.x;
+  stats += (int64_t)(block_row0 / c.mb) * stats_stride;
   double s_pi = 0.0, s_v = 0.0, s_ent = 0.0;
   float p[MAX_A];
 #pragma unroll
   for (int j = 0; j < MAX_A; ++j) p[j] = 0.0f;
-  if (b < c.mb) {
+  if (b < rows) {
     const float* h = head + (int64_t)b * ld_head;
     float l[MAX_A];
     float mx = -CUDART_INF_F, se = 0.0f;
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(tpp_loss_cfg c, const flo
     atomicAdd(stats + 0, s_pi);
     atomicAdd(stats + 1, s_v);
     atomicAdd(stats + 2, s_ent);
-    if (blockIdx.x == 0) atomicAdd(stats + 3, (double)c.mb);
+    if (block_row0 % c.mb == 0) atomicAdd(stats + 3, (double)c.mb);
   }
   for (int j = 0; j < A; ++j) {
     const double s = block_sum((double)p[j], red);
@@ -403,7 +408,22 @@ extern "C" int tpp_ppo_loss_fwd_bwd(const tpp_loss_cfg* cfg, const float* head, 
   TPP_CHECK_ARG(cfg->mb > 0 && cfg->n_actions > 0 && cfg->n_actions <= tpp::MAX_A && ld_head > cfg->n_actions);
   TPP_CHECK_ARG(cfg->x_entropy_coef == 0.0f || pbar);
   tpp::ppo_loss_kernel<<<tpp_ceil_div(cfg->mb, 256), 256, 0, tpp_stream(stream)>>>(
-      *cfg, head, ld_head, act, old_logp, old_value, ret, adv, pbar, dhead, stats);
+      *cfg, head, ld_head, act, old_logp, old_value, ret, adv, pbar, dhead, stats, cfg->mb, 0);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_ppo_loss_fwd_bwd_grouped(const tpp_loss_cfg* cfg, int32_t groups, const float* head, int32_t ld_head,
+                                            const int32_t* act, const float* old_logp, const float* old_value,
+                                            const float* ret, const float* adv, float* dhead, double* stats,
+                                            int32_t stats_stride, void* stream) {
+  TPP_CHECK_ARG(cfg && head && act && old_logp && old_value && ret && adv && dhead && stats);
+  TPP_CHECK_ARG(cfg->mb > 0 && cfg->n_actions > 0 && cfg->n_actions <= tpp::MAX_A && ld_head > cfg->n_actions);
+  TPP_CHECK_ARG(groups >= 1 && (groups == 1 || cfg->mb % 256 == 0) && stats_stride >= 4 + cfg->n_actions);
+  TPP_CHECK_ARG(cfg->x_entropy_coef == 0.0f);   // the cross-batch entropy needs per-group batch means: ungrouped path
+  TPP_CHECK_ARG((int64_t)groups * cfg->mb < (int64_t)1 << 31);
+  const int rows = groups * cfg->mb;
+  tpp::ppo_loss_kernel<<<tpp_ceil_div(rows, 256), 256, 0, tpp_stream(stream)>>>(
+      *cfg, head, ld_head, act, old_logp, old_value, ret, adv, nullptr, dhead, stats, rows, stats_stride);
   TPP_LAUNCH_STATUS();
 }
 
