@@ -201,3 +201,41 @@ def test_exact_operand_two_pass_mode(which, M, N, K, mn):
         want, scale = want / 255.0, scale / 255.0
     err = (out[:, :N].double().cpu() - want).abs() / scale
     assert err.max() < 2e-6, f"max scaled err {err.max():.3e}"
+
+
+# ---- 256 x 256 tile on a CTA pair (cta_group::2, block_n = 512) -------------------------------------------------
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 32), (512, 256, 256), (4096, 256, 588), (1000, 256, 200), (256, 588, 96),
+                                   (300, 500, 72)])
+@pytest.mark.parametrize("precision", [3, 1])
+def test_cta_pair_tile(a_mn, b_mn, M, N, K, precision):
+    """Forward (both K-major), data gradient (B MN-major) and weight-gradient (both MN-major) operand forms; ragged M / N
+    edges (rows and columns beyond the matrix come from TMA zero fill and are never stored)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 3 + K + 17)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    res = _gemm(a, b, precision, a_mn=a_mn, b_mn=b_mn, block_n=512)
+    want, scale = _ref(a, b)
+    err = (res["out"][:, :N].double().cpu() - want).abs() / scale
+    assert err.max() < (2e-6 if precision == 3 else 2e-3), f"max scaled err {err.max():.3e}"
+    assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])
+
+
+def test_cta_pair_epilogues_and_split_k():
+    M, N, K = 1024, 256, 200
+    a, b = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+    bias, mask = torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+    want, scale = _ref(a, b)
+    res = _gemm(a, b, 3, flags=1 | 2, bias=bias, block_n=512)                       # bias + relu
+    w = torch.relu(want + bias.double().cpu())
+    assert ((res["out"].double().cpu() - w).abs() / (scale + 1)).max() < 2e-6
+    res = _gemm(a, b, 3, flags=4, mask=mask, want_colsum=True, b_mn=True, block_n=512)   # data-gradient form
+    w = want * (mask.cpu() > 0)
+    assert ((res["out"].double().cpu() - w).abs() / scale).max() < 2e-6
+    np.testing.assert_allclose(res["colsum"].double().cpu().numpy() - 1.0, w.sum(0).numpy(), rtol=1e-4, atol=1e-3)
+    # weight-gradient form: long contraction split over CTAs pairs, atomically accumulated on top of existing values
+    a2, b2 = torch.randn(256, 8192, device="cuda"), torch.randn(588, 8192, device="cuda")
+    out = torch.ones(256, 588, device="cuda")
+    _gemm(a2, b2, 3, flags=8, split_k=16, a_mn=True, b_mn=True, out=out, block_n=512)
+    want2, scale2 = _ref(a2, b2)
+    assert ((out.double().cpu() - 1.0 - want2).abs() / scale2).max() < 2e-6

@@ -200,10 +200,11 @@ class MLPEngineTC(MLPEngine):
         # gather's writes); ScaledFloatFrame's 1/255 (common/env/procgen_wrappers.py:407-419) lives in a second copy of
         # the first layer's weights and in the ``alpha`` of its weight-gradient GEMM.
         self.raw_pixels = raw_pixels
-        # 128 x 256 output tiles for 256-wide layers once a pass has enough rows to fill the machine with them: the
-        # activation tile is then fetched once for all 256 output columns (3/4 of the L2 -> shared-memory bytes per
-        # FLOP of two 128 x 128 tiles, which is what bounds these kernels; profiles/README.md)
+        # 256 x 256 output tiles on CTA pairs (cta_group::2) for the 256-wide layers once a pass has enough rows to fill
+        # the machine with them: each CTA stages 128 rows of each operand for a 256 x 256 product, i.e. half the
+        # L2 -> shared-memory bytes per FLOP of 128 x 128 tiles, which is what bounds these kernels (profiles/README.md)
         self.wide_tile_rows = 32768
+        self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
         for (w_off, b_off, fin, fout, relu) in self.layers:
@@ -284,7 +285,12 @@ class MLPEngineTC(MLPEngine):
 
     # ------------------------------------------------------------------------------------------
     def _bn(self, M, N):
-        return 256 if (N % 256 == 0 and M >= self.wide_tile_rows) else 0
+        """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
+        if N >= 256 and M >= self.wide_tile_rows:
+            return 512         # 256 x 256 tiles on CTA pairs (cta_group::2)
+        if N >= 128 and M * N <= self.small_tile_elems:
+            return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
+        return 0
 
     def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False):
         """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given, or -- ``raw`` --
@@ -326,11 +332,14 @@ class MLPEngineTC(MLPEngine):
         return ws.head
 
     @staticmethod
-    def _wgrad_split(M, tiles):
-        """k-splits of a weight-gradient GEMM (contraction over the M samples): enough CTAs to fill the machine, and
-        at most ~1024 samples per TMEM accumulator (the tensor core adds into it with truncation; longer chains lose
-        ~1e-4, DESIGN.md 'Long contractions')."""
-        return max(1, min(_ceil(M, 32), max(_ceil(148, tiles), _ceil(M, 1024))))
+    def _wgrad_split(M, ctas):
+        """k-splits of a weight-gradient GEMM (contraction over the M samples; ``ctas`` CTAs per split): at most ~1024
+        samples per TMEM accumulator (the tensor core adds into it with truncation; longer chains lose ~1e-4,
+        DESIGN.md 'Long contractions'), at least one wave of CTAs, and then as many splits as fit the same number of
+        waves (150 CTAs on 148 SMs take as long as 296)."""
+        s_min = max(_ceil(148, ctas), _ceil(M, 1024))
+        waves = _ceil(s_min * ctas, 148)
+        return max(1, min(_ceil(M, 32), max(s_min, (waves * 148) // ctas)))
 
     def backward(self, dhead, M):
         ws, s = self._workspace(M), _lib.stream_ptr()
@@ -365,10 +374,11 @@ class MLPEngineTC(MLPEngine):
             dz = ws.dz[cur]
             inp, ld_inp = ((ws.h[i - 1]["hi"], ws.h[i - 1]["lo"]), ws.h[i - 1]["ld"]) if i > 0 else (x_pair, x_ld)
             # gW[fout, fin] += dZ^T X : both operands MN-major, contraction over the M samples split across CTAs
-            tiles = _ceil(fout, 128) * _ceil(fin, 128)
+            pair = fout >= 256 and fin >= 256 and M >= self.wide_tile_rows      # 256 x 256 tiles on CTA pairs
+            ctas = 2 * _ceil(fout, 256) * _ceil(fin, 256) if pair else _ceil(fout, 128) * _ceil(fin, 128)
             raw0 = i == 0 and self._x_raw         # gW1 = (1/255) dZ^T X_pixels, X exact: no lo half, two passes
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, tiles), block_n=128,
+                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas), block_n=512 if pair else 128,
                      exact=TC_B_EXACT if raw0 else 0, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad

@@ -167,6 +167,60 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC share one 256 x 256 MMA tile ----------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the same shared-memory offset in the pair's leader CTA (rank 0): clears the peer bit of a shared::cluster address
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives (once all previously issued MMAs of the pair have retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((unsigned short)3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -229,7 +283,13 @@ __device__ __forceinline__ float tf32_round(float x) {
 // ---------------------------------------------------------------------------------------------------
 // The kernel: one 128 x BLOCK_N output tile (x one k-split) per CTA
 // ---------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
+// PAIR (BLOCK_N = 256 only): the CTA is one half of a cluster of two (cta_group::2).  The pair computes a 256 x 256
+// output tile: each CTA stages ITS 128 rows of A and ITS 128 of the 256 B rows (half the L2 -> shared-memory bytes per
+// FLOP of a single-CTA 128 x 256 tile, a quarter of two 128 x 128 tiles -- the bound of these kernels), the leader
+// (rank 0) issues the 256 x 256 x 8 MMAs for both, each CTA's TMEM receives its own 128 accumulator rows and each CTA
+// runs the epilogue of those rows.  Both CTAs' TMA loads signal the LEADER's full barrier; tcgen05.commit multicasts
+// the stage-free / accumulator-complete arrivals to both CTAs.
+template <int BLOCK_N, bool PAIR = false>
 __global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
@@ -239,13 +299,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // previous one (per-tile prologue, epilogue and CTA launch were ~2/3 of a 9-k-block tile's time).  Wide tiles keep
   // compile-time constants, the lean epilogue and one work item per CTA.
   constexpr bool NARROW = BLOCK_N <= 32;
+  static_assert(!PAIR || BLOCK_N == 256, "the CTA-pair form is the 256 x 256 tile");
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;                // B rows this CTA stages
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
   constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;          // TMEM columns of one accumulator
   constexpr uint32_t TMEM_COLS = NARROW ? 2 * ACC_COLS : ACC_COLS;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), a_major bit 15,
   // b_major bit 16 (1 = MN-major), N>>3 at bit 17, M>>4 at bit 24
   const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                          ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                         ((uint32_t)(BLOCK_M >> 4) << 24);
+                         ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
 
   // 128B-swizzled tiles need 1024-byte alignment.  The alignment is requested on the declaration (and checked) instead
   // of rounding the address through an integer: that cast loses the shared address space and turns every staging
@@ -257,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // instruction of their single-thread producer / MMA roles -- measured +9 % on the convolution tiles)
   const int nops_a = NARROW ? (p.npass == 3 ? 2 : 1) : p.nops_a, nops_b = NARROW ? nops_a : p.nops_b;
   const int bk = NARROW ? p.bk : BLOCK_K;
-  const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : BLOCK_N * BLOCK_K * 4;
+  const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : B_ROWS * BLOCK_K * 4;
   const int stage_bytes = A_BYTES * nops_a + B_BYTES * nops_b;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -282,6 +346,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     m0 = (tile_ / p.ntn) * BLOCK_M;                                                  \
     n0 = (tile_ % p.ntn) * BLOCK_N;                                                  \
     kb0 = split_ * p.kb_per_split;                                                   \
+  } else if (PAIR) {   /* grid.x = 2 x n tiles (the pair), grid.y = 256-row tiles: this CTA owns 128 of the rows */ \
+    m0 = ((int)blockIdx.y * 2 + (int)cta_rank) * BLOCK_M;                            \
+    n0 = ((int)blockIdx.x >> 1) * BLOCK_N;                                           \
+    kb0 = (int)blockIdx.z * p.kb_per_split;                                          \
   } else {                                                                           \
     m0 = (int)blockIdx.y * BLOCK_M;                                                  \
     n0 = (int)blockIdx.x * BLOCK_N;                                                  \
@@ -308,9 +376,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   float* cs_sh = reinterpret_cast<float*>(smem + p.bar_offset + 256);
   if (p.colsum)
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) cs_sh[i] = 0.0f;
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything of this CTA signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) TPP_PROBE(1);
@@ -337,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         if (it == 0) TPP_PROBE(2);
-        mbar_expect_tx(full_bar + s, tx);
+        if (!PAIR || leader) mbar_expect_tx(full_bar + s, tx);   // PAIR: tx counts both CTAs' boxes, on the leader
         uint8_t* st = smem + s * stage_bytes;
         const int kc = (kb0 + kb) * bk;
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
@@ -356,6 +425,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else if (NARROW && p.conv_W) {
             const int tap = kb0 + kb;
             tma_load_im2col(tmA, full_bar + s, dst, cw, ch, cn, tap % 3, tap / 3);
+          } else if (PAIR) {
+            if (p.a_mn) tma_load_3d_pair(tmA, full_bar + s, dst, 0, kc, m0 >> 5);
+            else tma_load_2d_pair(tmA, full_bar + s, dst, kc, m0);
           } else if (p.a_mn) {
             tma_load_3d(tmA, full_bar + s, dst, 0, kc, m0 >> 5);
           } else {
@@ -365,16 +437,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (!NARROW && o >= nops_b) continue;
           const CUtensorMap* tmB = o ? &tmB_lo : &tmB_hi;
           uint8_t* dstb = st + A_BYTES * nops_a + o * B_BYTES;
-          if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
+          if (PAIR) {                                   // this CTA's half of the tile's 256 B rows
+            const int nb = n0 + (int)cta_rank * B_ROWS;
+            if (p.b_mn) tma_load_3d_pair(tmB, full_bar + s, dstb, 0, kc, nb >> 5);
+            else tma_load_2d_pair(tmB, full_bar + s, dstb, kc, nb);
+          } else if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
           else tma_load_2d(tmB, full_bar + s, dstb, kc, n0);
         }
       }
      }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
+    // ===== MMA issuer (one thread; the leader CTA of a pair issues for both) =====
     int it = 0, acc_i = 0;
-    for (int w = wbegin; w < wend; w += wstride, ++acc_i) {
+    for (int w = wbegin; w < (PAIR && !leader ? wbegin : wend); w += wstride, ++acc_i) {
      TPP_DECODE_WORK(w)
      (void)m0; (void)n0; (void)kb0;
      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_i & 1) * ACC_COLS;
@@ -408,11 +484,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // k-step: K-major advances 32 bytes inside the swizzled row, MN-major one 8-row group (1024 bytes)
             const uint64_t da = p.a_mn ? make_desc_mn(a + k * 1024) : make_desc(a + k * UMMA_K * 4, bk);
             const uint64_t db = p.b_mn ? make_desc_mn(b + k * 1024) : make_desc(b + k * UMMA_K * 4, bk);
-            umma_tf32(tmem_acc, da, db, IDESC, acc);
+            if (PAIR) umma_tf32_pair(tmem_acc, da, db, IDESC, acc); else umma_tf32(tmem_acc, da, db, IDESC, acc);
           }
         }
-        umma_commit(empty_bar + s);                 // frees the smem stage when these MMAs retire
-        if (kb == nkb - 1) { umma_commit(tmem_full + (acc_i & 1)); TPP_PROBE(4); }  // accumulator complete
+        // frees the smem stage when these MMAs retire (PAIR: in both CTAs)
+        if (PAIR) umma_commit_pair(empty_bar + s); else umma_commit(empty_bar + s);
+        if (kb == nkb - 1) {                        // accumulator complete
+          if (PAIR) umma_commit_pair(tmem_full + (acc_i & 1)); else umma_commit(tmem_full + (acc_i & 1));
+          TPP_PROBE(4);
+        }
       }
       __syncwarp();
      }
@@ -688,7 +768,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 2) TPP_PROBE(6);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) cluster_sync_all();      // neither CTA's shared memory / TMEM goes away while the pair's MMAs may use it
+  if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
   if (warp == 1) TPP_PROBE(7);
 #undef TPP_PROBE
 }
@@ -827,8 +908,9 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // B rows one CTA stages
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const int npass = (g->precision & 15) == 3 ? 3 : 1;
   if (BLOCK_N <= 32 && ((g->precision & 48) || (g->alpha != 0.0f && g->alpha != 1.0f))) return TPP_ENOTSUP;
@@ -836,7 +918,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const int nops_a = (npass == 3 && !a_exact) ? 2 : 1, nops_b = (npass == 3 && !b_exact) ? 2 : 1;
   if (BLOCK_N > 32 && ((g->flags & (F_ADD | F_RELU_OUT | F_PAIR_RELU)) || g->conv_C > 0))
     return TPP_ENOTSUP;   // residual / ReLU-pair epilogues and convolution mode are compiled into the narrow tiles only
-  int rc, a_bytes = A_BYTES, b_bytes = BLOCK_N * BLOCK_K * 4;
+  int rc, a_bytes = A_BYTES, b_bytes = B_ROWS * BLOCK_K * 4;
   const bool conv = g->conv_C > 0;
   const int wgrad = conv && g->conv_wgrad;
   int bk = BLOCK_K;
@@ -853,14 +935,14 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (nops_a == 2 && (rc = make_map_im2col(&tmA_lo, g->a_lo, g->conv_B, g->conv_H, g->conv_W, g->conv_C, wgrad, bk)))
       return rc;
   } else if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
-  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
+  if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, B_ROWS, g->b_mn, &b_bytes, bk))) return rc;
   if (nops_a == 2) {
     if (!conv && (rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
   } else {
     tmA_lo = tmA_hi;
   }
   if (nops_b == 2) {
-    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, BLOCK_N, g->b_mn, &b_bytes, bk))) return rc;
+    if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, B_ROWS, g->b_mn, &b_bytes, bk))) return rc;
   } else {
     tmB_lo = tmB_hi;
   }
@@ -871,7 +953,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.nops_a = nops_a; p.nops_b = nops_b;
   p.skip = (a_exact ? 4 : 0) | (b_exact ? 2 : 0);
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
-  p.tx_bytes = a_bytes * nops_a + b_bytes * nops_b;
+  p.tx_bytes = (a_bytes * nops_a + b_bytes * nops_b) * (PAIR ? 2 : 1);   // PAIR: both CTAs' boxes land on one barrier
   p.conv_W = conv ? g->conv_W : 0; p.conv_HW = conv ? g->conv_H * g->conv_W : 0;
   p.conv_wgrad = wgrad; p.b_tx = b_bytes;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
@@ -887,7 +969,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   // slots keep the full tile size: the MMA reads all BLOCK_M x BLOCK_N operand rows, also the ones a smaller TMA box
   // left unfilled (their products land in accumulator rows / columns that are never stored)
   p.a_slot = BLOCK_M * bk * 4;
-  p.b_slot = BLOCK_N * bk * 4;
+  p.b_slot = B_ROWS * bk * 4;
   const int stage_bytes = p.a_slot * nops_a + p.b_slot * nops_b;
   int stages = (224 * 1024 - 1024 - 256 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
   if (stages < 1) return TPP_ENOTSUP;
@@ -919,7 +1001,8 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -938,7 +1021,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     static int regs_per_cta = 0;
     if (!regs_per_cta) {
       cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N>) != cudaSuccess) return TPP_ENOTSUP;
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR>) != cudaSuccess) return TPP_ENOTSUP;
       regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N);
     }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -957,7 +1040,24 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (ntm > 65535) return TPP_ENOTSUP;
     grid = dim3((unsigned)p.ntn, (unsigned)ntm, (unsigned)split_k);
   }
-  gemm_tc_kernel<BLOCK_N><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  if (PAIR) {
+    // a cluster of two CTAs along grid.x per 256 x 256 tile; grid.y counts 256-row tiles
+    const int ntm2 = (g->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    if (ntm2 > 65535) return TPP_ENOTSUP;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)p.ntn, (unsigned)ntm2, (unsigned)split_k);
+    cfg.blockDim = dim3(num_threads(BLOCK_N), 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    if (e != cudaSuccess) return (int)e;
+    TPP_LAUNCH_STATUS();
+  }
+  gemm_tc_kernel<BLOCK_N, PAIR><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
 
@@ -984,6 +1084,7 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
     case 64: return tpp::tc::launch<64>(g, g->split_k, s);
     case 128: return tpp::tc::launch<128>(g, g->split_k, s);
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
+    case 512: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile on a CTA pair (cta_group::2)
     default: return TPP_ENOTSUP;
   }
 }
