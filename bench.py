@@ -127,7 +127,8 @@ def build_agent(name, hp, rank, device):
                             env.action_space.n).to(device).flatten_()
     st = Storage(obs_shape, hp["latent_size"], T, N, device)
     agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank,
-                matmul=hp.get("matmul", "tf32x3"), fuse_accum=hp.get("fuse_accum", "auto"))
+                matmul=hp.get("matmul", "tf32x3"), fuse_accum=hp.get("fuse_accum", "auto"),
+                rollout_chains=hp.get("rollout_chains", 1))
     return agent, in_dim
 
 
@@ -289,7 +290,8 @@ def run_ours(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     hp = dict(WORKLOADS[args.workload], matmul=args.matmul,
-              fuse_accum=args.fuse_accum if args.fuse_accum == "auto" else int(args.fuse_accum))
+              fuse_accum=args.fuse_accum if args.fuse_accum == "auto" else int(args.fuse_accum),
+              rollout_chains=args.rollout_chains)
     agent, in_dim = build_agent(args.workload, hp, rank, device)
     if world > 1:
         agent.shard(world)
@@ -678,6 +680,9 @@ def main():
                     help="dense-layer arithmetic: tcgen05 3xTF32 (fp32-parity, default), tcgen05 single TF32, CUDA-core fp32")
     ap.add_argument("--fuse-accum", default="auto",
                     help="minibatches of one gradient-accumulation window sharing a forward/backward pass (auto = all)")
+    ap.add_argument("--rollout-chains", type=int, default=1,
+                    help="env ranges stepping through the rollout as concurrent kernel chains (experiment: no gain, "
+                         "the T sequential steps are latency-bound whatever the range size)")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs only)")
     ap.add_argument("--timed-region-only", action="store_true", help="stop after the device-timed loop (ncu runs)")

@@ -100,10 +100,13 @@ typedef struct {
 /* One step of all envs: grid transition, rewards, done, level replacement in env-index order with the
  * sequential seed counter, and emit of the post-reset frame into frame_out (rollout slot t+1, uint8 NHWC).
  * Replaces BoxWorldVec.step (boxworld/box_world_env_vec.py:70-209).
- * reward_out int32 [N] (raw env reward), done_out uint8 [N]; fin_ret/fin_len/fin_solved nullable [N].     */
+ * reward_out int32 [N] (raw env reward), done_out uint8 [N]; fin_ret/fin_len/fin_solved nullable [N].
+ * obs_out (nullable) fp32 [N][ld_obs]: the same post-reset frames as the policy's next input rows, channel-major
+ * integer pixel values 0..255 (= tpp_frames_to_obs(raw) of frame_out, without a launch of its own in the rollout's
+ * dependent kernel chain).                                                                                  */
 int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* action, int32_t* reward_out,
                       uint8_t* done_out, uint8_t* frame_out, int32_t* fin_ret, int32_t* fin_len,
-                      uint8_t* fin_solved, void* stream);
+                      uint8_t* fin_solved, float* obs_out, int32_t ld_obs, void* stream);
 
 /* Host-side level generator (MT19937 + CPython random.sample/choices semantics), `count` consecutive seeds
  * starting at seed0.  Replaces world_gen / sampling_pairs (boxworld/boxworld_gen_vec.py:4-97).
@@ -127,6 +130,13 @@ int tpp_boxworld_emit_frames(const tpp_boxworld_state* st, uint8_t* frame_out, v
 int tpp_vecnormalize_step(double* ret, double* rms, const void* raw_rew, int raw_is_int, const uint8_t* done,
                           float* out_rew, int32_t n_envs, double gamma, double cliprew, double epsilon,
                           void* stream);
+/* The same for the T steps of a finished rollout in one launch (identical arithmetic, step after step): raw_rew int32
+ * [T][ld], done u8 [T][ld] -> out_rew f32 [T][ld] normalised+clipped and (nullable) out_raw f32 [T][ld] = the raw
+ * rewards as floats for the logger.  Rewards never feed back into the rollout, so the per-step cross-env reduction
+ * can leave the step's critical path (and env ranges can step independently).                              */
+int tpp_vecnormalize_rollout(double* ret, double* rms, const int32_t* raw_rew, const uint8_t* done, float* out_rew,
+                             float* out_raw, int32_t T, int32_t n_envs, int64_t ld, double gamma, double cliprew,
+                             double epsilon, void* stream);
 
 /* ---- rollout storage ----------------------------------------------------------------------------------- */
 /* GAE(gamma, lambda) reverse scan with done-masking + returns + global first/second moments.
@@ -290,10 +300,21 @@ int tpp_debug_tma_im2col(const float* x, int32_t B, int32_t H, int32_t W, int32_
 /* ---- policy: action sampling at rollout --------------------------------------------------------------- */
 /* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.
  * Replaces dist.sample()/log_prob in PPO.predict (agents/ppo.py:72-81, common/policy.py:74-87).
- * Philox(seed, env, tick + t_offset); greedy != 0 -> argmax.                                             */
+ * Philox(seed, env_offset + env, tick + t_offset); greedy != 0 -> argmax.  env_offset: index of row 0 among the
+ * rank's envs when the rollout runs in several env ranges (each range keeps its envs' random streams).      */
 int tpp_sample_actions(const float* head, int32_t ld_head, int32_t n_envs, int32_t n_actions, int32_t* act,
                        float* logp, float* value, uint64_t seed, const uint64_t* tick, uint64_t t_offset,
-                       int32_t greedy, void* stream);
+                       int32_t greedy, int32_t env_offset, void* stream);
+
+/* Rollout tail of an MLP policy in one launch: z = act(h W^T + b) for the LAST embedder layer (h [n_rows][ldh], K <= 256
+ * inputs, K % 4 == 0; W [L][K], L == 64 outputs (else TPP_ENOTSUP); relu != 0 applies max(.,0)), the policy / value heads
+ * (Wh [A+1][L], bh [A+1]) and tpp_sample_actions' draw, exact fp32 on the CUDA cores.  head_out (nullable)
+ * [n_rows][ld_head] receives the A logits + value.  Replaces MLPModel's last Linear (common/model.py:954-980),
+ * CategoricalPolicy.hidden_to_output (common/policy.py:74-87) and dist.sample()/log_prob (agents/ppo.py:77-79).  */
+int tpp_mlp_tail_sample(const float* h, int64_t ldh, int32_t K, const float* W, const float* b, int32_t L,
+                        int32_t relu, const float* Wh, const float* bh, int32_t n_actions, int32_t n_rows,
+                        float* head_out, int32_t ld_head, int32_t* act, float* logp, float* value, uint64_t seed,
+                        const uint64_t* tick, uint64_t t_offset, int32_t greedy, int32_t env_offset, void* stream);
 
 /* ---- PPO loss, fused forward + backward ---------------------------------------------------------------- */
 typedef struct {

@@ -274,3 +274,42 @@ def test_accumulation_groups_match_oracle_and_unfused(matmul, image):
     for k in results[1][1]:                                            # fused vs unfused: only summation order differs
         np.testing.assert_allclose(results["auto"][1][k].numpy(), results[1][1][k].numpy(), rtol=1e-4, atol=2e-6,
                                    err_msg=k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("image,N", [(False, 256), (True, 1000)])
+def test_rollout_tail_kernel_matches_gemm_head_and_sampler(image, N):
+    """Rollout step, policy side: trunk GEMMs + tpp_mlp_tail_sample (last layer, heads and the draw in one CUDA-core
+    launch) against the all-GEMM forward + tpp_sample_actions on the same slot: same draws, same log-probs / values."""
+    from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.engine import MLPEngineTC
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    from tpp_b200.common.storage import Storage
+    T, A = 4, 4
+    obs_shape = (3, 14, 14) if image else (9,)
+    torch.manual_seed(11)
+    pol = CategoricalPolicy(MLPModel(int(np.prod(obs_shape)), 4, 256, 64), False, A).to("cuda").flatten_()
+    with torch.no_grad():
+        pol.flat.mul_(3.0)                       # spread the logits so that the draws are not all near-uniform
+    st = Storage(obs_shape, 64, T, N, "cuda")
+    agent = PPO(None, pol, None, st, "cuda", 0, n_steps=T, n_envs=N, epoch=1, n_minibatch=1, mini_batch_size=N * T)
+    assert isinstance(agent.engine, MLPEngineTC) and agent.engine.tail_ok()
+    agent.engine.refresh_weights()
+    g = torch.Generator().manual_seed(5)
+    if image:
+        st.frames.copy_(torch.randint(0, 256, st.frames.shape, generator=g, dtype=torch.uint8).cuda())
+    else:
+        st.obs_batch[:] = torch.randn(T + 1, N, 9, generator=g).cuda()
+    outs = []
+    for fused in (True, False):
+        agent.fused_tail = fused
+        st.act_i32.fill_(-1)
+        agent._policy_sample(st, 2)
+        outs.append((st.act_i32[2, :N].clone(), st.logp[2, :N].clone(), st.value[2, :N].clone()))
+    (a1, l1, v1), (a0, l0, v0) = outs
+    assert (a1 >= 0).all() and (a1 < A).all() and len(a1.unique()) == A
+    assert (a1 == a0).float().mean() > 0.998          # a draw within ~1e-6 of a CDF step may fall either side
+    same = a1 == a0
+    torch.testing.assert_close(l1[same], l0[same], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(v1, v0, rtol=1e-4, atol=1e-5 * float(v0.abs().max()) + 2e-5)

@@ -57,3 +57,48 @@ def test_boxworld_train_runs():
     assert torch.isfinite(agent.policy.flat).all()
     rew, done, _ = agent.storage.fetch_log_data()
     assert set(np.unique(rew)).issubset({-1.0, 0.0, 1.0, 10.0, 11.0})
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_boxworld_rollout_in_env_ranges_equals_whole_batch_rollout(use_graph):
+    """The rollout of env ranges on concurrent streams (``rollout_chains``) must produce what the single-chain rollout
+    produces: per-env random streams are keyed by the env index, the level-seed counter is consumed in env order
+    (events between the ranges), and the reward normalisation runs once per rollout over all envs."""
+    from tpp_b200.boxworld.box_world_env_vec import create_bw_env
+    hp = dict(n_envs=512, grid_size=6, goal_length=2, num_distractor=1, distractor_length=1, max_steps=12)
+    outs = []
+    for chains in (1, 4, 2):
+        env = create_bw_env(None, hp)
+        agent = _agent(env, (3, 8, 8), 192, 24, 512, use_graph, rollout_chains=chains)
+        assert len(agent._env_ranges(env, agent.storage)) == chains
+        agent.train(24 * 512 * 3)
+        st = agent.storage
+        outs.append(dict(frames=st.frames.clone(), act=st.act_i32.clone(), done=st.done_u8.clone(),
+                         raw=st.env_rew_i32.clone(), rew=st.rew.clone(), value=st.value.clone(), logp=st.logp.clone(),
+                         seed=env.env._seed_counter.clone(), rms=env._rms.clone(), flat=agent.policy.flat.clone()))
+    assert (outs[0]["done"].sum() > 50) and (outs[0]["raw"] != 0).any()       # resets and rewards do occur
+    for o in outs[1:]:
+        for k in ("frames", "act", "done", "raw", "seed"):
+            assert torch.equal(outs[0][k], o[k]), k
+        for k in ("rew", "value", "logp", "rms", "flat"):
+            torch.testing.assert_close(outs[0][k], o[k], rtol=1e-5, atol=1e-6, msg=k)
+
+
+def test_vecnormalize_rollout_kernel_equals_per_step_kernel():
+    from tpp_b200 import _lib
+    T, N, ld = 37, 1000, 1024
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randint(-1, 12, (T, ld), generator=g, dtype=torch.int32).cuda()
+    done = (torch.rand(T, ld, generator=g) < 0.05).to(torch.uint8).cuda()
+    ret_a = torch.zeros(N, dtype=torch.float64, device="cuda"); ret_b = ret_a.clone()
+    rms_a = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device="cuda"); rms_b = rms_a.clone()
+    out_a = torch.zeros(T, ld, device="cuda"); out_b = out_a.clone(); raw_f = out_a.clone()
+    for t in range(T):
+        _lib.call("tpp_vecnormalize_step", _lib.ptr(ret_a), _lib.ptr(rms_a), _lib.ptr(raw[t]), 1, _lib.ptr(done[t]),
+                  _lib.ptr(out_a[t]), N, 0.999, 10.0, 1e-8, _lib.stream_ptr())
+    _lib.call("tpp_vecnormalize_rollout", _lib.ptr(ret_b), _lib.ptr(rms_b), _lib.ptr(raw), _lib.ptr(done),
+              _lib.ptr(out_b), _lib.ptr(raw_f), T, N, ld, 0.999, 10.0, 1e-8, _lib.stream_ptr())
+    torch.testing.assert_close(out_a[:, :N], out_b[:, :N], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(ret_a, ret_b, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(rms_a, rms_b, rtol=1e-12, atol=0)
+    assert torch.equal(raw_f[:, :N], raw[:, :N].float())

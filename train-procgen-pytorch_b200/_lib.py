@@ -71,7 +71,7 @@ SIGNATURES = {
     "tpp_env_step": [C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i64, _vp],
     "tpp_env_reset": [C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp, _u64, _i64, _vp],
     "tpp_tick_advance": [_vp, _u64, _vp],
-    "tpp_boxworld_step": [C.POINTER(BoxWorldState), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "tpp_boxworld_step": [C.POINTER(BoxWorldState), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_boxworld_gen_levels_host": [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp],
     "tpp_boxworld_gen_levels_device": [C.POINTER(BoxWorldState), _vp, _vp, _i32, _vp],
     "tpp_boxworld_emit_frames": [C.POINTER(BoxWorldState), _vp, _vp],
@@ -94,7 +94,10 @@ SIGNATURES = {
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
-    "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _vp],
+    "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _i32, _vp],
+    "tpp_mlp_tail_sample": [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _u64,
+                            _vp, _u64, _i32, _i32, _vp],
+    "tpp_vecnormalize_rollout": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f64, _f64, _f64, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],
     "tpp_ppo_loss_fwd_bwd_grouped": [C.POINTER(LossCfg), _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],

@@ -131,6 +131,12 @@ class PPO(BaseAgent):
         self.sample_seed = int(kwargs.get("sample_seed", 0))
         # minibatches of one gradient-accumulation window processed as one pass ("auto" = all, int = cap, 1 = off)
         self.fuse_accum = kwargs.get("fuse_accum", "auto")
+        # env ranges stepping through the rollout as concurrent kernel chains (an int or "auto"; default 1 = off:
+        # measured on B200 at 4096 envs, 1 / 2 / 4 chains take the same time -- the rollout is T sequential steps of
+        # dependent launches and a smaller range does not shorten a step; kept for larger env counts)
+        self.rollout_chains = kwargs.get("rollout_chains", 1)
+        # rollout: last embedder layer + heads + action draw in one CUDA-core launch (MLP policies, TC engine)
+        self.fused_tail = bool(kwargs.get("fused_tail", True))
         self.max_group_rows = int(kwargs.get("max_group_rows", 1 << 18))
 
         if policy.flat is None:
@@ -174,17 +180,22 @@ class PPO(BaseAgent):
         self.storage.world_size, self.storage.process_group = world_size, process_group
 
     # ------------------------------------------------------------------------------------------
-    def _policy_head(self, obs_slot, storage):
-        """Policy forward on a rollout slot -> head buffer [N, ld_head]."""
+    def _policy_head(self, obs_slot, storage, env_range=None, slot=0, trunk_only=False, obs_ready=False):
+        """Policy forward on a rollout slot (or on the env range ``(lo, hi)`` of an image slot, in workspace
+        ``slot``) -> head buffer [n, ld_head]."""
         N = storage.num_envs
         if storage.is_image:
+            lo, hi = env_range or (0, N)
+            n = hi - lo
             c, h, w = storage.obs_shape
-            mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
-            _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot), N, h, w, c, _lib.ptr(mb.obs), _lib.ptr(mb.obs_lo),
-                      mb.ld_obs, 1 if mb.raw else 0, _lib.stream_ptr())
-            self.n_launches += 1
-            return self._fwd(mb.obs, N, x_lo=mb.obs_lo, raw=mb.raw)
-        return self._fwd(obs_slot, N, feature_major_ld=storage.ld)
+            mb = storage.minibatch_buffers(n, *self._obs_buf_args(storage), slot=slot)
+            if not obs_ready:          # (obs_ready: the env's step kernel already wrote this slot's rows into mb.obs)
+                _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot[lo:hi]), n, h, w, c, _lib.ptr(mb.obs),
+                          _lib.ptr(mb.obs_lo), mb.ld_obs, 1 if mb.raw else 0, _lib.stream_ptr())
+                self.n_launches += 1
+            return self._fwd(mb.obs, n, x_lo=mb.obs_lo, raw=mb.raw, slot=slot, trunk_only=trunk_only)
+        assert env_range is None, "env ranges are implemented for image (row-major frame) slots"
+        return self._fwd(obs_slot, N, feature_major_ld=storage.ld, trunk_only=trunk_only)
 
     def _obs_buf_args(self, storage):
         """(row stride, split) of gathered-observation buffers: the TC engine wants TF32 pairs with ld = ceil32(in)."""
@@ -192,15 +203,41 @@ class PPO(BaseAgent):
             return self.engine.ld_in, ("raw" if self.engine.raw_pixels and storage.is_image else True)
         return _round4(storage.obs_width), False
 
-    def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False):
+    def _policy_sample(self, storage, t, env_range=None, slot=0, obs_ready=False):
+        """Rollout step t, policy side: forward on slot t (of an env range) and the action draw into act / logp /
+        value of slot t.  MLP policies on the tensor-core engine run the trunk as GEMMs and finish the last layer, the
+        heads and the draw in one launch (tpp_mlp_tail_sample)."""
+        lo, hi = env_range or (0, storage.num_envs)
+        n, eng = hi - lo, self.engine
+        act, logp, value = storage.act_i32[t, lo:hi], storage.logp[t, lo:hi], storage.value[t, lo:hi]
+        if self.fused_tail and isinstance(eng, MLPEngineTC) and eng.tail_ok():
+            h, ldh = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, trunk_only=True,
+                                       obs_ready=obs_ready)
+            w_off, b_off, fin, fout, relu = eng.layers[-1]
+            _lib.call("tpp_mlp_tail_sample", _lib.ptr(h), ldh, fin, eng._p(w_off), eng._p(b_off), fout,
+                      1 if relu else 0, eng._p(eng.head_w_off), eng._p(eng.head_b_off), self.n_actions, n, None,
+                      eng.ld_head, _lib.ptr(act), _lib.ptr(logp), _lib.ptr(value), self.sample_seed,
+                      _lib.ptr(self._tick), int(t), 0, int(lo), _lib.stream_ptr())
+            self.n_launches += 1
+            return
+        head = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, obs_ready=obs_ready)
+        self._sample(head, n, act, logp, value, t, env_offset=lo)
+
+    def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False, slot=0, trunk_only=False):
+        if trunk_only:
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False, raw=raw,
+                                       slot=slot, trunk_only=True)
         if isinstance(self.engine, MLPEngineTC):
-            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False, raw=raw)
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False, raw=raw,
+                                       slot=slot)
+        if slot:
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, slot=slot)
         return self.engine.forward(x, M, feature_major_ld=feature_major_ld)
 
-    def _sample(self, head, N, act, logp, value, t_offset, greedy=False):
+    def _sample(self, head, N, act, logp, value, t_offset, greedy=False, env_offset=0):
         _lib.call("tpp_sample_actions", _lib.ptr(head), self.engine.ld_head, N, self.n_actions, _lib.ptr(act),
                   _lib.ptr(logp), _lib.ptr(value), self.sample_seed, _lib.ptr(self._tick), int(t_offset),
-                  1 if greedy else 0, _lib.stream_ptr())
+                  1 if greedy else 0, int(env_offset), _lib.stream_ptr())
         self.n_launches += 1
 
     def predict(self, obs, hidden_state, done):
@@ -441,19 +478,78 @@ class PPO(BaseAgent):
     def _device_env(self, env):
         return hasattr(env, "rollout_step")
 
+    def _env_ranges(self, env, storage):
+        """Env ranges that step through the rollout as independent kernel chains on their own streams.  One step of
+        a few thousand envs is a chain of ~10 dependent launches of 30-130 CTAs each -- latency-bound, most SMs idle;
+        envs are independent, so ranges overlap each other's launches.  ``rollout_chains``: "auto" (ranges of >= 1024
+        envs, at most 4), an int, or 1 = off."""
+        N = storage.num_envs
+        want = self.rollout_chains
+        if not getattr(env, "supports_env_ranges", False) or not storage.is_image \
+                or not isinstance(self.engine, (MLPEngine, MLPEngineTC)):
+            return [(0, N)]
+        C = min(4, N // 1024) if want == "auto" else int(want)
+        C = max(1, min(C, N // 128))
+        step = -(-N // C // 128) * 128          # ranges start on multiples of 128 envs (GEMM row tiles)
+        return [(lo, min(N, lo + step)) for lo in range(0, N, step)]
+
     def _rollout_steps(self, env, storage):
         T, N = storage.num_steps, storage.num_envs
         if hasattr(self.engine, "refresh_weights"):
             self.engine.refresh_weights()     # always part of the (captured) rollout: weights changed since last time
-        for t in range(T):
-            head = self._policy_head(storage.obs_slot(t), storage)
-            self._sample(head, N, storage.act_i32[t], storage.logp[t], storage.value[t], t)
-            env.rollout_step(storage, t)
-        head = self._policy_head(storage.obs_slot(T), storage)
+        ranges = self._env_ranges(env, storage)
+        # envs that can emit the policy's next input rows from their step kernel (Box-World, raw-pixel first layer)
+        # save the frames -> obs launch of every step: only slot 0 is converted here
+        fold = (len(ranges) == 1 and getattr(env, "emits_policy_obs", False) and storage.is_image
+                and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels)
+        if fold:
+            mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
+            assert mb.raw and mb.obs_lo is None
+            for t in range(T):
+                self._policy_sample(storage, t, obs_ready=t > 0)
+                env.rollout_step(storage, t, obs_out=mb.obs)
+        elif len(ranges) == 1:
+            for t in range(T):
+                self._policy_sample(storage, t)
+                env.rollout_step(storage, t)
+        else:
+            self._rollout_chains(env, storage, ranges)
+        if hasattr(env, "finish_rollout"):
+            env.finish_rollout(storage)
+        head = self._policy_head(storage.obs_slot(T), storage, obs_ready=fold)
         storage.value[T, :N] = head[:N, self.n_actions]
         _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
         env.advance_tick(T)
         self.n_launches += 2
+
+    def _rollout_chains(self, env, storage, ranges):
+        """T steps of every env range, one stream per range (forked from / joined into the current stream, so the
+        whole thing is capturable as one CUDA graph with parallel branches).  The only cross-range dependency is the
+        env's sequential level-seed counter: the env transitions of one step run in ascending env order, and step
+        t + 1 of the first range follows step t of the last (events)."""
+        T = storage.num_steps
+        main = torch.cuda.current_stream()
+        if getattr(self, "_chain_streams", None) is None or len(self._chain_streams) != len(ranges):
+            self._chain_streams = [torch.cuda.Stream() for _ in ranges]
+        streams = self._chain_streams
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for s in streams:
+            s.wait_event(fork)
+        prev = None                                   # event after the previous env transition (global order)
+        for t in range(T):
+            for c, (lo, hi) in enumerate(ranges):
+                with torch.cuda.stream(streams[c]):
+                    self._policy_sample(storage, t, env_range=(lo, hi), slot=1 + c)
+                    if prev is not None:
+                        streams[c].wait_event(prev)
+                    env.rollout_step(storage, t, env_range=(lo, hi))
+                    prev = torch.cuda.Event()
+                    prev.record(streams[c])
+        for s in streams:
+            join = torch.cuda.Event()
+            join.record(s)
+            main.wait_event(join)
 
     def collect_rollout(self, env=None, storage=None):
         """T fused steps on the device (policy -> sample -> env) followed by the bootstrap value."""

@@ -58,8 +58,8 @@ class MLPEngine:
         self.n_launches = 0   # running count of this engine's kernel launches (for bench.py's gpu_launches)
 
     # ------------------------------------------------------------------------------------------
-    def _workspace(self, M):
-        ws = self._ws.get(M)
+    def _workspace(self, M, slot=0):
+        ws = self._ws.get((M, slot))
         if ws is None:
             ws = _Workspace()
             dev = self.device
@@ -67,7 +67,7 @@ class MLPEngine:
             ws.head = torch.zeros(M, self.ld_head, dtype=torch.float32, device=dev)
             ws.dhead = torch.zeros(M, self.ld_head, dtype=torch.float32, device=dev)
             ws.dbuf = [torch.empty(M, self.max_width, dtype=torch.float32, device=dev) for _ in range(2)]
-            self._ws[M] = ws
+            self._ws[(M, slot)] = ws
         return ws
 
     def _p(self, off):
@@ -82,10 +82,11 @@ class MLPEngine:
         self.n_launches += 1
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, x, M, feature_major_ld=None):
+    def forward(self, x, M, feature_major_ld=None, slot=0):
         """x: row-major [M, in_dim] tensor, or (with ``feature_major_ld``) a feature-major [in_dim, ld] rollout
-        slot.  Returns the head buffer [M, ld_head] = (A logits, value, zero padding)."""
-        ws = self._workspace(M)
+        slot.  Returns the head buffer [M, ld_head] = (A logits, value, zero padding).  ``slot`` selects a private
+        workspace (concurrent forwards of different env ranges on different streams)."""
+        ws = self._workspace(M, slot)
         a_ptr = _lib.ptr(x)
         sam, sak = (1, feature_major_ld) if feature_major_ld else (x.stride(0), 1)
         for i, (w_off, b_off, fin, fout, relu) in enumerate(self.layers):
@@ -236,8 +237,8 @@ class MLPEngineTC(MLPEngine):
                       _lib.ptr(self.w0_raw["lo"]), self.w0_raw["ldk"], None, None, 0, s)
             self.n_launches += 1
 
-    def _workspace(self, M):
-        ws = self._ws.get(M)
+    def _workspace(self, M, slot=0):
+        ws = self._ws.get((M, slot))
         if ws is None:
             ws = _Workspace()
             f = dict(dtype=torch.float32, device=self.device)
@@ -251,7 +252,7 @@ class MLPEngineTC(MLPEngine):
             ws.dz = [dict(plain=torch.zeros(M, mw, **f), hi=torch.zeros(M, mw, **f), lo=torch.zeros(M, mw, **f))
                      for _ in range(2)]
             ws.fm = None       # TF32 pair of a feature-major rollout slot, allocated on first use
-            self._ws[M] = ws
+            self._ws[(M, slot)] = ws
         return ws
 
     def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
@@ -284,6 +285,13 @@ class MLPEngineTC(MLPEngine):
         self.n_launches += 1
 
     # ------------------------------------------------------------------------------------------
+    def tail_ok(self):
+        """The rollout tail kernel covers the last embedder layer + heads (shape limits of tpp_mlp_tail_sample)."""
+        if len(self.layers) < 2:
+            return False
+        _, _, fin, fout, _ = self.layers[-1]
+        return fin <= 256 and fin % 4 == 0 and fout == 64 and self.A + 1 <= 16
+
     def _bn(self, M, N):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= 256 and M >= self.wide_tile_rows:
@@ -292,11 +300,14 @@ class MLPEngineTC(MLPEngine):
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
         return 0
 
-    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False):
+    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False, slot=0, trunk_only=False):
         """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given, or -- ``raw`` --
         integer pixel values 0..255 with row stride ``ld_in``), or with ``feature_major_ld`` a feature-major
-        [in_dim, ld] rollout slot."""
-        ws, s = self._workspace(M), _lib.stream_ptr()
+        [in_dim, ld] rollout slot.  ``slot``: private workspace for concurrent forwards on different streams.
+        ``trunk_only``: stop in front of the last embedder layer and return its input as plain fp32 ``(tensor, ld)`` --
+        the rollout finishes that layer, the heads and the action draw in one CUDA-core launch
+        (``tpp_mlp_tail_sample``)."""
+        ws, s = self._workspace(M, slot), _lib.stream_ptr()
         L = len(self.layers)
         if feature_major_ld:
             ld = feature_major_ld
@@ -318,9 +329,14 @@ class MLPEngineTC(MLPEngine):
             self.n_launches += 1
             cur, ld_cur, a_mn = (ws.x["hi"], ws.x["lo"]), self.ld_in, 0
         self._x_pair, self._x_ld, self._x_raw = (cur, ld_cur), None, raw
-        for i in range(L):
+        for i in range(L - 1 if trunk_only else L):
             w_off, b_off, fin, fout, relu = self.layers[i]
             h, w = ws.h[i], (self.w0_raw if raw and i == 0 else self.w[i])
+            if trunk_only and i == L - 2:       # plain fp32 only: its consumer is not a tensor-core GEMM
+                self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
+                         flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off), out=h["hi"], ldc=h["ld"],
+                         exact=TC_A_EXACT if raw and i == 0 else 0, block_n=self._bn(M, fout))
+                return h["hi"], h["ld"]
             self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
                      flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
                      out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"],

@@ -136,6 +136,8 @@ class Storage:
     def enable_raw_rewards(self):
         if self.env_rew is None:
             self.env_rew = torch.zeros(self.num_steps, self.ld, dtype=torch.float32, device=self.device)
+            # integer rewards as the env kernel writes them (normalised once per rollout, tpp_vecnormalize_rollout)
+            self.env_rew_i32 = torch.zeros(self.num_steps, self.ld, dtype=torch.int32, device=self.device)
 
     # ---- reference API: host-driven stores (compat path) -------------------------------------------------
     def _t(self, x, dtype):
@@ -209,9 +211,9 @@ class Storage:
             self.n_launches += 1
 
     # ---- minibatches -----------------------------------------------------------------------------------------
-    def minibatch_buffers(self, mb, ld_obs=None, split=False):
+    def minibatch_buffers(self, mb, ld_obs=None, split=False, slot=0):
         ld_obs = ld_obs or _round_up(self.obs_width, 4)
-        key = (mb, ld_obs, split)
+        key = (mb, ld_obs, split, slot)
         if key not in self._mb:
             self._mb[key] = MiniBatch(mb, self.obs_width, ld_obs, self.device, split)
         return self._mb[key]

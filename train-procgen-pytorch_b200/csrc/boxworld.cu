@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(1024) boxworld_scan_kernel(int32_t* scratch, i
 
 __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxworld_state st,
                                                                       const uint8_t* __restrict__ done_in,
-                                                                      uint8_t* __restrict__ frame_out, int use_prefix) {
+                                                                      uint8_t* __restrict__ frame_out, int use_prefix,
+                                                                      float* __restrict__ obs_out, int ld_obs) {
   __shared__ int red[32];
   __shared__ int base_s;
   __shared__ uint32_t mtbuf[BW_WARPS][624];
@@ -393,6 +394,24 @@ __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxwo
     }
     __syncwarp();
     if (frame_out) copy_frame(W, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
+  }
+  if (obs_out && e < st.n_envs) {
+    // every env: its (post-reset) frame as the policy's next input row -- channel-major integer pixel values as fp32
+    // (TransposeFrame; ScaledFloatFrame's 1/255 lives in the policy's first layer), i.e. what tpp_frames_to_obs(raw)
+    // would produce from slot t + 1 in a launch of its own
+    __syncwarp();
+    const uint8_t* W = st.world + (int64_t)e * cells * 3;
+    float* dst = obs_out + (int64_t)e * ld_obs;
+    int c = 0, p = lane;
+    for (int o = lane; o < ld_obs; o += 32) {
+      float v = 0.0f;
+      if (o < cells * 3) {
+        while (p >= cells) { p -= cells; ++c; }
+        v = (float)W[p * 3 + c];
+      }
+      p += 32;
+      dst[o] = v;
+    }
   }
   // last CTA to finish advances the seed counter by the total number of finished envs
   __shared__ bool last;
@@ -489,6 +508,128 @@ __global__ void __launch_bounds__(1024) vecnormalize_kernel(double* ret, double*
   }
 }
 
+// The T steps of a finished rollout, one after the other, in ONE launch: per step the same three passes as above.  A
+// thread keeps its envs' running returns in registers (4 x 1024 envs) and loads step t + 1's rewards / dones while the
+// block reduces step t (the loop is otherwise one L2 round trip per pass).
+__global__ void __launch_bounds__(1024) vecnormalize_rollout_kernel(double* ret, double* rms,
+                                                                    const int32_t* __restrict__ raw_rew,
+                                                                    const uint8_t* __restrict__ done,
+                                                                    float* __restrict__ out_rew,
+                                                                    float* __restrict__ out_raw, int T, int n, int64_t ld,
+                                                                    double gamma, double cliprew, double epsilon) {
+  constexpr int EPT = 4;                       // envs per thread (n <= 4096 takes this path)
+  __shared__ double red[32];
+  __shared__ double bc[2];
+  double mean = rms[0], var = rms[1], count = rms[2];      // running moments: maintained by thread 0
+  const double bn = (double)n;
+  if (n <= EPT * 1024) {
+    double rr[EPT];
+    int32_t rw_c[EPT];
+    uint8_t dn_c[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int i = threadIdx.x + j * 1024;
+      rr[j] = i < n ? ret[i] : 0.0;
+      rw_c[j] = i < n ? raw_rew[i] : 0;
+      dn_c[j] = i < n ? done[i] : 0;
+    }
+    for (int t = 0; t < T; ++t) {
+      int32_t rw_n[EPT];
+      uint8_t dn_n[EPT];
+      const int tn = t + 1 < T ? t + 1 : t;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {          // next step's inputs: in flight during this step's reductions
+        const int i = threadIdx.x + j * 1024;
+        rw_n[j] = i < n ? raw_rew[(int64_t)tn * ld + i] : 0;
+        dn_n[j] = i < n ? done[(int64_t)tn * ld + i] : 0;
+      }
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = threadIdx.x + j * 1024;
+        if (i < n) { rr[j] = rr[j] * gamma + (double)rw_c[j]; s += rr[j]; }
+      }
+      s = block_sum(s, red);
+      if (threadIdx.x == 0) bc[0] = s / bn;
+      __syncthreads();
+      const double bmean = bc[0];
+      double q = 0.0;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = threadIdx.x + j * 1024;
+        if (i < n) { const double d = rr[j] - bmean; q += d * d; }
+      }
+      q = block_sum(q, red);
+      if (threadIdx.x == 0) {                  // Chan merge of the batch moments into the running ones (one thread)
+        const double bvar = q / bn;
+        const double delta = bmean - mean, tot = count + bn;
+        const double m2 = var * count + bvar * bn + delta * delta * count * bn / tot;
+        mean = mean + delta * bn / tot;
+        var = m2 / tot;
+        count = tot;
+        bc[1] = sqrt(var + epsilon);
+      }
+      __syncthreads();
+      const double sd = bc[1];
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int i = threadIdx.x + j * 1024;
+        if (i < n) {
+          const double r = (double)rw_c[j];
+          double v = r / sd;
+          v = v < -cliprew ? -cliprew : (v > cliprew ? cliprew : v);
+          out_rew[(int64_t)t * ld + i] = (float)v;
+          if (out_raw) out_raw[(int64_t)t * ld + i] = (float)r;
+          if (dn_c[j]) rr[j] = 0.0;
+        }
+        rw_c[j] = rw_n[j];
+        dn_c[j] = dn_n[j];
+      }
+      __syncthreads();      // bc[] is rewritten by the next step
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+      const int i = threadIdx.x + j * 1024;
+      if (i < n) ret[i] = rr[j];
+    }
+  } else {
+    for (int t = 0; t < T; ++t) {
+      const int32_t* rw = raw_rew + (int64_t)t * ld;
+      const uint8_t* dn = done + (int64_t)t * ld;
+      double s = 0.0;
+      for (int i = threadIdx.x; i < n; i += 1024) { const double v = ret[i] * gamma + (double)rw[i]; ret[i] = v; s += v; }
+      s = block_sum(s, red);
+      if (threadIdx.x == 0) bc[0] = s / bn;
+      __syncthreads();
+      const double bmean = bc[0];
+      double q = 0.0;
+      for (int i = threadIdx.x; i < n; i += 1024) { const double d = ret[i] - bmean; q += d * d; }
+      q = block_sum(q, red);
+      if (threadIdx.x == 0) {                  // Chan merge of the batch moments into the running ones (one thread)
+        const double bvar = q / bn;
+        const double delta = bmean - mean, tot = count + bn;
+        const double m2 = var * count + bvar * bn + delta * delta * count * bn / tot;
+        mean = mean + delta * bn / tot;
+        var = m2 / tot;
+        count = tot;
+        bc[1] = sqrt(var + epsilon);
+      }
+      __syncthreads();
+      const double sd = bc[1];
+      for (int i = threadIdx.x; i < n; i += 1024) {
+        const double r = (double)rw[i];
+        double v = r / sd;
+        v = v < -cliprew ? -cliprew : (v > cliprew ? cliprew : v);
+        out_rew[(int64_t)t * ld + i] = (float)v;
+        if (out_raw) out_raw[(int64_t)t * ld + i] = (float)r;
+        if (dn[i]) ret[i] = 0.0;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) { rms[0] = mean; rms[1] = var; rms[2] = count; }
+}
+
 }  // namespace tpp
 
 static int bw_check(const tpp_boxworld_state* st) {
@@ -504,17 +645,18 @@ static int bw_check(const tpp_boxworld_state* st) {
 
 extern "C" int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* action, int32_t* reward_out,
                                  uint8_t* done_out, uint8_t* frame_out, int32_t* fin_ret, int32_t* fin_len,
-                                 uint8_t* fin_solved, void* stream) {
+                                 uint8_t* fin_solved, float* obs_out, int32_t ld_obs, void* stream) {
   const int rc = bw_check(st);
   if (rc) return rc;
   TPP_CHECK_ARG(action && reward_out && done_out);
+  TPP_CHECK_ARG(!obs_out || ld_obs >= 3 * (st->n + 2) * (st->n + 2));
   const int grid = tpp_ceil_div(st->n_envs, tpp::BW_WARPS);
   cudaStream_t s = tpp_stream(stream);
   tpp::boxworld_step_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, action, reward_out, done_out, frame_out, fin_ret,
                                                                fin_len, fin_solved);
   const int use_prefix = grid > 1024;
   if (use_prefix) tpp::boxworld_scan_kernel<<<1, 1024, 0, s>>>(st->scratch, grid);
-  tpp::boxworld_reset_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, done_out, frame_out, use_prefix);
+  tpp::boxworld_reset_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, done_out, frame_out, use_prefix, obs_out, ld_obs);
   TPP_LAUNCH_STATUS();
 }
 
@@ -546,6 +688,15 @@ extern "C" int tpp_boxworld_emit_frames(const tpp_boxworld_state* st, uint8_t* f
   TPP_CHECK_ARG(frame_out);
   tpp::boxworld_emit_kernel<<<tpp_ceil_div(st->n_envs, tpp::BW_WARPS), tpp::BW_WARPS * 32, 0, tpp_stream(stream)>>>(
       *st, frame_out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_vecnormalize_rollout(double* ret, double* rms, const int32_t* raw_rew, const uint8_t* done,
+                                        float* out_rew, float* out_raw, int32_t T, int32_t n_envs, int64_t ld,
+                                        double gamma, double cliprew, double epsilon, void* stream) {
+  TPP_CHECK_ARG(ret && rms && raw_rew && done && out_rew && T > 0 && n_envs > 0 && n_envs <= 65536 && ld >= n_envs);
+  tpp::vecnormalize_rollout_kernel<<<1, 1024, 0, tpp_stream(stream)>>>(ret, rms, raw_rew, done, out_rew, out_raw, T,
+                                                                      n_envs, ld, gamma, cliprew, epsilon);
   TPP_LAUNCH_STATUS();
 }
 

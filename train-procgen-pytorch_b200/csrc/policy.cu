@@ -115,13 +115,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 // ================================================================================================
 constexpr int MAX_A = 16;
 
-__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ head, int ld_head, int n_envs, int A,
-                                                     int32_t* __restrict__ act, float* __restrict__ logp,
-                                                     float* __restrict__ value, uint64_t seed, const uint64_t* tick,
-                                                     uint64_t t_offset, int greedy) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_envs) return;
-  const float* h = head + (int64_t)e * ld_head;
+// One env's action: softmax over the A logits of its head row, Philox inverse-CDF draw (or argmax), log-prob, value.
+__device__ __forceinline__ void sample_row(const float* __restrict__ h, int A, int env, uint64_t seed,
+                                           const uint64_t* tick, uint64_t t_offset, int greedy, int32_t* act,
+                                           float* logp, float* value) {
   float z[MAX_A];
   float mx = -CUDART_INF_F;
 #pragma unroll
@@ -140,7 +137,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ h
       if (j < A && z[j] > best) { best = z[j]; a = j; }
   } else {
     const uint64_t tk = (tick ? *tick : 0ull) + t_offset;
-    const uint4 r = Philox(seed)((uint32_t)e, (uint32_t)tk, (uint32_t)(tk >> 32), 0x5A17u);
+    const uint4 r = Philox(seed)((uint32_t)env, (uint32_t)tk, (uint32_t)(tk >> 32), 0x5A17u);
     const float u = u01(r.x);
     float cdf = 0.0f;
     bool found = false;
@@ -155,9 +152,112 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ h
 #pragma unroll
   for (int j = 0; j < MAX_A; ++j)
     if (j == a) la = z[j] - lse;
-  act[e] = a;
-  logp[e] = la;
-  value[e] = h[A];
+  *act = a;
+  *logp = la;
+  *value = h[A];
+}
+
+__global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ head, int ld_head, int n_envs, int A,
+                                                     int32_t* __restrict__ act, float* __restrict__ logp,
+                                                     float* __restrict__ value, uint64_t seed, const uint64_t* tick,
+                                                     uint64_t t_offset, int greedy, int env_offset) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_envs) return;
+  sample_row(head + (int64_t)e * ld_head, A, env_offset + e, seed, tick, t_offset, greedy, act + e, logp + e, value + e);
+}
+
+// Rollout tail of an MLP policy in ONE launch: last embedder layer z = act(h W^T + b) (K <= 256 inputs, 64 outputs),
+// both heads (A logits + value) and the action draw.  Exact fp32 FMAs on the CUDA cores: per step these are 3 dependent
+// launches of 8-13 us each on the tensor-core path (4096 rows: launch- and prologue-bound), one of ~5 us here.
+// CTA = 4 warps x 8 rows; a lane owns outputs (lane, lane + 32) of its warp's 8 rows: per 4 k it reads its two weight
+// float4s once (conflict-free, row pitch K + 4) and each row's activation float4 as a warp-wide broadcast -- 128 FMAs
+// per shared-memory wavefront (a row-per-thread mapping is shared-memory bound at 28).
+constexpr int TAIL_ROWS = 32, TAIL_L = 64, TAIL_RPW = 8;
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__global__ void __launch_bounds__(128) mlp_tail_sample_kernel(const float* __restrict__ h, int64_t ldh, int K,
+                                                              const float* __restrict__ W, const float* __restrict__ b,
+                                                              int relu, const float* __restrict__ Wh,
+                                                              const float* __restrict__ bh, int A, int n_rows,
+                                                              float* __restrict__ head_out, int ld_head,
+                                                              int32_t* __restrict__ act, float* __restrict__ logp,
+                                                              float* __restrict__ value, uint64_t seed,
+                                                              const uint64_t* tick, uint64_t t_offset, int greedy,
+                                                              int env_offset) {
+  extern __shared__ __align__(16) float tail_sm[];
+  constexpr int L = TAIL_L;
+  const int P = K + 4, nh = A + 1;
+  float* sW = tail_sm;                      // [L][P]
+  float* sH = sW + L * P;                   // [TAIL_ROWS][P]
+  float* sZ = sH + TAIL_ROWS * P;           // [TAIL_ROWS][L + 1]
+  float* sWh = sZ + TAIL_ROWS * (L + 1);    // [nh][L + 1]
+  float* sHd = sWh + nh * (L + 1);          // [TAIL_ROWS][nh + 1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, row0 = blockIdx.x * TAIL_ROWS;
+  const int K4 = K >> 2;
+  // cp.async fill: all 16-byte copies of a thread are in flight together (a load -> store loop pays one L2 round
+  // trip per iteration: measured 10 us of a 20 us kernel)
+  for (int l = warp; l < L; l += 4)
+    for (int k4 = lane; k4 < K4; k4 += 32)
+      cp_async16(sW + l * P + 4 * k4, W + (int64_t)l * K + 4 * k4);
+  for (int r = warp; r < TAIL_ROWS; r += 4)
+    for (int k4 = lane; k4 < K4; k4 += 32) {
+      if (row0 + r < n_rows) cp_async16(sH + r * P + 4 * k4, h + (int64_t)(row0 + r) * ldh + 4 * k4);
+      else *reinterpret_cast<float4*>(sH + r * P + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < nh * L; i += 128) sWh[(i / L) * (L + 1) + (i % L)] = __ldg(Wh + i);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float acc0[TAIL_RPW], acc1[TAIL_RPW];
+#pragma unroll
+  for (int r = 0; r < TAIL_RPW; ++r) acc0[r] = acc1[r] = 0.0f;
+  const float* w0p = sW + lane * P;
+  const float* w1p = sW + (lane + 32) * P;
+  const float* hp = sH + warp * TAIL_RPW * P;
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    const float4 w0 = *reinterpret_cast<const float4*>(w0p + k);
+    const float4 w1 = *reinterpret_cast<const float4*>(w1p + k);
+#pragma unroll
+    for (int r = 0; r < TAIL_RPW; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(hp + r * P + k);
+      acc0[r] = fmaf(x.x, w0.x, acc0[r]); acc1[r] = fmaf(x.x, w1.x, acc1[r]);
+      acc0[r] = fmaf(x.y, w0.y, acc0[r]); acc1[r] = fmaf(x.y, w1.y, acc1[r]);
+      acc0[r] = fmaf(x.z, w0.z, acc0[r]); acc1[r] = fmaf(x.z, w1.z, acc1[r]);
+      acc0[r] = fmaf(x.w, w0.w, acc0[r]); acc1[r] = fmaf(x.w, w1.w, acc1[r]);
+    }
+  }
+  const float b0 = __ldg(b + lane), b1 = __ldg(b + lane + 32);
+#pragma unroll
+  for (int r = 0; r < TAIL_RPW; ++r) {
+    float v0 = acc0[r] + b0, v1 = acc1[r] + b1;
+    if (relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+    float* z = sZ + (warp * TAIL_RPW + r) * (L + 1);
+    z[lane] = v0;
+    z[lane + 32] = v1;
+  }
+  __syncthreads();
+  for (int o = tid; o < TAIL_ROWS * nh; o += 128) {     // heads: (row, output j) pairs
+    const int rr = o / nh, j = o - rr * nh;
+    float v = __ldg(bh + j);
+    const float* z = sZ + rr * (L + 1);
+    const float* w = sWh + j * (L + 1);
+#pragma unroll 8
+    for (int l = 0; l < L; ++l) v = fmaf(z[l], w[l], v);
+    sHd[rr * (nh + 1) + j] = v;
+  }
+  __syncthreads();
+  if (tid < TAIL_ROWS && row0 + tid < n_rows) {
+    const int e = row0 + tid;
+    const float* hd = sHd + tid * (nh + 1);
+    if (head_out) {
+      for (int j = 0; j < nh; ++j) head_out[(int64_t)e * ld_head + j] = hd[j];
+    }
+    sample_row(hd, A, env_offset + e, seed, tick, t_offset, greedy, act + e, logp + e, value + e);
+  }
 }
 
 // ================================================================================================
@@ -385,12 +485,38 @@ extern "C" int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t 
 
 extern "C" int tpp_sample_actions(const float* head, int32_t ld_head, int32_t n_envs, int32_t n_actions, int32_t* act,
                                   float* logp, float* value, uint64_t seed, const uint64_t* tick, uint64_t t_offset,
-                                  int32_t greedy, void* stream) {
+                                  int32_t greedy, int32_t env_offset, void* stream) {
   TPP_CHECK_ARG(head && act && logp && value && n_envs > 0 && n_actions > 0 && n_actions <= tpp::MAX_A);
   TPP_CHECK_ARG(ld_head > n_actions);
   tpp::sample_kernel<<<tpp_ceil_div(n_envs, 256), 256, 0, tpp_stream(stream)>>>(head, ld_head, n_envs, n_actions, act,
                                                                                 logp, value, seed, tick, t_offset,
-                                                                                greedy);
+                                                                                greedy, env_offset);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_mlp_tail_sample(const float* h, int64_t ldh, int32_t K, const float* W, const float* b, int32_t L,
+                                   int32_t relu, const float* Wh, const float* bh, int32_t n_actions, int32_t n_rows,
+                                   float* head_out, int32_t ld_head, int32_t* act, float* logp, float* value,
+                                   uint64_t seed, const uint64_t* tick, uint64_t t_offset, int32_t greedy,
+                                   int32_t env_offset, void* stream) {
+  TPP_CHECK_ARG(h && W && b && Wh && bh && act && logp && value && n_rows > 0);
+  TPP_CHECK_ARG(K > 0 && K <= 256 && (K & 3) == 0 && ldh >= K && (ldh & 3) == 0);
+  if (L != tpp::TAIL_L) return TPP_ENOTSUP;
+  TPP_CHECK_ARG((reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  TPP_CHECK_ARG(n_actions > 0 && n_actions < tpp::MAX_A && (!head_out || ld_head > n_actions));
+  const int nh = n_actions + 1, P = K + 4;
+  const size_t smem = sizeof(float) * ((size_t)L * P + (size_t)tpp::TAIL_ROWS * P + (size_t)tpp::TAIL_ROWS * (L + 1) +
+                                       (size_t)nh * (L + 1) + (size_t)tpp::TAIL_ROWS * (nh + 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tpp::mlp_tail_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         128 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  tpp::mlp_tail_sample_kernel<<<tpp_ceil_div(n_rows, tpp::TAIL_ROWS), 128, smem, tpp_stream(stream)>>>(
+      h, ldh, K, W, b, relu, Wh, bh, n_actions, n_rows, head_out, ld_head, act, logp, value, seed, tick, t_offset, greedy,
+      env_offset);
   TPP_LAUNCH_STATUS();
 }
 
