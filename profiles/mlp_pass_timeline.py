@@ -22,12 +22,15 @@ def main():
     ap.add_argument("--matmul", default="tf32x3")
     ap.add_argument("--wide-tile-rows", type=int, default=None, help="override MLPEngineTC.wide_tile_rows")
     ap.add_argument("--small-tile-elems", type=int, default=None, help="override MLPEngineTC.small_tile_elems")
+    ap.add_argument("--pair-block-n", type=int, default=None, help="512: one tile per CTA pair, 513: persistent pairs")
     args = ap.parse_args()
     hp = dict(bench.WORKLOADS["boxworld"], matmul=args.matmul)
     agent, _ = bench.build_agent("boxworld", hp, 0, "cuda:0")
     st, env, eng = agent.storage, agent.env, agent.engine
     if args.wide_tile_rows is not None:
         eng.wide_tile_rows = args.wide_tile_rows
+    if args.pair_block_n is not None:
+        eng.pair_block_n = args.pair_block_n
     if args.small_tile_elems is not None:
         eng.small_tile_elems = args.small_tile_elems
     env.reset_rollout(st)

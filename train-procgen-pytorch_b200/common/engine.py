@@ -205,6 +205,7 @@ class MLPEngineTC(MLPEngine):
         # the machine with them: each CTA stages 128 rows of each operand for a 256 x 256 product, i.e. half the
         # L2 -> shared-memory bytes per FLOP of 128 x 128 tiles, which is what bounds these kernels (profiles/README.md)
         self.wide_tile_rows = 32768
+        self.pair_block_n = 513        # 512: one 256 x 256 tile per CTA pair; 513: persistent pairs looping over tiles
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
@@ -295,7 +296,7 @@ class MLPEngineTC(MLPEngine):
     def _bn(self, M, N):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= 256 and M >= self.wide_tile_rows:
-            return 512         # 256 x 256 tiles on CTA pairs (cta_group::2)
+            return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
         if N >= 128 and M * N <= self.small_tile_elems:
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
         return 0
@@ -394,7 +395,7 @@ class MLPEngineTC(MLPEngine):
             ctas = 2 * _ceil(fout, 256) * _ceil(fin, 256) if pair else _ceil(fout, 128) * _ceil(fin, 128)
             raw0 = i == 0 and self._x_raw         # gW1 = (1/255) dZ^T X_pixels, X exact: no lo half, two passes
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas), block_n=512 if pair else 128,
+                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas), block_n=self.pair_block_n if pair else 128,
                      exact=TC_B_EXACT if raw0 else 0, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad

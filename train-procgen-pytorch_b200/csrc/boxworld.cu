@@ -523,6 +523,10 @@ __global__ void __launch_bounds__(1024) vecnormalize_rollout_kernel(double* ret,
   double mean = rms[0], var = rms[1], count = rms[2];      // running moments: maintained by thread 0
   const double bn = (double)n;
   if (n <= EPT * 1024) {
+    // Rewards are small integers: the 32 values -8 .. 23 are normalised once per step by the lanes of warp 0 (which
+    // also keep the running moments, all lanes alike); every other reward value takes the division itself.
+    __shared__ float tab[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double rr[EPT];
     int32_t rw_c[EPT];
     uint8_t dn_c[EPT];
@@ -560,32 +564,42 @@ __global__ void __launch_bounds__(1024) vecnormalize_rollout_kernel(double* ret,
         if (i < n) { const double d = rr[j] - bmean; q += d * d; }
       }
       q = block_sum(q, red);
-      if (threadIdx.x == 0) {                  // Chan merge of the batch moments into the running ones (one thread)
+      if (wid == 0) {                          // Chan merge of the batch moments into the running ones
+        q = __shfl_sync(0xffffffffu, q, 0);
         const double bvar = q / bn;
         const double delta = bmean - mean, tot = count + bn;
         const double m2 = var * count + bvar * bn + delta * delta * count * bn / tot;
         mean = mean + delta * bn / tot;
         var = m2 / tot;
         count = tot;
-        bc[1] = sqrt(var + epsilon);
+        const double sd = sqrt(var + epsilon);
+        double v = (double)(lane - 8) / sd;
+        v = v < -cliprew ? -cliprew : (v > cliprew ? cliprew : v);
+        tab[lane] = (float)v;
+        if (lane == 0) bc[1] = sd;
       }
       __syncthreads();
-      const double sd = bc[1];
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         const int i = threadIdx.x + j * 1024;
         if (i < n) {
-          const double r = (double)rw_c[j];
-          double v = r / sd;
-          v = v < -cliprew ? -cliprew : (v > cliprew ? cliprew : v);
-          out_rew[(int64_t)t * ld + i] = (float)v;
+          const int r = rw_c[j];
+          float o;
+          if ((unsigned)(r + 8) < 32u) {
+            o = tab[r + 8];
+          } else {
+            double v = (double)r / bc[1];
+            v = v < -cliprew ? -cliprew : (v > cliprew ? cliprew : v);
+            o = (float)v;
+          }
+          out_rew[(int64_t)t * ld + i] = o;
           if (out_raw) out_raw[(int64_t)t * ld + i] = (float)r;
           if (dn_c[j]) rr[j] = 0.0;
         }
         rw_c[j] = rw_n[j];
         dn_c[j] = dn_n[j];
       }
-      __syncthreads();      // bc[] is rewritten by the next step
+      __syncthreads();      // bc[] / tab[] are rewritten by the next step
     }
 #pragma unroll
     for (int j = 0; j < EPT; ++j) {

@@ -36,6 +36,8 @@
 // common/model.py:954-980, common/policy.py:74-87, autograd of agents/ppo.py:170).
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "tpp_common.cuh"
 
 namespace tpp {
@@ -289,7 +291,11 @@ __device__ __forceinline__ float tf32_round(float x) {
 // (rank 0) issues the 256 x 256 x 8 MMAs for both, each CTA's TMEM receives its own 128 accumulator rows and each CTA
 // runs the epilogue of those rows.  Both CTAs' TMA loads signal the LEADER's full barrier; tcgen05.commit multicasts
 // the stage-free / accumulator-complete arrivals to both CTAs.
-template <int BLOCK_N, bool PAIR = false>
+// PERSIST (with PAIR): the pair loops over 256 x 256 work items like the narrow tiles do -- two TMEM accumulators (all 512
+// columns), the producer / MMA warps run into the next item while both CTAs' epilogue warps drain the previous one
+// (their transpose patches get their own shared memory; the pipeline keeps two 64 KB stages); the peer's epilogue warps
+// return an accumulator by arriving on the LEADER's barrier.
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false>
 __global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
@@ -304,7 +310,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
   constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;          // TMEM columns of one accumulator
-  constexpr uint32_t TMEM_COLS = NARROW ? 2 * ACC_COLS : ACC_COLS;
+  static_assert(!PERSIST || PAIR, "persistent wide tiles exist in the CTA-pair form only");
+  constexpr bool PERS = NARROW || PERSIST;                            // the CTA loops over work items
+  constexpr uint32_t TMEM_COLS = PERS ? 2 * ACC_COLS : ACC_COLS;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), a_major bit 15,
   // b_major bit 16 (1 = MN-major), N>>3 at bit 17, M>>4 at bit 24
   const uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
@@ -333,17 +341,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // Work items (tile, k-split) are flattened on grid.x (n tile fastest, then m tile, then split), so M is not limited
   // by the 65535 bound of grid.y.  A persistent CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...
   // Wide tiles: one work item per CTA on a (n tile, m tile, split) grid -- no index arithmetic on the critical path.
-  const int wbegin = NARROW ? (int)blockIdx.x : 0, wend = NARROW ? p.total_work : 1;
-  const int wstride = NARROW ? (int)gridDim.x : 1;
+  const int wbegin = PERS ? (int)(PAIR ? blockIdx.x >> 1 : blockIdx.x) : 0, wend = PERS ? p.total_work : 1;
+  const int wstride = PERS ? (int)(PAIR ? gridDim.x >> 1 : gridDim.x) : 1;
   const bool probe = p.dbg && blockIdx.x == 0 && (int)blockIdx.y == p.dbg_y && blockIdx.z == 0 && lane == 0;
 #define TPP_PROBE(i) do { if (probe) p.dbg[i] = clock64(); } while (0)
   if (warp == 0) TPP_PROBE(0);
   const int total_kb = (p.K + bk - 1) / bk;
 #define TPP_DECODE_WORK(w)                                                           \
   int m0, n0, kb0;                                                                   \
-  if (NARROW) {                                                                      \
+  if (PERS) {                                                                        \
     const int tile_ = (w) % p.ntiles, split_ = (w) / p.ntiles;                       \
-    m0 = (tile_ / p.ntn) * BLOCK_M;                                                  \
+    m0 = PAIR ? ((tile_ / p.ntn) * 2 + (int)cta_rank) * BLOCK_M : (tile_ / p.ntn) * BLOCK_M; \
     n0 = (tile_ % p.ntn) * BLOCK_N;                                                  \
     kb0 = split_ * p.kb_per_split;                                                   \
   } else if (PAIR) {   /* grid.x = 2 x n tiles (the pair), grid.y = 256-row tiles: this CTA owns 128 of the rows */ \
@@ -366,7 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, epi_warps(BLOCK_N));
+      mbar_init(tmem_empty + i, epi_warps(BLOCK_N) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogue warps, on the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -454,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
      TPP_DECODE_WORK(w)
      (void)m0; (void)n0; (void)kb0;
      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_i & 1) * ACC_COLS;
-     if (NARROW) {                                   // wait until the epilogue has drained this accumulator
+     if (PERS) {                                     // wait until the epilogue has drained this accumulator
        mbar_wait(tmem_empty + (acc_i & 1), ((acc_i >> 1) & 1) ^ 1);
        tc_fence_after();
      }
@@ -509,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
-    float* stg = reinterpret_cast<float*>(smem + (NARROW ? p.stg_offset : 0)) + ew * (32 * STG_PITCH);
+    float* stg = reinterpret_cast<float*>(smem + (PERS ? p.stg_offset : 0)) + ew * (32 * STG_PITCH);
     constexpr int GW = BLOCK_N < 32 ? BLOCK_N : 32;     // columns per staged group
     const int rr = lane >> 3, cc = (lane & 7) * 4;      // post-transpose mapping: 4 rows x (8 lanes x 4 columns)
     const bool atomic = p.flags & F_ATOMIC;
@@ -741,13 +749,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     if (!NARROW && p.colsum && !atomic) {      // all epilogue warps of the CTA: combine, then one atomic per column
       asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");
-      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N) * 32)
+      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N) * 32) {
         if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, cs_sh[i]);
+        if (PERSIST) cs_sh[i] = 0.0f;          // the next work item starts from zero ...
+      }
+      if (PERSIST) asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");   // ... in every warp's view
     }
-    if (NARROW) {                       // accumulator drained: hand it back to the MMA warp
+    if (PERS) {                         // accumulator drained: hand it back to the MMA warp (PAIR: the leader's)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + (acc_i & 1));
+      if (lane == 0) {
+        if (PAIR) {
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                           smem_u32(tmem_empty + (acc_i & 1)) & PEER_BIT_MASK)
+                       : "memory");
+        } else {
+          mbar_arrive(tmem_empty + (acc_i & 1));
+        }
+      }
     }
     }   // work items
     if (NARROW && p.colsum && !atomic) {
@@ -908,7 +927,7 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
 
-template <int BLOCK_N, bool PAIR = false>
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // B rows one CTA stages
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -971,7 +990,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.a_slot = BLOCK_M * bk * 4;
   p.b_slot = B_ROWS * bk * 4;
   const int stage_bytes = p.a_slot * nops_a + p.b_slot * nops_b;
-  int stages = (224 * 1024 - 1024 - 256 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
+  int stages = (224 * 1024 - 1024 - 256 - ((BLOCK_N <= 32 || PERSIST) ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
   if (stages < 1) return TPP_ENOTSUP;
   if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
@@ -984,11 +1003,11 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (few < 2) few = 2;
     if (stages > few) stages = few;
   }
-  if (stages > p.kb_per_split && BLOCK_N > 32) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
+  if (stages > p.kb_per_split && BLOCK_N > 32 && !PERSIST) stages = p.kb_per_split < 1 ? 1 : p.kb_per_split;
   p.stages = stages;
   constexpr bool NARROW = BLOCK_N <= 32;
   size_t region = (size_t)stages * stage_bytes;
-  if (NARROW) {
+  if (NARROW || PERSIST) {
     // persistent CTAs: the epilogue's transpose patches get their own region (the next tile's loads are in flight)
     p.stg_offset = (int)region;
     region += stg_bytes(BLOCK_N);
@@ -1001,13 +1020,13 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   p.ntn = (g->N + BLOCK_N - 1) / BLOCK_N;
-  p.ntiles = p.ntn * ((g->M + BLOCK_M - 1) / BLOCK_M);
+  p.ntiles = p.ntn * ((g->M + (PAIR ? 2 : 1) * BLOCK_M - 1) / ((PAIR ? 2 : 1) * BLOCK_M));   // PAIR: 256-row tiles
   p.total_work = p.ntiles * split_k;
   unsigned grid_x = (unsigned)p.total_work;
   if (NARROW) {
@@ -1021,7 +1040,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     static int regs_per_cta = 0;
     if (!regs_per_cta) {
       cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR>) != cudaSuccess) return TPP_ENOTSUP;
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>) != cudaSuccess) return TPP_ENOTSUP;
       regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N);
     }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -1046,6 +1065,13 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     if (ntm2 > 65535) return TPP_ENOTSUP;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * (unsigned)p.ntn, (unsigned)ntm2, (unsigned)split_k);
+    if (PERSIST) {                 // one pair per two SMs, each looping over the (tile, split) work items
+      int sms = 0, dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const unsigned pairs = (unsigned)std::min(p.total_work, sms / 2);
+      cfg.gridDim = dim3(2u * pairs, 1, 1);
+    }
     cfg.blockDim = dim3(num_threads(BLOCK_N), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -1053,11 +1079,11 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     if (e != cudaSuccess) return (int)e;
     TPP_LAUNCH_STATUS();
   }
-  gemm_tc_kernel<BLOCK_N, PAIR><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  gemm_tc_kernel<BLOCK_N, PAIR, false><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
 
@@ -1085,6 +1111,7 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
     case 128: return tpp::tc::launch<128>(g, g->split_k, s);
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
     case 512: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile on a CTA pair (cta_group::2)
+    case 513: return tpp::tc::launch<256, true, true>(g, g->split_k, s);   // ... with persistent pairs
     default: return TPP_ENOTSUP;
   }
 }

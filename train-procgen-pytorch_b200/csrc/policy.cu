@@ -169,16 +169,17 @@ __global__ void __launch_bounds__(256) sample_kernel(const float* __restrict__ h
 // Rollout tail of an MLP policy in ONE launch: last embedder layer z = act(h W^T + b) (K <= 256 inputs, 64 outputs),
 // both heads (A logits + value) and the action draw.  Exact fp32 FMAs on the CUDA cores: per step these are 3 dependent
 // launches of 8-13 us each on the tensor-core path (4096 rows: launch- and prologue-bound), one of ~5 us here.
-// CTA = 4 warps x 8 rows; a lane owns outputs (lane, lane + 32) of its warp's 8 rows: per 4 k it reads its two weight
-// float4s once (conflict-free, row pitch K + 4) and each row's activation float4 as a warp-wide broadcast -- 128 FMAs
-// per shared-memory wavefront (a row-per-thread mapping is shared-memory bound at 28).
-constexpr int TAIL_ROWS = 32, TAIL_L = 64, TAIL_RPW = 8;
+// CTA = 8 warps x 4 rows; a lane owns outputs (lane, lane + 32) of its warp's 4 rows: per 4 k it reads its two weight
+// float4s once (conflict-free, row pitch K + 4) and each row's activation float4 as a warp-wide broadcast -- 85 FMAs
+// per shared-memory wavefront (a row-per-thread mapping is shared-memory bound at 28); the loads of a k-step are issued
+// together, two warps per scheduler cover their latency.
+constexpr int TAIL_ROWS = 32, TAIL_L = 64, TAIL_RPW = 4, TAIL_WARPS = TAIL_ROWS / TAIL_RPW;
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                "l"(gmem_src)
                : "memory");
 }
-__global__ void __launch_bounds__(128) mlp_tail_sample_kernel(const float* __restrict__ h, int64_t ldh, int K,
+__global__ void __launch_bounds__(TAIL_WARPS * 32) mlp_tail_sample_kernel(const float* __restrict__ h, int64_t ldh, int K,
                                                               const float* __restrict__ W, const float* __restrict__ b,
                                                               int relu, const float* __restrict__ Wh,
                                                               const float* __restrict__ bh, int A, int n_rows,
@@ -199,16 +200,16 @@ __global__ void __launch_bounds__(128) mlp_tail_sample_kernel(const float* __res
   const int K4 = K >> 2;
   // cp.async fill: all 16-byte copies of a thread are in flight together (a load -> store loop pays one L2 round
   // trip per iteration: measured 10 us of a 20 us kernel)
-  for (int l = warp; l < L; l += 4)
+  for (int l = warp; l < L; l += TAIL_WARPS)
     for (int k4 = lane; k4 < K4; k4 += 32)
       cp_async16(sW + l * P + 4 * k4, W + (int64_t)l * K + 4 * k4);
-  for (int r = warp; r < TAIL_ROWS; r += 4)
+  for (int r = warp; r < TAIL_ROWS; r += TAIL_WARPS)
     for (int k4 = lane; k4 < K4; k4 += 32) {
       if (row0 + r < n_rows) cp_async16(sH + r * P + 4 * k4, h + (int64_t)(row0 + r) * ldh + 4 * k4);
       else *reinterpret_cast<float4*>(sH + r * P + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int i = tid; i < nh * L; i += 128) sWh[(i / L) * (L + 1) + (i % L)] = __ldg(Wh + i);
+  for (int i = tid; i < nh * L; i += TAIL_WARPS * 32) sWh[(i / L) * (L + 1) + (i % L)] = __ldg(Wh + i);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float acc0[TAIL_RPW], acc1[TAIL_RPW];
@@ -221,9 +222,12 @@ __global__ void __launch_bounds__(128) mlp_tail_sample_kernel(const float* __res
   for (int k = 0; k < K; k += 4) {
     const float4 w0 = *reinterpret_cast<const float4*>(w0p + k);
     const float4 w1 = *reinterpret_cast<const float4*>(w1p + k);
+    float4 xs[TAIL_RPW];
+#pragma unroll
+    for (int r = 0; r < TAIL_RPW; ++r) xs[r] = *reinterpret_cast<const float4*>(hp + r * P + k);
 #pragma unroll
     for (int r = 0; r < TAIL_RPW; ++r) {
-      const float4 x = *reinterpret_cast<const float4*>(hp + r * P + k);
+      const float4 x = xs[r];
       acc0[r] = fmaf(x.x, w0.x, acc0[r]); acc1[r] = fmaf(x.x, w1.x, acc1[r]);
       acc0[r] = fmaf(x.y, w0.y, acc0[r]); acc1[r] = fmaf(x.y, w1.y, acc1[r]);
       acc0[r] = fmaf(x.z, w0.z, acc0[r]); acc1[r] = fmaf(x.z, w1.z, acc1[r]);
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(128) mlp_tail_sample_kernel(const float* __res
     z[lane + 32] = v1;
   }
   __syncthreads();
-  for (int o = tid; o < TAIL_ROWS * nh; o += 128) {     // heads: (row, output j) pairs
+  for (int o = tid; o < TAIL_ROWS * nh; o += TAIL_WARPS * 32) {     // heads: (row, output j) pairs
     const int rr = o / nh, j = o - rr * nh;
     float v = __ldg(bh + j);
     const float* z = sZ + rr * (L + 1);
@@ -514,7 +518,7 @@ extern "C" int tpp_mlp_tail_sample(const float* h, int64_t ldh, int32_t K, const
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  tpp::mlp_tail_sample_kernel<<<tpp_ceil_div(n_rows, tpp::TAIL_ROWS), 128, smem, tpp_stream(stream)>>>(
+  tpp::mlp_tail_sample_kernel<<<tpp_ceil_div(n_rows, tpp::TAIL_ROWS), tpp::TAIL_WARPS * 32, smem, tpp_stream(stream)>>>(
       h, ldh, K, W, b, relu, Wh, bh, n_actions, n_rows, head_out, ld_head, act, logp, value, seed, tick, t_offset, greedy,
       env_offset);
   TPP_LAUNCH_STATUS();
