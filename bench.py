@@ -255,11 +255,15 @@ def gemm_roofline(agent, in_dim, hp, pk):
     if isinstance(eng, MLPEngineTC):
         w, h = (eng.w0_raw if raw else eng.w[0]), ws.h[0]
         a = (x, x) if raw else (ws.x["hi"], ws.x["lo"])
+        bn = eng._bn(mb, fout)
         one = lambda: eng._tc(a, eng.ld_in, (w["hi"], w["lo"]), w["ldk"], mb, fout, fin,
                               flags=EPI_BIAS | EPI_RELU, bias=eng._p(b_off), out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
-                              exact=TC_A_EXACT if raw else 0)
-        name = "gemm_tc_kernel<128> (tcgen05 kind::tf32, %s%s)" % (
-            "3xTF32" if eng.precision == 3 else "1xTF32",
+                              exact=TC_A_EXACT if raw else 0, block_n=bn)
+        tile = {0: "gemm_tc_kernel<128>", 64: "gemm_tc_kernel<64>", 256: "gemm_tc_kernel<256>",
+                512: "gemm_tc_kernel<256, pair> (256x256 tile on a CTA pair, cta_group::2)",
+                513: "gemm_tc_kernel<256, pair, persistent> (256x256 tiles on persistent CTA pairs, cta_group::2)"}[bn]
+        name = "%s (tcgen05 kind::tf32, %s%s)" % (
+            tile, "3xTF32" if eng.precision == 3 else "1xTF32",
             ", pixel operand exact in TF32: 2 of the 3 passes" if raw and eng.precision == 3 else "")
     else:
         one = lambda: eng._gemm(ptr(x), x.stride(0), 1, eng._p(w_off), fin, 1, ptr(ws.acts[0]), fout, eng._p(b_off),
@@ -270,7 +274,7 @@ def gemm_roofline(agent, in_dim, hp, pk):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-        traffic = json.load(open(tpath)).get(f"gemm_tc_kernel<128>[{mb},{fout},{fin}]")
+        traffic = json.load(open(tpath)).get(f"gemm_tc_kernel[{mb},{fout},{fin}]")
     return dict(kernel=name, shape=[mb, fout, fin], bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
                 unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=traffic, us_per_launch=round(dt * 1e6, 2),
                 policy_fwd_bwd_tflops=round(flops_all / dt_all / 1e12, 2),
@@ -394,7 +398,7 @@ def run_ours(args):
     e2e_value = total_steps / (ms_e2e * 1e-3)
     n_mb = (T * N) // mb
     h2d = hp["epoch"] * n_mb * mb * 8 + 8
-    d2h = hp["epoch"] * n_mb * 20 * 8 + 2 * T * N * 4
+    d2h = hp["epoch"] * n_mb * 20 * 8 + T * st.ld * (4 + 1)      # loss statistics + (raw reward f32, done u8) batches
     roof = gemm_roofline(agent, in_dim, hp, pk)
     extra = kernel_rooflines(pk, device) if not args.no_kernel_rooflines else []
     cpu = cpu_baseline(args.workload, budget_s=20.0) if not args.no_cpu_baseline else None
@@ -409,7 +413,9 @@ def run_ours(args):
                    "larger than 126 MB)" if args.workload == "boxworld" else "small working set (latency-bound)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
-                "api": "PPO.train(): host randperm -> pinned H2D per epoch; D2H loss summary + logger batches"},
+                "api": "PPO.train(): host randperm -> pinned H2D per epoch (copy stream, overlapping the previous epoch); "
+                       "D2H loss statistics + logger batches into pinned buffers, read by the host after the next "
+                       "rollout is enqueued"},
         "gpu_launches": int(launches), "clocks": clk, "replicas_in_sync": in_sync, "roofline": roof,
         "kernel_rooflines": extra,
         "cpu_baseline": cpu,

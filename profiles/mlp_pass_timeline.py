@@ -29,6 +29,8 @@ def main():
     st, env, eng = agent.storage, agent.env, agent.engine
     if args.wide_tile_rows is not None:
         eng.wide_tile_rows = args.wide_tile_rows
+    if os.environ.get("TPP_PAIR_MIN_N"):
+        eng.pair_min_n = int(os.environ["TPP_PAIR_MIN_N"])
     if args.pair_block_n is not None:
         eng.pair_block_n = args.pair_block_n
     if args.small_tile_elems is not None:

@@ -235,12 +235,15 @@ def test_accumulation_groups_match_oracle_and_unfused(matmul, image):
                value=torch.randn(T + 1, N, generator=g) * 0.3, rew=torch.randn(T, N, generator=g),
                done=(torch.rand(T, N, generator=g) < 0.1).to(torch.uint8))
     results = {}
-    for fuse in ("auto", 2, 1):
+    for fuse in ("auto", 2, 1, "per-group graphs"):
         torch.manual_seed(4)
         pol = CategoricalPolicy(MLPModel(in_dim, 4, 64, 32), False, A).to("cuda").flatten_()
         init = {k: v.detach().cpu().clone() for k, v in pol.state_dict().items()}
         st = Storage(obs_shape, 32, T, N, "cuda")
-        agent = PPO(None, pol, None, st, "cuda", 0, fuse_accum=fuse, **kw)
+        if fuse == "per-group graphs":         # the path multi-GPU runs take (all-reduce between group and step)
+            agent = PPO(None, pol, None, st, "cuda", 0, fuse_accum="auto", epoch_graph=False, **kw)
+        else:
+            agent = PPO(None, pol, None, st, "cuda", 0, fuse_accum=fuse, **kw)
         if image:
             st.frames.copy_(frames.cuda())
         else:
@@ -250,7 +253,7 @@ def test_accumulation_groups_match_oracle_and_unfused(matmul, image):
         st.compute_estimates(0.99, 0.95, True, True)
         torch.manual_seed(99)
         summary = agent.optimize()
-        assert agent._group_size(4, 8, 256, agent.engine) == {"auto": 4, 2: 2, 1: 1}[fuse]
+        assert agent._group_size(4, 8, 256, agent.engine) == {"auto": 4, 2: 2, 1: 1, "per-group graphs": 4}[fuse]
         assert agent.optimizer.step_count == 2 * 2
         results[fuse] = (summary, {k: v.detach().cpu() for k, v in pol.state_dict().items()},
                          {k: np.array(v) for k, v in agent.last_stats.items()})

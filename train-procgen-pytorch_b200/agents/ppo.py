@@ -129,6 +129,7 @@ class PPO(BaseAgent):
         self.adjust_lr = adjust_lr_grok if increasing_lr else adjust_lr
         self.use_cuda_graph = bool(kwargs.get("use_cuda_graph", True))
         self.sample_seed = int(kwargs.get("sample_seed", 0))
+        self.use_epoch_graph = bool(kwargs.get("epoch_graph", True))    # False: per-group graphs (the multi-GPU path)
         # minibatches of one gradient-accumulation window processed as one pass ("auto" = all, int = cap, 1 = off)
         self.fuse_accum = kwargs.get("fuse_accum", "auto")
         # env ranges stepping through the rollout as concurrent kernel chains (an int or "auto"; default 1 = off:
@@ -259,7 +260,10 @@ class PPO(BaseAgent):
         return act, logp, value, hidden_state
 
     # ------------------------------------------------------------------------------------------
-    def optimize(self):
+    def optimize(self, defer_summary=False):
+        """Reference signature ``optimize() -> summary dict``.  ``defer_summary=True`` returns a closure producing the
+        dict instead: everything is enqueued, the device -> host read of the statistics happens when it is called."""
+        self._defer_summary = defer_summary
         if self.entropy_scaling == "reward_based":
             mean_rew = np.mean(self.logger.episode_reward_buffer)
             self.entropy_multiplier = 1 - ((mean_rew - self.min_rew) / (self.max_rew - self.min_rew))
@@ -343,7 +347,8 @@ class PPO(BaseAgent):
         # and the optimizer steps + weight re-splits at their fixed positions are ONE graph replay per epoch; the
         # epoch's permutation is uploaded into a static index buffer first.  Removes the per-group graph launches, index
         # copies and stats copies of an iteration from the host's critical path.
-        epoch_graph = (use_graph and self.world_size == 1 and step_every > 0 and n_mb % step_every == 0
+        epoch_graph = (use_graph and self.use_epoch_graph and self.world_size == 1 and step_every > 0
+                       and n_mb % step_every == 0
                        and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0
                        and self.entropy_scaling is None)
         if epoch_graph:
@@ -365,8 +370,38 @@ class PPO(BaseAgent):
             def counts():
                 return (self.n_launches, self.engine.n_launches, self.storage.n_launches, self.optimizer.n_launches)
 
-            for _ in range(self.epoch):
-                self._epoch_idx.copy_(st.epoch_indices(mb))
+            # Index upload: epoch e + 1's permutation is drawn on the host and copied up on a side stream while epoch e's
+            # graph runs (double-buffered staging), unless the caller supplies device-resident indices itself
+            # (``storage.epoch_indices`` replaced, as bench.py's device-timed leg does).
+            pipelined = "epoch_indices" not in st.__dict__
+            if pipelined:
+                main = torch.cuda.current_stream()
+                if getattr(self, "_h2d_stream", None) is None:
+                    self._h2d_stream = torch.cuda.Stream()
+                if getattr(self, "_idx_stage", None) is None or self._idx_stage[0].shape != (n_mb, mb):
+                    self._idx_stage = [torch.zeros(n_mb, mb, dtype=torch.int64, device=dev) for _ in range(2)]
+                    self._stage_free = [None, None]
+
+                def upload(e):
+                    host, slot_state = st.epoch_perm_pinned(mb, e)
+                    side = self._h2d_stream
+                    if self._stage_free[e % 2] is not None:
+                        side.wait_event(self._stage_free[e % 2])      # main has consumed this staging buffer
+                    with torch.cuda.stream(side):
+                        self._idx_stage[e % 2].copy_(host, non_blocking=True)
+                        done = torch.cuda.Event()
+                        done.record(side)
+                    slot_state[1] = done
+                    return done
+                pending = upload(0)
+            for e in range(self.epoch):
+                if pipelined:
+                    main.wait_event(pending)
+                    self._epoch_idx.copy_(self._idx_stage[e % 2])
+                    self._stage_free[e % 2] = torch.cuda.Event()
+                    self._stage_free[e % 2].record(main)
+                else:
+                    self._epoch_idx.copy_(st.epoch_indices(mb))
                 self.optimizer._sync_lr()
                 entry = egraphs.get(ekey)
                 if entry is None:                      # first epoch ever: eager (allocates workspaces)
@@ -388,6 +423,8 @@ class PPO(BaseAgent):
                     self.engine.n_launches += entry[1][1]
                     self.storage.n_launches += entry[1][2]
                     self.optimizer.n_launches += entry[1][3]
+                if pipelined and e + 1 < self.epoch:
+                    pending = upload(e + 1)             # host draw + H2D overlap the epoch just launched
                 self._stats[k:k + n_mb].copy_(self._epoch_stats)
                 k += n_mb
             return self._summary(fs_vals)
@@ -448,9 +485,22 @@ class PPO(BaseAgent):
         return self._dhead_buf
 
     def _summary(self, fs_vals):
+        if getattr(self, "_defer_summary", False):
+            if getattr(self, "_stats_host", None) is None or self._stats_host.shape != self._stats.shape:
+                self._stats_host = torch.empty(self._stats.shape, dtype=torch.float64).pin_memory()
+            self._stats_host.copy_(self._stats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+
+            def finish():
+                ev.synchronize()
+                return self._summary_from(self._stats_host.numpy(), fs_vals)
+            return finish
+        return self._summary_from(self._stats.cpu().numpy(), fs_vals)
+
+    def _summary_from(self, S, fs_vals):
         """One device->host read of the accumulated sums, then the reference's nine summary keys in order
         (agents/ppo.py:199-207).  Loss/pi and Loss/v keep the reference's sign quirk (negated)."""
-        S = self._stats.cpu().numpy()
         A = self.n_actions
         B = S[:, 3]
         pi_loss = -S[:, 0] / B
@@ -589,33 +639,52 @@ class PPO(BaseAgent):
         self.env.reset_rollout(self.storage)
         if self.env_valid is not None:
             self.env_valid.reset_rollout(self.storage_valid)
-        while self.t < num_timesteps:
+
+        def rollouts():
             self.policy.eval()
             self.collect_rollout(self.env, self.storage)
             self.storage.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
             if self.env_valid is not None:
                 self.collect_rollout(self.env_valid, self.storage_valid)
                 self.storage_valid.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
-            summary = self.optimize()
+
+        # Software pipeline of the host side: iteration i's update is enqueued, its statistics / log batches start their
+        # device -> host copies, and iteration i + 1's rollout (which only needs the updated weights, in stream order) is
+        # enqueued BEFORE the host waits for those copies and runs the logger -- the GPU never idles behind host work.
+        rollouts()
+        while self.t < num_timesteps:
+            summary_fn = self.optimize(defer_summary=True)
+            logs = None
+            if self.logger is not None:
+                logs = (self.storage.snapshot_log_data(),
+                        self.storage_valid.snapshot_log_data() if self.storage_valid is not None else None)
             self.t += self.n_steps * self.n_envs
-            self._log(summary, num_timesteps)
             self._carry_over(self.storage)
             if self.env_valid is not None:
                 self._carry_over(self.storage_valid)
-            if self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]:
+            save = self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]
+            if save:                                   # (weights of iteration i: before the next update exists)
                 self.save_checkpoint()
                 checkpoint_cnt += 1
+            # the learning rate of the next update is set by _log (adjust_lr), i.e. before the next optimize()
+            if self.t < num_timesteps:
+                rollouts()
+            self._log(summary_fn(), num_timesteps, logs)
         self.env.close()
         if self.env_valid is not None:
             self.env_valid.close()
 
-    def _log(self, summary, num_timesteps):
+    def _log(self, summary, num_timesteps, snapshots=None):
         if self.logger is not None:
-            rew_batch, done_batch, tar = self.storage.fetch_log_data()
-            if self.storage_valid is not None:
-                rew_v, done_v, tar_v = self.storage_valid.fetch_log_data()
+            if snapshots is not None:
+                rew_batch, done_batch, tar = snapshots[0]()
+                rew_v, done_v, tar_v = snapshots[1]() if snapshots[1] is not None else (None, None, None)
             else:
-                rew_v = done_v = tar_v = None
+                rew_batch, done_batch, tar = self.storage.fetch_log_data()
+                if self.storage_valid is not None:
+                    rew_v, done_v, tar_v = self.storage_valid.fetch_log_data()
+                else:
+                    rew_v = done_v = tar_v = None
             self.logger.feed(rew_batch, done_batch, tar, rew_v, done_v, tar_v)
         self.optimizer, lr = self.adjust_lr(self.optimizer, self.learning_rate, self.t, num_timesteps)
         if self.logger is not None:

@@ -205,6 +205,7 @@ class MLPEngineTC(MLPEngine):
         # the machine with them: each CTA stages 128 rows of each operand for a 256 x 256 product, i.e. half the
         # L2 -> shared-memory bytes per FLOP of 128 x 128 tiles, which is what bounds these kernels (profiles/README.md)
         self.wide_tile_rows = 32768
+        self.pair_min_n = 256
         self.pair_block_n = 513        # 512: one 256 x 256 tile per CTA pair; 513: persistent pairs looping over tiles
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
@@ -295,7 +296,7 @@ class MLPEngineTC(MLPEngine):
 
     def _bn(self, M, N):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
-        if N >= 256 and M >= self.wide_tile_rows:
+        if N >= self.pair_min_n and M >= self.wide_tile_rows:
             return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
         if N >= 128 and M * N <= self.small_tile_elems:
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work

@@ -228,6 +228,24 @@ class Storage:
         idx = perm[:n_mb * mini_batch_size].view(n_mb, mini_batch_size)
         return idx.pin_memory().to(self.device, non_blocking=True)
 
+    def epoch_perm_pinned(self, mini_batch_size, slot):
+        """The same draw as ``epoch_indices`` left in a reusable pinned host buffer (``slot``): the caller uploads it
+        on a copy stream while the previous epoch's kernels run.  Returns (pinned int64 [n_mb, mb], ready event or
+        None): the event of the last upload from this buffer must have completed before it is overwritten."""
+        batch = self.num_steps * self.num_envs
+        n_mb = batch // mini_batch_size
+        pool = self.__dict__.setdefault("_perm_pool", {})
+        key = (slot, n_mb, mini_batch_size)
+        if key not in pool:
+            pool[key] = [torch.empty(n_mb, mini_batch_size, dtype=torch.int64).pin_memory(), None]
+        buf, busy = pool[key]
+        if busy is not None:
+            busy.synchronize()                      # the previous upload from this buffer has left the host
+        perm = torch.randperm(batch)
+        self.last_perm = perm
+        buf.view(-1).copy_(perm[:n_mb * mini_batch_size])
+        return buf, pool[key]
+
     def gather(self, idx_row, out):
         """Gather one minibatch (device int64 indices [mb]) into ``out`` (a MiniBatch)."""
         s, N = _lib.stream_ptr(), self.num_envs
@@ -261,6 +279,26 @@ class Storage:
             yield obs, hidden, out.act.float(), out.done, out.logp, out.value, out.ret, out.adv
 
     # ---- logging ---------------------------------------------------------------------------------------------
+    def snapshot_log_data(self):
+        """Start the device -> host copy of this rollout's (raw reward, done) batches into pinned buffers on the current
+        stream and return a closure that waits for it and yields ``fetch_log_data()``'s triple.  Lets ``PPO.train``
+        launch the next rollout before the host touches the log data (the rollout overwrites these buffers)."""
+        rew = self.env_rew if self.env_rew is not None else self.rew
+        if getattr(self, "_log_host", None) is None:
+            self._log_host = (torch.empty(rew.shape, dtype=torch.float32).pin_memory(),
+                              torch.empty(self.done_u8.shape, dtype=torch.uint8).pin_memory())
+        self._log_host[0].copy_(rew, non_blocking=True)
+        self._log_host[1].copy_(self.done_u8, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        N = self.num_envs
+
+        def finish():
+            ev.synchronize()
+            return (self._log_host[0][:, :N].numpy().copy(), self._log_host[1][:, :N].numpy().astype(np.float32),
+                    float("nan"))
+        return finish
+
     def fetch_log_data(self):
         """(rew_batch [T,N], done_batch [T,N], true_average_reward) as numpy, raw env rewards when available
         (common/storage.py:130-162; per-level tracking needs Procgen's prev_level_seed and stays NaN here)."""

@@ -27,41 +27,64 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
   float* slat = sW + HB_MAX_NH * 256;               // [HB_ROWS][H + 1]
   float* sred = slat + HB_ROWS * 257;               // [HB_THREADS]
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * HB_ROWS;
-  const int nb = min(HB_ROWS, mb - b0);
+  // A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its partial parameter-gradient sums in
+  // registers: one flush of ~400 global atomics per CTA instead of one per 64-row tile (2048 tiles of a fused
+  // accumulation window would queue 2048-deep on the same ~400 addresses: measured 85 us, mostly that).
+  constexpr int GW_SLOTS = HB_MAX_NH * 256 / HB_THREADS;      // gWh entries a thread owns (o = tid + q * HB_THREADS)
+  float gw_acc[GW_SLOTS];
+#pragma unroll
+  for (int q = 0; q < GW_SLOTS; ++q) gw_acc[q] = 0.0f;
+  float gbh_acc = 0.0f, colsum = 0.0f;
   for (int i = tid; i < nh * H; i += HB_THREADS) sW[i] = Wh[i];
-  for (int i = tid; i < HB_ROWS * nh; i += HB_THREADS) {
-    const int b = i / nh, a = i % nh;
-    sdh[b * (HB_MAX_NH + 1) + a] = b < nb ? dhead[(int64_t)(b0 + b) * ld_head + a] : 0.0f;
-  }
-  for (int i = tid; i < HB_ROWS * H; i += HB_THREADS) {       // coalesced: consecutive threads walk a row
-    const int b = i / H, k = i % H;
-    slat[b * (H + 1) + k] = b < nb ? latent[(int64_t)(b0 + b) * ldl + k] : 0.0f;
-  }
-  __syncthreads();
-
-  // ---- gbh[a] += sum_b dhead[b][a] ----
-  if (tid < nh) {
-    float s = 0.0f;
-    for (int b = 0; b < nb; ++b) s += sdh[b * (HB_MAX_NH + 1) + tid];
-    atomicAdd(gbh + tid, s);
-  }
-
-  // ---- dlatent[b][k] = sum_a dhead[b][a] Wh[a][k]; thread -> (row lane r, column k), coalesced row writes ----
+  const int ntiles = (mb + HB_ROWS - 1) / HB_ROWS;
   const int rows_per_pass = HB_THREADS / H;          // H in {16..256} -> 16..1 samples per pass
   const int k = tid % H, r = tid / H;
-  float colsum = 0.0f;
-  for (int b = r; b < nb; b += rows_per_pass) {
-    float acc = 0.0f;
-    for (int a = 0; a < nh; ++a) acc += sdh[b * (HB_MAX_NH + 1) + a] * sW[a * H + k];
-    const int64_t row = b0 + b;
-    if (mask && !(mask[row * ldl + k] > 0.0f)) acc = 0.0f;
-    colsum += acc;
-    const float hi = hb_tf32(acc);
-    dz_hi[row * ld_dz + k] = hi;
-    dz_lo[row * ld_dz + k] = acc - hi;
-    if (dz_plain) dz_plain[row * ld_dz + k] = acc;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * HB_ROWS;
+    const int nb = min(HB_ROWS, mb - b0);
+    for (int i = tid; i < HB_ROWS * nh; i += HB_THREADS) {
+      const int b = i / nh, a = i % nh;
+      sdh[b * (HB_MAX_NH + 1) + a] = b < nb ? dhead[(int64_t)(b0 + b) * ld_head + a] : 0.0f;
+    }
+    for (int i = tid; i < HB_ROWS * H; i += HB_THREADS) {       // coalesced: consecutive threads walk a row
+      const int b = i / H, kk = i % H;
+      slat[b * (H + 1) + kk] = b < nb ? latent[(int64_t)(b0 + b) * ldl + kk] : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- gbh[a] += sum_b dhead[b][a] ----
+    if (tid < nh) {
+      for (int b = 0; b < nb; ++b) gbh_acc += sdh[b * (HB_MAX_NH + 1) + tid];
+    }
+
+    // ---- dlatent[b][k] = sum_a dhead[b][a] Wh[a][k]; thread -> (row lane r, column k), coalesced row writes ----
+    for (int b = r; b < nb; b += rows_per_pass) {
+      float acc = 0.0f;
+      for (int a = 0; a < nh; ++a) acc += sdh[b * (HB_MAX_NH + 1) + a] * sW[a * H + k];
+      const int64_t row = b0 + b;
+      if (mask && !(mask[row * ldl + k] > 0.0f)) acc = 0.0f;
+      colsum += acc;
+      const float hi = hb_tf32(acc);
+      dz_hi[row * ld_dz + k] = hi;
+      dz_lo[row * ld_dz + k] = acc - hi;
+      if (dz_plain) dz_plain[row * ld_dz + k] = acc;
+    }
+
+    // ---- gWh[a][k] += sum_b dhead[b][a] latent[b][k] from the staged tile ----
+#pragma unroll
+    for (int q = 0; q < GW_SLOTS; ++q) {
+      const int o = tid + q * HB_THREADS;
+      if (o < nh * H) {
+        const int a = o / H, kk = o % H;
+        float s = 0.0f;
+#pragma unroll 8
+        for (int b = 0; b < HB_ROWS; ++b) s += sdh[b * (HB_MAX_NH + 1) + a] * slat[b * (H + 1) + kk];
+        gw_acc[q] += s;
+      }
+    }
+    __syncthreads();          // the staged tiles are rewritten by the next iteration
   }
+  if (tid < nh) atomicAdd(gbh + tid, gbh_acc);
   sred[tid] = colsum;
   __syncthreads();
   if (tid < H) {
@@ -69,14 +92,10 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
     for (int q = 0; q < rows_per_pass; ++q) s += sred[q * H + tid];
     atomicAdd(gb_last + tid, s);
   }
-
-  // ---- gWh[a][k] += sum_b dhead[b][a] latent[b][k] from the staged tile ----
-  for (int o = tid; o < nh * H; o += HB_THREADS) {
-    const int a = o / H, kk = o % H;
-    float s = 0.0f;
-#pragma unroll 8
-    for (int b = 0; b < HB_ROWS; ++b) s += sdh[b * (HB_MAX_NH + 1) + a] * slat[b * (H + 1) + kk];
-    atomicAdd(gWh + o, s);
+#pragma unroll
+  for (int q = 0; q < GW_SLOTS; ++q) {
+    const int o = tid + q * HB_THREADS;
+    if (o < nh * H) atomicAdd(gWh + o, gw_acc[q]);
   }
 }
 
@@ -97,7 +116,8 @@ extern "C" int tpp_head_backward(const float* dhead, int32_t ld_head, const floa
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int grid = tpp_ceil_div(mb, tpp::HB_ROWS);
+  int grid = tpp_ceil_div(mb, tpp::HB_ROWS);
+  if (grid > 2 * 148) grid = 2 * 148;        // tiles beyond two CTAs per SM are walked by the resident CTAs
   tpp::head_backward_kernel<<<grid, tpp::HB_THREADS, smem, tpp_stream(stream)>>>(
       dhead, ld_head, latent, relu_mask, ldl, Wh, nh, H, dz_hi, dz_lo, dz_plain, ld_dz, gWh, gbh, gb_last, mb);
   TPP_LAUNCH_STATUS();
