@@ -547,6 +547,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
+    if (PERSIST && (p.flags & F_MASK) && (lane & 7) == 0) {
+      // persistent wide tiles: the same for the ReLU-mask lines of this warp's column groups (one lane per 128-byte
+      // line).  The epilogue of a data-gradient item otherwise waits on 16 dependent HBM round trips per warp.
+      for (int c = half * GW; c < BLOCK_N; c += (EPI_WARPS / 4) * GW) {
+        if (n0 + c >= p.N) break;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const long long gm = mrow0 + it * 4 + rr;
+          if (gm < p.M) prefetch_l1(p.mask + gm * p.ld_mask + n0 + c);
+        }
+      }
+    }
     mbar_wait(tmem_full + (acc_i & 1), (acc_i >> 1) & 1);
     tc_fence_after();
     if (warp == 2) TPP_PROBE(5);

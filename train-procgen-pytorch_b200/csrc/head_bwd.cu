@@ -21,11 +21,11 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
     int64_t ldl, const float* __restrict__ Wh, int nh, int H, float* __restrict__ dz_hi, float* __restrict__ dz_lo,
     float* __restrict__ dz_plain, int64_t ld_dz, float* __restrict__ gWh, float* __restrict__ gbh,
     float* __restrict__ gb_last, int mb) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* sdh = sm;                                  // [HB_ROWS][HB_MAX_NH + 1]
   float* sW = sdh + HB_ROWS * (HB_MAX_NH + 1);      // [nh][H]
-  float* slat = sW + HB_MAX_NH * 256;               // [HB_ROWS][H + 1]
-  float* sred = slat + HB_ROWS * 257;               // [HB_THREADS]
+  float* slat = sW + HB_MAX_NH * 256;               // [HB_ROWS][H]  (16-byte aligned rows: filled with cp.async)
+  float* sred = slat + HB_ROWS * 256;               // [HB_THREADS]
   const int tid = threadIdx.x;
   // A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its partial parameter-gradient sums in
   // registers: one flush of ~400 global atomics per CTA instead of one per 64-row tile (2048 tiles of a fused
@@ -46,10 +46,22 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
       const int b = i / nh, a = i % nh;
       sdh[b * (HB_MAX_NH + 1) + a] = b < nb ? dhead[(int64_t)(b0 + b) * ld_head + a] : 0.0f;
     }
-    for (int i = tid; i < HB_ROWS * H; i += HB_THREADS) {       // coalesced: consecutive threads walk a row
-      const int b = i / H, kk = i % H;
-      slat[b * (H + 1) + kk] = b < nb ? latent[(int64_t)(b0 + b) * ldl + kk] : 0.0f;
+    // latent tile: 16-byte cp.async copies, all of a thread's in flight together (a load -> store loop pays one L2 round
+    // trip per iteration, and a CTA walks several tiles)
+    const int H4 = H >> 2;
+    for (int i = tid; i < HB_ROWS * H4; i += HB_THREADS) {
+      const int b = i / H4, k4 = i % H4;
+      float* dst = slat + b * H + 4 * k4;
+      if (b < nb) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                     "l"(latent + (int64_t)(b0 + b) * ldl + 4 * k4)
+                     : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     // ---- gbh[a] += sum_b dhead[b][a] ----
@@ -78,7 +90,7 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
         const int a = o / H, kk = o % H;
         float s = 0.0f;
 #pragma unroll 8
-        for (int b = 0; b < HB_ROWS; ++b) s += sdh[b * (HB_MAX_NH + 1) + a] * slat[b * (H + 1) + kk];
+        for (int b = 0; b < HB_ROWS; ++b) s += sdh[b * (HB_MAX_NH + 1) + a] * slat[b * H + kk];
         gw_acc[q] += s;
       }
     }
@@ -108,8 +120,9 @@ extern "C" int tpp_head_backward(const float* dhead, int32_t ld_head, const floa
   TPP_CHECK_ARG(dhead && latent && Wh && dz_hi && dz_lo && gWh && gbh && gb_last && mb > 0);
   TPP_CHECK_ARG(nh > 0 && nh <= tpp::HB_MAX_NH && ld_head >= nh && ldl >= H && ld_dz >= H);
   if (!(H == 64 || H == 128 || H == 256 || H == 32 || H == 16)) return TPP_ENOTSUP;
-  const size_t smem = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * 256 + tpp::HB_ROWS * 257 + tpp::HB_THREADS) *
+  const size_t smem = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * 256 + tpp::HB_ROWS * 256 + tpp::HB_THREADS) *
                       sizeof(float);
+  TPP_CHECK_ARG((ldl & 3) == 0 && (reinterpret_cast<uintptr_t>(latent) & 15) == 0);   // 16-byte row copies
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tpp::head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
