@@ -268,3 +268,17 @@ def test_cta_pair_epilogues_and_split_k():
     _gemm(a2, b2, 3, flags=8, split_k=16, a_mn=True, b_mn=True, out=out, block_n=512)
     want2, scale2 = _ref(a2, b2)
     assert ((out.double().cpu() - 1.0 - want2).abs() / scale2).max() < 2e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(256 * 180 + 100, 64, 256), (512, 64, 96), (256 * 80, 40, 64)])
+def test_persistent_cta_pairs_narrow_output(M, N, K):
+    """block_n = 65: 256 x 64 tiles on persistent CTA pairs (the 256 -> 64 layer of a fused accumulation window)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    b = torch.randn(N, K, device="cuda", generator=g)
+    bias = torch.randn(N, device="cuda", generator=g)
+    want, scale = _ref(a, b)
+    res = _gemm(a, b, 3, flags=1, bias=bias, block_n=65)
+    w = want + bias.double().cpu()
+    assert ((res["out"][:, :N].double().cpu() - w).abs() / (scale + 1)).max() < 2e-6
+    assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])

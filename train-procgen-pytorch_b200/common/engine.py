@@ -298,6 +298,8 @@ class MLPEngineTC(MLPEngine):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= self.pair_min_n and M >= self.wide_tile_rows:
             return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
+        if 32 < N <= 64 and M >= self.wide_tile_rows and self.pair_block_n == 513:
+            return 65                      # 256 x 64 tiles on persistent CTA pairs (HBM-bound: A is read once)
         if N >= 128 and M * N <= self.small_tile_elems:
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
         return 0

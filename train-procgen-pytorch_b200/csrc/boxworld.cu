@@ -402,15 +402,36 @@ __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxwo
     __syncwarp();
     const uint8_t* W = st.world + (int64_t)e * cells * 3;
     float* dst = obs_out + (int64_t)e * ld_obs;
-    int c = 0, p = lane;
-    for (int o = lane; o < ld_obs; o += 32) {
-      float v = 0.0f;
-      if (o < cells * 3) {
-        while (p >= cells) { p -= cells; ++c; }
-        v = (float)W[p * 3 + c];
+    constexpr int OB = 20;                    // rows up to 640 floats: all byte loads first, then the stores
+    if (ld_obs <= OB * 32) {
+      uint8_t px[OB];
+      int c = 0, p = lane;
+#pragma unroll
+      for (int i = 0; i < OB; ++i) {
+        const int o = lane + 32 * i;
+        px[i] = 0;
+        if (o < cells * 3) {
+          while (p >= cells) { p -= cells; ++c; }
+          px[i] = W[p * 3 + c];
+        }
+        p += 32;
       }
-      p += 32;
-      dst[o] = v;
+#pragma unroll
+      for (int i = 0; i < OB; ++i) {
+        const int o = lane + 32 * i;
+        if (o < ld_obs) dst[o] = (float)px[i];
+      }
+    } else {
+      int c = 0, p = lane;
+      for (int o = lane; o < ld_obs; o += 32) {
+        float v = 0.0f;
+        if (o < cells * 3) {
+          while (p >= cells) { p -= cells; ++c; }
+          v = (float)W[p * 3 + c];
+        }
+        p += 32;
+        dst[o] = v;
+      }
     }
   }
   // last CTA to finish advances the seed counter by the total number of finished envs

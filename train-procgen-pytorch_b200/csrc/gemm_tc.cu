@@ -305,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // previous one (per-tile prologue, epilogue and CTA launch were ~2/3 of a 9-k-block tile's time).  Wide tiles keep
   // compile-time constants, the lean epilogue and one work item per CTA.
   constexpr bool NARROW = BLOCK_N <= 32;
-  static_assert(!PAIR || BLOCK_N == 256, "the CTA-pair form is the 256 x 256 tile");
+  static_assert(!PAIR || BLOCK_N == 256 || BLOCK_N == 64, "CTA-pair forms: 256 x 256 and 256 x 64 tiles");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;                // B rows this CTA stages
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
@@ -1124,6 +1124,7 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
     case 512: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile on a CTA pair (cta_group::2)
     case 513: return tpp::tc::launch<256, true, true>(g, g->split_k, s);   // ... with persistent pairs
+    case 65: return tpp::tc::launch<64, true, true>(g, g->split_k, s);     // 256 x 64 tiles on persistent pairs
     default: return TPP_ENOTSUP;
   }
 }
