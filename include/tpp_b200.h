@@ -75,6 +75,12 @@ int tpp_env_reset(const tpp_env_cfg* cfg, float* obs_out, float* dyn_state, int3
 /* tick[0] += delta (one thread).  Lets a captured CUDA graph advance the RNG stream between replays.     */
 int tpp_tick_advance(uint64_t* tick, uint64_t delta, void* stream);
 
+/* torch.randperm(n) on torch's default CPU generator, restated on the host (MT19937 + ATen's Fisher-Yates loop): the
+ * permutation `out[n]` and the advanced generator state are bit-identical to torch's, several times faster.
+ * state624 / left / next: the MT19937 fields of torch.get_rng_state() (624 words, one per uint64; countdown; index).
+ * Replaces torch.randperm in Storage.fetch_train_generator (common/storage.py:87).  n < 2^32 / 20.            */
+int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out);
+
 /* ---- Box-World ----------------------------------------------------------------------------------------- */
 /* Device-resident state of N Box-World envs (replaces the numpy members of BoxWorldVec,
  * boxworld/box_world_env_vec.py:24-60).  cells = (n+2)*(n+2).                                            */

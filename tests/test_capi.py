@@ -71,3 +71,30 @@ def test_product_fails_loudly_without_cuda(lib):
     from tpp_b200.common.storage import Storage
     with pytest.raises(lib.TppError):
         Storage((9,), 4, 8, 8, "cpu")
+
+
+def test_host_randperm_equals_torch_randperm_and_leaves_the_same_generator_state(lib):
+    """Minibatch indices must be bit-exact (reference common/storage.py:87: torch.randperm on the default CPU
+    generator): the library's MT19937 + Fisher-Yates restatement against torch itself, including the generator state
+    it leaves behind and draws interleaved with other torch CPU random numbers."""
+    import torch
+    from tpp_b200.common.storage import Storage
+    for seed in (0, 1, 6033, 4321):
+        sizes = (10, 700, 5, 1 << 16, 3, 1000, 64, 65, 2, 1, 625, 624)
+        torch.manual_seed(seed)
+        want = [torch.randperm(n) for n in sizes]
+        s_want = torch.get_rng_state()
+        torch.manual_seed(seed)
+        got = [Storage.randperm(n) for n in sizes]
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
+        assert torch.equal(s_want, torch.get_rng_state())
+        torch.manual_seed(seed)
+        a1, x1, b1 = torch.randperm(1000), torch.rand(5), torch.randperm(77)
+        torch.manual_seed(seed)
+        a2, x2, b2 = Storage.randperm(1000), torch.rand(5), Storage.randperm(77)
+        assert torch.equal(a1, a2) and torch.equal(x1, x2) and torch.equal(b1, b2)
+    out = torch.empty(4096, dtype=torch.int64)
+    torch.manual_seed(7)
+    w = torch.randperm(4096)
+    torch.manual_seed(7)
+    assert Storage.randperm(4096, out=out) is out and torch.equal(out, w)

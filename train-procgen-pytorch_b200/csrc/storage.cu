@@ -177,6 +177,21 @@ __global__ void __launch_bounds__(GI_WARPS * 32) gather_img_kernel(const int64_t
   __syncwarp();
   float* dst = out_obs + (int64_t)k * ld_out;
   float* dlo = out_lo ? out_lo + (int64_t)k * ld_out : nullptr;
+  if (raw && !dlo && (HW & 3) == 0 && (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    // raw pixel rows, 128-bit stores: a lane owns 4 consecutive outputs (same channel: HW % 4 == 0), 512 bytes per warp
+    // instruction instead of 128 (the kernel is bound by the number of store instructions, not by their bytes)
+    for (int o = 4 * lane; o < ld_out; o += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < bytes) {
+        const int cch = o / HW, pp = o - cch * HW;
+        const uint8_t* q = px + pp * C + cch;
+        v = make_float4((float)q[0], (float)q[C], (float)q[2 * C], (float)q[3 * C]);
+      }
+      *reinterpret_cast<float4*>(dst + o) = v;
+    }
+    if (lane == 0 && idx) gather_scalars(g, (flat / N) * ld + (flat % N), k);
+    return;
+  }
   int c = 0, p = lane;                              // o = c*HW + p, advanced without div/mod
   for (int o = lane; o < ld_out; o += 32) {
     float v = 0.0f;
