@@ -100,7 +100,7 @@ typedef struct {
   const uint8_t* bank_world;     /* [n_levels][cells][3]   (NULL when n_levels == 0)                      */
   const int8_t* bank_dic;        /* [n_levels][cells]                                                     */
   const int32_t* bank_pos;       /* [n_levels][2]                                                         */
-  int32_t* scratch;              /* [N + 1024] per-CTA done counts + scan workspace                       */
+  int32_t* scratch;              /* [2 N + 4096], zero-initialised: per-CTA done counts, ticket, scan workspace         */
 } tpp_boxworld_state;
 
 /* One step of all envs: grid transition, rewards, done, level replacement in env-index order with the

@@ -62,7 +62,12 @@ class FlatAdam:
     def _sync_lr(self):
         lr = float(self.param_groups[0]["lr"])
         if lr != self._lr_on_device:
-            self._f64[0:1].copy_(torch.tensor([lr], dtype=torch.float64), non_blocking=True)
+            # pinned staging: an async copy from PAGEABLE memory first synchronises the stream, i.e. the host would wait
+            # for the whole rollout here and launch the epoch graph into an idle GPU
+            if getattr(self, "_lr_pinned", None) is None:
+                self._lr_pinned = torch.zeros(1, dtype=torch.float64).pin_memory()
+            self._lr_pinned[0] = lr
+            self._f64[0:1].copy_(self._lr_pinned, non_blocking=True)
             self._lr_on_device = lr
 
     def step(self):

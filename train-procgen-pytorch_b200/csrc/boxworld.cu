@@ -214,14 +214,191 @@ __host__ __device__ inline void gen_level(const LevelSpec& sp, int64_t seed, uin
 // ================================================================================================
 __device__ __forceinline__ bool px_is(const uint8_t* p, uint8_t g) { return p[0] == g && p[1] == g && p[2] == g; }
 
-__device__ __forceinline__ void copy_frame(const uint8_t* src, uint8_t* dst, int bytes, int lane) {
+// Warp copy of a frame.  Loads of a batch (8 words per lane) are all issued before the first store: a plain
+// load -> store loop pays one memory round trip per 128 bytes (the compiler cannot prove the pointers distinct).
+__device__ __forceinline__ void copy_frame(const uint8_t* src, uint8_t* dst, int bytes, int lane, uint8_t* dst2 = nullptr) {
   if ((bytes & 3) == 0) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    for (int i = lane; i < bytes / 4; i += 32) d[i] = s[i];
+    uint32_t* d2 = reinterpret_cast<uint32_t*>(dst2);
+    const int words = bytes >> 2;
+    for (int base = 0; base < words; base += 256) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + lane + 32 * j;
+        v[j] = i < words ? s[i] : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + lane + 32 * j;
+        if (i < words) {
+          d[i] = v[j];
+          if (d2) d2[i] = v[j];
+        }
+      }
+    }
   } else {
-    for (int i = lane; i < bytes; i += 32) dst[i] = src[i];
+    for (int i = lane; i < bytes; i += 32) {
+      const uint8_t b = src[i];
+      dst[i] = b;
+      if (dst2) dst2[i] = b;
+    }
   }
+}
+
+// One env's transition, executed by its warp: lane 0 resolves the move, the result (done) is broadcast.
+__device__ __forceinline__ int step_env(const tpp_boxworld_state& st, int e, int lane, const int32_t* __restrict__ action,
+                                        int32_t* __restrict__ reward_out, uint8_t* __restrict__ done_out,
+                                        int32_t* fin_ret, int32_t* fin_len, uint8_t* fin_solved) {
+  const int S = st.n + 2, cells = S * S;
+  uint8_t* W = st.world + (int64_t)e * cells * 3;
+  int done = 0;
+  if (lane == 0) {
+    const int8_t* D = st.world_dic + (int64_t)e * cells;
+    const int a = action[e];
+    const int pr = st.player_pos[2 * e], pc = st.player_pos[2 * e + 1];
+    const int nr = pr + (a == 0 ? -1 : (a == 1 ? 1 : 0)), nc = pc + (a == 2 ? -1 : (a == 3 ? 1 : 0));
+    const int steps = st.num_env_steps[e] + 1;
+    int reward = 0, solved = 0;
+    done = (steps == st.max_steps);
+    auto clampi = [&](int v) { return v < 0 ? 0 : (v > st.n + 1 ? st.n + 1 : v); };
+    const int ar = clampi(nr), ac = clampi(nc);
+    const int at = ar * S + ac, left = ar * S + clampi(nc - 1), right = ar * S + clampi(nc + 1);
+    const bool in_grid = nr > 0 && nc > 0 && nr <= st.n && nc <= st.n;
+    const uint8_t here[3] = {W[at * 3], W[at * 3 + 1], W[at * 3 + 2]};
+    const uint8_t lc[3] = {W[left * 3], W[left * 3 + 1], W[left * 3 + 2]};
+    const bool empty = px_is(here, C_GRID);
+    const bool left_clear = (nc == 1) || px_is(lc, C_GRID);
+    const bool first_key = !empty && left_clear && (px_is(W + right * 3, C_GRID) || px_is(W + right * 3, C_AGENT));
+    const int status = D[at];
+    const bool is_lock = status != -1;
+    uint8_t* own = st.owned_key + 4 * e;
+    const bool key_fits = own[0] == here[0] && own[0] != C_GRID && own[1] == here[1] && own[1] != C_GRID &&
+                          own[2] == here[2] && own[2] != C_GRID;
+    const bool blocked = !(empty || first_key || is_lock) || (is_lock && !key_fits);
+    if (in_grid && !blocked) {
+      const int cur = pr * S + pc;
+      const bool walk = empty, take = !walk && first_key, unlock = !walk && !take && is_lock && key_fits;
+      if (walk || take || unlock) {
+        W[cur * 3] = W[cur * 3 + 1] = W[cur * 3 + 2] = C_GRID;
+        if (unlock) W[left * 3] = W[left * 3 + 1] = W[left * 3 + 2] = C_GRID;
+        W[at * 3] = W[at * 3 + 1] = W[at * 3 + 2] = C_AGENT;
+        st.player_pos[2 * e] = nr;
+        st.player_pos[2 * e + 1] = nc;
+        if (take) {
+          W[0] = own[0] = here[0]; W[1] = own[1] = here[1]; W[2] = own[2] = here[2];
+          reward += 1;
+        }
+        if (unlock) {
+          W[0] = own[0] = lc[0]; W[1] = own[1] = lc[1]; W[2] = own[2] = lc[2];
+          const bool goal = px_is(lc, C_GOAL);
+          if (goal) { reward += 10; solved = 1; done = 1; }
+          if (status == 1) reward += 1;
+          if (status == 0) { reward -= 1; done = 1; }
+        }
+      }
+    }
+    const int ep = st.episode_reward[e] + reward;
+    st.num_env_steps[e] = steps;
+    st.episode_reward[e] = ep;
+    reward_out[e] = reward;
+    done_out[e] = (uint8_t)done;
+    if (fin_ret) fin_ret[e] = done ? ep : 0;
+    if (fin_len) fin_len[e] = done ? steps : 0;
+    if (fin_solved) fin_solved[e] = (uint8_t)(done ? solved : 0);
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, done, 0);
+}
+
+// An env's frame as the policy's next input row: channel-major integer pixel values as fp32 (TransposeFrame;
+// ScaledFloatFrame's 1/255 lives in the policy's first layer) = tpp_frames_to_obs(raw) of that frame.
+__device__ __forceinline__ void emit_obs_row(const uint8_t* W, float* __restrict__ dst, int cells, int ld_obs, int lane) {
+  constexpr int OB = 20;                    // rows up to 640 floats: all byte loads first, then the stores
+  if (ld_obs <= OB * 32) {
+    uint8_t px[OB];
+    int c = 0, p = lane;
+#pragma unroll
+    for (int i = 0; i < OB; ++i) {
+      const int o = lane + 32 * i;
+      px[i] = 0;
+      if (o < cells * 3) {
+        while (p >= cells) { p -= cells; ++c; }
+        px[i] = W[p * 3 + c];
+      }
+      p += 32;
+    }
+#pragma unroll
+    for (int i = 0; i < OB; ++i) {
+      const int o = lane + 32 * i;
+      if (o < ld_obs) dst[o] = (float)px[i];
+    }
+  } else {
+    int c = 0, p = lane;
+    for (int o = lane; o < ld_obs; o += 32) {
+      float v = 0.0f;
+      if (o < cells * 3) {
+        while (p >= cells) { p -= cells; ++c; }
+        v = (float)W[p * 3 + c];
+      }
+      p += 32;
+      dst[o] = v;
+    }
+  }
+}
+
+// Level replacement of finished env e, the k-th finished env of this step in env order (its level seed follows the
+// reference's sequential counter, box_world_env_vec.py:204-207,294-297), executed by one warp.
+__device__ __forceinline__ void reset_env(const tpp_boxworld_state& st, int e, int64_t k, int64_t sc, int lane,
+                                          uint32_t* mtbuf_w, uint8_t* __restrict__ frame_out) {
+  const int S = st.n + 2, cells = S * S;
+  int64_t seed = sc + k;
+  if (st.n_levels > 0) seed = ((sc - st.start_seed + k) % st.n_levels) + st.start_seed;
+  uint8_t* W = st.world + (int64_t)e * cells * 3;
+  int8_t* D = st.world_dic + (int64_t)e * cells;
+  if (st.n_levels > 0 && st.bank_world) {
+    // level bank: frame, lock table and position loads are all in flight together; the frame goes to the env state
+    // AND to the rollout slot from the same registers
+    const int64_t li = seed - st.start_seed;
+    const int8_t* bd = st.bank_dic + li * cells;
+    int8_t dv[8];
+    int pos = 0;
+    if (cells <= 256) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[j] = (lane + 32 * j) < cells ? bd[lane + 32 * j] : (int8_t)0;
+    }
+    if (lane < 2) pos = st.bank_pos[2 * li + lane];
+    copy_frame(st.bank_world + li * cells * 3, W, cells * 3, lane,
+               frame_out ? frame_out + (int64_t)e * cells * 3 : nullptr);
+    if (cells <= 256) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((lane + 32 * j) < cells) D[lane + 32 * j] = dv[j];
+    } else {
+      for (int i = lane; i < cells; i += 32) D[i] = bd[i];
+    }
+    if (lane < 2) st.player_pos[2 * e + lane] = pos;
+    if (lane == 0) {
+      st.num_env_steps[e] = 0;
+      st.episode_reward[e] = 0;
+      uint8_t* own = st.owned_key + 4 * e;
+      own[0] = own[1] = own[2] = C_GRID;
+    }
+    __syncwarp();
+    return;
+  } else if (lane == 0) {
+    const LevelSpec sp{st.n, st.goal_length, st.num_distractor, st.distractor_length};
+    gen_level(sp, seed, mtbuf_w, W, D, st.player_pos + 2 * e);
+  }
+  if (lane == 0) {
+    st.num_env_steps[e] = 0;
+    st.episode_reward[e] = 0;
+    uint8_t* own = st.owned_key + 4 * e;
+    own[0] = own[1] = own[2] = C_GRID;
+  }
+  __syncwarp();
+  if (frame_out) copy_frame(W, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
 }
 
 __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_step_kernel(tpp_boxworld_state st,
@@ -236,68 +413,12 @@ __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_step_kernel(tpp_boxwor
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
-  const int S = st.n + 2, cells = S * S;
-  int done = 0;
+  const int cells = (st.n + 2) * (st.n + 2);
   if (e < st.n_envs) {
-    uint8_t* W = st.world + (int64_t)e * cells * 3;
-    if (lane == 0) {
-      const int8_t* D = st.world_dic + (int64_t)e * cells;
-      const int a = action[e];
-      const int pr = st.player_pos[2 * e], pc = st.player_pos[2 * e + 1];
-      const int nr = pr + (a == 0 ? -1 : (a == 1 ? 1 : 0)), nc = pc + (a == 2 ? -1 : (a == 3 ? 1 : 0));
-      const int steps = st.num_env_steps[e] + 1;
-      int reward = 0, solved = 0;
-      done = (steps == st.max_steps);
-      auto clampi = [&](int v) { return v < 0 ? 0 : (v > st.n + 1 ? st.n + 1 : v); };
-      const int ar = clampi(nr), ac = clampi(nc);
-      const int at = ar * S + ac, left = ar * S + clampi(nc - 1), right = ar * S + clampi(nc + 1);
-      const bool in_grid = nr > 0 && nc > 0 && nr <= st.n && nc <= st.n;
-      const uint8_t here[3] = {W[at * 3], W[at * 3 + 1], W[at * 3 + 2]};
-      const uint8_t lc[3] = {W[left * 3], W[left * 3 + 1], W[left * 3 + 2]};
-      const bool empty = px_is(here, C_GRID);
-      const bool left_clear = (nc == 1) || px_is(lc, C_GRID);
-      const bool first_key = !empty && left_clear && (px_is(W + right * 3, C_GRID) || px_is(W + right * 3, C_AGENT));
-      const int status = D[at];
-      const bool is_lock = status != -1;
-      uint8_t* own = st.owned_key + 4 * e;
-      const bool key_fits = own[0] == here[0] && own[0] != C_GRID && own[1] == here[1] && own[1] != C_GRID &&
-                            own[2] == here[2] && own[2] != C_GRID;
-      const bool blocked = !(empty || first_key || is_lock) || (is_lock && !key_fits);
-      if (in_grid && !blocked) {
-        const int cur = pr * S + pc;
-        const bool walk = empty, take = !walk && first_key, unlock = !walk && !take && is_lock && key_fits;
-        if (walk || take || unlock) {
-          W[cur * 3] = W[cur * 3 + 1] = W[cur * 3 + 2] = C_GRID;
-          if (unlock) W[left * 3] = W[left * 3 + 1] = W[left * 3 + 2] = C_GRID;
-          W[at * 3] = W[at * 3 + 1] = W[at * 3 + 2] = C_AGENT;
-          st.player_pos[2 * e] = nr;
-          st.player_pos[2 * e + 1] = nc;
-          if (take) {
-            W[0] = own[0] = here[0]; W[1] = own[1] = here[1]; W[2] = own[2] = here[2];
-            reward += 1;
-          }
-          if (unlock) {
-            W[0] = own[0] = lc[0]; W[1] = own[1] = lc[1]; W[2] = own[2] = lc[2];
-            const bool goal = px_is(lc, C_GOAL);
-            if (goal) { reward += 10; solved = 1; done = 1; }
-            if (status == 1) reward += 1;
-            if (status == 0) { reward -= 1; done = 1; }
-          }
-        }
-      }
-      const int ep = st.episode_reward[e] + reward;
-      st.num_env_steps[e] = steps;
-      st.episode_reward[e] = ep;
-      reward_out[e] = reward;
-      done_out[e] = (uint8_t)done;
-      if (fin_ret) fin_ret[e] = done ? ep : 0;
-      if (fin_len) fin_len[e] = done ? steps : 0;
-      if (fin_solved) fin_solved[e] = (uint8_t)(done ? solved : 0);
-      if (done) atomicAdd(&cta_done, 1);
-    }
-    __syncwarp();
-    done = __shfl_sync(0xffffffffu, done, 0);
-    if (!done && frame_out) copy_frame(W, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
+    const int done = step_env(st, e, lane, action, reward_out, done_out, fin_ret, fin_len, fin_solved);
+    if (done && lane == 0) atomicAdd(&cta_done, 1);
+    if (!done && frame_out)
+      copy_frame(st.world + (int64_t)e * cells * 3, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
   }
   __syncthreads();
   if (threadIdx.x == 0) st.scratch[blockIdx.x] = cta_done;
@@ -371,68 +492,10 @@ __global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxwo
     if (w == wid) mine = d;
     own_total += d;
   }
-  if (mine) {
-    const int64_t k = (int64_t)base_s + before;
-    int64_t seed = sc + k;
-    if (st.n_levels > 0) seed = ((sc - st.start_seed + k) % st.n_levels) + st.start_seed;
-    uint8_t* W = st.world + (int64_t)e * cells * 3;
-    int8_t* D = st.world_dic + (int64_t)e * cells;
-    if (st.n_levels > 0 && st.bank_world) {
-      const int64_t li = seed - st.start_seed;
-      copy_frame(st.bank_world + li * cells * 3, W, cells * 3, lane);
-      for (int i = lane; i < cells; i += 32) D[i] = st.bank_dic[li * cells + i];
-      if (lane < 2) st.player_pos[2 * e + lane] = st.bank_pos[2 * li + lane];
-    } else if (lane == 0) {
-      const LevelSpec sp{st.n, st.goal_length, st.num_distractor, st.distractor_length};
-      gen_level(sp, seed, mtbuf[wid], W, D, st.player_pos + 2 * e);
-    }
-    if (lane == 0) {
-      st.num_env_steps[e] = 0;
-      st.episode_reward[e] = 0;
-      uint8_t* own = st.owned_key + 4 * e;
-      own[0] = own[1] = own[2] = C_GRID;
-    }
+  if (mine) reset_env(st, e, (int64_t)base_s + before, sc, lane, mtbuf[wid], frame_out);
+  if (obs_out && e < st.n_envs) {          // every env: its (post-reset) frame as the policy's next input row
     __syncwarp();
-    if (frame_out) copy_frame(W, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
-  }
-  if (obs_out && e < st.n_envs) {
-    // every env: its (post-reset) frame as the policy's next input row -- channel-major integer pixel values as fp32
-    // (TransposeFrame; ScaledFloatFrame's 1/255 lives in the policy's first layer), i.e. what tpp_frames_to_obs(raw)
-    // would produce from slot t + 1 in a launch of its own
-    __syncwarp();
-    const uint8_t* W = st.world + (int64_t)e * cells * 3;
-    float* dst = obs_out + (int64_t)e * ld_obs;
-    constexpr int OB = 20;                    // rows up to 640 floats: all byte loads first, then the stores
-    if (ld_obs <= OB * 32) {
-      uint8_t px[OB];
-      int c = 0, p = lane;
-#pragma unroll
-      for (int i = 0; i < OB; ++i) {
-        const int o = lane + 32 * i;
-        px[i] = 0;
-        if (o < cells * 3) {
-          while (p >= cells) { p -= cells; ++c; }
-          px[i] = W[p * 3 + c];
-        }
-        p += 32;
-      }
-#pragma unroll
-      for (int i = 0; i < OB; ++i) {
-        const int o = lane + 32 * i;
-        if (o < ld_obs) dst[o] = (float)px[i];
-      }
-    } else {
-      int c = 0, p = lane;
-      for (int o = lane; o < ld_obs; o += 32) {
-        float v = 0.0f;
-        if (o < cells * 3) {
-          while (p >= cells) { p -= cells; ++c; }
-          v = (float)W[p * 3 + c];
-        }
-        p += 32;
-        dst[o] = v;
-      }
-    }
+    emit_obs_row(st.world + (int64_t)e * cells * 3, obs_out + (int64_t)e * ld_obs, cells, ld_obs, lane);
   }
   // last CTA to finish advances the seed counter by the total number of finished envs
   __shared__ bool last;
@@ -685,6 +748,7 @@ extern "C" int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* ac
   if (rc) return rc;
   TPP_CHECK_ARG(action && reward_out && done_out);
   TPP_CHECK_ARG(!obs_out || ld_obs >= 3 * (st->n + 2) * (st->n + 2));
+  // scratch holds 2 N + 4096 ints (see tpp_boxworld_state)
   const int grid = tpp_ceil_div(st->n_envs, tpp::BW_WARPS);
   cudaStream_t s = tpp_stream(stream);
   tpp::boxworld_step_kernel<<<grid, tpp::BW_WARPS * 32, 0, s>>>(*st, action, reward_out, done_out, frame_out, fin_ret,
