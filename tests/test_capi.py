@@ -98,3 +98,18 @@ def test_host_randperm_equals_torch_randperm_and_leaves_the_same_generator_state
     w = torch.randperm(4096)
     torch.manual_seed(7)
     assert Storage.randperm(4096, out=out) is out and torch.equal(out, w)
+
+
+def test_weight_gradient_split_policy():
+    """Host logic of the engine: k-splits of a weight-gradient GEMM keep <= ~1024 samples per accumulator, fill at
+    least one wave of the 148 SMs and do not leave a nearly empty last wave."""
+    from tpp_b200.common.engine import MLPEngineTC
+    for M in (256, 2048, 8192, 32768, 131072, 1 << 20):
+        for ctas in (1, 2, 4, 6, 10):
+            s = MLPEngineTC._wgrad_split(M, ctas)
+            assert 1 <= s <= max(1, -(-M // 32))
+            if M >= 148 * 32:
+                assert s * ctas >= 148                                    # at least one wave
+                assert -(-M // s) <= 1024 + 32                            # accumulation length bound
+                waves = -(-s * ctas // 148)
+                assert s * ctas > (waves - 1) * 148 + 148 // 2 or waves == 1   # last wave at least half full
