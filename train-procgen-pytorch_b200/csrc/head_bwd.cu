@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(HB_THREADS) head_backward_kernel(
   extern __shared__ __align__(16) float sm[];
   float* sdh = sm;                                  // [HB_ROWS][HB_MAX_NH + 1]
   float* sW = sdh + HB_ROWS * (HB_MAX_NH + 1);      // [nh][H]
-  float* slat = sW + HB_MAX_NH * 256;               // [HB_ROWS][H]  (16-byte aligned rows: filled with cp.async)
-  float* sred = slat + HB_ROWS * 256;               // [HB_THREADS]
+  float* slat = sW + HB_MAX_NH * H;                 // [HB_ROWS][H]  (16-byte aligned rows: filled with cp.async)
+  float* sred = slat + HB_ROWS * H;                 // [HB_THREADS]
   const int tid = threadIdx.x;
   // A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... and keeps its partial parameter-gradient sums in
   // registers: one flush of ~400 global atomics per CTA instead of one per 64-row tile (2048 tiles of a fused
@@ -120,17 +120,22 @@ extern "C" int tpp_head_backward(const float* dhead, int32_t ld_head, const floa
   TPP_CHECK_ARG(dhead && latent && Wh && dz_hi && dz_lo && gWh && gbh && gb_last && mb > 0);
   TPP_CHECK_ARG(nh > 0 && nh <= tpp::HB_MAX_NH && ld_head >= nh && ldl >= H && ld_dz >= H);
   if (!(H == 64 || H == 128 || H == 256 || H == 32 || H == 16)) return TPP_ENOTSUP;
-  const size_t smem = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * 256 + tpp::HB_ROWS * 256 + tpp::HB_THREADS) *
-                      sizeof(float);
+  // sized by the actual H: a 64-wide latent needs 25 KB, so 4-5 CTAs share an SM and overlap each other's tile loads
+  const size_t smem = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * (size_t)H + tpp::HB_ROWS * (size_t)H +
+                       tpp::HB_THREADS) * sizeof(float);
+  const size_t smem_max = (tpp::HB_ROWS * (tpp::HB_MAX_NH + 1) + tpp::HB_MAX_NH * 256 + tpp::HB_ROWS * 256 +
+                           tpp::HB_THREADS) * sizeof(float);
   TPP_CHECK_ARG((ldl & 3) == 0 && (reinterpret_cast<uintptr_t>(latent) & 15) == 0);   // 16-byte row copies
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tpp::head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tpp::head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_max);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   int grid = tpp_ceil_div(mb, tpp::HB_ROWS);
-  if (grid > 2 * 148) grid = 2 * 148;        // tiles beyond two CTAs per SM are walked by the resident CTAs
+  const int per_sm = H <= 64 ? 4 : 2;
+  if (grid > per_sm * 148) grid = per_sm * 148;   // tiles beyond the resident CTAs are walked by them
   tpp::head_backward_kernel<<<grid, tpp::HB_THREADS, smem, tpp_stream(stream)>>>(
       dhead, ld_head, latent, relu_mask, ldl, Wh, nh, H, dz_hi, dz_lo, dz_plain, ld_dz, gWh, gbh, gb_last, mb);
   TPP_LAUNCH_STATUS();
