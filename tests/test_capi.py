@@ -113,3 +113,25 @@ def test_weight_gradient_split_policy():
                 assert -(-M // s) <= 1024 + 32                            # accumulation length bound
                 waves = -(-s * ctas // 148)
                 assert s * ctas > (waves - 1) * 148 + 148 // 2 or waves == 1   # last wave at least half full
+
+
+def test_accumulation_group_size_policy():
+    """Host logic of PPO.optimize: how many minibatches of a gradient-accumulation window share one pass."""
+    from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.engine import ImpalaEngineTC, MLPEngine
+    agent = PPO.__new__(PPO)
+    agent.fuse_accum, agent.x_entropy_coef, agent.max_group_rows = "auto", 0.0, 1 << 18
+    mlp, impala = object.__new__(MLPEngine), object.__new__(ImpalaEngineTC)
+    assert agent._group_size(16, 128, 8192, mlp) == 16            # the bench workload: the whole window
+    assert agent._group_size(16, 128, 8192, impala) == 1          # convolution engine: per minibatch
+    assert agent._group_size(1, 8, 4096, mlp) == 1                # no accumulation
+    assert agent._group_size(16, 120, 8192, mlp) == 1             # windows do not tile the epoch
+    assert agent._group_size(4, 8, 100, mlp) == 1                 # grouped loss kernel needs mb % 256 == 0
+    agent.max_group_rows = 40000
+    assert agent._group_size(16, 128, 8192, mlp) == 4             # row budget: largest divisor that fits
+    agent.max_group_rows, agent.fuse_accum = 1 << 18, 2
+    assert agent._group_size(16, 128, 8192, mlp) == 2
+    agent.fuse_accum = 1
+    assert agent._group_size(16, 128, 8192, mlp) == 1
+    agent.fuse_accum, agent.x_entropy_coef = "auto", 0.05
+    assert agent._group_size(16, 128, 8192, mlp) == 1             # cross-batch entropy keeps the ungrouped path
