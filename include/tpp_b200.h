@@ -213,7 +213,10 @@ int tpp_colsum_accum(const float* dZ, int64_t ld, int32_t M, int32_t N, float* o
  * flags: TPP_EPI_BIAS, TPP_EPI_RELU, TPP_EPI_MASK (zero where mask[m*ld_mask+n] <= 0), TPP_EPI_ACCUM (fp32 atomic
  *        accumulation of the raw product into `out`; the only mode that allows split_k > 1: weight gradients).
  * Outputs (each nullable): out (plain fp32 [M][ldc]), out_hi/out_lo (TF32 pair, [M][ldc]), colsum ([N], += column
- * sums of the result: the bias gradient of the layer below).  block_n: 0 = auto, or 16/32/64/128/256.
+ * sums of the result: the bias gradient of the layer below).  block_n: 0 = auto, 16/32/64/128/256 = 128 x block_n tile
+ * on one CTA, or a TPP_TC_TILE_* code: 256 x 256 (256 x 64) tiles on CTA pairs (clusters of two CTAs, tcgen05
+ * cta_group::2: each CTA stages 128 rows of A and half of the tile's B rows), optionally persistent (74 pairs loop over
+ * the work items with two TMEM accumulators, the epilogue of one item overlapping the next item's loads and MMAs).
  * Replaces nn.Linear forward / backward (common/model.py:954-980, common/policy.py:74-87).                  */
 typedef struct {
   const float* a_hi; const float* a_lo; int64_t lda;
@@ -225,7 +228,8 @@ typedef struct {
   const float* mask; int64_t ld_mask;
   float* out; float* out_hi; float* out_lo; int64_t ldc;
   float* colsum;
-  void* dbg;          /* optional int64[8]: clock64 timeline of CTA (0,0,0) — profiling aid, normally NULL */
+  void* dbg;          /* optional int64[16]: clock64 timeline of one CTA (x = 0, y = _reserved, z = 0) -- profiling aid,
+                         normally NULL */
   const float* addend; int64_t ld_add;   /* TPP_EPI_ADD (tpp_gemm_tc only): result += addend[m*ld_add + n], applied
                                             after bias / relu / mask: the residual connection (forward) and the
                                             skip-path gradient (backward) of ResidualBlock, common/model.py:134-153 */
@@ -247,6 +251,8 @@ typedef struct {
  * representable in TF32 (e.g. integer pixel values 0..255): it has no lo half (a_lo / b_lo unused, not loaded) and the
  * pass that would multiply it is skipped -- two passes, 3/4 of the operand traffic.                                */
 enum { TPP_TC_A_EXACT = 16, TPP_TC_B_EXACT = 32 };
+/* block_n codes of the CTA-pair tiles */
+enum { TPP_TC_TILE_PAIR = 512, TPP_TC_TILE_PAIR_PERSISTENT = 513, TPP_TC_TILE_PAIR64_PERSISTENT = 65 };
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
 /* Backward of the policy/value heads ([nh = A+1 <= 16][H] weights) in one kernel: from dhead [mb][ld_head]

@@ -84,9 +84,10 @@ def test_boxworld_rollout_in_env_ranges_equals_whole_batch_rollout(use_graph):
             torch.testing.assert_close(outs[0][k], o[k], rtol=1e-5, atol=1e-6, msg=k)
 
 
-def test_vecnormalize_rollout_kernel_equals_per_step_kernel():
+@pytest.mark.parametrize("N,ld", [(1000, 1024), (5000, 5024)])      # register path (<= 4096 envs) and the generic one
+def test_vecnormalize_rollout_kernel_equals_per_step_kernel(N, ld):
     from tpp_b200 import _lib
-    T, N, ld = 37, 1000, 1024
+    T = 37
     g = torch.Generator().manual_seed(3)
     raw = torch.randint(-1, 12, (T, ld), generator=g, dtype=torch.int32).cuda()
     done = (torch.rand(T, ld, generator=g) < 0.05).to(torch.uint8).cuda()

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import TC_A_EXACT, TC_B_EXACT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
+from .._lib import TC_TILE_PAIR64_PERSISTENT, TC_TILE_PAIR_PERSISTENT, TC_A_EXACT, TC_B_EXACT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -206,7 +206,7 @@ class MLPEngineTC(MLPEngine):
         # L2 -> shared-memory bytes per FLOP of 128 x 128 tiles, which is what bounds these kernels (profiles/README.md)
         self.wide_tile_rows = 32768
         self.pair_min_n = 256
-        self.pair_block_n = 513        # 512: one 256 x 256 tile per CTA pair; 513: persistent pairs looping over tiles
+        self.pair_block_n = TC_TILE_PAIR_PERSISTENT     # or TC_TILE_PAIR: one 256 x 256 tile per (non-persistent) pair
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
@@ -298,8 +298,8 @@ class MLPEngineTC(MLPEngine):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= self.pair_min_n and M >= self.wide_tile_rows:
             return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
-        if 32 < N <= 64 and M >= self.wide_tile_rows and self.pair_block_n == 513:
-            return 65                      # 256 x 64 tiles on persistent CTA pairs (HBM-bound: A is read once)
+        if 32 < N <= 64 and M >= self.wide_tile_rows and self.pair_block_n == TC_TILE_PAIR_PERSISTENT:
+            return TC_TILE_PAIR64_PERSISTENT   # 256 x 64 tiles on persistent CTA pairs (HBM-bound: A is read once)
         if N >= 128 and M * N <= self.small_tile_elems:
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
         return 0

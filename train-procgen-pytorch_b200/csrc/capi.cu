@@ -62,7 +62,7 @@ struct Mt {
 extern "C" int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out) {
   TPP_CHECK_ARG(state624 && left && next && out && n > 0);
   if (n >= (int64_t)(0xFFFFFFFFu / 20)) return TPP_ENOTSUP;      // ATen switches to another algorithm there
-  TPP_CHECK_ARG(*left >= 0 && *left <= 624 && *next <= 624);
+  TPP_CHECK_ARG(*left >= 1 && *left <= 624 && *next <= 624);   // ATen refills at left == 0 and never stores it
   Mt mt;
   for (int i = 0; i < 624; ++i) mt.s[i] = (uint32_t)state624[i];
   mt.left = *left;

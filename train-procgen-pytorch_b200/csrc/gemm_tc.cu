@@ -1122,9 +1122,9 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
     case 64: return tpp::tc::launch<64>(g, g->split_k, s);
     case 128: return tpp::tc::launch<128>(g, g->split_k, s);
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
-    case 512: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile on a CTA pair (cta_group::2)
-    case 513: return tpp::tc::launch<256, true, true>(g, g->split_k, s);   // ... with persistent pairs
-    case 65: return tpp::tc::launch<64, true, true>(g, g->split_k, s);     // 256 x 64 tiles on persistent pairs
+    case TPP_TC_TILE_PAIR: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile, one per CTA pair
+    case TPP_TC_TILE_PAIR_PERSISTENT: return tpp::tc::launch<256, true, true>(g, g->split_k, s);
+    case TPP_TC_TILE_PAIR64_PERSISTENT: return tpp::tc::launch<64, true, true>(g, g->split_k, s);   // 256 x 64 tiles
     default: return TPP_ENOTSUP;
   }
 }
