@@ -168,11 +168,14 @@ __device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, co
   constexpr float FPS = 50.0f, SC = 30.0f, W2 = 10.0f, H2 = 400.0f / 30.0f / 2.0f;
   constexpr float PAD = (400.0f / 30.0f) / 4.0f, LEG_DOWN = 18.0f / SC, DT = 1.0f / FPS;
   constexpr float MASS = 4.82f, INERTIA = 0.84f;
+  // divisions by constants as multiplications by the (compile-time) reciprocal: an IEEE division is ~10 instructions, and
+  // this transition is instruction-bound (<= 1 ulp per operation, far inside the stated 1e-5 tolerance)
+  constexpr float I_MASS = 1.0f / MASS, I_INERTIA = 1.0f / INERTIA, I_W2 = 1.0f / W2, I_H2 = 1.0f / H2, I_FPS = 1.0f / FPS;
   constexpr float K_N = 1500.0f, C_N = 60.0f, C_T = 30.0f, MU = 1.0f;
   const float gravity = c.p[0], main_power = c.p[1], side_power = c.p[2];
   const float prev = lander_shaping(s);
   float x = s[0] * W2 + W2, y = s[1] * H2 + (PAD + LEG_DOWN);
-  float vx = s[2] * FPS / W2, vy = s[3] * FPS / H2, ang = s[4], om = s[5] * FPS / 20.0f;
+  float vx = s[2] * (FPS * I_W2), vy = s[3] * (FPS * I_H2), ang = s[4], om = s[5] * (FPS / 20.0f);
   float sn, cs;
   sincosf(ang, &sn, &cs);
   const float tipx = sn, tipy = cs, sidex = -cs, sidey = sn;
@@ -180,9 +183,9 @@ __device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, co
   {
     const float ox = tipx * (4.0f / SC), oy = -tipy * (4.0f / SC);
     const float jx = -ox * main_power * mainf, jy = -oy * main_power * mainf;
-    vx += jx / MASS;
-    vy += jy / MASS;
-    om += (ox * jy - oy * jx) / INERTIA;
+    vx += jx * I_MASS;
+    vy += jy * I_MASS;
+    om += (ox * jy - oy * jx) * I_INERTIA;
   }
   const float sidef = (a == 1 || a == 3) ? 1.0f : 0.0f;
   {
@@ -190,9 +193,9 @@ __device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, co
     const float ox = sidex * (d * 12.0f / SC), oy = -sidey * (d * 12.0f / SC);
     const float jx = -ox * side_power, jy = -oy * side_power;
     const float rx = ox - tipx * 17.0f / SC, ry = oy + tipy * 14.0f / SC;
-    vx += jx / MASS;
-    vy += jy / MASS;
-    om += (rx * jy - ry * jx) / INERTIA * sidef;
+    vx += jx * I_MASS;
+    vy += jy * I_MASS;
+    om += (rx * jy - ry * jx) * I_INERTIA * sidef;
   }
   const float footx[2] = {-20.0f / SC, 20.0f / SC}, footy = -26.0f / SC;
   float fx = 0.0f, fy = 0.0f, tq = 0.0f;
@@ -209,9 +212,9 @@ __device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, co
       tq += rx * fn - ry * ft;
     }
   }
-  vx += fx * DT / MASS;
-  vy += (fy / MASS - gravity) * DT;
-  om += tq * DT / INERTIA;
+  vx += fx * (DT * I_MASS);
+  vy += (fy * I_MASS - gravity) * DT;
+  om += tq * (DT * I_INERTIA);
   x += vx * DT;
   y += vy * DT;
   ang += om * DT;
@@ -219,12 +222,12 @@ __device__ __forceinline__ void transition<TPP_LUNAR_LANDER>(float* s, int a, co
   const float c0 = (y + sn * footx[0] + cs * footy <= PAD) ? 1.0f : 0.0f;
   const float c1 = (y + sn * footx[1] + cs * footy <= PAD) ? 1.0f : 0.0f;
   const float hull = fminf(y + sn * (-17.0f / SC) + cs * (-10.0f / SC), y + sn * (17.0f / SC) + cs * (-10.0f / SC));
-  s[0] = (x - W2) / W2;
-  s[1] = (y - (PAD + LEG_DOWN)) / H2;
-  s[2] = vx * W2 / FPS;
-  s[3] = vy * H2 / FPS;
+  s[0] = (x - W2) * I_W2;
+  s[1] = (y - (PAD + LEG_DOWN)) * I_H2;
+  s[2] = vx * (W2 * I_FPS);
+  s[3] = vy * (H2 * I_FPS);
   s[4] = ang;
-  s[5] = 20.0f * om / FPS;
+  s[5] = om * (20.0f * I_FPS);
   s[6] = c0;
   s[7] = c1;
   rew = lander_shaping(s) - prev - 0.30f * mainf - 0.03f * sidef;
