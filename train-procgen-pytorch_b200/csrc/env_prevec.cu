@@ -99,9 +99,12 @@ __device__ __forceinline__ void acrobot_dsdt(const float* y, const float* tr, fl
   const float phi2 = m2 * lc2 * g * s12;
   const float phi1 = -m2 * l1 * lc2 * d2v * d2v * s2 - 2.0f * m2 * l1 * lc2 * d2v * d1v * s2 +
                      (m1 * lc1 + m2 * l1) * g * s1 + phi2;
-  const float ddth2 = (torque + dd2 / dd1 * phi1 - m2 * l1 * lc2 * d1v * d1v * s2 - phi2) /
-                      (m2 * lc2 * lc2 + moi - dd2 * dd2 / dd1);
-  const float ddth1 = -(dd2 * ddth2 + phi1) / dd1;
+  // two IEEE divisions per stage instead of four (1 / dd1 is shared: each division is ~10 instructions and the kernel is
+  // instruction-bound; <= 1-2 ulp per term, inside the 2e-6 + 1e-5 |b| tolerance of tests/test_env_parity.py)
+  const float inv_dd1 = 1.0f / dd1, r21 = dd2 * inv_dd1;
+  const float ddth2 = (torque + r21 * phi1 - m2 * l1 * lc2 * d1v * d1v * s2 - phi2) /
+                      (m2 * lc2 * lc2 + moi - dd2 * r21);
+  const float ddth1 = -(dd2 * ddth2 + phi1) * inv_dd1;
   dy[0] = d1v;
   dy[1] = d2v;
   dy[2] = ddth1;
@@ -137,8 +140,9 @@ __device__ __forceinline__ void transition<TPP_ACROBOT>(float* s, int a, const E
   sincosf(y[0], &tr[1], &tr[0]);
   sincosf(y[1], &tr[3], &tr[2]);
   acrobot_dsdt(y, tr, torque, pr, k4);
+  const float dt6 = dt * (1.0f / 6.0f);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) y[i] = s[i] + dt / 6.0f * (k1[i] + 2.0f * k2[i] + 2.0f * k3[i] + k4[i]);
+  for (int i = 0; i < 4; ++i) y[i] = s[i] + dt6 * (k1[i] + 2.0f * k2[i] + 2.0f * k3[i] + k4[i]);
   if (fabsf(y[0]) > 3.1415925f) y[0] = wrap_pi(y[0]);   // cheap pre-filter just below pi; exact test in double
   if (fabsf(y[1]) > 3.1415925f) y[1] = wrap_pi(y[1]);
   s[0] = y[0];
