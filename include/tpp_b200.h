@@ -156,6 +156,15 @@ int tpp_gae(const float* rew, const uint8_t* done, const float* value, float* ad
  * all-reduce of the three doubles).  Replaces common/storage.py:78-79.                                   */
 int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream);
 
+/* Device-side episode accounting for the logger.  Replaces the O(T*N) host loop of Logger.feed
+ * (common/logger.py:119-147) over the batches of Storage.fetch_log_data (common/storage.py:130-162).
+ * rew f32 / done u8: [T][ld] (the raw env rewards when the env normalises them).  run_ret f64 [N] / run_len i32 [N]:
+ * return and length of every env's open episode, carried between rollouts (updated in place).  scratch: i32 [N+1].
+ * out: f64 [2 + 2*keep] = (episodes finished during this rollout, records written = min(that, keep), then
+ * (return, length) pairs of the LAST `keep` finished episodes in the reference's env-major walk order).     */
+int tpp_episode_scan(const float* rew, const uint8_t* done, int32_t T, int32_t N, int64_t ld, double* run_ret,
+                     int32_t* run_len, int32_t* scratch, double* out, int32_t keep, void* stream);
+
 /* Minibatch gather from the resident rollout by flat sample index k = t*N + e (common/storage.py:112-128).
  * Vector observations: obs feature-major [T+1][n_obs][ld] -> out_obs row-major [mb][ld_out] (cols >= n_obs
  * zero-filled).  out_* arrays are [mb].  idx: int64 [mb] (from torch.randperm on the host: bit-exact).    */
@@ -295,19 +304,21 @@ int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t B, int32_t
 /* out[c] += sum_m x[m*C + c] for a narrow row-major [M][C] matrix (C in 4/8/16/32/64): a convolution's bias gradient
  * from its NHWC output gradient (autograd of nn.Conv2d bias, common/model.py:137-138,158).                     */
 int tpp_colsum_narrow(const float* x, int64_t M, int32_t C, float* out, void* stream);
+/* IMPALA feature sparsity fs = mean_j max_b tanh(|100 h_bj|) over the flattened ReLU'd block-3 features h [M][E]
+ * (ImpalaModel.forward_with_attn_indices, common/model.py:203-208; h = h_hi + h_lo, h_lo nullable).  fs_out[0] is
+ * written; scratch (uint64 [E]) keeps every column's (max value, first argmax row) for the backward call, which adds
+ * d(coef * fs)/dh to the feature gradient dx [M][E] (and refreshes the touched entries of its TF32 pair):
+ * the `fs_coef * feature_sparsity` term of the PPO loss (agents/ppo.py:164-169).                                */
+int tpp_feature_sparsity(const float* h_hi, const float* h_lo, int32_t M, int32_t E, uint64_t* scratch, float* fs_out,
+                         void* stream);
+int tpp_feature_sparsity_grad(const uint64_t* scratch, int32_t E, float coef, float* dx, float* dx_hi, float* dx_lo,
+                              void* stream);
 /* y = act(x + bias) -> plain fp32 (out) and/or TF32 pair (out_hi, out_lo), rows [M][ld]: finishes a dense layer whose
  * contraction was split across CTAs (TPP_EPI_ACCUM) -- the tensor core adds into its fp32 accumulator with
  * truncation, so contractions longer than ~512 terms are chunked and the chunks summed with IEEE adds to stay
  * fp32-grade (IMPALA's 2048-wide fc layer, common/model.py:175).                                               */
 int tpp_bias_act_split(const float* x, int64_t ld_in, int32_t M, int32_t N, const float* bias, int32_t relu, float* out,
                        float* out_hi, float* out_lo, int64_t ld_out, void* stream);
-
-/* Diagnostic (tests only): one TMA im2col box of an NHWC fp32 tensor (3x3 / pad-1 bounding box) copied out of shared
- * memory: out[pixels][channels_per_pixel].  (w, h, n) = base pixel in bounding-box coordinates (output pixel - 1),
- * (off_w, off_h) = filter tap; swizzle: 0 none, 128 = SWIZZLE_128B, 1 = SWIZZLE_128B_ATOM_32B.                 */
-int tpp_debug_tma_im2col(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t channels_per_pixel,
-                         int32_t pixels, int32_t w, int32_t h, int32_t n, int32_t off_w, int32_t off_h,
-                         int32_t swizzle, float* out, void* stream);
 
 /* ---- policy: action sampling at rollout --------------------------------------------------------------- */
 /* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.
@@ -332,6 +343,12 @@ int tpp_mlp_tail_sample(const float* h, int64_t ldh, int32_t K, const float* W, 
 typedef struct {
   float eps_clip, value_coef, entropy_coef, entropy_multiplier, x_entropy_coef;
   int32_t n_actions, mb;
+  int32_t _pad;
+  /* nullable DEVICE float[5] = (eps_clip, value_coef, entropy_coef, entropy_multiplier, x_entropy_coef): when given,
+   * the kernel reads the five coefficients from it at run time instead of from the by-value fields above, so a
+   * captured CUDA graph serves every value (agents/ppo.py:97-101 changes entropy_multiplier every optimize() under
+   * entropy_scaling).  The host fields still say whether the cross-batch entropy term is in use.               */
+  const float* coef_dev;
 } tpp_loss_cfg;
 
 /* head [mb][ld_head] = (A logits, value) -> dhead [mb][ld_head] = dLoss/d(logits, value) and raw sums

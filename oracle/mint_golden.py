@@ -194,13 +194,64 @@ def mint_ppo():
     print("ppo fixtures ok")
 
 
+def logger_batches(seed=9, T=48, N=56, iters=5, p_done=0.06, integer=False):
+    """Deterministic (reward, done) batches for the logger fixture / tests (train and validation streams)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(iters):
+        if integer:
+            rew = rng.integers(-1, 3, (2, T, N)).astype(np.float32)
+        else:
+            rew = rng.normal(size=(2, T, N)).astype(np.float32)
+        done = (rng.random((2, T, N)) < p_done).astype(np.float32)
+        done[:, :, 0] = (rng.random((2, T)) < 0.3)             # an env with many short episodes
+        done[:, :, N - 1] = 0                                  # an env that never finishes
+        out.append((rew[0], done[0], rew[1], done[1]))
+    return out
+
+
+def mint_logger():
+    """Rows of log-append.csv written by the reference Logger (common/logger.py) for fixed batches."""
+    import csv
+    import tempfile
+    import contextlib
+    import io
+    logger_mod = ref_shim.load("common.logger")
+    out = {}
+    for tag, integer, max_steps in (("float", False, 7), ("int", True, 5)):
+        with tempfile.TemporaryDirectory() as d:
+            lg = logger_mod.Logger(56, d)
+            lg.max_steps = max_steps
+            for i, (r, dn, rv, dv) in enumerate(logger_batches(integer=integer)):
+                lg.feed(r, dn, np.nan, rv, dv, np.nan)
+                summary = {k: 0.1 * (i + 1) * (j + 1) for j, k in enumerate(
+                    ["Loss/pi", "Loss/v", "Loss/entropy", "Loss/x_entropy", "Loss/atn_entropy", "Loss/atn_entropy2",
+                     "Loss/sparsity", "Loss/feature_sparsity", "Loss/total"])}
+                with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+                    warnings.simplefilter("ignore")
+                    lg.dump(summary, 1e-3 / (i + 1))
+            rows = list(csv.reader(open(os.path.join(d, "log-append.csv"))))
+        out[f"{tag}_columns"] = np.array(rows[0])
+        out[f"{tag}_rows"] = np.array([[float(x) if x != "" else np.nan for x in r] for r in rows[1:]])
+        out[f"{tag}_num_episodes"] = np.array(lg.num_episodes)
+        out[f"{tag}_reward_buffer"] = np.array(lg.episode_reward_buffer, dtype=np.float64)
+        out[f"{tag}_len_buffer"] = np.array(lg.episode_len_buffer)
+        out[f"{tag}_timeout_buffer"] = np.array(lg.episode_timeout_buffer)
+    np.savez_compressed(os.path.join(OUT, "logger.npz"), **out)
+    print("logger fixture ok:", out["float_rows"].shape, int(out["float_num_episodes"]))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.filterwarnings("ignore", category=SyntaxWarning)
+    if len(sys.argv) > 1 and sys.argv[1] == "logger":
+        mint_logger()
+        return
     for fam in FAMILIES:
         mint_prevec(fam)
     mint_boxworld()
     mint_ppo()
+    mint_logger()
     print("written to", OUT, [f for f in os.listdir(OUT)])
 
 

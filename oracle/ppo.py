@@ -150,9 +150,12 @@ def ppo_loss(dist, value, act, old_logp, old_value, ret, adv, eps_clip=0.2, valu
     v_loss = 0.5 * torch.max((value - ret).pow(2), (clipped - ret).pow(2)).mean()
     x_ent, ent = cross_batch_entropy(dist)
     loss = pi_loss + value_coef * v_loss - entropy_coef * ent * entropy_multiplier - x_entropy_coef * x_ent
+    terms = dict(pi_loss=pi_loss, value_loss=v_loss, entropy=ent, x_entropy=x_ent)
     if fs is not None:
         loss = loss + fs_coef * fs
-    return loss, dict(pi_loss=pi_loss, value_loss=v_loss, entropy=ent, x_entropy=x_ent, total=loss)
+        terms["fs"] = fs
+    terms["total"] = loss
+    return loss, terms
 
 
 def optimize(policy, optimizer, data, n_steps, n_envs, epoch=3, n_minibatch=8, mini_batch_size=8192,

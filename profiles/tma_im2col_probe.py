@@ -36,7 +36,11 @@ def run(name, B, H, W, C, cpp, pixels, w, h, n, ow, oh, swz=0):
     x = make(B, H, W, C)
     out = torch.full((pixels, cpp), -1.0, device="cuda")
     try:
-        L.call("tpp_debug_tma_im2col", L.ptr(x), B, H, W, C, cpp, pixels, w, h, n, ow, oh, swz, L.ptr(out), L.stream_ptr())
+        import ctypes
+        probe = ctypes.CDLL(os.path.join(ROOT, "tests", "native", "libtpp_probe.so"))     # make -C tests/native
+        probe.tpp_debug_tma_im2col.argtypes = [ctypes.c_void_p] + [ctypes.c_int32] * 12 + [ctypes.c_void_p] * 2
+        assert probe.tpp_debug_tma_im2col(L.ptr(x), B, H, W, C, cpp, pixels, w, h, n, ow, oh, swz, L.ptr(out),
+                                          L.stream_ptr()) == 0
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         print(f"{name}: ERROR {e}")

@@ -1,10 +1,10 @@
-// Diagnostic entry: one TMA im2col load (cp.async.bulk.tensor.4d ... .im2col) of an NHWC fp32 tensor into shared
+// Test-only diagnostic (built into tests/native/libtpp_probe.so, NOT part of the product library or its ABI): one TMA im2col load (cp.async.bulk.tensor.4d ... .im2col) of an NHWC fp32 tensor into shared
 // memory, copied out linearly.  tests/test_conv_ops.py uses it to pin the descriptor / coordinate conventions that
 // the implicit-GEMM convolution path of csrc/gemm_tc.cu relies on (bounding-box corners, base pixel coordinates, tap
 // offsets, zero fill of padding pixels, of channels beyond C and of pixels beyond the last image).
 #include <cuda.h>
 
-#include "tpp_common.cuh"
+#include "../../train-procgen-pytorch_b200/csrc/tpp_common.cuh"
 
 namespace tpp {
 namespace probe {

@@ -35,7 +35,7 @@ def test_header_symbols_are_exported_and_bound(lib):
 def test_struct_sizes_match_the_header(lib):
     assert ctypes.sizeof(lib.EnvCfg) == 4 * 4 + 8 + 16 * 4 * 2 + 8 * 4
     assert ctypes.sizeof(lib.BoxWorldState) == 4 * 4 + 8 + 4 * 4 + 11 * 8
-    assert ctypes.sizeof(lib.LossCfg) == 7 * 4
+    assert ctypes.sizeof(lib.LossCfg) == 8 * 4 + 8
     assert ctypes.sizeof(lib.AdamState) == 4 * 8 + 2 * 4 + 2 * 4 + 2 * 8
 
 

@@ -16,6 +16,19 @@ def _lib():
     return _lib
 
 
+def _probe():
+    """tests/native/libtpp_probe.so: the test-only TMA im2col probe (not part of the product library)."""
+    import ctypes
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "libtpp_probe.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/native/libtpp_probe.so not built (make -C tests/native)")
+    lib = ctypes.CDLL(path)
+    lib.tpp_debug_tma_im2col.argtypes = [ctypes.c_void_p] + [ctypes.c_int32] * 12 + [ctypes.c_void_p] * 2
+    lib.tpp_debug_tma_im2col.restype = ctypes.c_int
+    return lib
+
+
 def _pair(x):
     hi = ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
     return hi, x - hi
@@ -282,8 +295,9 @@ def test_tma_im2col_conventions(B, H, W, C, cpp, base, tap):
     b, h, w, c = torch.meshgrid(torch.arange(B), torch.arange(H), torch.arange(W), torch.arange(C), indexing="ij")
     x = ((b + 1) * 1000000 + h * 10000 + w * 100 + c).float().cuda().contiguous()
     out = torch.full((128, cpp), -1.0, device="cuda")
-    L.call("tpp_debug_tma_im2col", L.ptr(x), B, H, W, C, cpp, 128, base[0], base[1], base[2], tap[0], tap[1], 0,
-           L.ptr(out), L.stream_ptr())
+    rc = _probe().tpp_debug_tma_im2col(L.ptr(x), B, H, W, C, cpp, 128, base[0], base[1], base[2], tap[0], tap[1], 0,
+                                       L.ptr(out), L.stream_ptr())
+    assert rc == 0
     assert torch.equal(out.cpu(), _probe_expected(x, cpp, 128, *base, *tap))
 
 

@@ -1,5 +1,5 @@
 """GPU: IMPALA-CNN policy (reference common/model.py:134-208) through the hand-written engine (im2col + tcgen05 GEMM,
-matmul="tf32x3") and through the library cross-check path (cuDNN via torch, matmul="library"), both with this
+matmul="tf32x3") and through the tests' cross-check engine (cuDNN via torch autograd, tests/torch_engine.py), both with this
 repo's gather / fused loss / clip+Adam kernels, and the host-stepped env path
 (Procgen-style numpy VecEnv staged through Storage.store).  Parity: one optimize() against the torch-CPU oracle."""
 import numpy as np
@@ -19,18 +19,25 @@ def _impala_agent(T, N, A, hw=(64, 64), **kw):
     torch.manual_seed(3)
     pol = CategoricalPolicy(ImpalaModel(3, input_hw=hw), False, A).to("cuda").flatten_()
     st = Storage((3, *hw), 256, T, N, "cuda")
+    if kw.get("matmul") == "library":
+        from torch_engine import TorchModuleEngine
+        kw.pop("matmul")
+        kw["engine"] = TorchModuleEngine(pol, A, (3, *hw))
     agent = PPO(kw.pop("env", None), pol, None, st, "cuda", 0, n_steps=T, n_envs=N, epoch=1, n_minibatch=2,
                 mini_batch_size=64, learning_rate=5e-4, entropy_coef=0.01, **kw)
     return agent, pol, st
 
 
-@pytest.mark.parametrize("matmul", ["tf32x3", "library"])
-def test_impala_optimize_matches_oracle(matmul):
-    from tpp_b200.common.engine import ImpalaEngineTC, TorchModuleEngine
+@pytest.mark.parametrize("matmul,fs_coef", [("tf32x3", 0.0), ("library", 0.0), ("tf32x3", 0.3), ("library", 0.3)])
+def test_impala_optimize_matches_oracle(matmul, fs_coef):
+    """fs_coef != 0: the feature-sparsity term of the loss (common/model.py:203-208, agents/ppo.py:164-169) and its
+    gradient on the hand-written engine (tpp_feature_sparsity / _grad)."""
+    from tpp_b200.common.engine import ImpalaEngineTC
+    from torch_engine import TorchModuleEngine
     T, N, A = 8, 16, 15
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    agent, pol, st = _impala_agent(T, N, A, matmul=matmul)
+    agent, pol, st = _impala_agent(T, N, A, matmul=matmul, fs_coef=fs_coef)
     assert isinstance(agent.engine, ImpalaEngineTC if matmul == "tf32x3" else TorchModuleEngine)
     g = torch.Generator().manual_seed(0)
     frames = torch.randint(0, 256, (T + 1, N, 64, 64, 3), generator=g, dtype=torch.uint8)
@@ -51,12 +58,13 @@ def test_impala_optimize_matches_oracle(matmul):
     opt = oppo.make_adam(ref, 5e-4)
     torch.manual_seed(99)
     logs = oppo.optimize(ref, opt, data, T, N, epoch=1, n_minibatch=2, mini_batch_size=64, grad_clip_norm=0.5,
-                         eps_clip=0.2, value_coef=0.5, entropy_coef=0.01)
+                         eps_clip=0.2, value_coef=0.5, entropy_coef=0.01, fs_coef=fs_coef)
     torch.manual_seed(99)
     summary = agent.optimize()
     np.testing.assert_allclose(summary["Loss/total"], np.mean([l["total"] for l in logs]), rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(summary["Loss/entropy"], np.mean([l["entropy"] for l in logs]), rtol=2e-4)
-    assert np.isfinite(summary["Loss/feature_sparsity"])          # IMPALA reports it (common/model.py:203-208)
+    # IMPALA reports the feature sparsity every minibatch (common/model.py:203-208)
+    np.testing.assert_allclose(summary["Loss/feature_sparsity"], np.mean([l["fs"] for l in logs]), rtol=1e-4)
     for (k, p), (_, q) in zip(pol.state_dict().items(), ref.state_dict().items()):
         np.testing.assert_allclose(p.cpu().numpy(), q.numpy(), rtol=5e-3, atol=2e-5, err_msg=k)
 

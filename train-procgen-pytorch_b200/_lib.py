@@ -36,7 +36,7 @@ class BoxWorldState(C.Structure):
 class LossCfg(C.Structure):
     _fields_ = [("eps_clip", C.c_float), ("value_coef", C.c_float), ("entropy_coef", C.c_float),
                 ("entropy_multiplier", C.c_float), ("x_entropy_coef", C.c_float), ("n_actions", C.c_int32),
-                ("mb", C.c_int32)]
+                ("mb", C.c_int32), ("_pad", C.c_int32), ("coef_dev", C.c_void_p)]
 
 
 class AdamState(C.Structure):   # mirrors tpp_adam_state (lives in device memory; this is the host image)
@@ -80,6 +80,7 @@ SIGNATURES = {
     "tpp_vecnormalize_step": [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _f64, _f64, _f64, _vp],
     "tpp_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp],
     "tpp_adv_normalize": [_vp, _vp, _i32, _i32, _i64, _vp],
+    "tpp_episode_scan": [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
                        _vp, _vp, _vp, _vp],
     "tpp_gather_img": [_vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
@@ -90,8 +91,9 @@ SIGNATURES = {
     "tpp_gemm_tc": [C.POINTER(TcGemm), _vp],
     "tpp_split_tf32": [_vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp],
     "tpp_im2col3x3": [_vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _f32, _vp, _vp, _i32, _vp],
-    "tpp_debug_tma_im2col": [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp],
     "tpp_colsum_narrow": [_vp, _i64, _i32, _vp, _vp],
+    "tpp_feature_sparsity": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
+    "tpp_feature_sparsity_grad": [_vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "tpp_bias_act_split": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],

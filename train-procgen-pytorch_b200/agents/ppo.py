@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib, parallel
-from ..common.engine import ImpalaEngineTC, MLPEngine, MLPEngineTC, TorchModuleEngine
+from ..common.engine import ImpalaEngineTC, MLPEngine, MLPEngineTC
 from ..common.model import ImpalaModel, MLPModel
 from .base_agent import BaseAgent
 
@@ -149,9 +149,15 @@ class PPO(BaseAgent):
             policy.flatten_(device)
         self.n_actions = policy.action_size
         # dense-layer arithmetic: "tf32x3" (default) = tcgen05 tensor cores with the error-compensated 3xTF32 split
-        # (fp32-grade, the parity path), "tf32" = single-pass tensor-core fast mode (~1e-3), "fp32" = CUDA cores.
+        # (fp32-grade, the parity path), "tf32" = single-pass tensor-core fast mode (~1e-3), "fp32" = exact CUDA-core
+        # GEMM (MLP only).  All three are this library's kernels; there is no cuDNN / cuBLAS route in the product
+        # (tests inject their torch-autograd cross-check engine through ``engine=``).
         self.matmul = kwargs.get("matmul", "tf32x3")
-        if isinstance(policy.embedder, MLPModel):
+        if self.matmul not in ("tf32x3", "tf32", "fp32"):
+            raise ValueError(f"matmul must be tf32x3, tf32 or fp32, not {self.matmul!r}")
+        if kwargs.get("engine") is not None:
+            self.engine = kwargs["engine"]
+        elif isinstance(policy.embedder, MLPModel):
             if self.matmul == "fp32":
                 self.engine = MLPEngine(policy, self.n_actions)
             else:
@@ -159,14 +165,13 @@ class PPO(BaseAgent):
                 # MMA passes) with ScaledFloatFrame's 1/255 folded into the layer's weight copy
                 self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1,
                                           raw_pixels=bool(getattr(storage, "is_image", False)))
-        elif isinstance(policy.embedder, ImpalaModel) and self.matmul in ("tf32x3", "tf32") \
-                and not fs_coef:
-            # IMPALA convolutions as im2col + tcgen05 GEMM (hand-written path)
+        elif isinstance(policy.embedder, ImpalaModel):
+            # IMPALA convolutions as implicit GEMMs on the tcgen05 kernel (TMA im2col)
             self.engine = ImpalaEngineTC(policy, self.n_actions, storage.obs_shape,
-                                         precision=3 if self.matmul == "tf32x3" else 1)
+                                         precision=1 if self.matmul == "tf32" else 3)
         else:
-            # matmul="library": cuDNN/cuBLAS through torch autograd (cross-check path, other embedders)
-            self.engine = TorchModuleEngine(policy, self.n_actions, storage.obs_shape)
+            raise NotImplementedError(f"no engine for embedder {type(policy.embedder).__name__}: the hot path covers "
+                                      "MLPModel and ImpalaModel (SURVEY 8a10)")
         self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
         self.world_size = 1
         self.process_group = None
@@ -288,11 +293,22 @@ class PPO(BaseAgent):
         if self._stats is None or self._stats.shape[0] != total:
             self._stats = torch.zeros(total, NS, dtype=torch.float64, device=dev)
         self._stats.zero_()
-        cfg = _lib.LossCfg(self.eps_clip, self.value_coef, self.entropy_coef, float(self.entropy_multiplier),
-                           self.x_entropy_coef, A, mb)
+        # the five loss coefficients live in a small device buffer the loss kernel reads at run time (like Adam's lr), so
+        # a captured graph serves every value: entropy_scaling changes the multiplier every call (agents/ppo.py:97-101)
+        coef = (self.eps_clip, self.value_coef, self.entropy_coef, float(self.entropy_multiplier), self.x_entropy_coef)
+        if getattr(self, "_coef_dev", None) is None:
+            self._coef_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+            self._coef_pinned = torch.zeros(8, 8, dtype=torch.float32).pin_memory()   # ring: the host may run ahead
+            self._coef_host, self._coef_slot = None, 0
+        if coef != self._coef_host:
+            self._coef_slot = (self._coef_slot + 1) % 8
+            self._coef_pinned[self._coef_slot, :5] = torch.tensor(coef, dtype=torch.float32)
+            self._coef_dev.copy_(self._coef_pinned[self._coef_slot], non_blocking=True)
+            self._coef_host = coef
+        cfg = _lib.LossCfg(*coef, A, mb, 0, self._coef_dev.data_ptr())
         engine = self.engine
         fs_vals = []
-        is_torch_engine = isinstance(engine, TorchModuleEngine)
+        is_torch_engine = getattr(engine, "uses_autograd", False)
         step_every = int(accum) if float(accum).is_integer() else 0
         # Gradient-accumulation groups.  The reference runs `accum` minibatches between two optimizer steps
         # (agents/ppo.py:111,173-177) and the weights do not change in between, so G of them (G | accum) share ONE
@@ -339,12 +355,12 @@ class PPO(BaseAgent):
                           _lib.ptr(buf.logp), _lib.ptr(buf.value), _lib.ptr(buf.ret), _lib.ptr(buf.adv),
                           _lib.ptr(pbar), _lib.ptr(ws_dhead), _lib.ptr(stats_rows), s)
             self.n_launches += 1
-            if is_torch_engine:
+            if is_torch_engine or isinstance(engine, ImpalaEngineTC):
                 engine.backward(ws_dhead, rows, self.fs_coef)
             else:
                 engine.backward(ws_dhead, rows)
 
-        graph_key = (mb, G, float(self.entropy_multiplier), id(st))
+        graph_key = (mb, G, self.x_entropy_coef != 0.0, id(st))
         use_graph = self.use_cuda_graph and not is_torch_engine
         graphs = self.__dict__.setdefault("_mb_graphs", {})
         k = 0
@@ -354,14 +370,13 @@ class PPO(BaseAgent):
         # copies and stats copies of an iteration from the host's critical path.
         epoch_graph = (use_graph and self.use_epoch_graph and self.world_size == 1 and step_every > 0
                        and n_mb % step_every == 0
-                       and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0
-                       and self.entropy_scaling is None)
+                       and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0)
         if epoch_graph:
             if getattr(self, "_epoch_idx", None) is None or self._epoch_idx.shape != (n_mb, mb):
                 self._epoch_idx = torch.zeros(n_mb, mb, dtype=torch.int64, device=dev)
                 self._epoch_stats = torch.zeros(n_mb, NS, dtype=torch.float64, device=dev)
             egraphs = self.__dict__.setdefault("_epoch_graphs", {})
-            ekey = (mb, n_mb, G, step_every, float(self.entropy_multiplier), id(st))
+            ekey = (mb, n_mb, G, step_every, id(st))
             idx_g, stats_g = self._epoch_idx.view(n_grp, rows), self._epoch_stats.view(n_grp, G, NS)
 
             def epoch_body():
@@ -659,40 +674,48 @@ class PPO(BaseAgent):
         rollouts()
         while self.t < num_timesteps:
             summary_fn = self.optimize(defer_summary=True)
-            logs = None
-            if self.logger is not None:
-                logs = (self.storage.snapshot_log_data(),
-                        self.storage_valid.snapshot_log_data() if self.storage_valid is not None else None)
+            logs = self._snapshot_logs()
             self.t += self.n_steps * self.n_envs
             self._carry_over(self.storage)
             if self.env_valid is not None:
                 self._carry_over(self.storage_valid)
+            # reference order (agents/ppo.py:257-276): t advances, the learning rate of the NEXT update is set, then the
+            # checkpoint is written -- so a checkpoint's optimizer state carries the adjusted rate
+            self.optimizer, lr = self.adjust_lr(self.optimizer, self.learning_rate, self.t, num_timesteps)
             save = self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]
             if save:                                   # (weights of iteration i: before the next update exists)
                 self.save_checkpoint()
                 checkpoint_cnt += 1
-            # the learning rate of the next update is set by _log (adjust_lr), i.e. before the next optimize()
             if self.t < num_timesteps:
                 rollouts()
-            self._log(summary_fn(), num_timesteps, logs)
+            self._log(summary_fn(), lr, logs)
         self.env.close()
         if self.env_valid is not None:
             self.env_valid.close()
 
-    def _log(self, summary, num_timesteps, snapshots=None):
+    def _snapshot_logs(self):
+        """Start the device -> host copies the logger needs for the rollout just consumed.  A logger with
+        ``feed_episodes`` (this package's) gets the device-side episode records (a few hundred bytes); any other
+        object with the reference's ``feed`` gets the [T, N] reward / done batches."""
+        if self.logger is None:
+            return None
+        sv = self.storage_valid
+        if hasattr(self.logger, "feed_episodes"):
+            return ("episodes", self.storage.snapshot_episodes(), sv.snapshot_episodes() if sv is not None else None)
+        return ("batches", self.storage.snapshot_log_data(), sv.snapshot_log_data() if sv is not None else None)
+
+    def _log(self, summary, lr, snapshots=None):
         if self.logger is not None:
-            if snapshots is not None:
-                rew_batch, done_batch, tar = snapshots[0]()
-                rew_v, done_v, tar_v = snapshots[1]() if snapshots[1] is not None else (None, None, None)
+            if snapshots is None:
+                snapshots = self._snapshot_logs()
+            kind, tr, va = snapshots
+            if kind == "episodes":
+                nan = float("nan")
+                self.logger.feed_episodes(self.n_steps, tr(), nan, va() if va is not None else None, nan)
             else:
-                rew_batch, done_batch, tar = self.storage.fetch_log_data()
-                if self.storage_valid is not None:
-                    rew_v, done_v, tar_v = self.storage_valid.fetch_log_data()
-                else:
-                    rew_v = done_v = tar_v = None
-            self.logger.feed(rew_batch, done_batch, tar, rew_v, done_v, tar_v)
-        self.optimizer, lr = self.adjust_lr(self.optimizer, self.learning_rate, self.t, num_timesteps)
-        if self.logger is not None:
+                rew_batch, done_batch, tar = tr()
+                rew_v, done_v, tar_v = va() if va is not None else (None, None, None)
+                self.logger.feed(rew_batch, done_batch, tar, rew_v, done_v, tar_v)
             self.logger.dump(summary, lr)
 
     def save_checkpoint(self):
@@ -712,7 +735,7 @@ class PPO(BaseAgent):
         graphs = self.__dict__.setdefault("_host_graphs", {})
         key = (id(st), t)
         entry = graphs.get(key)
-        if not self.use_cuda_graph or isinstance(self.engine, TorchModuleEngine):
+        if not self.use_cuda_graph or getattr(self.engine, "uses_autograd", False):
             return body()
         if entry is None:                      # first visit: eager (allocates the workspaces)
             body()

@@ -6,9 +6,7 @@ kernels (no autograd on the hot path).
 * ``MLPEngineTC`` — the same on the tcgen05 tensor-core GEMM (3xTF32 parity mode or single-pass TF32).
 * ``ImpalaEngineTC`` — ImpalaModel + heads: NHWC activations, 3x3 convolutions as im2col + tcgen05 GEMM with the
                     residual adds / ReLU masks / bias gradients fused into the GEMM epilogues, max-pool kernels.
-* ``TorchModuleEngine`` — library path (cuDNN/cuBLAS through torch autograd) kept as the cross-check for
-                    ``ImpalaEngineTC`` and for embedders without hand-written kernels.  The heads' output still
-                    feeds the fused loss kernel and the flat-buffer Adam.
+(The cuDNN / cuBLAS cross-check engine used by the tests lives in tests/torch_engine.py: it is not part of the product.)
 
 Replaces: ``policy.embedder.forward_with_attn_indices`` + ``policy.hidden_to_output`` + ``loss.backward()``
 (agents/ppo.py:125-128,170) and ``policy(obs, hx, mask)`` in ``PPO.predict`` (agents/ppo.py:76).
@@ -144,40 +142,6 @@ class MLPEngine:
     def _split_k(M, rows, cols):
         tiles = _ceil(rows, 64) * _ceil(cols, 64)
         return max(1, min(_ceil(M, 256), _ceil(296, tiles)))
-
-
-class TorchModuleEngine:
-    """Library path: embedder + heads through torch (cuDNN/cuBLAS) with autograd, sharing the flat buffers."""
-
-    def __init__(self, policy, n_actions, obs_shape):
-        assert policy.flat is not None, "call policy.flatten_() first"
-        self.policy, self.A = policy, n_actions
-        self.ld_head = _ceil(n_actions + 1, 4) * 4
-        self.obs_shape = tuple(obs_shape)
-        self.device = policy.flat.device
-        self.n_launches = 0
-        self.last_fs = None
-
-    def forward(self, x, M, feature_major_ld=None, train=False):
-        assert feature_major_ld is None
-        x = x[:, :int(torch.tensor(self.obs_shape).prod())].reshape(M, *self.obs_shape)
-        with torch.set_grad_enabled(train):
-            feat, _, fs, _ = self.policy.embedder.forward_with_attn_indices(x)
-            logits = self.policy.fc_policy(feat)
-            value = self.policy.fc_value(feat)
-            head = torch.zeros(M, self.ld_head, dtype=torch.float32, device=self.device)
-            head = torch.cat((logits, value, head[:, self.A + 1:]), 1)
-        self._head, self.last_fs = head, fs
-        return head
-
-    def backward(self, dhead, M, fs_coef=0.0):
-        extra = None
-        if fs_coef and self.last_fs is not None:
-            extra = fs_coef * self.last_fs
-        if extra is not None:
-            torch.autograd.backward([self._head, extra], [dhead, torch.ones_like(extra)])
-        else:
-            self._head.backward(dhead)
 
 
 class MLPEngineTC(MLPEngine):
@@ -429,9 +393,10 @@ class ImpalaEngineTC:
 
     ``x`` for ``forward`` is what ``tpp_gather_img`` / ``tpp_frames_to_obs`` produce: fp32 rows ``[M][ld]`` holding
     the frame as NCHW / 255 (the first im2col reads it through strides, nothing is transposed).
-    The feature-sparsity term of ``forward_with_attn_indices`` (common/model.py:203-208) has coefficient 0 in every
-    shipped config: its VALUE is reported (three small torch reductions over the flattened features, logging only),
-    its gradient is not implemented here (``fs_coef != 0`` selects ``TorchModuleEngine``).
+    The feature-sparsity term of ``forward_with_attn_indices`` (common/model.py:203-208), fs = mean_j max_b
+    tanh(|100 h_bj|), is computed by ``tpp_feature_sparsity`` on the ReLU'd block-3 features (value logged every
+    minibatch like the reference); with ``fs_coef != 0`` its gradient is added to the feature gradient in front of
+    block 3's backward pass (``tpp_feature_sparsity_grad``).
     """
 
     _tc = MLPEngineTC._tc
@@ -571,6 +536,8 @@ class ImpalaEngineTC:
         ws.dz = (torch.zeros(M, self.latent, **f), torch.zeros(M, self.latent, **f))
         ws.head = torch.zeros(M, self.ld_head, **f)
         ws.dhead = torch.zeros(M, self.ld_head, **f)
+        ws.fs_key = torch.zeros(self.enc, dtype=torch.int64, device=self.device)   # (max, argmax row) per feature
+        ws.fs = torch.zeros(1, **f)
         self._ws[M] = ws
         return ws
 
@@ -643,8 +610,11 @@ class ImpalaEngineTC:
         self._tc(ws.f, self.latent, self.wh, self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
                  bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         self._x = x
-        if train:   # logged value only: mean_j max_b tanh(|100 h_bj|), h >= 0 so the max commutes with tanh
-            self.last_fs = torch.tanh(100.0 * (ws.h[0] + ws.h[1]).amax(0)).mean()
+        if train:   # feature sparsity (logged every minibatch; enters the loss when fs_coef != 0)
+            _lib.call("tpp_feature_sparsity", _lib.ptr(ws.h[0]), _lib.ptr(ws.h[1]), M, self.enc, _lib.ptr(ws.fs_key),
+                      _lib.ptr(ws.fs), _lib.stream_ptr())
+            self.n_launches += 2
+            self.last_fs = ws.fs[0]
         return ws.head
 
     # ------------------------------------------------------------------------------------------
@@ -685,8 +655,6 @@ class ImpalaEngineTC:
         self.n_launches += 1
 
     def backward(self, dhead, M, fs_coef=0.0):
-        if fs_coef:
-            raise NotImplementedError("feature-sparsity gradient: use the library engine (matmul='library')")
         ws, s = self._workspace(M), _lib.stream_ptr()
         H, nh = self.latent, self.A + 1
         assert H in (16, 32, 64, 128, 256) and nh <= 16
@@ -706,6 +674,10 @@ class ImpalaEngineTC:
         d = ws.blk[-1]["gX"]
         self._tc(ws.dz, H, self.wfc, self.enc, M, self.enc, H, b_mn=1, flags=EPI_MASK, mask=ws.h[0], ld_mask=self.enc,
                  out=d["plain"], out_pair=(d["hi"], d["lo"]), ldc=self.enc)
+        if fs_coef:      # + fs_coef * d feature_sparsity / d h (agents/ppo.py:164-169), needs forward(train=True)
+            _lib.call("tpp_feature_sparsity_grad", _lib.ptr(ws.fs_key), self.enc, float(fs_coef), _lib.ptr(d["plain"]),
+                      _lib.ptr(d["hi"]), _lib.ptr(d["lo"]), s)
+            self.n_launches += 1
         for k in range(len(self.blocks) - 1, -1, -1):
             b, wb = self.blocks[k], ws.blk[k]
             Hh, Ww, Ho, Wo, cout = b["H"], b["W"], b["Ho"], b["Wo"], b["cout"]

@@ -1,111 +1,154 @@
-"""Episode statistics + CSV logging with the reference Logger's interface and column schema
-(common/logger.py:13-236): ``feed(rew_batch, done_batch, true_mean_reward, rew_batch_v, done_batch_v,
-true_mean_reward_v)`` once per iteration, ``dump(summary, lr)``, ``episode_reward_buffer``, ``logdir``.
+"""Episode statistics + CSV logging with the reference Logger's interface, accounting and column schema
+(common/logger.py:13-200): ``feed(rew_batch, done_batch, true_mean_reward, rew_batch_v, done_batch_v,
+true_mean_reward_v)`` once per iteration, ``dump(summary, lr)``, ``episode_reward_buffer``, ``logdir``, ``max_steps``.
 
-The reference walks the [T, N] batches with an O(T*N) Python double loop (:119-147); here the episode boundaries are
-found with vectorised numpy on the arrays ``Storage.fetch_log_data`` returns (same episode accounting: a running
-return per env, closed at every done flag, last 40 episodes kept).  wandb / pandas are not used on the hot path."""
+Same accounting as the reference's double loop (:119-147): envs are walked in index order and, within an env, steps in
+time order (ENV-MAJOR), every done flag closes the env's open episode (return = sum of its rewards since the previous
+done, possibly begun in an earlier rollout; length likewise; time-out iff ``length == max_steps``), and the last 40
+closed episodes live in the deques the statistics are taken from.  ``log-append.csv`` has the reference's columns in
+the reference's order (time, 10 episode metrics, 10 ``val_`` metrics, ``ema_rewards``, the 9 loss metrics,
+``learning_rate``).
+
+Two producers feed it:
+* ``feed(...)`` -- the reference call with [T, N] host batches; the O(T*N) Python loop is vectorised numpy.
+* ``feed_episodes(...)`` -- the device path: ``Storage.snapshot_episodes`` runs ``tpp_episode_scan`` on the
+  rollout in HBM and hands over only the episode count and the last 40 (return, length) records.
+wandb / pandas are not used.
+"""
 from __future__ import annotations
 
 import csv
 import os
 import time
+import warnings
 from collections import deque
 
 import numpy as np
 
-LOSS_KEYS = ["Loss/pi", "Loss/v", "Loss/entropy", "Loss/x_entropy", "Loss/atn_entropy", "Loss/atn_entropy2",
-             "Loss/sparsity", "Loss/feature_sparsity", "Loss/total"]
-EPISODE_KEYS = ["max_episode_rewards", "mean_episode_rewards", "min_episode_rewards", "max_episode_len",
-                "mean_episode_len", "min_episode_len", "mean_timeouts"]
+TIME_METRICS = ["timesteps", "wall_time", "num_episodes"]
+LOSS_METRICS = ["loss_pi", "loss_v", "loss_entropy", "loss_x_entropy", "atn_entropy", "atn_entropy2",
+                "loss_sparsity", "loss_feature_sparsity", "loss_total"]
+EPISODE_METRICS = ["max_episode_rewards", "mean_episode_rewards", "median_episode_rewards", "min_episode_rewards",
+                   "max_episode_len", "mean_episode_len", "min_episode_len", "mean_timeouts",
+                   "mean_episode_len_pos_reward", "balanced_mean_rewards"]
+KEEP = 40          # maxlen of the reference's episode deques (common/logger.py:33-35)
+
+
+def close_episodes(rew, done, run_ret, run_len):
+    """Vectorised restatement of the reference's episode walk.  rew, done: [T, N]; run_ret (float64 [N]) / run_len
+    (int64 [N]) hold every env's open episode and are updated in place.  Returns (returns, lengths) of the episodes
+    closed by this batch in env-major order."""
+    rew = np.asarray(rew, dtype=np.float64)
+    T, N = rew.shape
+    csum = np.cumsum(rew, axis=0)
+    e_idx, t_idx = np.nonzero(np.asarray(done).T > 0)          # row-major over [N, T] = env-major episode order
+    prev_same = np.zeros(len(e_idx), dtype=bool)
+    prev_same[1:] = e_idx[1:] == e_idx[:-1]
+    start = np.where(prev_same, np.concatenate(([0], t_idx[:-1])), -1)       # previous done of the same env, or -1
+    seg = csum[t_idx, e_idx] - np.where(start >= 0, csum[np.maximum(start, 0), e_idx], 0.0)
+    rets = seg + np.where(start < 0, run_ret[e_idx], 0.0)
+    lens = (t_idx - start) + np.where(start < 0, run_len[e_idx], 0)
+    last = np.full(N, -1)
+    last[e_idx] = t_idx                                          # (later entries of an env overwrite earlier ones)
+    open_env = last < 0
+    run_ret[:] = np.where(open_env, run_ret + csum[-1], csum[-1] - csum[np.maximum(last, 0), np.arange(N)])
+    run_len[:] = np.where(open_env, run_len + T, T - 1 - last)
+    return rets, lens
 
 
 class Logger:
-    def __init__(self, n_envs, logdir=None, use_wandb=False, has_vq=False, transition_model=False, double_graph=False,
-                 ppo_pure=False, IPL=False, sae=False):
+    def __init__(self, n_envs, logdir=None, use_wandb=False, has_vq=False, algo="ppo", greedy=False):
         self.start_time = time.time()
-        self.n_envs, self.logdir = n_envs, logdir
-        self.episode_rewards = np.zeros(n_envs)
+        self.n_envs, self.logdir, self.use_wandb, self.greedy = n_envs, logdir, use_wandb, greedy
+        self.true_mean_reward = self.true_mean_reward_v = None
+        self.episode_rewards = np.zeros(n_envs)                       # open-episode return / length per env
         self.episode_lens = np.zeros(n_envs, dtype=np.int64)
         self.episode_rewards_v = np.zeros(n_envs)
         self.episode_lens_v = np.zeros(n_envs, dtype=np.int64)
-        self.episode_timeout_buffer = deque(maxlen=40)
-        self.episode_len_buffer = deque(maxlen=40)
-        self.episode_reward_buffer = deque(maxlen=40)
-        self.episode_timeout_buffer_v = deque(maxlen=40)
-        self.episode_len_buffer_v = deque(maxlen=40)
-        self.episode_reward_buffer_v = deque(maxlen=40)
-        self.true_mean_reward = self.true_mean_reward_v = np.nan
-        self.max_steps = 10 ** 9
-        self.columns = (["timesteps", "wall_time", "num_episodes"] + EPISODE_KEYS + ["val_" + k for k in EPISODE_KEYS]
-                        + ["true_mean_reward", "val_true_mean_reward", "learning_rate"] + LOSS_KEYS)
+        self.episode_timeout_buffer = deque(maxlen=KEEP)
+        self.episode_len_buffer = deque(maxlen=KEEP)
+        self.episode_reward_buffer = deque(maxlen=KEEP)
+        self.episode_timeout_buffer_v = deque(maxlen=KEEP)
+        self.episode_len_buffer_v = deque(maxlen=KEEP)
+        self.episode_reward_buffer_v = deque(maxlen=KEEP)
+        self.max_steps = None            # set by the caller like the reference does (train.py:201)
+        self.columns = (TIME_METRICS + EPISODE_METRICS + ["val_" + m for m in EPISODE_METRICS] + ["ema_rewards"]
+                        + LOSS_METRICS + ["learning_rate"])
         self.timesteps, self.num_episodes = 0, 0
-        self.rows = []
+        self.log = []                    # rows of log-append.csv
         if logdir:
             os.makedirs(logdir, exist_ok=True)
-            with open(os.path.join(logdir, "log-append.csv"), "w", newline="") as f:
-                csv.writer(f).writerow(self.columns)
 
-    @staticmethod
-    def _episodes(rew, done, run_ret, run_len):
-        """Close episodes at done flags.  rew, done: [T, N].  Returns (returns, lengths) in (t, env) order and
-        updates the running accumulators in place — the same bookkeeping as the reference's double loop."""
-        T, N = rew.shape
-        csum = np.cumsum(rew, axis=0)
-        rets, lens = [], []
-        t_idx, e_idx = np.nonzero(done > 0)
-        last_t = np.full(N, -1)
-        order = np.lexsort((e_idx, t_idx))
-        for t, e in zip(t_idx[order], e_idx[order]):
-            start = last_t[e]
-            seg = csum[t, e] - (csum[start, e] if start >= 0 else 0.0)
-            rets.append(run_ret[e] + seg if start < 0 else seg)
-            lens.append((run_len[e] if start < 0 else 0) + (t - start))
-            last_t[e] = t
-        for e in range(N):
-            if last_t[e] < 0:
-                run_ret[e] += csum[-1, e]
-                run_len[e] += T
-            else:
-                run_ret[e] = csum[-1, e] - csum[last_t[e], e]
-                run_len[e] = T - 1 - last_t[e]
-        return rets, lens
+    # ---- producers -------------------------------------------------------------------------------------------
+    def _append(self, bufs, rets, lens):
+        rew_buf, len_buf, to_buf = bufs
+        for r, l in zip(rets[-KEEP:], lens[-KEEP:]):
+            to_buf.append(1 if l == self.max_steps else 0)
+            len_buf.append(int(l))
+            rew_buf.append(r)
 
-    def feed(self, rew_batch, done_batch, true_mean_reward=np.nan, rew_batch_v=None, done_batch_v=None,
-             true_mean_reward_v=np.nan):
-        T, N = rew_batch.shape
-        rets, lens = self._episodes(np.asarray(rew_batch, dtype=np.float64), np.asarray(done_batch),
-                                    self.episode_rewards, self.episode_lens)
-        for r, l in zip(rets, lens):
-            self.episode_reward_buffer.append(r)
-            self.episode_len_buffer.append(l)
-            self.episode_timeout_buffer.append(1 if l >= self.max_steps else 0)
-        self.num_episodes += len(rets)
-        if rew_batch_v is not None:
-            rets, lens = self._episodes(np.asarray(rew_batch_v, dtype=np.float64), np.asarray(done_batch_v),
-                                        self.episode_rewards_v, self.episode_lens_v)
-            for r, l in zip(rets, lens):
-                self.episode_reward_buffer_v.append(r)
-                self.episode_len_buffer_v.append(l)
-                self.episode_timeout_buffer_v.append(1 if l >= self.max_steps else 0)
+    def feed(self, rew_batch, done_batch, true_mean_reward=None, rew_batch_v=None, done_batch_v=None,
+             true_mean_reward_v=None, *unused_greedy):
         self.true_mean_reward, self.true_mean_reward_v = true_mean_reward, true_mean_reward_v
-        self.timesteps += T * N
+        steps = rew_batch.shape[0]
+        rets, lens = close_episodes(rew_batch, done_batch, self.episode_rewards, self.episode_lens)
+        self._append((self.episode_reward_buffer, self.episode_len_buffer, self.episode_timeout_buffer), rets, lens)
+        self.num_episodes += len(rets)
+        if rew_batch_v is not None and done_batch_v is not None:
+            rets, lens = close_episodes(rew_batch_v, done_batch_v, self.episode_rewards_v, self.episode_lens_v)
+            self._append((self.episode_reward_buffer_v, self.episode_len_buffer_v, self.episode_timeout_buffer_v),
+                         rets, lens)
+        self.timesteps += self.n_envs * steps
 
+    def feed_episodes(self, steps, record, true_mean_reward=None, record_v=None, true_mean_reward_v=None):
+        """Device path: ``record`` = the float64 array ``tpp_episode_scan`` wrote (count, kept, (return, length) x kept);
+        the open-episode state of every env stays on the device."""
+        self.true_mean_reward, self.true_mean_reward_v = true_mean_reward, true_mean_reward_v
+        for rec, bufs, train in ((record, (self.episode_reward_buffer, self.episode_len_buffer,
+                                           self.episode_timeout_buffer), True),
+                                 (record_v, (self.episode_reward_buffer_v, self.episode_len_buffer_v,
+                                             self.episode_timeout_buffer_v), False)):
+            if rec is None:
+                continue
+            total, kept = int(rec[0]), int(rec[1])
+            pairs = np.asarray(rec[2:2 + 2 * kept]).reshape(kept, 2)
+            self._append(bufs, pairs[:, 0], pairs[:, 1].astype(np.int64))
+            if train:
+                self.num_episodes += total
+        self.timesteps += self.n_envs * steps
+
+    # ---- statistics + CSV --------------------------------------------------------------------------------------
     @staticmethod
-    def _stats(rew_buf, len_buf, to_buf):
-        if len(rew_buf) == 0:
-            return [np.nan] * 7
-        return [np.max(rew_buf), np.mean(rew_buf), np.min(rew_buf), np.max(len_buf), np.mean(len_buf), np.min(len_buf),
-                np.mean(to_buf)]
+    def _episode_statistics(rew_buf, len_buf, to_buf, balanced):
+        with warnings.catch_warnings():          # empty buffers give nan exactly like the reference's np.mean / np.median
+            warnings.simplefilter("ignore")
+            rew, ln = np.array(rew_buf, dtype=np.float64), np.array(len_buf)
+            return [np.max(rew, initial=0), np.mean(rew), np.median(rew), np.min(rew, initial=0),
+                    np.max(ln, initial=0), np.mean(ln), np.min(ln, initial=0), np.mean(np.array(to_buf)),
+                    np.mean(ln[rew > 0]), balanced]
 
-    def dump(self, summary=None, lr=None):
+    def _get_episode_statistics(self):
+        tr = self._episode_statistics(self.episode_reward_buffer, self.episode_len_buffer, self.episode_timeout_buffer,
+                                      self.true_mean_reward)
+        va = self._episode_statistics(self.episode_reward_buffer_v, self.episode_len_buffer_v,
+                                      self.episode_timeout_buffer_v, self.true_mean_reward_v)
+        return tr + va
+
+    def dump(self, summary=None, lr=0.):
         summary = summary or {}
-        row = ([self.timesteps, time.time() - self.start_time, self.num_episodes]
-               + self._stats(self.episode_reward_buffer, self.episode_len_buffer, self.episode_timeout_buffer)
-               + self._stats(self.episode_reward_buffer_v, self.episode_len_buffer_v, self.episode_timeout_buffer_v)
-               + [self.true_mean_reward, self.true_mean_reward_v, lr] + [summary.get(k, np.nan) for k in LOSS_KEYS])
-        self.rows.append(row)
+        wall_time = time.time() - self.start_time
+        stats = self._get_episode_statistics()
+        ema_reward = stats[1]
+        if len(self.log) > 0:                                           # common/logger.py:154-157
+            smoothing = .99 / (1 + len(self.log))
+            prev_ema = self.log[-1][len(TIME_METRICS) + 2 * len(EPISODE_METRICS)]
+            ema_reward = ema_reward * smoothing + prev_ema * (1 - smoothing)
+        row = [self.timesteps, wall_time, self.num_episodes] + stats + [ema_reward] + list(summary.values()) + [lr]
+        self.log.append(row)
         if self.logdir:
             with open(os.path.join(self.logdir, "log-append.csv"), "a", newline="") as f:
-                csv.writer(f).writerow(row)
+                writer = csv.writer(f)
+                if f.tell() == 0:
+                    writer.writerow(self.columns)
+                writer.writerow(row)
         return dict(zip(self.columns, row))

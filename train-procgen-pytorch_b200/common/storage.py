@@ -323,6 +323,33 @@ class Storage:
                     float("nan"))
         return finish
 
+    def snapshot_episodes(self, keep=40):
+        """Device-side episode accounting (replaces fetch_log_data + the loop of Logger.feed,
+        common/storage.py:130-162, common/logger.py:119-147): ``tpp_episode_scan`` closes the episodes of this rollout on
+        the device -- open-episode returns / lengths persist in HBM between rollouts -- and only the episode count and
+        the last ``keep`` (return, length) records in env-major order start their way to a pinned host buffer.  Returns a
+        closure that waits for the copy and yields that float64 record (``Logger.feed_episodes``)."""
+        rew = self.env_rew if self.env_rew is not None else self.rew
+        N, dev = self.num_envs, self.device
+        if getattr(self, "_ep_state", None) is None or self._ep_state[3].numel() != 2 + 2 * keep:
+            self._ep_state = (torch.zeros(N, dtype=torch.float64, device=dev),
+                              torch.zeros(N, dtype=torch.int32, device=dev),
+                              torch.zeros(N + 1, dtype=torch.int32, device=dev),
+                              torch.zeros(2 + 2 * keep, dtype=torch.float64, device=dev))
+            self._ep_host = torch.zeros(2 + 2 * keep, dtype=torch.float64).pin_memory()
+        run_ret, run_len, scratch, out = self._ep_state
+        _lib.call("tpp_episode_scan", _lib.ptr(rew), _lib.ptr(self.done_u8), self.num_steps, N, self.ld,
+                  _lib.ptr(run_ret), _lib.ptr(run_len), _lib.ptr(scratch), _lib.ptr(out), keep, _lib.stream_ptr())
+        self.n_launches += 3
+        self._ep_host.copy_(out, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+
+        def finish():
+            ev.synchronize()
+            return self._ep_host.numpy().copy()
+        return finish
+
     def fetch_log_data(self):
         """(rew_batch [T,N], done_batch [T,N], true_average_reward) as numpy, raw env rewards when available
         (common/storage.py:130-162; per-level tracking needs Procgen's prev_level_seed and stays NaN here)."""

@@ -242,6 +242,62 @@ __global__ void __launch_bounds__(256) bias_act_split_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// IMPALA feature sparsity (common/model.py:203-208): fs = mean_j max_b tanh(|100 h_bj|) over the flattened, ReLU'd
+// block-3 features h [M][E] (h >= 0, so |.| is the identity and fp32 bit patterns order like the values).
+// Forward: per column the 64-bit key (bits(h) << 32 | ~row) is max-reduced with atomicMax: the largest value and, on
+// ties, the smallest row -- torch.max(dim=0)'s choice.  Backward: d(coef*fs)/dh[b*, j] = coef/E * 100 * (1 - tanh^2)
+// for the argmax row of every column with h > 0 (ReLU and abs both have zero derivative at 0), added to the
+// gradient of the features and re-split into its TF32 pair.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fs_colmax_kernel(const float* __restrict__ hi, const float* __restrict__ lo,
+                                                        int M, int E, int rows_per_cta,
+                                                        unsigned long long* __restrict__ key) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= E) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  unsigned long long best = 0ull;
+  for (int r = r0; r < r1; ++r) {
+    const int64_t o = (int64_t)r * E + j;
+    const float v = hi[o] + (lo ? lo[o] : 0.0f);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(fmaxf(v, 0.0f)) << 32) |
+                                 (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+    best = k > best ? k : best;
+  }
+  atomicMax(key + j, best);
+}
+
+__global__ void __launch_bounds__(1024) fs_value_kernel(const unsigned long long* __restrict__ key, int E,
+                                                        float* __restrict__ fs_out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int j = threadIdx.x; j < E; j += blockDim.x)
+    s += (double)tanhf(100.0f * __uint_as_float((unsigned)(key[j] >> 32)));
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) fs_out[0] = (float)(s / (double)E);
+}
+
+__global__ void __launch_bounds__(256) fs_grad_kernel(const unsigned long long* __restrict__ key, int E, float coef,
+                                                      float* __restrict__ dx, float* __restrict__ dx_hi,
+                                                      float* __restrict__ dx_lo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= E) return;
+  const unsigned long long k = key[j];
+  const float h = __uint_as_float((unsigned)(k >> 32));
+  if (!(h > 0.0f)) return;
+  const unsigned row = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+  const float th = tanhf(100.0f * h);
+  const float g = coef / (float)E * 100.0f * (1.0f - th * th);
+  const int64_t o = (int64_t)row * E + j;
+  const float v = dx[o] + g;
+  dx[o] = v;
+  if (dx_hi) {
+    const float vh = cv_tf32(v);
+    dx_hi[o] = vh;
+    dx_lo[o] = v - vh;
+  }
+}
+
 }  // namespace tpp
 
 extern "C" int tpp_bias_act_split(const float* x, int64_t ld_in, int32_t M, int32_t N, const float* bias, int32_t relu,
@@ -310,5 +366,26 @@ extern "C" int tpp_colsum_narrow(const float* x, int64_t M, int32_t C, float* ou
   long long blocks = (total4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   tpp::colsum_narrow_kernel<<<(int)blocks, 256, 0, tpp_stream(stream)>>>(x, total4, C, out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_feature_sparsity(const float* h_hi, const float* h_lo, int32_t M, int32_t E, uint64_t* scratch,
+                                    float* fs_out, void* stream) {
+  TPP_CHECK_ARG(h_hi && scratch && fs_out && M > 0 && E > 0);
+  cudaStream_t s = tpp_stream(stream);
+  cudaMemsetAsync(scratch, 0, sizeof(uint64_t) * (size_t)E, s);
+  const int rows_per_cta = 64;
+  dim3 grid(tpp_ceil_div(E, 256), tpp_ceil_div(M, rows_per_cta));
+  tpp::fs_colmax_kernel<<<grid, 256, 0, s>>>(h_hi, h_lo, M, E, rows_per_cta,
+                                             reinterpret_cast<unsigned long long*>(scratch));
+  tpp::fs_value_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const unsigned long long*>(scratch), E, fs_out);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_feature_sparsity_grad(const uint64_t* scratch, int32_t E, float coef, float* dx, float* dx_hi,
+                                         float* dx_lo, void* stream) {
+  TPP_CHECK_ARG(scratch && dx && E > 0 && (!dx_hi == !dx_lo));
+  tpp::fs_grad_kernel<<<tpp_ceil_div(E, 256), 256, 0, tpp_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(scratch), E, coef, dx, dx_hi, dx_lo);
   TPP_LAUNCH_STATUS();
 }

@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(tpp_loss_cfg c, const flo
   // terms are means over mb samples, its sums go to stats + g*stats_stride).  With groups > 1, mb % 256 == 0, so a
   // block never straddles two groups.
   __shared__ double red[32];
+  if (c.coef_dev) {      // run-time coefficients (one captured graph serves every value)
+    c.eps_clip = c.coef_dev[0]; c.value_coef = c.coef_dev[1]; c.entropy_coef = c.coef_dev[2];
+    c.entropy_multiplier = c.coef_dev[3]; c.x_entropy_coef = c.coef_dev[4];
+  }
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int A = c.n_actions;
   const float invB = 1.0f / (float)c.mb;
