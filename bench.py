@@ -7,19 +7,21 @@ One "step" = one full PPO iteration: T fused rollout steps over the rank's envs 
 sampling -> env step kernel writing into the rollout), bootstrap value, GAE + advantage normalisation, and
 `epoch` x minibatch updates (device gather -> policy fwd -> fused loss fwd+bwd -> policy bwd -> clip+Adam).
 
-Default workload = BASELINE.json configs[1]: boxworld_env_vec PPO, n_envs=4096 per GPU (weak scaling), grid 12,
-goal 5, 3x3 distractors, 500-level bank, T=256, 3 epochs, n_minibatch 8, mini_batch_size 8192 (the reference's
-`boxworld-impala` YAML set, hyperparams/procgen/config.yml:575-601), with an MLP policy on the flattened
-3x14x14 frame (the reference has no working Box-World policy; choice documented in DESIGN.md).
+Hyperparameters come UNCHANGED from the reference's YAML sets (hyperparams/procgen/config.yml, read through
+tpp_b200.helper_local.get_hyperparams from $TPP_CONFIG_YML or the extracted copy tests/golden/config_subset.yml);
+only what BASELINE.json's configs name differently is overridden (n_envs).
 
-`--workload procgen` = BASELINE configs[3] shape (coinrun hard-500: IMPALA-CNN, 64 envs per GPU, 64x64x3 uint8
-frames) with a synthetic host engine (the Procgen engine is not in this image): `value` = policy rollout on frames
-resident in HBM + GAE + update, `e2e` = `PPO.train()` with every step's frames staged from pinned host memory and the
-actions read back.
+Default workload = BASELINE.json configs[1] (C2): boxworld_env_vec PPO, n_envs=4096 IN TOTAL, env-sharded over the N
+GPUs (`scaling: strong`; the same run also reports weak scaling, 4096 envs per GPU, under `weak_scaling`), YAML set
+`boxworld-impala` (config.yml:575-601: T=256, 3 epochs, n_minibatch 8, mini_batch_size 8192, grid 12, goal 5, 3x3
+distractors), 500-level bank, with an MLP policy on the flattened 3x14x14 frame (the reference has no working
+Box-World policy; choice documented in DESIGN.md).  At N=1 the JSON line also carries a `configs` block:
+C1 (`cartpole` set, 256 envs x 256 steps: device-timed, end-to-end and the CPU arm at the SAME 256 x 256), the C3
+env-step sweep (`kernel_rooflines`) and C4 (`hard-500` set, IMPALA-CNN, 64 envs, synthetic host engine).
 
-Prints ONE JSON line (rank 0).  `value` = device-timed iterations with inputs resident (minibatch permutations
-pre-uploaded); `e2e` = the same iterations through the public API `PPO.train()` with per-epoch index upload from
-pinned host memory and device->host reads of the loss summary and the logger's reward/done batches.
+`value` = device-timed iterations with inputs resident (minibatch permutations pre-uploaded); `e2e` = the same
+iterations through the public API `PPO.train()` with this package's `Logger`: per-epoch index upload from pinned host
+memory, device->host reads of the loss summary and of the logger's episode records.
 """
 from __future__ import annotations
 
@@ -37,22 +39,36 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # reference YAML set `boxworld-impala` (config.yml:575-601) at BASELINE configs[1]'s n_envs
-    "boxworld": dict(n_envs=4096, n_steps=256, epoch=3, n_minibatch=8, mini_batch_size=8192, gamma=0.999, lmbda=0.95,
-                     learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.01,
-                     grid_size=12, goal_length=5, num_distractor=3, distractor_length=3, max_steps=1000,
-                     normalize_rew=True, depth=4, mid_weight=256, latent_size=64),
-    # reference YAML set `cartpole` (config.yml:972-995): BASELINE configs[0], the reference's CPU-runnable case
-    "cartpole": dict(n_envs=256, n_steps=256, epoch=3, n_minibatch=16, mini_batch_size=8192, gamma=0.99, lmbda=0.95,
-                     learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.02,
-                     depth=4, mid_weight=256, latent_size=64),
-    # reference YAML set `hard-500` (config.yml:81-99) as launched for coinrun / maze / heist: BASELINE configs[3]
-    "procgen": dict(n_envs=64, n_steps=256, epoch=3, n_minibatch=8, mini_batch_size=8192, gamma=0.999, lmbda=0.95,
-                    learning_rate=5e-4, grad_clip_norm=0.5, eps_clip=0.2, value_coef=0.5, entropy_coef=0.01),
-}
+CONFIG_YML = os.environ.get("TPP_CONFIG_YML") or os.path.join(ROOT, "tests", "golden", "config_subset.yml")
 PPO_KEYS = ("n_steps", "n_envs", "epoch", "n_minibatch", "mini_batch_size", "gamma", "lmbda", "learning_rate",
             "grad_clip_norm", "eps_clip", "value_coef", "entropy_coef")
+METRIC = "PPO env-steps/sec (rollout+GAE+update)"
+
+
+def workload_hp(name):
+    """YAML set of the workload + the overrides BASELINE.json's configs ask for."""
+    import yaml
+    with open(CONFIG_YML) as f:
+        sets = yaml.safe_load(f)
+    if name == "boxworld":          # configs[1]: n_envs=4096; MLP policy on the flattened frame (SURVEY 0.13)
+        return dict(sets["boxworld-impala"], n_envs=4096, max_steps=1000, depth=4, mid_weight=256, latent_size=64)
+    if name == "cartpole":          # configs[0]: the set as it is
+        return dict(sets["cartpole"])
+    if name == "procgen":           # configs[3]: hard-500 with 64 envs per GPU (n_minibatch: PPO's default, 8)
+        return dict(sets["hard-500"], n_envs=64, n_minibatch=8)
+    raise KeyError(name)
+
+
+# bounded CPU samples of the same workloads: (n_envs, n_steps) of one CPU "step"; everything else is the GPU arm's
+CPU_SAMPLE = {"boxworld": (4096, 16), "cartpole": (256, 256), "procgen": (64, 32)}
+
+
+def workload_string(name, hp):
+    mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
+    pol = {"boxworld": "MLP policy 588-256-256-256-64 on the flattened 3x14x14 frame",
+           "cartpole": "MLP policy 9-256-256-256-64", "procgen": "IMPALA-CNN policy, synthetic 64x64x3 uint8 frames"}[name]
+    return (f"{name} PPO: n_envs={hp['n_envs']}, n_steps={hp['n_steps']}, epoch={hp['epoch']}, "
+            f"n_minibatch={hp['n_minibatch']}, mini_batch_size={mb}, {pol}")
 
 
 def peaks():
@@ -101,7 +117,7 @@ class ClockSampler:
 # Our arm
 # --------------------------------------------------------------------------------------------------
 
-def build_agent(name, hp, rank, device):
+def build_agent(name, hp, rank, device, **extra):
     from tpp_b200.agents.ppo import PPO
     from tpp_b200.common.model import MLPModel
     from tpp_b200.common.policy import CategoricalPolicy
@@ -113,22 +129,19 @@ def build_agent(name, hp, rank, device):
         class A:
             seed, num_levels = 6033 + 1000 * rank, 500
         env = create_bw_env(A, dict(hp, device=device))
-        obs_shape = env.observation_space.shape
     else:
         from tpp_b200.discrete_env.cartpole_pre_vec import create_cartpole
 
         class A:
             seed = 6033 + rank
         env = create_cartpole(A, dict(hp, device=device))
-        obs_shape = env.observation_space.shape
+    obs_shape = env.observation_space.shape
     in_dim = int(np.prod(obs_shape))
     torch.manual_seed(6033)                      # identical initial weights on every rank
     pol = CategoricalPolicy(MLPModel(in_dim, hp["depth"], hp["mid_weight"], hp["latent_size"]), False,
                             env.action_space.n).to(device).flatten_()
     st = Storage(obs_shape, hp["latent_size"], T, N, device)
-    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank,
-                matmul=hp.get("matmul", "tf32x3"), fuse_accum=hp.get("fuse_accum", "auto"),
-                rollout_chains=hp.get("rollout_chains", 1))
+    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17, **extra)
     return agent, in_dim
 
 
@@ -185,10 +198,11 @@ def kernel_rooflines(pk, device, sweep=True):
                 state["cur"] = c ^ 1
             dt = time_kernel(step, iters=50)
             gbs = bytes_per_step * N / dt / 1e9
+            ws = 2 * env.n_obs * 4 * N / 1e6
             out.append(dict(kernel=f"env_step_{env.family}", n_envs=N, bytes_per_unit=bytes_per_step, bound="hbm",
                             achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                            env_steps_per_s=round(N / dt, 1), us=round(dt * 1e6, 2),
-                            working_set_mb=round(2 * env.n_obs * 4 * N / 1e6, 1)))
+                            env_steps_per_s=round(N / dt, 1), us=round(dt * 1e6, 2), working_set_mb=round(ws, 1),
+                            l2_resident=bool(ws < 126)))
             del env
     # Box-World step (+ in-order level replacement + frame emit into the rollout slot), uint8 rollout contract:
     # read frame 588 + write frame 588 + ~57 B of cells / meta / reward / done per env-step
@@ -222,81 +236,109 @@ def kernel_rooflines(pk, device, sweep=True):
 
 
 def gemm_roofline(agent, in_dim, hp, pk):
-    """Roofline of the dominant kernel of the PPO iteration: the policy's dense-layer GEMM.  Timed live with CUDA
-    events on the launching stream: the largest layer of the update (layer 1 forward, M = minibatch, N = 256,
-    K = in_dim) launched alone, algorithmic FLOPs = 2*M*N*K per launch (the 3xTF32 split passes are overhead, not
-    algorithmic work), against the measured dense bf16 tensor peak.  Also reports the whole policy forward+backward
-    (all its launches) in TFLOP/s."""
+    """Roofline of the DOMINANT kernel of the PPO iteration (largest share of the timed region, profiles/breakdown):
+    the update phase's tensor-core GEMM at the accumulation-window size.  One gather-sized forward + backward pass of
+    the policy is run with every `tpp_gemm_tc` launch bracketed by CUDA events on the launching stream (the kernels
+    are 50-250 us, the host stays ahead); `achieved` = sum of algorithmic FLOPs (2*M*N*K per launch; the 3xTF32 split
+    passes are overhead, not work) / sum of durations over ALL launches of that kernel = its time-weighted average,
+    against the measured dense bf16 peak.  `traffic` / `hbm_frac`: dram bytes per launch (average) from the committed
+    `ncu --set full` capture of the same launches (profiles/ncu_traffic.json) over the live average duration."""
     from tpp_b200.common.engine import MLPEngineTC
-    from tpp_b200._lib import EPI_BIAS, EPI_RELU, TC_A_EXACT, ptr
     mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
-    mb *= getattr(agent, "group_size", 1)     # rows of one launch: the minibatches of an accumulation window share a pass
+    rows = mb * getattr(agent, "group_size", 1)   # rows of one launch: the minibatches of an accumulation window share a pass
     eng = agent.engine
-    ld = (in_dim + 3) // 4 * 4
+    dev = agent.policy.flat.device
     raw = bool(getattr(eng, "raw_pixels", False))     # image observations reach layer 1 as integer pixel values
     if raw:
-        x = torch.randint(0, 256, (mb, eng.ld_in), device=agent.policy.flat.device).float()
+        x = torch.randint(0, 256, (rows, eng.ld_in), device=dev).float()
     else:
-        x = torch.randn(mb, ld, device=agent.policy.flat.device)[:, :in_dim]
-    dhead = torch.randn(mb, eng.ld_head, device=x.device) / mb
+        x = torch.randn(rows, (in_dim + 3) // 4 * 4, device=dev)[:, :in_dim]
+    dhead = torch.randn(rows, eng.ld_head, device=dev) / rows
 
     def fb():
         if raw:
-            eng.forward(x, mb, raw=True)
+            eng.forward(x, rows, raw=True)
         else:
-            eng.forward(x, mb)
-        eng.backward(dhead, mb)
+            eng.forward(x, rows)
+        eng.backward(dhead, rows)
     dt_all = time_kernel(fb, iters=10)
     agent.policy.flat_grad.zero_()
     macs = sum(l[2] * l[3] for l in eng.layers) + eng.latent * (eng.A + 1)
-    flops_all = 6.0 * macs * mb - 2.0 * eng.layers[0][2] * eng.layers[0][3] * mb    # no dgrad for the first layer
-    w_off, b_off, fin, fout, relu = eng.layers[0]
-    ws = eng._workspace(mb)
-    if isinstance(eng, MLPEngineTC):
-        w, h = (eng.w0_raw if raw else eng.w[0]), ws.h[0]
-        a = (x, x) if raw else (ws.x["hi"], ws.x["lo"])
-        bn = eng._bn(mb, fout)
-        one = lambda: eng._tc(a, eng.ld_in, (w["hi"], w["lo"]), w["ldk"], mb, fout, fin,
-                              flags=EPI_BIAS | EPI_RELU, bias=eng._p(b_off), out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
-                              exact=TC_A_EXACT if raw else 0, block_n=bn)
-        tile = {0: "gemm_tc_kernel<128>", 64: "gemm_tc_kernel<64>", 256: "gemm_tc_kernel<256>",
-                512: "gemm_tc_kernel<256, pair> (256x256 tile on a CTA pair, cta_group::2)",
-                513: "gemm_tc_kernel<256, pair, persistent> (256x256 tiles on persistent CTA pairs, cta_group::2)"}[bn]
-        name = "%s (tcgen05 kind::tf32, %s%s)" % (
-            tile, "3xTF32" if eng.precision == 3 else "1xTF32",
-            ", pixel operand exact in TF32: 2 of the 3 passes" if raw and eng.precision == 3 else "")
-    else:
-        one = lambda: eng._gemm(ptr(x), x.stride(0), 1, eng._p(w_off), fin, 1, ptr(ws.acts[0]), fout, eng._p(b_off),
-                                None, mb, fout, fin, EPI_BIAS | EPI_RELU)
-        name = "gemm_f32_kernel (CUDA cores, exact fp32)"
-    dt = time_kernel(one, iters=50)
-    tf = 2.0 * mb * fout * fin / dt / 1e12
-    traffic = None
+    flops_all = 6.0 * macs * rows - 2.0 * eng.layers[0][2] * eng.layers[0][3] * rows    # no dgrad for the first layer
+    out = dict(bound="tensor", peak=pk["bf16"], unit="TFLOP/s", rows_per_launch=rows,
+               policy_fwd_bwd_tflops=round(flops_all / dt_all / 1e12, 2), policy_fwd_bwd_us=round(dt_all * 1e6, 1),
+               note="peak = dense bf16 cuBLAS (" + pk["source"] + "); a TF32 kernel tops out at 1/2 of it, the "
+                    "fp32-parity 3xTF32 mode at 1/6; frac is the time-weighted average over every launch of the kernel in "
+                    "one window pass, not the best launch")
+    if not isinstance(eng, MLPEngineTC):
+        out.update(kernel="gemm_f32_kernel (CUDA cores, exact fp32)", achieved=out["policy_fwd_bwd_tflops"],
+                   frac=round(out["policy_fwd_bwd_tflops"] / pk["bf16"], 4), traffic=None)
+        return out
+    # per-launch events around every tensor-core GEMM of one pass
+    records, inner = [], eng._tc
+
+    def timed_tc(a, lda, b, ldb, M, N, K, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        inner(a, lda, b, ldb, M, N, K, **kw)
+        e1.record()
+        records.append((kw.get("block_n", 0), M, N, K, e0, e1))
+    eng._tc = timed_tc
+    try:
+        for _ in range(4):
+            fb()
+        torch.cuda.synchronize()
+        records.clear()
+        reps = 5
+        for _ in range(reps):
+            fb()
+        torch.cuda.synchronize()
+    finally:
+        del eng._tc
+    agent.policy.flat_grad.zero_()
+    by_tile = {}
+    for bn, M, N, K, e0, e1 in records:
+        d = by_tile.setdefault(bn, dict(ms=0.0, flops=0.0, n=0, shapes=set()))
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += 2.0 * M * N * K
+        d["n"] += 1
+        d["shapes"].add((M, N, K))
+    bn_dom = max(by_tile, key=lambda k: by_tile[k]["ms"])           # the tile variant with the largest time share
+    d = by_tile[bn_dom]
+    tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    tile = {0: "gemm_tc_kernel<128>", 64: "gemm_tc_kernel<64>", 128: "gemm_tc_kernel<128>", 256: "gemm_tc_kernel<256>",
+            512: "gemm_tc_kernel<256, pair> (256x256 tile on a CTA pair, cta_group::2)",
+            513: "gemm_tc_kernel<256, pair, persistent> (256x256 tiles on persistent CTA pairs, cta_group::2)",
+            65: "gemm_tc_kernel<64, pair, persistent>"}.get(bn_dom, f"gemm_tc_kernel<{bn_dom}>")
+    us_avg = d["ms"] * 1e3 / d["n"]
+    traffic = hbm_frac = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-        traffic = json.load(open(tpath)).get(f"gemm_tc_kernel[{mb},{fout},{fin}]")
-    return dict(kernel=name, shape=[mb, fout, fin], bound="tensor", achieved=round(tf, 2), peak=pk["bf16"],
-                unit="TFLOP/s", frac=round(tf / pk["bf16"], 4), traffic=traffic, us_per_launch=round(dt * 1e6, 2),
-                policy_fwd_bwd_tflops=round(flops_all / dt_all / 1e12, 2),
-                policy_fwd_bwd_us=round(dt_all * 1e6, 1),
-                note="peak = dense bf16 cuBLAS (" + pk["source"] + "); a TF32 kernel tops out at 1/2 of it, the "
-                     "fp32-parity 3xTF32 mode at 1/6")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        per = [tj.get(f"gemm_tc_kernel[{M},{N},{K}]") for (M, N, K) in d["shapes"]]
+        key = tj.get(f"window_pass[{rows}]")           # average dram bytes per launch of the dominant kernel in a pass
+        if key is not None:
+            traffic = key
+        elif per and all(p is not None for p in per):
+            traffic = float(np.mean(per))
+        if traffic is not None:
+            hbm_frac = round(traffic / (us_avg * 1e-6) / 1e9 / pk["hbm"], 4)
+    share = d["ms"] / sum(v["ms"] for v in by_tile.values())
+    out.update(kernel="%s (tcgen05 kind::tf32, %s)" % (tile, "3xTF32" if eng.precision == 3 else "1xTF32"),
+               launches_per_pass=d["n"] // reps, shapes=sorted(d["shapes"]), achieved=round(tf, 2),
+               frac=round(tf / pk["bf16"], 4), frac_of_sustained=round(tf / pk["bf16_sustained"], 4)
+               if pk.get("bf16_sustained") else None, us_per_launch=round(us_avg, 2), traffic=traffic,
+               hbm_frac=hbm_frac, share_of_gemm_time_in_pass=round(share, 3))
+    return out
 
 
-def run_ours(args):
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local)
+def measure(name, hp, rank, local, world, args, logger=True, extra=None):
+    """Device-timed (`ms`) and end-to-end (`ms_e2e`) PPO iterations of one workload on this rank's shard."""
+    from tpp_b200.common.logger import Logger
     device = f"cuda:{local}"
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
-    hp = dict(WORKLOADS[args.workload], matmul=args.matmul,
-              fuse_accum=args.fuse_accum if args.fuse_accum == "auto" else int(args.fuse_accum),
-              rollout_chains=args.rollout_chains)
-    agent, in_dim = build_agent(args.workload, hp, rank, device)
+    agent, in_dim = build_agent(name, hp, rank, device, matmul=args.matmul,
+                                fuse_accum=args.fuse_accum if args.fuse_accum == "auto" else int(args.fuse_accum),
+                                rollout_chains=args.rollout_chains, **(extra or {}))
     if world > 1:
         agent.shard(world)
     N, T = hp["n_envs"], hp["n_steps"]
@@ -319,9 +361,7 @@ def run_ours(args):
     # ---- device-resident timing: minibatch permutations pre-generated and pre-uploaded -------------------
     env.reset_rollout(st)
     mb = min(hp["mini_batch_size"], T * N // hp["n_minibatch"])
-    n_perm = hp["epoch"] * (args.warmup + args.steps + 2)
     pre = [torch.randperm(T * N)[:(T * N) // mb * mb].view(-1, mb).to(device) for _ in range(hp["epoch"])]
-    real_epoch_indices = st.epoch_indices
     cyc = {"i": 0}
 
     def resident_indices(_mb):
@@ -346,24 +386,22 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = counters() - l0
     clk = clocks.stop() if rank == 0 else None
-
+    res = dict(agent=agent, in_dim=in_dim, ms=ms, launches=launches, clocks=clk, mb=mb)
     if args.timed_region_only:
-        if rank == 0:
-            print(json.dumps({"ms_per_step": ms / args.steps, "gpu_launches": int(launches)}))
-        return
+        return res
+    # phase split (CUDA events, outside the timed region): the rollout alone
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(3):
+        agent.collect_rollout(env, st)
+    r1.record()
+    torch.cuda.synchronize()
+    res["rollout_ms"] = r0.elapsed_time(r1) / 3
     # ---- end to end through the public API: PPO.train() with host-side index generation + upload + readbacks -
-    st.epoch_indices = real_epoch_indices
-
-    class NullLogger:      # the reference's Logger consumes (rew_batch, done_batch) on the host every iteration
-        logdir = None
-        episode_reward_buffer = [0.0]
-
-        def feed(self, *a):
-            self.n = sum(x.size for x in a[:2])
-
-        def dump(self, *a):
-            pass
-    agent.logger = NullLogger()
+    del st.__dict__["epoch_indices"]
+    if logger:
+        agent.logger = Logger(N)                  # this package's Logger: device-side episode accounting
+        agent.logger.max_steps = hp.get("max_steps", 500)
     agent.t = 0
     agent.train(T * N * 2)                              # warm the API path (graph already captured)
     barrier()
@@ -386,58 +424,138 @@ def run_ours(args):
         torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
         torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
         in_sync = bool((lo == hi).item())
-    ms, ms_e2e = times.tolist()
+    res["ms"], res["ms_e2e"] = times.tolist()
+    n_mb = (T * N) // mb
+    res.update(in_sync=in_sync, h2d=hp["epoch"] * n_mb * mb * 4 + 8 + 32,       # int32 indices + lr + loss coefficients
+               d2h=hp["epoch"] * n_mb * 20 * 8 + (2 + 80) * 8,                 # loss statistics + episode records
+               episodes=getattr(agent.logger, "num_episodes", None))
+    return res
 
+
+def run_ours(args):
+    from tpp_b200 import parallel
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(device))
+    name = args.workload
+    hp_total = workload_hp(name)
+    strong = name == "boxworld"        # configs[1] names a TOTAL env count: shard it; cartpole stays per-GPU (weak)
+    hp = parallel.shard_hyperparameters(hp_total, world) if (strong and world > 1) else hp_total
+    res = measure(name, hp, rank, local, world, args)
+    if args.timed_region_only:
+        if rank == 0:
+            print(json.dumps({"ms_per_step": res["ms"] / args.steps, "gpu_launches": int(res["launches"])}))
+        return
+    weak = None
+    if strong and world > 1:           # the same run, 4096 envs PER GPU (round 1's headline), as an extra key
+        del res["agent"]
+        torch.cuda.empty_cache()
+        w = measure(name, hp_total, rank, local, world, args)
+        tot = hp_total["n_envs"] * hp_total["n_steps"] * args.steps * world
+        weak = {"scaling": "weak", "n_envs_per_gpu": hp_total["n_envs"], "value": round(tot / (w["ms"] * 1e-3), 1),
+                "ms_per_step": round(w["ms"] / args.steps, 3), "e2e_value": round(tot / (w["ms_e2e"] * 1e-3), 1),
+                "replicas_in_sync": w["in_sync"]}
+        res_agent = w["agent"]
+    else:
+        res_agent = res["agent"]
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
     pk = peaks()
+    N, T = hp["n_envs"], hp["n_steps"]
     total_steps = N * T * args.steps * world
-    value = total_steps / (ms * 1e-3)
-    e2e_value = total_steps / (ms_e2e * 1e-3)
-    n_mb = (T * N) // mb
-    h2d = hp["epoch"] * n_mb * mb * 8 + 8
-    d2h = hp["epoch"] * n_mb * 20 * 8 + T * st.ld * (4 + 1)      # loss statistics + (raw reward f32, done u8) batches
-    roof = gemm_roofline(agent, in_dim, hp, pk)
-    extra = kernel_rooflines(pk, device) if not args.no_kernel_rooflines else []
-    cpu = cpu_baseline(args.workload, budget_s=20.0) if not args.no_cpu_baseline else None
+    value = total_steps / (res["ms"] * 1e-3)
+    e2e_value = total_steps / (res["ms_e2e"] * 1e-3)
+    roof = gemm_roofline(res_agent, res["in_dim"], hp_total if weak else hp, pk)
+    extra = kernel_rooflines(pk, device) if (not args.no_kernel_rooflines and world == 1) else []
+    cpu = cpu_baseline(name, budget_s=20.0) if not args.no_cpu_baseline else None
+    configs = None
+    if world == 1 and name == "boxworld" and not args.no_configs:
+        configs = other_configs(args, rank, local, pk)
+    n_e, n_s = CPU_SAMPLE[name]
     line = {
-        "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(value, 1), "unit": "env-steps/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}_env_vec PPO: n_envs={N}/GPU, n_steps={T}, "
-                               f"epoch={hp['epoch']}, minibatch={mb} (x{getattr(agent, 'group_size', 1)} per pass: "
-                               f"gradient-accumulation window), MLP policy {in_dim}-256-256-256-64 ({args.matmul})",
-                   "parallelism": f"env-sharded dp{world}", "l2": "rollout + minibatch working set > L2 (inputs "
-                   "larger than 126 MB)" if args.workload == "boxworld" else "small working set (latency-bound)"},
-        "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
-                "api": "PPO.train(): host randperm -> pinned H2D per epoch (copy stream, overlapping the previous epoch); "
-                       "D2H loss statistics + logger batches into pinned buffers, read by the host after the next "
-                       "rollout is enqueued"},
-        "gpu_launches": int(launches), "clocks": clk, "replicas_in_sync": in_sync, "roofline": roof,
-        "kernel_rooflines": extra,
-        "cpu_baseline": cpu,
+        "metric": METRIC, "value": round(value, 1), "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(res["ms"] / args.steps, 3),
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_string(name, hp_total),
+                   "parallelism": f"env-sharded dp{world}: {N} envs and minibatch {res['mb']} per GPU "
+                                  f"(x{getattr(res_agent, 'group_size', 1)} minibatches per pass: gradient-accumulation "
+                                  f"window), {args.matmul}",
+                   "yaml_set": {"boxworld": "boxworld-impala", "cartpole": "cartpole"}[name],
+                   "l2": "rollout + minibatch working set > L2 (inputs larger than 126 MB)" if name == "boxworld"
+                   else "small working set (latency-bound)",
+                   "reference_arm": f"--impl reference times the CPU port on the same workload with n_steps={n_s} of "
+                                    f"{hp_total['n_steps']} per CPU step (n_envs={n_e}, minibatch and epochs unchanged; "
+                                    "every phase is linear in n_steps, so env-steps/s is the same quantity)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": res["h2d"],
+                "d2h_bytes_per_step": res["d2h"], "ms_per_step": round(res["ms_e2e"] / args.steps, 3),
+                "episodes_logged": res["episodes"],
+                "api": "PPO.train() with tpp_b200 Logger: host randperm -> pinned int32 H2D per epoch (copy stream, "
+                       "overlapping the previous epoch); D2H loss statistics + device-side episode records (last 40 "
+                       "episodes + count) into pinned buffers, read by the host after the next rollout is enqueued"},
+        "phases": {"rollout_ms": round(res["rollout_ms"], 3),
+                   "us_per_rollout_step": round(res["rollout_ms"] * 1e3 / T, 2),
+                   "gae_plus_update_ms": round(res["ms"] / args.steps - res["rollout_ms"], 3)},
+        "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "replicas_in_sync": res["in_sync"],
+        "roofline": roof, "weak_scaling": weak, "kernel_rooflines": extra, "cpu_baseline": cpu, "configs": configs,
     }
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+def other_configs(args, rank, local, pk):
+    """BASELINE configs[0] (C1) and configs[3] (C4) measured in the same run (N=1)."""
+    out = {}
+    a = argparse.Namespace(**vars(args))
+    a.steps, a.warmup = max(args.steps, 10), 3
+    hp = workload_hp("cartpole")
+    r = measure("cartpole", hp, rank, local, 1, a)
+    tot = hp["n_envs"] * hp["n_steps"] * a.steps
+    c1 = {"workload": workload_string("cartpole", hp), "yaml_set": "cartpole",
+          "value": round(tot / (r["ms"] * 1e-3), 1), "ms_per_step": round(r["ms"] / a.steps, 3),
+          "e2e": {"value": round(tot / (r["ms_e2e"] * 1e-3), 1), "ms_per_step": round(r["ms_e2e"] / a.steps, 3),
+                  "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+          "gpu_launches": int(r["launches"]), "unit": "env-steps/s", "steps": a.steps,
+          "rollout_ms": round(r["rollout_ms"], 3), "us_per_rollout_step": round(r["rollout_ms"] * 1e3 / hp["n_steps"], 2)}
+    del r
+    torch.cuda.empty_cache()
+    if not args.no_cpu_baseline:
+        c1["cpu_baseline"] = cpu_baseline("cartpole", budget_s=12.0)       # the SAME 256 x 256 on the host cores
+    out["C1_cartpole"] = c1
+    try:
+        p = argparse.Namespace(**vars(args))
+        p.steps, p.warmup = 2, 1
+        out["C4_procgen"] = run_procgen(p, emit=False)
+    except Exception as e:      # the headline line must survive a failure of an extra config
+        out["C4_procgen"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
 class SyntheticProcgen:
-    """Host-stepped VecEnv with Procgen's contract (uint8 64x64x3 frames, 15 actions): cycles a pool of pre-generated
-    frames, Bernoulli(0.01)*10 rewards, Bernoulli(1/200) dones at no CPU cost."""
+    """Host-stepped VecEnv with Procgen's contract after VecExtractDictObs (uint8 64x64x3 frames, 15 actions, float
+    rewards): cycles a pool of pre-generated frames, Bernoulli(0.01)*10 rewards, Bernoulli(1/200) dones at
+    no CPU cost.  Wrapped in tpp_b200's StagedVecEnv (device VecNormalize, frames staged as uint8)."""
 
     def __init__(self, n, pool=64, seed=0):
         from tpp_b200.discrete_env.pre_vec_env import Box, Discrete
         rng = np.random.default_rng(seed)
-        self.n = n
+        self.num_envs = n
         self.frames = rng.integers(0, 256, (pool, n, 64, 64, 3), dtype=np.uint8)
         self.rew = ((rng.random((pool, n)) < 0.01) * 10.0).astype(np.float32)
         self.done = rng.random((pool, n)) < (1 / 200)
         self.i = 0
-        self.observation_space = Box(np.zeros((3, 64, 64)), np.ones((3, 64, 64)))
+        self.observation_space = Box(np.zeros((64, 64, 3)), np.full((64, 64, 3), 255), dtype=np.uint8)
         self.action_space = Discrete(15)
 
     def reset(self):
@@ -451,7 +569,7 @@ class SyntheticProcgen:
         pass
 
 
-def run_procgen(args):
+def run_procgen(args, emit=True):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -459,21 +577,26 @@ def run_procgen(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
-    if world > 1:
+    if world > 1 and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl", device_id=torch.device(device))
     from tpp_b200 import _lib
     from tpp_b200.agents.ppo import PPO
+    from tpp_b200.common.env.procgen_wrappers import StagedVecEnv
+    from tpp_b200.common.logger import Logger
     from tpp_b200.common.model import ImpalaModel
     from tpp_b200.common.policy import CategoricalPolicy
     from tpp_b200.common.storage import Storage
-    hp = WORKLOADS["procgen"]
+    hp = workload_hp("procgen")
     N, T = hp["n_envs"], hp["n_steps"]
     matmul = args.matmul if args.matmul in ("tf32x3", "tf32") else "tf32x3"
-    env = SyntheticProcgen(N, seed=rank)
+    env = StagedVecEnv(SyntheticProcgen(N, seed=rank), normalize_rew=hp.get("normalize_rew", True), gamma=hp["gamma"],
+                       device=device)
     torch.manual_seed(6033)
     pol = CategoricalPolicy(ImpalaModel(3), False, 15).to(device).flatten_()
     st = Storage((3, 64, 64), 256, T, N, device)
-    agent = PPO(env, pol, None, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17 + rank, matmul=matmul)
+    lg = Logger(N)
+    lg.max_steps = 1000
+    agent = PPO(env, pol, lg, st, device, 0, **{k: hp[k] for k in PPO_KEYS}, sample_seed=17, matmul=matmul)
     if world > 1:
         agent.shard(world)
     A = agent.n_actions
@@ -497,7 +620,7 @@ def run_procgen(args):
         agent.optimize()
 
     agent.train(T * N * 2)             # eager iteration, then the iteration that captures the graphs
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 1)):
         resident_iteration()
     barrier()
     clocks = ClockSampler(local)
@@ -513,21 +636,22 @@ def run_procgen(args):
     ms = e0.elapsed_time(e1)
     launches = counters() - l0
     clk = clocks.stop() if rank == 0 else None
-    st.h2d_bytes = 0
+    st.h2d_bytes, st.d2h_bytes = 0, 0
     agent.t = 0
     w0 = time.perf_counter()
     agent.train(T * N * args.steps)
     barrier()
     ms_e2e = (time.perf_counter() - w0) * 1e3
     h2d = st.h2d_bytes // args.steps
+    d2h = st.d2h_bytes // args.steps + 24 * 20 * 8 + 82 * 8
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = times.tolist()
     if rank != 0:
-        if world > 1:
+        if world > 1 and emit:
             torch.distributed.destroy_process_group()
-        return
+        return None
     pk = peaks()
     sys.path.insert(0, os.path.join(ROOT, "profiles"))
     import run_conv_kernels as rck
@@ -548,22 +672,28 @@ def run_procgen(args):
             "note": f"peak = dense bf16 ({pk['source']}); algorithmic FLOPs 2*pixels*9*Cin*Cout; the tile is bound by "
                     "the L2->shared-memory gather of 9 taps x (hi, lo), see profiles/ncu_conv_r01.md"}
     total = N * T * args.steps * world
-    mb = min(hp["mini_batch_size"], T * N // hp["n_minibatch"])
-    cpu = cpu_baseline("procgen", budget_s=20.0) if not args.no_cpu_baseline else None
-    print(json.dumps({
-        "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(total / (ms * 1e-3), 1),
-        "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    cpu = cpu_baseline("procgen", budget_s=15.0) if not args.no_cpu_baseline else None
+    n_e, n_s = CPU_SAMPLE["procgen"]
+    line = {
+        "metric": METRIC, "value": round(total / (ms * 1e-3), 1),
+        "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"procgen-shaped PPO (coinrun hard-500): n_envs={N}/GPU, n_steps={T}, epoch=3, "
-                               f"minibatch={mb}, IMPALA-CNN policy ({matmul}), synthetic 64x64x3 uint8 frames",
-                   "parallelism": f"env-sharded dp{world}", "l2": "minibatch activations (GBs) >> L2"},
+        "config": {"workload": workload_string("procgen", hp), "yaml_set": "hard-500",
+                   "parallelism": f"env-sharded dp{world}: {N} envs per GPU, {matmul}",
+                   "l2": "minibatch activations (GBs) >> L2",
+                   "reference_arm": f"CPU port on the same workload with n_steps={n_s} of {T} per CPU step (n_envs={n_e})"},
         "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(T * N * 4 + 24 * 20 * 8), "ms_per_step": round(ms_e2e / args.steps, 3),
-                "api": "PPO.train() with a host-stepped env: per step pinned uint8 frames H2D, actions D2H"},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / args.steps, 3),
+                "api": "PPO.train() with a host-stepped env behind StagedVecEnv: per step double-buffered pinned uint8 "
+                       "frames H2D, actions D2H (event wait); rewards / dones one H2D per rollout; VecNormalize on the "
+                       "device; tpp_b200 Logger"},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    if emit:
+        print(json.dumps(line))
+        if world > 1:
+            torch.distributed.destroy_process_group()
+    return line
 
 
 # --------------------------------------------------------------------------------------------------
@@ -575,8 +705,11 @@ def _cpu_setup(name, n_envs, n_steps):
     from oracle import boxworld as obw
     from oracle import ppo as oppo
     from oracle.prevec import OraclePreVec
-    hp = dict(WORKLOADS[name], n_envs=n_envs, n_steps=n_steps)
+    hp = dict(workload_hp(name), n_envs=n_envs, n_steps=n_steps)
     torch.manual_seed(6033)
+    kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
+              grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
+              entropy_coef=hp["entropy_coef"])
     if name == "procgen":
         rng = np.random.default_rng(0)
         pool = rng.integers(0, 256, (8, n_envs, 64, 64, 3), dtype=np.uint8)
@@ -588,9 +721,6 @@ def _cpu_setup(name, n_envs, n_steps):
         tf = lambda f: np.ascontiguousarray(f.transpose(0, 3, 1, 2)).astype(np.float32) / 255.0
         pol = oppo.OraclePolicy(oppo.OracleImpala(3), 15)
         opt = oppo.make_adam(pol, hp["learning_rate"])
-        kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
-                  grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
-                  entropy_coef=hp["entropy_coef"])
 
         def iteration(obs):
             obs, _ = oppo.ppo_iteration(env_step, obs, pol, opt, n_steps, n_envs, hp["gamma"], hp["lmbda"],
@@ -616,9 +746,6 @@ def _cpu_setup(name, n_envs, n_steps):
         tf, obs0, in_dim, A = None, env.obs(), 9, 2
     pol = oppo.OraclePolicy(oppo.OracleMLP(in_dim, hp["depth"], hp["mid_weight"], hp["latent_size"]), A)
     opt = oppo.make_adam(pol, hp["learning_rate"])
-    kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
-              grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
-              entropy_coef=hp["entropy_coef"])
 
     def iteration(obs):
         obs, _ = oppo.ppo_iteration(env_step, obs, pol, opt, n_steps, n_envs, hp["gamma"], hp["lmbda"],
@@ -627,12 +754,19 @@ def _cpu_setup(name, n_envs, n_steps):
     return iteration, obs0
 
 
-CPU_SAMPLE = {"boxworld": (256, 64), "cartpole": (256, 256), "procgen": (16, 32)}   # bounded (n_envs, n_steps)
+def _host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host core it can use."""
+    n = os.cpu_count() or 1
+    if torch.get_num_threads() < n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
 def cpu_baseline(name, budget_s=20.0, steps=None):
     """Time the oracle port on the host cores on a bounded sample of the same workload."""
+    threads = _host_threads()
     n_envs, n_steps = CPU_SAMPLE[name]
+    full = workload_hp(name)
     iteration, obs = _cpu_setup(name, n_envs, n_steps)
     obs = iteration(obs)                     # warm-up
     t0, k = time.perf_counter(), 0
@@ -642,19 +776,24 @@ def cpu_baseline(name, budget_s=20.0, steps=None):
         el = time.perf_counter() - t0
         if (steps is not None and k >= steps) or (steps is None and (el > budget_s or k >= 50)):
             break
-    return {"value": round(n_envs * n_steps * k / el, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(),
-            "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"{k} PPO iterations of the oracle port at n_envs={n_envs}, n_steps={n_steps} "
-                      f"(same hyperparameters, minibatch clamped); numpy env step is single-threaded, torch uses "
-                      f"{torch.get_num_threads()} threads"}
+    same = (n_envs, n_steps) == (full["n_envs"], full["n_steps"])
+    return {"value": round(n_envs * n_steps * k / el, 1), "unit": "env-steps/s", "cores": threads,
+            "host_cpus": os.cpu_count(), "kind": "port", "same_config": same,
+            "sample": f"{k} PPO iterations of the oracle port at n_envs={n_envs}, n_steps={n_steps}"
+                      + ("" if same else f" (of {full['n_steps']})")
+                      + f" (same YAML hyperparameters: minibatch, epochs); numpy env step is single-threaded, torch uses "
+                      f"{threads} threads"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n_envs, n_steps = CPU_SAMPLE[args.workload]
-    iteration, obs = _cpu_setup(args.workload, n_envs, n_steps)
+    threads = _host_threads()
+    name = args.workload
+    n_envs, n_steps = CPU_SAMPLE[name]
+    full = workload_hp(name)
+    iteration, obs = _cpu_setup(name, n_envs, n_steps)
     for _ in range(max(1, min(args.warmup, 2))):
         obs = iteration(obs)
     t0 = time.perf_counter()
@@ -662,15 +801,20 @@ def run_reference(args):
         obs = iteration(obs)
     el = time.perf_counter() - t0
     value = n_envs * n_steps * args.steps / el
-    cpu = {"value": round(value, 1), "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-           "sample": f"{args.steps} PPO iterations at n_envs={n_envs}, n_steps={n_steps} on the host CPU"}
+    sample = (f"{args.steps} PPO iterations at n_envs={n_envs}, n_steps={n_steps} of {full['n_steps']} on the host CPU "
+              f"({threads} torch threads; numpy env step single-threaded)")
+    cpu = {"value": round(value, 1), "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps({
-        "impl": "reference", "metric": "PPO env-steps/sec (rollout+GAE+update)", "value": round(value, 1),
+        "impl": "reference", "metric": METRIC, "value": round(value, 1),
         "unit": "env-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}_env_vec PPO (CPU port of the reference path, bounded sample "
-                               f"n_envs={n_envs}, n_steps={n_steps}; hyperparameters of the GPU arm)"},
+        "scaling": "strong" if name == "boxworld" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(name, full),
+                   "yaml_set": {"boxworld": "boxworld-impala", "cartpole": "cartpole", "procgen": "hard-500"}[name],
+                   "parallelism": f"host CPU, {threads} threads (not sharded: rank 0 only)",
+                   "reference_arm": f"CPU port of the reference path on the same workload with n_steps={n_steps} of "
+                                    f"{full['n_steps']} per CPU step (n_envs={n_envs}, minibatch and epochs unchanged; "
+                                    "every phase is linear in n_steps, so env-steps/s is the same quantity)"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -681,7 +825,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="boxworld", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="boxworld", choices=["boxworld", "cartpole", "procgen"])
     ap.add_argument("--matmul", default="tf32x3", choices=["tf32x3", "tf32", "fp32"],
                     help="dense-layer arithmetic: tcgen05 3xTF32 (fp32-parity, default), tcgen05 single TF32, CUDA-core fp32")
     ap.add_argument("--fuse-accum", default="auto",
@@ -691,6 +835,7 @@ def main():
                          "the T sequential steps are latency-bound whatever the range size)")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs only)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C4 block of the default run")
     ap.add_argument("--timed-region-only", action="store_true", help="stop after the device-timed loop (ncu runs)")
     ap.add_argument("--only-kernel-rooflines", action="store_true", help="time just the HBM-bound kernels")
     args = ap.parse_args()

@@ -80,6 +80,9 @@ int tpp_tick_advance(uint64_t* tick, uint64_t delta, void* stream);
  * state624 / left / next: the MT19937 fields of torch.get_rng_state() (624 words, one per uint64; countdown; index).
  * Replaces torch.randperm in Storage.fetch_train_generator (common/storage.py:87).  n < 2^32 / 20.            */
 int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out);
+/* The same permutation written as int32 (n < 2^31 always holds here): half the pinned bytes / H2D traffic of an epoch's
+ * minibatch indices; the device widens them when it copies the staging buffer into the gather's index buffer.      */
+int tpp_randperm_mt19937_i32(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int32_t* out);
 
 /* ---- Box-World ----------------------------------------------------------------------------------------- */
 /* Device-resident state of N Box-World envs (replaces the numpy members of BoxWorldVec,

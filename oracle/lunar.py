@@ -5,8 +5,9 @@ NotImplementedError at import and the rest of the file is Gymnasium's scalar Box
 not installable here).  This file is therefore a float64 restatement of THIS repository's own vectorised semantics
 (csrc/env_prevec.cu, family TPP_LUNAR_LANDER); it checks the CUDA kernel against an independent implementation of
 the same equations, not against the reference.  What is taken from the reference file: the 8-wide observation
-layout and its normalisation (:606-615), the four discrete actions and engine impulse geometry (:520-601), the
-reward shaping formula (:617-633) and the terminal rewards (:635-642).
+layout and its normalisation (:615-624), the four discrete actions and engine impulse geometry (:520-608), the
+reward shaping formula (:628-637) and the terminal rewards (:644-651); the observation and shaping formulas are
+executed from the reference's own source lines in tests/test_oracle_vs_reference.py.
 
 Model: one rigid body (hull) with two massless legs; flat ground at the helipad height across
 the whole width; feet are penalty (spring-damper) contacts; no engine dispersion noise; dt = 1/50.
@@ -27,6 +28,12 @@ K_N, C_N, C_T, MU = 1500.0, 60.0, 30.0, 1.0
 DT = 1.0 / FPS
 START_LOW = np.array([0.0, (400 / SCALE - (HELIPAD_Y + LEG_DOWN)) / H2, -0.83, -0.553, 0.0, 0.0, 0.0, 0.0])
 START_HIGH = np.array([0.0, (400 / SCALE - (HELIPAD_Y + LEG_DOWN)) / H2, 0.83, 0.553, 0.0, 0.0, 0.0, 0.0])
+
+
+def observation(x, y, vx, vy, ang, om, c0, c1):
+    """The 8-wide normalised observation of the reference file (discrete_env/lunar_lander_pre_vec.py:615-624)."""
+    return np.stack([(x - W2) / W2, (y - (HELIPAD_Y + LEG_DOWN)) / H2, vx * W2 / FPS, vy * H2 / FPS, ang,
+                     20.0 * om / FPS, c0, c1], axis=1)
 
 
 def shaping(s):
@@ -79,8 +86,7 @@ def lunar_transition(state, action):
         ry = sn * FOOT[f, 0] + cs * FOOT[f, 1]
         c.append((y + ry <= HELIPAD_Y).astype(np.float64))
     hull_low = np.minimum(y + sn * HULL[0, 0] + cs * HULL[0, 1], y + sn * HULL[1, 0] + cs * HULL[1, 1])
-    ns = np.stack([(x - W2) / W2, (y - (HELIPAD_Y + LEG_DOWN)) / H2, vx * W2 / FPS, vy * H2 / FPS, ang,
-                   20.0 * om / FPS, c[0], c[1]], axis=1)
+    ns = observation(x, y, vx, vy, ang, om, c[0], c[1])
     reward = shaping(ns) - prev_shaping - 0.30 * main - 0.03 * side
     crashed = (hull_low <= HELIPAD_Y) | (np.abs(ns[:, 0]) >= 1.0)
     landed = (c[0] > 0) & (c[1] > 0) & (np.abs(vx) < 0.05) & (np.abs(vy) < 0.05) & (np.abs(om) < 0.05) & ~crashed

@@ -241,17 +241,37 @@ def mint_logger():
     print("logger fixture ok:", out["float_rows"].shape, int(out["float_num_episodes"]))
 
 
+CONFIG_SETS = ("boxworld-impala", "cartpole", "hard-500", "acrobot", "mountain_car", "cartpole_swing")
+
+
+def mint_config():
+    """The YAML sets the tests / bench run, extracted (values unchanged) from the reference's
+    hyperparams/procgen/config.yml: the GPU box has no /root/reference."""
+    import yaml
+    with open(os.path.join(ref_shim.REFERENCE_ROOT, "hyperparams/procgen/config.yml")) as f:
+        full = yaml.safe_load(f)
+    sub = {k: full[k] for k in CONFIG_SETS if k in full}
+    with open(os.path.join(OUT, "config_subset.yml"), "w") as f:
+        f.write("# extracted by oracle/mint_golden.py from the reference's hyperparams/procgen/config.yml (values unchanged)\n")
+        yaml.safe_dump(sub, f, sort_keys=False)
+    print("config sets:", list(sub))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.filterwarnings("ignore", category=SyntaxWarning)
     if len(sys.argv) > 1 and sys.argv[1] == "logger":
         mint_logger()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "config":
+        mint_config()
+        return
     for fam in FAMILIES:
         mint_prevec(fam)
     mint_boxworld()
     mint_ppo()
     mint_logger()
+    mint_config()
     print("written to", OUT, [f for f in os.listdir(OUT)])
 
 

@@ -98,6 +98,13 @@ def test_host_randperm_equals_torch_randperm_and_leaves_the_same_generator_state
     w = torch.randperm(4096)
     torch.manual_seed(7)
     assert Storage.randperm(4096, out=out) is out and torch.equal(out, w)
+    # int32 form (what PPO.train uploads: half the pinned bytes): same permutation, same generator state afterwards
+    out32 = torch.empty(1 << 20, dtype=torch.int32)
+    torch.manual_seed(8)
+    w, after = torch.randperm(1 << 20), torch.rand(3)
+    torch.manual_seed(8)
+    Storage.randperm(1 << 20, out=out32)
+    assert torch.equal(out32.long(), w) and torch.equal(torch.rand(3), after)
 
 
 def test_weight_gradient_split_policy():

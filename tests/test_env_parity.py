@@ -103,12 +103,25 @@ def test_teacher_forced_against_golden(golden_dir, family):
 @pytest.mark.parametrize("n_envs", [2, 37, 4096])
 def test_teacher_forced_random_states(family, n_envs):
     """Ragged (N % 4 != 0 -> scalar kernel) and large N (vectorised kernel) against the oracle."""
+    _random_state_check(family, n_envs, 12)
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("log2n", [16, 20])
+def test_teacher_forced_at_sweep_sizes(family, log2n):
+    """BASELINE configs[2] (C3) sizes: the same teacher-forced comparison at N = 2^16 and 2^20 envs per launch (grid
+    sizing, 64-bit offsets and the ld padding of the large rollout slots), every env checked."""
+    _random_state_check(family, 1 << log2n, 2)
+    _random_state_check(family, (1 << log2n) + 36, 1)        # ragged tail: N not a multiple of the vector width / CTA
+
+
+def _random_state_check(family, n_envs, steps):
     kw = dict(max_steps=5)
     env = _make(family, n_envs, seed=3, **kw)
     orc = OraclePreVec(family, n_envs, seed=3, **kw)
     rng = np.random.default_rng(n_envs)
     n_act = env.n_actions
-    for t in range(12):
+    for t in range(steps):
         # widen the start block so that terminations (not only truncations) occur
         lo, hi = orc.low.copy(), orc.high.copy()
         if family in ("cartpole", "cartpole_swing"):

@@ -1,6 +1,7 @@
 """CPU, container only: the oracle against the LIVE, unmodified reference imported from /root/reference through
 oracle/ref_shim.py.  Skipped where the reference tree is absent (the GPU box): there the committed fixtures
 (tests/golden, minted from this same reference) carry the pin."""
+import os
 import warnings
 
 import numpy as np
@@ -106,3 +107,38 @@ def test_product_policy_state_dict_keys_match_reference():
         for (k, a), (_, b) in zip(ref.state_dict().items(), mine.state_dict().items()):
             assert torch.equal(a, b), k
         mine.load_state_dict(ref.state_dict())
+
+
+def test_lunar_observation_and_shaping_formulas_are_the_reference_files():
+    """Lunar lander stays PARITY UNPINNED (the reference module raises at import, :16, and its dynamics are Box2D's).
+    What the file does state in closed form -- the observation normalisation (:615-624) and the shaping reward
+    (:628-634) -- is executed here FROM THE REFERENCE SOURCE LINES on stand-in objects and compared with oracle/lunar.py,
+    so at least those two formulas (and the constants they use, :36-57,339) are pinned."""
+    import re
+    import types
+    from oracle import lunar
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "discrete_env/lunar_lander_pre_vec.py")).read().split("\n")
+    ns = {"np": np}
+    for line in src[35:58]:                       # module constants FPS .. VIEWPORT_H (single-line assignments only)
+        if re.match(r"^[A-Z_]+ = [-+0-9.]+", line):
+            exec(line, ns)
+    assert src[614].strip() == "state = [" and src[627].strip().startswith("shaping = (")
+    state_src = "\n".join(l.strip() for l in src[614:624])
+    shaping_src = "\n".join(l.strip() for l in src[627:633]) + ")"
+    rng = np.random.default_rng(0)
+    H = ns["VIEWPORT_H"] / ns["SCALE"]
+    for _ in range(50):
+        x, y, vx, vy, ang, om = rng.uniform(-5, 25), rng.uniform(0, 14), *rng.normal(size=2) * 3, *rng.normal(size=2)
+        c = rng.integers(0, 2, 2)
+        ns.update(pos=types.SimpleNamespace(x=x, y=y), vel=types.SimpleNamespace(x=vx, y=vy),
+                  self=types.SimpleNamespace(helipad_y=H / 4, lander=types.SimpleNamespace(angle=ang, angularVelocity=om),
+                                             legs=[types.SimpleNamespace(ground_contact=bool(c[0])),
+                                                   types.SimpleNamespace(ground_contact=bool(c[1]))]))
+        exec(state_src, ns)
+        exec(shaping_src, ns)
+        a = np.array([[x], [y], [vx], [vy], [ang], [om], [float(c[0])], [float(c[1])]])
+        ours = lunar.observation(*a)
+        np.testing.assert_allclose(ours[0], np.array(ns["state"], dtype=np.float64), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(lunar.shaping(ours)[0], ns["shaping"], rtol=1e-13)
+    assert (lunar.FPS, lunar.SCALE, lunar.MAIN_POWER, lunar.SIDE_POWER) == \
+        (ns["FPS"], ns["SCALE"], ns["MAIN_ENGINE_POWER"], ns["SIDE_ENGINE_POWER"])

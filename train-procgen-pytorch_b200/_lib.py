@@ -73,6 +73,7 @@ SIGNATURES = {
     "tpp_env_reset": [C.POINTER(EnvCfg), _vp, _vp, _vp, _vp, _vp, _u64, _i64, _vp],
     "tpp_tick_advance": [_vp, _u64, _vp],
     "tpp_randperm_mt19937": [_vp, _vp, _vp, _i64, _vp],
+    "tpp_randperm_mt19937_i32": [_vp, _vp, _vp, _i64, _vp],
     "tpp_boxworld_step": [C.POINTER(BoxWorldState), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_boxworld_gen_levels_host": [_i32, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp],
     "tpp_boxworld_gen_levels_device": [C.POINTER(BoxWorldState), _vp, _vp, _i32, _vp],

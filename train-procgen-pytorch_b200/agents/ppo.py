@@ -144,6 +144,9 @@ class PPO(BaseAgent):
         # rollout: last embedder layer + heads + action draw in one CUDA-core launch (MLP policies, TC engine)
         self.fused_tail = bool(kwargs.get("fused_tail", True))
         self.max_group_rows = int(kwargs.get("max_group_rows", 1 << 18))
+        # sharded runs keep the whole-epoch graph: the per-step ncclAllReduce is captured with the kernels around it
+        # (False: per-group graphs with the all-reduce launched from the host between them)
+        self.graph_allreduce = bool(kwargs.get("graph_allreduce", True))
 
         if policy.flat is None:
             policy.flatten_(device)
@@ -175,6 +178,8 @@ class PPO(BaseAgent):
         self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
         self.world_size = 1
         self.process_group = None
+        if storage_valid is not None:        # decorrelate the validation rollout's action draws from the training one's
+            storage_valid.sample_offset = int(n_envs)
         self._tick = torch.zeros(1, dtype=torch.int64, device=policy.flat.device)
         self._rollout_graph = None
         self._stats = None
@@ -183,9 +188,20 @@ class PPO(BaseAgent):
         self.n_launches = 0
 
     # ------------------------------------------------------------------------------------------
-    def shard(self, world_size, process_group=None):
+    def shard(self, world_size, process_group=None, rank=None):
         """Env-sharded data parallel: gradients are summed with ONE all-reduce per optimizer step and scaled by
-        1/world inside the clip+Adam kernel; advantage moments are all-reduced once per rollout."""
+        1/world inside the clip+Adam kernel; advantage moments are all-reduced once per rollout.  The rank is folded
+        into the action-sampling key (global env index = rank * n_envs + e), so shards never draw the same uniforms;
+        env seeds are the caller's (use seed + rank)."""
+        if rank is None:
+            rank = torch.distributed.get_rank(process_group) if torch.distributed.is_initialized() else 0
+        if getattr(self, "_shard_rank", 0) != rank:
+            assert not self.__dict__.get("_graphs") and not self.__dict__.get("_host_graphs"), \
+                "shard() must precede the first rollout (the sampling offset is baked into captured graphs)"
+        self._shard_rank = rank
+        for st in (self.storage, self.storage_valid):
+            if st is not None:
+                st.sample_offset = getattr(st, "sample_offset", 0) % (2 * self.n_envs) + 2 * self.n_envs * rank
         self.world_size, self.process_group = world_size, process_group
         self.optimizer.set_grad_scale(1.0 / world_size)
         self.storage.world_size, self.storage.process_group = world_size, process_group
@@ -228,11 +244,12 @@ class PPO(BaseAgent):
             _lib.call("tpp_mlp_tail_sample", _lib.ptr(h), ldh, fin, eng._p(w_off), eng._p(b_off), fout,
                       1 if relu else 0, eng._p(eng.head_w_off), eng._p(eng.head_b_off), self.n_actions, n, None,
                       eng.ld_head, _lib.ptr(act), _lib.ptr(logp), _lib.ptr(value), self.sample_seed,
-                      _lib.ptr(self._tick), int(t), 0, int(lo), _lib.stream_ptr())
+                      _lib.ptr(self._tick), int(t), 0, int(lo) + getattr(storage, "sample_offset", 0),
+                      _lib.stream_ptr())
             self.n_launches += 1
             return
         head = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, obs_ready=obs_ready)
-        self._sample(head, n, act, logp, value, t, env_offset=lo)
+        self._sample(head, n, act, logp, value, t, env_offset=lo + getattr(storage, "sample_offset", 0))
 
     def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False, slot=0, trunk_only=False):
         if trunk_only:
@@ -364,11 +381,12 @@ class PPO(BaseAgent):
         use_graph = self.use_cuda_graph and not is_torch_engine
         graphs = self.__dict__.setdefault("_mb_graphs", {})
         k = 0
-        # Whole-epoch graph (single GPU, MLP engines): every group of an epoch -- gather, forward, loss, backward --
+        # Whole-epoch graph (MLP engines): every group of an epoch -- gather, forward, loss, backward --
         # and the optimizer steps + weight re-splits at their fixed positions are ONE graph replay per epoch; the
         # epoch's permutation is uploaded into a static index buffer first.  Removes the per-group graph launches, index
         # copies and stats copies of an iteration from the host's critical path.
-        epoch_graph = (use_graph and self.use_epoch_graph and self.world_size == 1 and step_every > 0
+        epoch_graph = (use_graph and self.use_epoch_graph and (self.world_size == 1 or self.graph_allreduce)
+                       and step_every > 0
                        and n_mb % step_every == 0
                        and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0)
         if epoch_graph:
@@ -383,6 +401,8 @@ class PPO(BaseAgent):
                 for i in range(n_grp):
                     group_body(idx_g[i], stats_g[i])
                     if ((i + 1) * G) % step_every == 0:
+                        if self.world_size > 1:    # NCCL all-reduce captured into the epoch graph (one replay per epoch)
+                            parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
                         self.optimizer.launch()
                         if hasattr(engine, "refresh_weights"):
                             engine.refresh_weights()
@@ -399,7 +419,7 @@ class PPO(BaseAgent):
                 if getattr(self, "_h2d_stream", None) is None:
                     self._h2d_stream = torch.cuda.Stream()
                 if getattr(self, "_idx_stage", None) is None or self._idx_stage[0].shape != (n_mb, mb):
-                    self._idx_stage = [torch.zeros(n_mb, mb, dtype=torch.int64, device=dev) for _ in range(2)]
+                    self._idx_stage = [torch.zeros(n_mb, mb, dtype=torch.int32, device=dev) for _ in range(2)]
                     self._stage_free = [None, None]
 
                 def upload(e):
@@ -726,63 +746,84 @@ class PPO(BaseAgent):
                    self.logger.logdir + "/model_" + str(self.t) + ".pth")
 
     def _host_step_device(self, st, t, N):
-        """Device side of one host-env step (frames -> policy forward -> Philox sampling into slot t).  The ~40
-        launches are captured once per slot (second visit) and replayed afterwards: the step is launch-bound."""
+        """Device side of one host-env step (frames -> policy forward -> Philox sampling into slot t, then the start of
+        the actions' device -> host copy).  The ~40 launches are captured once per slot (second visit) and replayed
+        afterwards: the step is launch-bound."""
         def body():
             head = self._policy_head(st.obs_slot(t), st)
-            self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t)
+            self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t,
+                         env_offset=getattr(st, "sample_offset", 0))
 
         graphs = self.__dict__.setdefault("_host_graphs", {})
         key = (id(st), t)
         entry = graphs.get(key)
         if not self.use_cuda_graph or getattr(self.engine, "uses_autograd", False):
-            return body()
-        if entry is None:                      # first visit: eager (allocates the workspaces)
+            body()
+        elif entry is None:                    # first visit: eager (allocates the workspaces)
             body()
             graphs[key] = "warm"
-            return
-        if entry == "warm":
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            c0 = (self.n_launches, self.engine.n_launches)
-            with torch.cuda.graph(g):
-                body()
-            entry = graphs[key] = (g, self.n_launches - c0[0], self.engine.n_launches - c0[1])
-            self.n_launches, self.engine.n_launches = c0
-        entry[0].replay()
-        self.n_launches += entry[1]
-        self.engine.n_launches += entry[2]
+        else:
+            if entry == "warm":
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                c0 = (self.n_launches, self.engine.n_launches)
+                with torch.cuda.graph(g):
+                    body()
+                entry = graphs[key] = (g, self.n_launches - c0[0], self.engine.n_launches - c0[1])
+                self.n_launches, self.engine.n_launches = c0
+            entry[0].replay()
+            self.n_launches += entry[1]
+            self.engine.n_launches += entry[2]
+        st.start_action_fetch(t)
 
     def _train_host_env(self, num_timesteps, checkpoints):
-        """Host-stepped envs (Procgen or any numpy VecEnv; reference loop agents/ppo.py:216-236).  Per step: the
-        observation is staged once into rollout slot t (pinned H2D; uint8 frames stay uint8), the policy forward and
-        the action sampling run on the device on that slot, only the N actions come back to the host for
-        ``env.step``, and reward / done go up.  GAE and the update never leave the device."""
+        """Host-stepped envs (Procgen or any numpy VecEnv; reference loop agents/ppo.py:216-279).  Per step: the
+        observation is staged into rollout slot t (double-buffered pinned H2D; uint8 frames stay uint8), the policy
+        forward and the action draw run on the device on that slot, only the N actions come back to the host (pinned,
+        event wait -- no stream synchronisation) for ``env.step``; rewards / dones collect in pinned host rows and go up
+        once per rollout.  The validation env steps in the same loop like the reference's (:228-252): its device work
+        overlaps the training env's host step.  GAE and the update never leave the device."""
         checkpoint_cnt = 0
-        st, N, T = self.storage, self.n_envs, self.n_steps
-        obs = self.env.reset()
+        N, T = self.n_envs, self.n_steps
+        pairs = [(self.env, self.storage)]
+        if self.env_valid is not None:
+            pairs.append((self.env_valid, self.storage_valid))
+        raw = [bool(getattr(e, "stages_raw_frames", False)) for e, _ in pairs]
+        obs = [e.host_reset() if r else e.reset() for (e, _), r in zip(pairs, raw)]
         while self.t < num_timesteps:
             self.policy.eval()
             if hasattr(self.engine, "refresh_weights"):
                 self.engine.refresh_weights()
             for t in range(T):
-                st.stage_obs(t, obs)
-                self._host_step_device(st, t, N)
-                act = st.act_i32[t, :N].cpu().numpy().astype(np.int64)      # the step's only device->host read
-                obs, rew, done, info = self.env.step(act)
-                st.stage_step(t, rew, done)
-            st.stage_obs(T, obs)
-            head = self._policy_head(st.obs_slot(T), st)
-            st.value[T, :N] = head[:N, self.n_actions]
+                for k, (e, st) in enumerate(pairs):
+                    st.stage_obs(t, obs[k])
+                    self._host_step_device(st, t, N)
+                for k, (e, st) in enumerate(pairs):
+                    act = st.finish_action_fetch()                 # the step's only device -> host read
+                    if raw[k]:
+                        obs[k], rew, done, info = e.host_step(act)
+                        st.stage_step(t, rew, done, raw_rew=rew)
+                    else:
+                        obs[k], rew, done, info = e.step(act)
+                        st.stage_step(t, rew, done, info=info)
+            for k, (e, st) in enumerate(pairs):
+                st.stage_obs(T, obs[k])
+                st.flush_steps()
+                if hasattr(e, "finish_rollout"):
+                    e.finish_rollout(st)
+                head = self._policy_head(st.obs_slot(T), st)
+                st.value[T, :N] = head[:N, self.n_actions]
+                st.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
             _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
-            st.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
             summary = self.optimize()
             self.t += T * N
-            self._log(summary, num_timesteps)
+            self.optimizer, lr = self.adjust_lr(self.optimizer, self.learning_rate, self.t, num_timesteps)
+            self._log(summary, lr)
             if self.num_checkpoints and checkpoint_cnt < len(checkpoints) and self.t > checkpoints[checkpoint_cnt]:
                 self.save_checkpoint()
                 checkpoint_cnt += 1
-        self.env.close()
+        for e, _ in pairs:
+            e.close()
 
 
 def _round4(x):

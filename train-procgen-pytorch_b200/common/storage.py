@@ -147,16 +147,26 @@ class Storage:
 
     def _store_obs(self, slot, obs):
         if self.is_image and getattr(obs, "dtype", None) in (np.uint8, torch.uint8):
-            # raw uint8 NHWC frames (what the Procgen engine emits before Transpose/Scale): staged through a pinned
-            # buffer straight into the rollout slot, 4x less PCIe traffic than the float NCHW contract
+            # raw uint8 NHWC frames (what the Procgen engine emits before Transpose/Scale): staged through DOUBLE-BUFFERED
+            # pinned memory straight into the rollout slot, 4x less PCIe traffic than the float NCHW contract.  The host
+            # fills buffer k % 2 while the copy out of buffer (k - 1) % 2 may still be in flight; a buffer is reused only
+            # after the event behind its last copy has completed (an event wait, not a stream synchronisation).
             src = obs if torch.is_tensor(obs) else torch.from_numpy(np.ascontiguousarray(obs))
             assert tuple(src.shape) == tuple(self.frames[slot].shape), (src.shape, self.frames[slot].shape)
             if not src.is_cuda:
                 if self._pinned is None:
-                    self._pinned = torch.empty_like(src).pin_memory()
-                self._pinned.copy_(src)
-                src = self._pinned
-            self.frames[slot].copy_(src, non_blocking=True)
+                    self._pinned = [[torch.empty_like(src).pin_memory(), None] for _ in range(2)]
+                    self._pinned_k = 0
+                buf = self._pinned[self._pinned_k]
+                self._pinned_k ^= 1
+                if buf[1] is not None:
+                    buf[1].synchronize()
+                buf[0].copy_(src)
+                self.frames[slot].copy_(buf[0], non_blocking=True)
+                buf[1] = torch.cuda.Event()
+                buf[1].record()
+            else:
+                self.frames[slot].copy_(src, non_blocking=True)
             self.h2d_bytes += src.numel()
             return
         o = self._t(obs, torch.float32)
@@ -181,13 +191,61 @@ class Storage:
         """Host-env staging: copy one observation batch (uint8 NHWC frames, float NCHW, or [N, n_obs]) into a slot."""
         self._store_obs(slot, obs)
 
-    def stage_step(self, slot, rew, done):
-        """Host-env staging of the step's reward / done vectors (the action, log-prob and value are already in the
-        rollout: they were produced on the device)."""
-        N = self.num_envs
-        self.rew[slot, :N] = self._t(rew, torch.float32).reshape(-1)
-        self.done_u8[slot, :N] = self._t(done, torch.uint8).reshape(-1)
-        self.h2d_bytes += 5 * N
+    def _host_rows(self):
+        if getattr(self, "_host_step", None) is None:
+            T, ld = self.num_steps, self.ld
+            self._host_step = dict(rew=torch.zeros(T, ld, dtype=torch.float32).pin_memory(),
+                                   raw=torch.zeros(T, ld, dtype=torch.float32).pin_memory(),
+                                   done=torch.zeros(T, ld, dtype=torch.uint8).pin_memory(),
+                                   act=torch.zeros(self.num_envs, dtype=torch.int32).pin_memory(), has_raw=False)
+        return self._host_step
+
+    def start_action_fetch(self, slot):
+        """Host-env staging: start the device -> host copy of the N actions the policy drew into slot ``slot`` (pinned,
+        asynchronous) and record ITS event."""
+        h = self._host_rows()
+        h["act"].copy_(self.act_i32[slot, :self.num_envs], non_blocking=True)
+        h["act_event"] = torch.cuda.Event()
+        h["act_event"].record()
+
+    def finish_action_fetch(self):
+        """Wait for that copy alone (an event wait: the host never synchronises the whole stream) -> int64 numpy."""
+        h = self._host_rows()
+        h["act_event"].synchronize()
+        self.d2h_bytes = getattr(self, "d2h_bytes", 0) + 4 * self.num_envs
+        return h["act"].numpy().astype(np.int64)
+
+    def fetch_actions(self, slot):
+        self.start_action_fetch(slot)
+        return self.finish_action_fetch()
+
+    def stage_step(self, slot, rew, done, info=None, raw_rew=None):
+        """Host-env staging of one step's reward / done vectors (the action, log-prob and value are already in the rollout:
+        they were produced on the device).  Rows collect in pinned host memory and go up in ONE copy per rollout
+        (``flush_steps``).  The raw env reward the logger wants (common/storage.py:131-137) is ``raw_rew`` or, like the
+        reference, ``info[i]['env_reward']`` when the env's VecNormalize wrapper put it there; ``info[i]['env_done']``
+        likewise overrides ``done`` for the logger's episode accounting only when present."""
+        h, N = self._host_rows(), self.num_envs
+        h["rew"][slot, :N] = torch.as_tensor(np.asarray(rew, dtype=np.float32).reshape(-1))
+        h["done"][slot, :N] = torch.as_tensor(np.asarray(done).reshape(-1).astype(np.uint8))
+        if raw_rew is None and info is not None and len(info) == N and isinstance(info[0], dict) \
+                and "env_reward" in info[0]:
+            raw_rew = np.fromiter((i["env_reward"] for i in info), dtype=np.float32, count=N)
+        if raw_rew is not None:
+            h["raw"][slot, :N] = torch.as_tensor(np.asarray(raw_rew, dtype=np.float32).reshape(-1))
+            h["has_raw"] = True
+
+    def flush_steps(self):
+        """One H2D copy per rollout of the staged reward / done (/ raw reward) rows."""
+        h = self._host_rows()
+        self.rew.copy_(h["rew"], non_blocking=True)
+        self.done_u8.copy_(h["done"], non_blocking=True)
+        self.h2d_bytes += self.num_steps * self.num_envs * 5
+        if h["has_raw"]:
+            if self.env_rew is None:
+                self.enable_raw_rewards()
+            self.env_rew.copy_(h["raw"], non_blocking=True)
+            self.h2d_bytes += self.num_steps * self.num_envs * 4
 
     def store_last(self, last_obs, last_hidden_state, last_value):
         self._store_obs(self.num_steps, last_obs)
@@ -233,9 +291,9 @@ class Storage:
             return perm
         a = state.numpy()           # [0:8) seed, [8:12) left, [12:16) seeded, [16:24) next, [24:5016) 624 words (u64 each)
         out = torch.empty(n, dtype=torch.int64) if out is None else out
-        assert out.dtype == torch.int64 and out.is_contiguous() and out.numel() == n and not out.is_cuda
-        _lib.call("tpp_randperm_mt19937", a[24:24 + 624 * 8].ctypes.data, a[8:12].ctypes.data, a[16:24].ctypes.data,
-                  int(n), out.data_ptr())
+        assert out.dtype in (torch.int64, torch.int32) and out.is_contiguous() and out.numel() == n and not out.is_cuda
+        _lib.call("tpp_randperm_mt19937" if out.dtype == torch.int64 else "tpp_randperm_mt19937_i32",
+                  a[24:24 + 624 * 8].ctypes.data, a[8:12].ctypes.data, a[16:24].ctypes.data, int(n), out.data_ptr())
         torch.set_rng_state(state)
         return out
 
@@ -251,14 +309,15 @@ class Storage:
 
     def epoch_perm_pinned(self, mini_batch_size, slot):
         """The same draw as ``epoch_indices`` left in a reusable pinned host buffer (``slot``): the caller uploads it
-        on a copy stream while the previous epoch's kernels run.  Returns (pinned int64 [n_mb, mb], ready event or
-        None): the event of the last upload from this buffer must have completed before it is overwritten."""
+        on a copy stream while the previous epoch's kernels run.  Returns (pinned int32 [n_mb, mb], ready event or
+        None): the event of the last upload from this buffer must have completed before it is overwritten.  The buffer is
+        int32 (the device widens it to the gather's int64 index buffer in the copy it makes anyway)."""
         batch = self.num_steps * self.num_envs
         n_mb = batch // mini_batch_size
         pool = self.__dict__.setdefault("_perm_pool", {})
         key = (slot, n_mb, mini_batch_size)
-        if key not in pool:
-            pool[key] = [torch.empty(n_mb, mini_batch_size, dtype=torch.int64).pin_memory(), None]
+        if key not in pool:         # int32: T*N < 2^31 for every config; half the pinned bytes and H2D traffic
+            pool[key] = [torch.empty(n_mb, mini_batch_size, dtype=torch.int32).pin_memory(), None]
         buf, busy = pool[key]
         if busy is not None:
             busy.synchronize()                      # the previous upload from this buffer has left the host

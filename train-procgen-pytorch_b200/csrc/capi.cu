@@ -59,20 +59,12 @@ struct Mt {
 };
 }  // namespace
 
-extern "C" int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out) {
-  TPP_CHECK_ARG(state624 && left && next && out && n > 0);
-  if (n >= (int64_t)(0xFFFFFFFFu / 20)) return TPP_ENOTSUP;      // ATen switches to another algorithm there
-  TPP_CHECK_ARG(*left >= 1 && *left <= 624 && *next <= 624);   // ATen refills at left == 0 and never stores it
-  Mt mt;
-  for (int i = 0; i < 624; ++i) mt.s[i] = (uint32_t)state624[i];
-  mt.left = *left;
-  mt.next = (uint32_t)*next;
-  std::vector<uint32_t> r((size_t)n);
-  for (int64_t i = 0; i < n; ++i) r[(size_t)i] = (uint32_t)i;
+// the Fisher-Yates loop on a 4-byte index array r[0..n)
+static void randperm_core(Mt& mt, uint32_t* rp, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) rp[i] = (uint32_t)i;
   // the draws of a block first (the generator is the only sequential part), their swap partners prefetched: the
   // swaps themselves are random accesses into a multi-megabyte array
   constexpr int BLK = 64;
-  uint32_t* rp = r.data();
   for (int64_t i0 = 0; i0 < n - 1; i0 += BLK) {
     const int m = (int)((n - 1 - i0) < BLK ? (n - 1 - i0) : BLK);
     uint32_t tgt[BLK];
@@ -86,9 +78,33 @@ extern "C" int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t*
       rp[tgt[k]] = sav;
     }
   }
-  for (int64_t i = 0; i < n; ++i) out[i] = (int64_t)r[(size_t)i];
+}
+
+static int randperm_any(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out64, int32_t* out32) {
+  TPP_CHECK_ARG(state624 && left && next && (out64 || out32) && n > 0);
+  if (n >= (int64_t)(0xFFFFFFFFu / 20)) return TPP_ENOTSUP;      // ATen switches to another algorithm there
+  TPP_CHECK_ARG(*left >= 1 && *left <= 624 && *next <= 624);   // ATen refills at left == 0 and never stores it
+  Mt mt;
+  for (int i = 0; i < 624; ++i) mt.s[i] = (uint32_t)state624[i];
+  mt.left = *left;
+  mt.next = (uint32_t)*next;
+  if (out32) {                       // n < 2^32 / 20 < 2^31: the indices fit int32; permuted in place
+    randperm_core(mt, reinterpret_cast<uint32_t*>(out32), n);
+  } else {
+    std::vector<uint32_t> r((size_t)n);
+    randperm_core(mt, r.data(), n);
+    for (int64_t i = 0; i < n; ++i) out64[i] = (int64_t)r[(size_t)i];
+  }
   for (int i = 0; i < 624; ++i) state624[i] = mt.s[i];
   *left = mt.left;
   *next = mt.next;
   return TPP_OK;
+}
+
+extern "C" int tpp_randperm_mt19937(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int64_t* out) {
+  return randperm_any(state624, left, next, n, out, nullptr);
+}
+
+extern "C" int tpp_randperm_mt19937_i32(uint64_t* state624, int32_t* left, uint64_t* next, int64_t n, int32_t* out) {
+  return randperm_any(state624, left, next, n, nullptr, out);
 }
