@@ -342,6 +342,31 @@ int tpp_mlp_tail_sample(const float* h, int64_t ldh, int32_t K, const float* W, 
                         float* head_out, int32_t ld_head, int32_t* act, float* logp, float* value, uint64_t seed,
                         const uint64_t* tick, uint64_t t_offset, int32_t greedy, int32_t env_offset, void* stream);
 
+/* The whole rollout-step policy in ONE launch (csrc/rollout_fused.cu): a depth-4 MLPModel forward (hidden width 256,
+ * latent 64), both heads and tpp_sample_actions' draw for n_rows envs; a cluster of 4 CTAs per 128 envs splits every
+ * layer's contraction four ways and exchanges partial sums over distributed shared memory, so activations never leave
+ * the SMs.  Replaces PPO.predict's policy(obs) -> Categorical -> sample / log_prob per rollout step
+ * (agents/ppo.py:72-81, common/policy.py:61-87, common/model.py:954-980).
+ * a1_mode 0: x = row-major fp32 rows [n_rows][ldx] that are EXACT in TF32 (integer pixel values; ldx % 4 == 0, zero
+ *            beyond k[0]); a1_mode 1: x = feature-major slot [k[0]][ldx] (k[0] <= 128), split into hi / lo in-kernel.
+ * w_hi / w_lo[l]: the layer's TF32 weight pair [n[l]][ldw[l]] (zero beyond k[l]); bias[l] fp32; relu[l] != 0 applies
+ * max(., 0).  head_w [A+1][64] / head_b [A+1] plain fp32.  head_out (nullable) [n_rows][ld_head] receives logits + value.
+ * Returns TPP_ENOTSUP for other shapes (callers fall back to the per-layer GEMM path).                          */
+typedef struct {
+  int32_t n_rows, a1_mode;
+  const float* x; int64_t ldx;
+  const float* w_hi[4]; const float* w_lo[4]; int64_t ldw[4];
+  int32_t k[4], n[4];
+  const float* bias[4]; int32_t relu[4];
+  const float* head_w; const float* head_b; int32_t n_actions, ld_head;
+  int32_t* act; float* logp; float* value; float* head_out;
+  uint64_t seed; const uint64_t* tick; uint64_t t_offset; int32_t greedy, env_offset;
+  void* dbg;      /* nullable: int64 [4][64] clock64 timeline of cluster 0 (profiles/fused_rollout_timeline.py)     */
+  void* scratch; int64_t scratch_bytes;   /* exchange slots of the clusters (device memory, stays in L2): 384 KB per
+                                             128 envs processed concurrently; 33 x 384 KB covers a full B200            */
+} tpp_fused_policy;
+int tpp_policy_rollout_fused(const tpp_fused_policy* f, void* stream);
+
 /* ---- PPO loss, fused forward + backward ---------------------------------------------------------------- */
 typedef struct {
   float eps_clip, value_coef, entropy_coef, entropy_multiplier, x_entropy_coef;

@@ -74,7 +74,8 @@ def test_cartpole_yaml_set_trains_with_validation_env_and_checkpoints(tmp_path):
     for pre in ("", "val_"):
         assert np.isfinite(rows[-1, c[pre + "mean_episode_rewards"]])
         assert rows[-1, c[pre + "mean_episode_rewards"]] == rows[-1, c[pre + "mean_episode_len"]]
-        assert 1 <= rows[-1, c[pre + "min_episode_len"]] <= rows[-1, c[pre + "max_episode_len"]] <= 500
+        # (the reference takes np.min / np.max with initial=0, common/logger.py:180-186: the minimum column is 0)
+        assert rows[-1, c[pre + "min_episode_len"]] == 0 and 1 <= rows[-1, c[pre + "max_episode_len"]] <= 500
     # the validation env draws its physics from the `_v` parameter ranges (discrete_env/helper_pre_vec.py:49-62)
     assert agent.env_valid.degrees == hp["degrees_v"] and agent.env.degrees == 12
     # linear lr decay applied after every iteration (agents/ppo.py:267): column = lr of the NEXT update
@@ -220,12 +221,16 @@ def test_staged_host_env_pipeline_normalises_on_device_and_logs_raw_rewards(tmp_
     vn = VecNormalizeOracle(N, gamma=0.999)
     want = np.stack([vn.step(r.astype(np.float64), d) for r, d in zip(raw_env.raw_log, raw_env.done_log)])
     np.testing.assert_allclose(st.rew[:, :N].cpu().numpy(), want[-T:], rtol=1e-6, atol=1e-7)
-    run_r, run_l = np.zeros(N), np.zeros(N, dtype=np.int64)
-    rets, _ = close_episodes(np.stack(raw_env.raw_log), np.stack(raw_env.done_log), run_r, run_l)
+    def fed_per_iteration(e):        # the logger is fed once per rollout: env-major inside every T-step batch
+        run_r, run_l, out = np.zeros(N), np.zeros(N, dtype=np.int64), []
+        for i in range(iters):
+            r, _ = close_episodes(np.stack(e.raw_log[i * T:(i + 1) * T]), np.stack(e.done_log[i * T:(i + 1) * T]), run_r,
+                                  run_l)
+            out += list(r)
+        return np.array(out)
+    rets = fed_per_iteration(raw_env)
     assert lg.num_episodes == len(rets)
     np.testing.assert_allclose(np.array(lg.episode_reward_buffer), rets[-40:])
-    rets_v, _ = close_episodes(np.stack(raw_valid.raw_log), np.stack(raw_valid.done_log), np.zeros(N),
-                               np.zeros(N, dtype=np.int64))
-    np.testing.assert_allclose(np.array(lg.episode_reward_buffer_v), rets_v[-40:])
+    np.testing.assert_allclose(np.array(lg.episode_reward_buffer_v), fed_per_iteration(raw_valid)[-40:])
     cols, rows = _read_csv(str(tmp_path))
     assert rows.shape[0] == iters

@@ -58,6 +58,16 @@ class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
                 ("alpha", C.c_float), ("_reserved", C.c_int32)]
 
 
+class FusedPolicy(C.Structure):   # mirrors tpp_fused_policy
+    _fields_ = [("n_rows", C.c_int32), ("a1_mode", C.c_int32), ("x", C.c_void_p), ("ldx", C.c_int64),
+                ("w_hi", C.c_void_p * 4), ("w_lo", C.c_void_p * 4), ("ldw", C.c_int64 * 4),
+                ("k", C.c_int32 * 4), ("n", C.c_int32 * 4), ("bias", C.c_void_p * 4), ("relu", C.c_int32 * 4),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("n_actions", C.c_int32), ("ld_head", C.c_int32),
+                ("act", C.c_void_p), ("logp", C.c_void_p), ("value", C.c_void_p), ("head_out", C.c_void_p),
+                ("seed", C.c_uint64), ("tick", C.c_void_p), ("t_offset", C.c_uint64), ("greedy", C.c_int32),
+                ("env_offset", C.c_int32), ("dbg", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
+
+
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}
 TC_A_EXACT, TC_B_EXACT = 16, 32
 TC_TILE_PAIR, TC_TILE_PAIR_PERSISTENT, TC_TILE_PAIR64_PERSISTENT = 512, 513, 65     # tpp_tc_gemm.block_n codes
@@ -102,6 +112,7 @@ SIGNATURES = {
     "tpp_sample_actions": [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _u64, _vp, _u64, _i32, _i32, _vp],
     "tpp_mlp_tail_sample": [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _u64,
                             _vp, _u64, _i32, _i32, _vp],
+    "tpp_policy_rollout_fused": [C.POINTER(FusedPolicy), _vp],
     "tpp_vecnormalize_rollout": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f64, _f64, _f64, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],

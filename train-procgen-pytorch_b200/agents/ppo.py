@@ -143,6 +143,9 @@ class PPO(BaseAgent):
         self.rollout_chains = kwargs.get("rollout_chains", 1)
         # rollout: last embedder layer + heads + action draw in one CUDA-core launch (MLP policies, TC engine)
         self.fused_tail = bool(kwargs.get("fused_tail", True))
+        # rollout: the WHOLE policy step (4 dense layers + heads + action draw) in one cluster kernel
+        # (tpp_policy_rollout_fused); False keeps the per-layer GEMM launches + tail kernel
+        self.fused_rollout = bool(kwargs.get("fused_rollout", True))
         self.max_group_rows = int(kwargs.get("max_group_rows", 1 << 18))
         # sharded runs keep the whole-epoch graph: the per-step ncclAllReduce is captured with the kernels around it
         # (False: per-group graphs with the all-reduce launched from the host between them)
@@ -237,6 +240,23 @@ class PPO(BaseAgent):
         lo, hi = env_range or (0, storage.num_envs)
         n, eng = hi - lo, self.engine
         act, logp, value = storage.act_i32[t, lo:hi], storage.logp[t, lo:hi], storage.value[t, lo:hi]
+        off = int(lo) + getattr(storage, "sample_offset", 0)
+        if self.fused_rollout and isinstance(eng, MLPEngineTC):
+            raw = bool(storage.is_image and eng.raw_pixels)
+            if eng.fused_rollout_ok(raw) and (raw or not storage.is_image):
+                if raw:          # pixel rows of the slot: written by the env's step kernel, or converted here
+                    c, h, w = storage.obs_shape
+                    mb = storage.minibatch_buffers(n, *self._obs_buf_args(storage), slot=slot)
+                    if not obs_ready:
+                        _lib.call("tpp_frames_to_obs", _lib.ptr(storage.obs_slot(t)[lo:hi]), n, h, w, c,
+                                  _lib.ptr(mb.obs), None, mb.ld_obs, 1, _lib.stream_ptr())
+                        self.n_launches += 1
+                    eng.rollout_fused(mb.obs, n, mb.ld_obs, True, act, logp, value, self.sample_seed, self._tick, t, off)
+                else:
+                    assert env_range is None
+                    eng.rollout_fused(storage.obs_slot(t), n, storage.ld, False, act, logp, value, self.sample_seed,
+                                      self._tick, t, off)
+                return
         if self.fused_tail and isinstance(eng, MLPEngineTC) and eng.tail_ok():
             h, ldh = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, trunk_only=True,
                                        obs_ready=obs_ready)

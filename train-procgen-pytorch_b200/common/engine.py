@@ -258,6 +258,42 @@ class MLPEngineTC(MLPEngine):
         _, _, fin, fout, _ = self.layers[-1]
         return fin <= 256 and fin % 4 == 0 and fout == 64 and self.A + 1 <= 16
 
+    def fused_rollout_ok(self, raw=False):
+        """Shapes ``tpp_policy_rollout_fused`` is built for: the reference's depth-4 ``mlpmodel`` sets (hidden 256, latent
+        64) in the fp32-parity 3xTF32 mode; the first layer either reads raw pixel rows (<= 768 inputs) or a feature-major
+        vector slot (<= 128 inputs)."""
+        if self.precision != 3 or len(self.layers) != 4 or self.A + 1 > 16:
+            return False
+        if [l[3] for l in self.layers] != [256, 256, 256, 64] or [l[2] for l in self.layers[1:]] != [256, 256, 256]:
+            return False
+        return self.in_dim <= (768 if raw else 128)
+
+    def rollout_fused(self, x, M, ldx, raw, act, logp, value, seed, tick, t_offset, env_offset=0, greedy=False,
+                      head_out=None, dbg=None):
+        """One launch: whole forward + heads + action draw for M rows (csrc/rollout_fused.cu).  ``raw``: x = row-major
+        integer pixel rows [M][ldx] (exact TF32 operand, 1/255 folded into the first layer's weight copy); otherwise x = a
+        feature-major rollout slot [in_dim][ldx]."""
+        f = _lib.FusedPolicy()
+        f.n_rows, f.a1_mode, f.x, f.ldx = M, 0 if raw else 1, x.data_ptr(), ldx
+        for i, (w_off, b_off, fin, fout, relu) in enumerate(self.layers):
+            w = self.w0_raw if (raw and i == 0) else self.w[i]
+            f.w_hi[i], f.w_lo[i], f.ldw[i] = w["hi"].data_ptr(), w["lo"].data_ptr(), w["ldk"]
+            f.k[i], f.n[i], f.relu[i] = fin, fout, 1 if relu else 0
+            f.bias[i] = self.flat.data_ptr() + 4 * b_off
+        f.head_w = self.flat.data_ptr() + 4 * self.head_w_off
+        f.head_b = self.flat.data_ptr() + 4 * self.head_b_off
+        f.n_actions, f.ld_head = self.A, self.ld_head
+        f.act, f.logp, f.value = act.data_ptr(), logp.data_ptr(), value.data_ptr()
+        f.head_out = head_out.data_ptr() if head_out is not None else None
+        f.seed, f.tick, f.t_offset = seed, tick.data_ptr(), int(t_offset)
+        f.greedy, f.env_offset = 1 if greedy else 0, int(env_offset)
+        f.dbg = dbg.data_ptr() if dbg is not None else None
+        if getattr(self, "_fused_scratch", None) is None:      # exchange slots of up to 37 concurrent clusters (148 SMs / 4)
+            self._fused_scratch = torch.zeros(37 * 4 * 3 * 128 * 256, dtype=torch.uint8, device=self.device)
+        f.scratch, f.scratch_bytes = self._fused_scratch.data_ptr(), self._fused_scratch.numel()
+        _lib.call("tpp_policy_rollout_fused", _lib.C.byref(f), _lib.stream_ptr())
+        self.n_launches += 1
+
     def _bn(self, M, N):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= self.pair_min_n and M >= self.wide_tile_rows:

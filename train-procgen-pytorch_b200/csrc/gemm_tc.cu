@@ -38,14 +38,11 @@
 
 #include <algorithm>
 
-#include "tpp_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace tpp {
 namespace tc {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;              // fp32 words per row of a stage = 128 bytes = one 128B-swizzle row
-constexpr int UMMA_K = 8;                // tf32: 32 bytes per MMA k-step
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
 // Epilogue warps: 4 per TMEM lane quarter for wide tiles (the epilogue is instruction-latency bound, not bandwidth
 // bound); narrow tiles (one 32-column group: convolution outputs) have work for 4 warps only, and the small CTA
@@ -89,198 +86,6 @@ struct Params {
 };
 
 enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT = 32, F_PAIR_RELU = 64 };
-
-// ---------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {   // try_wait suspends the thread in hardware for a bounded time, so this is not a hot spin
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-// im2col-mode TMA (NHWC tensor, 3x3 / pad-1 bounding box): BLOCK_M consecutive output pixels starting at base pixel
-// (w, h, n) [bounding-box coordinates = output pixel - 1], shifted by the filter tap (off_w, off_h); 32 channel slots
-// per pixel (channels beyond C, padding pixels and pixels behind the last image are zero-filled by the TMA unit).
-__device__ __forceinline__ void tma_load_im2col(const CUtensorMap* map, uint64_t* bar, void* dst, int w, int h, int n,
-                                                int off_w, int off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-      "[%2], {%7, %8};" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(w), "r"(h), "r"(n), "h"((unsigned short)off_w), "h"((unsigned short)off_h)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC share one 256 x 256 MMA tile ----------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// the same shared-memory offset in the pair's leader CTA (rank 0): clears the peer bit of a shared::cluster address
-constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
-                                                 int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// arrives (once all previously issued MMAs of the pair have retired) on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"((unsigned short)3)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-
-// 32 lanes x 16 consecutive fp32 columns of the accumulator -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 32 lanes x 32 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor, sm_100 version 1):
-// start address >> 4 | LBO(=1, ignored for swizzled K-major) << 16 | SBO(=1024 B between 8-row groups) << 32 |
-// version 1 << 46 | layout SWIZZLE_128B (2) << 61.
-// With 64-byte rows (bk = 16): SBO = 512 B, layout SWIZZLE_64B (4).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int bk) {
-  const uint64_t sbo = bk == 32 ? 64ull : 32ull, layout = bk == 32 ? 2ull : 4ull;
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
-}
-
-// MN-major 32-bit operands have exactly one legal shared-memory layout on sm_100: "128B swizzle with 32B atoms"
-// (cute::UMMA::Layout_MN_SW128_32B_Atom, LayoutType::SWIZZLE_128B_BASE32B = 1, TMA mode SWIZZLE_128B_ATOM_32B):
-// atoms of 4 k-rows x 128 bytes (32 fp32 along m/n), 32-byte chunks XOR-swizzled by (k-row mod 4).
-// LBO = distance between 32-wide m/n blocks (= BLOCK_K rows x 128 B, one TMA box column block),
-// SBO = distance between 4-row k groups (= 512 B, rows are contiguous).
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-  constexpr uint64_t LBO = (BLOCK_K * 128) >> 4;
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (LBO << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
-}
-
-// Round to TF32 (10-bit mantissa), nearest with ties away from zero — the same result as `cvt.rna.tf32.f32`, but
-// as two full-rate integer ops: measured on B200 the cvt form issues at ~1 warp instruction per 32-64 cycles and
-// made the epilogue 10x slower (profiles/README.md).  Adding half an ulp to the magnitude bits and truncating is
-// exact for all finite values (a carry into the exponent is the correct rounding).
-__device__ __forceinline__ float tf32_round(float x) {
-  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // The kernel: one 128 x BLOCK_N output tile (x one k-split) per CTA
@@ -849,58 +654,6 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 // canonical MN-major SW128_32B layout (atoms 4 k-rows x 128 B; m/n blocks BLOCK_K*128 B apart).
 // cuTensorMapEncodeTiled is a driver-API symbol: resolve it through the runtime at first use so that the library has
 // no link-time dependency on libcuda.so (it must load, and export its symbols, on machines without a driver).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// *box_bytes: bytes one box delivers.  A narrow MN-major operand (fewer 32-wide blocks than the tile has) gets a
-// smaller box: the blocks it does not fill only feed accumulator rows / columns that are never stored.
-static int make_map(CUtensorMap* tm, const float* base, long long ld, int rows, int K, int box_rows, int mn_major,
-                    int* box_bytes, int bk = BLOCK_K) {
-  if (!base) return TPP_EINVAL;
-  EncodeTiledFn cuTensorMapEncodeTiled = encode_tiled();
-  if (!cuTensorMapEncodeTiled) return TPP_ENOTSUP;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3)) return TPP_EINVAL;   // TMA: 16-byte address and stride
-  CUresult r;
-  cuuint32_t estr[3] = {1, 1, 1};
-  if (!mn_major) {
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
-    *box_bytes = bk * box_rows * 4;
-    r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    if (box_rows < 32) return TPP_ENOTSUP;
-    const long long blocks = (rows + 31) / 32;
-    // the last 32-wide block must lie inside the (padded) row; a single narrow block (ld < 32, e.g. 16 conv channels)
-    // is described with its true width and the rest of the box is zero-filled by TMA
-    if (ld < blocks * 32 && blocks != 1) return TPP_EINVAL;
-    cuuint64_t gdim[3] = {(cuuint64_t)(ld < 32 ? ld : 32), (cuuint64_t)K, (cuuint64_t)blocks};
-    cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, 128};
-    const long long box_blocks = blocks < box_rows / 32 ? blocks : box_rows / 32;
-    cuuint32_t box[3] = {32, (cuuint32_t)BLOCK_K, (cuuint32_t)box_blocks};
-    *box_bytes = (int)(box_blocks * 32 * BLOCK_K * 4);
-    r = cuTensorMapEncodeTiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  }
-  return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
-}
-
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
