@@ -465,8 +465,8 @@ def run_ours(args):
     else:
         res_agent = res["agent"]
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        torch.distributed.barrier()          # rank 0 is done with its single-GPU legs (roofline, CPU baseline)
+        finish(world)
         return
     pk = peaks()
     N, T = hp["n_envs"], hp["n_steps"]
@@ -510,7 +510,8 @@ def run_ours(args):
     }
     print(json.dumps(line))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        torch.distributed.barrier()
+    finish(world)
 
 
 def other_configs(args, rank, local, pk):
@@ -650,7 +651,8 @@ def run_procgen(args, emit=True):
     ms, ms_e2e = times.tolist()
     if rank != 0:
         if world > 1 and emit:
-            torch.distributed.destroy_process_group()
+            torch.distributed.barrier()
+            finish(world)
         return None
     pk = peaks()
     sys.path.insert(0, os.path.join(ROOT, "profiles"))
@@ -692,7 +694,8 @@ def run_procgen(args, emit=True):
     if emit:
         print(json.dumps(line))
         if world > 1:
-            torch.distributed.destroy_process_group()
+            torch.distributed.barrier()
+        finish(world)
     return line
 
 
@@ -817,6 +820,15 @@ def run_reference(args):
                                     "every phase is linear in n_steps, so env-steps/s is the same quantity)"},
         "cpu_baseline": cpu,
         "e2e": {"value": round(value, 1), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def finish(world):
+    """Leave without tearing the NCCL communicator down: CUDA graphs that captured its all-reduce are still alive, and
+    destroy_process_group() then waits forever (observed on 2 GPUs).  Every rank has passed the last barrier."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
 
 
 def main():

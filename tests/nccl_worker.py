@@ -99,9 +99,12 @@ def main():
                       max_abs=float(np.abs(a - b).max()), scale=float(np.abs(b).max()),
                       rel_ok=bool(np.allclose(a, b, rtol=2e-4, atol=2e-6)),
                       loss=[summary["Loss/total"], s_ref["Loss/total"]])
-    json.dump(result, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
+    with open(os.path.join(out_dir, f"rank{rank}.json"), "w") as f:
+        json.dump(result, f)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)       # (no destroy_process_group: CUDA graphs that captured the all-reduce are still alive)
 
 
 if __name__ == "__main__":
