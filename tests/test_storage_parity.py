@@ -29,8 +29,11 @@ def test_gae_bit_exact_against_golden(golden_dir):
     np.testing.assert_allclose(st.adv_batch.cpu().numpy(), g["gae_adv_norm"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("T,N", [(1, 2), (7, 5), (256, 256), (64, 4099), (256, 65536)])
+@pytest.mark.parametrize("T,N", [(1, 2), (7, 5), (256, 256), (64, 4099), (256, 4096), (37, 8192), (16, 8200),
+                                 (720, 100), (256, 65536)])
 def test_gae_against_oracle(T, N):
+    """Returns bit-exact on both kernels: the shared-memory staged scan (N <= 8192 and T*512 B <= 200 KB: the PPO
+    configs) and the streaming thread-per-env scan (the C3 sweep sizes; long rollouts)."""
     gen = torch.Generator().manual_seed(T * 1000 + N)
     rew = torch.randn(T, N, generator=gen)
     value = torch.randn(T + 1, N, generator=gen)

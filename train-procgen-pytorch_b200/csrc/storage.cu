@@ -86,6 +86,99 @@ __global__ void __launch_bounds__(128) gae_kernel(const float* __restrict__ rew,
   }
 }
 
+// Small env counts (the PPO configs themselves: N = 256 .. 4096 per GPU).  With one thread per env there are too few
+// threads to cover the load latency of 256 dependent batches (measured 20.7 us at T = 256, N = 4096, 0.19 of HBM peak).
+// Here a CTA owns 32 envs and splits the work by what is parallel and what is not:
+//   1. all 8 warps stage the env columns of rew / done / value for ALL T steps in shared memory (coalesced 128-byte rows,
+//      every load in flight at once) and turn them into delta[t] = (rew + (gamma * V[t+1]) * (1 - done)) - V[t];
+//   2. warp 0 walks the only sequential part, A = ((gamma*lambda) * A) * (1 - done) + delta -- three dependent fp32
+//      operations per step, operands streamed from shared memory, nothing else on the chain;
+//   3. all warps write adv / ret (= A + V) rows back and accumulate the moments.
+// Every value is produced by the SAME non-fused fp32 operations in the reference's order, so raw advantages and returns
+// stay bit-identical to torch CPU (an affine-map warp scan over time would re-associate the products; the sequential chain
+// is ~2 us, it is not what made the small case slow).
+__global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                         const float* __restrict__ value, float* __restrict__ adv,
+                                                         float* __restrict__ ret, double* moments, int T, int N,
+                                                         int64_t ld, float gamma, float gl) {
+  extern __shared__ __align__(16) uint8_t gae_sm[];
+  __shared__ double red[32];
+  float* sdl = reinterpret_cast<float*>(gae_sm);           // [T][32]   rewards -> delta
+  float* sv = sdl + (size_t)T * 32;                        // [T+1][32] values
+  float* sa = sv + (size_t)(T + 1) * 32;                   // [T][32]   advantages
+  float* snd = sa + (size_t)T * 32;                        // [T][32]   1 - done
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const bool on = e < N;
+  // staging: cp.async moves rew / value rows global -> shared without passing through registers, so all 2 T row copies
+  // of the CTA are in flight together (a load -> store loop keeps only a few rows per warp in flight: ~1 us per batch)
+  if (on) {
+    for (int t = warp; t < T; t += 8) {
+      const int64_t o = (int64_t)t * ld + e;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sdl + t * 32 + lane)),
+                   "l"(rew + o) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + t * 32 + lane)),
+                   "l"(value + o) : "memory");
+    }
+    if (warp == 0)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + T * 32 + lane)),
+                   "l"(value + (int64_t)T * ld + e) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 8
+  for (int t = warp; t < T; t += 8)
+    snd[t * 32 + lane] = on ? 1.0f - (float)__ldcs(done + (int64_t)t * ld + e) : 0.0f;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (on)
+    for (int t = warp; t < T; t += 8) {
+      const float nd = snd[t * 32 + lane];
+      sdl[t * 32 + lane] = __fsub_rn(__fadd_rn(sdl[t * 32 + lane], __fmul_rn(__fmul_rn(gamma, sv[(t + 1) * 32 + lane]), nd)),
+                                     sv[t * 32 + lane]);
+    }
+  __syncthreads();
+  if (warp == 0) {
+    // batches of 16 steps: operands into registers, the dependent chain on registers, results out (the compiler does
+    // not move shared-memory loads across the stores of the previous step, which put a 30-cycle round trip on the chain)
+    float A = 0.0f;
+    for (int t0 = T - 1; t0 >= 0; t0 -= 16) {
+      float nd[16], dl[16], a[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int t = t0 - u;
+        nd[u] = t >= 0 ? snd[t * 32 + lane] : 0.0f;
+        dl[u] = t >= 0 ? sdl[t * 32 + lane] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        A = __fadd_rn(__fmul_rn(__fmul_rn(gl, A), nd[u]), dl[u]);
+        a[u] = A;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (t0 - u >= 0) sa[(t0 - u) * 32 + lane] = a[u];
+    }
+  }
+  __syncthreads();
+  double s1 = 0.0, s2 = 0.0;
+  if (on)
+    for (int t = warp; t < T; t += 8) {
+      const int64_t o = (int64_t)t * ld + e;
+      const float A = sa[t * 32 + lane];
+      __stcs(adv + o, A);
+      __stcs(ret + o, __fadd_rn(A, sv[t * 32 + lane]));
+      s1 += (double)A;
+      s2 += (double)A * (double)A;
+    }
+  s1 = block_sum(s1, red);
+  s2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(moments + 0, s1);
+    atomicAdd(moments + 1, s2);
+    if (blockIdx.x == 0) atomicAdd(moments + 2, (double)T * (double)N);
+  }
+}
+
 __global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const double* moments, int T, int N,
                                                             int64_t ld) {
   // grid = (column chunks, T): no per-element div/mod; 128-bit accesses when the row allows it
@@ -226,6 +319,18 @@ extern "C" int tpp_gae(const float* rew, const uint8_t* done, const float* value
   TPP_CHECK_ARG(rew && done && value && adv && ret && moments && T > 0 && N > 0 && ld >= N);
   // (gamma*lambda) is formed in double and rounded once, as python does before it meets the fp32 tensor
   const float gl = (float)((double)gamma * (double)lambda);
+  const size_t staged = ((size_t)T * 4 + 1) * 32 * 4;          // shared memory of the staged kernel (32 envs per CTA)
+  if (N <= 8192 && staged <= 200 * 1024) {      // (beyond ~2 CTAs per SM the streaming kernel is faster: measured)
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(tpp::gae_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    tpp::gae_staged_kernel<<<tpp_ceil_div(N, 32), 256, staged, tpp_stream(stream)>>>(rew, done, value, adv, ret, moments, T,
+                                                                                    N, ld, gamma, gl);
+    TPP_LAUNCH_STATUS();
+  }
   const int grid = tpp_ceil_div(N, 128);
   tpp::gae_kernel<8><<<grid, 128, 0, tpp_stream(stream)>>>(rew, done, value, adv, ret, moments, T, N, ld, gamma, gl);
   TPP_LAUNCH_STATUS();
