@@ -73,6 +73,33 @@ def test_fused_rollout_policy_on_pixel_rows(N):
     assert len(torch.unique(act)) == A and (logp <= 0).all()
 
 
+@pytest.mark.parametrize("N", [4096, 77])
+def test_fused_rollout_policy_on_uint8_frames(N):
+    """The uint8 NHWC frames themselves as the first-layer operand (weight columns in frame byte order): same logits as
+    the float NCHW / 255 contract of TransposeFrame + ScaledFloatFrame (common/env/procgen_wrappers.py:391-419)."""
+    from tpp_b200.common.engine import MLPEngineTC
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    A, shape = 4, (3, 14, 14)
+    torch.manual_seed(12)
+    pol = CategoricalPolicy(MLPModel(588, 4, 256, 64), False, A).to("cuda").flatten_()
+    with torch.no_grad():
+        pol.flat.add_(0.02 * torch.randn_like(pol.flat))
+        pol.fc_policy.weight.mul_(30.0)
+    eng = MLPEngineTC(pol, A, raw_pixels=True, obs_shape=shape)
+    assert eng.w0_bytes is not None
+    g = torch.Generator().manual_seed(N)
+    frames = torch.randint(0, 256, (N, 14, 14, 3), generator=g, dtype=torch.uint8).cuda()
+    act, logp, value = (torch.zeros(N, dtype=torch.int32, device="cuda"), torch.zeros(N, device="cuda"),
+                        torch.zeros(N, device="cuda"))
+    head = torch.zeros(N, eng.ld_head, device="cuda")
+    tick = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.rollout_fused(frames, N, 588, "u8", act, logp, value, 1, tick, 0, head_out=head)
+    torch.cuda.synchronize()
+    x = frames.permute(0, 3, 1, 2).reshape(N, -1).double().cpu() / 255.0        # NCHW flatten / 255
+    _check(head[:, :A + 1], _ref_head(pol, x))
+
+
 @pytest.mark.parametrize("N,n_obs,A", [(256, 9, 2), (4096, 14, 3), (100, 5, 3)])
 def test_fused_rollout_policy_on_feature_major_slots(N, n_obs, A):
     """Vector envs (cartpole / acrobot / mountain car): the layer-1 operand is the feature-major rollout slot."""

@@ -170,7 +170,8 @@ class PPO(BaseAgent):
                 # image observations reach the first layer as integer pixel values (exact in TF32: no lo half, two
                 # MMA passes) with ScaledFloatFrame's 1/255 folded into the layer's weight copy
                 self.engine = MLPEngineTC(policy, self.n_actions, precision=3 if self.matmul == "tf32x3" else 1,
-                                          raw_pixels=bool(getattr(storage, "is_image", False)))
+                                          raw_pixels=bool(getattr(storage, "is_image", False)),
+                                          obs_shape=getattr(storage, "obs_shape", None))
         elif isinstance(policy.embedder, ImpalaModel):
             # IMPALA convolutions as implicit GEMMs on the tcgen05 kernel (TMA im2col)
             self.engine = ImpalaEngineTC(policy, self.n_actions, storage.obs_shape,
@@ -244,7 +245,11 @@ class PPO(BaseAgent):
         if self.fused_rollout and isinstance(eng, MLPEngineTC):
             raw = bool(storage.is_image and eng.raw_pixels)
             if eng.fused_rollout_ok(raw) and (raw or not storage.is_image):
-                if raw:          # pixel rows of the slot: written by the env's step kernel, or converted here
+                if raw and eng.w0_bytes is not None and storage.obs_width <= 768 and storage.obs_width % 4 == 0:
+                    # the uint8 frames of the slot ARE the first-layer operand (no TransposeFrame / float copy at all)
+                    eng.rollout_fused(storage.obs_slot(t)[lo:hi], n, storage.obs_width, "u8", act, logp, value,
+                                      self.sample_seed, self._tick, t, off)
+                elif raw:        # pixel rows of the slot: written by the env's step kernel, or converted here
                     c, h, w = storage.obs_shape
                     mb = storage.minibatch_buffers(n, *self._obs_buf_args(storage), slot=slot)
                     if not obs_ready:
@@ -610,8 +615,11 @@ class PPO(BaseAgent):
         ranges = self._env_ranges(env, storage)
         # envs that can emit the policy's next input rows from their step kernel (Box-World, raw-pixel first layer)
         # save the frames -> obs launch of every step: only slot 0 is converted here
+        u8_direct = (self.fused_rollout and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels
+                     and self.engine.fused_rollout_ok(True) and getattr(self.engine, "w0_bytes", None) is not None
+                     and storage.obs_width <= 768 and storage.obs_width % 4 == 0)
         fold = (len(ranges) == 1 and getattr(env, "emits_policy_obs", False) and storage.is_image
-                and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels)
+                and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels and not u8_direct)
         if fold:
             mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
             assert mb.raw and mb.obs_lo is None

@@ -156,7 +156,7 @@ class MLPEngineTC(MLPEngine):
     the CUDA-core kernel: they are < 1 % of the FLOPs.
     """
 
-    def __init__(self, policy, n_actions, precision=3, raw_pixels=False):
+    def __init__(self, policy, n_actions, precision=3, raw_pixels=False, obs_shape=None):
         super().__init__(policy, n_actions)
         assert precision in (1, 3)
         self.precision = precision
@@ -184,6 +184,15 @@ class MLPEngineTC(MLPEngine):
             fin, fout, ldk = self.layers[0][2], self.layers[0][3], self.w[0]["ldk"]
             self.w0_scaled = torch.zeros(fout, fin, **f)
             self.w0_raw = dict(hi=torch.zeros(fout, ldk, **f), lo=torch.zeros(fout, ldk, **f), ldk=ldk)
+            # the same weights with their columns in FRAME BYTE ORDER (NHWC: byte p*C + c <-> feature c*H*W + p): the
+            # fused rollout kernel then reads a uint8 frame as its first-layer operand without TransposeFrame
+            self.w0_bytes = None
+            if obs_shape is not None and len(obs_shape) == 3 and int(obs_shape[0] * obs_shape[1] * obs_shape[2]) == fin:
+                c, h, w = (int(v) for v in obs_shape)
+                b = torch.arange(fin, device=self.device)
+                self._byte_perm = (b % c) * (h * w) + b // c
+                self.w0_bytes_plain = torch.zeros(fout, fin, **f)
+                self.w0_bytes = dict(hi=torch.zeros(fout, ldk, **f), lo=torch.zeros(fout, ldk, **f), ldk=ldk)
         self.refresh_weights()
 
     # ------------------------------------------------------------------------------------------
@@ -202,6 +211,11 @@ class MLPEngineTC(MLPEngine):
             _lib.call("tpp_split_tf32", _lib.ptr(self.w0_scaled), fin, fout, fin, _lib.ptr(self.w0_raw["hi"]),
                       _lib.ptr(self.w0_raw["lo"]), self.w0_raw["ldk"], None, None, 0, s)
             self.n_launches += 1
+            if self.w0_bytes is not None:
+                torch.index_select(self.w0_scaled, 1, self._byte_perm, out=self.w0_bytes_plain)
+                _lib.call("tpp_split_tf32", _lib.ptr(self.w0_bytes_plain), fin, fout, fin, _lib.ptr(self.w0_bytes["hi"]),
+                          _lib.ptr(self.w0_bytes["lo"]), self.w0_bytes["ldk"], None, None, 0, s)
+                self.n_launches += 1
 
     def _workspace(self, M, slot=0):
         ws = self._ws.get((M, slot))
@@ -270,13 +284,14 @@ class MLPEngineTC(MLPEngine):
 
     def rollout_fused(self, x, M, ldx, raw, act, logp, value, seed, tick, t_offset, env_offset=0, greedy=False,
                       head_out=None, dbg=None):
-        """One launch: whole forward + heads + action draw for M rows (csrc/rollout_fused.cu).  ``raw``: x = row-major
-        integer pixel rows [M][ldx] (exact TF32 operand, 1/255 folded into the first layer's weight copy); otherwise x = a
-        feature-major rollout slot [in_dim][ldx]."""
+        """One launch: whole forward + heads + action draw for M rows (csrc/rollout_fused.cu).  ``raw``: True = x is
+        row-major integer pixel rows [M][ldx] fp32 (exact TF32 operand, 1/255 folded into the first layer's weight
+        copy); "u8" = x is the uint8 NHWC frames [M][ldx bytes] themselves (weight columns in frame byte order);
+        False = x is a feature-major rollout slot [in_dim][ldx]."""
         f = _lib.FusedPolicy()
-        f.n_rows, f.a1_mode, f.x, f.ldx = M, 0 if raw else 1, x.data_ptr(), ldx
+        f.n_rows, f.a1_mode, f.x, f.ldx = M, {True: 0, False: 1, "u8": 2}[raw], x.data_ptr(), ldx
         for i, (w_off, b_off, fin, fout, relu) in enumerate(self.layers):
-            w = self.w0_raw if (raw and i == 0) else self.w[i]
+            w = (self.w0_bytes if raw == "u8" else self.w0_raw) if (raw and i == 0) else self.w[i]
             f.w_hi[i], f.w_lo[i], f.ldw[i] = w["hi"].data_ptr(), w["lo"].data_ptr(), w["ldk"]
             f.k[i], f.n[i], f.relu[i] = fin, fout, 1 if relu else 0
             f.bias[i] = self.flat.data_ptr() + 4 * b_off

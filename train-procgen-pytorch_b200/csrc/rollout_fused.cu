@@ -56,8 +56,9 @@ struct Params {
   int nout[NL];              // output width per layer: 256 / 256 / 256 / 64
   const float* bias[NL];
   int relu[NL];
-  int a1_mode;               // 0: TMA rows, exact operand; 1: feature-major slot, split in the kernel
-  const float* x; long long ldx; int n_obs;
+  int a1_mode;               // 0: TMA rows, exact operand; 1: feature-major slot, split in the kernel;
+                             // 2: uint8 frames (K order = byte order), converted by the epilogue threads per k-block
+  const float* x; long long ldx; int n_obs;      // mode 2: x = uint8 frames, ldx = bytes per frame, n_obs = bytes used
   const float* head_w; const float* head_b; int A;
   int32_t* act; float* logp; float* value; float* head_out; int ld_head;
   uint64_t seed; const uint64_t* tick; uint64_t t_offset; int greedy; int env_offset;
@@ -135,7 +136,8 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
   uint64_t* inbox_late = bars + 21;   // my pair mate's
   uint64_t* inbox_all = bars + 22;    // last layer, CTA 0: all three peers'
   uint64_t* tile_done = bars + 23;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* a_tile_full = bars + 24;  // [2], mode 2: the epilogue threads have written big stage s's A tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
   const CUtensorMap* tmw[NL][2] = {{&tmW0h, &tmW0l}, {&tmW1h, &tmW1l}, {&tmW2h, &tmW2l}, {&tmW3h, &tmW3l}};
 
   if (warp == 0 && lane == 0) {
@@ -160,6 +162,8 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     mbar_init(inbox_late, EPI_WARPS);
     mbar_init(inbox_all, 3 * EPI_WARPS);
     mbar_init(tile_done, EPI_THREADS);
+    mbar_init(a_tile_full, EPI_THREADS);
+    mbar_init(a_tile_full + 1, EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -223,10 +227,11 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         for (int kb = 0; kb < nkb0; ++kb, ++big_it) {
           const int s = big_it % BIG_STAGES;
           mbar_wait(big_full + s, (uint32_t)((big_it / BIG_STAGES) & 1));
+          if (p.a1_mode == 2) mbar_wait(a_tile_full + s, (uint32_t)((big_it / BIG_STAGES) & 1));
           tc_fence_after();
           if (lane == 0) {
             const uint32_t st = smem_u32(smem + OFF_R + s * BIG_STAGE);
-            const uint32_t a_hi = p.a1_mode == 0 ? st : smem_u32(smem + OFF_Y), a_lo = a_hi + TILE;
+            const uint32_t a_hi = p.a1_mode != 1 ? st : smem_u32(smem + OFF_Y), a_lo = a_hi + TILE;
             const uint32_t b_hi = st + TILE, b_lo = st + 3 * TILE;
             bool first = kb == 0;
             for (int pass = (p.a1_mode == 1 ? 2 : 1); pass >= 0; --pass) {
@@ -288,7 +293,7 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     uint8_t* my_slots = p.scratch + ((size_t)cluster_id * CL + rank) * (CL - 1) * SLOT_BYTES;   // where peers write for me
     uint32_t acc_ph[2] = {0u, 0u}, ie_ph = 0, il_ph = 0, ia_ph = 0;
     int pf_sig = 0, pf_wait = 0;             // peer_free signals sent / waits done (barrier = count & 1, parity = count >> 1)
-    int titer = 0;
+    int titer = 0, big_it_e = 0;
     auto signal_peer_free = [&]() {          // this warp's part of MY exchange slots may be overwritten
       __syncwarp();                          // (its loads have returned: their values were consumed before this point)
       if (lane == 0) {
@@ -376,6 +381,37 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(a1_full);
+      }
+      if (p.a1_mode == 2) {
+        // layer-1 operand straight from the uint8 frame: this CTA's k-slice is a contiguous byte range of the frame (the
+        // first layer's weight columns are stored in frame byte order), 16 bytes per thread and k-block; converted to the
+        // exact fp32 pixel values and written into the A slot of the big stage its weight k-block streams into
+        const uint8_t* fr = reinterpret_cast<const uint8_t*>(p.x) + (long long)grow * p.ldx;
+        uint32_t px[6][4];
+#pragma unroll
+        for (int kb = 0; kb < 6; ++kb)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int b0 = (int)rank * p.ks[0] + kb * BLOCK_K + 16 * ch + 4 * w;
+            px[kb][w] = (kb < nkb0 && grow < p.M && b0 < p.n_obs) ? __ldg(reinterpret_cast<const uint32_t*>(fr + b0)) : 0u;
+          }
+#pragma unroll
+        for (int kb = 0; kb < 6; ++kb) {
+          if (kb < nkb0) {
+            const int it = big_it_e + kb, s = it % BIG_STAGES;
+            mbar_wait(big_empty + s, (uint32_t)(((it / BIG_STAGES) & 1) ^ 1));
+            uint8_t* a_t = smem + OFF_R + s * BIG_STAGE;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const uint32_t v = px[kb][w];
+              *reinterpret_cast<float4*>(a_t + tile_off(row, 4 * ch + w)) =
+                  make_float4((float)(v & 255u), (float)((v >> 8) & 255u), (float)((v >> 16) & 255u), (float)(v >> 24));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(a_tile_full + s);
+          }
+        }
+        big_it_e += nkb0;
       }
       signal_peer_free();      // (layer 1 of this tile) my slots were consumed in the previous tile
       for (int l = 0; l < NL; ++l) {
@@ -522,7 +558,7 @@ extern "C" int tpp_policy_rollout_fused(const tpp_fused_policy* f, void* stream)
   using namespace tpp::fused;
   TPP_CHECK_ARG(f && f->x && f->n_rows > 0 && f->act && f->logp && f->value && f->head_w && f->head_b);
   TPP_CHECK_ARG(f->n_actions > 0 && f->n_actions + 1 <= tpp::MAX_A + 1 && f->n_actions <= tpp::MAX_A);
-  TPP_CHECK_ARG(f->a1_mode == 0 || f->a1_mode == 1);
+  TPP_CHECK_ARG(f->a1_mode >= 0 && f->a1_mode <= 2);
   for (int l = 0; l < NL; ++l) TPP_CHECK_ARG(f->w_hi[l] && f->w_lo[l] && f->bias[l] && f->k[l] > 0 && f->ldw[l] >= f->k[l]);
   // shapes this kernel is built for: depth-4 MLPModel, hidden width 256, latent 64 (the reference's mlpmodel sets)
   if (f->n[0] != 256 || f->n[1] != 256 || f->n[2] != 256 || f->n[3] != 64) return TPP_ENOTSUP;
@@ -537,6 +573,8 @@ extern "C" int tpp_policy_rollout_fused(const tpp_fused_policy* f, void* stream)
     p.relu[l] = f->relu[l];
   }
   if (f->a1_mode == 1 && p.ks[0] != 32) return TPP_ENOTSUP;      // feature-major slots: n_obs <= 128
+  if (f->a1_mode == 2 && (p.ks[0] > 6 * 32 || (f->k[0] & 3) || (f->ldx & 3) || (reinterpret_cast<uintptr_t>(f->x) & 3)))
+    return TPP_ENOTSUP;                                            // uint8 frames: <= 768 bytes, word-aligned
   TPP_CHECK_ARG(f->scratch);
   p.a1_mode = f->a1_mode; p.x = f->x; p.ldx = f->ldx; p.n_obs = f->k[0];
   p.head_w = f->head_w; p.head_b = f->head_b; p.A = f->n_actions;
