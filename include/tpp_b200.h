@@ -362,6 +362,8 @@ typedef struct {
   int32_t* act; float* logp; float* value; float* head_out;
   uint64_t seed; const uint64_t* tick; uint64_t t_offset; int32_t greedy, env_offset;
   void* dbg;      /* nullable: int64 [4][64] clock64 timeline of cluster 0 (profiles/fused_rollout_timeline.py)     */
+  int32_t no_pdl, _pad;                   /* != 0: plain stream order (default: programmatic dependent launch -- the
+                                             kernel's prologue and weight prefetch overlap the tail of the previous one) */
   void* scratch; int64_t scratch_bytes;   /* exchange slots of the clusters (device memory, stays in L2): 384 KB per
                                              128 envs processed concurrently; 33 x 384 KB covers a full B200            */
 } tpp_fused_policy;

@@ -65,7 +65,8 @@ class FusedPolicy(C.Structure):   # mirrors tpp_fused_policy
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("n_actions", C.c_int32), ("ld_head", C.c_int32),
                 ("act", C.c_void_p), ("logp", C.c_void_p), ("value", C.c_void_p), ("head_out", C.c_void_p),
                 ("seed", C.c_uint64), ("tick", C.c_void_p), ("t_offset", C.c_uint64), ("greedy", C.c_int32),
-                ("env_offset", C.c_int32), ("dbg", C.c_void_p), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
+                ("env_offset", C.c_int32), ("dbg", C.c_void_p), ("no_pdl", C.c_int32), ("_pad", C.c_int32),
+                ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
 
 
 FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "lunar_lander": 4}

@@ -31,8 +31,10 @@ using namespace tpp::tc;
 
 constexpr int CL = 4;                       // CTAs per cluster = K split
 constexpr int NL = 4;                       // dense layers of the embedder
-constexpr int EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = 64 + EPI_THREADS;   // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: epilogue (2 threads per row)
+constexpr int TPR = 2;                      // epilogue threads per accumulator row (4: measured slower, 38.7 vs 36.5 us)
+constexpr int CW = 64 / TPR, NCH = CW / 4;  // fp32 columns / 16-byte chunks of a 64-column slice per thread
+constexpr int EPI_WARPS = 4 * TPR, EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;   // warp 0: TMA, warp 1: MMA + TMEM, then the epilogue warps (TPR threads per row)
 constexpr int TILE = BLOCK_M * BLOCK_K * 4; // bytes of one [128][32] fp32 operand tile
 // Region R (160 KB): the TMA ring.  Layer 1 uses it as 2 big stages [A tile 16 KB][W hi 32 KB][W lo 32 KB] (one k-block,
 // all 256 output columns); layers 2..4 as 5 small stages [W hi 16 KB][W lo 16 KB] (one k-block of one 128-column half:
@@ -182,6 +184,7 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++titer) {
         const int row0 = tile * BLOCK_M;
         if (titer > 0) mbar_wait(tile_done, (uint32_t)((titer - 1) & 1));     // every small stage has been consumed
+        if (titer == 0 && p.a1_mode == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // (A rows come from the env kernel)
         for (int kb = 0; kb < nkb0; ++kb, ++big_it) {
           const int s = big_it % BIG_STAGES;
           mbar_wait(big_empty + s, (uint32_t)(((big_it / BIG_STAGES) & 1) ^ 1));
@@ -312,15 +315,18 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       acc_ph[h] ^= 1u;
       tc_fence_after();
     };
-    // my 32 columns of the 64-column slice starting at accumulator column col0 -> slot `slot` of CTA `dst_rank`
+    auto tmem_ld_cw = [&](uint32_t taddr, float* v) {
+      if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+    };
+    // my CW columns of the 64-column slice starting at accumulator column col0 -> slot `slot` of CTA `dst_rank`
     // (st.global, L2-resident; a warp instruction writes 512 contiguous bytes), then the release-arrive on its barrier
     auto send_slice = [&](uint32_t col0, uint32_t dst_rank, int slot) {
-      float v[32];
-      tmem_ld32(t_row + col0 + (uint32_t)(32 * ch), v);
+      float v[CW];
+      tmem_ld_cw(t_row + col0 + (uint32_t)(CW * ch), v);
       uint8_t* dst = p.scratch + (((size_t)cluster_id * CL + dst_rank) * (CL - 1) + slot) * SLOT_BYTES;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st_global_v4(dst + slot_off(row, 8 * ch + j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < NCH; ++j)
+        st_global_v4(dst + slot_off(row, NCH * ch + j), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     };
     // publish this warp's stores to the CTAs in `mask`: warp barrier, ONE cluster-scope fence by lane 0, relaxed arrives
     auto publish = [&](uint32_t mask, uint64_t* bar) {
@@ -334,24 +340,21 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     };
     // acc[32] += the partials of my 32 columns in slots [s0, s0 + n) (16-byte L2 loads, all in flight together)
     auto gather_slots = [&](float* acc, int s0, int n) {
+      float4 t[3][NCH];
 #pragma unroll
-      for (int j0 = 0; j0 < 8; j0 += 4) {
-        float4 t[3][4];
+      for (int k = 0; k < 3; ++k)
+        if (k < n)
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < n)
+          for (int j = 0; j < NCH; ++j)
+            t[k][j] = ld_global_cg_v4(my_slots + ((s0 + k) % 3) * SLOT_BYTES + slot_off(row, NCH * ch + j));
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              t[k][j] = ld_global_cg_v4(my_slots + ((s0 + k) % 3) * SLOT_BYTES + slot_off(row, 8 * ch + j0 + j));
+      for (int k = 0; k < 3; ++k)
+        if (k < n)
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < n)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              acc[4 * (j0 + j)] += t[k][j].x; acc[4 * (j0 + j) + 1] += t[k][j].y;
-              acc[4 * (j0 + j) + 2] += t[k][j].z; acc[4 * (j0 + j) + 3] += t[k][j].w;
-            }
-      }
+          for (int j = 0; j < NCH; ++j) {
+            acc[4 * j] += t[k][j].x; acc[4 * j + 1] += t[k][j].y;
+            acc[4 * j + 2] += t[k][j].z; acc[4 * j + 3] += t[k][j].w;
+          }
     };
     // slot of source s at destination d: ((s - d) mod 4) - 1.  My pair mate's slot, and the first of the other two
     const uint32_t mate = rank ^ 1u;
@@ -359,6 +362,9 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     const bool probe = p.dbg && cluster_id == 0 && warp == 2 && lane == 0;
 #define FPROBE(l, i) do { if (probe) p.dbg[rank * 64 + (l) * 8 + (i)] = clock64(); } while (0)
     if (probe) p.dbg[rank * 64 + 32] = clock64();
+    // programmatic dependent launch: everything above (barriers, TMEM, the weight stream of layer 1) may run while the
+    // previous kernel of the stream (the env's step) is still finishing; its outputs are first touched below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int tile = cluster_id; tile < p.n_tiles; tile += n_clusters, ++titer) {
       const int grow = tile * BLOCK_M + row;
       if (p.a1_mode == 1) {
@@ -366,8 +372,8 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         uint8_t* hi_t = smem + OFF_Y;
         uint8_t* lo_t = hi_t + TILE;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = 4 * ch + cc;
+        for (int cc = 0; cc < 8 / TPR; ++cc) {
+          const int c = (8 / TPR) * ch + cc;
           float v[4], h[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -384,15 +390,16 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       }
       if (p.a1_mode == 2) {
         // layer-1 operand straight from the uint8 frame: this CTA's k-slice is a contiguous byte range of the frame (the
-        // first layer's weight columns are stored in frame byte order), 16 bytes per thread and k-block; converted to the
+        // first layer's weight columns are stored in frame byte order), 32 / TPR bytes per thread and k-block; converted to the
         // exact fp32 pixel values and written into the A slot of the big stage its weight k-block streams into
         const uint8_t* fr = reinterpret_cast<const uint8_t*>(p.x) + (long long)grow * p.ldx;
-        uint32_t px[6][4];
+        constexpr int WPT = 8 / TPR;            // 32-bit words (= 16-byte chunks of the tile) per thread and k-block
+        uint32_t px[6][WPT];
 #pragma unroll
         for (int kb = 0; kb < 6; ++kb)
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int b0 = (int)rank * p.ks[0] + kb * BLOCK_K + 16 * ch + 4 * w;
+          for (int w = 0; w < WPT; ++w) {
+            const int b0 = (int)rank * p.ks[0] + kb * BLOCK_K + 4 * WPT * ch + 4 * w;
             px[kb][w] = (kb < nkb0 && grow < p.M && b0 < p.n_obs) ? __ldg(reinterpret_cast<const uint32_t*>(fr + b0)) : 0u;
           }
 #pragma unroll
@@ -402,9 +409,9 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             mbar_wait(big_empty + s, (uint32_t)(((it / BIG_STAGES) & 1) ^ 1));
             uint8_t* a_t = smem + OFF_R + s * BIG_STAGE;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < WPT; ++w) {
               const uint32_t v = px[kb][w];
-              *reinterpret_cast<float4*>(a_t + tile_off(row, 4 * ch + w)) =
+              *reinterpret_cast<float4*>(a_t + tile_off(row, WPT * ch + w)) =
                   make_float4((float)(v & 255u), (float)((v >> 8) & 255u), (float)((v >> 16) & 255u), (float)(v >> 24));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -418,10 +425,10 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         FPROBE(l, 0);
         if (l < NL - 1) {
           // ---- reduce-scatter of the 128 x 256 partial: 64 columns per owner (owners 0, 1 in column half 0) ----
-          float own[32], bv[32];
-          const float* bias = p.bias[l] + rank * 64 + 32 * ch;
+          float own[CW], bv[CW];
+          const float* bias = p.bias[l] + rank * 64 + CW * ch;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) bv[j] = __ldg(bias + j);
+          for (int j = 0; j < CW; ++j) bv[j] = __ldg(bias + j);
           wait_peer_free();                    // the peers' slots are writable
           FPROBE(l, 2);
           wait_acc(0);                         // the other pair's half (layer 1: all 256 columns, one commit)
@@ -432,7 +439,7 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             publish(3u << other, inbox_early);
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) own[j] = 0.0f;
+          for (int j = 0; j < CW; ++j) own[j] = 0.0f;
           mbar_wait_cluster(inbox_early, ie_ph);     // the other pair computed MY half first: gather it under my MMAs
           ie_ph ^= 1u;
           gather_slots(own, early_slot0, 2);
@@ -441,10 +448,10 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
           send_slice(mate * 64, mate, (int)((rank - mate + CL) & 3) - 1);
           publish(1u << mate, inbox_late);
           {
-            float mine[32];
-            tmem_ld32(t_row + rank * 64 + (uint32_t)(32 * ch), mine);
+            float mine[CW];
+            tmem_ld_cw(t_row + rank * 64 + (uint32_t)(CW * ch), mine);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) own[j] += mine[j];
+            for (int j = 0; j < CW; ++j) own[j] += mine[j];
           }
           tc_fence_before();
           FPROBE(l, 3);
@@ -453,17 +460,18 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
           FPROBE(l, 4);
           gather_slots(own, late_slot, 1);
           const float floor_v = p.relu[l] ? 0.0f : -3.402823466e38f;
-          // my 32 columns = k-block `ch` of my A slice of the next layer: hi / lo swizzled tiles
-          uint8_t* hi_t = smem + OFF_Y + ch * 2 * TILE;
+          // my CW columns of my A slice of the next layer (k-block = column / 32): hi / lo swizzled tiles
+          uint8_t* hi_t = smem + OFF_Y + ((CW * ch) >> 5) * 2 * TILE;
+          const int c_in = ((CW * ch) & 31) >> 2;          // first 16-byte chunk inside the k-block's row
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < NCH; ++j) {
             float x[4], h[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               x[i] = fmaxf(own[4 * j + i] + bv[4 * j + i], floor_v);
               h[i] = tf32_round(x[i]);
             }
-            const uint32_t o = tile_off(row, j);
+            const uint32_t o = tile_off(row, c_in + j);
             *reinterpret_cast<float4*>(hi_t + o) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(hi_t + TILE + o) = make_float4(x[0] - h[0], x[1] - h[1], x[2] - h[2], x[3] - h[3]);
           }
@@ -474,20 +482,18 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         } else {
           // ---- last embedder layer (N = 64): every partial goes to CTA 0, which finishes the step ----
           const int nh = p.A + 1;
-          float wreg[(MAX_A + 1) * 64 / EPI_THREADS + 1];       // CTA 0: head weights, in flight during the waits
-          float bz[32], hb[MAX_A + 1];
+          float wreg[(MAX_A + 1) * 65 / EPI_THREADS + 1];       // CTA 0: head weights + biases, in flight during the waits
+          float bz[CW];
           uint64_t tick_v = 0;
           if (rank == 0) {
             tick_v = p.tick ? *p.tick : 0ull;          // (the draw's inputs: loaded now, used ~10 us of latency later)
 #pragma unroll
-            for (int j = 0; j < MAX_A + 1; ++j) hb[j] = j < nh ? __ldg(p.head_b + j) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < (MAX_A + 1) * 64 / EPI_THREADS + 1; ++i) {
+            for (int i = 0; i < (MAX_A + 1) * 65 / EPI_THREADS + 1; ++i) {
               const int idx = i * EPI_THREADS + (warp - 2) * 32 + lane;
-              wreg[i] = idx < nh * 64 ? __ldg(p.head_w + idx) : 0.0f;
+              wreg[i] = idx < nh * 64 ? __ldg(p.head_w + idx) : (idx < nh * 65 ? __ldg(p.head_b + idx - nh * 64) : 0.0f);
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) bz[j] = __ldg(p.bias[l] + 32 * ch + j);
+            for (int j = 0; j < CW; ++j) bz[j] = __ldg(p.bias[l] + CW * ch + j);
           }
           wait_peer_free();
           wait_acc(0);
@@ -497,16 +503,16 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             publish(1u, inbox_all);
             tc_fence_before();
           } else {
-            float z[32];
-            tmem_ld32(t_row + (uint32_t)(32 * ch), z);
+            float z[CW];
+            tmem_ld_cw(t_row + (uint32_t)(CW * ch), z);
             tc_fence_before();
             // head weights -> shared memory (region Y is free: this layer's MMAs have retired)
             float* sWh = reinterpret_cast<float*>(smem + OFF_Y);
-            float* sHp = sWh + (MAX_A + 1) * 64;                    // [2][128][MAX_A + 1] partial head sums
+            float* sHp = sWh + (MAX_A + 1) * 65;                    // [TPR][128][MAX_A + 1] partial head sums
 #pragma unroll
-            for (int i = 0; i < (MAX_A + 1) * 64 / EPI_THREADS + 1; ++i) {
+            for (int i = 0; i < (MAX_A + 1) * 65 / EPI_THREADS + 1; ++i) {
               const int idx = i * EPI_THREADS + (warp - 2) * 32 + lane;
-              if (idx < nh * 64) sWh[idx] = wreg[i];
+              if (idx < nh * 65) sWh[idx] = wreg[i];                  // [nh][64] weights, then the nh biases
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             mbar_wait_cluster(inbox_all, ia_ph);
@@ -515,13 +521,13 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
             gather_slots(z, 0, 3);
             const float floor_v = p.relu[l] ? 0.0f : -3.402823466e38f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = fmaxf(z[j] + bz[j], floor_v);
+            for (int j = 0; j < CW; ++j) z[j] = fmaxf(z[j] + bz[j], floor_v);
             FPROBE(l, 6);
             for (int j = 0; j < nh; ++j) {
               float a = 0.0f;
-              const float* w = sWh + j * 64 + 32 * ch;
+              const float* w = sWh + j * 64 + CW * ch;
 #pragma unroll
-              for (int k = 0; k < 32; ++k) a = fmaf(z[k], w[k], a);
+              for (int k = 0; k < CW; ++k) a = fmaf(z[k], w[k], a);
               sHp[(ch * BLOCK_M + row) * (MAX_A + 1) + j] = a;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -530,7 +536,13 @@ fused_policy_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
               float hd[MAX_A + 1];
 #pragma unroll
               for (int j = 0; j < MAX_A + 1; ++j)
-                hd[j] = j < nh ? hb[j] + (sHp[row * (MAX_A + 1) + j] + sHp[(BLOCK_M + row) * (MAX_A + 1) + j]) : 0.0f;
+                hd[j] = 0.0f;
+              for (int j = 0; j < nh; ++j) {
+                float a = 0.0f;
+#pragma unroll
+                for (int c = 0; c < TPR; ++c) a += sHp[(c * BLOCK_M + row) * (MAX_A + 1) + j];
+                hd[j] = sWh[nh * 64 + j] + a;
+              }
               if (p.head_out)
                 for (int j = 0; j < nh; ++j) p.head_out[(long long)grow * p.ld_head + j] = hd[j];
               sample_row(hd, p.A, p.env_offset + grow, p.seed, &tick_v, p.t_offset, p.greedy, p.act + grow, p.logp + grow,
@@ -622,10 +634,12 @@ extern "C" int tpp_policy_rollout_fused(const tpp_fused_policy* f, void* stream)
   cfg.blockDim = dim3(THREADS, 1, 1);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = tpp_stream(stream);
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // prologue + weight prefetch overlap the env kernel
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = f->no_pdl ? 1 : 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, fused_policy_kernel, tmA1, tmW[0][0], tmW[0][1], tmW[1][0], tmW[1][1],
                                      tmW[2][0], tmW[2][1], tmW[3][0], tmW[3][1], p);
   if (e != cudaSuccess) return (int)e;
