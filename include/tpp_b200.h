@@ -416,6 +416,21 @@ int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n, void* stre
  * Replaces agents/ppo.py:173-176 (torch.nn.utils.clip_grad_norm_, optim.Adam(eps=1e-5)).                 */
 int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n, void* stream);
 
+/* ---- multi-GPU: gradient all-reduce over peer memory, fused with the norm reduction ----------------------- */
+/* One-shot all-reduce of the flat gradient across `world` (<= 8) GPUs of one node + tpp_grad_sqnorm of the SUM, in one
+ * launch (csrc/peer_reduce.cu).  The sharded design's only collective: the sum of the per-rank gradients in front of
+ * clip_grad_norm_ + Adam (agents/ppo.py:173-176 under env sharding).
+ * staging_ptrs / pad_ptrs: HOST arrays [world] of device addresses as mapped into this process -- rank r's symmetric
+ * staging buffer (float [2][n_pad], double-buffered by launch parity) and rank r's signal pad (uint32 words; flags live at
+ * pad_offset + rank).  g_local [n]: this rank's gradient, copied out and ZEROED; g_reduced [n]: the sum in rank order
+ * (bit-identical on every rank); state->sqnorm[step & 1] += sum (grad_scale * g_reduced)^2.  epoch_counter / ticket2[2] /
+ * error_flag: zero-initialised device words owned by the caller (error_flag != 0: a peer never arrived).
+ * Every rank must issue the call in the same order; all CTAs of the launch are co-resident (<= 148).              */
+int tpp_peer_allreduce_sqnorm(const uint64_t* staging_ptrs, const uint64_t* pad_ptrs, int32_t rank, int32_t world,
+                              int32_t pad_offset, float* g_local, float* g_reduced, tpp_adam_state* state, int64_t n,
+                              int64_t n_pad, uint32_t* epoch_counter, uint32_t* ticket2, uint32_t* error_flag,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,9 @@ def fill(st, data, lo, hi):
 
 def main():
     out_dir = sys.argv[1]
-    use_graph = len(sys.argv) > 2 and sys.argv[2] == "graph"
+    mode = sys.argv[2] if len(sys.argv) > 2 else "eager"
+    use_graph = mode in ("graph", "nccl")          # "nccl": ncclAllReduce captured in the epoch graph instead of the
+    peer = mode != "nccl"                          # one-shot peer-memory all-reduce kernel
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     device = f"cuda:{local}"
@@ -57,8 +59,9 @@ def main():
     perms = [[torch.randperm(T * n_loc, generator=g) for _ in range(world)] for _ in range(epochs)]
 
     lo, hi = rank * n_loc, (rank + 1) * n_loc
-    agent, st = make_agent(T, n_loc, A, device, use_graph, mini_batch_size=mb_loc)
+    agent, st = make_agent(T, n_loc, A, device, use_graph, mini_batch_size=mb_loc, peer_reduce=peer)
     agent.shard(world)
+    assert (agent.optimizer.peer is not None) == peer
     fill(st, data, lo, hi)
     calls = {"e": 0}
 
@@ -73,6 +76,8 @@ def main():
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     in_sync = all(torch.equal(gathered[0], x) for x in gathered)
+    if agent.optimizer.peer is not None:
+        agent.optimizer.peer.check()
     result = {"rank": rank, "in_sync": bool(in_sync), "steps": agent.optimizer.step_count}
     if rank == 0:
         # the single-GPU run on the union: minibatch k = union over ranks of their minibatch k

@@ -1,4 +1,6 @@
-"""GPU, 2 ranks over NCCL (skipped with fewer than two devices): the PRODUCT kernels under env sharding.  torchrun is
+"""GPU, 2 ranks (skipped with fewer than two devices): the PRODUCT kernels under env sharding -- the one-shot gradient
+all-reduce over NVLink peer memory fused with the norm reduction (modes "eager" / "graph"), and ncclAllReduce captured in
+the epoch graph (mode "nccl").  torchrun is
 launched from inside pytest; tests/nccl_worker.py holds the body.  Stated tolerance: parameters after 2 epochs x 4
 optimizer steps agree with the single-GPU run on the union to rtol 2e-4 / atol 2e-6 (fp32 summation order of the
 gradient differs: per-rank partial sums + all-reduce vs one pass), advantages to 2e-6, replicas bit-identical."""
@@ -21,7 +23,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("mode", ["eager", "graph"])
+@pytest.mark.parametrize("mode", ["eager", "graph", "nccl"])
 def test_two_rank_sharded_optimize_equals_single_gpu_union(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")

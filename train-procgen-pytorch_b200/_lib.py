@@ -120,6 +120,7 @@ SIGNATURES = {
     "tpp_ppo_loss_fwd_bwd_grouped": [C.POINTER(LossCfg), _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_grad_sqnorm": [_vp, _vp, _i64, _vp],
     "tpp_adam_clip_step": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "tpp_peer_allreduce_sqnorm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
 }
 _NO_STATUS = {"tpp_version"}
 

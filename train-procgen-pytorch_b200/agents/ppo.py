@@ -55,6 +55,7 @@ class FlatAdam:
         self._i32 = self.state.view(torch.int32)      # step @10, ticket @11
         self._lr_on_device = lr
         self.n_launches = 0
+        self.peer = None          # parallel.PeerReducer under env sharding
 
     def set_grad_scale(self, s):
         self._f32[9:10].copy_(torch.tensor([s], dtype=torch.float32))
@@ -75,10 +76,17 @@ class FlatAdam:
         self.launch()
 
     def launch(self):
-        """The two kernels of a step (capturable in a CUDA graph; ``_sync_lr`` must have run outside the capture)."""
+        """The two kernels of a step (capturable in a CUDA graph; ``_sync_lr`` must have run outside the capture).  With a
+        peer reducer (env sharding on one node) the first one is the one-shot all-reduce over NVLink peer memory fused
+        with the norm reduction, and Adam runs on the reduced copy."""
         n, s = self.flat.numel(), _lib.stream_ptr()
-        _lib.call("tpp_grad_sqnorm", _lib.ptr(self.state), _lib.ptr(self.gflat), n, s)
-        _lib.call("tpp_adam_clip_step", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(self.gflat),
+        g = self.gflat
+        if self.peer is not None:
+            self.peer.launch(self.gflat, self.state)
+            g = self.peer.reduced
+        else:
+            _lib.call("tpp_grad_sqnorm", _lib.ptr(self.state), _lib.ptr(self.gflat), n, s)
+        _lib.call("tpp_adam_clip_step", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(g),
                   _lib.ptr(self.m), _lib.ptr(self.v), n, s)
         self.n_launches += 2
 
@@ -150,6 +158,7 @@ class PPO(BaseAgent):
         # sharded runs keep the whole-epoch graph: the per-step ncclAllReduce is captured with the kernels around it
         # (False: per-group graphs with the all-reduce launched from the host between them)
         self.graph_allreduce = bool(kwargs.get("graph_allreduce", True))
+        self.peer_reduce = bool(kwargs.get("peer_reduce", True))
 
         if policy.flat is None:
             policy.flatten_(device)
@@ -208,6 +217,17 @@ class PPO(BaseAgent):
                 st.sample_offset = getattr(st, "sample_offset", 0) % (2 * self.n_envs) + 2 * self.n_envs * rank
         self.world_size, self.process_group = world_size, process_group
         self.optimizer.set_grad_scale(1.0 / world_size)
+        # the step's only collective: one-shot all-reduce over NVLink peer memory fused with the norm reduction
+        # (``peer_reduce=False`` keeps ncclAllReduce, captured in the epoch graph)
+        if world_size > 1 and self.peer_reduce and torch.distributed.is_initialized() \
+                and torch.distributed.get_backend(process_group) == "nccl":
+            try:
+                self.optimizer.peer = parallel.PeerReducer(self.policy.flat.numel(), self.policy.flat.device,
+                                                           process_group)
+            except Exception as e:      # no peer-mapped (symmetric) memory on this system: NCCL does the sum instead
+                import sys
+                print(f"[tpp_b200] peer-memory all-reduce unavailable ({e!r}); using ncclAllReduce", file=sys.stderr)
+                self.optimizer.peer = None
         self.storage.world_size, self.storage.process_group = world_size, process_group
 
     # ------------------------------------------------------------------------------------------
@@ -426,7 +446,7 @@ class PPO(BaseAgent):
                 for i in range(n_grp):
                     group_body(idx_g[i], stats_g[i])
                     if ((i + 1) * G) % step_every == 0:
-                        if self.world_size > 1:    # NCCL all-reduce captured into the epoch graph (one replay per epoch)
+                        if self.world_size > 1 and self.optimizer.peer is None:   # NCCL all-reduce captured in the graph
                             parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
                         self.optimizer.launch()
                         if hasattr(engine, "refresh_weights"):
@@ -521,7 +541,7 @@ class PPO(BaseAgent):
                 self._stats[k:k + G].copy_(self._stats_cur)
                 k += G
                 if k % accum == 0:                 # k minibatches done this call (reference: cnt % accum, :173)
-                    if self.world_size > 1:
+                    if self.world_size > 1 and self.optimizer.peer is None:
                         parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
                     self.optimizer.step()
                     if hasattr(engine, "refresh_weights"):

@@ -64,3 +64,43 @@ def mean_std_from_moments(moments):
     mean = s / n
     var = max((ss - s * mean) / (n - 1.0), 0.0)
     return mean, var ** 0.5
+
+
+class PeerReducer:
+    """One-shot gradient all-reduce over NVLink peer memory fused with the gradient-norm reduction
+    (``tpp_peer_allreduce_sqnorm``, csrc/peer_reduce.cu): replaces ``ncclAllReduce`` + ``tpp_grad_sqnorm`` in front of the
+    clip + Adam kernel.  The staging buffers and signal pads are torch symmetric memory (peer-mapped allocations of
+    the ranks of ONE node); the pointers go through the C-ABI as plain addresses."""
+
+    PAD_OFFSET = 768          # our flags live behind the words torch's own symmetric-memory primitives use
+
+    def __init__(self, n, device, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("peer all-reduce covers the GPUs of one node (<= 8)")
+        self.n, self.n_pad = int(n), (int(n) + 3) // 4 * 4
+        self.staging = symm_mem.empty(2 * self.n_pad, dtype=torch.float32, device=device)
+        self.staging.zero_()
+        self.handle = symm_mem.rendezvous(self.staging, group)
+        if self.handle.signal_pad_size < 4 * (self.PAD_OFFSET + self.world):
+            raise RuntimeError("symmetric-memory signal pad too small")
+        self._staging_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self._pad_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self.handle.signal_pad_ptrs])
+        self.reduced = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.words = torch.zeros(8, dtype=torch.int32, device=device)      # [0] epoch, [2:4] tickets, [4] error flag
+        torch.cuda.synchronize()
+        dist.barrier(group)
+
+    def launch(self, g_local, adam_state):
+        from . import _lib
+        w = self.words.data_ptr()
+        _lib.call("tpp_peer_allreduce_sqnorm", self._staging_ptrs, self._pad_ptrs, self.rank, self.world,
+                  self.PAD_OFFSET, _lib.ptr(g_local), _lib.ptr(self.reduced), _lib.ptr(adam_state), self.n, self.n_pad,
+                  _lib.C.c_void_p(w), _lib.C.c_void_p(w + 8), _lib.C.c_void_p(w + 16), _lib.stream_ptr())
+
+    def check(self):
+        if int(self.words[4].item()) != 0:
+            raise RuntimeError("peer all-reduce: a rank never raised its flag (tpp_peer_allreduce_sqnorm timed out)")
