@@ -1,0 +1,80 @@
+"""Measured numerical error of the floating-point kernels against float64 evaluations of the same operations
+(round 2; feeds the tolerance table of DESIGN.md section 5).  err = max |x - x64| / max |x64| over the tensor."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tpp_b200.common.engine import MLPEngineTC  # noqa: E402
+from tpp_b200.common.model import MLPModel  # noqa: E402
+from tpp_b200.common.policy import CategoricalPolicy  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def main():
+    rows = []
+    torch.manual_seed(0)
+    for name, in_dim, raw, M in (("MLP 588-256-256-256-64 on pixel rows (Box-World), M=16384", 588, True, 16384),
+                                 ("MLP 9-256-256-256-64 (cartpole), M=4096", 9, False, 4096)):
+        A = 4
+        pol = CategoricalPolicy(MLPModel(in_dim, 4, 256, 64), False, A).to("cuda").flatten_()
+        with torch.no_grad():
+            pol.flat.add_(0.02 * torch.randn_like(pol.flat))
+        for prec in (3, 1):
+            eng = MLPEngineTC(pol, A, precision=prec, raw_pixels=raw)
+            if raw:
+                x = torch.zeros(M, eng.ld_in, device="cuda")
+                x[:, :in_dim] = torch.randint(0, 256, (M, in_dim), device="cuda").float()
+                x64 = (x[:, :in_dim].double() / 255.0)
+            else:
+                x = torch.randn(M, in_dim, device="cuda")
+                x64 = x.double()
+            head = eng.forward(x, M, raw=raw).clone()
+            dhead = torch.randn(M, eng.ld_head, device="cuda") / M
+            dhead[:, A + 1:] = 0
+            pol.flat_grad.zero_()
+            eng.backward(dhead, M)
+            g = pol.flat_grad.clone()
+            # float64 autograd of the same network
+            p64 = {k: v.detach().double().clone().requires_grad_(True) for k, v in pol.state_dict().items()}
+            names = sorted({k.rsplit(".", 1)[0] for k in p64 if k.startswith("embedder.")},
+                           key=lambda s: [int(t) if t.isdigit() else t for t in s.split(".")])
+            h = x64
+            for i, n in enumerate(names):
+                h = h @ p64[n + ".weight"].t() + p64[n + ".bias"]
+                if i < len(names) - 1:
+                    h = h.clamp_min(0)
+            out = torch.cat((h @ p64["fc_policy.weight"].t() + p64["fc_policy.bias"],
+                             h @ p64["fc_value.weight"].t() + p64["fc_value.bias"]), 1)
+            (out * dhead[:, :A + 1].double()).sum().backward()
+            g64 = torch.cat([p64[k].grad.reshape(-1) for k in pol.flat_order()])
+            rows.append((f"{name}, {'3xTF32' if prec == 3 else '1xTF32'}: logits + value", rel(head[:, :A + 1], out.detach())))
+            rows.append((f"{name}, {'3xTF32' if prec == 3 else '1xTF32'}: flat parameter gradient", rel(g, g64)))
+            if prec == 3 and eng.fused_rollout_ok(raw):
+                N = 4096
+                act = torch.zeros(N, dtype=torch.int32, device="cuda")
+                lp, vv = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+                ho = torch.zeros(N, eng.ld_head, device="cuda")
+                tick = torch.zeros(1, dtype=torch.int64, device="cuda")
+                if raw:
+                    eng.rollout_fused(x[:N], N, eng.ld_in, True, act, lp, vv, 0, tick, 0, head_out=ho)
+                else:
+                    xs = x[:N].t().contiguous()
+                    eng.rollout_fused(xs, N, N, False, act, lp, vv, 0, tick, 0, head_out=ho)
+                rows.append((f"{name}: fused rollout kernel logits + value (first 4096 rows)",
+                             rel(ho[:, :A + 1], out.detach()[:N])))
+    print("| quantity | max err / max |ref| vs float64 |")
+    print("|---|---:|")
+    for n, e in rows:
+        print(f"| {n} | {e:.2e} |")
+
+
+if __name__ == "__main__":
+    main()
