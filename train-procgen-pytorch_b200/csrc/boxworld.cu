@@ -247,69 +247,69 @@ __device__ __forceinline__ void copy_frame(const uint8_t* src, uint8_t* dst, int
   }
 }
 
-// One env's transition, executed by its warp: lane 0 resolves the move, the result (done) is broadcast.
-__device__ __forceinline__ int step_env(const tpp_boxworld_state& st, int e, int lane, const int32_t* __restrict__ action,
+// One env's transition by ONE thread: every byte it needs (action, position, counters, the target cell and its two
+// neighbours, the lock table entry, the owned key) is loaded before the move is resolved -- two dependent rounds of
+// global loads per env, and as many envs in flight as there are threads (the warp-per-env form kept 31 of 32 lanes
+// waiting behind lane 0's chain: 0.19 of HBM peak at 2^18 envs).  Returns the env's done flag.
+__device__ __forceinline__ int step_env(const tpp_boxworld_state& st, int e, const int32_t* __restrict__ action,
                                         int32_t* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                                         int32_t* fin_ret, int32_t* fin_len, uint8_t* fin_solved) {
   const int S = st.n + 2, cells = S * S;
   uint8_t* W = st.world + (int64_t)e * cells * 3;
   int done = 0;
-  if (lane == 0) {
-    const int8_t* D = st.world_dic + (int64_t)e * cells;
-    const int a = action[e];
-    const int pr = st.player_pos[2 * e], pc = st.player_pos[2 * e + 1];
-    const int nr = pr + (a == 0 ? -1 : (a == 1 ? 1 : 0)), nc = pc + (a == 2 ? -1 : (a == 3 ? 1 : 0));
-    const int steps = st.num_env_steps[e] + 1;
-    int reward = 0, solved = 0;
-    done = (steps == st.max_steps);
-    auto clampi = [&](int v) { return v < 0 ? 0 : (v > st.n + 1 ? st.n + 1 : v); };
-    const int ar = clampi(nr), ac = clampi(nc);
-    const int at = ar * S + ac, left = ar * S + clampi(nc - 1), right = ar * S + clampi(nc + 1);
-    const bool in_grid = nr > 0 && nc > 0 && nr <= st.n && nc <= st.n;
-    const uint8_t here[3] = {W[at * 3], W[at * 3 + 1], W[at * 3 + 2]};
-    const uint8_t lc[3] = {W[left * 3], W[left * 3 + 1], W[left * 3 + 2]};
-    const bool empty = px_is(here, C_GRID);
-    const bool left_clear = (nc == 1) || px_is(lc, C_GRID);
-    const bool first_key = !empty && left_clear && (px_is(W + right * 3, C_GRID) || px_is(W + right * 3, C_AGENT));
-    const int status = D[at];
-    const bool is_lock = status != -1;
-    uint8_t* own = st.owned_key + 4 * e;
-    const bool key_fits = own[0] == here[0] && own[0] != C_GRID && own[1] == here[1] && own[1] != C_GRID &&
-                          own[2] == here[2] && own[2] != C_GRID;
-    const bool blocked = !(empty || first_key || is_lock) || (is_lock && !key_fits);
-    if (in_grid && !blocked) {
-      const int cur = pr * S + pc;
-      const bool walk = empty, take = !walk && first_key, unlock = !walk && !take && is_lock && key_fits;
-      if (walk || take || unlock) {
-        W[cur * 3] = W[cur * 3 + 1] = W[cur * 3 + 2] = C_GRID;
-        if (unlock) W[left * 3] = W[left * 3 + 1] = W[left * 3 + 2] = C_GRID;
-        W[at * 3] = W[at * 3 + 1] = W[at * 3 + 2] = C_AGENT;
-        st.player_pos[2 * e] = nr;
-        st.player_pos[2 * e + 1] = nc;
-        if (take) {
-          W[0] = own[0] = here[0]; W[1] = own[1] = here[1]; W[2] = own[2] = here[2];
-          reward += 1;
-        }
-        if (unlock) {
-          W[0] = own[0] = lc[0]; W[1] = own[1] = lc[1]; W[2] = own[2] = lc[2];
-          const bool goal = px_is(lc, C_GOAL);
-          if (goal) { reward += 10; solved = 1; done = 1; }
-          if (status == 1) reward += 1;
-          if (status == 0) { reward -= 1; done = 1; }
-        }
+  const int8_t* D = st.world_dic + (int64_t)e * cells;
+  const int a = action[e];
+  const int pr = st.player_pos[2 * e], pc = st.player_pos[2 * e + 1];
+  const int nr = pr + (a == 0 ? -1 : (a == 1 ? 1 : 0)), nc = pc + (a == 2 ? -1 : (a == 3 ? 1 : 0));
+  const int steps = st.num_env_steps[e] + 1;
+  int reward = 0, solved = 0;
+  done = (steps == st.max_steps);
+  auto clampi = [&](int v) { return v < 0 ? 0 : (v > st.n + 1 ? st.n + 1 : v); };
+  const int ar = clampi(nr), ac = clampi(nc);
+  const int at = ar * S + ac, left = ar * S + clampi(nc - 1), right = ar * S + clampi(nc + 1);
+  const bool in_grid = nr > 0 && nc > 0 && nr <= st.n && nc <= st.n;
+  const uint8_t here[3] = {W[at * 3], W[at * 3 + 1], W[at * 3 + 2]};
+  const uint8_t lc[3] = {W[left * 3], W[left * 3 + 1], W[left * 3 + 2]};
+  const bool empty = px_is(here, C_GRID);
+  const bool left_clear = (nc == 1) || px_is(lc, C_GRID);
+  const bool first_key = !empty && left_clear && (px_is(W + right * 3, C_GRID) || px_is(W + right * 3, C_AGENT));
+  const int status = D[at];
+  const bool is_lock = status != -1;
+  uint8_t* own = st.owned_key + 4 * e;
+  const bool key_fits = own[0] == here[0] && own[0] != C_GRID && own[1] == here[1] && own[1] != C_GRID &&
+                        own[2] == here[2] && own[2] != C_GRID;
+  const bool blocked = !(empty || first_key || is_lock) || (is_lock && !key_fits);
+  if (in_grid && !blocked) {
+    const int cur = pr * S + pc;
+    const bool walk = empty, take = !walk && first_key, unlock = !walk && !take && is_lock && key_fits;
+    if (walk || take || unlock) {
+      W[cur * 3] = W[cur * 3 + 1] = W[cur * 3 + 2] = C_GRID;
+      if (unlock) W[left * 3] = W[left * 3 + 1] = W[left * 3 + 2] = C_GRID;
+      W[at * 3] = W[at * 3 + 1] = W[at * 3 + 2] = C_AGENT;
+      st.player_pos[2 * e] = nr;
+      st.player_pos[2 * e + 1] = nc;
+      if (take) {
+        W[0] = own[0] = here[0]; W[1] = own[1] = here[1]; W[2] = own[2] = here[2];
+        reward += 1;
+      }
+      if (unlock) {
+        W[0] = own[0] = lc[0]; W[1] = own[1] = lc[1]; W[2] = own[2] = lc[2];
+        const bool goal = px_is(lc, C_GOAL);
+        if (goal) { reward += 10; solved = 1; done = 1; }
+        if (status == 1) reward += 1;
+        if (status == 0) { reward -= 1; done = 1; }
       }
     }
-    const int ep = st.episode_reward[e] + reward;
-    st.num_env_steps[e] = steps;
-    st.episode_reward[e] = ep;
-    reward_out[e] = reward;
-    done_out[e] = (uint8_t)done;
-    if (fin_ret) fin_ret[e] = done ? ep : 0;
-    if (fin_len) fin_len[e] = done ? steps : 0;
-    if (fin_solved) fin_solved[e] = (uint8_t)(done ? solved : 0);
   }
-  __syncwarp();
-  return __shfl_sync(0xffffffffu, done, 0);
+  const int ep = st.episode_reward[e] + reward;
+  st.num_env_steps[e] = steps;
+  st.episode_reward[e] = ep;
+  reward_out[e] = reward;
+  done_out[e] = (uint8_t)done;
+  if (fin_ret) fin_ret[e] = done ? ep : 0;
+  if (fin_len) fin_len[e] = done ? steps : 0;
+  if (fin_solved) fin_solved[e] = (uint8_t)(done ? solved : 0);
+  return done;
 }
 
 // An env's frame as the policy's next input row: channel-major integer pixel values as fp32 (TransposeFrame;
@@ -401,36 +401,62 @@ __device__ __forceinline__ void reset_env(const tpp_boxworld_state& st, int e, i
   if (frame_out) copy_frame(W, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
 }
 
-__global__ void __launch_bounds__(BW_WARPS * 32) boxworld_step_kernel(tpp_boxworld_state st,
-                                                                     const int32_t* __restrict__ action,
-                                                                     int32_t* __restrict__ reward_out,
-                                                                     uint8_t* __restrict__ done_out,
-                                                                     uint8_t* __restrict__ frame_out,
-                                                                     int32_t* fin_ret, int32_t* fin_len,
-                                                                     uint8_t* fin_solved) {
+// Step kernel.  A CTA owns GROUP consecutive envs: thread-per-env transitions, then the whole CTA copies the group's
+// frames -- one contiguous span of the world array -- into the rollout slot with 16-byte accesses, every load of a
+// batch in flight before the first store.  (Finished envs are copied too; the reset kernel overwrites their frames.)
+// The group's finished-env count goes to scratch[group] for the reset kernel's in-order ranks.
+template <int GROUP>
+__global__ void __launch_bounds__(256) boxworld_step_kernel(tpp_boxworld_state st, const int32_t* __restrict__ action,
+                                                            int32_t* __restrict__ reward_out,
+                                                            uint8_t* __restrict__ done_out,
+                                                            uint8_t* __restrict__ frame_out, int32_t* fin_ret,
+                                                            int32_t* fin_len, uint8_t* fin_solved) {
   __shared__ int cta_done;
   if (threadIdx.x == 0) cta_done = 0;
-  // programmatic dependent launch (rollout chain policy -> step -> reset -> policy): the CTAs may already be resident
-  // while the policy kernel finishes; its actions are read below
+  // programmatic dependent launch (rollout chain policy -> step -> reset -> policy): harmless when launched plainly
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * BW_WARPS + (threadIdx.x >> 5);
+  const int e0 = blockIdx.x * GROUP, e = e0 + threadIdx.x;
   const int cells = (st.n + 2) * (st.n + 2);
-  if (e < st.n_envs) {
-    const int done = step_env(st, e, lane, action, reward_out, done_out, fin_ret, fin_len, fin_solved);
-    if (done && lane == 0) atomicAdd(&cta_done, 1);
-    if (!done && frame_out)
-      copy_frame(st.world + (int64_t)e * cells * 3, frame_out + (int64_t)e * cells * 3, cells * 3, lane);
+  if (threadIdx.x < GROUP && e < st.n_envs) {
+    const int done = step_env(st, e, action, reward_out, done_out, fin_ret, fin_len, fin_solved);
+    if (done) atomicAdd(&cta_done, 1);
   }
-  __syncthreads();
+  __syncthreads();               // the group's cells are updated (same-SM stores are visible to the loads below)
   if (threadIdx.x == 0) st.scratch[blockIdx.x] = cta_done;
+  if (!frame_out) return;
+  const int n_here = min(GROUP, st.n_envs - e0);
+  const int64_t bytes = (int64_t)n_here * cells * 3;
+  const uint8_t* src = st.world + (int64_t)e0 * cells * 3;
+  uint8_t* dst = frame_out + (int64_t)e0 * cells * 3;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const int n16 = (int)(bytes >> 4);
+    for (int base = 0; base < n16; base += 256 * 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = base + threadIdx.x + 256 * j;
+        if (i < n16) v[j] = s4[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = base + threadIdx.x + 256 * j;
+        if (i < n16) d4[i] = v[j];
+      }
+    }
+  } else if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)bytes) & 3) == 0) {
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+    for (int i = threadIdx.x; i < (int)(bytes >> 2); i += 256) d1[i] = s1[i];
+  } else {
+    for (int64_t i = threadIdx.x; i < bytes; i += 256) dst[i] = src[i];
+  }
 }
 
-// Reset kernel: same grid.  rank of a finished env = (# finished envs in lower CTAs) + (# finished in lower
-// warps of this CTA); its level seed follows the reference's sequential counter.
-// Exclusive prefix sum of the per-CTA finished-env counts (single CTA; only launched when there are many CTAs, where
+// Exclusive prefix sum of the per-group finished-env counts (single CTA; only launched when there are many groups, where
 // letting every reset CTA re-sum its predecessors would be quadratic).  scratch: [0, n) counts, [n] ticket,
 // [n+1, 2n+1) prefix.
 __global__ void __launch_bounds__(1024) boxworld_scan_kernel(int32_t* scratch, int n) {
@@ -467,43 +493,54 @@ __global__ void __launch_bounds__(1024) boxworld_scan_kernel(int32_t* scratch, i
   }
 }
 
-__global__ void __launch_bounds__(BW_WARPS * 32) boxworld_reset_kernel(tpp_boxworld_state st,
-                                                                      const uint8_t* __restrict__ done_in,
-                                                                      uint8_t* __restrict__ frame_out, int use_prefix,
-                                                                      float* __restrict__ obs_out, int ld_obs) {
+// Reset kernel: same groups.  Rank of a finished env = (# finished envs in lower groups) + (# finished before it in its
+// group); its level seed follows the reference's sequential counter.  Thread-per-env flags and ranks, then the CTA's
+// warps replace the levels of the (few) finished envs from the compacted list.
+template <int GROUP>
+__global__ void __launch_bounds__(256) boxworld_reset_kernel(tpp_boxworld_state st, const uint8_t* __restrict__ done_in,
+                                                             uint8_t* __restrict__ frame_out, int use_prefix,
+                                                             float* __restrict__ obs_out, int ld_obs) {
   __shared__ int red[32];
-  __shared__ int base_s;
-  __shared__ uint32_t mtbuf[BW_WARPS][624];
-  // a dependent kernel launched with programmatic stream serialisation (the fused rollout policy) may start its
-  // prologue now; it waits (griddepcontrol.wait) for this grid to finish before it reads the frames
+  __shared__ int base_s, n_fin;
+  __shared__ int warp_cnt[8];
+  __shared__ int fin_env[GROUP], fin_rank[GROUP];
+  extern __shared__ uint32_t mtbuf_dyn[];          // [8][624], only when levels are generated on the device
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ncta = gridDim.x;
-  if (use_prefix) {          // exclusive prefix of the per-CTA counts was produced by boxworld_scan_kernel
+  if (use_prefix) {          // exclusive prefix of the per-group counts was produced by boxworld_scan_kernel
     if (threadIdx.x == 0) base_s = st.scratch[ncta + 1 + blockIdx.x];
-  } else {                   // few CTAs: sum the counts of the lower CTAs directly
+  } else {                   // few groups: sum the counts of the lower groups directly
     int part = 0;
     for (int c = threadIdx.x; c < (int)blockIdx.x; c += blockDim.x) part += st.scratch[c];
     part = block_sum(part, red);
     if (threadIdx.x == 0) base_s = part;
   }
-  __syncthreads();
   const int64_t sc = *st.seed_counter;
-  const int e = blockIdx.x * BW_WARPS + wid;
+  const int e0 = blockIdx.x * GROUP, e = e0 + threadIdx.x;
   const int S = st.n + 2, cells = S * S;
-  int mine = 0, before = 0, own_total = 0;
-  for (int w = 0; w < BW_WARPS; ++w) {
-    const int ew = blockIdx.x * BW_WARPS + w;
-    const int d = (ew < st.n_envs) ? done_in[ew] : 0;
-    if (w < wid) before += d;
-    if (w == wid) mine = d;
-    own_total += d;
+  const int mine = (threadIdx.x < GROUP && e < st.n_envs) ? (done_in[e] != 0) : 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, mine);
+  if (lane == 0) warp_cnt[wid] = __popc(bal);
+  __syncthreads();
+  int before = __popc(bal & ((1u << lane) - 1u));
+  for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+    n_fin = t;
   }
-  if (mine) reset_env(st, e, (int64_t)base_s + before, sc, lane, mtbuf[wid], frame_out);
-  if (obs_out && e < st.n_envs) {          // every env: its (post-reset) frame as the policy's next input row
-    __syncwarp();
-    emit_obs_row(st.world + (int64_t)e * cells * 3, obs_out + (int64_t)e * ld_obs, cells, ld_obs, lane);
+  if (mine) { fin_env[before] = e; fin_rank[before] = before; }
+  __syncthreads();
+  for (int k = wid; k < n_fin; k += 8)
+    reset_env(st, fin_env[k], (int64_t)base_s + fin_rank[k], sc, lane, mtbuf_dyn + wid * 624, frame_out);
+  if (obs_out) {          // every env: its (post-reset) frame as the policy's next input row
+    __syncthreads();
+    for (int k = wid; k < GROUP; k += 8) {
+      const int ee = e0 + k;
+      if (ee < st.n_envs) emit_obs_row(st.world + (int64_t)ee * cells * 3, obs_out + (int64_t)ee * ld_obs, cells, ld_obs, lane);
+    }
   }
   // last CTA to finish advances the seed counter by the total number of finished envs
   __shared__ bool last;
@@ -757,28 +794,24 @@ extern "C" int tpp_boxworld_step(const tpp_boxworld_state* st, const int32_t* ac
   TPP_CHECK_ARG(action && reward_out && done_out);
   TPP_CHECK_ARG(!obs_out || ld_obs >= 3 * (st->n + 2) * (st->n + 2));
   // scratch holds 2 N + 4096 ints (see tpp_boxworld_state)
-  const int grid = tpp_ceil_div(st->n_envs, tpp::BW_WARPS);
   cudaStream_t s = tpp_stream(stream);
+  // groups of 64 envs per CTA while that still fills the machine, 256 beyond (the C3-sized sweeps)
+  const bool big = st->n_envs > 64 * 148 * 4;
+  const int group = big ? 256 : 64;
+  const int grid = tpp_ceil_div(st->n_envs, group);
   const int use_prefix = grid > 1024;
-  // programmatic stream serialisation on both launches: in the rollout's dependent chain (policy -> step -> reset ->
-  // policy) every kernel is resident before its predecessor has drained and waits inside (griddepcontrol.wait)
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(tpp::BW_WARPS * 32, 1, 1);
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 0;       // measured: step / reset CTAs that become resident early only take SM slots from the policy
-                          // kernel (49.8 vs 48.5 us per rollout step); the policy kernel IS launched this way, see below
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tpp::boxworld_step_kernel, *st, action, reward_out, done_out, frame_out, fin_ret,
-                                     fin_len, fin_solved);
-  if (e != cudaSuccess) return (int)e;
-  if (use_prefix) tpp::boxworld_scan_kernel<<<1, 1024, 0, s>>>(st->scratch, grid);
-  e = cudaLaunchKernelEx(&cfg, tpp::boxworld_reset_kernel, *st, (const uint8_t*)done_out, frame_out, use_prefix, obs_out,
-                         (int)ld_obs);
-  if (e != cudaSuccess) return (int)e;
+  const size_t dyn = (st->n_levels > 0 && st->bank_world) ? 0 : sizeof(uint32_t) * 8 * 624;
+  if (big) {
+    tpp::boxworld_step_kernel<256><<<grid, 256, 0, s>>>(*st, action, reward_out, done_out, frame_out, fin_ret, fin_len,
+                                                        fin_solved);
+    if (use_prefix) tpp::boxworld_scan_kernel<<<1, 1024, 0, s>>>(st->scratch, grid);
+    tpp::boxworld_reset_kernel<256><<<grid, 256, dyn, s>>>(*st, done_out, frame_out, use_prefix, obs_out, ld_obs);
+  } else {
+    tpp::boxworld_step_kernel<64><<<grid, 256, 0, s>>>(*st, action, reward_out, done_out, frame_out, fin_ret, fin_len,
+                                                       fin_solved);
+    if (use_prefix) tpp::boxworld_scan_kernel<<<1, 1024, 0, s>>>(st->scratch, grid);
+    tpp::boxworld_reset_kernel<64><<<grid, 256, dyn, s>>>(*st, done_out, frame_out, use_prefix, obs_out, ld_obs);
+  }
   TPP_LAUNCH_STATUS();
 }
 
