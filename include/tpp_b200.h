@@ -240,8 +240,9 @@ typedef struct {
   const float* mask; int64_t ld_mask;
   float* out; float* out_hi; float* out_lo; int64_t ldc;
   float* colsum;
-  void* dbg;          /* optional int64[16]: clock64 timeline of one CTA (x = 0, y = _reserved, z = 0) -- profiling aid,
-                         normally NULL */
+  void* dbg;          /* optional int64[16] (int64[96] with a TPP_TC_*_SPLIT flag: + the splitter warps' per-k-block
+                         times): clock64 timeline of one CTA (x = 0, y = _reserved, z = 0) -- profiling aid, normally
+                         NULL */
   const float* addend; int64_t ld_add;   /* TPP_EPI_ADD (tpp_gemm_tc only): result += addend[m*ld_add + n], applied
                                             after bias / relu / mask: the residual connection (forward) and the
                                             skip-path gradient (backward) of ResidualBlock, common/model.py:134-153 */
@@ -263,6 +264,14 @@ typedef struct {
  * representable in TF32 (e.g. integer pixel values 0..255): it has no lo half (a_lo / b_lo unused, not loaded) and the
  * pass that would multiply it is skipped -- two passes, 3/4 of the operand traffic.                                */
 enum { TPP_TC_A_EXACT = 16, TPP_TC_B_EXACT = 32 };
+/* with 3, | TPP_TC_A_SPLIT / TPP_TC_B_SPLIT (tiles wider than 32 columns): a_hi / b_hi is the PLAIN fp32 operand and the
+ * kernel forms the lo half in shared memory (the tensor core reads an fp32 word as its truncated TF32 value, so the plain
+ * tile IS the hi half; four extra warps write lo = tf32_round(x - trunc(x)) next to it before the MMAs of the stage are
+ * issued).  Same three passes, half the operand bytes from HBM / L2, no separate split pass.  a_lo / b_lo unused.
+ * Measured (profiles/README.md, round 2): the HBM bytes halve but the launch is NOT faster -- the plain tiles and the
+ * lo ring share the 227 KB of shared memory and the splitters sit between the TMA landing and the MMAs, so the k-block
+ * period is bound by (TMA latency + split + cross-CTA signal + MMA) / stages.  The engine keeps pairs by default.   */
+enum { TPP_TC_A_SPLIT = 64, TPP_TC_B_SPLIT = 128 };
 /* block_n codes of the CTA-pair tiles */
 enum { TPP_TC_TILE_PAIR = 512, TPP_TC_TILE_PAIR_PERSISTENT = 513, TPP_TC_TILE_PAIR64_PERSISTENT = 65 };
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);

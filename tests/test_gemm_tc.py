@@ -282,3 +282,71 @@ def test_persistent_cta_pairs_narrow_output(M, N, K):
     w = want + bias.double().cpu()
     assert ((res["out"][:, :N].double().cpu() - w).abs() / (scale + 1)).max() < 2e-6
     assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])
+
+
+# ---- operands split on chip (TPP_TC_A_SPLIT / TPP_TC_B_SPLIT) ----------------------------------------------------
+def _plain_operand(x, mn_major):
+    """The plain fp32 array a producer would leave in HBM (no hi / lo pair)."""
+    rows, K = x.shape
+    if not mn_major:
+        ld = (K + 3) // 4 * 4
+        buf = torch.zeros(rows, ld, device="cuda")
+        buf[:, :K] = x
+        return buf, ld
+    ld = (rows + 31) // 32 * 32
+    buf = torch.zeros(K, ld, device="cuda")
+    buf[:, :rows] = x.t()
+    return buf, ld
+
+
+@pytest.mark.parametrize("which", ["a", "b", "ab"])
+@pytest.mark.parametrize("block_n", [64, 128, 256, 512, 513, 65])
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(512, 256, 256, False, False), (1000, 256, 200, False, True),
+                                             (256, 300, 1024, True, True), (256 * 160 + 40, 64, 96, False, False)])
+def test_operands_split_on_chip(which, block_n, M, N, K, a_mn, b_mn):
+    """The operand is handed over as ONE plain fp32 array; four extra warps form its lo half in shared memory.  Same
+    fp32-grade bound as the pair path, on every wide tile, K-major and MN-major, with the other operand a pair."""
+    from tpp_b200 import _lib
+    if block_n == 65 and N > 64:
+        pytest.skip("256 x 64 tile: N <= 64")
+    atomic = a_mn and b_mn                      # the weight-gradient form: split-k, atomic accumulation
+    g0 = torch.Generator(device="cuda").manual_seed(M + 7 * N + K)
+    a = torch.randn(M, K, device="cuda", generator=g0)
+    b = torch.randn(N, K, device="cuda", generator=g0) * 0.05
+    g = _lib.TcGemm()
+    prec = 3
+    if "a" in which:
+        buf_a, lda = _plain_operand(a, a_mn)
+        g.a_hi, prec = buf_a.data_ptr(), prec | _lib.TC_A_SPLIT
+    else:
+        a_hi, a_lo, lda = _operand(a, a_mn)
+        g.a_hi, g.a_lo = a_hi.data_ptr(), a_lo.data_ptr()
+    if "b" in which:
+        buf_b, ldb = _plain_operand(b, b_mn)
+        g.b_hi, prec = buf_b.data_ptr(), prec | _lib.TC_B_SPLIT
+    else:
+        b_hi, b_lo, ldb = _operand(b, b_mn)
+        g.b_hi, g.b_lo = b_hi.data_ptr(), b_lo.data_ptr()
+    ldc = (N + 3) // 4 * 4
+    out = torch.zeros(M, ldc, device="cuda")
+    g.lda, g.ldb, g.a_mn, g.b_mn = lda, ldb, int(a_mn), int(b_mn)
+    g.M, g.N, g.K, g.precision, g.block_n = M, N, K, prec, block_n
+    g.split_k, g.flags, g.out, g.ldc = (5 if atomic else 1), (_lib.EPI_ACCUM if atomic else 0), out.data_ptr(), ldc
+    _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want, scale = _ref(a, b)
+    err = (out[:, :N].double().cpu() - want).abs() / scale
+    assert err.max() < 2e-6, f"max scaled err {err.max():.3e}"
+
+
+def test_split_on_chip_refused_on_narrow_tiles():
+    from tpp_b200 import _lib
+    a = torch.randn(128, 64, device="cuda")
+    b = torch.randn(16, 64, device="cuda")
+    out = torch.zeros(128, 16, device="cuda")
+    g = _lib.TcGemm()
+    g.a_hi, g.lda, g.b_hi, g.ldb = a.data_ptr(), 64, b.data_ptr(), 64
+    g.M, g.N, g.K, g.precision, g.block_n, g.out, g.ldc = 128, 16, 64, 3 | _lib.TC_A_SPLIT | _lib.TC_B_SPLIT, 16, \
+        out.data_ptr(), 16
+    with pytest.raises(Exception):
+        _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())

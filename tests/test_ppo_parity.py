@@ -28,14 +28,17 @@ def _close(a, b, rtol=1e-5, atol=1e-6, what=""):
 
 @pytest.mark.parametrize("M,in_dim,A,mid,latent", [(64, 9, 2, 32, 16), (4096, 9, 2, 256, 64), (1000, 588, 4, 256, 64),
                                                    (130, 5, 3, 48, 24), (256, 14, 15, 256, 64)])
-@pytest.mark.parametrize("kind", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("kind", ["fp32", "tf32x3", "tf32x3-split-on-chip"])
 def test_engine_forward_backward_vs_torch(M, in_dim, A, mid, latent, kind):
     """Hand-written forward/backward on the flat buffer == torch autograd on the same (aliased) parameters, for
-    the CUDA-core fp32 engine and the tcgen05 3xTF32 engine (both must hold the fp32 tolerance)."""
+    the CUDA-core fp32 engine and the tcgen05 3xTF32 engine (both must hold the fp32 tolerance); the latter also with
+    the hidden activations kept as plain fp32 arrays whose lo halves are formed on chip (TPP_TC_A_SPLIT / B_SPLIT)."""
     from tpp_b200.common.engine import MLPEngine, MLPEngineTC
     torch.backends.cuda.matmul.allow_tf32 = False
     pol = _policy(in_dim, A, mid=mid, latent=latent, seed=M)
-    eng = MLPEngine(pol, A) if kind == "fp32" else MLPEngineTC(pol, A, precision=3)
+    eng = MLPEngine(pol, A) if kind == "fp32" else MLPEngineTC(pol, A, precision=3, split_on_chip=kind.endswith("chip"))
+    if kind.endswith("chip") and not eng.split_on_chip:
+        pytest.skip("a layer narrower than 33 columns: the engine keeps (hi, lo) pairs")
     x = torch.randn(M, (in_dim + 3) // 4 * 4, device="cuda")[:, :in_dim]
     head = eng.forward(x, M)
     dist, v, _ = pol(x, None, None)

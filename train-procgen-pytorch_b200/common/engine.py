@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import TC_TILE_PAIR64_PERSISTENT, TC_TILE_PAIR_PERSISTENT, TC_A_EXACT, TC_B_EXACT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
+from .._lib import TC_TILE_PAIR64_PERSISTENT, TC_TILE_PAIR_PERSISTENT, TC_A_EXACT, TC_B_EXACT, TC_A_SPLIT, TC_B_SPLIT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -156,10 +156,15 @@ class MLPEngineTC(MLPEngine):
     the CUDA-core kernel: they are < 1 % of the FLOPs.
     """
 
-    def __init__(self, policy, n_actions, precision=3, raw_pixels=False, obs_shape=None):
+    def __init__(self, policy, n_actions, precision=3, raw_pixels=False, obs_shape=None, split_on_chip=False):
         super().__init__(policy, n_actions)
         assert precision in (1, 3)
         self.precision = precision
+        # split_on_chip: hidden activations and their gradients live in HBM as ONE plain fp32 array; the GEMMs that read
+        # them form the lo halves in shared memory (TPP_TC_A_SPLIT / TPP_TC_B_SPLIT), so every large operand is read
+        # once and every epilogue writes once.  Needs the wide tiles (> 32 output columns) in every GEMM of the trunk.
+        self.split_on_chip = bool(split_on_chip) and precision == 3 and \
+            all(l[3] > 32 for l in self.layers) and all(l[2] > 32 for l in self.layers[1:])
         # raw_pixels: image observations may arrive as integer pixel values 0..255 (``forward(..., raw=True)``).  They are
         # exact in TF32, so the first layer needs no lo half of X (two MMA passes, 3/4 of the operand traffic, half the
         # gather's writes); ScaledFloatFrame's 1/255 (common/env/procgen_wrappers.py:407-419) lives in a second copy of
@@ -223,14 +228,19 @@ class MLPEngineTC(MLPEngine):
             ws = _Workspace()
             f = dict(dtype=torch.float32, device=self.device)
             ws.x = dict(hi=torch.zeros(M, self.ld_in, **f), lo=torch.zeros(M, self.ld_in, **f))
-            ws.h = [dict(hi=torch.zeros(M, _ceil(l[3], 32) * 32, **f), lo=torch.zeros(M, _ceil(l[3], 32) * 32, **f),
-                         ld=_ceil(l[3], 32) * 32) for l in self.layers]
+            L = len(self.layers)
+            ws.h = []
+            for i, l in enumerate(self.layers):
+                hi = torch.zeros(M, _ceil(l[3], 32) * 32, **f)
+                # split_on_chip: "hi" is the plain activation, only the head GEMM's operand (last layer) keeps a lo half
+                lo = hi if (self.split_on_chip and i < L - 1) else torch.zeros(M, _ceil(l[3], 32) * 32, **f)
+                ws.h.append(dict(hi=hi, lo=lo, ld=_ceil(l[3], 32) * 32))
             ws.last_plain = torch.zeros(M, _ceil(self.latent, 32) * 32, **f)   # same row stride as its TF32 pair
             ws.head = torch.zeros(M, self.ld_head, **f)
             ws.dhead = torch.zeros(M, self.ld_head, **f)
             mw = _ceil(self.max_width, 32) * 32
             ws.dz = [dict(plain=torch.zeros(M, mw, **f), hi=torch.zeros(M, mw, **f), lo=torch.zeros(M, mw, **f))
-                     for _ in range(2)]
+                     for _ in range(2)]     # split_on_chip: "hi" of ws.dz[1] / later ws.dz[0] is the plain gradient
             ws.fm = None       # TF32 pair of a feature-major rollout slot, allocated on first use
             self._ws[(M, slot)] = ws
         return ws
@@ -351,15 +361,19 @@ class MLPEngineTC(MLPEngine):
         for i in range(L - 1 if trunk_only else L):
             w_off, b_off, fin, fout, relu = self.layers[i]
             h, w = ws.h[i], (self.w0_raw if raw and i == 0 else self.w[i])
+            soc = self.split_on_chip
+            a_flag = TC_A_EXACT if raw and i == 0 else (TC_A_SPLIT if soc and i > 0 else 0)
             if trunk_only and i == L - 2:       # plain fp32 only: its consumer is not a tensor-core GEMM
                 self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
                          flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off), out=h["hi"], ldc=h["ld"],
-                         exact=TC_A_EXACT if raw and i == 0 else 0, block_n=self._bn(M, fout))
+                         exact=a_flag, block_n=self._bn(M, fout))
                 return h["hi"], h["ld"]
+            plain_only = soc and i < L - 1     # the next GEMM splits it on chip
             self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
                      flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
-                     out=ws.last_plain if i == L - 1 else None, out_pair=(h["hi"], h["lo"]), ldc=h["ld"],
-                     exact=TC_A_EXACT if raw and i == 0 else 0, block_n=self._bn(M, fout))
+                     out=ws.last_plain if i == L - 1 else (h["hi"] if plain_only else None),
+                     out_pair=None if plain_only else (h["hi"], h["lo"]), ldc=h["ld"],
+                     exact=a_flag, block_n=self._bn(M, fout))
             cur, ld_cur, a_mn = (h["hi"], h["lo"]), h["ld"], 0
         self._tc(cur, ld_cur, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
                  bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
@@ -412,17 +426,23 @@ class MLPEngineTC(MLPEngine):
             pair = fout >= 256 and fin >= 256 and M >= self.wide_tile_rows      # 256 x 256 tiles on CTA pairs
             ctas = 2 * _ceil(fout, 256) * _ceil(fin, 256) if pair else _ceil(fout, 128) * _ceil(fin, 128)
             raw0 = i == 0 and self._x_raw         # gW1 = (1/255) dZ^T X_pixels, X exact: no lo half, two passes
+            soc = self.split_on_chip
+            # split_on_chip: dZ of layers below the last and the hidden activations are plain arrays (the head kernel's
+            # dZ of the last layer and the gathered observations are pairs)
+            flag = (TC_B_EXACT if raw0 else (TC_B_SPLIT if soc and i > 0 else 0)) | (TC_A_SPLIT if soc and i < L - 1 else 0)
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
                      out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas), block_n=self.pair_block_n if pair else 128,
-                     exact=TC_B_EXACT if raw0 else 0, alpha=1.0 / 255.0 if raw0 else 0.0)
+                     exact=flag, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
                 nxt, w, prev = ws.dz[cur ^ 1], self.w[i], ws.h[i - 1]
                 prev_relu = self.layers[i - 1][4]
                 self._tc((dz["hi"], dz["lo"]), ld_dz, (w["hi"], w["lo"]), w["ldk"], M, fin, fout, b_mn=1,
                          flags=EPI_MASK if prev_relu else 0, mask=prev["hi"] if prev_relu else None,
-                         ld_mask=prev["ld"], out_pair=(nxt["hi"], nxt["lo"]), ldc=prev["ld"],
-                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin))
+                         ld_mask=prev["ld"], out=nxt["hi"] if soc else None,
+                         out_pair=None if soc else (nxt["hi"], nxt["lo"]), ldc=prev["ld"],
+                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin),
+                         exact=TC_A_SPLIT if soc and i < L - 1 else 0)
                 cur, ld_dz = cur ^ 1, prev["ld"]
 
 

@@ -47,16 +47,30 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
 // Epilogue warps: 4 per TMEM lane quarter for wide tiles (the epilogue is instruction-latency bound, not bandwidth
 // bound); narrow tiles (one 32-column group: convolution outputs) have work for 4 warps only, and the small CTA
 // (192 threads x 80 registers) lets 3-4 tiles share an SM so that prologue / epilogue overlap other tiles' loads.
-constexpr int epi_warps(int block_n) { return block_n <= 32 ? 4 : 16; }
-constexpr int num_threads(int block_n) { return 64 + epi_warps(block_n) * 32; }   // warp 0: TMA, warp 1: MMA + TMEM
+// (SPLIT kernels of the 256-wide tiles: 8 epilogue warps, i.e. 36 KB of transpose patches instead of 72 -- the room
+// goes to the stage rings)
+constexpr int epi_warps(int block_n, bool split = false) { return block_n <= 32 ? 4 : (split && block_n == 256 ? 8 : 16); }
+// wide tiles carry 4 more warps behind the epilogue warps: the on-chip operand splitters (see Params::split_a)
+// two groups, group g splits the k-blocks it = g (mod 2); 256-wide tiles (8 epilogue warps) have room for 2 x 8 warps
+constexpr int conv_warps(int block_n) { return block_n == 256 ? 16 : 8; }
+constexpr int num_threads(int block_n, bool split = false) {   // warp 0: TMA, warp 1: MMA + TMEM, epilogue warps, [splitters]
+  return 64 + epi_warps(block_n, split) * 32 + (split ? conv_warps(block_n) * 32 : 0);
+}
 constexpr int STG_PITCH = 36;            // floats per staged row (16-byte aligned, conflict-free 128-bit LDS/STS)
-constexpr int stg_bytes(int block_n) { return epi_warps(block_n) * 32 * STG_PITCH * 4; }   // a 32x32 patch per warp
+constexpr int stg_bytes(int block_n, bool split = false) { return epi_warps(block_n, split) * 32 * STG_PITCH * 4; }   // a 32x32 patch per warp
 
 struct Params {
   int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
   int npass;                   // 1 (tf32) or 3 (3xTF32)
   int nops_a, nops_b;          // operand copies staged per k-block: 2 = (hi, lo), 1 = hi only (single pass, or the
                                // operand is exact in TF32 -- e.g. integer pixel values -- and has no lo half)
+  int split_a, split_b;        // wide tiles: the operand arrives as ONE plain fp32 copy; the tensor core reads it as its hi
+                               // half (it truncates fp32 words to TF32) and the splitter warps form lo = x - trunc(x) in
+                               // shared memory between the TMA landing and the MMA -- half the HBM / L2 bytes of a pair
+  int tma_a, tma_b;            // operand copies the TMA producer loads (1 when split on chip or exact)
+  int lo_stages, lo_offset;    // split on chip: the lo halves live in their own ring of lo_stages slots at smem +
+                               // lo_offset ([A lo][B lo], split operands only), so that the TMA ring holds plain tiles
+                               // only and is deeper for the same shared memory
   int skip;                    // bit `pass` set: that pass is not issued (2: a_lo*b_hi, 1: a_hi*b_lo)
   float alpha;                 // scale of the atomically accumulated product (TPP_EPI_ACCUM)
   int stages;
@@ -100,8 +114,15 @@ enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT 
 // columns), the producer / MMA warps run into the next item while both CTAs' epilogue warps drain the previous one
 // (their transpose patches get their own shared memory; the pipeline keeps two 64 KB stages); the peer's epilogue warps
 // return an accumulator by arriving on the LEADER's barrier.
-template <int BLOCK_N, bool PAIR = false, bool PERSIST = false>
-__global__ void __launch_bounds__(num_threads(BLOCK_N), 1)
+// lo half of an operand whose hi half is the fp32 word itself: the tensor core drops the 13 low mantissa bits of a
+// kind::tf32 operand (measured, profiles/tf32_operand_probe.py), so hi = trunc(x) and x - trunc(x) is exact in fp32 (13
+// significant bits); rounding it to TF32's 11 keeps the residual error unbiased at 2^-21 |x|.
+__device__ __forceinline__ float split_lo(float x) {
+  return tf32_round(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
+}
+
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false>
+__global__ void __launch_bounds__(num_threads(BLOCK_N, SPLIT), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
   // Narrow tiles (BLOCK_N <= 32) are the convolution tiles.  Only they carry the residual / ReLU-pair epilogue extras,
@@ -110,6 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   // previous one (per-tile prologue, epilogue and CTA launch were ~2/3 of a 9-k-block tile's time).  Wide tiles keep
   // compile-time constants, the lean epilogue and one work item per CTA.
   constexpr bool NARROW = BLOCK_N <= 32;
+  constexpr int CONV_GROUP = conv_warps(BLOCK_N) / 2;                 // splitter warps per group
   static_assert(!PAIR || BLOCK_N == 256 || BLOCK_N == 64, "CTA-pair forms: 256 x 256 and 256 x 64 tiles");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;                // B rows this CTA stages
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -135,12 +157,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int nops_a = NARROW ? (p.npass == 3 ? 2 : 1) : p.nops_a, nops_b = NARROW ? nops_a : p.nops_b;
   const int bk = NARROW ? p.bk : BLOCK_K;
   const int A_BYTES = NARROW ? p.a_slot : BLOCK_M * BLOCK_K * 4, B_BYTES = NARROW ? p.b_slot : B_ROWS * BLOCK_K * 4;
-  const int stage_bytes = A_BYTES * nops_a + B_BYTES * nops_b;
+  const int ta = NARROW ? nops_a : p.tma_a, tb = NARROW ? nops_b : p.tma_b;   // copies per operand in a TMA stage
+  const int stage_bytes = A_BYTES * ta + B_BYTES * tb;
+  const int lo_bytes = NARROW ? 0 : A_BYTES * p.split_a + B_BYTES * p.split_b;
+  const int LS = NARROW ? 0 : p.lo_stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.bar_offset);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;      // [2]: accumulator i complete (MMA -> epilogue)
   uint64_t* tmem_empty = tmem_full + 2;            // [2]: accumulator i drained (epilogue -> MMA)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* conv_bar = tmem_empty + 2;             // [lo_stages]: the splitter warps have filled lo slot l
+  uint64_t* lo_empty = conv_bar + LS;              // [lo_stages]: the MMAs reading lo slot l have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lo_empty + LS);
+  // on-chip split: every CTA's loads complete on its OWN full barrier (its splitters wait there) and the MMA issuer waits
+  // for the splitters of the CTA (of both CTAs of a pair) instead of for the loads
+  static_assert(!SPLIT || BLOCK_N > 32, "operands are split on chip by the wide tiles only");
+  constexpr bool split_mode = SPLIT;     // (a separate kernel: the pair-operand kernels keep their round-1 shape)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Work items (tile, k-split) are flattened on grid.x (n tile fastest, then m tile, then split), so M is not limited
@@ -177,9 +208,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
+    for (int l = 0; l < LS; ++l) {
+      mbar_init(conv_bar + l, CONV_GROUP + (PAIR && leader ? 1 : 0));   // own splitters (+ the peer's relay)
+      mbar_init(lo_empty + l, 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, epi_warps(BLOCK_N) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogue warps, on the leader
+      mbar_init(tmem_empty + i, epi_warps(BLOCK_N, SPLIT) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogue warps, on the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -219,15 +254,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         if (it == 0) TPP_PROBE(2);
-        if (!PAIR || leader) mbar_expect_tx(full_bar + s, tx);   // PAIR: tx counts both CTAs' boxes, on the leader
+        if (split_mode) mbar_expect_tx(full_bar + s, PAIR ? tx / 2 : tx);      // this CTA's own boxes, own barrier
+        else if (!PAIR || leader) mbar_expect_tx(full_bar + s, tx);   // PAIR: tx counts both CTAs' boxes, on the leader
         uint8_t* st = smem + s * stage_bytes;
         const int kc = (kb0 + kb) * bk;
         // A.  K-major: 2-D box {32 k, rows}; MN-major: 3-D box {32 m/n, 32 k-rows, blocks of 32 m/n};
         // implicit convolution: k-block = filter tap, rows = 128 consecutive output pixels gathered by TMA im2col;
         // its weight-gradient form: k-block = 32 consecutive pixels, one im2col box {32 slots, 32 pixels} per tap
         for (int o = 0; o < 2; ++o) {
-          if (o >= nops_a && o >= nops_b) break;
-          if (NARROW || o < nops_a) {
+          if (o >= ta && o >= tb) break;
+          if (NARROW || o < ta) {
           const CUtensorMap* tmA = o ? &tmA_lo : &tmA_hi;
           uint8_t* dst = st + o * A_BYTES;
           if (NARROW && p.conv_wgrad) {
@@ -238,7 +274,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           } else if (NARROW && p.conv_W) {
             const int tap = kb0 + kb;
             tma_load_im2col(tmA, full_bar + s, dst, cw, ch, cn, tap % 3, tap / 3);
-          } else if (PAIR) {
+          } else if (PAIR && !split_mode) {
             if (p.a_mn) tma_load_3d_pair(tmA, full_bar + s, dst, 0, kc, m0 >> 5);
             else tma_load_2d_pair(tmA, full_bar + s, dst, kc, m0);
           } else if (p.a_mn) {
@@ -247,12 +283,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tma_load_2d(tmA, full_bar + s, dst, kc, m0);
           }
           }
-          if (!NARROW && o >= nops_b) continue;
+          if (!NARROW && o >= tb) continue;
           const CUtensorMap* tmB = o ? &tmB_lo : &tmB_hi;
-          uint8_t* dstb = st + A_BYTES * nops_a + o * B_BYTES;
+          uint8_t* dstb = st + A_BYTES * ta + o * B_BYTES;
           if (PAIR) {                                   // this CTA's half of the tile's 256 B rows
             const int nb = n0 + (int)cta_rank * B_ROWS;
-            if (p.b_mn) tma_load_3d_pair(tmB, full_bar + s, dstb, 0, kc, nb >> 5);
+            if (split_mode) {
+              if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, nb >> 5);
+              else tma_load_2d(tmB, full_bar + s, dstb, kc, nb);
+            } else if (p.b_mn) tma_load_3d_pair(tmB, full_bar + s, dstb, 0, kc, nb >> 5);
             else tma_load_2d_pair(tmB, full_bar + s, dstb, kc, nb);
           } else if (p.b_mn) tma_load_3d(tmB, full_bar + s, dstb, 0, kc, n0 >> 5);
           else tma_load_2d(tmB, full_bar + s, dstb, kc, n0);
@@ -262,6 +301,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread; the leader CTA of a pair issues for both) =====
+    if (PAIR && !leader && split_mode) {
+      // the peer CTA's warp 1 has no MMAs to issue: it forwards "my lo halves of stage s are written" to the leader
+      int it = 0;
+      for (int w = wbegin; w < wend; w += wstride) {
+        TPP_DECODE_WORK(w)
+        (void)m0; (void)n0; (void)kb0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int l = it % LS;
+          mbar_wait(conv_bar + l, (it / LS) & 1);
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+                             smem_u32(conv_bar + l) & PEER_BIT_MASK)
+                         : "memory");
+          __syncwarp();
+        }
+      }
+    }
     int it = 0, acc_i = 0;
     for (int w = wbegin; w < (PAIR && !leader ? wbegin : wend); w += wstride, ++acc_i) {
      TPP_DECODE_WORK(w)
@@ -274,14 +330,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
      for (int kb = 0; kb < nkb; ++kb, ++it) {
       const int s = it % p.stages;
       const uint32_t ph = (it / p.stages) & 1;
-      mbar_wait(full_bar + s, ph);
+      const int l = split_mode ? it % LS : 0;
+      if (split_mode) mbar_wait(conv_bar + l, (it / LS) & 1);     // (implies the stage has landed, in both CTAs)
+      else mbar_wait(full_bar + s, ph);
       tc_fence_after();
       if (it == 0) TPP_PROBE(3);
+      if (split_mode && probe && it < 12) p.dbg[64 + it] = clock64();
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes);
-        const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + A_BYTES * nops_a;
-        const uint32_t b_lo = b_hi + B_BYTES;
+        const uint32_t b_hi = a_hi + A_BYTES * ta;
+        uint32_t a_lo = a_hi + A_BYTES, b_lo = b_hi + B_BYTES;
+        if (split_mode) {
+          const uint32_t lo = smem_u32(smem + p.lo_offset + l * lo_bytes);
+          if (p.split_a) a_lo = lo;
+          if (p.split_b) b_lo = lo + (p.split_a ? A_BYTES : 0);
+        }
         // small terms first, then hi*hi
         bool first = kb == 0;                       // the first MMA of a work item overwrites the accumulator
         for (int pass = p.npass - 1; pass >= 0; --pass) {
@@ -302,6 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         // frees the smem stage when these MMAs retire (PAIR: in both CTAs)
         if (PAIR) umma_commit_pair(empty_bar + s); else umma_commit(empty_bar + s);
+        if (split_mode) { if (PAIR) umma_commit_pair(lo_empty + l); else umma_commit(lo_empty + l); }
         if (kb == nkb - 1) {                        // accumulator complete
           if (PAIR) umma_commit_pair(tmem_full + (acc_i & 1)); else umma_commit(tmem_full + (acc_i & 1));
           TPP_PROBE(4);
@@ -309,6 +373,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       __syncwarp();
      }
+    }
+  } else if (SPLIT && warp >= 2 + epi_warps(BLOCK_N, SPLIT)) {
+    // ===== operand splitters (wide tiles): lo = x - trunc_tf32(x), elementwise in place of the landed tile =====
+    // The conversion is elementwise, so the swizzled layout of the hi tile is the layout of the lo tile: a thread walks
+    // 16-byte chunks linearly (conflict-free).  One arrive per warp on the MMA issuer's barrier (the leader's, in a pair).
+    if (split_mode) {
+      const int cwarp = warp - 2 - epi_warps(BLOCK_N, SPLIT);
+      const int ctid = (cwarp % CONV_GROUP) * 32 + lane, cgroup = cwarp / CONV_GROUP;
+      int it = 0;
+      for (int w = wbegin; w < wend; w += wstride) {
+        TPP_DECODE_WORK(w)
+        (void)m0; (void)n0; (void)kb0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          if ((it & 1) != cgroup) continue;
+          const int s = it % p.stages, l = it % LS;
+          mbar_wait(lo_empty + l, ((it / LS) & 1) ^ 1);
+          mbar_wait(full_bar + s, (it / p.stages) & 1);
+          const bool cprobe = probe && ctid == 0 && it < 12;      // (dbg is int64[96] when a split flag is set)
+          if (cprobe) p.dbg[16 + 4 * it] = clock64();
+          uint8_t* st = smem + s * stage_bytes;
+#pragma unroll
+          for (int op = 0; op < 2; ++op) {
+            if (!(op == 0 ? p.split_a : p.split_b)) continue;
+            const int bytes = op == 0 ? A_BYTES : B_BYTES;
+            const float4* hi = reinterpret_cast<const float4*>(st + (op == 0 ? 0 : A_BYTES * ta));
+            float4* lo = reinterpret_cast<float4*>(smem + p.lo_offset + l * lo_bytes + (op == 1 && p.split_a ? A_BYTES : 0));
+            for (int base = 0; base < bytes / 16; base += CONV_GROUP * 32 * 4) {
+              float4 v[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = base + ctid + CONV_GROUP * 32 * j;
+                if (i < bytes / 16) v[j] = hi[i];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = base + ctid + CONV_GROUP * 32 * j;
+                if (i < bytes / 16) {
+                  const float4 x = v[j];
+                  lo[i] = make_float4(split_lo(x.x), split_lo(x.y), split_lo(x.z), split_lo(x.w));
+                }
+              }
+            }
+          }
+          if (cprobe) p.dbg[16 + 4 * it + 1] = clock64();
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the tensor core's reads
+          __syncwarp();
+          if (cprobe) p.dbg[16 + 4 * it + 2] = clock64();
+          if (lane == 0) mbar_arrive(conv_bar + l);            // this CTA's barrier: a cluster-scope release costs ~1000
+          if (cprobe) p.dbg[16 + 4 * it + 3] = clock64();       // cycles, the peer's idle MMA warp relays it instead
+        }
+      }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> smem transpose -> (bias / relu / mask / tf32 split) -> coalesced global ====
@@ -318,7 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // lines (8 lanes per row, 4 rows per instruction), column sums are register accumulations.  EPI_WARPS/4 warps serve each
     // TMEM lane quarter (column groups round-robin).  The pipeline stages are free by now (tmem_full => all MMAs
     // retired), the patches alias them.
-    constexpr int EPI_WARPS = epi_warps(BLOCK_N);
+    constexpr int EPI_WARPS = epi_warps(BLOCK_N, SPLIT);
     const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
@@ -565,12 +680,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
     if (!NARROW && p.colsum && !atomic) {      // all epilogue warps of the CTA: combine, then one atomic per column
-      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");
-      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N) * 32) {
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");
+      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N, SPLIT) * 32) {
         if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, cs_sh[i]);
         if (PERSIST) cs_sh[i] = 0.0f;          // the next work item starts from zero ...
       }
-      if (PERSIST) asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");   // ... in every warp's view
+      if (PERSIST) asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");   // ... in every warp's view
     }
     if (PERS) {                         // accumulator drained: hand it back to the MMA warp (PAIR: the leader's)
       tc_fence_before();
@@ -597,7 +712,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (rr == 0 && cc < GW) atomicAdd(cs_sh + cc + j, v);
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N) * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");
       if (ew == 0 && cs_n >= 0 && lane < GW && cs_n + lane < p.N) atomicAdd(p.colsum + cs_n + lane, cs_sh[lane]);
     }
   }
@@ -692,13 +807,15 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
 
-template <int BLOCK_N, bool PAIR = false, bool PERSIST = false>
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // B rows one CTA stages
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const int npass = (g->precision & 15) == 3 ? 3 : 1;
   if (BLOCK_N <= 32 && ((g->precision & 48) || (g->alpha != 0.0f && g->alpha != 1.0f))) return TPP_ENOTSUP;
   const bool a_exact = npass == 3 && (g->precision & 16), b_exact = npass == 3 && (g->precision & 32);
+  const bool a_split = npass == 3 && (g->precision & 64) && !a_exact, b_split = npass == 3 && (g->precision & 128) && !b_exact;
+  if ((a_split || b_split) != SPLIT) return TPP_EINVAL;     // (dispatched by tpp_gemm_tc)
   const int nops_a = (npass == 3 && !a_exact) ? 2 : 1, nops_b = (npass == 3 && !b_exact) ? 2 : 1;
   if (BLOCK_N > 32 && ((g->flags & (F_ADD | F_RELU_OUT | F_PAIR_RELU)) || g->conv_C > 0))
     return TPP_ENOTSUP;   // residual / ReLU-pair epilogues and convolution mode are compiled into the narrow tiles only
@@ -720,12 +837,12 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
       return rc;
   } else if ((rc = make_map(&tmA_hi, g->a_hi, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
   if ((rc = make_map(&tmB_hi, g->b_hi, g->ldb, g->N, g->K, B_ROWS, g->b_mn, &b_bytes, bk))) return rc;
-  if (nops_a == 2) {
+  if (nops_a == 2 && !a_split) {
     if (!conv && (rc = make_map(&tmA_lo, g->a_lo, g->lda, g->M, g->K, BLOCK_M, g->a_mn, &a_bytes))) return rc;
   } else {
     tmA_lo = tmA_hi;
   }
-  if (nops_b == 2) {
+  if (nops_b == 2 && !b_split) {
     if ((rc = make_map(&tmB_lo, g->b_lo, g->ldb, g->N, g->K, B_ROWS, g->b_mn, &b_bytes, bk))) return rc;
   } else {
     tmB_lo = tmB_hi;
@@ -735,9 +852,11 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
   p.addend = g->addend; p.ld_add = g->ld_add;
   p.nops_a = nops_a; p.nops_b = nops_b;
+  p.split_a = a_split ? 1 : 0; p.split_b = b_split ? 1 : 0;
+  p.tma_a = a_split ? 1 : nops_a; p.tma_b = b_split ? 1 : nops_b;
   p.skip = (a_exact ? 4 : 0) | (b_exact ? 2 : 0);
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
-  p.tx_bytes = (a_bytes * nops_a + b_bytes * nops_b) * (PAIR ? 2 : 1);   // PAIR: both CTAs' boxes land on one barrier
+  p.tx_bytes = (a_bytes * p.tma_a + b_bytes * p.tma_b) * (PAIR ? 2 : 1);   // PAIR: both CTAs' boxes land on one barrier
   p.conv_W = conv ? g->conv_W : 0; p.conv_HW = conv ? g->conv_H * g->conv_W : 0;
   p.conv_wgrad = wgrad; p.b_tx = b_bytes;
   p.out = g->out; p.ldc = g->ldc; p.out_hi = g->out_hi; p.out_lo = g->out_lo;
@@ -754,8 +873,12 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   // left unfilled (their products land in accumulator rows / columns that are never stored)
   p.a_slot = BLOCK_M * bk * 4;
   p.b_slot = B_ROWS * bk * 4;
-  const int stage_bytes = p.a_slot * nops_a + p.b_slot * nops_b;
-  int stages = (224 * 1024 - 1024 - 256 - ((BLOCK_N <= 32 || PERSIST) ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;
+  const int stage_bytes = p.a_slot * p.tma_a + p.b_slot * p.tma_b;
+  const int lo_bytes = p.a_slot * p.split_a + p.b_slot * p.split_b;
+  p.lo_stages = lo_bytes ? 2 : 0;
+  // (split on chip: every byte counts -- the exact 227 KB limit; otherwise the round-1 budget the tuning was done with)
+  const int budget = (lo_bytes ? 227 * 1024 - 1024 - 256 : 224 * 1024 - 1024 - 256) - p.lo_stages * lo_bytes;
+  int stages = (budget - ((BLOCK_N <= 32 || PERSIST) ? stg_bytes(BLOCK_N, SPLIT) : 0)) / stage_bytes;
   if (stages < 1) return TPP_ENOTSUP;
   if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
@@ -764,7 +887,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
   // (narrow tiles only: the wide CTAs -- 576 threads x 67 registers -- are alone on their SM whatever their stage count)
   if (n_tiles >= 4 * 148 && BLOCK_N <= 32) {
-    int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N) : 0)) / stage_bytes;   // three resident CTAs
+    int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N, SPLIT) : 0)) / stage_bytes;   // three resident CTAs
     if (few < 2) few = 2;
     if (stages > few) stages = few;
   }
@@ -772,20 +895,22 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   p.stages = stages;
   constexpr bool NARROW = BLOCK_N <= 32;
   size_t region = (size_t)stages * stage_bytes;
+  p.lo_offset = (int)region;
+  region += (size_t)p.lo_stages * lo_bytes;
   if (NARROW || PERSIST) {
     // persistent CTAs: the epilogue's transpose patches get their own region (the next tile's loads are in flight)
     p.stg_offset = (int)region;
-    region += stg_bytes(BLOCK_N);
+    region += stg_bytes(BLOCK_N, SPLIT);
   } else {
     // the patches alias the pipeline stages (free once the accumulator is complete): the region must hold them
     p.stg_offset = 0;
-    if (region < (size_t)stg_bytes(BLOCK_N)) region = stg_bytes(BLOCK_N);
+    if (region < (size_t)stg_bytes(BLOCK_N, SPLIT)) region = stg_bytes(BLOCK_N, SPLIT);
   }
   p.bar_offset = (int)region;
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -805,14 +930,14 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     static int regs_per_cta = 0;
     if (!regs_per_cta) {
       cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>) != cudaSuccess) return TPP_ENOTSUP;
-      regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N);
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>) != cudaSuccess) return TPP_ENOTSUP;
+      regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N, SPLIT);
     }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     // registers are allocated per warp inside each of the 4 SM sub-partitions (16384 registers each)
-    const int regs_per_warp = regs_per_cta / (num_threads(BLOCK_N) / 32);
+    const int regs_per_warp = regs_per_cta / (num_threads(BLOCK_N, SPLIT) / 32);
     const int warps_per_sm = 4 * (16384 / regs_per_warp);
-    if (per_sm > warps_per_sm / (num_threads(BLOCK_N) / 32)) per_sm = warps_per_sm / (num_threads(BLOCK_N) / 32);
+    if (per_sm > warps_per_sm / (num_threads(BLOCK_N, SPLIT) / 32)) per_sm = warps_per_sm / (num_threads(BLOCK_N, SPLIT) / 32);
     if (per_sm > 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N))) per_sm = 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N));
     if (per_sm < 1) per_sm = 1;
     const unsigned resident = (unsigned)(per_sm * sms);
@@ -837,18 +962,18 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
       const unsigned pairs = (unsigned)std::min(p.total_work, sms / 2);
       cfg.gridDim = dim3(2u * pairs, 1, 1);
     }
-    cfg.blockDim = dim3(num_threads(BLOCK_N), 1, 1);
+    cfg.blockDim = dim3(num_threads(BLOCK_N, SPLIT), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     if (e != cudaSuccess) return (int)e;
     TPP_LAUNCH_STATUS();
   }
-  gemm_tc_kernel<BLOCK_N, PAIR, false><<<grid, num_threads(BLOCK_N), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  gemm_tc_kernel<BLOCK_N, PAIR, false, SPLIT><<<grid, num_threads(BLOCK_N, SPLIT), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
 
@@ -857,8 +982,8 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
 
 extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
   TPP_CHECK_ARG(g && g->a_hi && g->b_hi && g->M > 0 && g->N > 0 && g->K > 0);
-  TPP_CHECK_ARG((g->precision & ~48) == 1 || (g->precision & ~48) == 3);
-  TPP_CHECK_ARG((g->precision & 15) == 1 || ((g->a_lo || (g->precision & 16)) && (g->b_lo || (g->precision & 32))));
+  TPP_CHECK_ARG((g->precision & ~240) == 1 || (g->precision & ~240) == 3);
+  TPP_CHECK_ARG((g->precision & 15) == 1 || ((g->a_lo || (g->precision & (16 | 64))) && (g->b_lo || (g->precision & (32 | 128)))));
   const bool atomic = g->flags & tpp::tc::F_ATOMIC;
   TPP_CHECK_ARG(!atomic || g->out);
   TPP_CHECK_ARG(g->split_k <= 1 || atomic);
@@ -869,6 +994,23 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
   cudaStream_t s = tpp_stream(stream);
   int bn = g->block_n;
   if (bn == 0) bn = g->N <= 16 ? 16 : (g->N <= 32 ? 32 : (g->N <= 64 ? 64 : 128));
+  if ((g->precision & 15) == 3 && (g->precision & (TPP_TC_A_SPLIT | TPP_TC_B_SPLIT)) &&
+      !((g->precision & TPP_TC_A_EXACT) && (g->precision & TPP_TC_B_EXACT))) {
+    // lo halves formed on chip: the SPLIT kernels (extra splitter warps, separate lo ring)
+    const bool a_s = (g->precision & TPP_TC_A_SPLIT) && !(g->precision & TPP_TC_A_EXACT);
+    const bool b_s = (g->precision & TPP_TC_B_SPLIT) && !(g->precision & TPP_TC_B_EXACT);
+    if (a_s || b_s) {
+      switch (bn) {
+        case 64: return tpp::tc::launch<64, false, false, true>(g, g->split_k, s);
+        case 128: return tpp::tc::launch<128, false, false, true>(g, g->split_k, s);
+        case 256: return tpp::tc::launch<256, false, false, true>(g, g->split_k, s);
+        case TPP_TC_TILE_PAIR: return tpp::tc::launch<256, true, false, true>(g, g->split_k, s);
+        case TPP_TC_TILE_PAIR_PERSISTENT: return tpp::tc::launch<256, true, true, true>(g, g->split_k, s);
+        case TPP_TC_TILE_PAIR64_PERSISTENT: return tpp::tc::launch<64, true, true, true>(g, g->split_k, s);
+        default: return TPP_ENOTSUP;      // the narrow (convolution) tiles take pairs only
+      }
+    }
+  }
   switch (bn) {
     case 16: return tpp::tc::launch<16>(g, g->split_k, s);
     case 32: return tpp::tc::launch<32>(g, g->split_k, s);
