@@ -14,10 +14,11 @@ from tpp_b200.common.policy import CategoricalPolicy  # noqa: E402
 
 
 def rel(a, b):
-    """(max-norm error, L2 error), both relative to the float64 reference.  The max norm of a GRADIENT is dominated by
-    ReLU-kink flips: a pre-activation within rounding of zero is masked differently in fp32 and float64, which moves one
-    sample's whole contribution (~1/M of a bias gradient) -- a property of comparing across precisions, not of the
-    kernels (every engine variant hits the same element); the L2 column is insensitive to it."""
+    """(max-norm error, L2 error), both relative to the float64 reference.  The float64 network uses the ENGINE's ReLU
+    masks: a pre-activation within rounding of zero is otherwise masked differently in fp32 and float64, which moves
+    one sample's whole contribution to a weight row (with the random loss gradient used here ~1/sqrt(M) of the row's
+    magnitude: 1e-3 at M = 16384, identical for every engine variant) -- a property of comparing a piecewise-linear
+    network across precisions, not of the kernels."""
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max()), float((a - b).norm() / b.norm())
 
@@ -51,11 +52,14 @@ def main():
             p64 = {k: v.detach().double().clone().requires_grad_(True) for k, v in pol.state_dict().items()}
             names = sorted({k.rsplit(".", 1)[0] for k in p64 if k.startswith("embedder.")},
                            key=lambda s: [int(t) if t.isdigit() else t for t in s.split(".")])
+            # (ReLU masks taken from the engine's own activations: a pre-activation within rounding of zero would
+            # otherwise be masked differently in float64, moving one sample's whole contribution -- see rel())
+            ws = eng._workspace(M)
             h = x64
             for i, n in enumerate(names):
                 h = h @ p64[n + ".weight"].t() + p64[n + ".bias"]
-                if i < len(names) - 1:
-                    h = h.clamp_min(0)
+                if eng.layers[i][4]:
+                    h = h * (ws.h[i]["hi"][:, :h.shape[1]] > 0).double()
             out = torch.cat((h @ p64["fc_policy.weight"].t() + p64["fc_policy.bias"],
                              h @ p64["fc_value.weight"].t() + p64["fc_value.bias"]), 1)
             (out * dhead[:, :A + 1].double()).sum().backward()
