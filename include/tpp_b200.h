@@ -332,6 +332,20 @@ int tpp_feature_sparsity_grad(const uint64_t* scratch, int32_t E, float coef, fl
 int tpp_bias_act_split(const float* x, int64_t ld_in, int32_t M, int32_t N, const float* bias, int32_t relu, float* out,
                        float* out_hi, float* out_lo, int64_t ld_out, void* stream);
 
+/* ---- recurrent policy: GRU cell at prediction time ------------------------------------------------------ */
+/* CategoricalPolicy(recurrent=True) (common/policy.py:49-69) runs the embedder's latent through nn.GRU(D, D) in
+ * PPO.predict (agents/ppo.py:72-81, common/model.py:219-226: one cell step on hxs * (1 - done)); PPO.optimize does
+ * not call it (agents/ppo.py:116-121).  The cell is two tpp_gemm_tc launches (gi = x W_ih^T + b_ih and
+ * gh = hm W_hh^T + b_hh, [N][3D], gate order r, z, n) between these two kernels:
+ * tpp_gru_mask_split: hm = h * (1 - done) as the TF32 (hi, lo) operand [N][ld] (columns >= D zero); done nullable.
+ * tpp_gru_gates: r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r gh_n), h' = (1 - z) n + z hm -> h_out
+ *   [N][ldo] plain fp32 (may alias h_prev) and, when non-NULL, the (hi, lo) pair [N][ld] the head GEMM reads.      */
+int tpp_gru_mask_split(const float* h, int64_t ldh, const uint8_t* done, int32_t N, int32_t D, float* hm_hi,
+                       float* hm_lo, int64_t ld, void* stream);
+int tpp_gru_gates(const float* gi, const float* gh, int64_t ldg, const float* h_prev, int64_t ldh, const uint8_t* done,
+                  int32_t N, int32_t D, float* h_out, int64_t ldo, float* out_hi, float* out_lo, int64_t ld,
+                  void* stream);
+
 /* ---- policy: action sampling at rollout --------------------------------------------------------------- */
 /* head: [N][ld_head] rows of (A logits, 1 value).  Writes act int32, logp, value for slot t.
  * Replaces dist.sample()/log_prob in PPO.predict (agents/ppo.py:72-81, common/policy.py:74-87).

@@ -257,9 +257,75 @@ def mint_config():
     print("config sets:", list(sub))
 
 
+def mint_recurrent():
+    """Row N4: the reference's recurrent policy (CategoricalPolicy(recurrent=True)) -- a chain of predict-time forward
+    passes with done masks, and PPO.optimize on env-permuting minibatches (which does not call the GRU)."""
+    storage_mod = ref_shim.load("common.storage")
+    model_mod = ref_shim.load("common.model")
+    policy_mod = ref_shim.load("common.policy")
+    ppo_mod = ref_shim.load("agents.ppo")
+    out = {}
+    T, N, A, D = 16, 16, 3, 64
+    torch.manual_seed(78)
+    pol = policy_mod.CategoricalPolicy(model_mod.MLPModel(in_channels=9, depth=4, mid_weight=64, latent_size=D), True, A)
+    names = [n for n, _ in pol.named_parameters()]
+    out["param_names"] = np.array(names)
+    for n, p in pol.named_parameters():
+        out[f"init/{n}"] = p.detach().numpy().copy()
+    g = torch.Generator().manual_seed(6)
+    # --- predict chain: obs_t, done_{t-1} -> logits, value, hidden_{t+1} (agents/ppo.py:72-81) ---
+    steps = 6
+    obs = torch.randn(steps, N, 9, generator=g)
+    done = (torch.rand(steps, N, generator=g) < 0.3).float()
+    done[0] = 0
+    h = torch.zeros(N, D)
+    logits, values, hiddens = [], [], [h.numpy().copy()]
+    with torch.no_grad():
+        for t in range(steps):
+            dist, v, h = pol(obs[t], h, 1 - done[t])
+            logits.append(dist.logits.numpy().copy())
+            values.append(v.numpy().copy())
+            hiddens.append(h.numpy().copy())
+    out["chain_obs"], out["chain_done_prev"] = obs.numpy(), done.numpy()
+    out["chain_logits"], out["chain_value"], out["chain_hidden"] = np.stack(logits), np.stack(values), np.stack(hiddens)
+    # --- optimize() ---
+    st = storage_mod.Storage((9,), D, T, N, "cpu")
+    st.obs_batch = torch.randn(T + 1, N, 9, generator=g)
+    st.hidden_states_batch = torch.randn(T + 1, N, D, generator=g)
+    st.act_batch = torch.randint(0, A, (T, N), generator=g).float()
+    st.log_prob_act_batch = -torch.rand(T, N, generator=g) * 1.5 - 0.4
+    st.value_batch = torch.randn(T + 1, N, generator=g) * 0.3
+    st.rew_batch = torch.randn(T, N, generator=g)
+    st.done_batch = (torch.rand(T, N, generator=g) < 0.1).float()
+    st.compute_estimates(0.99, 0.95, True, True)
+    for k in ("obs_batch", "act_batch", "log_prob_act_batch", "value_batch", "rew_batch", "done_batch", "return_batch",
+              "adv_batch"):
+        out[f"opt_{k}"] = getattr(st, k).numpy().copy()
+    agent = ppo_mod.PPO(None, pol, _DummyLogger(), st, "cpu", 1, n_steps=T, n_envs=N, epoch=2, n_minibatch=4,
+                        mini_batch_size=64, gamma=0.99, lmbda=0.95, learning_rate=5e-3, grad_clip_norm=0.5,
+                        eps_clip=0.2, value_coef=0.5, entropy_coef=0.02, x_entropy_coef=0.0)
+    torch.manual_seed(4321)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        summary = agent.optimize()
+    for n, p in pol.named_parameters():
+        out[f"final/{n}"] = p.detach().numpy().copy()
+    out["summary_keys"] = np.array(list(summary.keys()))
+    out["summary_vals"] = np.array([float(v) for v in summary.values()])
+    sd = agent.optimizer.state_dict()
+    out["adam_step"] = np.array(float(sd["state"][0]["step"]))
+    out["adam_state_params"] = np.array(sorted(sd["state"].keys()))       # the GRU's four tensors never get a state
+    np.savez_compressed(os.path.join(OUT, "recurrent.npz"), **out)
+    print("recurrent fixtures ok; GRU unchanged by optimize:",
+          all(np.array_equal(out[f"init/{n}"], out[f"final/{n}"]) for n in names if n.startswith("gru.")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     warnings.filterwarnings("ignore", category=SyntaxWarning)
+    if len(sys.argv) > 1 and sys.argv[1] == "recurrent":
+        mint_recurrent()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "logger":
         mint_logger()
         return
@@ -272,6 +338,7 @@ def main():
     mint_ppo()
     mint_logger()
     mint_config()
+    mint_recurrent()
     print("written to", OUT, [f for f in os.listdir(OUT)])
 
 

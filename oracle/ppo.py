@@ -4,6 +4,10 @@ CPU restatement (torch CPU fp32, the reference's own arithmetic library) of the 
 
 * rollout buffer + GAE + advantage normalisation   -> common/storage.py:21-79
 * minibatch index stream                             -> common/storage.py:81-92 (SubsetRandomSampler/BatchSampler)
+* recurrent (env-permuting) minibatches + GRU policy -> common/storage.py:93-110, common/model.py:212-276,
+                                                        common/policy.py:49-69; NOTE agents/ppo.py:116-121: optimize()
+                                                        evaluates embedder + heads WITHOUT the GRU (its call through
+                                                        the policy is commented out), so the GRU only acts in predict()
 * MLP / IMPALA policies and heads                    -> common/model.py:134-208, 954-980; common/policy.py:36-87
 * PPO loss                                           -> agents/ppo.py:131-169, common/misc_util.py:32-51
 * clip_grad_norm_ + Adam(eps=1e-5) + LR anneal       -> agents/ppo.py:58,173-176; common/misc_util.py:92-96
@@ -45,6 +49,21 @@ def epoch_indices(batch_size, mini_batch_size):
     perm = torch.randperm(batch_size).tolist()
     n = batch_size // mini_batch_size
     return [perm[i * mini_batch_size:(i + 1) * mini_batch_size] for i in range(n)]
+
+
+def recurrent_epoch_indices(n_steps, n_envs, mini_batch_size):
+    """common/storage.py:93-110: one ``torch.randperm(num_envs)``, whole trajectories of ``num_envs_per_batch`` envs per
+    minibatch, rows flattened time-major (``batch[:, idxes].reshape(-1)``).  Returns (list of flat index lists into the
+    [T*N] arrays, list of env index lists)."""
+    per_epoch = (n_steps * n_envs) // mini_batch_size
+    envs_per_batch = n_envs // per_epoch
+    perm = torch.randperm(n_envs)
+    flat, envs = [], []
+    for start in range(0, n_envs, envs_per_batch):
+        idxes = perm[start:start + envs_per_batch]
+        envs.append(idxes.tolist())
+        flat.append((torch.arange(n_steps)[:, None] * n_envs + idxes[None, :]).reshape(-1).tolist())
+    return flat, envs
 
 
 # ----------------------------------------------------------------------------------------------
@@ -113,12 +132,33 @@ class OracleImpala(nn.Module):
         return F.relu(self.fc(h)), fs
 
 
+class _GRU(nn.Module):
+    """common/model.py:212-216: nn.GRU under the name ``gru`` (orthogonal_init leaves an nn.GRU untouched)."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.gru = nn.GRU(d, d)
+
+
 class OraclePolicy(nn.Module):
-    def __init__(self, embedder, action_size):
+    def __init__(self, embedder, action_size, recurrent=False):
         super().__init__()
         self.embedder = embedder
         self.fc_policy = _orth(nn.Linear(embedder.output_dim, action_size), 0.01)
         self.fc_value = _orth(nn.Linear(embedder.output_dim, 1), 1.0)
+        self.recurrent = recurrent
+        if recurrent:
+            self.gru = _GRU(embedder.output_dim)
+
+    def predict(self, x, hx, mask):
+        """policy(obs, hidden, mask) with one row per hidden state (agents/ppo.py:72-81, common/model.py:219-226):
+        -> (distribution, value, next hidden)."""
+        feat, _ = self.embedder.features(x)
+        if self.recurrent:
+            out, hx = self.gru.gru(feat.unsqueeze(0), (hx * mask.unsqueeze(-1)).unsqueeze(0))
+            feat, hx = out.squeeze(0), hx.squeeze(0)
+        log_probs = F.log_softmax(self.fc_policy(feat), dim=1)
+        return torch.distributions.Categorical(logits=log_probs), self.fc_value(feat).reshape(-1), hx
 
     def forward(self, x):
         feat, fs = self.embedder.features(x)
@@ -159,7 +199,7 @@ def ppo_loss(dist, value, act, old_logp, old_value, ret, adv, eps_clip=0.2, valu
 
 
 def optimize(policy, optimizer, data, n_steps, n_envs, epoch=3, n_minibatch=8, mini_batch_size=8192,
-             grad_clip_norm=0.5, **loss_kw):
+             grad_clip_norm=0.5, recurrent=False, **loss_kw):
     """agents/ppo.py:96-208 on a dict of flat [T*N, ...] fp32 tensors
     (obs, act, old_logp, old_value, ret, adv).  Returns the per-minibatch term lists."""
     batch_size = n_steps * n_envs // n_minibatch
@@ -168,8 +208,10 @@ def optimize(policy, optimizer, data, n_steps, n_envs, epoch=3, n_minibatch=8, m
     cnt, logs = 1, []
     fs_coef = loss_kw.pop("fs_coef", 0.0)
     for _ in range(epoch):
-        for idx in epoch_indices(n_steps * n_envs, mini_batch_size):
-            dist, value, fs = policy(data["obs"][idx])
+        batches = recurrent_epoch_indices(n_steps, n_envs, mini_batch_size)[0] if recurrent \
+            else epoch_indices(n_steps * n_envs, mini_batch_size)
+        for idx in batches:
+            dist, value, fs = policy(data["obs"][idx])        # (recurrent too: the GRU is not on optimize()'s path)
             loss, terms = ppo_loss(dist, value, data["act"][idx], data["old_logp"][idx], data["old_value"][idx],
                                    data["ret"][idx], data["adv"][idx], fs=fs, fs_coef=fs_coef, **loss_kw)
             loss.backward()

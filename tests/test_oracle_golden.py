@@ -158,3 +158,36 @@ def test_optimize_matches_reference(golden_dir, tag, x_coef):
     np.testing.assert_allclose(np.mean([l["entropy"] for l in logs]), summ["Loss/entropy"], rtol=1e-6)
     np.testing.assert_allclose(np.mean([l["x_entropy"] for l in logs]), summ["Loss/x_entropy"], rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(np.mean([l["total"] for l in logs]), summ["Loss/total"], rtol=1e-6, atol=1e-9)
+
+
+def test_recurrent_policy_chain_and_optimize_match_reference(golden_dir):
+    """Row N4: the oracle's recurrent policy (GRU cell at prediction time) and its optimize() on env-permuting
+    minibatches against fixtures minted from the live reference (oracle/mint_golden.py::mint_recurrent)."""
+    g = _load(golden_dir, "recurrent.npz")
+    T, N, A, D = 16, 16, 3, 64
+    pol = oppo.OraclePolicy(oppo.OracleMLP(9, 4, 64, D), A, recurrent=True)
+    assert [n for n, _ in pol.named_parameters()] == [str(n) for n in g["param_names"]]
+    with torch.no_grad():
+        for n, p in pol.named_parameters():
+            p.copy_(torch.from_numpy(g[f"init/{n}"]))
+        h = torch.zeros(N, D)
+        for t in range(g["chain_obs"].shape[0]):
+            dist, v, h = pol.predict(torch.from_numpy(g["chain_obs"][t]), h, 1 - torch.from_numpy(g["chain_done_prev"][t]))
+            assert np.array_equal(dist.logits.numpy(), g["chain_logits"][t])
+            assert np.array_equal(v.numpy(), g["chain_value"][t]) and np.array_equal(h.numpy(), g["chain_hidden"][t + 1])
+    data = dict(obs=torch.from_numpy(g["opt_obs_batch"][:-1]).reshape(T * N, 9),
+                act=torch.from_numpy(g["opt_act_batch"]).reshape(-1),
+                old_logp=torch.from_numpy(g["opt_log_prob_act_batch"]).reshape(-1),
+                old_value=torch.from_numpy(g["opt_value_batch"][:-1]).reshape(-1),
+                ret=torch.from_numpy(g["opt_return_batch"]).reshape(-1), adv=torch.from_numpy(g["opt_adv_batch"]).reshape(-1))
+    opt = oppo.make_adam(pol, 5e-3)
+    torch.manual_seed(4321)
+    logs = oppo.optimize(pol, opt, data, T, N, epoch=2, n_minibatch=4, mini_batch_size=64, grad_clip_norm=0.5,
+                         eps_clip=0.2, value_coef=0.5, entropy_coef=0.02, x_entropy_coef=0.0, recurrent=True)
+    for n, p in pol.named_parameters():
+        np.testing.assert_allclose(p.detach().numpy(), g[f"final/{n}"], rtol=1e-6, atol=1e-8, err_msg=n)
+        if n.startswith("gru."):                 # optimize() never calls the GRU: no gradient, no Adam state, no change
+            assert np.array_equal(p.detach().numpy(), g[f"init/{n}"])
+    summ = dict(zip(g["summary_keys"], g["summary_vals"]))
+    np.testing.assert_allclose(np.mean([l["total"] for l in logs]), summ["Loss/total"], rtol=1e-6, atol=1e-9)
+    assert len(g["adam_state_params"]) == len(g["param_names"]) - 4

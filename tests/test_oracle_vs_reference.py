@@ -142,3 +142,69 @@ def test_lunar_observation_and_shaping_formulas_are_the_reference_files():
         np.testing.assert_allclose(lunar.shaping(ours)[0], ns["shaping"], rtol=1e-13)
     assert (lunar.FPS, lunar.SCALE, lunar.MAIN_POWER, lunar.SIDE_POWER) == \
         (ns["FPS"], ns["SCALE"], ns["MAIN_ENGINE_POWER"], ns["SIDE_ENGINE_POWER"])
+
+
+def test_recurrent_policy_gru_and_env_permuting_minibatches_match_reference():
+    """Row N4 (recurrent): the reference's CategoricalPolicy(recurrent=True) -- nn.GRU created after the heads, left at
+    torch's default init -- its predict-time cell step, its through-time forward, and Storage.fetch_train_generator(
+    recurrent=True) (common/storage.py:93-110), against the oracle and the product's modules / index generator."""
+    import inspect
+    from oracle import ppo as oppo
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    from tpp_b200.common.storage import Storage
+    model, policy, storage = ref_shim.load("common.model"), ref_shim.load("common.policy"), ref_shim.load("common.storage")
+    torch.manual_seed(4)
+    ref = policy.CategoricalPolicy(model.MLPModel(9, 4, 256, 64), True, 3)
+    torch.manual_seed(4)
+    orc = oppo.OraclePolicy(oppo.OracleMLP(9, 4, 256, 64), 3, recurrent=True)
+    torch.manual_seed(4)
+    mine = CategoricalPolicy(MLPModel(9, 4, 256, 64), True, 3)
+    for other in (orc, mine):
+        assert list(ref.state_dict().keys()) == list(other.state_dict().keys())
+        for (k, a), (_, b) in zip(ref.state_dict().items(), other.state_dict().items()):
+            assert torch.equal(a, b), k
+    g = torch.Generator().manual_seed(0)
+    x, hx = torch.randn(7, 9, generator=g), torch.randn(7, 64, generator=g)
+    mask = torch.tensor([1, 0, 1, 1, 0, 1, 1.0])
+    with torch.no_grad():
+        d_r, v_r, h_r = ref(x, hx, mask)
+        d_o, v_o, h_o = orc.predict(x, hx, mask)
+        d_m, v_m, h_m = mine(x, hx, mask)
+    for d, v, h in ((d_o, v_o, h_o), (d_m, v_m, h_m)):
+        assert torch.equal(d_r.logits, d.logits) and torch.equal(v_r, v) and torch.equal(h_r, h)
+    # through-time forward (T*N rows, hidden re-computed, reset where the mask is zero)
+    T, N = 6, 4
+    xs, h0 = torch.randn(T * N, 9, generator=g), torch.randn(N, 64, generator=g)
+    masks = (torch.rand(T * N, generator=g) > 0.3).float()
+    with torch.no_grad():
+        d_r, v_r, h_r = ref(xs, h0, masks)
+        d_m, v_m, h_m = mine(xs, h0, masks)
+    torch.testing.assert_close(d_m.logits, d_r.logits, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(h_m, h_r, rtol=1e-6, atol=1e-7)
+    # optimize() does not call the GRU: its call through the policy is commented out (agents/ppo.py:116-121)
+    src = inspect.getsource(ref_shim.load("agents.ppo").PPO.optimize)
+    assert "# dist_batch, value_batch, _ = self.policy(obs_batch, hidden_state_batch, mask_batch)" in src
+    assert "self.policy.hidden_to_output(feature_batch)" in src and "self.policy.gru" not in src
+    # env-permuting minibatches
+    T, N, mb = 8, 12, 24                                  # 4 minibatches per epoch of 3 whole trajectories each
+    st_ref = storage.Storage((1,), 5, T, N, "cpu")
+    code = torch.arange((T + 1) * N, dtype=torch.float32).view(T + 1, N)
+    st_ref.obs_batch[:] = code[:, :, None]
+    st_ref.hidden_states_batch[:] = code[:, :, None] + torch.arange(5) / 8.0
+    st_ref.act_batch[:] = code[:T] + 0.25
+    st_ref.done_batch[:] = (code[:T] % 5 == 0).float()
+    st_ref.adv_batch[:] = -code[:T]
+    torch.manual_seed(9)
+    batches = list(st_ref.fetch_train_generator(mini_batch_size=mb, recurrent=True))
+    torch.manual_seed(9)
+    flat, envs = oppo.recurrent_epoch_indices(T, N, mb)
+    torch.manual_seed(9)
+    mine_idx, mine_envs = Storage.recurrent_perm(T, N, mb)
+    assert mine_envs.tolist() == envs
+    assert len(batches) == len(flat) == mine_idx.shape[0] == 4
+    for b, f, e, m in zip(batches, flat, envs, mine_idx):
+        obs, hid, act, done, _, _, _, adv = b
+        assert obs.reshape(-1).long().tolist() == f == m.tolist()
+        assert torch.equal(act, code[:T].reshape(-1)[f] + 0.25) and torch.equal(adv, -code[:T].reshape(-1)[f])
+        assert torch.equal(hid, st_ref.hidden_states_batch[0, e])

@@ -108,6 +108,8 @@ SIGNATURES = {
     "tpp_feature_sparsity": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
     "tpp_feature_sparsity_grad": [_vp, _i32, _f32, _vp, _vp, _vp, _vp],
     "tpp_bias_act_split": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
+    "tpp_gru_mask_split": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp],
+    "tpp_gru_gates": [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],

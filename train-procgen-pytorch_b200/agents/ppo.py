@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _lib, parallel
-from ..common.engine import ImpalaEngineTC, MLPEngine, MLPEngineTC
+from ..common.engine import GRUCellTC, ImpalaEngineTC, MLPEngine, MLPEngineTC
 from ..common.model import ImpalaModel, MLPModel
 from .base_agent import BaseAgent
 
@@ -188,6 +188,16 @@ class PPO(BaseAgent):
         else:
             raise NotImplementedError(f"no engine for embedder {type(policy.embedder).__name__}: the hot path covers "
                                       "MLPModel and ImpalaModel (SURVEY 8a10)")
+        # Recurrent policies (row N4): the GRU acts at prediction time only -- the reference's optimize() evaluates
+        # embedder + heads without it (agents/ppo.py:116-121) on env-permuting minibatches (common/storage.py:93-110).
+        self.recurrent = bool(policy.is_recurrent())
+        self.gru = None
+        if self.recurrent:
+            if not isinstance(self.engine, (MLPEngineTC, ImpalaEngineTC)):
+                raise NotImplementedError("recurrent policies run on the tensor-core engines (matmul='tf32x3' or 'tf32')")
+            self.gru = GRUCellTC(policy)
+            self.fused_rollout = self.fused_tail = False       # the cell sits between the embedder and the heads
+            self.rollout_chains = 1
         self.optimizer = FlatAdam(policy, learning_rate, eps=1e-5, max_grad_norm=grad_clip_norm)
         self.world_size = 1
         self.process_group = None
@@ -231,9 +241,9 @@ class PPO(BaseAgent):
         self.storage.world_size, self.storage.process_group = world_size, process_group
 
     # ------------------------------------------------------------------------------------------
-    def _policy_head(self, obs_slot, storage, env_range=None, slot=0, trunk_only=False, obs_ready=False):
+    def _policy_head(self, obs_slot, storage, env_range=None, slot=0, trunk_only=False, obs_ready=False, heads=True):
         """Policy forward on a rollout slot (or on the env range ``(lo, hi)`` of an image slot, in workspace
-        ``slot``) -> head buffer [n, ld_head]."""
+        ``slot``) -> head buffer [n, ld_head] (``heads=False``: the embedder's latent pair, see ``_recurrent_head``)."""
         N = storage.num_envs
         if storage.is_image:
             lo, hi = env_range or (0, N)
@@ -244,9 +254,21 @@ class PPO(BaseAgent):
                 _lib.call("tpp_frames_to_obs", _lib.ptr(obs_slot[lo:hi]), n, h, w, c, _lib.ptr(mb.obs),
                           _lib.ptr(mb.obs_lo), mb.ld_obs, 1 if mb.raw else 0, _lib.stream_ptr())
                 self.n_launches += 1
-            return self._fwd(mb.obs, n, x_lo=mb.obs_lo, raw=mb.raw, slot=slot, trunk_only=trunk_only)
+            return self._fwd(mb.obs, n, x_lo=mb.obs_lo, raw=mb.raw, slot=slot, trunk_only=trunk_only, heads=heads)
         assert env_range is None, "env ranges are implemented for image (row-major frame) slots"
-        return self._fwd(obs_slot, N, feature_major_ld=storage.ld, trunk_only=trunk_only)
+        return self._fwd(obs_slot, N, feature_major_ld=storage.ld, trunk_only=trunk_only, heads=heads)
+
+    def _recurrent_head(self, storage, t):
+        """Recurrent policy on slot t (agents/ppo.py:72-81): embedder -> GRU cell on the slot's hidden state, masked by
+        the done flags of the PREVIOUS env step (slot 0: the last step of the previous rollout) -> heads.  The new state
+        goes to slot t + 1; the bootstrap call (t = T) advances slot T in place -- like the reference, whose
+        ``store_last`` keeps the state AFTER the extra predict and starts the next rollout from it (:236-237)."""
+        T, N = storage.num_steps, storage.num_envs
+        hid = storage.hidden_states_batch
+        done_prev = storage.done_carry if t == 0 else storage.done_u8[t - 1]
+        pair, ld = self._policy_head(storage.obs_slot(t), storage, heads=False)
+        out, ld_out = self.gru.step(pair, ld, hid[t], done_prev, hid[min(t + 1, T)], N)
+        return self.engine.head_gemm(out, ld_out, N)
 
     def _obs_buf_args(self, storage):
         """(row stride, split) of gathered-observation buffers: the TC engine wants TF32 pairs with ld = ceil32(in)."""
@@ -293,10 +315,26 @@ class PPO(BaseAgent):
                       _lib.stream_ptr())
             self.n_launches += 1
             return
-        head = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, obs_ready=obs_ready)
+        if self.recurrent:
+            assert env_range is None
+            head = self._recurrent_head(storage, t)
+        else:
+            head = self._policy_head(storage.obs_slot(t), storage, env_range=env_range, slot=slot, obs_ready=obs_ready)
         self._sample(head, n, act, logp, value, t, env_offset=lo + getattr(storage, "sample_offset", 0))
 
-    def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False, slot=0, trunk_only=False):
+    def _bootstrap_value(self, storage, obs_ready=False):
+        """value_batch[T] = V(obs_T) (agents/ppo.py:236-237)."""
+        T, N = storage.num_steps, storage.num_envs
+        head = self._recurrent_head(storage, T) if self.recurrent \
+            else self._policy_head(storage.obs_slot(T), storage, obs_ready=obs_ready)
+        storage.value[T, :N] = head[:N, self.n_actions]
+
+    def _fwd(self, x, M, feature_major_ld=None, x_lo=None, raw=False, slot=0, trunk_only=False, heads=True):
+        if not heads:
+            if isinstance(self.engine, MLPEngineTC):
+                return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False,
+                                           raw=raw, slot=slot, heads=False)
+            return self.engine.forward(x, M, feature_major_ld=feature_major_ld, heads=False)
         if trunk_only:
             return self.engine.forward(x, M, feature_major_ld=feature_major_ld, x_lo=x_lo, need_backward=False, raw=raw,
                                        slot=slot, trunk_only=True)
@@ -321,7 +359,17 @@ class PPO(BaseAgent):
         x = torch.as_tensor(np.asarray(obs) if was_numpy else obs).to(dev, torch.float32)
         N = x.shape[0]
         x = x.reshape(N, -1).contiguous()
-        head = self._fwd(x, N)
+        if self.recurrent:      # (hidden_state, done) -> GRU cell -> heads; returns the next hidden state
+            h_np = not torch.is_tensor(hidden_state)
+            h = torch.as_tensor(np.asarray(hidden_state) if h_np else hidden_state).to(dev, torch.float32).contiguous()
+            d = torch.as_tensor(np.asarray(done) if not torch.is_tensor(done) else done).to(dev).ne(0).to(torch.uint8)
+            pair, ld = self._fwd(x, N, heads=False)
+            h_next = torch.empty_like(h)
+            out, ld_out = self.gru.step(pair, ld, h, d.contiguous(), h_next, N)
+            head = self.engine.head_gemm(out, ld_out, N)
+            hidden_state = h_next.cpu().numpy() if h_np else h_next
+        else:
+            head = self._fwd(x, N)
         act = torch.empty(N, dtype=torch.int32, device=dev)
         logp = torch.empty(N, dtype=torch.float32, device=dev)
         value = torch.empty(N, dtype=torch.float32, device=dev)
@@ -349,6 +397,12 @@ class PPO(BaseAgent):
         accum = batch_size / self.mini_batch_size
         mb = self.mini_batch_size
         n_mb = (st.num_steps * st.num_envs) // mb
+        if self.recurrent:      # whole trajectories of num_envs // n_mb permuted envs per minibatch (storage.py:93-110)
+            envs_per_batch = st.num_envs // max(n_mb, 1)
+            if n_mb < 1 or envs_per_batch < 1 or st.num_envs % envs_per_batch:
+                raise NotImplementedError("recurrent minibatches: num_envs must split evenly into T*N // mini_batch_size "
+                                          "groups of whole trajectories")
+            mb, n_mb = st.num_steps * envs_per_batch, st.num_envs // envs_per_batch
         total = n_mb * self.epoch
         dev, A = self.policy.flat.device, self.n_actions
         NS = 4 + 16                                    # doubles per minibatch row of the statistics
@@ -433,7 +487,8 @@ class PPO(BaseAgent):
         epoch_graph = (use_graph and self.use_epoch_graph and (self.world_size == 1 or self.graph_allreduce)
                        and step_every > 0
                        and n_mb % step_every == 0
-                       and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0)
+                       and isinstance(engine, (MLPEngine, MLPEngineTC)) and self.x_entropy_coef == 0.0
+                       and not self.recurrent)
         if epoch_graph:
             if getattr(self, "_epoch_idx", None) is None or self._epoch_idx.shape != (n_mb, mb):
                 self._epoch_idx = torch.zeros(n_mb, mb, dtype=torch.int64, device=dev)
@@ -514,7 +569,8 @@ class PPO(BaseAgent):
                 k += n_mb
             return self._summary(fs_vals)
         for _ in range(self.epoch):
-            idx = st.epoch_indices(mb).view(n_grp, rows)
+            idx = (st.epoch_indices_recurrent(self.mini_batch_size) if self.recurrent
+                   else st.epoch_indices(mb)).view(n_grp, rows)
             for i in range(n_grp):
                 self._idx_cur.copy_(idx[i])
                 entry = graphs.get(graph_key) if use_graph else None
@@ -632,6 +688,8 @@ class PPO(BaseAgent):
         T, N = storage.num_steps, storage.num_envs
         if hasattr(self.engine, "refresh_weights"):
             self.engine.refresh_weights()     # always part of the (captured) rollout: weights changed since last time
+        if self.gru is not None:
+            self.gru.refresh_weights()
         ranges = self._env_ranges(env, storage)
         # envs that can emit the policy's next input rows from their step kernel (Box-World, raw-pixel first layer)
         # save the frames -> obs launch of every step: only slot 0 is converted here
@@ -639,7 +697,8 @@ class PPO(BaseAgent):
                      and self.engine.fused_rollout_ok(True) and getattr(self.engine, "w0_bytes", None) is not None
                      and storage.obs_width <= 768 and storage.obs_width % 4 == 0)
         fold = (len(ranges) == 1 and getattr(env, "emits_policy_obs", False) and storage.is_image
-                and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels and not u8_direct)
+                and isinstance(self.engine, MLPEngineTC) and self.engine.raw_pixels and not u8_direct
+                and not self.recurrent)
         if fold:
             mb = storage.minibatch_buffers(N, *self._obs_buf_args(storage))
             assert mb.raw and mb.obs_lo is None
@@ -654,8 +713,7 @@ class PPO(BaseAgent):
             self._rollout_chains(env, storage, ranges)
         if hasattr(env, "finish_rollout"):
             env.finish_rollout(storage)
-        head = self._policy_head(storage.obs_slot(T), storage, obs_ready=fold)
-        storage.value[T, :N] = head[:N, self.n_actions]
+        self._bootstrap_value(storage, obs_ready=fold)
         _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
         env.advance_tick(T)
         self.n_launches += 2
@@ -716,6 +774,9 @@ class PPO(BaseAgent):
         """Slot T of the finished rollout is slot 0 of the next one."""
         T = storage.num_steps
         storage.obs_slot(0).copy_(storage.obs_slot(T))
+        if self.recurrent:      # hidden state and done flags travel with the observation (agents/ppo.py:219-237)
+            storage.hidden_states_batch[0].copy_(storage.hidden_states_batch[T])
+            storage.done_carry.copy_(storage.done_u8[T - 1])
 
     def train(self, num_timesteps):
         self.total_timesteps = num_timesteps
@@ -798,7 +859,7 @@ class PPO(BaseAgent):
         the actions' device -> host copy).  The ~40 launches are captured once per slot (second visit) and replayed
         afterwards: the step is launch-bound."""
         def body():
-            head = self._policy_head(st.obs_slot(t), st)
+            head = self._recurrent_head(st, t) if self.recurrent else self._policy_head(st.obs_slot(t), st)
             self._sample(head, N, st.act_i32[t], st.logp[t], st.value[t], t,
                          env_offset=getattr(st, "sample_offset", 0))
 
@@ -842,6 +903,8 @@ class PPO(BaseAgent):
             self.policy.eval()
             if hasattr(self.engine, "refresh_weights"):
                 self.engine.refresh_weights()
+            if self.gru is not None:
+                self.gru.refresh_weights()
             for t in range(T):
                 for k, (e, st) in enumerate(pairs):
                     st.stage_obs(t, obs[k])
@@ -850,18 +913,20 @@ class PPO(BaseAgent):
                     act = st.finish_action_fetch()                 # the step's only device -> host read
                     if raw[k]:
                         obs[k], rew, done, info = e.host_step(act)
-                        st.stage_step(t, rew, done, raw_rew=rew)
+                        st.stage_step(t, rew, done, raw_rew=rew, upload_done=self.recurrent)
                     else:
                         obs[k], rew, done, info = e.step(act)
-                        st.stage_step(t, rew, done, info=info)
+                        st.stage_step(t, rew, done, info=info, upload_done=self.recurrent)
             for k, (e, st) in enumerate(pairs):
                 st.stage_obs(T, obs[k])
                 st.flush_steps()
                 if hasattr(e, "finish_rollout"):
                     e.finish_rollout(st)
-                head = self._policy_head(st.obs_slot(T), st)
-                st.value[T, :N] = head[:N, self.n_actions]
+                self._bootstrap_value(st)
                 st.compute_estimates(self.gamma, self.lmbda, self.use_gae, self.normalize_adv)
+                if self.recurrent:      # the next rollout's slot 0 (stage_obs refills the observation itself)
+                    st.hidden_states_batch[0].copy_(st.hidden_states_batch[T])
+                    st.done_carry.copy_(st.done_u8[T - 1])
             _lib.call("tpp_tick_advance", _lib.ptr(self._tick), T, _lib.stream_ptr())
             summary = self.optimize()
             self.t += T * N

@@ -329,13 +329,15 @@ class MLPEngineTC(MLPEngine):
             return 64          # few tiles (rollout forward, M = n_envs): 128 x 64 tiles put twice as many SMs to work
         return 0
 
-    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False, slot=0, trunk_only=False):
+    def forward(self, x, M, feature_major_ld=None, x_lo=None, need_backward=True, raw=False, slot=0, trunk_only=False,
+                heads=True):
         """x: row-major [M, >= in_dim] (plain fp32, or the hi half of a TF32 pair when ``x_lo`` is given, or -- ``raw`` --
         integer pixel values 0..255 with row stride ``ld_in``), or with ``feature_major_ld`` a feature-major
         [in_dim, ld] rollout slot.  ``slot``: private workspace for concurrent forwards on different streams.
         ``trunk_only``: stop in front of the last embedder layer and return its input as plain fp32 ``(tensor, ld)`` --
         the rollout finishes that layer, the heads and the action draw in one CUDA-core launch
-        (``tpp_mlp_tail_sample``)."""
+        (``tpp_mlp_tail_sample``).  ``heads=False``: stop behind the embedder and return its output as the TF32 pair
+        ``((hi, lo), ld)`` -- a recurrent policy puts its GRU cell between the embedder and ``head_gemm``."""
         ws, s = self._workspace(M, slot), _lib.stream_ptr()
         L = len(self.layers)
         if feature_major_ld:
@@ -375,9 +377,16 @@ class MLPEngineTC(MLPEngine):
                      out_pair=None if plain_only else (h["hi"], h["lo"]), ldc=h["ld"],
                      exact=a_flag, block_n=self._bn(M, fout))
             cur, ld_cur, a_mn = (h["hi"], h["lo"]), h["ld"], 0
-        self._tc(cur, ld_cur, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
-                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         self._x = (x, feature_major_ld)
+        if not heads:
+            return cur, ld_cur
+        return self.head_gemm(cur, ld_cur, M, slot)
+
+    def head_gemm(self, latent_pair, ld, M, slot=0):
+        """[A logits | value] = latent Wh^T + bh for M rows of a TF32 latent pair -> the workspace's head buffer."""
+        ws = self._workspace(M, slot)
+        self._tc(latent_pair, ld, (self.wh["hi"], self.wh["lo"]), self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
+                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         return ws.head
 
     @staticmethod
@@ -642,7 +651,7 @@ class ImpalaEngineTC:
             ws.col_src = src
             self._tc(ws.col, c["Kf"], c["wf"], c["Kf"], rows, c["cout"], c["Kf"], **kw)
 
-    def forward(self, x, M, feature_major_ld=None, need_backward=True, train=False):
+    def forward(self, x, M, feature_major_ld=None, need_backward=True, train=False, heads=True):
         assert feature_major_ld is None
         ws = self._workspace(M)
         C0, H0, W0 = self.obs_shape
@@ -678,14 +687,21 @@ class ImpalaEngineTC:
         else:
             self._tc(ws.h, self.enc, self.wfc, self.enc, M, self.latent, self.enc, flags=EPI_BIAS | EPI_RELU,
                      bias=self._p(self.fc_b_off), out=ws.last_plain, out_pair=ws.f, ldc=self.latent)
-        self._tc(ws.f, self.latent, self.wh, self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
-                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         self._x = x
+        if not heads:            # recurrent policies: the GRU cell sits between the fc layer and head_gemm
+            return ws.f, self.latent
+        self.head_gemm(ws.f, self.latent, M)
         if train:   # feature sparsity (logged every minibatch; enters the loss when fs_coef != 0)
             _lib.call("tpp_feature_sparsity", _lib.ptr(ws.h[0]), _lib.ptr(ws.h[1]), M, self.enc, _lib.ptr(ws.fs_key),
                       _lib.ptr(ws.fs), _lib.stream_ptr())
             self.n_launches += 2
             self.last_fs = ws.fs[0]
+        return ws.head
+
+    def head_gemm(self, latent_pair, ld, M, slot=0):
+        ws = self._workspace(M)
+        self._tc(latent_pair, ld, self.wh, self.latent, M, self.A + 1, self.latent, flags=EPI_BIAS,
+                 bias=self._p(self.head_b_off), out=ws.head, ldc=self.ld_head, block_n=16)
         return ws.head
 
     # ------------------------------------------------------------------------------------------
@@ -793,3 +809,58 @@ class ImpalaEngineTC:
                 g += c["gw"][:9 * cin].view(3, 3, cin, cout).permute(3, 2, 0, 1)
         g = self.gflat[self.fc_w_off:self.fc_w_off + self.latent * self.enc].view(self.latent, self.enc_c, self.enc_hw)
         g += self.gfc.view(self.latent, self.enc_hw, self.enc_c).permute(0, 2, 1)
+
+
+class GRUCellTC:
+    """The recurrent core of ``CategoricalPolicy(recurrent=True)`` at prediction time: one ``nn.GRU(D, D)`` cell step
+    (common/model.py:219-226) on the embedder's latent pair, as two 3xTF32 tensor-core GEMMs (``gi``, ``gh``: [N, 3D])
+    between ``tpp_gru_mask_split`` and ``tpp_gru_gates`` (csrc/gru.cu).  There is no backward pass: the reference's
+    ``optimize`` does not call the GRU (agents/ppo.py:116-121), its parameters never receive a gradient."""
+
+    _tc = MLPEngineTC._tc
+
+    def __init__(self, policy):
+        assert policy.flat is not None and policy.recurrent
+        self.policy, self.precision, self.n_launches = policy, 3, 0
+        self.device = policy.flat.device
+        self.D = D = policy.embedder.output_dim
+        self.ld = _ceil(D, 32) * 32
+        f = dict(dtype=torch.float32, device=self.device)
+        self.off = {k: policy.layout[f"gru.gru.{k}"][0] for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0",
+                                                                   "bias_hh_l0")}
+        self.w = {k: (torch.zeros(3 * D, self.ld, **f), torch.zeros(3 * D, self.ld, **f)) for k in ("ih", "hh")}
+        self._ws = {}
+        self.refresh_weights()
+
+    def _p(self, off):
+        return _lib.C.c_void_p(self.policy.flat.data_ptr() + 4 * off)
+
+    def refresh_weights(self):
+        for k in ("ih", "hh"):
+            _lib.call("tpp_split_tf32", self._p(self.off[f"weight_{k}_l0"]), self.D, 3 * self.D, self.D,
+                      _lib.ptr(self.w[k][0]), _lib.ptr(self.w[k][1]), self.ld, None, None, 0, _lib.stream_ptr())
+        self.n_launches += 2
+
+    def step(self, x_pair, ldx, h_prev, done, h_out, N, slot=0):
+        """x_pair: the latent ((hi, lo), row stride ldx); h_prev / h_out: [N, D] fp32 rows (may be the same tensor);
+        done: uint8 [>= N] of the PREVIOUS env step (or None).  Returns ((hi, lo), ld) of h' for ``head_gemm``."""
+        D, ld, s = self.D, self.ld, _lib.stream_ptr()
+        ws = self._ws.get((N, slot))
+        if ws is None:
+            f = dict(dtype=torch.float32, device=self.device)
+            ws = self._ws[(N, slot)] = dict(hm=(torch.zeros(N, ld, **f), torch.zeros(N, ld, **f)),
+                                            out=(torch.zeros(N, ld, **f), torch.zeros(N, ld, **f)),
+                                            gi=torch.zeros(N, 3 * D, **f), gh=torch.zeros(N, 3 * D, **f))
+        assert h_prev.stride(-1) == 1 and h_out.stride(-1) == 1
+        _lib.call("tpp_gru_mask_split", _lib.ptr(h_prev), h_prev.stride(0), _lib.ptr(done), N, D, _lib.ptr(ws["hm"][0]),
+                  _lib.ptr(ws["hm"][1]), ld, s)
+        bn = 64 if N * 3 * D <= 148 * 128 * 128 // 2 else 0
+        self._tc(x_pair, ldx, self.w["ih"], ld, N, 3 * D, D, flags=EPI_BIAS, bias=self._p(self.off["bias_ih_l0"]),
+                 out=ws["gi"], ldc=3 * D, block_n=bn)
+        self._tc(ws["hm"], ld, self.w["hh"], ld, N, 3 * D, D, flags=EPI_BIAS, bias=self._p(self.off["bias_hh_l0"]),
+                 out=ws["gh"], ldc=3 * D, block_n=bn)
+        _lib.call("tpp_gru_gates", _lib.ptr(ws["gi"]), _lib.ptr(ws["gh"]), 3 * D, _lib.ptr(h_prev), h_prev.stride(0),
+                  _lib.ptr(done), N, D, _lib.ptr(h_out), h_out.stride(0), _lib.ptr(ws["out"][0]), _lib.ptr(ws["out"][1]),
+                  ld, s)
+        self.n_launches += 2
+        return ws["out"], ld

@@ -112,3 +112,29 @@ class ImpalaModel(nn.Module):
         out = self.forward_from_pool(h)
         feature_sparsity = torch.mean(torch.max(torch.tanh(torch.abs(h * 100)), 0)[0])
         return out, [], feature_sparsity, None
+
+
+class GRU(nn.Module):
+    """The reference's recurrent core (common/model.py:212-276): ``nn.GRU(input, hidden)`` under the name ``gru`` -- the
+    reference passes it through ``orthogonal_init``, which only touches Linear / Conv2d, so it keeps torch's default
+    uniform initialisation (and its draws from the global generator).  ``forward(x, hxs, masks)``: with one row per
+    hidden state (prediction) a single cell step on ``hxs * masks``; otherwise ``x`` is a ``(T, N, .)`` batch flattened
+    to ``(T*N, .)`` and the hidden state is re-computed through time, reset where ``masks`` is zero.  This module is the
+    torch statement of the contract (tests, checkpoints); rollouts run ``tpp_gru_cell`` on its parameters."""
+
+    def __init__(self, input_size, hidden_size):
+        super().__init__()
+        self.gru = orthogonal_init(nn.GRU(input_size, hidden_size), gain=1.0)
+
+    def forward(self, x, hxs, masks):
+        if x.size(0) == hxs.size(0):
+            x, hxs = self.gru(x.unsqueeze(0), (hxs * masks.unsqueeze(-1)).unsqueeze(0))
+            return x.squeeze(0), hxs.squeeze(0)
+        N = hxs.size(0)
+        T = x.size(0) // N
+        x, masks = x.view(T, N, x.size(1)), masks.view(T, N)
+        h, outs = hxs, []
+        for t in range(T):          # the reference batches runs of mask == 1 into one cuDNN call: the same recurrence
+            h = self.gru(x[t:t + 1], (h * masks[t].unsqueeze(-1)).unsqueeze(0))[1].squeeze(0)
+            outs.append(h)
+        return torch.stack(outs).view(T * N, -1), h

@@ -11,23 +11,25 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.distributions import Categorical
 
-from .model import orthogonal_init
+from .model import GRU, orthogonal_init
 
 
 class CategoricalPolicy(nn.Module):
     def __init__(self, embedder, recurrent, action_size, has_vq=False, continuous_actions=False,
                  logsumexp_logits_is_v=False, extra_params=False):
         super().__init__()
-        if recurrent or has_vq or continuous_actions or logsumexp_logits_is_v or extra_params:
-            raise NotImplementedError("recurrent / VQ / continuous / logsumexp-value / extra-param policies are "
-                                      "outside the north-star hot path (SURVEY section 8f, N4)")
+        if has_vq or continuous_actions or logsumexp_logits_is_v or extra_params:
+            raise NotImplementedError("VQ / continuous / logsumexp-value / extra-param policies are outside the "
+                                      "north-star hot path (SURVEY section 8f)")
         self.embedder = embedder
-        self.has_vq, self.continuous_actions, self.recurrent = False, False, False
+        self.has_vq, self.continuous_actions, self.recurrent = False, False, bool(recurrent)
         self.action_size = action_size
         self.logsumexp_logits_is_v = False
         self.fc_policy = orthogonal_init(nn.Linear(embedder.output_dim, action_size), gain=0.01)
         self.fc_value = orthogonal_init(nn.Linear(embedder.output_dim, 1), gain=1.0)
         self.target_entropy = np.log(action_size)
+        if self.recurrent:      # created last, like the reference (common/policy.py:49-51): same draws, same keys
+            self.gru = GRU(embedder.output_dim, embedder.output_dim)
         self.flat = self.flat_grad = None
         self.layout = None
 
@@ -37,6 +39,8 @@ class CategoricalPolicy(nn.Module):
     # ---- reference forward contract (plain torch ops; the engine does not use these) -----------------
     def forward(self, x, hx, masks):
         hidden = self.embedder(x)
+        if self.recurrent:
+            hidden, hx = self.gru(hidden, hx, masks)
         p, v = self.hidden_to_output(hidden)
         return p, v, hx
 
@@ -50,7 +54,10 @@ class CategoricalPolicy(nn.Module):
     # ---- flat parameter buffer ------------------------------------------------------------------------
     def flat_order(self):
         names = [f"embedder.{n}" for n, _ in self.embedder.named_parameters()]
-        return names + ["fc_policy.weight", "fc_value.weight", "fc_policy.bias", "fc_value.bias"]
+        names += ["fc_policy.weight", "fc_value.weight", "fc_policy.bias", "fc_value.bias"]
+        if self.recurrent:      # behind the heads: the engines' offsets do not move
+            names += [f"gru.gru.{n}" for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+        return names
 
     def flatten_(self, device=None):
         """Move every parameter into one flat fp32 buffer (and .grad into a parallel flat buffer)."""

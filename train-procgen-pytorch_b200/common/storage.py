@@ -86,6 +86,7 @@ class Storage:
         self.moments = torch.zeros(3, dtype=torch.float64, device=dev)
         self.info_batch = deque(maxlen=T)
         self._hidden = None
+        self.done_carry = torch.zeros(ld, dtype=torch.uint8, device=dev)   # done flags of the previous rollout's last step
         self.step = 0
 
     # ---- reference-shaped public tensors -------------------------------------------------------------
@@ -179,6 +180,8 @@ class Storage:
     def store(self, obs, hidden_state, act, rew, done, info, log_prob_act, value):
         s, N = self.step, self.num_envs
         self._store_obs(s, obs)
+        if self.hidden_state_size and hidden_state is not None and np.size(hidden_state):
+            self.hidden_states_batch[s] = self._t(hidden_state, torch.float32).reshape(N, -1)
         self.act_i32[s, :N] = self._t(act, torch.int32).reshape(-1)
         self.rew[s, :N] = self._t(rew, torch.float32).reshape(-1)
         self.done_u8[s, :N] = self._t(done, torch.uint8).reshape(-1)
@@ -219,7 +222,7 @@ class Storage:
         self.start_action_fetch(slot)
         return self.finish_action_fetch()
 
-    def stage_step(self, slot, rew, done, info=None, raw_rew=None):
+    def stage_step(self, slot, rew, done, info=None, raw_rew=None, upload_done=False):
         """Host-env staging of one step's reward / done vectors (the action, log-prob and value are already in the rollout:
         they were produced on the device).  Rows collect in pinned host memory and go up in ONE copy per rollout
         (``flush_steps``).  The raw env reward the logger wants (common/storage.py:131-137) is ``raw_rew`` or, like the
@@ -234,6 +237,9 @@ class Storage:
         if raw_rew is not None:
             h["raw"][slot, :N] = torch.as_tensor(np.asarray(raw_rew, dtype=np.float32).reshape(-1))
             h["has_raw"] = True
+        if upload_done:      # recurrent policies mask the hidden state of step slot + 1 with these flags: N bytes now
+            self.done_u8[slot].copy_(h["done"][slot], non_blocking=True)
+            self.h2d_bytes += N
 
     def flush_steps(self):
         """One H2D copy per rollout of the staged reward / done (/ raw reward) rows."""
@@ -249,6 +255,8 @@ class Storage:
 
     def store_last(self, last_obs, last_hidden_state, last_value):
         self._store_obs(self.num_steps, last_obs)
+        if self.hidden_state_size and last_hidden_state is not None and np.size(last_hidden_state):
+            self.hidden_states_batch[self.num_steps] = self._t(last_hidden_state, torch.float32).reshape(self.num_envs, -1)
         self.value[self.num_steps, :self.num_envs] = self._t(last_value, torch.float32).reshape(-1)
 
     # ---- GAE -----------------------------------------------------------------------------------------------
@@ -307,6 +315,29 @@ class Storage:
         idx = perm[:n_mb * mini_batch_size].view(n_mb, mini_batch_size)
         return idx.pin_memory().to(self.device, non_blocking=True)
 
+    @staticmethod
+    def recurrent_perm(num_steps, num_envs, mini_batch_size):
+        """Minibatches of a recurrent policy (common/storage.py:93-110): ONE ``torch.randperm(num_envs)`` on the default
+        CPU generator, ``num_envs // (T*N // mini_batch_size)`` whole trajectories per minibatch, rows flattened
+        time-major like ``batch[:, idxes].reshape(-1)``.  Host side: returns (int64 [n_batches, T * envs_per_batch] flat
+        indices t*N + e, int64 [n_batches, envs_per_batch] env indices).  Ragged last batches (num_envs not a multiple
+        of the per-batch env count) are refused: every kernel of the update is shaped by the minibatch size."""
+        per_epoch = (num_steps * num_envs) // mini_batch_size
+        if per_epoch < 1 or num_envs // per_epoch < 1:
+            raise ValueError("recurrent minibatches need mini_batch_size <= T*N and at least one env per minibatch")
+        envs_per_batch = num_envs // per_epoch
+        if num_envs % envs_per_batch:
+            raise NotImplementedError(f"ragged recurrent minibatches ({num_envs} envs in batches of {envs_per_batch})")
+        envs = torch.randperm(num_envs).view(-1, envs_per_batch)
+        flat = (torch.arange(num_steps).view(1, -1, 1) * num_envs + envs.view(-1, 1, envs_per_batch))
+        return flat.reshape(envs.shape[0], -1), envs
+
+    def epoch_indices_recurrent(self, mini_batch_size):
+        """``recurrent_perm`` for this storage, on the device ([n_batches, rows] int64): rows of ``gather``."""
+        flat, envs = self.recurrent_perm(self.num_steps, self.num_envs, mini_batch_size)
+        self.last_env_perm = envs
+        return flat.pin_memory().to(self.device, non_blocking=True)
+
     def epoch_perm_pinned(self, mini_batch_size, slot):
         """The same draw as ``epoch_indices`` left in a reusable pinned host buffer (``slot``): the caller uploads it
         on a copy stream while the previous epoch's kernels run.  Returns (pinned int32 [n_mb, mb], ready event or
@@ -349,10 +380,17 @@ class Storage:
         return out
 
     def fetch_train_generator(self, mini_batch_size=None, recurrent=False):
-        if recurrent:
-            raise NotImplementedError("recurrent minibatching is a 'next' row (SURVEY 8f N4)")
         batch = self.num_steps * self.num_envs
         mini_batch_size = mini_batch_size or batch
+        if recurrent:       # whole trajectories of permuted envs; only the INITIAL hidden states travel (storage.py:99-102)
+            idx = self.epoch_indices_recurrent(mini_batch_size)
+            for i in range(idx.shape[0]):
+                rows = idx.shape[1]
+                out = self.gather(idx[i], MiniBatch(rows, self.obs_width, _round_up(self.obs_width, 4), self.device))
+                obs = out.obs[:, :self.obs_width].reshape(rows, *self.obs_shape)
+                hidden = self.hidden_states_batch[0, self.last_env_perm[i].to(self.device)]
+                yield obs, hidden, out.act.float(), out.done, out.logp, out.value, out.ret, out.adv
+            return
         idx = self.epoch_indices(mini_batch_size)
         hidden = torch.zeros(1, self.hidden_state_size, device=self.device).expand(batch, self.hidden_state_size)
         for i in range(idx.shape[0]):
