@@ -142,10 +142,12 @@ int tpp_vecnormalize_step(double* ret, double* rms, const void* raw_rew, int raw
 /* The same for the T steps of a finished rollout in one launch (identical arithmetic, step after step): raw_rew int32
  * [T][ld], done u8 [T][ld] -> out_rew f32 [T][ld] normalised+clipped and (nullable) out_raw f32 [T][ld] = the raw
  * rewards as floats for the logger.  Rewards never feed back into the rollout, so the per-step cross-env reduction
- * can leave the step's critical path (and env ranges can step independently).                              */
+ * can leave the step's critical path (and env ranges can step independently).  With scratch (>= T*ld + 3T doubles)
+ * the work is four short parallel launches -- returns per env, batch moments per step, the sequential Chan merge of T
+ * moment pairs, normalisation -- instead of one CTA walking the T steps (n_envs <= 65536 there).                */
 int tpp_vecnormalize_rollout(double* ret, double* rms, const int32_t* raw_rew, const uint8_t* done, float* out_rew,
                              float* out_raw, int32_t T, int32_t n_envs, int64_t ld, double gamma, double cliprew,
-                             double epsilon, void* stream);
+                             double epsilon, double* scratch, int64_t scratch_doubles, void* stream);
 
 /* ---- rollout storage ----------------------------------------------------------------------------------- */
 /* GAE(gamma, lambda) reverse scan with done-masking + returns + global first/second moments.

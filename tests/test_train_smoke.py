@@ -84,10 +84,12 @@ def test_boxworld_rollout_in_env_ranges_equals_whole_batch_rollout(use_graph):
             torch.testing.assert_close(outs[0][k], o[k], rtol=1e-5, atol=1e-6, msg=k)
 
 
+@pytest.mark.parametrize("parallel", [False, True])                 # one CTA walking the steps / four parallel launches
 @pytest.mark.parametrize("N,ld", [(1000, 1024), (5000, 5024)])      # register path (<= 4096 envs) and the generic one
-def test_vecnormalize_rollout_kernel_equals_per_step_kernel(N, ld):
+def test_vecnormalize_rollout_kernel_equals_per_step_kernel(N, ld, parallel):
     from tpp_b200 import _lib
     T = 37
+    scratch = torch.zeros(T * ld + 3 * T if parallel else 1, dtype=torch.float64, device="cuda")
     g = torch.Generator().manual_seed(3)
     raw = torch.randint(-1, 12, (T, ld), generator=g, dtype=torch.int32).cuda()
     done = (torch.rand(T, ld, generator=g) < 0.05).to(torch.uint8).cuda()
@@ -98,7 +100,8 @@ def test_vecnormalize_rollout_kernel_equals_per_step_kernel(N, ld):
         _lib.call("tpp_vecnormalize_step", _lib.ptr(ret_a), _lib.ptr(rms_a), _lib.ptr(raw[t]), 1, _lib.ptr(done[t]),
                   _lib.ptr(out_a[t]), N, 0.999, 10.0, 1e-8, _lib.stream_ptr())
     _lib.call("tpp_vecnormalize_rollout", _lib.ptr(ret_b), _lib.ptr(rms_b), _lib.ptr(raw), _lib.ptr(done),
-              _lib.ptr(out_b), _lib.ptr(raw_f), T, N, ld, 0.999, 10.0, 1e-8, _lib.stream_ptr())
+              _lib.ptr(out_b), _lib.ptr(raw_f), T, N, ld, 0.999, 10.0, 1e-8, _lib.ptr(scratch) if parallel else None,
+              scratch.numel() if parallel else 0, _lib.stream_ptr())
     torch.testing.assert_close(out_a[:, :N], out_b[:, :N], rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(ret_a, ret_b, rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(rms_a, rms_b, rtol=1e-12, atol=0)

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TPP_B200_LIB") or os.path.join(_HERE, "csrc", "libtpp_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class TppError(RuntimeError):
@@ -117,7 +117,7 @@ SIGNATURES = {
     "tpp_mlp_tail_sample": [_vp, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _u64,
                             _vp, _u64, _i32, _i32, _vp],
     "tpp_policy_rollout_fused": [C.POINTER(FusedPolicy), _vp],
-    "tpp_vecnormalize_rollout": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f64, _f64, _f64, _vp],
+    "tpp_vecnormalize_rollout": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f64, _f64, _f64, _vp, _i64, _vp],
     "tpp_ppo_loss_fwd_bwd": [C.POINTER(LossCfg), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "tpp_ppo_pbar": [_vp, _i32, _i32, _i32, _vp, _vp],
     "tpp_ppo_loss_fwd_bwd_grouped": [C.POINTER(LossCfg), _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
