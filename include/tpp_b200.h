@@ -440,6 +440,20 @@ int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n, void* stre
 /* clip_grad_norm_(max_grad_norm) + Adam(lr, betas, eps) + zero grad over flat buffers, one pass.
  * Replaces agents/ppo.py:173-176 (torch.nn.utils.clip_grad_norm_, optim.Adam(eps=1e-5)).                 */
 int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n, void* stream);
+/* The same step that also refreshes the tensor-core operand copies of the parameters it moves: view k says that the
+ * flat range [offset, offset + rows*cols) is a row-major [rows][cols] weight whose TF32 (hi, lo) pair lives at
+ * hi / lo [rows][ld] (x = p * scale when scale != 0; column c written at col_of[c] when col_of != NULL -- the
+ * frame-byte-order copy of a first layer).  Arithmetic of tpp_split_tf32.  Replaces the re-split launches behind every
+ * optimizer step (nine for the depth-4 MLP).                                                                    */
+#define TPP_MAX_WEIGHT_VIEWS 8
+typedef struct {
+  int64_t offset; int32_t rows, cols;
+  float* hi; float* lo; int64_t ld;
+  float scale; int32_t _pad;
+  const int32_t* col_of;
+} tpp_weight_view;
+int tpp_adam_clip_step_views(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n,
+                             const tpp_weight_view* views, int32_t n_views, void* stream);
 
 /* ---- multi-GPU: gradient all-reduce over peer memory, fused with the norm reduction ----------------------- */
 /* One-shot all-reduce of the flat gradient across `world` (<= 8) GPUs of one node + tpp_grad_sqnorm of the SUM, in one

@@ -319,3 +319,28 @@ def test_rollout_tail_kernel_matches_gemm_head_and_sampler(image, N):
     same = a1 == a0
     torch.testing.assert_close(l1[same], l0[same], rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(v1, v0, rtol=1e-4, atol=1e-5 * float(v0.abs().max()) + 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("image", [False, True])
+def test_adam_step_refreshes_operand_views(image):
+    """tpp_adam_clip_step_views leaves every tensor-core operand copy of the parameters (plain, 1/255-scaled and
+    frame-byte-order first layer, heads) exactly as tpp_split_tf32-based refresh_weights() would."""
+    from tpp_b200.agents.ppo import FlatAdam
+    from tpp_b200.common.engine import MLPEngineTC
+    from tpp_b200.common.model import MLPModel
+    from tpp_b200.common.policy import CategoricalPolicy
+    torch.manual_seed(5)
+    in_dim = 588 if image else 9
+    pol = CategoricalPolicy(MLPModel(in_dim, 4, 256, 64), False, 4).to("cuda").flatten_()
+    eng = MLPEngineTC(pol, 4, raw_pixels=image, obs_shape=(3, 14, 14) if image else None)
+    opt = FlatAdam(pol, 1e-2)
+    pairs = [w for w in eng.w] + [eng.wh] + ([eng.w0_raw, eng.w0_bytes] if image else [])
+    for it in range(3):
+        pol.flat_grad.copy_(torch.randn_like(pol.flat_grad))
+        opt.step(eng.weight_views())
+        got = [(w["hi"].clone(), w["lo"].clone()) for w in pairs]
+        eng.refresh_weights()
+        for (hi, lo), w in zip(got, pairs):
+            assert torch.equal(hi, w["hi"]) and torch.equal(lo, w["lo"])
+    assert opt.step_count == 3

@@ -77,6 +77,13 @@ EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM, EPI_ADD, EPI_RELU_OUT, EPI_PAIR_RELU = 
 
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double
 
+class WeightView(C.Structure):            # == tpp_weight_view
+    _fields_ = [("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32), ("hi", C.c_void_p), ("lo", C.c_void_p),
+                ("ld", C.c_int64), ("scale", C.c_float), ("_pad", C.c_int32), ("col_of", C.c_void_p)]
+
+
+MAX_WEIGHT_VIEWS = 8
+
 # name -> argtypes (every function returns int status unless listed in _SPECIAL)
 SIGNATURES = {
     "tpp_version": [],
@@ -123,6 +130,7 @@ SIGNATURES = {
     "tpp_ppo_loss_fwd_bwd_grouped": [C.POINTER(LossCfg), _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_grad_sqnorm": [_vp, _vp, _i64, _vp],
     "tpp_adam_clip_step": [_vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "tpp_adam_clip_step_views": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp],
     "tpp_peer_allreduce_sqnorm": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
 }
 _NO_STATUS = {"tpp_version"}

@@ -71,11 +71,11 @@ class FlatAdam:
             self._f64[0:1].copy_(self._lr_pinned, non_blocking=True)
             self._lr_on_device = lr
 
-    def step(self):
+    def step(self, views=None):
         self._sync_lr()
-        self.launch()
+        self.launch(views)
 
-    def launch(self):
+    def launch(self, views=None):
         """The two kernels of a step (capturable in a CUDA graph; ``_sync_lr`` must have run outside the capture).  With a
         peer reducer (env sharding on one node) the first one is the one-shot all-reduce over NVLink peer memory fused
         with the norm reduction, and Adam runs on the reduced copy."""
@@ -86,8 +86,10 @@ class FlatAdam:
             g = self.peer.reduced
         else:
             _lib.call("tpp_grad_sqnorm", _lib.ptr(self.state), _lib.ptr(self.gflat), n, s)
-        _lib.call("tpp_adam_clip_step", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(g),
-                  _lib.ptr(self.m), _lib.ptr(self.v), n, s)
+        # ``views``: an engine's (tpp_weight_view array, count): the step also rewrites the tensor-core operand copies
+        arr, cnt = views if views is not None else (None, 0)
+        _lib.call("tpp_adam_clip_step_views", _lib.ptr(self.state), _lib.ptr(self.flat), _lib.ptr(g),
+                  _lib.ptr(self.m), _lib.ptr(self.v), n, arr, cnt, s)
         self.n_launches += 2
 
     @property
@@ -503,8 +505,9 @@ class PPO(BaseAgent):
                     if ((i + 1) * G) % step_every == 0:
                         if self.world_size > 1 and self.optimizer.peer is None:   # NCCL all-reduce captured in the graph
                             parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
-                        self.optimizer.launch()
-                        if hasattr(engine, "refresh_weights"):
+                        views = engine.weight_views() if hasattr(engine, "weight_views") else None
+                        self.optimizer.launch(views)
+                        if views is None and hasattr(engine, "refresh_weights"):
                             engine.refresh_weights()
 
             def counts():
@@ -599,8 +602,9 @@ class PPO(BaseAgent):
                 if k % accum == 0:                 # k minibatches done this call (reference: cnt % accum, :173)
                     if self.world_size > 1 and self.optimizer.peer is None:
                         parallel.allreduce_gradients_(self.policy.flat_grad, self.process_group)
-                    self.optimizer.step()
-                    if hasattr(engine, "refresh_weights"):
+                    views = engine.weight_views() if hasattr(engine, "weight_views") else None
+                    self.optimizer.step(views)
+                    if views is None and hasattr(engine, "refresh_weights"):
                         engine.refresh_weights()
         return self._summary(fs_vals)
 

@@ -222,6 +222,34 @@ class MLPEngineTC(MLPEngine):
                           _lib.ptr(self.w0_bytes["lo"]), self.w0_bytes["ldk"], None, None, 0, s)
                 self.n_launches += 1
 
+    def weight_views(self):
+        """(ctypes array of tpp_weight_view, count): where the TF32 operand copies of every parameter live, for
+        ``tpp_adam_clip_step_views`` -- the optimizer step then leaves them current and ``refresh_weights`` is not
+        needed behind it."""
+        if getattr(self, "_views", None) is None:
+            views = []
+
+            def add(off, rows, cols, w, scale=0.0, col_of=None):
+                v = _lib.WeightView()
+                v.offset, v.rows, v.cols, v.ld, v.scale = off, rows, cols, w["ldk"] if "ldk" in w else cols, scale
+                v.hi, v.lo = w["hi"].data_ptr(), w["lo"].data_ptr()
+                v.col_of = col_of.data_ptr() if col_of is not None else None
+                views.append(v)
+            for (w_off, b_off, fin, fout, relu), w in zip(self.layers, self.w):
+                add(w_off, fout, fin, w)
+            add(self.head_w_off, self.A + 1, self.latent, self.wh)
+            if self.raw_pixels:
+                w_off, _, fin, fout, _ = self.layers[0]
+                add(w_off, fout, fin, self.w0_raw, 1.0 / 255.0)
+                if self.w0_bytes is not None:
+                    inv = torch.empty_like(self._byte_perm)
+                    inv[self._byte_perm] = torch.arange(fin, device=self.device)
+                    self._byte_col = inv.to(torch.int32)       # feature c of a weight row sits at frame byte inv[c]
+                    add(w_off, fout, fin, self.w0_bytes, 1.0 / 255.0, self._byte_col)
+            assert len(views) <= _lib.MAX_WEIGHT_VIEWS
+            self._views = ((_lib.WeightView * len(views))(*views), len(views))
+        return self._views
+
     def _workspace(self, M, slot=0):
         ws = self._ws.get((M, slot))
         if ws is None:

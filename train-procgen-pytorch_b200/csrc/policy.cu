@@ -374,9 +374,15 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(tpp_adam_state* st, co
   if (threadIdx.x == 0) atomicAdd(&st->sqnorm[slot], s);
 }
 
+struct WeightViews {
+  tpp_weight_view v[TPP_MAX_WEIGHT_VIEWS];
+  int n;
+};
+
 __global__ void __launch_bounds__(256) adam_clip_kernel(tpp_adam_state* st, float* __restrict__ p,
                                                         float* __restrict__ g, float* __restrict__ m,
-                                                        float* __restrict__ v, int64_t n, unsigned int* ticket) {
+                                                        float* __restrict__ v, int64_t n, unsigned int* ticket,
+                                                        const __grid_constant__ WeightViews views) {
   __shared__ float sc[6];
   const int step0 = st->step;
   const int slot = step0 & 1;
@@ -401,10 +407,25 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(tpp_adam_state* st, floa
     const float mi = m[i] + (gi - m[i]) * omb1;                     // exp_avg.lerp_(grad, 1-beta1)
     const float vi = v[i] * b2 + omb2 * gi * gi;                     // mul_(beta2).addcmul_(g, g, 1-beta2)
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
+    const float pi = p[i] - step_size * (mi / denom);
+    p[i] = pi;
     m[i] = mi;
     v[i] = vi;
     g[i] = 0.0f;
+    // the tensor-core operand copies of this parameter (TF32 (hi, lo) pairs in GEMM layout, tpp_split_tf32's arithmetic):
+    // written here instead of by ~9 re-split launches behind every optimizer step
+    for (int k = 0; k < views.n; ++k) {
+      const tpp_weight_view& w = views.v[k];
+      const int64_t j = i - w.offset;
+      if (j >= 0 && j < (int64_t)w.rows * w.cols) {
+        const int r = (int)(j / w.cols), c = (int)(j - (int64_t)r * w.cols);
+        const float x = w.scale != 0.0f ? pi * w.scale : pi;
+        const float h = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+        const int64_t o = (int64_t)r * w.ld + (w.col_of ? w.col_of[c] : c);
+        w.hi[o] = h;
+        w.lo[o] = x - h;
+      }
+    }
   }
   // the last CTA to finish publishes step+1 and clears the OTHER accumulator for the next reduction
   __shared__ bool last;
@@ -527,10 +548,23 @@ extern "C" int tpp_grad_sqnorm(tpp_adam_state* state, const float* g, int64_t n,
 
 extern "C" int tpp_adam_clip_step(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n,
                                   void* stream) {
+  return tpp_adam_clip_step_views(state, p, g, m, v, n, nullptr, 0, stream);
+}
+
+extern "C" int tpp_adam_clip_step_views(tpp_adam_state* state, float* p, float* g, float* m, float* v, int64_t n,
+                                        const tpp_weight_view* views, int32_t n_views, void* stream) {
   TPP_CHECK_ARG(state && p && g && m && v && n > 0);
+  TPP_CHECK_ARG(n_views >= 0 && n_views <= TPP_MAX_WEIGHT_VIEWS && (n_views == 0 || views));
+  tpp::WeightViews wv;
+  wv.n = n_views;
+  for (int k = 0; k < n_views; ++k) {
+    wv.v[k] = views[k];
+    TPP_CHECK_ARG(views[k].hi && views[k].lo && views[k].rows > 0 && views[k].cols > 0 && views[k].offset >= 0 &&
+                  views[k].offset + (int64_t)views[k].rows * views[k].cols <= n && views[k].ld >= views[k].cols);
+  }
   int grid = tpp_ceil_div(n, 256 * 4);
   if (grid > 148 * 4) grid = 148 * 4;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(&state->ticket);
-  tpp::adam_clip_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(state, p, g, m, v, n, ticket);
+  tpp::adam_clip_kernel<<<grid, 256, 0, tpp_stream(stream)>>>(state, p, g, m, v, n, ticket, wv);
   TPP_LAUNCH_STATUS();
 }
