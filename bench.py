@@ -298,6 +298,7 @@ def gemm_roofline(agent, in_dim, hp, pk):
     agent.policy.flat_grad.zero_()
     by_tile = {}
     for bn, M, N, K, e0, e1 in records:
+        bn = 513 if bn == 514 else bn      # the LEAN (3-stage, 8 epilogue warps) instantiation is the same kernel
         d = by_tile.setdefault(bn, dict(ms=0.0, flops=0.0, n=0, shapes=set()))
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += 2.0 * M * N * K
@@ -308,7 +309,8 @@ def gemm_roofline(agent, in_dim, hp, pk):
     tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
     tile = {0: "gemm_tc_kernel<128>", 64: "gemm_tc_kernel<64>", 128: "gemm_tc_kernel<128>", 256: "gemm_tc_kernel<256>",
             512: "gemm_tc_kernel<256, pair> (256x256 tile on a CTA pair, cta_group::2)",
-            513: "gemm_tc_kernel<256, pair, persistent> (256x256 tiles on persistent CTA pairs, cta_group::2)",
+            513: "gemm_tc_kernel<256, pair, persistent> (256x256 tiles on persistent CTA pairs, cta_group::2; forward + "
+                 "weight-gradient launches in the 3-stage / 8-epilogue-warp instantiation)",
             65: "gemm_tc_kernel<64, pair, persistent>"}.get(bn_dom, f"gemm_tc_kernel<{bn_dom}>")
     us_avg = d["ms"] * 1e3 / d["n"]
     traffic = hbm_frac = None

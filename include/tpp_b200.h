@@ -275,7 +275,11 @@ enum { TPP_TC_A_EXACT = 16, TPP_TC_B_EXACT = 32 };
  * period is bound by (TMA latency + split + cross-CTA signal + MMA) / stages.  The engine keeps pairs by default.   */
 enum { TPP_TC_A_SPLIT = 64, TPP_TC_B_SPLIT = 128 };
 /* block_n codes of the CTA-pair tiles */
-enum { TPP_TC_TILE_PAIR = 512, TPP_TC_TILE_PAIR_PERSISTENT = 513, TPP_TC_TILE_PAIR64_PERSISTENT = 65 };
+enum { TPP_TC_TILE_PAIR = 512, TPP_TC_TILE_PAIR_PERSISTENT = 513, TPP_TC_TILE_PAIR64_PERSISTENT = 65,
+       /* the persistent pair tile with 8 instead of 16 epilogue warps and 4 KB swizzled transpose patches: THREE
+        * instead of two 64 KB operand stages fit (two stages do not cover the TMA latency: the k-block period is
+        * (latency + MMAs) / 2 = 2380 cycles against 1840 of MMAs).  For launches with a light epilogue (forward). */
+       TPP_TC_TILE_PAIR_PERSISTENT_LEAN = 514 };
 int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream);
 
 /* Backward of the policy/value heads ([nh = A+1 <= 16][H] weights) in one kernel: from dhead [mb][ld_head]

@@ -45,7 +45,11 @@ def main():
         for tag, prec, om in (("pairs -> pair out", 3, "pair"), ("pairs -> plain out", 3, "plain"),
                               ("A split on chip -> plain", 3 | _lib.TC_A_SPLIT, "plain"),
                               ("A+B split on chip -> plain", 3 | S, "plain"), ("1xTF32 -> plain", 1, "plain")):
-            t = run(M, N, K, prec, 513, om)
+            try:
+                t = run(M, N, K, prec, int(os.environ.get("TILE", "513")), om)
+            except Exception as e:
+                print(f"{name:28s} {tag:28s} {str(e)[-60:]}")
+                continue
             kb = (M // 256) * (K // 32) / 74.0
             print(f"{name:28s} {tag:28s} {t:8.1f} us   {t / kb * 1e3:7.1f} ns / k-block / pair   "
                   f"{2.0 * M * N * K / t * 1e-6:7.1f} TFLOP/s")

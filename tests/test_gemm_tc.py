@@ -208,7 +208,7 @@ def test_exact_operand_two_pass_mode(which, M, N, K, mn):
 @pytest.mark.parametrize("M,N,K", [(256, 256, 32), (512, 256, 256), (4096, 256, 588), (1000, 256, 200), (256, 588, 96),
                                    (300, 500, 72)])
 @pytest.mark.parametrize("precision", [3, 1])
-@pytest.mark.parametrize("block_n", [512, 513])
+@pytest.mark.parametrize("block_n", [512, 513, 514])
 def test_cta_pair_tile(a_mn, b_mn, M, N, K, precision, block_n):
     """Forward (both K-major), data gradient (B MN-major) and weight-gradient (both MN-major) operand forms; ragged M / N
     edges (rows and columns beyond the matrix come from TMA zero fill and are never stored)."""
@@ -222,8 +222,9 @@ def test_cta_pair_tile(a_mn, b_mn, M, N, K, precision, block_n):
     assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])
 
 
+@pytest.mark.parametrize("tile", [513, 514])
 @pytest.mark.parametrize("M,N,K,b_mn", [(256 * 200, 256, 96, False), (256 * 163 + 40, 256, 64, True), (256 * 90, 500, 40, False)])
-def test_persistent_cta_pairs_loop_over_work_items(M, N, K, b_mn):
+def test_persistent_cta_pairs_loop_over_work_items(M, N, K, b_mn, tile):
     """block_n = 513: 74 CTA pairs loop over more 256 x 256 work items than there are pairs (two TMEM accumulators,
     the epilogue of one item overlapping the loads / MMAs of the next), with the fused epilogue pieces."""
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
@@ -231,17 +232,17 @@ def test_persistent_cta_pairs_loop_over_work_items(M, N, K, b_mn):
     b = torch.randn(N, K, device="cuda", generator=g)
     bias, mask = torch.randn(N, device="cuda", generator=g), torch.randn(M, N, device="cuda", generator=g)
     want, scale = _ref(a, b)
-    res = _gemm(a, b, 3, flags=1 | 2, bias=bias, b_mn=b_mn, block_n=513)
+    res = _gemm(a, b, 3, flags=1 | 2, bias=bias, b_mn=b_mn, block_n=tile)
     w = torch.relu(want + bias.double().cpu())
     assert ((res["out"][:, :N].double().cpu() - w).abs() / (scale + 1)).max() < 2e-6
     assert torch.equal(res["hi"][:, :N] + res["lo"][:, :N], res["out"][:, :N])
-    res = _gemm(a, b, 3, flags=4, mask=mask, want_colsum=True, b_mn=b_mn, block_n=513)
+    res = _gemm(a, b, 3, flags=4, mask=mask, want_colsum=True, b_mn=b_mn, block_n=tile)
     w = want * (mask.cpu() > 0)
     assert ((res["out"][:, :N].double().cpu() - w).abs() / scale).max() < 2e-6
     np.testing.assert_allclose(res["colsum"].double().cpu().numpy() - 1.0, w.sum(0).numpy(), rtol=1e-4, atol=2e-2)
 
 
-@pytest.mark.parametrize("block_n", [512, 513])
+@pytest.mark.parametrize("block_n", [512, 513, 514])
 def test_cta_pair_weight_gradient_many_splits(block_n):
     a2, b2 = torch.randn(256, 131072 // 4, device="cuda"), torch.randn(588, 131072 // 4, device="cuda")
     out = torch.ones(256, 588, device="cuda")

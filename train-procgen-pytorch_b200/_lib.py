@@ -73,6 +73,7 @@ FAMILY = {"cartpole": 0, "cartpole_swing": 1, "mountain_car": 2, "acrobot": 3, "
 TC_A_EXACT, TC_B_EXACT = 16, 32
 TC_A_SPLIT, TC_B_SPLIT = 64, 128      # the operand is plain fp32; its lo half is formed in shared memory
 TC_TILE_PAIR, TC_TILE_PAIR_PERSISTENT, TC_TILE_PAIR64_PERSISTENT = 512, 513, 65     # tpp_tc_gemm.block_n codes
+TC_TILE_PAIR_PERSISTENT_LEAN = 514          # 3 operand stages, 8 epilogue warps
 EPI_BIAS, EPI_RELU, EPI_MASK, EPI_ACCUM, EPI_ADD, EPI_RELU_OUT, EPI_PAIR_RELU = 1, 2, 4, 8, 16, 32, 64
 
 _vp, _i32, _i64, _u64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_double

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib
-from .._lib import TC_TILE_PAIR64_PERSISTENT, TC_TILE_PAIR_PERSISTENT, TC_A_EXACT, TC_B_EXACT, TC_A_SPLIT, TC_B_SPLIT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
+from .._lib import TC_TILE_PAIR64_PERSISTENT, TC_TILE_PAIR_PERSISTENT, TC_TILE_PAIR_PERSISTENT_LEAN, TC_A_EXACT, TC_B_EXACT, TC_A_SPLIT, TC_B_SPLIT, EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_MASK, EPI_PAIR_RELU, EPI_RELU, EPI_RELU_OUT
 
 
 def _ceil(a, b):
@@ -176,6 +176,8 @@ class MLPEngineTC(MLPEngine):
         self.wide_tile_rows = 32768
         self.pair_min_n = 256
         self.pair_block_n = TC_TILE_PAIR_PERSISTENT     # or TC_TILE_PAIR: one 256 x 256 tile per (non-persistent) pair
+        # launches whose epilogue 8 warps can hide (see TPP_TC_TILE_PAIR_PERSISTENT_LEAN): three operand stages
+        self.lean_kinds = ("fwd", "wgrad")      # (measured: the data gradient's mask + column-sum + pair epilogue needs 16 warps)
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
@@ -347,9 +349,11 @@ class MLPEngineTC(MLPEngine):
         _lib.call("tpp_policy_rollout_fused", _lib.C.byref(f), _lib.stream_ptr())
         self.n_launches += 1
 
-    def _bn(self, M, N):
+    def _bn(self, M, N, kind="fwd"):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= self.pair_min_n and M >= self.wide_tile_rows:
+            if self.pair_block_n == TC_TILE_PAIR_PERSISTENT and kind in self.lean_kinds and self.precision == 3:
+                return TC_TILE_PAIR_PERSISTENT_LEAN
             return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
         if 32 < N <= 64 and M >= self.wide_tile_rows and self.pair_block_n == TC_TILE_PAIR_PERSISTENT:
             return TC_TILE_PAIR64_PERSISTENT   # 256 x 64 tiles on persistent CTA pairs (HBM-bound: A is read once)
@@ -468,7 +472,9 @@ class MLPEngineTC(MLPEngine):
             # dZ of the last layer and the gathered observations are pairs)
             flag = (TC_B_EXACT if raw0 else (TC_B_SPLIT if soc and i > 0 else 0)) | (TC_A_SPLIT if soc and i < L - 1 else 0)
             self._tc((dz["hi"], dz["lo"]), ld_dz, inp, ld_inp, fout, fin, M, a_mn=1, b_mn=1, flags=EPI_ACCUM,
-                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas), block_n=self.pair_block_n if pair else 128,
+                     out=self._g(w_off), ldc=fin, split_k=self._wgrad_split(M, ctas),
+                     block_n=(TC_TILE_PAIR_PERSISTENT_LEAN if "wgrad" in self.lean_kinds and self.precision == 3 and
+                              self.pair_block_n == TC_TILE_PAIR_PERSISTENT else self.pair_block_n) if pair else 128,
                      exact=flag, alpha=1.0 / 255.0 if raw0 else 0.0)
             if i > 0:
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
@@ -478,7 +484,7 @@ class MLPEngineTC(MLPEngine):
                          flags=EPI_MASK if prev_relu else 0, mask=prev["hi"] if prev_relu else None,
                          ld_mask=prev["ld"], out=nxt["hi"] if soc else None,
                          out_pair=None if soc else (nxt["hi"], nxt["lo"]), ldc=prev["ld"],
-                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin),
+                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin, "dgrad"),
                          exact=TC_A_SPLIT if soc and i < L - 1 else 0)
                 cur, ld_dz = cur ^ 1, prev["ld"]
 

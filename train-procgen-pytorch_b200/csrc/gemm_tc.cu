@@ -49,15 +49,28 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
 // (192 threads x 80 registers) lets 3-4 tiles share an SM so that prologue / epilogue overlap other tiles' loads.
 // (SPLIT kernels of the 256-wide tiles: 8 epilogue warps, i.e. 36 KB of transpose patches instead of 72 -- the room
 // goes to the stage rings)
-constexpr int epi_warps(int block_n, bool split = false) { return block_n <= 32 ? 4 : (split && block_n == 256 ? 8 : 16); }
+// LEAN kernels (256 x 256 persistent pairs): also 8 epilogue warps, with 4 KB XOR-swizzled patches, so that THREE pair
+// stages fit the 227 KB -- for launches whose epilogue is light enough to hide behind the main loop with 8 warps
+constexpr int epi_warps(int block_n, bool split = false, bool lean = false) {
+  return block_n <= 32 ? 4 : (((split && block_n == 256) || lean) ? 8 : 16);
+}
 // wide tiles carry 4 more warps behind the epilogue warps: the on-chip operand splitters (see Params::split_a)
 // two groups, group g splits the k-blocks it = g (mod 2); 256-wide tiles (8 epilogue warps) have room for 2 x 8 warps
 constexpr int conv_warps(int block_n) { return block_n == 256 ? 16 : 8; }
-constexpr int num_threads(int block_n, bool split = false) {   // warp 0: TMA, warp 1: MMA + TMEM, epilogue warps, [splitters]
-  return 64 + epi_warps(block_n, split) * 32 + (split ? conv_warps(block_n) * 32 : 0);
+constexpr int num_threads(int block_n, bool split = false, bool lean = false) {   // warp 0: TMA, warp 1: MMA + TMEM, epilogue warps, [splitters]
+  return 64 + epi_warps(block_n, split, lean) * 32 + (split ? conv_warps(block_n) * 32 : 0);
 }
 constexpr int STG_PITCH = 36;            // floats per staged row (16-byte aligned, conflict-free 128-bit LDS/STS)
-constexpr int stg_bytes(int block_n, bool split = false) { return epi_warps(block_n, split) * 32 * STG_PITCH * 4; }   // a 32x32 patch per warp
+constexpr int stg_pitch(bool lean) { return lean ? 32 : STG_PITCH; }
+constexpr int stg_bytes(int block_n, bool split = false, bool lean = false) {     // a 32x32 patch per warp
+  return epi_warps(block_n, split, lean) * 32 * stg_pitch(lean) * 4;
+}
+// float index of (row, col) in a patch; LEAN: pitch 32 with the 16-byte chunk XOR-swizzled by the row (conflict-free
+// 128-bit accesses from both sides of the transpose: a quarter-warp touches 8 distinct chunks)
+template <bool LEAN>
+__device__ __forceinline__ int stg_at(int row, int col) {
+  return LEAN ? row * 32 + ((((col >> 2) ^ (row & 7)) << 2) | (col & 3)) : row * STG_PITCH + col;
+}
 
 struct Params {
   int M, N, K;                 // logical problem (rows of A, rows of B, contraction)
@@ -121,8 +134,8 @@ __device__ __forceinline__ float split_lo(float x) {
   return tf32_round(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
 }
 
-template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false>
-__global__ void __launch_bounds__(num_threads(BLOCK_N, SPLIT), 1)
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false, bool LEAN = false>
+__global__ void __launch_bounds__(num_threads(BLOCK_N, SPLIT, LEAN), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, Params p) {
   // Narrow tiles (BLOCK_N <= 32) are the convolution tiles.  Only they carry the residual / ReLU-pair epilogue extras,
@@ -214,7 +227,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, epi_warps(BLOCK_N, SPLIT) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogue warps, on the leader
+      mbar_init(tmem_empty + i, epi_warps(BLOCK_N, SPLIT, LEAN) * (PAIR ? 2 : 1));   // PAIR: both CTAs' epilogue warps, on the leader
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -374,12 +387,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();
      }
     }
-  } else if (SPLIT && warp >= 2 + epi_warps(BLOCK_N, SPLIT)) {
+  } else if (SPLIT && warp >= 2 + epi_warps(BLOCK_N, SPLIT, LEAN)) {
     // ===== operand splitters (wide tiles): lo = x - trunc_tf32(x), elementwise in place of the landed tile =====
     // The conversion is elementwise, so the swizzled layout of the hi tile is the layout of the lo tile: a thread walks
     // 16-byte chunks linearly (conflict-free).  One arrive per warp on the MMA issuer's barrier (the leader's, in a pair).
     if (split_mode) {
-      const int cwarp = warp - 2 - epi_warps(BLOCK_N, SPLIT);
+      const int cwarp = warp - 2 - epi_warps(BLOCK_N, SPLIT, LEAN);
       const int ctid = (cwarp % CONV_GROUP) * 32 + lane, cgroup = cwarp / CONV_GROUP;
       int it = 0;
       for (int w = wbegin; w < wend; w += wstride) {
@@ -433,11 +446,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // lines (8 lanes per row, 4 rows per instruction), column sums are register accumulations.  EPI_WARPS/4 warps serve each
     // TMEM lane quarter (column groups round-robin).  The pipeline stages are free by now (tmem_full => all MMAs
     // retired), the patches alias them.
-    constexpr int EPI_WARPS = epi_warps(BLOCK_N, SPLIT);
+    constexpr int EPI_WARPS = epi_warps(BLOCK_N, SPLIT, LEAN);
     const int ew = warp - 2;                            // 0 .. EPI_WARPS-1
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = ew >> 2;                           // which column groups this warp takes (round-robin)
-    float* stg = reinterpret_cast<float*>(smem + (PERS ? p.stg_offset : 0)) + ew * (32 * STG_PITCH);
+    float* stg = reinterpret_cast<float*>(smem + (PERS ? p.stg_offset : 0)) + ew * (32 * stg_pitch(LEAN));
     constexpr int GW = BLOCK_N < 32 ? BLOCK_N : 32;     // columns per staged group
     const int rr = lane >> 3, cc = (lane & 7) * 4;      // post-transpose mapping: 4 rows x (8 lanes x 4 columns)
     const bool atomic = p.flags & F_ATOMIC;
@@ -492,7 +505,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();                                     // previous group's readers are done with the patch
 #pragma unroll
       for (int j = 0; j < GW; j += 4)
-        *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4*>(stg + stg_at<LEAN>(lane, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
       if (warp == 2 && c == 0) TPP_PROBE(9);
       const bool lane_on = cc < GW;                     // (BLOCK_N == 16: lanes owning columns >= 16 idle)
@@ -525,10 +538,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const float floor_v = (p.flags & F_RELU) ? 0.0f : -3.402823466e38f;
           const float floor_out = (p.flags & F_RELU_OUT) ? 0.0f : -3.402823466e38f;
           const float floor_pair = (p.flags & F_PAIR_RELU) ? 0.0f : -3.402823466e38f;   // pair = relu(plain)
-          const float* sp = stg + rr * STG_PITCH + cc;
+          const float* sp = stg + rr * STG_PITCH + cc;    // (LEAN: per-row swizzle, see the load below)
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
-            const float4 q = *reinterpret_cast<const float4*>(sp + it * 4 * STG_PITCH);
+            const float4 q = LEAN ? *reinterpret_cast<const float4*>(stg + stg_at<true>(it * 4 + rr, cc))
+                                  : *reinterpret_cast<const float4*>(sp + it * 4 * STG_PITCH);
             float x[4] = {fmaxf(q.x + b4[0], floor_v), fmaxf(q.y + b4[1], floor_v), fmaxf(q.z + b4[2], floor_v),
                           fmaxf(q.w + b4[3], floor_v)};
             if (pm) {
@@ -571,7 +585,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll 1
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + rr, gm = mrow0 + r;
-        const float4 q = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cc);
+        const float4 q = *reinterpret_cast<const float4*>(stg + stg_at<LEAN>(r, cc));
         float x[4] = {q.x, q.y, q.z, q.w};
         if (gm >= p.M || !lane_on) continue;
         const long long off = (long long)gm * p.ldc + nc;
@@ -680,12 +694,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
     if (!NARROW && p.colsum && !atomic) {      // all epilogue warps of the CTA: combine, then one atomic per column
-      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");
-      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N, SPLIT) * 32) {
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT, LEAN) * 32) : "memory");
+      for (int i = ew * 32 + lane; i < BLOCK_N; i += epi_warps(BLOCK_N, SPLIT, LEAN) * 32) {
         if (n0 + i < p.N) atomicAdd(p.colsum + n0 + i, cs_sh[i]);
         if (PERSIST) cs_sh[i] = 0.0f;          // the next work item starts from zero ...
       }
-      if (PERSIST) asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");   // ... in every warp's view
+      if (PERSIST) asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT, LEAN) * 32) : "memory");   // ... in every warp's view
     }
     if (PERS) {                         // accumulator drained: hand it back to the MMA warp (PAIR: the leader's)
       tc_fence_before();
@@ -712,7 +726,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (rr == 0 && cc < GW) atomicAdd(cs_sh + cc + j, v);
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT) * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(epi_warps(BLOCK_N, SPLIT, LEAN) * 32) : "memory");
       if (ew == 0 && cs_n >= 0 && lane < GW && cs_n + lane < p.N) atomicAdd(p.colsum + cs_n + lane, cs_sh[lane]);
     }
   }
@@ -807,7 +821,7 @@ static int make_map_im2col(CUtensorMap* tm, const float* base, int B, int H, int
   return r == CUDA_SUCCESS ? TPP_OK : TPP_EINVAL;
 }
 
-template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false>
+template <int BLOCK_N, bool PAIR = false, bool PERSIST = false, bool SPLIT = false, bool LEAN = false>
 static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // B rows one CTA stages
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -877,8 +891,8 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const int lo_bytes = p.a_slot * p.split_a + p.b_slot * p.split_b;
   p.lo_stages = lo_bytes ? 2 : 0;
   // (split on chip: every byte counts -- the exact 227 KB limit; otherwise the round-1 budget the tuning was done with)
-  const int budget = (lo_bytes ? 227 * 1024 - 1024 - 256 : 224 * 1024 - 1024 - 256) - p.lo_stages * lo_bytes;
-  int stages = (budget - ((BLOCK_N <= 32 || PERSIST) ? stg_bytes(BLOCK_N, SPLIT) : 0)) / stage_bytes;
+  const int budget = ((lo_bytes || LEAN) ? 227 * 1024 - 1024 - 256 : 224 * 1024 - 1024 - 256) - p.lo_stages * lo_bytes;
+  int stages = (budget - ((BLOCK_N <= 32 || PERSIST) ? stg_bytes(BLOCK_N, SPLIT, LEAN) : 0)) / stage_bytes;
   if (stages < 1) return TPP_ENOTSUP;
   if (stages > (BLOCK_N <= 32 ? 8 : 4)) stages = BLOCK_N <= 32 ? 8 : 4;
   // many more tiles than SMs and a short contraction (convolution rows): trade pipeline depth for 2-3 resident CTAs
@@ -887,7 +901,7 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   const long long n_tiles = (long long)((g->N + BLOCK_N - 1) / BLOCK_N) * ((g->M + BLOCK_M - 1) / BLOCK_M) * split_k;
   // (narrow tiles only: the wide CTAs -- 576 threads x 67 registers -- are alone on their SM whatever their stage count)
   if (n_tiles >= 4 * 148 && BLOCK_N <= 32) {
-    int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N, SPLIT) : 0)) / stage_bytes;   // three resident CTAs
+    int few = (74 * 1024 - (BLOCK_N <= 32 ? stg_bytes(BLOCK_N, SPLIT, LEAN) : 0)) / stage_bytes;   // three resident CTAs
     if (few < 2) few = 2;
     if (stages > few) stages = few;
   }
@@ -900,17 +914,17 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   if (NARROW || PERSIST) {
     // persistent CTAs: the epilogue's transpose patches get their own region (the next tile's loads are in flight)
     p.stg_offset = (int)region;
-    region += stg_bytes(BLOCK_N, SPLIT);
+    region += stg_bytes(BLOCK_N, SPLIT, LEAN);
   } else {
     // the patches alias the pipeline stages (free once the accumulator is complete): the region must hold them
     p.stg_offset = 0;
-    if (region < (size_t)stg_bytes(BLOCK_N, SPLIT)) region = stg_bytes(BLOCK_N, SPLIT);
+    if (region < (size_t)stg_bytes(BLOCK_N, SPLIT, LEAN)) region = stg_bytes(BLOCK_N, SPLIT, LEAN);
   }
   p.bar_offset = (int)region;
   const size_t smem = region + 1024 + 256;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -930,14 +944,14 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
     static int regs_per_cta = 0;
     if (!regs_per_cta) {
       cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>) != cudaSuccess) return TPP_ENOTSUP;
-      regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N, SPLIT);
+      if (cudaFuncGetAttributes(&fa, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT, LEAN>) != cudaSuccess) return TPP_ENOTSUP;
+      regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * num_threads(BLOCK_N, SPLIT, LEAN);
     }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     // registers are allocated per warp inside each of the 4 SM sub-partitions (16384 registers each)
-    const int regs_per_warp = regs_per_cta / (num_threads(BLOCK_N, SPLIT) / 32);
+    const int regs_per_warp = regs_per_cta / (num_threads(BLOCK_N, SPLIT, LEAN) / 32);
     const int warps_per_sm = 4 * (16384 / regs_per_warp);
-    if (per_sm > warps_per_sm / (num_threads(BLOCK_N, SPLIT) / 32)) per_sm = warps_per_sm / (num_threads(BLOCK_N, SPLIT) / 32);
+    if (per_sm > warps_per_sm / (num_threads(BLOCK_N, SPLIT, LEAN) / 32)) per_sm = warps_per_sm / (num_threads(BLOCK_N, SPLIT, LEAN) / 32);
     if (per_sm > 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N))) per_sm = 512 / (2 * (BLOCK_N < 32 ? 32 : BLOCK_N));
     if (per_sm < 1) per_sm = 1;
     const unsigned resident = (unsigned)(per_sm * sms);
@@ -962,18 +976,18 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
       const unsigned pairs = (unsigned)std::min(p.total_work, sms / 2);
       cfg.gridDim = dim3(2u * pairs, 1, 1);
     }
-    cfg.blockDim = dim3(num_threads(BLOCK_N, SPLIT), 1, 1);
+    cfg.blockDim = dim3(num_threads(BLOCK_N, SPLIT, LEAN), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, PAIR, PERSIST, SPLIT, LEAN>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     if (e != cudaSuccess) return (int)e;
     TPP_LAUNCH_STATUS();
   }
-  gemm_tc_kernel<BLOCK_N, PAIR, false, SPLIT><<<grid, num_threads(BLOCK_N, SPLIT), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  gemm_tc_kernel<BLOCK_N, PAIR, false, SPLIT, LEAN><<<grid, num_threads(BLOCK_N, SPLIT, LEAN), smem, s>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
   TPP_LAUNCH_STATUS();
 }
 
@@ -1019,6 +1033,7 @@ extern "C" int tpp_gemm_tc(const tpp_tc_gemm* g, void* stream) {
     case 256: return tpp::tc::launch<256>(g, g->split_k, s);
     case TPP_TC_TILE_PAIR: return tpp::tc::launch<256, true>(g, g->split_k, s);   // 256 x 256 tile, one per CTA pair
     case TPP_TC_TILE_PAIR_PERSISTENT: return tpp::tc::launch<256, true, true>(g, g->split_k, s);
+    case TPP_TC_TILE_PAIR_PERSISTENT_LEAN: return tpp::tc::launch<256, true, true, false, true>(g, g->split_k, s);
     case TPP_TC_TILE_PAIR64_PERSISTENT: return tpp::tc::launch<64, true, true>(g, g->split_k, s);   // 256 x 64 tiles
     default: return TPP_ENOTSUP;
   }
