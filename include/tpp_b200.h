@@ -261,6 +261,13 @@ typedef struct {
                                             M = 288, K = conv_B*conv_H*conv_W pixels, B = dY [K][ldb] MN-major
                                             (a_mn = b_mn = 1, TPP_EPI_ACCUM, any split_k).                          */
   float alpha; int32_t _reserved;          /* TPP_EPI_ACCUM: out += alpha * product (0 means 1)                      */
+  uint32_t* mask_bits_out;                 /* 1-bit ReLU masks (tiles wider than 32 columns; M, N multiples of 32):     */
+  const uint32_t* mask_bits;               /* mask_bits_out receives (result > 0) of every element, 32 words per 32 x 32
+                                              block ([M/32][N/32][32] uint32, 1/32 of the fp32 activation it stands
+                                              for); mask_bits zeroes the result where the bit is clear -- relu'(H) of
+                                              the data gradient without re-reading H (TPP_EPI_MASK's 4-byte form).
+                                              The word / bit order inside a block is the kernel's own: only a buffer
+                                              written through mask_bits_out may be passed as mask_bits.             */
 } tpp_tc_gemm;
 /* precision: 1 = single-pass TF32, 3 = 3xTF32; with 3, | TPP_TC_A_EXACT / TPP_TC_B_EXACT declares that operand exactly
  * representable in TF32 (e.g. integer pixel values 0..255): it has no lo half (a_lo / b_lo unused, not loaded) and the

@@ -40,7 +40,7 @@ def _operand(x, mn_major):
 
 
 def _gemm(a, b, precision, flags=0, bias=None, mask=None, split_k=1, block_n=0, want_colsum=False, out=None,
-          a_mn=False, b_mn=False):
+          a_mn=False, b_mn=False, mask_bits_out=None, mask_bits=None):
     from tpp_b200 import _lib
     M, K = a.shape
     N = b.shape[0]
@@ -70,6 +70,10 @@ def _gemm(a, b, precision, flags=0, bias=None, mask=None, split_k=1, block_n=0, 
         g.bias = bias.data_ptr()
     if mask is not None:
         g.mask, g.ld_mask = mask.data_ptr(), mask.stride(0)
+    if mask_bits_out is not None:
+        g.mask_bits_out = mask_bits_out.data_ptr()
+    if mask_bits is not None:
+        g.mask_bits = mask_bits.data_ptr()
     _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())
     torch.cuda.synchronize()
     return res
@@ -351,3 +355,34 @@ def test_split_on_chip_refused_on_narrow_tiles():
         out.data_ptr(), 16
     with pytest.raises(Exception):
         _lib.call("tpp_gemm_tc", C.byref(g), _lib.stream_ptr())
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256, 512, 513, 514, 65])
+def test_one_bit_relu_masks(block_n):
+    """mask_bits_out / mask_bits: the forward epilogue leaves (relu output > 0) as one bit per element, the data
+    gradient's epilogue masks with those bits -- same result, bit for bit, as TPP_EPI_MASK on the fp32 activation."""
+    M, N, K = 256 * 5 + 64, (64 if block_n == 65 else 256), 96
+    g0 = torch.Generator(device="cuda").manual_seed(block_n)
+    a = torch.randn(M, K, device="cuda", generator=g0)
+    b = torch.randn(N, K, device="cuda", generator=g0) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g0) * 0.1
+    bits = torch.full((M // 32 * (N // 32) * 32,), -1, dtype=torch.int32, device="cuda")
+    fwd = _gemm(a, b, 3, flags=1 | 2, bias=bias, block_n=block_n, mask_bits_out=bits)
+    H = fwd["out"][:, :N].contiguous()
+    assert 0.3 < (H > 0).float().mean() < 0.7
+    a2 = torch.randn(M, 64, device="cuda", generator=g0)
+    b2 = torch.randn(N, 64, device="cuda", generator=g0)
+    ref = _gemm(a2, b2, 3, flags=4, mask=H, want_colsum=True, block_n=block_n)
+    got = _gemm(a2, b2, 3, want_colsum=True, block_n=block_n, mask_bits=bits)
+    for k in ("out", "hi", "lo"):
+        assert torch.equal(ref[k], got[k]), k
+    torch.testing.assert_close(ref["colsum"], got["colsum"], rtol=1e-5, atol=1e-4)     # atomics: order varies per run
+    assert ((got["out"][:, :N] != 0) <= (H > 0)).all()
+
+
+def test_one_bit_masks_refused_where_the_fast_path_does_not_run():
+    a = torch.randn(100, 64, device="cuda")        # rows not a multiple of 32
+    b = torch.randn(256, 64, device="cuda")
+    bits = torch.zeros(4 * 8 * 32, dtype=torch.int32, device="cuda")
+    with pytest.raises(Exception):
+        _gemm(a, b, 3, flags=2, block_n=128, mask_bits_out=bits)

@@ -55,7 +55,7 @@ class TcGemm(C.Structure):   # mirrors tpp_tc_gemm
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ldc", C.c_int64),
                 ("colsum", C.c_void_p), ("dbg", C.c_void_p), ("addend", C.c_void_p), ("ld_add", C.c_int64),
                 ("conv_B", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32),
-                ("alpha", C.c_float), ("_reserved", C.c_int32)]
+                ("alpha", C.c_float), ("_reserved", C.c_int32), ("mask_bits_out", C.c_void_p), ("mask_bits", C.c_void_p)]
 
 
 class FusedPolicy(C.Structure):   # mirrors tpp_fused_policy

@@ -177,7 +177,7 @@ class MLPEngineTC(MLPEngine):
         self.pair_min_n = 256
         self.pair_block_n = TC_TILE_PAIR_PERSISTENT     # or TC_TILE_PAIR: one 256 x 256 tile per (non-persistent) pair
         # launches whose epilogue 8 warps can hide (see TPP_TC_TILE_PAIR_PERSISTENT_LEAN): three operand stages
-        self.lean_kinds = ("fwd", "wgrad")      # (measured: the data gradient's mask + column-sum + pair epilogue needs 16 warps)
+        self.lean_kinds = ("fwd", "dgrad", "wgrad")
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
@@ -272,12 +272,18 @@ class MLPEngineTC(MLPEngine):
             ws.dz = [dict(plain=torch.zeros(M, mw, **f), hi=torch.zeros(M, mw, **f), lo=torch.zeros(M, mw, **f))
                      for _ in range(2)]     # split_on_chip: "hi" of ws.dz[1] / later ws.dz[0] is the plain gradient
             ws.fm = None       # TF32 pair of a feature-major rollout slot, allocated on first use
+            # 1-bit ReLU masks of the hidden layers (written by the forward epilogue, read by the data gradient): 1/32 of
+            # the fp32 activation the mask would otherwise be re-read from
+            ws.bits = None
+            if M % 32 == 0 and all(l[3] % 32 == 0 and l[3] > 32 for l in self.layers[:-1]) and self.precision in (1, 3):
+                ws.bits = [torch.zeros(M // 32 * (l[3] // 32) * 32, dtype=torch.int32, device=self.device)
+                           for l in self.layers[:-1]]
             self._ws[(M, slot)] = ws
         return ws
 
     def _tc(self, a, lda, b, ldb, M, N, K, a_mn=0, b_mn=0, flags=0, bias=None, mask=None, ld_mask=0, out=None,
             out_pair=None, ldc=0, colsum=None, split_k=1, block_n=0, addend=None, ld_add=0, conv=None, conv_wgrad=0,
-            exact=0, alpha=0.0):
+            exact=0, alpha=0.0, mask_bits_out=None, mask_bits=None):
         g = _lib.TcGemm()
         g.a_hi, g.a_lo, g.lda = a[0].data_ptr(), a[1].data_ptr(), lda
         g.b_hi, g.b_lo, g.ldb = b[0].data_ptr(), b[1].data_ptr(), ldb
@@ -295,6 +301,10 @@ class MLPEngineTC(MLPEngine):
             g.out_hi, g.out_lo = out_pair[0].data_ptr(), out_pair[1].data_ptr()
         if colsum is not None:
             g.colsum = colsum.value
+        if mask_bits_out is not None:
+            g.mask_bits_out = mask_bits_out.data_ptr()
+        if mask_bits is not None:
+            g.mask_bits = mask_bits.data_ptr()
         if addend is not None:
             g.addend, g.ld_add = addend.data_ptr(), ld_add
         if conv is not None:
@@ -392,6 +402,7 @@ class MLPEngineTC(MLPEngine):
             self.n_launches += 1
             cur, ld_cur, a_mn = (ws.x["hi"], ws.x["lo"]), self.ld_in, 0
         self._x_pair, self._x_ld, self._x_raw = (cur, ld_cur), None, raw
+        self._bits_valid = bool(need_backward and ws.bits is not None and not trunk_only and not feature_major_ld)
         for i in range(L - 1 if trunk_only else L):
             w_off, b_off, fin, fout, relu = self.layers[i]
             h, w = ws.h[i], (self.w0_raw if raw and i == 0 else self.w[i])
@@ -403,7 +414,8 @@ class MLPEngineTC(MLPEngine):
                          exact=a_flag, block_n=self._bn(M, fout))
                 return h["hi"], h["ld"]
             plain_only = soc and i < L - 1     # the next GEMM splits it on chip
-            self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn,
+            bits = ws.bits[i] if (ws.bits is not None and need_backward and relu and i < L - 1) else None
+            self._tc(cur, ld_cur, (w["hi"], w["lo"]), w["ldk"], M, fout, fin, a_mn=a_mn, mask_bits_out=bits,
                      flags=EPI_BIAS | (EPI_RELU if relu else 0), bias=self._p(b_off),
                      out=ws.last_plain if i == L - 1 else (h["hi"] if plain_only else None),
                      out_pair=None if plain_only else (h["hi"], h["lo"]), ldc=h["ld"],
@@ -480,8 +492,11 @@ class MLPEngineTC(MLPEngine):
                 # dZ_{i-1} = (dZ_i W_i) * relu'(H_{i-1}); W_i read as an MN-major operand; column sums = bias grad
                 nxt, w, prev = ws.dz[cur ^ 1], self.w[i], ws.h[i - 1]
                 prev_relu = self.layers[i - 1][4]
+                use_bits = prev_relu and ws.bits is not None and self._bits_valid
                 self._tc((dz["hi"], dz["lo"]), ld_dz, (w["hi"], w["lo"]), w["ldk"], M, fin, fout, b_mn=1,
-                         flags=EPI_MASK if prev_relu else 0, mask=prev["hi"] if prev_relu else None,
+                         mask_bits=ws.bits[i - 1] if use_bits else None,
+                         flags=EPI_MASK if (prev_relu and not use_bits) else 0,
+                         mask=prev["hi"] if (prev_relu and not use_bits) else None,
                          ld_mask=prev["ld"], out=nxt["hi"] if soc else None,
                          out_pair=None if soc else (nxt["hi"], nxt["lo"]), ldc=prev["ld"],
                          colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin, "dgrad"),

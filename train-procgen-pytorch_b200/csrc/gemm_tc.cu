@@ -92,6 +92,9 @@ struct Params {
   int flags;
   const float* bias;
   const float* mask; long long ld_mask;
+  uint32_t* bits_out;          // wide tiles: (result > 0) of every 32 x 32 output block as 32 words (128 B instead of 4 KB)
+  const uint32_t* bits_in;     // ... and the same words read back as the ReLU mask of a data gradient
+  int bits_ncb;                // 32-column blocks per row of blocks (ceil(N / 32))
   float* out; long long ldc;   // plain fp32 (or atomic accumulation target)
   float* out_hi; float* out_lo;
   float* colsum;               // optional: colsum[n] += sum over this tile's rows of the (masked) result (bias grad)
@@ -113,6 +116,7 @@ struct Params {
 };
 
 enum { F_BIAS = 1, F_RELU = 2, F_MASK = 4, F_ATOMIC = 8, F_ADD = 16, F_RELU_OUT = 32, F_PAIR_RELU = 64 };
+// (1-bit ReLU masks: Params::bits_out / bits_in, wide tiles, see tpp_tc_gemm.mask_bits)
 
 // ---------------------------------------------------------------------------------------------------
 // The kernel: one 128 x BLOCK_N output tile (x one k-split) per CTA
@@ -539,19 +543,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const float floor_out = (p.flags & F_RELU_OUT) ? 0.0f : -3.402823466e38f;
           const float floor_pair = (p.flags & F_PAIR_RELU) ? 0.0f : -3.402823466e38f;   // pair = relu(plain)
           const float* sp = stg + rr * STG_PITCH + cc;    // (LEAN: per-row swizzle, see the load below)
-#pragma unroll 2
+          // wide tiles: the 8 ReLU-mask loads of this lane are issued together, in front of the loop (one dependent
+          // global load per iteration left the epilogue of a data-gradient item latency-bound)
+          constexpr int UNR = NARROW ? 2 : 8;
+          float4 mq8[NARROW ? 1 : 8];
+          if (!NARROW && pm) {
+#pragma unroll
+            for (int it = 0; it < (NARROW ? 1 : 8); ++it) mq8[it] = *reinterpret_cast<const float4*>(pm + it * mstep);
+          }
+          // 1-bit masks: the 32 x 32 block at (mrow0, n) owns 32 words; word it*4 + j holds, at bit `lane`, whether the
+          // element this lane handles in iteration it (row it*4 + rr, column cc + j) is positive.  The producing and the
+          // consuming epilogue share this lane mapping, so the layout is private to the kernel.
+          const long long wbase = !NARROW && (p.bits_out || p.bits_in)
+                                      ? ((long long)(mrow0 >> 5) * p.bits_ncb + (n >> 5)) * 32 : 0;
+          uint32_t wmine = 0u;
+          if (!NARROW && p.bits_in) wmine = p.bits_in[wbase + lane];
+#pragma unroll UNR
           for (int it = 0; it < 8; ++it) {
             const float4 q = LEAN ? *reinterpret_cast<const float4*>(stg + stg_at<true>(it * 4 + rr, cc))
                                   : *reinterpret_cast<const float4*>(sp + it * 4 * STG_PITCH);
             float x[4] = {fmaxf(q.x + b4[0], floor_v), fmaxf(q.y + b4[1], floor_v), fmaxf(q.z + b4[2], floor_v),
                           fmaxf(q.w + b4[3], floor_v)};
             if (pm) {
-              const float4 mq = *reinterpret_cast<const float4*>(pm);
-              pm += mstep;
+              float4 mq;
+              if (NARROW) { mq = *reinterpret_cast<const float4*>(pm); pm += mstep; }
+              else mq = mq8[NARROW ? 0 : it];
               x[0] = mq.x > 0.0f ? x[0] : 0.0f;
               x[1] = mq.y > 0.0f ? x[1] : 0.0f;
               x[2] = mq.z > 0.0f ? x[2] : 0.0f;
               x[3] = mq.w > 0.0f ? x[3] : 0.0f;
+            }
+            if (!NARROW && p.bits_in) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t wd = __shfl_sync(0xffffffffu, wmine, it * 4 + j);
+                x[j] = ((wd >> lane) & 1u) ? x[j] : 0.0f;
+              }
+            }
+            if (!NARROW && p.bits_out) {
+              uint32_t wd = 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t b = __ballot_sync(0xffffffffu, x[j] > 0.0f);
+                if (lane == j) wd = b;
+              }
+              if (lane < 4) p.bits_out[wbase + it * 4 + lane] = wd;
             }
             if (NARROW) {
               if (pa) {
@@ -864,6 +900,14 @@ static int launch(const tpp_tc_gemm* g, int split_k, cudaStream_t s) {
   Params p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.npass = npass; p.flags = g->flags;
   p.bias = g->bias; p.mask = g->mask; p.ld_mask = g->ld_mask;
+  p.bits_out = g->mask_bits_out; p.bits_in = g->mask_bits; p.bits_ncb = (g->N + 31) / 32;
+  if (g->mask_bits_out || g->mask_bits) {
+    // the bit words are written / read by the interior fast path of the wide tiles' epilogue only
+    if (BLOCK_N <= 32 || (g->M & 31) || (g->N & 31) || (g->ldc & 3) || (g->flags & F_ATOMIC) ||
+        ((reinterpret_cast<uintptr_t>(g->out) | reinterpret_cast<uintptr_t>(g->out_hi) |
+          reinterpret_cast<uintptr_t>(g->out_lo)) & 15))
+      return TPP_ENOTSUP;
+  }
   p.addend = g->addend; p.ld_add = g->ld_add;
   p.nops_a = nops_a; p.nops_b = nops_b;
   p.split_a = a_split ? 1 : 0; p.split_b = b_split ? 1 : 0;
