@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PPO rollout-and-update hot path (BASELINE.json metric: PPO env-steps/sec, rollout+GAE+update).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload boxworld|cartpole|procgen]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload boxworld|cartpole|procgen|procgen_c5]
 
 One "step" = one full PPO iteration: T fused rollout steps over the rank's envs (policy forward -> Philox action
 sampling -> env step kernel writing into the rollout), bootstrap value, GAE + advantage normalisation, and
@@ -17,7 +17,8 @@ GPUs (`scaling: strong`; the same run also reports weak scaling, 4096 envs per G
 distractors), 500-level bank, with an MLP policy on the flattened 3x14x14 frame (the reference has no working
 Box-World policy; choice documented in DESIGN.md).  At N=1 the JSON line also carries a `configs` block:
 C1 (`cartpole` set, 256 envs x 256 steps: device-timed, end-to-end and the CPU arm at the SAME 256 x 256), the C3
-env-step sweep (`kernel_rooflines`) and C4 (`hard-500` set, IMPALA-CNN, 64 envs, synthetic host engine).
+env-step sweep (`kernel_rooflines`), C4 (`hard-500` set, IMPALA-CNN, 64 envs, synthetic host engine) and C5 (the
+`hard-500` set as it is: 256 envs, minibatch 8192 -- the maze_aisc / heist_aisc_many_chests shape).
 
 `value` = device-timed iterations with inputs resident (minibatch permutations pre-uploaded); `e2e` = the same
 iterations through the public API `PPO.train()` with this package's `Logger`: per-epoch index upload from pinned host
@@ -56,17 +57,20 @@ def workload_hp(name):
         return dict(sets["cartpole"])
     if name == "procgen":           # configs[3]: hard-500 with 64 envs per GPU (n_minibatch: PPO's default, 8)
         return dict(sets["hard-500"], n_envs=64, n_minibatch=8)
+    if name == "procgen_c5":        # configs[4]: the hard-500 set as it is (256 envs, minibatch 8192) -- the shape the
+        return dict(sets["hard-500"], n_minibatch=8)      # maze_aisc / heist_aisc_many_chests 200M-step runs use
     raise KeyError(name)
 
 
 # bounded CPU samples of the same workloads: (n_envs, n_steps) of one CPU "step"; everything else is the GPU arm's
-CPU_SAMPLE = {"boxworld": (4096, 16), "cartpole": (256, 256), "procgen": (64, 32)}
+CPU_SAMPLE = {"boxworld": (4096, 16), "cartpole": (256, 256), "procgen": (64, 32), "procgen_c5": (256, 8)}
 
 
 def workload_string(name, hp):
     mb = min(hp["mini_batch_size"], hp["n_steps"] * hp["n_envs"] // hp["n_minibatch"])
     pol = {"boxworld": "MLP policy 588-256-256-256-64 on the flattened 3x14x14 frame",
-           "cartpole": "MLP policy 9-256-256-256-64", "procgen": "IMPALA-CNN policy, synthetic 64x64x3 uint8 frames"}[name]
+           "cartpole": "MLP policy 9-256-256-256-64", "procgen": "IMPALA-CNN policy, synthetic 64x64x3 uint8 frames",
+           "procgen_c5": "IMPALA-CNN policy, synthetic 64x64x3 uint8 frames"}[name]
     return (f"{name} PPO: n_envs={hp['n_envs']}, n_steps={hp['n_steps']}, epoch={hp['epoch']}, "
             f"n_minibatch={hp['n_minibatch']}, mini_batch_size={mb}, {pol}")
 
@@ -229,7 +233,20 @@ def kernel_rooflines(pk, device, sweep=True):
         gbs = 25 * T * Ng / dt / 1e9
         out.append(dict(kernel="gae_scan+adv_normalize", T=T, n_envs=Ng, bytes_per_unit=25, bound="hbm",
                         achieved=round(gbs, 1), peak=pk["hbm"], unit="GB/s", frac=round(gbs / pk["hbm"], 4),
-                        us=round(dt * 1e6, 2)))
+                        us=round(dt * 1e6, 2), mode="exact (bit-identical to the reference's fp32 recurrence; default)"))
+        if Ng <= 4096:      # the opt-in one-launch form: warp-level segmented scan + moments + normalisation
+            st.gae_mode = "warp_scan"
+            try:
+                dt = time_kernel(lambda: st.compute_estimates(0.99, 0.95, True, True), iters=10)
+            except Exception as e:          # an extra row must not take the headline line down
+                out.append(dict(kernel="gae_scan_fused", error=repr(e)[:200]))
+                del st
+                continue
+            gbs = 21 * T * Ng / dt / 1e9          # adv written once, never re-read: 21 B per (t, env)
+            out.append(dict(kernel="gae_scan_fused (warp-level segmented scan + normalisation, one launch)", T=T,
+                            n_envs=Ng, bytes_per_unit=21, bound="hbm", achieved=round(gbs, 1), peak=pk["hbm"],
+                            unit="GB/s", frac=round(gbs / pk["hbm"], 4), us=round(dt * 1e6, 2),
+                            mode="warp_scan (gae_mode='warp_scan'; within 1e-5 of the exact kernels)"))
         del st
     torch.cuda.empty_cache()
     return out
@@ -542,6 +559,13 @@ def other_configs(args, rank, local, pk):
     except Exception as e:      # the headline line must survive a failure of an extra config
         out["C4_procgen"] = {"error": repr(e)[:300]}
     torch.cuda.empty_cache()
+    try:                        # configs[4]: the hard-500 set as it is (256 envs, minibatch 8192), throughput only
+        p = argparse.Namespace(**vars(args))
+        p.steps, p.warmup = 2, 1
+        out["C5_procgen_hard500"] = run_procgen(p, emit=False, name="procgen_c5", with_roofline=False)
+    except Exception as e:
+        out["C5_procgen_hard500"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
     return out
 
 
@@ -572,7 +596,7 @@ class SyntheticProcgen:
         pass
 
 
-def run_procgen(args, emit=True):
+def run_procgen(args, emit=True, name="procgen", with_roofline=True):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -589,7 +613,7 @@ def run_procgen(args, emit=True):
     from tpp_b200.common.model import ImpalaModel
     from tpp_b200.common.policy import CategoricalPolicy
     from tpp_b200.common.storage import Storage
-    hp = workload_hp("procgen")
+    hp = workload_hp(name)
     N, T = hp["n_envs"], hp["n_steps"]
     matmul = args.matmul if args.matmul in ("tf32x3", "tf32") else "tf32x3"
     env = StagedVecEnv(SyntheticProcgen(N, seed=rank), normalize_rew=hp.get("normalize_rew", True), gamma=hp["gamma"],
@@ -656,6 +680,13 @@ def run_procgen(args, emit=True):
             torch.distributed.barrier()
             finish(world)
         return None
+    total = N * T * args.steps * world
+    if not with_roofline:           # configs-block entry: the throughput numbers only (C4's entry carries the roofline)
+        return {"workload": workload_string(name, hp), "yaml_set": "hard-500", "value": round(total / (ms * 1e-3), 1),
+                "unit": "env-steps/s", "ms_per_step": round(ms / args.steps, 3), "steps": args.steps,
+                "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(launches), "clocks": clk}
     pk = peaks()
     sys.path.insert(0, os.path.join(ROOT, "profiles"))
     import run_conv_kernels as rck
@@ -675,15 +706,14 @@ def run_procgen(args, emit=True):
             "gathered_operand_GBps": round(18 * pixels * rck.SHAPE["C"] * 4 / forms["forward"] / 1e3, 1),
             "note": f"peak = dense bf16 ({pk['source']}); algorithmic FLOPs 2*pixels*9*Cin*Cout; the tile is bound by "
                     "the L2->shared-memory gather of 9 taps x (hi, lo), see profiles/ncu_conv_r01.md"}
-    total = N * T * args.steps * world
-    cpu = cpu_baseline("procgen", budget_s=15.0) if not args.no_cpu_baseline else None
-    n_e, n_s = CPU_SAMPLE["procgen"]
+    cpu = cpu_baseline(name, budget_s=15.0) if not args.no_cpu_baseline else None
+    n_e, n_s = CPU_SAMPLE[name]
     line = {
         "metric": METRIC, "value": round(total / (ms * 1e-3), 1),
         "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_string("procgen", hp), "yaml_set": "hard-500",
+        "config": {"workload": workload_string(name, hp), "yaml_set": "hard-500",
                    "parallelism": f"env-sharded dp{world}: {N} envs per GPU, {matmul}",
                    "l2": "minibatch activations (GBs) >> L2",
                    "reference_arm": f"CPU port on the same workload with n_steps={n_s} of {T} per CPU step (n_envs={n_e})"},
@@ -715,7 +745,7 @@ def _cpu_setup(name, n_envs, n_steps):
     kw = dict(epoch=hp["epoch"], n_minibatch=hp["n_minibatch"], mini_batch_size=hp["mini_batch_size"],
               grad_clip_norm=hp["grad_clip_norm"], eps_clip=hp["eps_clip"], value_coef=hp["value_coef"],
               entropy_coef=hp["entropy_coef"])
-    if name == "procgen":
+    if name.startswith("procgen"):
         rng = np.random.default_rng(0)
         pool = rng.integers(0, 256, (8, n_envs, 64, 64, 3), dtype=np.uint8)
         state = {"i": 0}
@@ -815,7 +845,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True,
         "scaling": "strong" if name == "boxworld" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(name, full),
-                   "yaml_set": {"boxworld": "boxworld-impala", "cartpole": "cartpole", "procgen": "hard-500"}[name],
+                   "yaml_set": {"boxworld": "boxworld-impala", "cartpole": "cartpole", "procgen": "hard-500",
+                                "procgen_c5": "hard-500"}[name],
                    "parallelism": f"host CPU, {threads} threads (not sharded: rank 0 only)",
                    "reference_arm": f"CPU port of the reference path on the same workload with n_steps={n_steps} of "
                                     f"{full['n_steps']} per CPU step (n_envs={n_envs}, minibatch and epochs unchanged; "
@@ -839,7 +870,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="boxworld", choices=["boxworld", "cartpole", "procgen"])
+    ap.add_argument("--workload", default="boxworld", choices=["boxworld", "cartpole", "procgen", "procgen_c5"])
     ap.add_argument("--matmul", default="tf32x3", choices=["tf32x3", "tf32", "fp32"],
                     help="dense-layer arithmetic: tcgen05 3xTF32 (fp32-parity, default), tcgen05 single TF32, CUDA-core fp32")
     ap.add_argument("--fuse-accum", default="auto",
@@ -857,8 +888,8 @@ def main():
         print(json.dumps(kernel_rooflines(peaks(), "cuda:0")))
     elif args.impl == "reference":
         run_reference(args)
-    elif args.workload == "procgen":
-        run_procgen(args)
+    elif args.workload.startswith("procgen"):
+        run_procgen(args, name=args.workload)
     else:
         run_ours(args)
 

@@ -157,6 +157,18 @@ int tpp_vecnormalize_rollout(double* ret, double* rms, const int32_t* raw_rew, c
 int tpp_gae(const float* rew, const uint8_t* done, const float* value, float* adv, float* ret,
             double* moments, int32_t T, int32_t N, int64_t ld, float gamma, float lambda, void* stream);
 
+/* The same estimates as a warp-level segmented scan over n_steps (affine-map composition, done = segment boundary),
+ * fused with the advantage moments and -- normalize != 0 -- with the normalisation itself (one cooperative launch with
+ * a grid barrier; adv is written once, already normalised).  Replaces common/storage.py:56-79 in ONE launch.
+ * moments4: double[4], zeroed by the caller: (sum, sum of squares, count) of the RAW advantages + the barrier's counter.
+ * Re-associates the products: raw advantages / returns agree with tpp_gae to ~4e-7 of their scale, not bit for bit.
+ * TPP_ENOTSUP when T needs more than 200 KB of shared memory or (normalize) the grid (N / 32 CTAs) cannot be
+ * co-resident -- callers then use tpp_gae + tpp_adv_normalize.  normalize = 0: raw adv (sharded runs all-reduce the
+ * moments first).                                                                                              */
+int tpp_gae_scan(const float* rew, const uint8_t* done, const float* value, float* adv, float* ret,
+                 double* moments4, int32_t T, int32_t N, int64_t ld, float gamma, float lambda, int32_t normalize,
+                 void* stream);
+
 /* adv <- (adv - mean) / (std_unbiased + 1e-8) with the moments from tpp_gae (after an optional cross-rank
  * all-reduce of the three doubles).  Replaces common/storage.py:78-79.                                   */
 int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream);
@@ -319,6 +331,16 @@ int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t H, int32_t 
                   void* stream);
 /* (sb, sy, sx, sc): element strides of x over (sample, row, column, channel): NHWC = (HWC, WC, C, 1); the gathered
  * NCHW observation rows of tpp_gather_img = (ld_out, W, 1, HW).                                                 */
+
+/* Weight gradient of a 3x3 / padding-1 convolution on the fp32 FMA pipe (csrc/conv_cc.cu), for the IMPALA-CNN's
+ * narrow layers: gw[(ky*3 + kx)*32 + ci][co] += sum_{b,y,x} X[b][y+ky-1][x+kx-1][ci] * dY[b][y][x][co], X = relu(x)
+ * when relu != 0.  x: NHWC [B][H][W][cin] plain fp32 (the tensor the forward convolution's input pair was split
+ * from), dy: NHWC [B][H][W][cout] plain fp32, gw: the engine's GEMM layout [9*32][cout] (32 channel slots per tap),
+ * ACCUMULATED into.  Replaces autograd's conv2d weight gradient (reference common/model.py:134-208).
+ * Shapes: (cin, cout, H = W) in {(16,16,32), (16,32,32), (32,32,16), (32,32,8)}; anything else returns TPP_ENOTSUP
+ * and the caller uses the tensor-core form (tpp_gemm_tc with conv_wgrad).                                        */
+int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, float* gw, int32_t B, int32_t H, int32_t W,
+                      int32_t cin, int32_t cout, void* stream);
 
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (common/model.py:163,171): y [B][(H+1)/2][(W+1)/2][C],
  * arg = winning tap (first maximum); backward routes dy to the winning input pixel (gather form, no atomics).   */

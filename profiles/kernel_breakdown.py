@@ -21,8 +21,9 @@ def main():
     ap.add_argument("--workload", default="boxworld")
     ap.add_argument("--matmul", default="tf32x3")
     args = ap.parse_args()
-    hp = dict(bench.WORKLOADS[args.workload], matmul=args.matmul)
-    agent, _ = bench.build_agent(args.workload, hp, 0, "cuda:0")
+    hp = bench.workload_hp(args.workload)
+    _matmul = args.matmul
+    agent, _ = bench.build_agent(args.workload, hp, 0, "cuda:0", matmul=_matmul)
     st, env = agent.storage, agent.env
     env.reset_rollout(st)
 

@@ -24,8 +24,9 @@ def main():
     ap.add_argument("--small-tile-elems", type=int, default=None, help="override MLPEngineTC.small_tile_elems")
     ap.add_argument("--pair-block-n", type=int, default=None, help="512: one tile per CTA pair, 513: persistent pairs")
     args = ap.parse_args()
-    hp = dict(bench.WORKLOADS["boxworld"], matmul=args.matmul)
-    agent, _ = bench.build_agent("boxworld", hp, 0, "cuda:0")
+    hp = bench.workload_hp("boxworld")
+    _matmul = args.matmul
+    agent, _ = bench.build_agent("boxworld", hp, 0, "cuda:0", matmul=_matmul)
     st, env, eng = agent.storage, agent.env, agent.engine
     if args.wide_tile_rows is not None:
         eng.wide_tile_rows = args.wide_tile_rows

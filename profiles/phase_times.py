@@ -20,8 +20,9 @@ def main():
     ap.add_argument("--matmul", default="tf32x3")
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()
-    hp = dict(bench.WORKLOADS[args.workload], matmul=args.matmul)
-    agent, _ = bench.build_agent(args.workload, hp, 0, "cuda:0")
+    hp = bench.workload_hp(args.workload)
+    _matmul = args.matmul
+    agent, _ = bench.build_agent(args.workload, hp, 0, "cuda:0", matmul=_matmul)
     st, env = agent.storage, agent.env
     env.reset_rollout(st)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.iters + 3)]

@@ -58,21 +58,30 @@ def time_forms(only=None):
     wg.conv_B, wg.conv_H, wg.conv_W, wg.conv_C, wg.conv_wgrad = B, H, W, Cc, 1
     wg.flags, wg.out, wg.ldc, wg.block_n = L.EPI_ACCUM, gw.data_ptr(), Cc, 32
 
+    x_plain = (x[0] + x[1]).contiguous()
+    dy_plain = (dy[0] + dy[1]).contiguous()
+
+    def launch(name, g):
+        if name == "wgrad_fma":     # csrc/conv_cc.cu: the weight gradient on the fp32 FMA pipe (the engine's default)
+            L.call("tpp_conv3x3_wgrad", L.ptr(x_plain), 1, L.ptr(dy_plain), L.ptr(gw), B, H, W, Cc, Cc, L.stream_ptr())
+        else:
+            L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+
     res = {}
-    for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg)):
+    for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg), ("wgrad_fma", None)):
         if only:
             if name == only:
                 for _ in range(3):
-                    L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+                    launch(name, g)
                 torch.cuda.synchronize()
             continue
         for _ in range(2):
-            L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+            launch(name, g)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for _ in range(10):
-                L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
+                launch(name, g)
         graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -85,7 +94,7 @@ def time_forms(only=None):
 
 
 def main():
-    only = sys.argv[1] if len(sys.argv) > 1 else None      # forward | dgrad | wgrad: 3 plain launches (ncu: -s 2 -c 1)
+    only = sys.argv[1] if len(sys.argv) > 1 else None      # forward | dgrad | wgrad | wgrad_fma: 3 plain launches (ncu: -s 2 -c 1)
     res = time_forms(only)
     B, H, W, Cc = SHAPE["B"], SHAPE["H"], SHAPE["W"], SHAPE["C"]
     rows = B * H * W

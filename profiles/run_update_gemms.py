@@ -12,8 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-hp = dict(bench.WORKLOADS["boxworld"], matmul="tf32x3")
-agent, _ = bench.build_agent("boxworld", hp, 0, "cuda:0")
+hp = bench.workload_hp("boxworld")
+_matmul = "tf32x3"
+agent, _ = bench.build_agent("boxworld", hp, 0, "cuda:0", matmul=_matmul)
 st, env, eng = agent.storage, agent.env, agent.engine
 env.reset_rollout(st)
 agent.collect_rollout(env, st)

@@ -365,3 +365,36 @@ def test_implicit_conv3x3_weight_gradient(B, H, W, cin, cout, split):
     got = gw.view(3, 3, 32, cout)
     _close(got[:, :, :cin, :], ref, 1e-4)
     assert (got[:, :, cin:, :] == 0).all()
+
+
+@pytest.mark.parametrize("B,W,cin,cout", [(3, 32, 16, 16), (2, 32, 16, 32), (5, 16, 32, 32), (9, 8, 32, 32),
+                                          (160, 32, 16, 16), (700, 8, 32, 32)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_conv3x3_weight_gradient_fma_kernel(B, W, cin, cout, relu):
+    """tpp_conv3x3_wgrad (csrc/conv_cc.cu): exact-fp32 FMA form of the weight gradient for the narrow IMPALA layers,
+    gw[(ky*3 + kx)*32 + ci][co] += sum X[y+ky-1][x+kx-1][ci] dY[y][x][co] with X = relu(x), against float64 autograd;
+    accumulates into gw (checked by calling it twice); more CTAs than tiles and fewer (persistent loop) both covered."""
+    L = _lib()
+    torch.manual_seed(B * 100 + W + cin)
+    H = W
+    x = torch.randn(B, H, W, cin, device="cuda")
+    dy = torch.randn(B * H * W, cout, device="cuda")
+    gw = torch.zeros(288, cout, device="cuda")
+    for _ in range(2):
+        L.call("tpp_conv3x3_wgrad", L.ptr(x), 1 if relu else 0, L.ptr(dy), L.ptr(gw), B, H, W, cin, cout, L.stream_ptr())
+    xd = (x.clamp_min(0) if relu else x).double().permute(0, 3, 1, 2)
+    wd = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(xd, wd, padding=1).backward(dy.double().view(B, H, W, cout).permute(0, 3, 1, 2))
+    ref = 2 * wd.grad.permute(2, 3, 1, 0)                   # [ky][kx][ci][co], accumulated twice
+    got = gw.view(3, 3, 32, cout)
+    _close(got[:, :, :cin, :], ref, 2e-6)                   # fp32 FMA chains of <= ~1000 terms + fp32 partial sums
+    assert (got[:, :, cin:, :] == 0).all()
+
+
+def test_conv3x3_weight_gradient_fma_kernel_refuses_other_shapes():
+    L = _lib()
+    x = torch.randn(2, 14, 14, 16, device="cuda")
+    dy = torch.randn(2 * 14 * 14, 16, device="cuda")
+    gw = torch.zeros(288, 16, device="cuda")
+    rc = L.load().tpp_conv3x3_wgrad(L.ptr(x), 0, L.ptr(dy), L.ptr(gw), 2, 14, 14, 16, 16, L.stream_ptr())
+    assert rc == L.ENOTSUP

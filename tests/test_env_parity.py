@@ -195,6 +195,47 @@ def test_numpy_compat_matches_reference_types():
     assert rew.dtype == np.float64 and done.dtype == np.bool_ and info[0]["env_reward"] == 1.0
 
 
+def test_b200_env_steps_under_the_reference_shaped_cpu_training_loop():
+    """Drop-in the other way round: the B200 env with ``numpy_compat=True`` is the env of the
+    REFERENCE's own training loop (agents/ppo.py:228-254, restated in oracle.ppo.ppo_iteration: torch-CPU policy,
+    FloatTensor(obs) -> dist.sample() -> env.step(act.numpy())), nothing else of this package involved.  The loop must
+    run on the reference's types, every transition it sees must be the oracle env's transition from the same state,
+    and the policy must come out finite."""
+    from oracle import ppo as oppo
+    from oracle.prevec import OraclePreVec
+    from tpp_b200.discrete_env.cartpole_pre_vec import CartPoleVecEnv
+    N, T = 64, 32
+    env = CartPoleVecEnv(n_envs=N, seed=3, max_steps=20, numpy_compat=True)
+    orc = OraclePreVec("cartpole", N, seed=3, max_steps=20)
+    seen = {"steps": 0, "dones": 0}
+
+    def env_step(a):
+        assert isinstance(a, np.ndarray) and a.dtype == np.int64
+        orc.state = np.asarray(env.state.cpu() if torch.is_tensor(env.state) else env.state, dtype=np.float64)
+        orc.n_steps = np.asarray(env.n_steps.cpu() if torch.is_tensor(env.n_steps) else env.n_steps, dtype=np.float64)
+        obs, rew, done, info = env.step(a)
+        assert obs.dtype == np.float64 and rew.dtype == np.float64 and done.dtype == np.bool_ and len(info) == N
+        o_obs, o_rew, o_done = orc.step(a, reset_rows=orc.sample_block())
+        assert np.array_equal(done, o_done)
+        keep = ~done                                    # reset rows come from the B200 env's own Philox stream
+        np.testing.assert_allclose(obs[keep], o_obs[keep], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(rew, o_rew, rtol=1e-5, atol=2e-6)
+        seen["steps"] += N
+        seen["dones"] += int(done.sum())
+        return obs, rew, done
+
+    torch.manual_seed(0)
+    pol = oppo.OraclePolicy(oppo.OracleMLP(9, 4, 64, 32), 2)
+    opt = oppo.make_adam(pol, 5e-4)
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (N, 9)
+    for _ in range(2):
+        obs, logs = oppo.ppo_iteration(env_step, obs, pol, opt, T, N, 0.99, 0.95, epoch=1, n_minibatch=2,
+                                       mini_batch_size=1024)
+    assert seen["steps"] == 2 * T * N and seen["dones"] > 0
+    assert all(torch.isfinite(p).all() for p in pol.parameters())
+
+
 def test_create_from_yaml_set():
     from tpp_b200.discrete_env.cartpole_pre_vec import create_cartpole
     hp = dict(n_envs=32, degrees_v=9, h_range_v=1.8, n_steps=256, gamma=0.99)

@@ -47,6 +47,74 @@ def test_gae_against_oracle(T, N):
         np.testing.assert_allclose(st.adv_batch.cpu().numpy(), oppo.normalize_adv(adv).numpy(), rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("T,N", [(1, 2), (7, 5), (31, 33), (32, 64), (33, 40), (100, 300), (256, 256), (256, 4096),
+                                 (257, 1000), (500, 2048), (256, 4736)])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_gae_warp_scan_fused(T, N, normalize):
+    """``gae_mode="warp_scan"``: warp-level segmented scan over n_steps + moments + normalisation in ONE launch
+    (tpp_gae_scan).  The scan re-associates the recurrence's products, so it is compared within the stated tolerance
+    (north_star: 1e-5 relative; here 1e-5 of the tensor's scale + 1e-5 relative) -- and against the exact kernels."""
+    gen = torch.Generator().manual_seed(T * 1000 + N)
+    rew = torch.randn(T, N, generator=gen)
+    value = torch.randn(T + 1, N, generator=gen)
+    done = (torch.rand(T, N, generator=gen) < 0.05).float()
+    st = _storage((3,), T, N)
+    st.gae_mode = "warp_scan"
+    st.rew[:, :N], st.value[:, :N], st.done_u8[:, :N] = rew.cuda(), value.cuda(), done.cuda().to(torch.uint8)
+    launches = st.n_launches
+    st.compute_estimates(0.999, 0.9, True, normalize)
+    assert st.n_launches - launches == 1, "the fused scan is one launch (normalisation included)"
+    adv, ret = oppo.gae(rew, done, value, 0.999, 0.9)
+    scale = float(adv.abs().max())
+    np.testing.assert_allclose(st.return_batch.cpu().numpy(), ret.numpy(), rtol=1e-5, atol=1e-5 * scale)
+    want = oppo.normalize_adv(adv) if (normalize and T * N > 1) else adv
+    if normalize and T * N <= 1:
+        return
+    np.testing.assert_allclose(st.adv_batch.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    # moments of the raw advantages (what a sharded run all-reduces)
+    m = st.moments.cpu().numpy()
+    assert m[2] == T * N
+    np.testing.assert_allclose(m[0], float(adv.double().sum()), rtol=1e-6, atol=1e-4 * scale)
+    np.testing.assert_allclose(m[1], float((adv.double() ** 2).sum()), rtol=1e-5)
+
+
+def test_gae_warp_scan_falls_back_outside_its_range():
+    """N / 32 CTAs must be co-resident for the grid barrier: larger env counts run the exact kernels (bit-exact)."""
+    T, N = 64, 1 << 16
+    gen = torch.Generator().manual_seed(5)
+    rew, value = torch.randn(T, N, generator=gen), torch.randn(T + 1, N, generator=gen)
+    done = (torch.rand(T, N, generator=gen) < 0.05).float()
+    st = _storage((3,), T, N)
+    st.gae_mode = "warp_scan"
+    st.rew[:, :N], st.value[:, :N], st.done_u8[:, :N] = rew.cuda(), value.cuda(), done.cuda().to(torch.uint8)
+    st.compute_estimates(0.99, 0.95, True, True)
+    assert torch.equal(st.return_batch.cpu(), oppo.gae(rew, done, value, 0.99, 0.95)[1])
+
+
+def test_gae_warp_scan_inside_a_cuda_graph():
+    """The cooperative launch is capturable: PPO.train's rollout graph ends with it."""
+    T, N = 256, 4096
+    gen = torch.Generator().manual_seed(9)
+    rew, value = torch.randn(T, N, generator=gen), torch.randn(T + 1, N, generator=gen)
+    done = (torch.rand(T, N, generator=gen) < 0.02).float()
+    st = _storage((3,), T, N)
+    st.gae_mode = "warp_scan"
+    st.rew[:, :N], st.value[:, :N], st.done_u8[:, :N] = rew.cuda(), value.cuda(), done.cuda().to(torch.uint8)
+    st.compute_estimates(0.99, 0.95, True, True)
+    eager = st.adv_batch.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            st.compute_estimates(0.99, 0.95, True, True)
+    st.adv.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(st.adv_batch.cpu().numpy(), eager.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
 def test_use_gae_false_is_refused():
     st = _storage((3,), 4, 4)
     with pytest.raises(NotImplementedError):

@@ -10,7 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TPP_B200_LIB") or os.path.join(_HERE, "csrc", "libtpp_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
+ENOTSUP = 10002          # TPP_ENOTSUP
 
 
 class TppError(RuntimeError):
@@ -100,6 +101,7 @@ SIGNATURES = {
     "tpp_boxworld_emit_frames": [C.POINTER(BoxWorldState), _vp, _vp],
     "tpp_vecnormalize_step": [_vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _f64, _f64, _f64, _vp],
     "tpp_gae": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _vp],
+    "tpp_gae_scan": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _f32, _f32, _i32, _vp],
     "tpp_adv_normalize": [_vp, _vp, _i32, _i32, _i64, _vp],
     "tpp_episode_scan": [_vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
     "tpp_gather_vec": [_vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
@@ -118,6 +120,7 @@ SIGNATURES = {
     "tpp_bias_act_split": [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
     "tpp_gru_mask_split": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp],
     "tpp_gru_gates": [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
+    "tpp_conv3x3_wgrad": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],

@@ -157,6 +157,12 @@ class PPO(BaseAgent):
         # (tpp_policy_rollout_fused); False keeps the per-layer GEMM launches + tail kernel
         self.fused_rollout = bool(kwargs.get("fused_rollout", True))
         self.max_group_rows = int(kwargs.get("max_group_rows", 1 << 18))
+        # GAE: "exact" (bit-identical to the reference's sequential fp32 recurrence) or "warp_scan" (one fused launch:
+        # warp-level segmented scan over n_steps + moments + normalisation, common/storage.py::compute_estimates)
+        if "gae_mode" in kwargs:
+            for st in (storage, storage_valid):
+                if st is not None:
+                    st.gae_mode = kwargs["gae_mode"]
         # sharded runs keep the whole-epoch graph: the per-step ncclAllReduce is captured with the kernels around it
         # (False: per-group graphs with the all-reduce launched from the host between them)
         self.graph_allreduce = bool(kwargs.get("graph_allreduce", True))

@@ -543,6 +543,9 @@ class ImpalaEngineTC:
         self.n_launches = 0
         self.last_fs = None
         self._ws = {}
+        # weight gradients of the 16 / 32-channel convolutions on the fp32 FMA pipe (tpp_conv3x3_wgrad: exact fp32, each
+        # operand byte staged once; 3-4x the tensor-core form at these channel counts); False = tcgen05 im2col form
+        self.wgrad_cc = True
         emb = policy.embedder
         self._names = {id(p): n for n, p in policy.named_parameters()}
         C, H, W = self.obs_shape
@@ -754,13 +757,23 @@ class ImpalaEngineTC:
         return ws.head
 
     # ------------------------------------------------------------------------------------------
-    def _wgrad(self, ws, ci, dy, src, B, H, W, strides=None):
+    def _wgrad(self, ws, ci, dy, src, B, H, W, strides=None, plain=None, relu=True):
         """Weight gradient from the dY pair and the convolution's input.  Implicit form (src = TF32 pair of the NHWC
         input, already ReLU'd): gw[tap*32 + ci][co] += sum_p X[p + tap][ci] dY[p][co], the A tiles gathered by TMA im2col.
         Explicit form (first convolution, src = plain tensor + strides): gw[co][tap*cin + ci] += dY^T col(X)."""
         c = self.convs[ci]
         rows = B * H * W
         chunks = _ceil(rows, self.WGRAD_CHUNK)
+        if c["implicit"] and plain is not None and self.wgrad_cc:
+            # narrow layers: exact-fp32 FMA kernel with the halo staged once per tile (csrc/conv_cc.cu); shapes it was
+            # not built for answer ENOTSUP and take the tensor-core form below
+            rc = _lib.load().tpp_conv3x3_wgrad(_lib.ptr(plain), 1 if relu else 0, _lib.ptr(dy["plain"]), _lib.ptr(c["gw"]),
+                                               B, H, W, c["cin"], c["cout"], _lib.stream_ptr())
+            if rc == 0:
+                self.n_launches += 1
+                return
+            if rc != _lib.ENOTSUP:
+                raise _lib.TppError(f"tpp_conv3x3_wgrad failed with status {rc}")
         if c["implicit"]:
             self._tc(src, 0, (dy["hi"], dy["lo"]), c["cout"], self.KI, c["cout"], rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
                      out=c["gw"], ldc=c["cout"], block_n=32, conv=(B, H, W, c["cin"]), conv_wgrad=1,
@@ -825,14 +838,14 @@ class ImpalaEngineTC:
             if k == len(self.blocks) - 1:
                 self._colsum(X["plain"], rows, cout, self.convs[b2]["b_off"])
             # res2: r2 = conv_b2(relu(c2)) + r1 ; c2 = conv_a2(relu(r1))
-            self._wgrad(ws, b2, X, pair(wb["c2"]), M, Ho, Wo)
+            self._wgrad(ws, b2, X, pair(wb["c2"]), M, Ho, Wo, plain=c2)
             self._dgrad(ws, b2, X, M, Ho, Wo, Y, mask=c2, colsum_off=self.convs[a2]["b_off"])
-            self._wgrad(ws, a2, Y, pair(wb["r1"]), M, Ho, Wo)
+            self._wgrad(ws, a2, Y, pair(wb["r1"]), M, Ho, Wo, plain=r1)
             self._dgrad(ws, a2, Y, M, Ho, Wo, Z, mask=r1, addend=X["plain"], colsum_off=self.convs[b1]["b_off"])
             # res1: r1 = conv_b1(relu(c1)) + p ; c1 = conv_a1(relu(p))
-            self._wgrad(ws, b1, Z, pair(wb["c1"]), M, Ho, Wo)
+            self._wgrad(ws, b1, Z, pair(wb["c1"]), M, Ho, Wo, plain=c1)
             self._dgrad(ws, b1, Z, M, Ho, Wo, Y, mask=c1, colsum_off=self.convs[a1]["b_off"])
-            self._wgrad(ws, a1, Y, pair(wb["p"]), M, Ho, Wo)
+            self._wgrad(ws, a1, Y, pair(wb["p"]), M, Ho, Wo, plain=p)
             self._dgrad(ws, a1, Y, M, Ho, Wo, X, mask=p, addend=Z["plain"])
             # max-pool, then the block's first convolution
             ga = wb["ga"]
@@ -845,7 +858,7 @@ class ImpalaEngineTC:
                 self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, strides=(self._x.stride(0), W0, 1, H0 * W0))
             else:
                 prev = ws.blk[k - 1]
-                self._wgrad(ws, b["conv"], ga, pair(prev["r2"]), M, Hh, Ww)
+                self._wgrad(ws, b["conv"], ga, pair(prev["r2"]), M, Hh, Ww, plain=prev["r2"]["plain"], relu=False)
                 self._dgrad(ws, b["conv"], ga, M, Hh, Ww, prev["gX"],
                             colsum_off=self.convs[self.blocks[k - 1]["res"][1][1]]["b_off"])
         # fold the GEMM-layout weight gradients back into the flat gradient buffer

@@ -58,6 +58,10 @@ class Storage:
         self.is_image = len(self.obs_shape) == 3
         self.obs_width = int(np.prod(self.obs_shape))
         self.world_size, self.process_group = 1, None
+        # "exact": sequential recurrence in the reference's fp32 operation order (raw advantages / returns bit-identical
+        # to torch CPU); "warp_scan": warp-level segmented scan over n_steps fused with moments + normalisation in one
+        # launch (tpp_gae_scan; agrees to ~4e-7 of the advantage scale, stated tolerance 1e-5)
+        self.gae_mode = "exact"
         self._mb = {}
         self._pinned = None
         self.h2d_bytes = 0       # bytes staged from the host by store()/stage_step() (bench accounting)
@@ -83,7 +87,8 @@ class Storage:
         self.value = torch.zeros(T + 1, ld, **f)
         self.ret = torch.zeros(T, ld, **f)
         self.adv = torch.zeros(T, ld, **f)
-        self.moments = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.moments4 = torch.zeros(4, dtype=torch.float64, device=dev)   # [3]: grid-barrier counter of tpp_gae_scan
+        self.moments = self.moments4[:3]
         self.info_batch = deque(maxlen=T)
         self._hidden = None
         self.done_carry = torch.zeros(ld, dtype=torch.uint8, device=dev)   # done flags of the previous rollout's last step
@@ -266,7 +271,23 @@ class Storage:
             # use_gae=False branch is broken upstream; refuse rather than silently reproduce or "fix" it.
             raise NotImplementedError("use_gae=False is broken in the reference (storage.py:69-77); unsupported")
         T, N, s = self.num_steps, self.num_envs, _lib.stream_ptr()
-        self.moments.zero_()
+        self.moments4.zero_()
+        if self.gae_mode == "warp_scan":
+            fuse = 1 if (normalize_adv and self.world_size == 1) else 0
+            rc = _lib.load().tpp_gae_scan(_lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value),
+                                          _lib.ptr(self.adv), _lib.ptr(self.ret), _lib.ptr(self.moments4), T, N, self.ld,
+                                          float(gamma), float(lmbda), fuse, s)
+            if rc == 0:
+                self.n_launches += 1
+                if normalize_adv and not fuse:
+                    parallel.allreduce_moments_(self.moments, self.process_group)
+                    _lib.call("tpp_adv_normalize", _lib.ptr(self.adv), _lib.ptr(self.moments), T, N, self.ld, s)
+                    self.n_launches += 1
+                return
+            if rc != _lib.ENOTSUP:      # (ENOTSUP: T or N outside the fused kernel's range -> the exact kernels below)
+                raise _lib.TppError(f"tpp_gae_scan failed with status {rc}")
+        elif self.gae_mode != "exact":
+            raise ValueError(f"gae_mode must be 'exact' or 'warp_scan', not {self.gae_mode!r}")
         _lib.call("tpp_gae", _lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value), _lib.ptr(self.adv),
                   _lib.ptr(self.ret), _lib.ptr(self.moments), T, N, self.ld, float(gamma), float(lmbda), s)
         self.n_launches += 1

@@ -1,7 +1,7 @@
 // Library-level entry points of the C-ABI (include/tpp_b200.h).
 #include "tpp_common.cuh"
 
-extern "C" int tpp_version(void) { return 2; }
+extern "C" int tpp_version(void) { return 3; }
 
 extern "C" int tpp_device_sm_count(int* out_sm_count) {
   TPP_CHECK_ARG(out_sm_count);

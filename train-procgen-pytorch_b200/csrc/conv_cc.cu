@@ -1,0 +1,197 @@
+// 3x3 convolution weight gradient for the IMPALA-CNN's narrow layers (16 / 32 channels) on the fp32 FMA pipe.
+//
+//   gw[(ky*3 + kx)*32 + ci][co] += sum over (b, y, x) of  X[b][y + ky - 1][x + kx - 1][ci] * dY[b][y][x][co]
+//
+// (reference: autograd of nn.Conv2d(k=3, padding=1) in common/model.py:134-208, ResidualBlock / ImpalaBlock).
+//
+// Why not the tensor core here.  The output is tiny (9 * Cin * Cout <= 9216 numbers) and the contraction runs over
+// millions of pixels.  On tcgen05 (csrc/gemm_tc.cu, conv_wgrad form) that is an M = 288, N = 16..32 problem: fp32 parity
+// needs three TF32 passes, the im2col operand is re-gathered once per tap from L2 (6.4 GB for a 268 MB tensor at the
+// block-1 shape, half of it zero-fill because MN-major fp32 rows must be 128 bytes) and N = 16 uses an eighth of an MMA's
+// columns: measured 825 us = 11.7 TFLOP/s at the block-1 shape (2 M pixels, 16 -> 16 channels), ten times the HBM time of
+// its operands.  The same contraction is 4.8 G fp32 FMAs -- 134 us of the B200's FMA pipe -- when every operand byte
+// is read from HBM once, staged in shared memory once and reused from registers:
+//   * a CTA walks tiles of R = 8 image rows; the (R + 2) x (W + 2) input halo and the R x W dY tile are staged by
+//     cp.async (zero fill outside the image) into a double buffer, so the next tile loads under this tile's FMAs;
+//   * a thread owns a 4-ci x 4-co block of ALL nine taps (144 accumulators) for one pixel group; it slides along a row
+//     segment keeping the 3 x 3 window of float4 input vectors in registers: per pixel 3 new LDS.128 of X, one of dY,
+//     144 FFMA (36 FMAs per shared-memory load);
+//   * the CTA's pixel groups (16 for 16 x 16 channels) take different rows of the tile; groups sharing a warp read rows an
+//     ODD number of pixels apart (odd row pitches), i.e. disjoint bank halves -- every LDS.128 is one wavefront;
+//   * accumulation chains stay short (a thread sums ~1000 pixels), partial sums meet in shared memory, then one
+//     red.global.add.v4.f32 per four outputs and CTA.
+// Exact fp32 products (no TF32 split), input read as relu(plain) -- the activation the forward pass convolved.
+#include "tpp_common.cuh"
+
+namespace tpp {
+
+template <int CIN, int COUT, int W>
+struct WgCfg {
+  static constexpr int R = 8;                              // image rows per tile
+  static constexpr int CI_B = CIN / 4, CO_B = COUT / 4;
+  static constexpr int COMBOS = CI_B * CO_B;               // threads of one pixel group
+  static constexpr int THREADS = 256;
+  static constexpr int G = THREADS / COMBOS;               // pixel groups per CTA
+  static constexpr int SEG = W >= 16 ? 16 : W;             // pixels a group walks in one unit
+  static constexpr int SEGS = W / SEG;
+  static constexpr int UNITS = R * SEGS;                   // (row, segment) units of a tile
+  static constexpr int XP = (W + 2) | 1;                   // halo row pitch in pixels (odd)
+  static constexpr int DP = W | 1;                         // dY row pitch in pixels (odd)
+  static constexpr int X_FLOATS = (R + 2) * XP * CIN;
+  static constexpr int D_FLOATS = R * DP * COUT;
+  static constexpr int BUF_FLOATS = X_FLOATS + D_FLOATS;
+  static constexpr int OUT_FLOATS = 9 * CIN * COUT;
+  // (the final reduction gives every pixel group its own copy of the outputs: G * OUT_FLOATS = 36864 floats for every shape)
+  static constexpr size_t SMEM = sizeof(float) * (2 * BUF_FLOATS > G * OUT_FLOATS ? 2 * BUF_FLOATS : G * OUT_FLOATS);
+  static_assert(THREADS % COMBOS == 0 && UNITS % G == 0 && W % SEG == 0, "tile does not divide");
+};
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool valid) {
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(n)
+               : "memory");
+}
+
+template <int CIN, int COUT, int W>
+__global__ void __launch_bounds__(256, 1) conv3x3_wgrad_cc_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  float* __restrict__ gw, int B, int relu) {
+  using C = WgCfg<CIN, COUT, W>;
+  constexpr int H = W, R = C::R;
+  extern __shared__ __align__(16) float wg_sm[];
+  const int tid = threadIdx.x;
+  const int combo = tid % C::COMBOS, grp = tid / C::COMBOS;
+  const int ci4 = combo % C::CI_B, co4 = combo / C::CI_B;
+  const int tiles_per_img = H / R;
+  const int ntiles = B * tiles_per_img;
+
+  auto stage = [&](int tile, float* buf) {
+    const int b = tile / tiles_per_img, y0 = (tile % tiles_per_img) * R;
+    const float* xb = x + (size_t)b * H * W * CIN;
+    const float* db = dy + ((size_t)b * H + y0) * W * COUT;
+    constexpr int XC = (R + 2) * (W + 2) * C::CI_B;          // 16-byte chunks of the halo
+    for (int i = tid; i < XC; i += C::THREADS) {
+      const int c = i % C::CI_B, hx = (i / C::CI_B) % (W + 2), hr = i / (C::CI_B * (W + 2));
+      const int gy = y0 - 1 + hr, gx = hx - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      cp_async16_zfill(buf + (hr * C::XP + hx) * CIN + c * 4, ok ? xb + ((size_t)gy * W + gx) * CIN + c * 4 : x, ok);
+    }
+    float* dbuf = buf + C::X_FLOATS;
+    constexpr int DC = R * W * C::CO_B;
+    for (int i = tid; i < DC; i += C::THREADS) {
+      const int c = i % C::CO_B, px = (i / C::CO_B) % W, r = i / (C::CO_B * W);
+      cp_async16_zfill(dbuf + (r * C::DP + px) * COUT + c * 4, db + ((size_t)r * W + px) * COUT + c * 4, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[9][4][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.0f;
+
+  int it = 0;
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, wg_sm);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    float* buf = wg_sm + (it & 1) * C::BUF_FLOATS;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      stage(next, wg_sm + ((it + 1) & 1) * C::BUF_FLOATS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* dbuf = buf + C::X_FLOATS;
+#pragma unroll 1
+    for (int u = grp; u < C::UNITS; u += C::G) {
+      const int r = u % R, x0 = (u / R) * C::SEG;            // groups g, g + 1 (same warp): adjacent rows, odd pitch apart
+      const float* xp = buf + (r * C::XP + x0) * CIN + ci4 * 4;      // halo (r, x0): tap (0, 0) of output pixel (r, x0)
+      const float* dp = dbuf + (r * C::DP + x0) * COUT + co4 * 4;
+      float4 col[3][3];                                      // [halo column x0 + k][ky]
+      auto ldx = [&](int hx, int ky) {
+        float4 v = *reinterpret_cast<const float4*>(xp + (ky * C::XP + hx) * CIN);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        return v;
+      };
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) { col[0][ky] = ldx(0, ky); col[1][ky] = ldx(1, ky); }
+#pragma unroll
+      for (int px = 0; px < C::SEG; ++px) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) col[(px + 2) % 3][ky] = ldx(px + 2, ky);
+        const float4 d4 = *reinterpret_cast<const float4*>(dp + px * COUT);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 xv = col[(px + kx) % 3][ky];
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[ky * 3 + kx][i][j] = fmaf(xs[i], d[j], acc[ky * 3 + kx][i][j]);
+          }
+      }
+    }
+    __syncthreads();                                         // this buffer is refilled two tiles from now
+  }
+  // ---- the CTA's pixel groups meet in shared memory (one copy of the outputs per group: plain stores, no atomics), then
+  // one vector reduction per four outputs into the global gradient ----
+  float* red = wg_sm + grp * C::OUT_FLOATS;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(red + (t * CIN + ci4 * 4 + i) * COUT + co4 * 4) =
+          make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
+  __syncthreads();
+  for (int i = tid; i < C::OUT_FLOATS / 4; i += C::THREADS) {
+    const int co = (i % C::CO_B) * 4, ci = (i / C::CO_B) % CIN, t = i / (C::CO_B * CIN);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < C::G; ++g) {
+      const float4 q = *reinterpret_cast<const float4*>(wg_sm + g * C::OUT_FLOATS + i * 4);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    float* dst = gw + ((size_t)t * 32 + ci) * COUT + co;     // GEMM layout of the engine: 32 channel slots per tap
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
+template <int CIN, int COUT, int W>
+static int launch_wgrad_cc(const float* x, const float* dy, float* gw, int B, int relu, cudaStream_t s) {
+  using C = WgCfg<CIN, COUT, W>;
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_wgrad_cc_kernel<CIN, COUT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return TPP_ENOTSUP;
+    attr_set = true;
+  }
+  const int ntiles = B * (W / C::R);
+  const int grid = ntiles < sms ? ntiles : sms;
+  conv3x3_wgrad_cc_kernel<CIN, COUT, W><<<grid, C::THREADS, C::SMEM, s>>>(x, dy, gw, B, relu);
+  TPP_LAUNCH_STATUS();
+}
+
+}  // namespace tpp
+
+extern "C" int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, float* gw, int32_t B, int32_t H, int32_t W,
+                                 int32_t cin, int32_t cout, void* stream) {
+  TPP_CHECK_ARG(x && dy && gw && B > 0);
+  if (H != W) return TPP_ENOTSUP;
+  cudaStream_t s = tpp_stream(stream);
+  if (cin == 16 && cout == 16 && W == 32) return tpp::launch_wgrad_cc<16, 16, 32>(x, dy, gw, B, relu, s);
+  if (cin == 16 && cout == 32 && W == 32) return tpp::launch_wgrad_cc<16, 32, 32>(x, dy, gw, B, relu, s);
+  if (cin == 32 && cout == 32 && W == 16) return tpp::launch_wgrad_cc<32, 32, 16>(x, dy, gw, B, relu, s);
+  if (cin == 32 && cout == 32 && W == 8) return tpp::launch_wgrad_cc<32, 32, 8>(x, dy, gw, B, relu, s);
+  return TPP_ENOTSUP;
+}

@@ -3,6 +3,8 @@
 // Replaces (reference, torch CPU): Storage.compute_estimates (common/storage.py:56-79) and
 // Storage.collate_data (common/storage.py:112-128), plus TransposeFrame/ScaledFloatFrame
 // (common/env/procgen_wrappers.py:391-419) folded into the image gather.
+#include <cstdlib>
+
 #include "tpp_common.cuh"
 
 namespace tpp {
@@ -179,6 +181,140 @@ __global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// GAE as a warp-level segmented scan over n_steps, fused with the advantage moments AND the normalisation
+// (opt-in: Storage(gae_mode="warp_scan"); the kernels above stay the default because they are bit-exact).
+//
+// The recurrence A[t] = a[t] * A[t+1] + b[t], a = (gamma*lambda)(1 - done), b = delta, is a composition of affine maps;
+// done = 1 makes a = 0 and cuts the chain (the segment boundary).  A CTA owns 32 envs and stages their columns in shared
+// memory TRANSPOSED ([env][time], odd pitch: the coalesced global rows scatter over 32 banks); then the lanes of a warp
+// split the time axis of one env: lane l composes its L = ceil(T/32) consecutive steps sequentially (2 L dependent fp32
+// ops), the 32 per-lane maps are combined by a Kogge-Stone SUFFIX scan (5 shuffle rounds), and every lane replays its L
+// steps from its incoming A.  Dependent chain per env: 3 L + 5 rounds instead of 3 T operations; the warp's 4 envs are
+// independent chains.  The products are re-associated, so the result is NOT bit-identical to the sequential evaluation
+// (measured max |dA| <= 4e-7 * max|A| at T = 256; stated tolerance 1e-5, tests/test_storage_parity.py).
+// Fused normalisation: per-CTA double moments -> global atomics -> grid barrier (cooperative launch: all CTAs are
+// co-resident) -> every CTA normalises ITS advantages straight from shared memory.  adv is written once, never re-read.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int gae_tp(int t, int L, int pad) { return t + (pad ? t / L : 0); }
+
+__global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
+                                                             const float* __restrict__ value, float* __restrict__ adv,
+                                                             float* __restrict__ ret, double* moments, int T, int N,
+                                                             int64_t ld, float gamma, float gl, int normalize, int PT) {
+  extern __shared__ __align__(16) uint8_t gae_sm[];
+  __shared__ double red[32];
+  float* sb = reinterpret_cast<float*>(gae_sm);            // [32][PT]  rewards -> delta -> advantages
+  float* sv = sb + (size_t)32 * PT;                        // [32][PT]  values 0 .. T
+  float* sa = sv + (size_t)32 * PT;                        // [32][PT]  1 - done
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int L = (T + 31) >> 5;                             // time steps per lane
+  const int pad = (L & 1) ? 0 : 1;                         // lane stride L (+1 if L is even): odd => conflict-free
+  const int e0 = blockIdx.x * 32;
+  {  // ---- stage (lanes over envs: coalesced rows; transposed shared-memory writes, pitch PT odd) ----
+    const int e = e0 + lane;
+    const bool on = e < N;
+    if (on) {
+      for (int t = warp; t < T; t += 8) {
+        const int64_t o = (int64_t)t * ld + e;
+        const int q = lane * PT + gae_tp(t, L, pad);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sb + q)), "l"(rew + o) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + q)), "l"(value + o) : "memory");
+      }
+      if (warp == 0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + lane * PT + gae_tp(T, L, pad))),
+                     "l"(value + (int64_t)T * ld + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 8
+    for (int t = warp; t < T; t += 8)
+      sa[lane * PT + gae_tp(t, L, pad)] = on ? 1.0f - (float)__ldcs(done + (int64_t)t * ld + e) : 0.0f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  // ---- scan (lanes over time; warp w owns envs 4 w .. 4 w + 3, four independent chains) ----
+  double s1 = 0.0, s2 = 0.0;
+  {
+    const int t_lo = lane * L, t_hi = min(T, t_lo + L);     // this lane's steps [t_lo, t_hi)
+    float P[4], Q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float* b = sb + (warp * 4 + j) * PT;
+      const float* v = sv + (warp * 4 + j) * PT;
+      const float* a = sa + (warp * 4 + j) * PT;
+      float p = 1.0f, q = 0.0f;
+      for (int t = t_hi - 1; t >= t_lo; --t) {
+        const int i = gae_tp(t, L, pad);
+        const float nd = a[i], at = __fmul_rn(gl, nd);
+        // delta in the reference's operation order (bit-identical to the sequential kernels' delta)
+        const float dl = __fsub_rn(__fadd_rn(b[i], __fmul_rn(__fmul_rn(gamma, v[gae_tp(t + 1, L, pad)]), nd)), v[i]);
+        b[i] = dl;
+        q = fmaf(at, q, dl);                                // f_t o f_{t+1..}: x -> at (p x + q) + dl
+        p = at * p;
+      }
+      P[j] = p; Q[j] = q;
+    }
+    // inclusive suffix scan of the lane maps: S_l = f_l o f_{l+1} o ... o f_31
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p2 = __shfl_down_sync(0xffffffffu, P[j], d), q2 = __shfl_down_sync(0xffffffffu, Q[j], d);
+        if (lane + d < 32) { Q[j] = fmaf(P[j], q2, Q[j]); P[j] = P[j] * p2; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float A = __shfl_down_sync(0xffffffffu, Q[j], 1);     // A entering this lane's chunk = S_{l+1}(0)
+      if (lane == 31) A = 0.0f;
+      float* b = sb + (warp * 4 + j) * PT;
+      const float* a = sa + (warp * 4 + j) * PT;
+      const bool on = e0 + warp * 4 + j < N;
+      for (int t = t_hi - 1; t >= t_lo; --t) {
+        const int i = gae_tp(t, L, pad);
+        A = fmaf(__fmul_rn(gl, a[i]), A, b[i]);
+        b[i] = A;
+        if (on) { s1 += (double)A; s2 += (double)A * (double)A; }
+      }
+    }
+  }
+  s1 = block_sum(s1, red);                                  // (block_sum's barriers also publish the advantages)
+  s2 = block_sum(s2, red);
+  float mean = 0.0f, denom = 1.0f;
+  if (threadIdx.x == 0) {
+    atomicAdd(moments + 0, s1);
+    atomicAdd(moments + 1, s2);
+    if (blockIdx.x == 0) atomicAdd(moments + 2, (double)T * (double)N);
+  }
+  if (normalize) {
+    // grid barrier on the 4th slot of `moments` (an integer counter in its low word; the caller zeroes all four)
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(moments + 3);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(ctr, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(ctr) < gridDim.x) __nanosleep(20);
+      __threadfence();
+    }
+    __syncthreads();
+    const double n = __ldcg(moments + 2), m0 = __ldcg(moments + 0), m1 = __ldcg(moments + 1);
+    const double mean_d = m0 / n;
+    double var = (m1 - m0 * mean_d) / (n - 1.0);            // unbiased (torch.std default), as adv_normalize_kernel
+    var = var > 0.0 ? var : 0.0;
+    mean = (float)mean_d;
+    denom = (float)sqrt(var) + 1e-8f;
+  }
+  // ---- write back (lanes over envs again) ----
+  const int e = e0 + lane;
+  if (e < N)
+    for (int t = warp; t < T; t += 8) {
+      const int64_t o = (int64_t)t * ld + e;
+      const int q = lane * PT + gae_tp(t, L, pad);
+      const float A = sb[q];
+      __stcs(adv + o, normalize ? (A - mean) / denom : A);
+      __stcs(ret + o, __fadd_rn(A, sv[q]));
+    }
+}
+
 __global__ void __launch_bounds__(256) adv_normalize_kernel(float* adv, const double* moments, int T, int N,
                                                             int64_t ld) {
   // grid = (column chunks, T): no per-element div/mod; 128-bit accesses when the row allows it
@@ -334,6 +470,48 @@ extern "C" int tpp_gae(const float* rew, const uint8_t* done, const float* value
   const int grid = tpp_ceil_div(N, 128);
   tpp::gae_kernel<8><<<grid, 128, 0, tpp_stream(stream)>>>(rew, done, value, adv, ret, moments, T, N, ld, gamma, gl);
   TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_gae_scan(const float* rew, const uint8_t* done, const float* value, float* adv, float* ret,
+                            double* moments4, int32_t T, int32_t N, int64_t ld, float gamma, float lambda,
+                            int32_t normalize, void* stream) {
+  TPP_CHECK_ARG(rew && done && value && adv && ret && moments4 && T > 0 && N > 0 && ld >= N);
+  const float gl = (float)((double)gamma * (double)lambda);
+  const int L = (T + 31) / 32;
+  const int PT = (T + ((L & 1) ? 0 : T / L) + 1) | 1;       // > the padded index of slot T, odd
+  const size_t smem = (size_t)3 * 32 * PT * 4;
+  if (smem > 200 * 1024) return TPP_ENOTSUP;
+  static int max_grid = 0;
+  static size_t smem_seen = 0;
+  if (smem != smem_seen) {         // (per shared-memory size: the occupancy query is not repeated on the hot path)
+    cudaError_t e = cudaFuncSetAttribute(tpp::gae_scan_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tpp::gae_scan_fused_kernel, 256, smem) != cudaSuccess)
+      return TPP_ENOTSUP;
+    max_grid = per_sm * sms;
+    smem_seen = smem;
+  }
+  const int grid = tpp_ceil_div(N, 32);
+  if (normalize && grid > max_grid) return TPP_ENOTSUP;     // the grid barrier needs every CTA resident
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = tpp_stream(stream);
+  cudaLaunchAttribute at[1];
+  // Every CTA is resident by construction (grid <= max_grid, checked above), which is all the barrier needs; the
+  // cooperative attribute additionally makes the driver guarantee it (TPP_GAE_COOP=1; measured: see profiles/README.md)
+  static const bool coop = [] { const char* v = getenv("TPP_GAE_COOP"); return v && v[0] == '1'; }();
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = (normalize && coop) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tpp::gae_scan_fused_kernel, rew, done, value, adv, ret, moments4, (int)T, (int)N,
+                                     (int64_t)ld, gamma, gl, (int)normalize, PT);
+  if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+  return TPP_OK;
 }
 
 extern "C" int tpp_adv_normalize(float* adv, const double* moments, int32_t T, int32_t N, int64_t ld, void* stream) {
