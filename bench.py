@@ -702,7 +702,11 @@ def run_procgen(args, emit=True, name="procgen", with_roofline=True):
                       "2048 x 32x32 pixels, 16 -> 16 channels", "bound": "tensor", "achieved": round(tf, 2),
             "peak": pk["bf16"], "unit": "TFLOP/s", "frac": round(tf / pk["bf16"], 4), "traffic": traffic,
             "us_per_launch": round(forms["forward"], 1), "dgrad_us": round(forms["dgrad"], 1),
-            "wgrad_us": round(forms["wgrad"], 1),
+            "wgrad_us": round(forms["wgrad_fma"], 1), "wgrad_tensor_core_form_us": round(forms["wgrad"], 1),
+            "wgrad_note": "weight gradients of the narrow layers run on the fp32 FMA pipe (csrc/conv_cc.cu, exact fp32, "
+                          "every operand byte staged once): 2*pixels*9*Cin*Cout FLOP at "
+                          f"{flops / forms['wgrad_fma'] / 1e6:.1f} TFLOP/s; the tcgen05 im2col form of the same "
+                          "contraction is kept for other shapes",
             "gathered_operand_GBps": round(18 * pixels * rck.SHAPE["C"] * 4 / forms["forward"] / 1e3, 1),
             "note": f"peak = dense bf16 ({pk['source']}); algorithmic FLOPs 2*pixels*9*Cin*Cout; the tile is bound by "
                     "the L2->shared-memory gather of 9 taps x (hi, lo), see profiles/ncu_conv_r01.md"}

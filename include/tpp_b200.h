@@ -342,6 +342,19 @@ int tpp_im2col3x3(const void* x, int32_t x_is_u8, int32_t B, int32_t H, int32_t 
 int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, float* gw, int32_t B, int32_t H, int32_t W,
                       int32_t cin, int32_t cout, void* stream);
 
+/* The same for the network's first convolution (3 -> 16 channels, 64 x 64): x is the channel-planar float observation
+ * [B][3][H][W] with element strides sb (sample), sc (channel), sh (row), unit stride along x; gw is the engine's
+ * explicit layout [(ky*3 + kx)*3 + ci][cout] (row stride cout), accumulated into.  Other shapes: TPP_ENOTSUP.    */
+int tpp_conv3x3_wgrad_first(const float* x, int64_t sb, int64_t sc, int64_t sh, const float* dy, float* gw, int32_t B,
+                            int32_t H, int32_t W, int32_t cout, void* stream);
+
+/* Forward of that first convolution: out[b][y][x][co] = bias[co] + sum X[b][ci][y+ky-1][x+kx-1] * w[co][ci][ky][kx],
+ * x as above, w = the reference's nn.Conv2d weight [cout][3][3][3] and bias [cout] as they lie in the flat parameter
+ * buffer, out = NHWC [B][H][W][cout] plain fp32 (exact fp32 FMAs).  Replaces ImpalaBlock.conv on the observation
+ * (reference common/model.py:134-150).  H = W = 64, cout = 16; other shapes: TPP_ENOTSUP.                       */
+int tpp_conv3x3_fwd_first(const float* x, int64_t sb, int64_t sc, int64_t sh, const float* w, const float* bias,
+                          float* out, int32_t B, int32_t H, int32_t W, int32_t cout, void* stream);
+
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (common/model.py:163,171): y [B][(H+1)/2][(W+1)/2][C],
  * arg = winning tap (first maximum); backward routes dy to the winning input pixel (gather form, no atomics).   */
 int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,

@@ -14,7 +14,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-MINE = ("gemm_tc_kernel", "im2col3x3", "maxpool_", "colsum_narrow", "head_backward", "bias_act_split", "split_tf32")
+MINE = ("gemm_tc_kernel", "im2col3x3", "maxpool_", "colsum_narrow", "head_backward", "bias_act_split", "split_tf32",
+        "conv3x3_wgrad", "conv3x3_fwd_first")
 
 
 def main():

@@ -398,3 +398,40 @@ def test_conv3x3_weight_gradient_fma_kernel_refuses_other_shapes():
     gw = torch.zeros(288, 16, device="cuda")
     rc = L.load().tpp_conv3x3_wgrad(L.ptr(x), 0, L.ptr(dy), L.ptr(gw), 2, 14, 14, 16, 16, L.stream_ptr())
     assert rc == L.ENOTSUP
+
+
+@pytest.mark.parametrize("B", [1, 3, 40])
+def test_first_conv_weight_gradient_fma_kernel(B):
+    """tpp_conv3x3_wgrad_first: 3 -> 16 channels on the channel-planar 64 x 64 observation (a row of the minibatch's
+    [B, 3*64*64] float matrix, possibly with a padded row stride), gw[(ky*3 + kx)*3 + ci][co], against float64 autograd."""
+    L = _lib()
+    torch.manual_seed(B)
+    H = W = 64
+    ld = 3 * H * W + 32
+    xbuf = torch.rand(B, ld, device="cuda")
+    dy = torch.randn(B * H * W, 16, device="cuda")
+    gw = torch.zeros(32, 16, device="cuda")
+    L.call("tpp_conv3x3_wgrad_first", L.ptr(xbuf), ld, H * W, W, L.ptr(dy), L.ptr(gw), B, H, W, 16, L.stream_ptr())
+    xd = xbuf[:, :3 * H * W].reshape(B, 3, H, W).double()
+    wd = torch.zeros(16, 3, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    F.conv2d(xd, wd, padding=1).backward(dy.double().view(B, H, W, 16).permute(0, 3, 1, 2))
+    ref = wd.grad.permute(2, 3, 1, 0).reshape(27, 16)        # [(ky, kx, ci)][co]
+    _close(gw[:27], ref, 2e-6)
+    assert (gw[27:] == 0).all()
+
+
+@pytest.mark.parametrize("B", [1, 5, 64])
+def test_first_conv_forward_fma_kernel(B):
+    """tpp_conv3x3_fwd_first against torch conv2d (float64) on the planar observation, NHWC output, torch weight layout."""
+    L = _lib()
+    torch.manual_seed(B + 7)
+    H = W = 64
+    ld = 3 * H * W + 16
+    xbuf = torch.rand(B, ld, device="cuda")
+    w = torch.randn(16, 3, 3, 3, device="cuda") * 0.3
+    bias = torch.randn(16, device="cuda")
+    out = torch.zeros(B, H, W, 16, device="cuda")
+    L.call("tpp_conv3x3_fwd_first", L.ptr(xbuf), ld, H * W, W, L.ptr(w), L.ptr(bias), L.ptr(out), B, H, W, 16,
+           L.stream_ptr())
+    ref = F.conv2d(xbuf[:, :3 * H * W].reshape(B, 3, H, W).double(), w.double(), bias.double(), padding=1)
+    _close(out, ref.permute(0, 2, 3, 1), 1e-6)

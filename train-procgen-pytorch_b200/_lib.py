@@ -121,6 +121,8 @@ SIGNATURES = {
     "tpp_gru_mask_split": [_vp, _i64, _vp, _i32, _i32, _vp, _vp, _i64, _vp],
     "tpp_gru_gates": [_vp, _vp, _i64, _vp, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
     "tpp_conv3x3_wgrad": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
+    "tpp_conv3x3_wgrad_first": [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "tpp_conv3x3_fwd_first": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],

@@ -698,6 +698,12 @@ class ImpalaEngineTC:
                   ld_add=c["cout"])
         if c["implicit"]:
             self._tc(src, 0, c["wf"], 9 * c["sf"], rows, c["cout"], 9 * c["sf"], conv=(B, H, W, c["cin"]), **kw)
+        elif self._first_cc(c, H, W, strides) and flags == EPI_BIAS and pair is None:
+            # first convolution (K = 27): FMA-pipe kernel straight from the planar observation and the flat fp32
+            # parameters -- no col matrix, no TF32 weight copies
+            _lib.call("tpp_conv3x3_fwd_first", _lib.ptr(src), strides[0], strides[3], strides[1], self._p(c["w_off"]),
+                      self._p(c["b_off"]), _lib.ptr(plain), B, H, W, c["cout"], _lib.stream_ptr())
+            self.n_launches += 1
         else:
             self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
             ws.col_src = src
@@ -779,6 +785,13 @@ class ImpalaEngineTC:
                      out=c["gw"], ldc=c["cout"], block_n=32, conv=(B, H, W, c["cin"]), conv_wgrad=1,
                      split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, 3), chunks))))
             return
+        if self._first_cc(c, H, W, strides):
+            # first convolution (3 -> 16 on the planar 64 x 64 observation): FMA-pipe kernel straight from the observation
+            # and the plain dY (no col matrix, no dY pair)
+            _lib.call("tpp_conv3x3_wgrad_first", _lib.ptr(src), strides[0], strides[3], strides[1], _lib.ptr(dy["plain"]),
+                      _lib.ptr(c["gw"]), B, H, W, c["cout"], _lib.stream_ptr())
+            self.n_launches += 1
+            return
         if ws.col_src is not src:        # the forward pass of this minibatch left col(X) in place
             self._im2col(src, B, H, W, c["cin"], strides, False, ws.col, c["Kf"])
             ws.col_src = src
@@ -788,6 +801,11 @@ class ImpalaEngineTC:
         self._tc(ws.col, c["Kf"], (dy["hi"], dy["lo"]), c["cout"], n, c["cout"], rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
                  out=c["gw"], ldc=c["cout"], block_n=32,
                  split_k=max(1, min(_ceil(rows, 32), max(_ceil(296, _ceil(n, 128)), chunks))))
+
+    def _first_cc(self, c, H, W, strides):
+        """Shapes tpp_conv3x3_wgrad_first was built for (everything else: col matrix + tensor-core GEMM)."""
+        return bool(self.wgrad_cc and not c["implicit"] and c["cin"] == 3 and c["cout"] == 16 and H == 64 and W == 64
+                    and strides is not None and strides[2] == 1)
 
     def _dgrad(self, ws, ci, dy, B, H, W, out, mask=None, addend=None, colsum_off=None):
         """dX = conv(dY, flipped W) (* relu mask of the conv input) (+ skip gradient); column sums -> bias grad below."""
@@ -849,13 +867,17 @@ class ImpalaEngineTC:
             self._dgrad(ws, a1, Y, M, Ho, Wo, X, mask=p, addend=Z["plain"])
             # max-pool, then the block's first convolution
             ga = wb["ga"]
+            x_strides = (self._x.stride(0), self.obs_shape[2], 1, self.obs_shape[1] * self.obs_shape[2])
+            # block 1: the pooled gradient feeds only the first convolution's weight gradient; when that runs on the FMA
+            # kernel it reads the plain tensor and the TF32 pair (2/3 of this kernel's writes) is not produced
+            need_pair = not (k == 0 and self._first_cc(self.convs[b["conv"]], Hh, Ww, x_strides))
             _lib.call("tpp_maxpool3x3s2_bwd", _lib.ptr(X["plain"]), _lib.ptr(wb["arg"]), M, Hh, Ww, cout,
-                      _lib.ptr(ga["plain"]), _lib.ptr(ga["hi"]), _lib.ptr(ga["lo"]), s)
+                      _lib.ptr(ga["plain"]), _lib.ptr(ga["hi"]) if need_pair else None,
+                      _lib.ptr(ga["lo"]) if need_pair else None, s)
             self.n_launches += 1
             self._colsum(ga["plain"], M * Hh * Ww, cout, self.convs[b["conv"]]["b_off"])
             if k == 0:
-                C0, H0, W0 = self.obs_shape
-                self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, strides=(self._x.stride(0), W0, 1, H0 * W0))
+                self._wgrad(ws, b["conv"], ga, self._x, M, Hh, Ww, strides=x_strides)
             else:
                 prev = ws.blk[k - 1]
                 self._wgrad(ws, b["conv"], ga, pair(prev["r2"]), M, Hh, Ww, plain=prev["r2"]["plain"], relu=False)

@@ -182,6 +182,215 @@ static int launch_wgrad_cc(const float* x, const float* dy, float* gw, int B, in
   TPP_LAUNCH_STATUS();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// First convolution of the network (3 -> 16 channels on the 64 x 64 observation): the input is the channel-PLANAR float
+// observation [B][3][H][W] (element strides sb / sc / sh, unit stride along x), the output has 27 x 16 numbers.  Same
+// scheme as above with the roles re-balanced: a thread owns all nine taps x 3 input channels x 4 output channels (108
+// accumulators), a pixel group is 4 threads, the CTA's 64 groups take the 64 (row, 8-pixel segment) units of an
+// 8 x 64 tile.  gw layout = the engine's explicit form: gw[(ky*3 + kx)*3 + ci][co].  (The tensor-core path needed a
+// materialised col matrix and ran this contraction -- M = 27 -- at 911 us.)
+// ------------------------------------------------------------------------------------------------------------------
+template <int COUT, int W>
+struct WgFirstCfg {
+  static constexpr int CIN = 3, R = 8, SEG = 8;
+  static constexpr int CO_B = COUT / 4;
+  static constexpr int THREADS = 256;
+  static constexpr int G = THREADS / CO_B;
+  static constexpr int UNITS = R * (W / SEG);
+  static constexpr int XP = (W + 2) | 1;                   // halo row pitch in floats (odd)
+  static constexpr int DP = W | 1;                         // dY row pitch in pixels (odd)
+  static constexpr int X_FLOATS = ((CIN * (R + 2) * XP + 3) / 4) * 4;
+  static constexpr int D_FLOATS = R * DP * COUT;
+  static constexpr int BUF_FLOATS = X_FLOATS + D_FLOATS;
+  static constexpr int OUT_FLOATS = 9 * CIN * COUT;
+  static constexpr size_t SMEM = sizeof(float) * (2 * BUF_FLOATS > G * OUT_FLOATS ? 2 * BUF_FLOATS : G * OUT_FLOATS);
+  static_assert(UNITS % G == 0, "tile does not divide");
+};
+
+template <int COUT, int W>
+__global__ void __launch_bounds__(256, 1) conv3x3_wgrad_first_kernel(const float* __restrict__ x, long long sb, long long sc,
+                                                                     long long sh, const float* __restrict__ dy,
+                                                                     float* __restrict__ gw, int B) {
+  using C = WgFirstCfg<COUT, W>;
+  constexpr int H = W, R = C::R, CIN = 3;
+  extern __shared__ __align__(16) float wg_sm[];
+  const int tid = threadIdx.x;
+  const int co4 = tid % C::CO_B, grp = tid / C::CO_B;
+  const int tiles_per_img = H / R;
+  const int ntiles = B * tiles_per_img;
+
+  auto stage = [&](int tile, float* buf) {
+    const int b = tile / tiles_per_img, y0 = (tile % tiles_per_img) * R;
+    const float* xb = x + (size_t)b * sb;
+    constexpr int XE = CIN * (R + 2) * (W + 2);              // halo elements (4-byte copies: planar rows are not 16-byte
+    for (int i = tid; i < XE; i += C::THREADS) {             // aligned behind the left halo column)
+      const int hx = i % (W + 2), hr = (i / (W + 2)) % (R + 2), c = i / ((W + 2) * (R + 2));
+      const int gy = y0 - 1 + hr, gx = hx - 1;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* src = ok ? xb + c * sc + gy * sh + gx : x;
+      const int n = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(buf + (c * (R + 2) + hr) * C::XP + hx)), "l"(src), "r"(n) : "memory");
+    }
+    float* dbuf = buf + C::X_FLOATS;
+    const float* db = dy + ((size_t)b * H + y0) * W * COUT;
+    constexpr int DC = R * W * C::CO_B;
+    for (int i = tid; i < DC; i += C::THREADS) {
+      const int c = i % C::CO_B, px = (i / C::CO_B) % W, r = i / (C::CO_B * W);
+      cp_async16_zfill(dbuf + (r * C::DP + px) * COUT + c * 4, db + ((size_t)r * W + px) * COUT + c * 4, true);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[9][CIN][4];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.0f;
+
+  int it = 0;
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, wg_sm);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    float* buf = wg_sm + (it & 1) * C::BUF_FLOATS;
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      stage(next, wg_sm + ((it + 1) & 1) * C::BUF_FLOATS);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* dbuf = buf + C::X_FLOATS;
+#pragma unroll 1
+    for (int u = grp; u < C::UNITS; u += C::G) {
+      const int r = u % R, x0 = (u / R) * C::SEG;            // a warp's 8 groups: the 8 rows of one segment (odd pitch apart)
+      const float* xp = buf + r * C::XP + x0;                // plane 0, halo (r, x0)
+      const float* dp = dbuf + (r * C::DP + x0) * COUT + co4 * 4;
+      float col[3][3][CIN];                                  // [halo column x0 + k][ky][ci]
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) col[k][ky][c] = xp[(c * (R + 2) + ky) * C::XP + k];
+#pragma unroll
+      for (int px = 0; px < C::SEG; ++px) {
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) col[(px + 2) % 3][ky][c] = xp[(c * (R + 2) + ky) * C::XP + px + 2];
+        const float4 d4 = *reinterpret_cast<const float4*>(dp + px * COUT);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                acc[ky * 3 + kx][c][j] = fmaf(col[(px + kx) % 3][ky][c], d[j], acc[ky * 3 + kx][c][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* red = wg_sm + grp * C::OUT_FLOATS;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+      *reinterpret_cast<float4*>(red + (t * CIN + c) * COUT + co4 * 4) =
+          make_float4(acc[t][c][0], acc[t][c][1], acc[t][c][2], acc[t][c][3]);
+  __syncthreads();
+  for (int i = tid; i < C::OUT_FLOATS / 4; i += C::THREADS) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int g = 0; g < C::G; ++g) {
+      const float4 q = *reinterpret_cast<const float4*>(wg_sm + g * C::OUT_FLOATS + i * 4);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    float* dst = gw + (size_t)i * 4;                         // [(tap*3 + ci)][co], rows contiguous (ldc == COUT)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// First convolution, forward: out[b][y][x][co] = bias[co] + sum_{ky,kx,ci} X[b][ci][y+ky-1][x+kx-1] * W[co][ci][ky][kx]
+// from the channel-planar observation to the NHWC activation (plain fp32: its consumer is the max-pool).  K = 27 is far
+// too short for a tensor-core tile (the GEMM form needed a materialised 32-wide col matrix: im2col 453 us + GEMM 465 us
+// for 2048 frames); here a CTA of 128 threads stages the 10 x 66 x 3 halo of an 8-row tile and the 432 weights, and a
+// thread computes 8 pixels x 8 channels (64 accumulators, 90 scalar + 54 vector shared-memory loads per 1728 FFMA).
+// Small CTAs (10 KB, ~100 registers): several tiles per SM overlap their staging with each other's arithmetic.
+// ------------------------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(128) conv3x3_fwd_first_kernel(const float* __restrict__ x, long long sb, long long sc,
+                                                                long long sh, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float* __restrict__ out, int B) {
+  constexpr int H = W, R = 8, CIN = 3, COUT = 16, XP = (W + 2) | 1, SEG = 8;
+  static_assert(R * (W / SEG) * 2 == 128, "one (row, segment, channel half) per thread");
+  __shared__ __align__(16) float xs[CIN * (R + 2) * XP];
+  __shared__ __align__(16) float ws[27 * COUT];
+  const int tid = threadIdx.x;
+  const int tiles_per_img = H / R;
+  const int b = blockIdx.x / tiles_per_img, y0 = (blockIdx.x % tiles_per_img) * R;
+  const float* xb = x + (size_t)b * sb;
+  for (int i = tid; i < CIN * (R + 2) * (W + 2); i += 128) {
+    const int hx = i % (W + 2), hr = (i / (W + 2)) % (R + 2), c = i / ((W + 2) * (R + 2));
+    const int gy = y0 - 1 + hr, gx = hx - 1;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    const float* src = ok ? xb + c * sc + gy * sh + gx : x;
+    const int n = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(xs + (c * (R + 2) + hr) * XP + hx)), "l"(src), "r"(n) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < 27 * COUT; i += 128) {              // ws[(ky*3 + kx)*3 + ci][co] <- W[co][ci][ky][kx]
+    const int co = i % COUT, k = i / COUT, ci = k % 3, tap = k / 3;
+    ws[i] = __ldg(w + (co * 3 + ci) * 9 + tap);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int half = tid & 1, u = tid >> 1;                    // a warp: 2 segments x 8 rows (odd pitch: distinct banks)
+  const int r = u % R, x0 = (u / R) * SEG;
+  float acc[SEG][8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + half * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + half * 8 + 4));
+#pragma unroll
+    for (int p = 0; p < SEG; ++p) {
+      acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w;
+      acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
+    }
+  }
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float xr[SEG + 2];
+      const float* xp = xs + (ci * (R + 2) + r + ky) * XP + x0;
+#pragma unroll
+      for (int k = 0; k < SEG + 2; ++k) xr[k] = xp[k];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wp = ws + ((ky * 3 + kx) * 3 + ci) * COUT + half * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int p = 0; p < SEG; ++p)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xr[p + kx], wv[j], acc[p][j]);
+      }
+    }
+  float* op = out + (((size_t)b * H + y0 + r) * W + x0) * COUT + half * 8;
+#pragma unroll
+  for (int p = 0; p < SEG; ++p) {
+    __stcs(reinterpret_cast<float4*>(op + p * COUT), make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]));
+    __stcs(reinterpret_cast<float4*>(op + p * COUT + 4), make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]));
+  }
+}
+
 }  // namespace tpp
 
 extern "C" int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, float* gw, int32_t B, int32_t H, int32_t W,
@@ -194,4 +403,34 @@ extern "C" int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, 
   if (cin == 32 && cout == 32 && W == 16) return tpp::launch_wgrad_cc<32, 32, 16>(x, dy, gw, B, relu, s);
   if (cin == 32 && cout == 32 && W == 8) return tpp::launch_wgrad_cc<32, 32, 8>(x, dy, gw, B, relu, s);
   return TPP_ENOTSUP;
+}
+
+extern "C" int tpp_conv3x3_wgrad_first(const float* x, int64_t sb, int64_t sc, int64_t sh, const float* dy, float* gw,
+                                       int32_t B, int32_t H, int32_t W, int32_t cout, void* stream) {
+  TPP_CHECK_ARG(x && dy && gw && B > 0);
+  if (H != 64 || W != 64 || cout != 16) return TPP_ENOTSUP;
+  using C = tpp::WgFirstCfg<16, 64>;
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tpp::conv3x3_wgrad_first_kernel<16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return TPP_ENOTSUP;
+    attr_set = true;
+  }
+  const int ntiles = B * (H / C::R);
+  const int grid = ntiles < sms ? ntiles : sms;
+  tpp::conv3x3_wgrad_first_kernel<16, 64><<<grid, C::THREADS, C::SMEM, tpp_stream(stream)>>>(x, sb, sc, sh, dy, gw, B);
+  TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_conv3x3_fwd_first(const float* x, int64_t sb, int64_t sc, int64_t sh, const float* w, const float* bias,
+                                     float* out, int32_t B, int32_t H, int32_t W, int32_t cout, void* stream) {
+  TPP_CHECK_ARG(x && w && bias && out && B > 0);
+  if (H != 64 || W != 64 || cout != 16) return TPP_ENOTSUP;
+  tpp::conv3x3_fwd_first_kernel<64><<<B * (64 / 8), 128, 0, tpp_stream(stream)>>>(x, sb, sc, sh, w, bias, out, B);
+  TPP_LAUNCH_STATUS();
 }

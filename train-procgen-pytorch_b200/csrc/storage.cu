@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict
 // Fused normalisation: per-CTA double moments -> global atomics -> grid barrier (cooperative launch: all CTAs are
 // co-resident) -> every CTA normalises ITS advantages straight from shared memory.  adv is written once, never re-read.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int gae_tp(int t, int L, int pad) { return t + (pad ? t / L : 0); }
+// padded index of time step t: t + t / L when the lane stride L is even (magic = 2^32 / L + 1: t / L == umulhi(t, magic)
+// for t < 2^32 / L; an integer division per staged element cost more than the scan itself)
+__device__ __forceinline__ int gae_tp(int t, unsigned magic, int pad) { return t + (pad ? (int)__umulhi((unsigned)t, magic) : 0); }
 
 __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ done,
                                                              const float* __restrict__ value, float* __restrict__ adv,
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int L = (T + 31) >> 5;                             // time steps per lane
   const int pad = (L & 1) ? 0 : 1;                         // lane stride L (+1 if L is even): odd => conflict-free
+  const unsigned magic = (unsigned)(0x100000000ull / (unsigned)L) + 1u;
   const int e0 = blockIdx.x * 32;
   {  // ---- stage (lanes over envs: coalesced rows; transposed shared-memory writes, pitch PT odd) ----
     const int e = e0 + lane;
@@ -217,18 +220,18 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
     if (on) {
       for (int t = warp; t < T; t += 8) {
         const int64_t o = (int64_t)t * ld + e;
-        const int q = lane * PT + gae_tp(t, L, pad);
+        const int q = lane * PT + gae_tp(t, magic, pad);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sb + q)), "l"(rew + o) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + q)), "l"(value + o) : "memory");
       }
       if (warp == 0)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + lane * PT + gae_tp(T, L, pad))),
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + lane * PT + gae_tp(T, magic, pad))),
                      "l"(value + (int64_t)T * ld + e) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll 8
     for (int t = warp; t < T; t += 8)
-      sa[lane * PT + gae_tp(t, L, pad)] = on ? 1.0f - (float)__ldcs(done + (int64_t)t * ld + e) : 0.0f;
+      sa[lane * PT + gae_tp(t, magic, pad)] = on ? 1.0f - (float)__ldcs(done + (int64_t)t * ld + e) : 0.0f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -244,10 +247,11 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
       const float* a = sa + (warp * 4 + j) * PT;
       float p = 1.0f, q = 0.0f;
       for (int t = t_hi - 1; t >= t_lo; --t) {
-        const int i = gae_tp(t, L, pad);
+        const int i = t + pad * lane;                       // (t / L == lane inside this lane's chunk)
+        const int i1 = t + 1 + pad * (t + 1 == t_lo + L ? lane + 1 : lane);
         const float nd = a[i], at = __fmul_rn(gl, nd);
         // delta in the reference's operation order (bit-identical to the sequential kernels' delta)
-        const float dl = __fsub_rn(__fadd_rn(b[i], __fmul_rn(__fmul_rn(gamma, v[gae_tp(t + 1, L, pad)]), nd)), v[i]);
+        const float dl = __fsub_rn(__fadd_rn(b[i], __fmul_rn(__fmul_rn(gamma, v[i1]), nd)), v[i]);
         b[i] = dl;
         q = fmaf(at, q, dl);                                // f_t o f_{t+1..}: x -> at (p x + q) + dl
         p = at * p;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
       const float* a = sa + (warp * 4 + j) * PT;
       const bool on = e0 + warp * 4 + j < N;
       for (int t = t_hi - 1; t >= t_lo; --t) {
-        const int i = gae_tp(t, L, pad);
+        const int i = t + pad * lane;
         A = fmaf(__fmul_rn(gl, a[i]), A, b[i]);
         b[i] = A;
         if (on) { s1 += (double)A; s2 += (double)A * (double)A; }
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
   if (e < N)
     for (int t = warp; t < T; t += 8) {
       const int64_t o = (int64_t)t * ld + e;
-      const int q = lane * PT + gae_tp(t, L, pad);
+      const int q = lane * PT + gae_tp(t, magic, pad);
       const float A = sb[q];
       __stcs(adv + o, normalize ? (A - mean) / denom : A);
       __stcs(ret + o, __fadd_rn(A, sv[q]));
