@@ -355,6 +355,18 @@ int tpp_conv3x3_wgrad_first(const float* x, int64_t sb, int64_t sc, int64_t sh, 
 int tpp_conv3x3_fwd_first(const float* x, int64_t sb, int64_t sc, int64_t sh, const float* w, const float* bias,
                           float* out, int32_t B, int32_t H, int32_t W, int32_t cout, void* stream);
 
+/* Forward / data gradient of a 3x3 / padding-1 convolution with a 16-channel tensor on one side at 32 x 32, on the
+ * fp32 FMA pipe (exact fp32): y[p][co] = sum_{ky,kx,ci} X[p + (ky-1, kx-1)][ci] * wg[co][(ky*3 + kx)*slots + ci],
+ * X = relu(x) when relu_in.  x: NHWC [B][H][W][cin] plain; wg: the engine's GEMM-layout plain weights (forward: Wf,
+ * data gradient: the flipped Wd, with cin / cout swapped by the caller).  Epilogue in the order of tpp_gemm_tc's:
+ * + bias (or NULL), zero where mask <= 0 (or NULL; [rows][cout]), + addend (or NULL), colsum[co] += column sums (or
+ * NULL), then out (plain, or NULL) and the TF32 pair out_hi / out_lo (or NULL) of relu(y) when pair_relu else of y.
+ * Replaces nn.Conv2d forward / autograd data gradient of ResidualBlock / ImpalaBlock (reference
+ * common/model.py:134-208).  (cin, cout, H = W) in {(16,16,32), (16,32,32), (32,16,32)}; else TPP_ENOTSUP.      */
+int tpp_conv3x3_fma(const float* x, int32_t relu_in, const float* wg, int32_t slots, const float* bias,
+                    const float* mask, const float* addend, int32_t pair_relu, float* out, float* out_hi, float* out_lo,
+                    float* colsum, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, void* stream);
+
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC (common/model.py:163,171): y [B][(H+1)/2][(W+1)/2][C],
  * arg = winning tap (first maximum); backward routes dy to the winning input pixel (gather form, no atomics).   */
 int tpp_maxpool3x3s2_fwd(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, float* y, uint8_t* arg,

@@ -56,6 +56,14 @@ def main():
         step()
     torch.cuda.synchronize()
     _lib.call = logged
+    real_try = _lib.try_call
+
+    def logged_try(name, *a):
+        ok = real_try(name, *a)
+        if ok:
+            labels.append(name + (f" cin={a[-3]} cout={a[-2]} W={a[-4]}" if name.startswith("tpp_conv3x3") else ""))
+        return ok
+    _lib.try_call = logged_try
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
         e0.record()

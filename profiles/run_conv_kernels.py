@@ -61,14 +61,23 @@ def time_forms(only=None):
     x_plain = (x[0] + x[1]).contiguous()
     dy_plain = (dy[0] + dy[1]).contiguous()
 
+    wf_plain = (w16[0] + w16[1]).contiguous()
+
     def launch(name, g):
-        if name == "wgrad_fma":     # csrc/conv_cc.cu: the weight gradient on the fp32 FMA pipe (the engine's default)
+        if name == "forward_fma":   # csrc/conv_cc.cu: same epilogue as `forward` (bias, plain + TF32 pair of relu(y))
+            L.call("tpp_conv3x3_fma", L.ptr(x_plain), 1, L.ptr(wf_plain), 16, L.ptr(bias), None, None, 1, L.ptr(out),
+                   L.ptr(oh), L.ptr(ol), None, B, H, W, Cc, Cc, L.stream_ptr())
+        elif name == "dgrad_fma":   # ... and as `dgrad` (ReLU mask, skip-gradient add, bias-gradient column sums)
+            L.call("tpp_conv3x3_fma", L.ptr(dy_plain), 0, L.ptr(wf_plain), 16, None, L.ptr(mask), L.ptr(mask), 0,
+                   L.ptr(out), L.ptr(oh), L.ptr(ol), L.ptr(cs), B, H, W, Cc, Cc, L.stream_ptr())
+        elif name == "wgrad_fma":     # csrc/conv_cc.cu: the weight gradient on the fp32 FMA pipe (the engine's default)
             L.call("tpp_conv3x3_wgrad", L.ptr(x_plain), 1, L.ptr(dy_plain), L.ptr(gw), B, H, W, Cc, Cc, L.stream_ptr())
         else:
             L.call("tpp_gemm_tc", C.byref(g), L.stream_ptr())
 
     res = {}
-    for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg), ("wgrad_fma", None)):
+    for name, g in (("forward", fwd), ("dgrad", dg), ("wgrad", wg), ("forward_fma", None), ("dgrad_fma", None),
+                    ("wgrad_fma", None)):
         if only:
             if name == only:
                 for _ in range(3):

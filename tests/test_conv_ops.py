@@ -435,3 +435,45 @@ def test_first_conv_forward_fma_kernel(B):
            L.stream_ptr())
     ref = F.conv2d(xbuf[:, :3 * H * W].reshape(B, 3, H, W).double(), w.double(), bias.double(), padding=1)
     _close(out, ref.permute(0, 2, 3, 1), 1e-6)
+
+
+@pytest.mark.parametrize("B,cin,cout", [(1, 16, 16), (3, 16, 32), (2, 32, 16), (70, 16, 16)])
+@pytest.mark.parametrize("mode", ["fwd_pair_relu", "fwd_add", "dgrad_mask_add_colsum", "plain_only"])
+def test_conv3x3_fma_forward_and_data_gradient_forms(B, cin, cout, mode):
+    """tpp_conv3x3_fma (csrc/conv_cc.cu) against torch conv2d in float64, with the epilogue variants the engine uses:
+    forward (bias, ReLU'd input, residual add, plain + TF32 pair of relu(y)) and data gradient (ReLU mask, skip-gradient
+    add, bias-gradient column sums).  GEMM-layout weights wg[co][tap*slots + ci], slots = 16 or 32."""
+    L = _lib()
+    torch.manual_seed(B * 31 + cin + len(mode))
+    H = W = 32
+    rows = B * H * W
+    slots = 16 if cin <= 16 else 32
+    x = torch.randn(B, H, W, cin, device="cuda")
+    w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.2
+    wg = torch.zeros(cout, 9 * slots, device="cuda")
+    wg.view(cout, 3, 3, slots)[..., :cin] = w.permute(0, 2, 3, 1)
+    bias = torch.randn(cout, device="cuda") if mode.startswith("fwd") else None
+    relu_in = mode.startswith("fwd")
+    mask = torch.randn(rows, cout, device="cuda") if "mask" in mode else None
+    addend = torch.randn(rows, cout, device="cuda") if "add" in mode else None
+    pair_relu = mode == "fwd_pair_relu"
+    want_pair = mode != "plain_only"
+    colsum = torch.full((cout,), 0.5, device="cuda") if "colsum" in mode else None
+    out = torch.zeros(rows, cout, device="cuda")
+    oh, ol = (torch.zeros_like(out), torch.zeros_like(out)) if want_pair else (None, None)
+    L.call("tpp_conv3x3_fma", L.ptr(x), 1 if relu_in else 0, L.ptr(wg), slots, L.ptr(bias), L.ptr(mask), L.ptr(addend),
+           1 if pair_relu else 0, L.ptr(out), L.ptr(oh), L.ptr(ol), L.ptr(colsum), B, H, W, cin, cout, L.stream_ptr())
+    xin = (x.clamp_min(0) if relu_in else x).double().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, w.double(), bias.double() if bias is not None else None, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(rows, cout)
+    if mask is not None:
+        ref = ref * (mask > 0)
+    if addend is not None:
+        ref = ref + addend.double()
+    _close(out, ref, 2e-6)
+    if want_pair:
+        y = out.clamp_min(0) if pair_relu else out
+        assert torch.equal(oh + ol, y)                                     # the pair is an exact split of the fp32 value
+        assert torch.equal(oh, ((y.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
+    if colsum is not None:
+        _close(colsum - 0.5, ref.sum(0), 1e-5)

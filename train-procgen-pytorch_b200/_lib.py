@@ -123,6 +123,7 @@ SIGNATURES = {
     "tpp_conv3x3_wgrad": [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "tpp_conv3x3_wgrad_first": [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "tpp_conv3x3_fwd_first": [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "tpp_conv3x3_fma": [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp],
     "tpp_maxpool3x3s2_fwd": [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "tpp_maxpool3x3s2_bwd": [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "tpp_head_backward": [_vp, _i32, _vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp],
@@ -174,6 +175,19 @@ def call(name, *args):
         msg = lib.tpp_error_string(rc)
         raise TppError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")
     return rc
+
+
+def try_call(name, *args):
+    """``call`` for entry points that are built for a fixed set of shapes: False when the library answers TPP_ENOTSUP
+    (the caller then takes its general path), True on success, TppError on anything else."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc == ENOTSUP:
+        return False
+    if rc != 0:
+        msg = lib.tpp_error_string(rc)
+        raise TppError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")
+    return True
 
 
 def ptr(t):

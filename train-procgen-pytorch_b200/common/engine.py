@@ -13,6 +13,8 @@ Replaces: ``policy.embedder.forward_with_attn_indices`` + ``policy.hidden_to_out
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .. import _lib
@@ -545,7 +547,11 @@ class ImpalaEngineTC:
         self._ws = {}
         # weight gradients of the 16 / 32-channel convolutions on the fp32 FMA pipe (tpp_conv3x3_wgrad: exact fp32, each
         # operand byte staged once; 3-4x the tensor-core form at these channel counts); False = tcgen05 im2col form
-        self.wgrad_cc = True
+        self.wgrad_cc = os.environ.get("TPP_WGRAD_FMA", "1") != "0"
+        # forward / data gradient of the convolutions with a 16-channel side at 32 x 32 on the FMA pipe too (tpp_conv3x3_fma)
+        # -- opt-in (TPP_FMA_FWD=1): measured 303 / 336 us against 335 / 349 us of the tensor-core tiles at 16 -> 16 channels,
+        # but slower at 16 <-> 32, and no gain over a whole forward + backward (11.19 vs 11.03 ms per 2048 frames)
+        self.fma_fwd = os.environ.get("TPP_FMA_FWD", "0") == "1"
         emb = policy.embedder
         self._names = {id(p): n for n, p in policy.named_parameters()}
         C, H, W = self.obs_shape
@@ -684,7 +690,7 @@ class ImpalaEngineTC:
         return (H * W * C, W * C, C, 1)
 
     def _conv_fwd(self, ws, ci, src, B, H, W, out=None, addend=None, relu_out=False, pair_relu=False, pair=None,
-                  strides=None):
+                  strides=None, plain_in=None, relu_in=True):
         """src: TF32 pair of the (already ReLU'd) NHWC input for an implicit convolution, or -- first convolution --
         the plain source tensor with its element strides.  out: trio (plain + pair written) or plain tensor."""
         c = self.convs[ci]
@@ -696,6 +702,15 @@ class ImpalaEngineTC:
             pair = (out["hi"], out["lo"])
         kw = dict(flags=flags, bias=self._p(c["b_off"]), out=plain, out_pair=pair, ldc=c["cout"], addend=addend,
                   ld_add=c["cout"])
+        if c["implicit"] and plain_in is not None and self.fma_fwd and not relu_out:
+            # a 16-channel tensor on either side at 32 x 32: exact-fp32 FMA kernel (tpp_conv3x3_fma); other shapes answer
+            # ENOTSUP and take the tensor-core tile below
+            if _lib.try_call("tpp_conv3x3_fma", _lib.ptr(plain_in), 1 if relu_in else 0, _lib.ptr(c["wf_plain"]), c["sf"],
+                             self._p(c["b_off"]), None, _lib.ptr(addend), 1 if pair_relu else 0, _lib.ptr(plain),
+                             _lib.ptr(pair[0]) if pair else None, _lib.ptr(pair[1]) if pair else None, None, B, H, W,
+                             c["cin"], c["cout"], _lib.stream_ptr()):
+                self.n_launches += 1
+                return
         if c["implicit"]:
             self._tc(src, 0, c["wf"], 9 * c["sf"], rows, c["cout"], 9 * c["sf"], conv=(B, H, W, c["cin"]), **kw)
         elif self._first_cc(c, H, W, strides) and flags == EPI_BIAS and pair is None:
@@ -720,19 +735,21 @@ class ImpalaEngineTC:
                 self._conv_fwd(ws, b["conv"], x, M, H, W, out=wb["a"], strides=(x.stride(0), W0, 1, H0 * W0))
             else:
                 prev = ws.blk[k - 1]["r2"]
-                self._conv_fwd(ws, b["conv"], (prev["hi"], prev["lo"]), M, H, W, out=wb["a"])
+                self._conv_fwd(ws, b["conv"], (prev["hi"], prev["lo"]), M, H, W, out=wb["a"], plain_in=prev["plain"],
+                               relu_in=False)
             p, c1, r1, c2, r2 = wb["p"], wb["c1"], wb["r1"], wb["c2"], wb["r2"]
             _lib.call("tpp_maxpool3x3s2_fwd", _lib.ptr(wb["a"]), M, H, W, cout, _lib.ptr(p["plain"]), _lib.ptr(wb["arg"]),
                       _lib.ptr(p["hi"]), _lib.ptr(p["lo"]), _lib.stream_ptr())
             self.n_launches += 1
             (a1, b1), (a2, b2) = b["res"]
-            self._conv_fwd(ws, a1, (p["hi"], p["lo"]), M, Ho, Wo, out=c1, pair_relu=True)
-            self._conv_fwd(ws, b1, (c1["hi"], c1["lo"]), M, Ho, Wo, out=r1, addend=p["plain"], pair_relu=True)
-            self._conv_fwd(ws, a2, (r1["hi"], r1["lo"]), M, Ho, Wo, out=c2, pair_relu=True)
+            self._conv_fwd(ws, a1, (p["hi"], p["lo"]), M, Ho, Wo, out=c1, pair_relu=True, plain_in=p["plain"])
+            self._conv_fwd(ws, b1, (c1["hi"], c1["lo"]), M, Ho, Wo, out=r1, addend=p["plain"], pair_relu=True,
+                           plain_in=c1["plain"])
+            self._conv_fwd(ws, a2, (r1["hi"], r1["lo"]), M, Ho, Wo, out=c2, pair_relu=True, plain_in=r1["plain"])
             if k == nb - 1:   # trailing ReLU + flatten: written directly as the fc layer's TF32 operand
                 self._conv_fwd(ws, b2, (c2["hi"], c2["lo"]), M, Ho, Wo, pair=ws.h, addend=r1["plain"], relu_out=True)
             else:             # the next block's convolution reads r2 without a ReLU
-                self._conv_fwd(ws, b2, (c2["hi"], c2["lo"]), M, Ho, Wo, out=r2, addend=r1["plain"])
+                self._conv_fwd(ws, b2, (c2["hi"], c2["lo"]), M, Ho, Wo, out=r2, addend=r1["plain"], plain_in=c2["plain"])
         if self.enc > 512 and self.precision == 3:
             # long contraction: chunks of 256 accumulated with IEEE adds (the tensor core truncates when it adds into
             # its fp32 accumulator), then bias + ReLU + TF32 split
@@ -773,13 +790,10 @@ class ImpalaEngineTC:
         if c["implicit"] and plain is not None and self.wgrad_cc:
             # narrow layers: exact-fp32 FMA kernel with the halo staged once per tile (csrc/conv_cc.cu); shapes it was
             # not built for answer ENOTSUP and take the tensor-core form below
-            rc = _lib.load().tpp_conv3x3_wgrad(_lib.ptr(plain), 1 if relu else 0, _lib.ptr(dy["plain"]), _lib.ptr(c["gw"]),
-                                               B, H, W, c["cin"], c["cout"], _lib.stream_ptr())
-            if rc == 0:
+            if _lib.try_call("tpp_conv3x3_wgrad", _lib.ptr(plain), 1 if relu else 0, _lib.ptr(dy["plain"]),
+                             _lib.ptr(c["gw"]), B, H, W, c["cin"], c["cout"], _lib.stream_ptr()):
                 self.n_launches += 1
                 return
-            if rc != _lib.ENOTSUP:
-                raise _lib.TppError(f"tpp_conv3x3_wgrad failed with status {rc}")
         if c["implicit"]:
             self._tc(src, 0, (dy["hi"], dy["lo"]), c["cout"], self.KI, c["cout"], rows, a_mn=1, b_mn=1, flags=EPI_ACCUM,
                      out=c["gw"], ldc=c["cout"], block_n=32, conv=(B, H, W, c["cin"]), conv_wgrad=1,
@@ -812,6 +826,13 @@ class ImpalaEngineTC:
         c = self.convs[ci]
         rows = B * H * W
         flags = (EPI_MASK if mask is not None else 0) | (EPI_ADD if addend is not None else 0)
+        if self.fma_fwd:
+            if _lib.try_call("tpp_conv3x3_fma", _lib.ptr(dy["plain"]), 0, _lib.ptr(c["wd_plain"]), c["sd"], None,
+                             _lib.ptr(mask), _lib.ptr(addend), 0, _lib.ptr(out["plain"]), _lib.ptr(out["hi"]),
+                             _lib.ptr(out["lo"]), self._g(colsum_off) if colsum_off is not None else None, B, H, W,
+                             c["cout"], c["cin"], _lib.stream_ptr()):
+                self.n_launches += 1
+                return
         self._tc((dy["hi"], dy["lo"]), 0, c["wd"], 9 * c["sd"], rows, c["cin"], 9 * c["sd"], conv=(B, H, W, c["cout"]),
                  flags=flags, mask=mask, ld_mask=c["cin"], out=out["plain"], out_pair=(out["hi"], out["lo"]),
                  ldc=c["cin"], addend=addend, ld_add=c["cin"],

@@ -274,18 +274,16 @@ class Storage:
         self.moments4.zero_()
         if self.gae_mode == "warp_scan":
             fuse = 1 if (normalize_adv and self.world_size == 1) else 0
-            rc = _lib.load().tpp_gae_scan(_lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value),
-                                          _lib.ptr(self.adv), _lib.ptr(self.ret), _lib.ptr(self.moments4), T, N, self.ld,
-                                          float(gamma), float(lmbda), fuse, s)
-            if rc == 0:
+            if _lib.try_call("tpp_gae_scan", _lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value),
+                             _lib.ptr(self.adv), _lib.ptr(self.ret), _lib.ptr(self.moments4), T, N, self.ld, float(gamma),
+                             float(lmbda), fuse, s):
                 self.n_launches += 1
                 if normalize_adv and not fuse:
                     parallel.allreduce_moments_(self.moments, self.process_group)
                     _lib.call("tpp_adv_normalize", _lib.ptr(self.adv), _lib.ptr(self.moments), T, N, self.ld, s)
                     self.n_launches += 1
                 return
-            if rc != _lib.ENOTSUP:      # (ENOTSUP: T or N outside the fused kernel's range -> the exact kernels below)
-                raise _lib.TppError(f"tpp_gae_scan failed with status {rc}")
+            # (ENOTSUP: T or N outside the fused kernel's range -> the exact kernels below)
         elif self.gae_mode != "exact":
             raise ValueError(f"gae_mode must be 'exact' or 'warp_scan', not {self.gae_mode!r}")
         _lib.call("tpp_gae", _lib.ptr(self.rew), _lib.ptr(self.done_u8), _lib.ptr(self.value), _lib.ptr(self.adv),

@@ -118,24 +118,28 @@ __global__ void __launch_bounds__(256, 1) conv3x3_wgrad_cc_kernel(const float* _
       };
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) { col[0][ky] = ldx(0, ky); col[1][ky] = ldx(1, ky); }
+      // one pixel: the new halo column replaces the oldest of the three register columns (k = px mod 3 is a compile-time
+      // constant: the segment is fully unrolled.  Unrolling by the rotation period only -- to keep the 2.5 K-instruction
+      // body inside the instruction cache, ncu shows 21 % "no instruction" stalls -- measured slower: 285 vs 269 us)
+      auto pixel = [&](int px, int k) {
 #pragma unroll
-      for (int px = 0; px < C::SEG; ++px) {
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) col[(px + 2) % 3][ky] = ldx(px + 2, ky);
+        for (int ky = 0; ky < 3; ++ky) col[(k + 2) % 3][ky] = ldx(px + 2, ky);
         const float4 d4 = *reinterpret_cast<const float4*>(dp + px * COUT);
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
-            const float4 xv = col[(px + kx) % 3][ky];
+            const float4 xv = col[(k + kx) % 3][ky];
             const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
               for (int j = 0; j < 4; ++j) acc[ky * 3 + kx][i][j] = fmaf(xs[i], d[j], acc[ky * 3 + kx][i][j]);
           }
-      }
+      };
+#pragma unroll
+      for (int px = 0; px < C::SEG; ++px) pixel(px, px % 3);
     }
     __syncthreads();                                         // this buffer is refilled two tiles from now
   }
@@ -275,12 +279,11 @@ __global__ void __launch_bounds__(256, 1) conv3x3_wgrad_first_kernel(const float
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
           for (int c = 0; c < CIN; ++c) col[k][ky][c] = xp[(c * (R + 2) + ky) * C::XP + k];
-#pragma unroll
-      for (int px = 0; px < C::SEG; ++px) {
+      auto pixel = [&](int px, int k) {
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int c = 0; c < CIN; ++c) col[(px + 2) % 3][ky][c] = xp[(c * (R + 2) + ky) * C::XP + px + 2];
+          for (int c = 0; c < CIN; ++c) col[(k + 2) % 3][ky][c] = xp[(c * (R + 2) + ky) * C::XP + px + 2];
         const float4 d4 = *reinterpret_cast<const float4*>(dp + px * COUT);
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -291,8 +294,10 @@ __global__ void __launch_bounds__(256, 1) conv3x3_wgrad_first_kernel(const float
             for (int c = 0; c < CIN; ++c)
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                acc[ky * 3 + kx][c][j] = fmaf(col[(px + kx) % 3][ky][c], d[j], acc[ky * 3 + kx][c][j]);
-      }
+                acc[ky * 3 + kx][c][j] = fmaf(col[(k + kx) % 3][ky][c], d[j], acc[ky * 3 + kx][c][j]);
+      };
+#pragma unroll
+      for (int px = 0; px < C::SEG; ++px) pixel(px, px % 3);
     }
     __syncthreads();
   }
@@ -391,6 +396,176 @@ __global__ void __launch_bounds__(128) conv3x3_fwd_first_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Forward / data gradient of the 3x3 convolutions that touch a 16-channel tensor at 32 x 32 (IMPALA block 1 and the
+// first convolution of block 2), on the fp32 FMA pipe:
+//   y[b][y][x][co] = sum_{ky,kx,ci} X[b][y+ky-1][x+kx-1][ci] * Wg[co][(ky*3 + kx)*S + ci]      (S = channel slots per tap)
+// with the epilogue of the tensor-core tiles (bias -> ReLU mask -> residual add -> column sums -> plain / TF32 pair).
+// The data gradient is the same contraction on dY with the flipped weights the engine already keeps (Wd).
+// Why: with 16 output (or input) channels a tcgen05 tile uses an eighth of an MMA's columns, needs three TF32 passes for
+// fp32 parity and re-gathers its operand nine times from L2 (measured 335 - 350 us for 4.8 GFMA); the FMA pipe does the
+// same arithmetic exactly, once, from a halo staged once.
+//   * CTA = R rows x 32 pixels of one image; the halo is staged CHANNEL-CHUNK-PLANAR ([ci / 4][row][pixel] float4s, odd
+//     row pitch): lanes of a warp sit on different rows of the same pixel column, i.e. 8 distinct 16-byte bank groups;
+//   * a thread computes 8 pixels x 8 output channels (64 accumulators): per (ky, 4 input channels) 10 LDS.128 of X and
+//     24 broadcast LDS.128 of weights for 768 FFMA.
+// ------------------------------------------------------------------------------------------------------------------
+template <int CI, int CO, int W, int R>
+struct FmaCfg {
+  static constexpr int SEG = 8, CO_Q = CO / 8, UNITS = R * (W / SEG), THREADS = UNITS * CO_Q;
+  static constexpr int XP = (W + 2) | 1;                   // halo row pitch in pixels (odd)
+  static constexpr int X_FLOATS = (CI / 4) * (R + 2) * XP * 4;
+  static constexpr int W_FLOATS = 9 * CI * CO;
+  static constexpr size_t SMEM = sizeof(float) * (X_FLOATS + W_FLOATS);
+  static_assert(THREADS % 32 == 0 && THREADS <= 256, "CTA shape");
+};
+
+struct FmaEpi {
+  const float* bias; const float* mask; const float* addend;
+  float* out; float* out_hi; float* out_lo; float* colsum;
+  int relu_in, pair_relu;
+};
+
+template <int CI, int CO, int W, int R>
+__global__ void __launch_bounds__(FmaCfg<CI, CO, W, R>::THREADS) conv3x3_fma_kernel(const float* __restrict__ x,
+                                                                                 const float* __restrict__ wg, int slots,
+                                                                                 FmaEpi e, int B) {
+  using C = FmaCfg<CI, CO, W, R>;
+  constexpr int H = W, SEG = C::SEG, CI4 = CI / 4;
+  extern __shared__ __align__(16) float fm_sm[];
+  __shared__ float cs_sh[C::THREADS / 32][CO];
+  float* xs = fm_sm;                                         // [CI4][R + 2][XP] float4
+  float* ws = fm_sm + C::X_FLOATS;                           // [(tap * CI + ci)][CO]
+  const int tid = threadIdx.x;
+  const int tiles_per_img = H / R;
+  const int b = blockIdx.x / tiles_per_img, y0 = (blockIdx.x % tiles_per_img) * R;
+  const float* xb = x + (size_t)b * H * W * CI;
+  for (int i = tid; i < CI4 * (R + 2) * (W + 2); i += C::THREADS) {
+    const int c = i % CI4, hx = (i / CI4) % (W + 2), hr = i / (CI4 * (W + 2));
+    const int gy = y0 - 1 + hr, gx = hx - 1;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    cp_async16_zfill(xs + ((c * (R + 2) + hr) * C::XP + hx) * 4, ok ? xb + ((size_t)gy * W + gx) * CI + c * 4 : x, ok);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < C::W_FLOATS; i += C::THREADS) {      // ws[tap][ci][co] <- Wg[co][tap * slots + ci]
+    const int ci = i % CI, tap = (i / CI) % 9, co = i / (CI * 9);
+    ws[(tap * CI + ci) * CO + co] = __ldg(wg + (size_t)co * 9 * slots + tap * slots + ci);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const int q = tid % C::CO_Q, u = tid / C::CO_Q;
+  const int r = u % R, x0 = (u / R) * SEG;                   // a warp's units: rows of one pixel column (odd pitch apart)
+  float acc[SEG][8];
+#pragma unroll
+  for (int p = 0; p < SEG; ++p)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.0f;
+#pragma unroll 1                                             // (one (ky, 4 channels) body = ~800 instructions: stays in the
+  for (int ky = 0; ky < 3; ++ky)                             // instruction cache)
+#pragma unroll 1
+    for (int c = 0; c < CI4; ++c) {
+      float4 xr[SEG + 2];
+      const float* xp = xs + ((c * (R + 2) + r + ky) * C::XP + x0) * 4;
+#pragma unroll
+      for (int k = 0; k < SEG + 2; ++k) {
+        float4 v = *reinterpret_cast<const float4*>(xp + k * 4);
+        if (e.relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        xr[k] = v;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float* wp = ws + ((ky * 3 + kx) * CI + c * 4 + i) * CO + q * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int p = 0; p < SEG; ++p) {
+            const float4 xq = xr[p + kx];
+            const float xv = i == 0 ? xq.x : (i == 1 ? xq.y : (i == 2 ? xq.z : xq.w));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(xv, wv[j], acc[p][j]);
+          }
+        }
+    }
+  // ---- epilogue: bias -> mask -> residual -> column sums -> plain / pair (the order of csrc/gemm_tc.cu) ----
+  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = __ldg(e.bias + q * 8 + j);
+  }
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t row0 = ((size_t)b * H + y0 + r) * W + x0;
+#pragma unroll
+  for (int p = 0; p < SEG; ++p) {
+    const size_t off = (row0 + p) * CO + q * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = acc[p][j] + bv[j];
+    if (e.mask) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(e.mask + off)), m1 = __ldg(reinterpret_cast<const float4*>(e.mask + off + 4));
+      const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = mv[j] > 0.0f ? v[j] : 0.0f;
+    }
+    if (e.addend) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(e.addend + off)), a1 = __ldg(reinterpret_cast<const float4*>(e.addend + off + 4));
+      v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cs[j] += v[j];
+    if (e.out) {
+      *reinterpret_cast<float4*>(e.out + off) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(e.out + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (e.out_hi) {
+      float h[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = e.pair_relu ? fmaxf(v[j], 0.0f) : v[j];
+        h[j] = __uint_as_float((__float_as_uint(y) + 0x1000u) & 0xFFFFE000u);      // tf32_round of csrc/gemm_tc.cu
+        l[j] = y - h[j];
+      }
+      *reinterpret_cast<float4*>(e.out_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(e.out_hi + off + 4) = make_float4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<float4*>(e.out_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4*>(e.out_lo + off + 4) = make_float4(l[4], l[5], l[6], l[7]);
+    }
+  }
+  if (e.colsum) {                                            // lanes with the same channel octet: tid = q (mod CO_Q)
+#pragma unroll
+    for (int o = C::CO_Q; o < 32; o <<= 1)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane < C::CO_Q) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs_sh[warp][lane * 8 + j] = cs[j];
+    }
+    __syncthreads();
+    if (tid < CO) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w2 = 0; w2 < C::THREADS / 32; ++w2) t += cs_sh[w2][tid];
+      atomicAdd(e.colsum + tid, t);
+    }
+  }
+}
+
+template <int CI, int CO, int W, int R>
+static int launch_fma(const float* x, const float* wg, int slots, const FmaEpi& e, int B, cudaStream_t s) {
+  using C = FmaCfg<CI, CO, W, R>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(conv3x3_fma_kernel<CI, CO, W, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C::SMEM);
+    if (err != cudaSuccess) return (int)err;
+    attr_set = true;
+  }
+  conv3x3_fma_kernel<CI, CO, W, R><<<B * (W / R), C::THREADS, C::SMEM, s>>>(x, wg, slots, e, B);
+  TPP_LAUNCH_STATUS();
+}
+
 }  // namespace tpp
 
 extern "C" int tpp_conv3x3_wgrad(const float* x, int32_t relu, const float* dy, float* gw, int32_t B, int32_t H, int32_t W,
@@ -433,4 +608,18 @@ extern "C" int tpp_conv3x3_fwd_first(const float* x, int64_t sb, int64_t sc, int
   if (H != 64 || W != 64 || cout != 16) return TPP_ENOTSUP;
   tpp::conv3x3_fwd_first_kernel<64><<<B * (64 / 8), 128, 0, tpp_stream(stream)>>>(x, sb, sc, sh, w, bias, out, B);
   TPP_LAUNCH_STATUS();
+}
+
+extern "C" int tpp_conv3x3_fma(const float* x, int32_t relu_in, const float* wg, int32_t slots, const float* bias,
+                               const float* mask, const float* addend, int32_t pair_relu, float* out, float* out_hi,
+                               float* out_lo, float* colsum, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout,
+                               void* stream) {
+  TPP_CHECK_ARG(x && wg && B > 0 && (out || out_hi) && (!out_hi == !out_lo) && slots >= cin);
+  if (H != W) return TPP_ENOTSUP;
+  tpp::FmaEpi e{bias, mask, addend, out, out_hi, out_lo, colsum, relu_in, pair_relu};
+  cudaStream_t s = tpp_stream(stream);
+  if (cin == 16 && cout == 16 && W == 32) return tpp::launch_fma<16, 16, 32, 16>(x, wg, slots, e, B, s);
+  if (cin == 16 && cout == 32 && W == 32) return tpp::launch_fma<16, 32, 32, 8>(x, wg, slots, e, B, s);
+  if (cin == 32 && cout == 16 && W == 32) return tpp::launch_fma<32, 16, 32, 16>(x, wg, slots, e, B, s);
+  return TPP_ENOTSUP;
 }
