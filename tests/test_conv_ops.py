@@ -302,7 +302,8 @@ def test_tma_im2col_conventions(B, H, W, C, cpp, base, tap):
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout", [(4, 16, 16, 16, 16), (2, 32, 32, 16, 32), (3, 8, 8, 32, 32), (5, 7, 7, 32, 32),
-                                            (2, 14, 14, 4, 16), (1, 5, 3, 16, 16), (3, 64, 64, 4, 16)])
+                                            (2, 14, 14, 4, 16), (1, 5, 3, 16, 16), (3, 64, 64, 4, 16),
+                                            (5, 32, 32, 32, 16), (40, 16, 16, 32, 32), (300, 32, 32, 16, 16)])
 @pytest.mark.parametrize("precision,slots", [(3, 32), (1, 32), (3, 16)])
 def test_implicit_conv3x3_matches_conv2d(B, H, W, cin, cout, precision, slots):
     """tpp_gemm_tc in convolution mode (A tiles gathered by TMA im2col from the NHWC TF32 pair) against F.conv2d:
