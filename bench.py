@@ -709,7 +709,9 @@ def run_procgen(args, emit=True, name="procgen", with_roofline=True):
                           "contraction is kept for other shapes",
             "gathered_operand_GBps": round(18 * pixels * rck.SHAPE["C"] * 4 / forms["forward"] / 1e3, 1),
             "note": f"peak = dense bf16 ({pk['source']}); algorithmic FLOPs 2*pixels*9*Cin*Cout; the tile is bound by "
-                    "the L2->shared-memory gather of 9 taps x (hi, lo), see profiles/ncu_conv_r01.md"}
+                    "the fixed cost of its 54 MMAs of 128 x 16 x 8 per tile (an MMA with N = 16 takes as long as a wide one); "
+                    "staging the input rows once per filter column -- a third of the L2 gather -- left the time "
+                    "unchanged (profiles/conv_halo_experiment_r02.patch: 345 vs 340 us)"}
     cpu = cpu_baseline(name, budget_s=15.0) if not args.no_cpu_baseline else None
     n_e, n_s = CPU_SAMPLE[name]
     line = {
