@@ -197,6 +197,65 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restric
   }
 }
 
+// The same for even H, W: one thread per 2 x 2 block of input pixels and 4 channels.  The block (by, bx) is touched by the
+// four windows (by .. by + 1) x (bx .. bx + 1) only, so their (arg, dy) vectors are loaded once -- 4 loads for 4 output
+// pixels instead of 1 + 2 + 2 + 4 -- and four times fewer threads walk the index arithmetic.  Sums run in the per-pixel
+// kernel's window order (bit-identical results).
+__global__ void __launch_bounds__(256) maxpool_bwd_quad_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                                               int B, int H, int W, int C, int Ho, int Wo,
+                                                               float* __restrict__ dx, float* __restrict__ dx_hi,
+                                                               float* __restrict__ dx_lo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = C >> 2, Wb = W >> 1, Hb = H >> 1;
+  const long long total = (long long)B * Hb * Wb * cq;
+  if (t >= total) return;
+  const int c = (int)(t % cq) * 4;
+  const int bx = (int)((t / cq) % Wb), by = (int)((t / ((long long)cq * Wb)) % Hb);
+  const long long b = t / ((long long)cq * Wb * Hb);
+  uchar4 a[2][2];
+  float4 g[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int oy = by + i, ox = bx + j;
+      a[i][j] = make_uchar4(255, 255, 255, 255);
+      g[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oy < Ho && ox < Wo) {
+        const long long o = ((b * Ho + oy) * Wo + ox) * C + c;
+        a[i][j] = *reinterpret_cast<const uchar4*>(arg + o);
+        g[i][j] = __ldg(reinterpret_cast<const float4*>(dy + o));
+      }
+    }
+  // input pixel (2 by + py, 2 bx + px) lies in window (by + i, bx + j) at tap ((py + 1 - 2 i) * 3 + (px + 1 - 2 j)), for the
+  // (i, j) with that tap inside 0 .. 2
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i <= py; ++i)
+#pragma unroll
+        for (int j = 0; j <= px; ++j) {
+          const int want = (py + 1 - 2 * i) * 3 + (px + 1 - 2 * j);
+          if (a[i][j].x == want) s[0] += g[i][j].x;
+          if (a[i][j].y == want) s[1] += g[i][j].y;
+          if (a[i][j].z == want) s[2] += g[i][j].z;
+          if (a[i][j].w == want) s[3] += g[i][j].w;
+        }
+      const long long o = ((b * H + 2 * by + py) * W + 2 * bx + px) * C + c;
+      *reinterpret_cast<float4*>(dx + o) = make_float4(s[0], s[1], s[2], s[3]);
+      if (dx_hi) {
+        float h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = cv_tf32(s[k]);
+        *reinterpret_cast<float4*>(dx_hi + o) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dx_lo + o) = make_float4(s[0] - h[0], s[1] - h[1], s[2] - h[2], s[3] - h[3]);
+      }
+    }
+}
+
 // Column sums of a narrow row-major matrix [M][C], C in {4, 8, 16, 32, 64} (bias gradient of a convolution from its
 // NHWC output gradient): the matrix is read as one flat float4 stream, a thread's 4 columns never change.
 __global__ void __launch_bounds__(256) colsum_narrow_kernel(const float* __restrict__ x, long long total4, int C,
@@ -353,6 +412,12 @@ extern "C" int tpp_maxpool3x3s2_bwd(const float* dy, const uint8_t* arg, int32_t
   TPP_CHECK_ARG(dy && arg && dx && B > 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0);
   TPP_CHECK_ARG((dx_hi == nullptr) == (dx_lo == nullptr));
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  if (((H | W) & 1) == 0) {       // even sizes (every IMPALA stage): one thread per 2 x 2 input block
+    const long long quads = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    tpp::maxpool_bwd_quad_kernel<<<tpp_ceil_div(quads, 256), 256, 0, tpp_stream(stream)>>>(dy, arg, B, H, W, C, Ho, Wo, dx,
+                                                                                           dx_hi, dx_lo);
+    TPP_LAUNCH_STATUS();
+  }
   const long long total = (long long)B * H * W * (C / 4);
   tpp::maxpool_bwd_kernel<<<tpp_ceil_div(total, 256), 256, 0, tpp_stream(stream)>>>(dy, arg, B, H, W, C, Ho, Wo, dx,
                                                                                     dx_hi, dx_lo);
