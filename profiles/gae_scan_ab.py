@@ -1,7 +1,7 @@
 """GAE at the PPO configs' sizes: the exact kernels (tpp_gae + tpp_adv_normalize) against the fused warp-level segmented
 scan (tpp_gae_scan), graph-timed like bench.py's kernel_rooflines (the moments memset is part of every variant).
 
-    python profiles/gae_scan_ab.py            # TPP_GAE_COOP=1 for the cooperative-launch form of the grid barrier
+    python profiles/gae_scan_ab.py            # TPP_GAE_COOP=0: plain launch instead of the cooperative one (the default)
 """
 import os
 import sys
@@ -15,7 +15,7 @@ from tpp_b200.common.storage import Storage  # noqa: E402
 
 
 def main():
-    print(f"TPP_GAE_COOP={os.environ.get('TPP_GAE_COOP', '0')}")
+    print(f"TPP_GAE_COOP={os.environ.get('TPP_GAE_COOP', '1')}")
     print("| T | n_envs | exact gae + normalize | exact gae only | scan, raw adv (no barrier) | scan fused (barrier + normalize) |")
     print("|---:|---:|---:|---:|---:|---:|")
     for T, N in ((256, 256), (256, 1024), (256, 4096), (128, 4096), (64, 4096)):
