@@ -142,3 +142,18 @@ def test_accumulation_group_size_policy():
     assert agent._group_size(16, 128, 8192, mlp) == 1
     agent.fuse_accum, agent.x_entropy_coef = "auto", 0.05
     assert agent._group_size(16, 128, 8192, mlp) == 1             # cross-batch entropy keeps the ungrouped path
+
+
+def test_shape_specialised_entries_refuse_other_shapes_without_a_gpu():
+    """The FMA-pipe convolution entries check their shape table before anything touches the device: unsupported
+    shapes answer TPP_ENOTSUP (``_lib.try_call`` -> False, the caller takes the tensor-core form), bad arguments
+    TPP_EINVAL (TppError).  Dummy non-null pointers: no launch happens on either path."""
+    from tpp_b200 import _lib
+    one = ctypes.c_void_p(16)
+    assert _lib.try_call("tpp_conv3x3_wgrad", one, 0, one, one, 2, 14, 14, 16, 16, None) is False
+    assert _lib.try_call("tpp_conv3x3_fma", one, 0, one, 16, None, None, None, 0, one, None, None, None, 2, 14, 14, 16,
+                         16, None) is False
+    assert _lib.try_call("tpp_conv3x3_wgrad_first", one, 1, 1, 1, one, one, 2, 32, 32, 16, None) is False
+    assert _lib.try_call("tpp_conv3x3_fwd_first", one, 1, 1, 1, one, one, one, 2, 32, 32, 16, None) is False
+    with pytest.raises(_lib.TppError):
+        _lib.try_call("tpp_conv3x3_wgrad", None, 0, one, one, 2, 32, 32, 16, 16, None)

@@ -114,6 +114,31 @@ __global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict
   const bool on = e < N;
   // staging: cp.async moves rew / value rows global -> shared without passing through registers, so all 2 T row copies
   // of the CTA are in flight together (a load -> store loop keeps only a few rows per warp in flight: ~1 us per batch)
+  // 16-byte copies: a lane moves four envs of a row, a warp instruction four rows (the rows are padded to ld, a multiple of
+  // 32 floats, so the CTA's 32 columns are always readable and 16-byte aligned).  With 4-byte copies the kernel's time grew
+  // by 32 ns per time step -- the LSU instruction count of the staging, not the recurrence, was what bounded it.
+  const bool vec = ((ld & 3) == 0) && (int64_t)gridDim.x * 32 <= ld &&
+                   (((reinterpret_cast<uintptr_t>(rew) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(adv) |
+                      reinterpret_cast<uintptr_t>(ret)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(done) & 3) == 0);
+  if (vec) {
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;          // row within the group of four, first env of this lane's chunk
+    const int64_t col = (int64_t)blockIdx.x * 32 + c4;
+    for (int t = warp * 4 + sub; t <= T; t += 32) {
+      const int64_t o = (int64_t)t * ld + col;
+      if (t < T)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdl + t * 32 + c4)),
+                     "l"(rew + o) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sv + t * 32 + c4)),
+                   "l"(value + o) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int t = warp * 4 + sub; t < T; t += 32) {
+      const uchar4 d4 = *reinterpret_cast<const uchar4*>(done + (int64_t)t * ld + col);
+      *reinterpret_cast<float4*>(snd + t * 32 + c4) =
+          make_float4(1.0f - (float)d4.x, 1.0f - (float)d4.y, 1.0f - (float)d4.z, 1.0f - (float)d4.w);
+    }
+  } else {
   if (on) {
     for (int t = warp; t < T; t += 8) {
       const int64_t o = (int64_t)t * ld + e;
@@ -130,6 +155,7 @@ __global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict
 #pragma unroll 8
   for (int t = warp; t < T; t += 8)
     snd[t * 32 + lane] = on ? 1.0f - (float)__ldcs(done + (int64_t)t * ld + e) : 0.0f;
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (on)
@@ -163,7 +189,29 @@ __global__ void __launch_bounds__(256) gae_staged_kernel(const float* __restrict
   }
   __syncthreads();
   double s1 = 0.0, s2 = 0.0;
-  if (on)
+  if (vec) {
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const int64_t col = (int64_t)blockIdx.x * 32 + c4;
+    const int nv = (int)min((int64_t)4, (int64_t)N - col);    // valid envs of this lane's chunk (<= 0: none)
+    for (int t = warp * 4 + sub; t < T; t += 32) {
+      const float4 a4 = *reinterpret_cast<const float4*>(sa + t * 32 + c4);
+      const float4 v4 = *reinterpret_cast<const float4*>(sv + t * 32 + c4);
+      const float A[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float R[4] = {__fadd_rn(a4.x, v4.x), __fadd_rn(a4.y, v4.y), __fadd_rn(a4.z, v4.z), __fadd_rn(a4.w, v4.w)};
+      const int64_t o = (int64_t)t * ld + col;
+      if (nv >= 4) {
+        __stcs(reinterpret_cast<float4*>(adv + o), a4);
+        __stcs(reinterpret_cast<float4*>(ret + o), make_float4(R[0], R[1], R[2], R[3]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < nv) {
+          if (nv < 4) { adv[o + k] = A[k]; ret[o + k] = R[k]; }
+          s1 += (double)A[k];
+          s2 += (double)A[k] * (double)A[k];
+        }
+    }
+  } else if (on)
     for (int t = warp; t < T; t += 8) {
       const int64_t o = (int64_t)t * ld + e;
       const float A = sa[t * 32 + lane];
@@ -214,7 +262,29 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
   const int pad = (L & 1) ? 0 : 1;                         // lane stride L (+1 if L is even): odd => conflict-free
   const unsigned magic = (unsigned)(0x100000000ull / (unsigned)L) + 1u;
   const int e0 = blockIdx.x * 32;
-  {  // ---- stage (lanes over envs: coalesced rows; transposed shared-memory writes, pitch PT odd) ----
+  const bool vec = ((ld & 3) == 0) && (int64_t)gridDim.x * 32 <= ld &&
+                   (((reinterpret_cast<uintptr_t>(rew) | reinterpret_cast<uintptr_t>(value) | reinterpret_cast<uintptr_t>(adv) |
+                      reinterpret_cast<uintptr_t>(ret)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(done) & 3) == 0);
+  if (vec) {
+    // ---- stage, 16 bytes per lane: four envs of a row per lane, four rows per warp instruction; the transposed stores of
+    // a warp (4 consecutive time slots x 8 env groups 4 PT floats apart, PT odd) fall into 32 different banks ----
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const int64_t col = (int64_t)e0 + c4;
+    for (int t = warp * 4 + sub; t <= T; t += 32) {
+      const int64_t o = (int64_t)t * ld + col;
+      const int q = gae_tp(t, magic, pad);
+      const float4 v4 = __ldcs(reinterpret_cast<const float4*>(value + o));
+      sv[(c4 + 0) * PT + q] = v4.x; sv[(c4 + 1) * PT + q] = v4.y; sv[(c4 + 2) * PT + q] = v4.z; sv[(c4 + 3) * PT + q] = v4.w;
+      if (t < T) {
+        const float4 r4 = __ldcs(reinterpret_cast<const float4*>(rew + o));
+        const uchar4 d4 = *reinterpret_cast<const uchar4*>(done + o);
+        sb[(c4 + 0) * PT + q] = r4.x; sb[(c4 + 1) * PT + q] = r4.y; sb[(c4 + 2) * PT + q] = r4.z; sb[(c4 + 3) * PT + q] = r4.w;
+        sa[(c4 + 0) * PT + q] = 1.0f - (float)d4.x; sa[(c4 + 1) * PT + q] = 1.0f - (float)d4.y;
+        sa[(c4 + 2) * PT + q] = 1.0f - (float)d4.z; sa[(c4 + 3) * PT + q] = 1.0f - (float)d4.w;
+      }
+    }
+  } else {  // ---- stage (lanes over envs: coalesced rows; transposed shared-memory writes, pitch PT odd) ----
     const int e = e0 + lane;
     const bool on = e < N;
     if (on) {
@@ -308,6 +378,29 @@ __global__ void __launch_bounds__(256) gae_scan_fused_kernel(const float* __rest
     denom = (float)sqrt(var) + 1e-8f;
   }
   // ---- write back (lanes over envs again) ----
+  if (vec) {
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const int64_t col = (int64_t)e0 + c4;
+    const int nv = (int)min((int64_t)4, (int64_t)N - col);
+    for (int t = warp * 4 + sub; t < T; t += 32) {
+      const int q = gae_tp(t, magic, pad);
+      float A[4], R[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = sb[(c4 + k) * PT + q];
+        R[k] = __fadd_rn(a, sv[(c4 + k) * PT + q]);
+        A[k] = normalize ? (a - mean) / denom : a;
+      }
+      const int64_t o = (int64_t)t * ld + col;
+      if (nv >= 4) {
+        __stcs(reinterpret_cast<float4*>(adv + o), make_float4(A[0], A[1], A[2], A[3]));
+        __stcs(reinterpret_cast<float4*>(ret + o), make_float4(R[0], R[1], R[2], R[3]));
+      } else {
+        for (int k = 0; k < nv; ++k) { adv[o + k] = A[k]; ret[o + k] = R[k]; }
+      }
+    }
+    return;
+  }
   const int e = e0 + lane;
   if (e < N)
     for (int t = warp; t < T; t += 8) {
