@@ -180,6 +180,9 @@ class MLPEngineTC(MLPEngine):
         self.pair_block_n = TC_TILE_PAIR_PERSISTENT     # or TC_TILE_PAIR: one 256 x 256 tile per (non-persistent) pair
         # launches whose epilogue 8 warps can hide (see TPP_TC_TILE_PAIR_PERSISTENT_LEAN): three operand stages
         self.lean_kinds = ("fwd", "dgrad", "wgrad")
+        # contractions shorter than this keep the 16-epilogue-warp tile: two k-blocks of main loop cannot hide a lean epilogue
+        # (the 256 <- 64 data gradient: 89.6 us lean, 73.7 us with 16 epilogue warps at 131072 rows)
+        self.lean_min_k = int(os.environ.get("TPP_LEAN_MIN_K", "128"))
         self.small_tile_elems = 148 * 128 * 128 // 2
         f = dict(dtype=torch.float32, device=self.device)
         self.w = []   # per layer: hi, lo [out, ceil32(in)]
@@ -361,10 +364,11 @@ class MLPEngineTC(MLPEngine):
         _lib.call("tpp_policy_rollout_fused", _lib.C.byref(f), _lib.stream_ptr())
         self.n_launches += 1
 
-    def _bn(self, M, N, kind="fwd"):
+    def _bn(self, M, N, kind="fwd", K=None):
         """Tile of a forward / data-gradient GEMM with M rows and N output columns (tpp_tc_gemm.block_n)."""
         if N >= self.pair_min_n and M >= self.wide_tile_rows:
-            if self.pair_block_n == TC_TILE_PAIR_PERSISTENT and kind in self.lean_kinds and self.precision == 3:
+            lean = kind in self.lean_kinds and not (K is not None and K < self.lean_min_k)
+            if self.pair_block_n == TC_TILE_PAIR_PERSISTENT and lean and self.precision == 3:
                 return TC_TILE_PAIR_PERSISTENT_LEAN
             return self.pair_block_n       # 256 x 256 tiles on CTA pairs (cta_group::2)
         if 32 < N <= 64 and M >= self.wide_tile_rows and self.pair_block_n == TC_TILE_PAIR_PERSISTENT:
@@ -501,7 +505,7 @@ class MLPEngineTC(MLPEngine):
                          mask=prev["hi"] if (prev_relu and not use_bits) else None,
                          ld_mask=prev["ld"], out=nxt["hi"] if soc else None,
                          out_pair=None if soc else (nxt["hi"], nxt["lo"]), ldc=prev["ld"],
-                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin, "dgrad"),
+                         colsum=self._g(self.layers[i - 1][1]), block_n=self._bn(M, fin, "dgrad", K=fout),
                          exact=TC_A_SPLIT if soc and i < L - 1 else 0)
                 cur, ld_dz = cur ^ 1, prev["ld"]
 
