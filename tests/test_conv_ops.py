@@ -478,3 +478,64 @@ def test_conv3x3_fma_forward_and_data_gradient_forms(B, cin, cout, mode):
         assert torch.equal(oh, ((y.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32))
     if colsum is not None:
         _close(colsum - 0.5, ref.sum(0), 1e-5)
+
+
+def test_fma_conv_kernels_at_the_full_minibatch_size():
+    """The FMA-pipe kernels at the Procgen minibatch's size (2048 frames: 2.1 M pixels at 32 x 32, 8.4 M at 64 x 64 -- the
+    persistent tile loop, 64-bit offsets, every CTA's partial sums), through properties that do not need a float64
+    convolution of that size: (1) the centre tap of the weight gradient is the plain contraction X^T dY; (2) corner taps
+    equal the contraction of shifted views; (3) linearity in dY; (4) agreement with the tensor-core form of the same
+    contraction; (5) first-layer forward against torch's fp32 convolution."""
+    L = _lib()
+    torch.manual_seed(11)
+    B, H, W, Cc = 2048, 32, 32, 16
+    rows = B * H * W
+    x = torch.randn(B, H, W, Cc, device="cuda")
+    dy1, dy2 = torch.randn(rows, Cc, device="cuda"), torch.randn(rows, Cc, device="cuda")
+
+    def wgrad(dy, relu=1):
+        gw = torch.zeros(288, Cc, device="cuda")
+        L.call("tpp_conv3x3_wgrad", L.ptr(x), relu, L.ptr(dy), L.ptr(gw), B, H, W, Cc, Cc, L.stream_ptr())
+        return gw.view(3, 3, 32, Cc)[:, :, :Cc, :]
+
+    g1, g2 = wgrad(dy1), wgrad(dy2)
+    xr = x.clamp_min(0)
+    centre = torch.einsum("pi,pj->ij", xr.view(rows, Cc).double(), dy1.double())
+    _close(g1[1, 1], centre, 2e-6)
+    d4 = dy1.view(B, H, W, Cc)
+    corner = torch.einsum("bhwi,bhwj->ij", xr[:, :-1, :-1].double(), d4[:, 1:, 1:].double())     # tap (0, 0): X[y-1][x-1]
+    _close(g1[0, 0], corner, 2e-6)
+    corner = torch.einsum("bhwi,bhwj->ij", xr[:, 1:, :-1].double(), d4[:, :-1, 1:].double())      # tap (2, 0): X[y+1][x-1]
+    _close(g1[2, 0], corner, 2e-6)
+    _close(wgrad((dy1 + 2 * dy2).contiguous()), g1.double() + 2 * g2.double(), 2e-6)
+    # the tensor-core form (TMA im2col, 3xTF32) on the same operands
+    xp, dyp = _pair(xr.contiguous()), _pair(dy1)
+    gtc = torch.zeros(288, Cc, device="cuda")
+    g = L.TcGemm()
+    g.a_hi, g.a_lo = xp[0].data_ptr(), xp[1].data_ptr()
+    g.b_hi, g.b_lo, g.ldb = dyp[0].data_ptr(), dyp[1].data_ptr(), Cc
+    g.M, g.N, g.K, g.precision, g.split_k, g.a_mn, g.b_mn = 288, Cc, rows, 3, rows // 1024, 1, 1
+    g.conv_B, g.conv_H, g.conv_W, g.conv_C, g.conv_wgrad = B, H, W, Cc, 1
+    g.flags, g.out, g.ldc, g.block_n = L.EPI_ACCUM, gtc.data_ptr(), Cc, 32
+    L.call("tpp_gemm_tc", L.C.byref(g), L.stream_ptr())
+    _close(gtc.view(3, 3, 32, Cc)[:, :, :Cc, :], g1.double(), 1e-4)
+    # first convolution at 2048 frames of 64 x 64
+    xb = torch.rand(B, 3 * 64 * 64, device="cuda")
+    w = torch.randn(16, 3, 3, 3, device="cuda") * 0.3
+    bias = torch.randn(16, device="cuda")
+    out = torch.zeros(B, 64, 64, 16, device="cuda")
+    L.call("tpp_conv3x3_fwd_first", L.ptr(xb), 3 * 64 * 64, 64 * 64, 64, L.ptr(w), L.ptr(bias), L.ptr(out), B, 64, 64, 16,
+           L.stream_ptr())
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = F.conv2d(xb.view(B, 3, 64, 64), w, bias, padding=1).permute(0, 2, 3, 1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
+    _close(out, ref, 3e-6)
+    dyf = torch.randn(B * 64 * 64, 16, device="cuda")
+    gwf = torch.zeros(32, 16, device="cuda")
+    L.call("tpp_conv3x3_wgrad_first", L.ptr(xb), 3 * 64 * 64, 64 * 64, 64, L.ptr(dyf), L.ptr(gwf), B, 64, 64, 16,
+           L.stream_ptr())
+    centre = torch.einsum("bcp,bpj->cj", xb.view(B, 3, 4096).double(), dyf.view(B, 4096, 16).double())
+    _close(gwf[:27].view(3, 3, 3, 16)[1, 1], centre, 2e-6)
