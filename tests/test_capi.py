@@ -157,3 +157,29 @@ def test_shape_specialised_entries_refuse_other_shapes_without_a_gpu():
     assert _lib.try_call("tpp_conv3x3_fwd_first", one, 1, 1, 1, one, one, one, 2, 32, 32, 16, None) is False
     with pytest.raises(_lib.TppError):
         _lib.try_call("tpp_conv3x3_wgrad", None, 0, one, one, 2, 32, 32, 16, 16, None)
+
+
+def test_tile_and_kernel_selection_policies():
+    """Host logic of the engines: which tile a dense GEMM gets (lean persistent pairs unless the contraction is too short
+    to hide a lean epilogue) and which convolutions leave the tensor core for the FMA-pipe kernels."""
+    from tpp_b200 import _lib
+    from tpp_b200.common.engine import ImpalaEngineTC, MLPEngineTC
+    e = object.__new__(MLPEngineTC)
+    e.pair_min_n, e.wide_tile_rows, e.pair_block_n = 256, 8192, _lib.TC_TILE_PAIR_PERSISTENT
+    e.lean_kinds, e.lean_min_k, e.precision, e.small_tile_elems = ("fwd", "dgrad", "wgrad"), 128, 3, 148 * 128 * 128 // 2
+    assert e._bn(131072, 256, "fwd") == _lib.TC_TILE_PAIR_PERSISTENT_LEAN
+    assert e._bn(131072, 256, "dgrad", K=256) == _lib.TC_TILE_PAIR_PERSISTENT_LEAN
+    assert e._bn(131072, 256, "dgrad", K=64) == _lib.TC_TILE_PAIR_PERSISTENT          # 16 epilogue warps
+    assert e._bn(131072, 64, "fwd") == _lib.TC_TILE_PAIR64_PERSISTENT
+    assert e._bn(4096, 256, "fwd") == 64 and e._bn(256, 64, "fwd") == 0
+    e.precision = 1
+    assert e._bn(131072, 256, "fwd") == _lib.TC_TILE_PAIR_PERSISTENT                    # lean exists for 3xTF32 only
+    i = object.__new__(ImpalaEngineTC)
+    i.wgrad_cc = True
+    first = dict(implicit=False, cin=3, cout=16)
+    assert i._first_cc(first, 64, 64, (12288, 64, 1, 4096))
+    assert not i._first_cc(first, 14, 14, (588, 14, 1, 196))                            # Box-World frames: col + GEMM
+    assert not i._first_cc(first, 64, 64, (12288, 64, 2, 4096))                         # x stride must be 1
+    assert not i._first_cc(dict(implicit=True, cin=16, cout=16), 64, 64, (1, 1, 1, 1))
+    i.wgrad_cc = False
+    assert not i._first_cc(first, 64, 64, (12288, 64, 1, 4096))
